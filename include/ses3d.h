@@ -1,0 +1,215 @@
+/*
+ * ses3d.h — C ABI of the B200-native multi-view geometry hot path
+ * (cross-view association -> per-joint DLT triangulation + UT covariance ->
+ *  skeleton plausibility/merge -> reprojection into every camera).
+ *
+ * This header is the drop-in boundary for the two reference entry points
+ *   triangulate_persons(...)      skeleton_3d/src/skeleton_3d_triang_mult_node.cpp:525-526 (called :1069)
+ *   fusedSkeletonCallback(...)    pose_reprojection/src/skeleton_reproj_mult_node.cpp:139 (bound :293)
+ * and for the one-time table set-up done in their main()s
+ *   skeleton_3d_triang_mult_node.cpp:1184-1214, skeleton_reproj_mult_node.cpp:272-279.
+ * The reference has no library target (both functions live in node executables),
+ * so the ABI is derived from those signatures: ROS messages become POD mirror
+ * structs of person_msgs/msg/(.msg files), tf/CameraInfo become ses3d_camera.
+ *
+ * Plain C, no CUDA/torch types. All functions return an int status (0 = ok,
+ * <0 = error, see SES3D_E_*), never throw, and never allocate on the steady
+ * state per-batch path (device scratch is grown once and kept in the handle).
+ */
+#ifndef SES3D_H_
+#define SES3D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ layouts */
+
+#define SES3D_NUM_KEYPOINTS 17        /* detector joints, NUM_KEYPOINTS S3D:56,1098 */
+#define SES3D_NUM_FUSION_KEYPOINTS 21 /* FUSION_BODY_PARTS::NUM_KEYPOINTS, fusion_body_parts.h:25 */
+
+/* person_msgs/msg/Keypoint2D.msg:1-4 — 24 B */
+typedef struct ses3d_keypoint2d {
+  float x, y, score;
+  float cov[3]; /* xx, xy, yy */
+} ses3d_keypoint2d;
+
+/* person_msgs/msg/Person2D.msg:1-5 — 428 B (fixed 17 keypoints, no length prefix) */
+typedef struct ses3d_person2d {
+  float score;
+  ses3d_keypoint2d keypoints[SES3D_NUM_KEYPOINTS];
+  float bbox[4]; /* x0, y0, x1, y1 */
+} ses3d_person2d;
+
+/* person_msgs/msg/KeypointWithCovariance.msg:1-3 — 80 B with natural alignment */
+typedef struct ses3d_keypoint_cov {
+  double x, y, z; /* geometry_msgs/Point joint */
+  float score;
+  float pad_;
+  double cov[6]; /* xx, xy, xz, yy, yz, zz */
+} ses3d_keypoint_cov;
+
+/* person_msgs/msg/PersonCov.msg:1-8 — 1768 B; keypoints indexed by FUSION_BODY_PARTS slot */
+typedef struct ses3d_person_cov {
+  uint32_t id;
+  float score;
+  ses3d_keypoint_cov keypoints[SES3D_NUM_FUSION_KEYPOINTS];
+  double bbox_center[7]; /* geometry_msgs/Pose: position xyz, orientation xyzw */
+  double bbox_size[3];   /* geometry_msgs/Vector3 */
+} ses3d_person_cov;
+
+/* FUSION_BODY_PARTS slots, skeleton_3d/include/skeleton_3d/fusion_body_parts.h:4-25 */
+enum {
+  SES3D_FBP_NOSE = 0, SES3D_FBP_NECK = 1, SES3D_FBP_RSHOULDER = 2, SES3D_FBP_RELBOW = 3,
+  SES3D_FBP_RWRIST = 4, SES3D_FBP_LSHOULDER = 5, SES3D_FBP_LELBOW = 6, SES3D_FBP_LWRIST = 7,
+  SES3D_FBP_MIDHIP = 8, SES3D_FBP_RHIP = 9, SES3D_FBP_RKNEE = 10, SES3D_FBP_RANKLE = 11,
+  SES3D_FBP_LHIP = 12, SES3D_FBP_LKNEE = 13, SES3D_FBP_LANKLE = 14, SES3D_FBP_REYE = 15,
+  SES3D_FBP_LEYE = 16, SES3D_FBP_REAR = 17, SES3D_FBP_LEAR = 18, SES3D_FBP_HEAD = 19,
+  SES3D_FBP_BELLY = 20
+};
+
+/* One camera: what getTransforms()/getIntrinsics() deliver in the reference
+ * (S3D:161-228, REP:77-137). T_cam_base is the row-major 3x4 [R|t] that maps a
+ * base-frame point into the camera optical frame (lookupTransform(target=cam,
+ * source=base), S3D:166-167, 1192). fx..Ty are the CameraInfo P-matrix entries
+ * image_geometry::PinholeCameraModel exposes (P[0],P[5],P[2],P[6],P[3],P[7]). */
+typedef struct ses3d_camera {
+  double T_cam_base[12];
+  double fx, fy, cx, cy, Tx, Ty;
+  uint32_t width, height;
+} ses3d_camera;
+
+enum { SES3D_POSE_SIMPLE = 0, SES3D_POSE_H36M = 1 };   /* param pose_method, S3D:1095,1101-1112 */
+enum { SES3D_PRECISION_FP32 = 0, SES3D_PRECISION_FP64 = 1 };
+
+/* The reference's run-time parameters and compile-time constants (S3D:43-64,149). */
+typedef struct ses3d_params {
+  int32_t pose_method;                 /* SES3D_POSE_SIMPLE */
+  int32_t precision;                   /* SES3D_PRECISION_FP32 = the reference's float DLT */
+  int32_t lm_refine;                   /* 0 = off (reference behaviour); 1 = LM refinement (not in the reference) */
+  int32_t lm_max_iters;                /* 10 */
+  int32_t min_num_valid_keypoints;     /* 9     S3D:57 */
+  float triangulation_threshold;       /* 0.30f S3D:58,1099 */
+  double max_epipolar_error;           /* 0.050 S3D:60,1097 (demo launch file: 0.045) */
+  double reproj_error_max_acceptable;  /* 0.050 S3D:59 */
+  double max_joint_dist_to_root;       /* 2.0   S3D:61 */
+  double merge_dist_thresh;            /* 0.20  S3D:62 */
+  double limb_cov_offset_sigma;        /* 0.075 S3D:149 */
+} ses3d_params;
+
+/* Optional association dump used for the bit-exact index check; every pointer may be NULL. */
+typedef struct ses3d_assoc_dump {
+  int32_t* hyp_of;      /* [n_frames][n_cams][p_max]: hypothesis index of each detection, -1 = none */
+  int32_t* n_hyp;       /* [n_frames]: number of hypotheses H.size() after the last camera (S3D:674) */
+  int32_t* n_hungarian; /* [n_frames]: how many cameras needed the Hungarian solve (S3D:628-634) */
+} ses3d_assoc_dump;
+
+typedef struct ses3d_handle_s* ses3d_handle;
+
+/* ------------------------------------------------------------------- status */
+enum {
+  SES3D_OK = 0,
+  SES3D_E_INVALID = -1,   /* bad argument */
+  SES3D_E_CUDA = -2,      /* CUDA runtime error (see ses3d_last_error_string) */
+  SES3D_E_CAPACITY = -3,  /* a frame produced more hypotheses / persons than h_max */
+  SES3D_E_NOMEM = -4
+};
+
+/* flags for the *_batch calls */
+enum {
+  SES3D_HOST_BUFFERS = 0,   /* all data pointers are host memory (pinned recommended) */
+  SES3D_DEVICE_BUFFERS = 1  /* all data pointers are device memory on the handle's GPU */
+};
+
+/* -------------------------------------------------------------- entry points */
+
+void ses3d_default_params(ses3d_params* p);
+
+/* Replaces the set-up in main(): S3D:1184-1211 (P, camera centres, fundamental
+ * matrices F_ij for i<j in FP64 then cast to float) and REP:272-279.
+ * device = CUDA device ordinal. */
+int ses3d_create(int32_t n_cams, const ses3d_camera* cams, const ses3d_params* params,
+                 int32_t device, ses3d_handle* out);
+int ses3d_destroy(ses3d_handle h);
+
+/* Read back the constant tables (host memory): P [n_cams][12] float row-major,
+ * F [n_cams*(n_cams-1)/2][9] float row-major in get_fundamental_idx order (S3D:242-253). */
+int ses3d_get_tables(ses3d_handle h, float* P, float* F);
+
+/* Replaces triangulate_persons() (S3D:525-997) for a batch of frames.
+ *   persons   [n_frames][n_cams][p_max]   n_persons [n_frames][n_cams]
+ *   out       [n_frames][h_max]           n_out     [n_frames]
+ * Output persons are in hypothesis-index order (the reference built without
+ * OpenMP), after plausibility checks and merge. Fewer than two cameras with
+ * detections is not an error (n_out = 0, S3D:557-560).
+ * stream: a cudaStream_t cast to void* (NULL = the handle's own stream); the
+ * call is synchronous for host buffers and stream-ordered for device buffers. */
+int ses3d_triangulate_batch(ses3d_handle h, int32_t n_frames, int32_t p_max,
+                            const ses3d_person2d* persons, const int32_t* n_persons,
+                            int32_t h_max, ses3d_person_cov* out, int32_t* n_out,
+                            const ses3d_assoc_dump* dump, uint32_t flags, void* stream);
+
+/* Replaces fusedSkeletonCallback() (REP:139-235) for a batch of frames.
+ *   persons3d [n_frames][h_max]            n_persons3d [n_frames]
+ *   out       [n_frames][n_cams][h_max]    n_out       [n_frames][n_cams] */
+int ses3d_reproject_batch(ses3d_handle h, int32_t n_frames, int32_t h_max,
+                          const ses3d_person_cov* persons3d, const int32_t* n_persons3d,
+                          ses3d_person2d* out, int32_t* n_out, uint32_t flags, void* stream);
+
+/* Both stages chained on the device (skeleton_3d -> pose_reprojection, the
+ * PersonCovList never leaves HBM); any of out3d/n_out3d may be NULL with host
+ * buffers to skip that copy. */
+int ses3d_process_batch(ses3d_handle h, int32_t n_frames, int32_t p_max,
+                        const ses3d_person2d* persons, const int32_t* n_persons,
+                        int32_t h_max, ses3d_person_cov* out3d, int32_t* n_out3d,
+                        ses3d_person2d* out2d, int32_t* n_out2d,
+                        const ses3d_assoc_dump* dump, uint32_t flags, void* stream);
+
+/* Pre-size the handle's device scratch (otherwise grown on first use). */
+int ses3d_reserve(ses3d_handle h, int32_t n_frames, int32_t p_max, int32_t h_max);
+
+/* How many kernels the handle has launched so far (bench.py's gpu_launches). */
+int64_t ses3d_launch_count(ses3d_handle h);
+
+/* Device-time (ms, CUDA events on the launching stream) of each kernel of the
+ * most recent device-buffer call when profiling was enabled with
+ * ses3d_set_profiling(h, 1): order = {associate, triangulate, finalize, reproject}. */
+int ses3d_set_profiling(ses3d_handle h, int32_t on);
+int ses3d_last_kernel_ms(ses3d_handle h, float ms[4]);
+
+const char* ses3d_last_error_string(void);
+const char* ses3d_version(void);
+
+/* ------------------------------------------------- synthetic frame generator
+ * Test/bench input source; not part of the reference. Counter
+ * based (Philox4x32-10), IEEE-only arithmetic, so host and device variants are
+ * bit-identical. gt_id (nullable) [n_frames][n_cams][p_max] = generator person
+ * id of every emitted detection (-1 = empty slot). */
+typedef struct ses3d_synth_config {
+  uint64_t seed;
+  int32_t n_people;       /* people in the scene */
+  int32_t p_max;          /* slots per camera (>= n_people) */
+  float dropout;          /* per-keypoint dropout probability */
+  float noise_px;         /* 2-D noise sigma in pixels */
+  float area[4];          /* x0, y0, x1, y1 of the floor area people stand in (base frame) */
+  float min_separation;   /* metres between roots */
+  int32_t min_visible;    /* emit a detection only if >= this many keypoints are inside the image */
+} ses3d_synth_config;
+
+int ses3d_synth_frames(int32_t n_cams, const ses3d_camera* cams, const ses3d_synth_config* cfg,
+                       int64_t first_frame, int32_t n_frames,
+                       ses3d_person2d* persons, int32_t* n_persons, int32_t* gt_id,
+                       float* gt_joints /* nullable [n_frames][n_people][17][3] */);
+
+/* Same frames, generated on the GPU into device buffers (cams is a host array). Synchronous. */
+int ses3d_synth_frames_device(int32_t n_cams, const ses3d_camera* cams, const ses3d_synth_config* cfg,
+                              int64_t first_frame, int32_t n_frames,
+                              ses3d_person2d* persons, int32_t* n_persons, int32_t* gt_id, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SES3D_H_ */

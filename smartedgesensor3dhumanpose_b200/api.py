@@ -1,0 +1,170 @@
+"""Host-side mirror of the reference's entry points on top of the C ABI (libses3d.so).
+
+    Skeleton3D.triangulate_persons(people)        <- triangulate_persons(), S3D:525-997 (called S3D:1069)
+    PoseReprojection.fused_skeleton_callback(msg) <- fusedSkeletonCallback(), REP:139-235
+
+plus the batched calls the benchmark uses (`GeometryPipeline.*_batch`). ROS messages are
+replaced by numpy structured arrays with the person_msgs layouts (layouts.py). All compute
+happens in the CUDA library; there is no CPU path here.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import lib as _lib
+from .layouts import (DEVICE_BUFFERS, HOST_BUFFERS, AssocDump, camera_dtype, default_params, person2d_dtype,
+                      person_cov_dtype)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class GeometryPipeline:
+    """One handle = one camera rig on one GPU (ses3d_create: the set-up of S3D:1184-1214 / REP:272-279)."""
+
+    def __init__(self, cameras, params=None, device=0):
+        self._L = _lib.load()
+        self.cameras = np.ascontiguousarray(cameras, dtype=camera_dtype)
+        self.n_cams = len(self.cameras)
+        self.params = params if params is not None else default_params()
+        self.device = device
+        h = C.c_void_p()
+        _lib.check(self._L.ses3d_create(self.n_cams, _p(self.cameras), C.byref(self.params), device, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.ses3d_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    # ------------------------------------------------------------------ tables
+    def tables(self):
+        P = np.zeros((self.n_cams, 12), np.float32)
+        F = np.zeros((self.n_cams * (self.n_cams - 1) // 2, 9), np.float32)
+        _lib.check(self._L.ses3d_get_tables(self._h, _p(P), _p(F)))
+        return P, F
+
+    def reserve(self, n_frames, p_max, h_max):
+        _lib.check(self._L.ses3d_reserve(self._h, n_frames, p_max, h_max))
+
+    @property
+    def launch_count(self):
+        return int(self._L.ses3d_launch_count(self._h))
+
+    def set_profiling(self, on=True):
+        _lib.check(self._L.ses3d_set_profiling(self._h, int(on)))
+
+    def last_kernel_ms(self):
+        ms = np.zeros(4, np.float32)
+        _lib.check(self._L.ses3d_last_kernel_ms(self._h, _p(ms)))
+        return dict(zip(("associate", "triangulate", "finalize", "reproject"), ms.tolist()))
+
+    # ------------------------------------------------------- host-buffer calls
+    def triangulate_batch(self, persons, n_persons, h_max, dump=True, out=None, n_out=None):
+        persons = np.ascontiguousarray(persons, dtype=person2d_dtype)
+        n_frames, n_cams, p_max = persons.shape
+        if n_cams != self.n_cams:
+            raise ValueError(f"persons has {n_cams} cameras, the rig has {self.n_cams}")
+        n_persons = np.ascontiguousarray(n_persons, dtype=np.int32).reshape(n_frames, n_cams)
+        out = np.zeros((n_frames, h_max), person_cov_dtype) if out is None else out
+        n_out = np.zeros(n_frames, np.int32) if n_out is None else n_out
+        res = dict(persons3d=out, n_out=n_out)
+        d = None
+        if dump:
+            res["hyp_of"] = np.full((n_frames, n_cams, p_max), -1, np.int32)
+            res["n_hyp"] = np.zeros(n_frames, np.int32)
+            res["n_hungarian"] = np.zeros(n_frames, np.int32)
+            d = AssocDump(res["hyp_of"].ctypes.data, res["n_hyp"].ctypes.data, res["n_hungarian"].ctypes.data)
+        _lib.check(self._L.ses3d_triangulate_batch(self._h, n_frames, p_max, _p(persons), _p(n_persons), h_max, _p(out),
+                                                   _p(n_out), C.byref(d) if d else None, HOST_BUFFERS, None))
+        return res
+
+    def reproject_batch(self, persons3d, n_persons3d, out=None, n_out=None):
+        persons3d = np.ascontiguousarray(persons3d, dtype=person_cov_dtype)
+        n_frames, h_max = persons3d.shape
+        n_persons3d = np.ascontiguousarray(n_persons3d, dtype=np.int32).reshape(n_frames)
+        out = np.zeros((n_frames, self.n_cams, h_max), person2d_dtype) if out is None else out
+        n_out = np.zeros((n_frames, self.n_cams), np.int32) if n_out is None else n_out
+        _lib.check(self._L.ses3d_reproject_batch(self._h, n_frames, h_max, _p(persons3d), _p(n_persons3d), _p(out),
+                                                 _p(n_out), HOST_BUFFERS, None))
+        return dict(persons2d=out, n_out=n_out)
+
+    def process_batch(self, persons, n_persons, h_max, want_3d=True, bufs=None):
+        """association + triangulation + reprojection chained on the GPU (host buffers in/out)."""
+        persons = np.ascontiguousarray(persons, dtype=person2d_dtype)
+        n_frames, n_cams, p_max = persons.shape
+        n_persons = np.ascontiguousarray(n_persons, dtype=np.int32).reshape(n_frames, n_cams)
+        b = bufs or {}
+        out3d = b.get("persons3d", np.zeros((n_frames, h_max), person_cov_dtype) if want_3d else None)
+        n3d = b.get("n_out3d", np.zeros(n_frames, np.int32))
+        out2d = b.get("persons2d", np.zeros((n_frames, n_cams, h_max), person2d_dtype))
+        n2d = b.get("n_out2d", np.zeros((n_frames, n_cams), np.int32))
+        _lib.check(self._L.ses3d_process_batch(self._h, n_frames, p_max, _p(persons), _p(n_persons), h_max, _p(out3d),
+                                               _p(n3d), _p(out2d), _p(n2d), None, HOST_BUFFERS, None))
+        return dict(persons3d=out3d, n_out3d=n3d, persons2d=out2d, n_out2d=n2d)
+
+    # ----------------------------------------------------- device-buffer calls
+    # Arguments are raw device addresses (e.g. torch_tensor.data_ptr()) on this handle's GPU.
+    def triangulate_device(self, n_frames, p_max, h_max, persons_ptr, n_persons_ptr, out_ptr, n_out_ptr, stream=0,
+                           hyp_of_ptr=0, n_hyp_ptr=0, n_hung_ptr=0):
+        d = AssocDump(hyp_of_ptr or None, n_hyp_ptr or None, n_hung_ptr or None)
+        _lib.check(self._L.ses3d_triangulate_batch(self._h, n_frames, p_max, persons_ptr, n_persons_ptr, h_max, out_ptr,
+                                                   n_out_ptr, C.byref(d), DEVICE_BUFFERS, stream or None))
+
+    def reproject_device(self, n_frames, h_max, persons3d_ptr, n_persons3d_ptr, out_ptr, n_out_ptr, stream=0):
+        _lib.check(self._L.ses3d_reproject_batch(self._h, n_frames, h_max, persons3d_ptr, n_persons3d_ptr, out_ptr,
+                                                 n_out_ptr, DEVICE_BUFFERS, stream or None))
+
+    def process_device(self, n_frames, p_max, h_max, persons_ptr, n_persons_ptr, out3d_ptr, n_out3d_ptr, out2d_ptr,
+                       n_out2d_ptr, stream=0):
+        _lib.check(self._L.ses3d_process_batch(self._h, n_frames, p_max, persons_ptr, n_persons_ptr, h_max, out3d_ptr,
+                                               n_out3d_ptr, out2d_ptr, n_out2d_ptr, None, DEVICE_BUFFERS,
+                                               stream or None))
+
+
+def _pack_frame(people, n_cams):
+    """list (per camera) of Person2D arrays -> ([1][C][p_max] array, [1][C] counts)."""
+    if len(people) != n_cams:
+        raise ValueError(f"expected one Person2DList per camera ({n_cams}), got {len(people)}")  # assert S3D:534
+    p_max = max(1, max(len(p) for p in people))
+    persons = np.zeros((1, n_cams, p_max), person2d_dtype)
+    n_persons = np.zeros((1, n_cams), np.int32)
+    for c, plist in enumerate(people):
+        plist = np.asarray(plist, dtype=person2d_dtype).reshape(-1)
+        persons[0, c, :len(plist)] = plist
+        n_persons[0, c] = len(plist)
+    return persons, n_persons
+
+
+class Skeleton3D:
+    """skeleton_3d node body: per-frame triangulate_persons (S3D:525-997) with n_frames = 1."""
+
+    def __init__(self, cameras, params=None, device=0, h_max=32):
+        self.pipe = GeometryPipeline(cameras, params, device)
+        self.h_max = h_max
+
+    def triangulate_persons(self, people):
+        """people: one array of Person2D per camera (a Person2DList each). Returns the PersonCov array
+        (persons3d_msg.persons); fewer than two cameras with detections gives an empty list (S3D:557-560)."""
+        persons, n_persons = _pack_frame(people, self.pipe.n_cams)
+        r = self.pipe.triangulate_batch(persons, n_persons, self.h_max, dump=False)
+        return r["persons3d"][0, :r["n_out"][0]].copy()
+
+
+class PoseReprojection:
+    """pose_reprojection node body: fusedSkeletonCallback (REP:139-235) with n_frames = 1."""
+
+    def __init__(self, cameras, params=None, device=0):
+        self.pipe = GeometryPipeline(cameras, params, device)
+
+    def fused_skeleton_callback(self, persons3d):
+        """persons3d: PersonCov array (PersonCovList.persons). Returns one Person2D array per camera."""
+        persons3d = np.asarray(persons3d, dtype=person_cov_dtype).reshape(1, -1)
+        n = persons3d.shape[1]
+        if n == 0:
+            return [np.zeros(0, person2d_dtype) for _ in range(self.pipe.n_cams)]
+        r = self.pipe.reproject_batch(persons3d, np.array([n], np.int32))
+        return [r["persons2d"][0, c, :r["n_out"][0, c]].copy() for c in range(self.pipe.n_cams)]

@@ -1,0 +1,81 @@
+"""In-tree build of the C-ABI library libses3d.so for sm_100a (nvcc, no cmake).
+
+    python -m smartedgesensor3dhumanpose_b200.build [--force] [--verbose]
+
+The association / finalize / reproject kernels are compiled with -fmad=false (bit-exact with the
+reference's x86-64 arithmetic); host code with -ffp-contract=off. The .so stays in the package
+directory so that it travels to the GPU box with the repo snapshot.
+"""
+import argparse
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+INCLUDE = PKG.parent / "include"
+BUILD = PKG / "build"
+LIB = PKG / "libses3d.so"
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", f"-I{INCLUDE}", f"-I{CSRC}", "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math",
+          "--expt-relaxed-constexpr"]
+UNITS = [
+    ("kernels_exact.cu", ["-fmad=false"]),
+    ("kernels_tri.cu", []),
+    ("synth_device.cu", ["-fmad=false"]),
+    ("api.cpp", []),
+    ("host_setup.cpp", []),
+    ("synth.cpp", []),
+]
+
+
+def _nvcc():
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not Path(exe).exists():
+        raise RuntimeError("nvcc not found: the CUDA library cannot be built")
+    return exe
+
+
+def _stale(out: Path, deps):
+    if not out.exists():
+        return True
+    t = out.stat().st_mtime
+    return any(d.stat().st_mtime > t for d in deps if d.exists())
+
+
+def build(force=False, verbose=False, ptxas_info=False):
+    nvcc = _nvcc()
+    BUILD.mkdir(exist_ok=True)
+    headers = list(CSRC.glob("*.h")) + list(INCLUDE.glob("*.h")) + [Path(__file__)]
+    objs = []
+    for name, extra in UNITS:
+        src = CSRC / name
+        if not src.exists():
+            continue
+        obj = BUILD / (src.stem + ".o")
+        objs.append(obj)
+        if force or _stale(obj, [src] + headers):
+            cmd = [nvcc, "-c", str(src), "-o", str(obj)] + ARCH + COMMON + extra
+            if ptxas_info and src.suffix == ".cu":
+                cmd += ["-Xptxas", "-v"]
+            if verbose:
+                print(" ".join(cmd), file=sys.stderr)
+            subprocess.run(cmd, check=True)
+    if force or _stale(LIB, objs):
+        cmd = [nvcc, "-shared", "-o", str(LIB)] + [str(o) for o in objs] + ARCH + ["-Xcompiler", "-fPIC", "-lpthread"]
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        subprocess.run(cmd, check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--ptxas-info", action="store_true")
+    a = ap.parse_args()
+    print(build(a.force, a.verbose, a.ptxas_info))

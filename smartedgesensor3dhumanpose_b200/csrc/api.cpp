@@ -1,0 +1,444 @@
+// api.cpp — the C ABI of include/ses3d.h on top of the sm_100a kernels.
+//
+// ses3d_create            <- main() set-up of skeleton_3d / pose_reprojection (S3D:1184-1214, REP:272-279)
+// ses3d_triangulate_batch <- triangulate_persons (S3D:525-997), batched over frames
+// ses3d_reproject_batch   <- fusedSkeletonCallback (REP:139-235), batched over frames
+// ses3d_process_batch     <- both, chained on the device
+//
+// There is no CPU fallback: every entry point that computes needs a CUDA device and fails
+// with SES3D_E_CUDA otherwise. Host-buffer calls stream the batch through two device slots
+// (H2D, kernels and D2H of neighbouring chunks overlap); device-buffer calls run in place.
+// Device scratch belongs to the handle, grows monotonically and is reused across calls.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "host_setup.h"
+#include "launch.h"
+#include "ses3d.h"
+
+namespace {
+
+thread_local std::string g_last_error = "";
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(SES3D_E_CUDA, std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
+}
+#define CU(call)                                         \
+  do {                                                   \
+    cudaError_t e_ = (call);                             \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #call);  \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct Scratch {  // per-slot intermediates of the triangulation path
+  DevBuf hyp_det, n_hyp, n_hung, keep, tmp, nk;
+  void release() { hyp_det.release(); n_hyp.release(); n_hung.release(); keep.release(); tmp.release(); nk.release(); }
+};
+
+struct Slot {  // one in-flight chunk of a host-buffer call
+  cudaStream_t stream = nullptr;
+  Scratch sc;
+  DevBuf persons, n_persons, out3d, n_out3d, out2d, n_out2d, hyp_of;
+  void release() {
+    sc.release(); persons.release(); n_persons.release(); out3d.release(); n_out3d.release(); out2d.release();
+    n_out2d.release(); hyp_of.release();
+    if (stream) cudaStreamDestroy(stream);
+    stream = nullptr;
+  }
+};
+
+}  // namespace
+
+struct ses3d_handle_s {
+  int device = 0;
+  ses3d_params prm;
+  ses3d::HostTables host;
+  DevBuf d_camf, d_camd, d_F, d_frow, d_overflow;
+  ses3d::Tables tb;
+  Slot slot[2];
+  std::mutex mu;
+  int64_t launches = 0;
+  bool profiling = false;
+  float kernel_ms[4] = {0, 0, 0, 0};
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending_events;
+};
+
+namespace {
+
+using ses3d::LaunchDims;
+
+const int kDeviceChunk = 16384;  // frames per kernel launch on the device path (bounds scratch)
+
+struct ProfScope {  // optional CUDA-event bracket around one kernel launch
+  ses3d_handle_s* h;
+  int idx;
+  cudaStream_t st;
+  cudaEvent_t a = nullptr, b = nullptr;
+  ProfScope(ses3d_handle_s* h_, int idx_, cudaStream_t st_) : h(h_), idx(idx_), st(st_) {
+    if (h->profiling) {
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      cudaEventRecord(a, st);
+    }
+  }
+  ~ProfScope() {
+    if (h->profiling) {
+      cudaEventRecord(b, st);
+      h->pending_events.push_back({idx, {a, b}});
+    }
+  }
+};
+
+void resolve_events(ses3d_handle_s* h) {
+  for (auto& pe : h->pending_events) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, pe.second.first, pe.second.second) == cudaSuccess) h->kernel_ms[pe.first] += ms;
+    cudaEventDestroy(pe.second.first);
+    cudaEventDestroy(pe.second.second);
+  }
+  h->pending_events.clear();
+}
+
+// K2 -> K3 -> K4 on device pointers, stream-ordered, no synchronisation.
+int triangulate_on_device(ses3d_handle_s* h, Scratch& sc, cudaStream_t st, int n_frames, int p_max, int h_max,
+                          const ses3d_person2d* persons, const int32_t* n_persons, ses3d_person_cov* out,
+                          int32_t* n_out, int32_t* hyp_of, int32_t* n_hyp_dump, int32_t* n_hung_dump) {
+  const int C = h->tb.n_cams;
+  bool need_nk = false;
+  ses3d::associate_smem_bytes(C, p_max, h_max, &need_nk);
+  for (int f0 = 0; f0 < n_frames; f0 += kDeviceChunk) {
+    const int nf = std::min(kDeviceChunk, n_frames - f0);
+    CU(sc.hyp_det.ensure((size_t)nf * h_max * C));
+    CU(sc.n_hyp.ensure((size_t)nf * 4));
+    CU(sc.n_hung.ensure((size_t)nf * 4));
+    CU(sc.keep.ensure((size_t)nf * h_max * 4));
+    CU(sc.tmp.ensure((size_t)nf * h_max * sizeof(ses3d_person_cov)));
+    if (need_nk) CU(sc.nk.ensure((size_t)nf * C * p_max * ses3d::NKP * 3 * sizeof(float)));
+    LaunchDims d{nf, p_max, h_max};
+    const ses3d_person2d* pin = persons + (size_t)f0 * C * p_max;
+    const int32_t* nin = n_persons + (size_t)f0 * C;
+    int32_t* n_hyp = n_hyp_dump ? n_hyp_dump + f0 : sc.n_hyp.as<int32_t>();
+    int32_t* n_hung = n_hung_dump ? n_hung_dump + f0 : sc.n_hung.as<int32_t>();
+    {
+      ProfScope ps(h, 0, st);
+      CU(ses3d::launch_associate(h->tb, d, pin, nin, need_nk ? sc.nk.as<float>() : nullptr, sc.hyp_det.as<int8_t>(),
+                                 n_hyp, n_hung, h->d_overflow.as<int32_t>(),
+                                 hyp_of ? hyp_of + (size_t)f0 * C * p_max : nullptr, st));
+    }
+    {
+      ProfScope ps(h, 1, st);
+      CU(ses3d::launch_triangulate(h->tb, d, pin, sc.hyp_det.as<int8_t>(), sc.tmp.as<ses3d_person_cov>(),
+                                   sc.keep.as<int32_t>(), st));
+    }
+    {
+      ProfScope ps(h, 2, st);
+      CU(ses3d::launch_finalize(h->tb, d, n_hyp, sc.tmp.as<ses3d_person_cov>(), sc.keep.as<int32_t>(),
+                                out + (size_t)f0 * h_max, n_out + f0, st));
+    }
+    h->launches += 3;
+  }
+  return SES3D_OK;
+}
+
+int reproject_on_device(ses3d_handle_s* h, cudaStream_t st, int n_frames, int h_max, const ses3d_person_cov* persons3d,
+                        const int32_t* n_persons3d, ses3d_person2d* out, int32_t* n_out) {
+  const int C = h->tb.n_cams;
+  for (int f0 = 0; f0 < n_frames; f0 += kDeviceChunk) {
+    const int nf = std::min(kDeviceChunk, n_frames - f0);
+    ProfScope ps(h, 3, st);
+    CU(ses3d::launch_reproject(h->tb, nf, h_max, persons3d + (size_t)f0 * h_max, n_persons3d + f0,
+                               out + (size_t)f0 * C * h_max, n_out + (size_t)f0 * C, st));
+    h->launches += 1;
+  }
+  return SES3D_OK;
+}
+
+int check_dims(const ses3d_handle_s* h, int n_frames, int p_max, int h_max) {
+  if (!h) return fail(SES3D_E_INVALID, "null handle");
+  if (n_frames < 0) return fail(SES3D_E_INVALID, "n_frames < 0");
+  if (p_max < 1 || p_max > 127) return fail(SES3D_E_INVALID, "p_max must be in [1,127]");
+  if (h_max < 1 || h_max > 1024) return fail(SES3D_E_INVALID, "h_max must be in [1,1024]");
+  return SES3D_OK;
+}
+
+int host_chunk_frames(int n_frames) { return std::max(1, std::min(8192, std::max(1024, (n_frames + 3) / 4))); }
+
+enum Stage { TRI = 1, REP = 2 };
+
+// Shared implementation of the three batch entry points.
+int run_batch(ses3d_handle_s* h, int stages, int n_frames, int p_max, const ses3d_person2d* persons,
+              const int32_t* n_persons, int h_max, ses3d_person_cov* io3d, int32_t* n_io3d, ses3d_person2d* out2d,
+              int32_t* n_out2d, const ses3d_assoc_dump* dump, uint32_t flags, void* stream) {
+  std::lock_guard<std::mutex> lock(h->mu);
+  CU(cudaSetDevice(h->device));
+  const int C = h->tb.n_cams;
+  if (n_frames == 0) return SES3D_OK;
+  const bool dev = (flags & SES3D_DEVICE_BUFFERS) != 0;
+  if (h->profiling) for (float& m : h->kernel_ms) m = 0.f;
+  int32_t* hyp_of = dump ? dump->hyp_of : nullptr;
+  int32_t* n_hyp_d = dump ? dump->n_hyp : nullptr;
+  int32_t* n_hung_d = dump ? dump->n_hungarian : nullptr;
+
+  if (dev) {
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->slot[0].stream;
+    CU(cudaMemsetAsync(h->d_overflow.p, 0, 4, st));
+    if (stages & TRI) {
+      int rc = triangulate_on_device(h, h->slot[0].sc, st, n_frames, p_max, h_max, persons, n_persons, io3d, n_io3d,
+                                     hyp_of, n_hyp_d, n_hung_d);
+      if (rc) return rc;
+    }
+    if (stages & REP) {
+      int rc = reproject_on_device(h, st, n_frames, h_max, io3d, n_io3d, out2d, n_out2d);
+      if (rc) return rc;
+    }
+    int32_t overflow = 0;
+    CU(cudaMemcpyAsync(&overflow, h->d_overflow.p, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    resolve_events(h);
+    if (overflow) return fail(SES3D_E_CAPACITY, "a frame produced more hypotheses than h_max");
+    return SES3D_OK;
+  }
+
+  // host buffers: stream chunks through the two slots
+  const int chunk = host_chunk_frames(n_frames);
+  CU(cudaMemsetAsync(h->d_overflow.p, 0, 4, h->slot[0].stream));
+  CU(cudaStreamSynchronize(h->slot[0].stream));
+  int ci = 0;
+  for (int f0 = 0; f0 < n_frames; f0 += chunk, ++ci) {
+    const int nf = std::min(chunk, n_frames - f0);
+    Slot& s = h->slot[ci & 1];
+    cudaStream_t st = s.stream;
+    CU(s.out3d.ensure((size_t)nf * h_max * sizeof(ses3d_person_cov)));
+    CU(s.n_out3d.ensure((size_t)nf * 4));
+    if (stages & TRI) {
+      CU(s.persons.ensure((size_t)nf * C * p_max * sizeof(ses3d_person2d)));
+      CU(s.n_persons.ensure((size_t)nf * C * 4));
+      CU(cudaMemcpyAsync(s.persons.p, persons + (size_t)f0 * C * p_max, (size_t)nf * C * p_max * sizeof(ses3d_person2d),
+                         cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(s.n_persons.p, n_persons + (size_t)f0 * C, (size_t)nf * C * 4, cudaMemcpyHostToDevice, st));
+      int32_t* d_hyp_of = nullptr;
+      if (hyp_of) {
+        CU(s.hyp_of.ensure((size_t)nf * C * p_max * 4));
+        d_hyp_of = s.hyp_of.as<int32_t>();
+      }
+      int rc = triangulate_on_device(h, s.sc, st, nf, p_max, h_max, s.persons.as<ses3d_person2d>(),
+                                     s.n_persons.as<int32_t>(), s.out3d.as<ses3d_person_cov>(),
+                                     s.n_out3d.as<int32_t>(), d_hyp_of, nullptr, nullptr);
+      if (rc) return rc;
+      if (io3d) CU(cudaMemcpyAsync(io3d + (size_t)f0 * h_max, s.out3d.p, (size_t)nf * h_max * sizeof(ses3d_person_cov),
+                                   cudaMemcpyDeviceToHost, st));
+      if (n_io3d) CU(cudaMemcpyAsync(n_io3d + f0, s.n_out3d.p, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
+      if (hyp_of) CU(cudaMemcpyAsync(hyp_of + (size_t)f0 * C * p_max, d_hyp_of, (size_t)nf * C * p_max * 4,
+                                     cudaMemcpyDeviceToHost, st));
+      if (n_hyp_d) CU(cudaMemcpyAsync(n_hyp_d + f0, s.sc.n_hyp.p, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
+      if (n_hung_d) CU(cudaMemcpyAsync(n_hung_d + f0, s.sc.n_hung.p, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
+    } else {
+      CU(cudaMemcpyAsync(s.out3d.p, io3d + (size_t)f0 * h_max, (size_t)nf * h_max * sizeof(ses3d_person_cov),
+                         cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(s.n_out3d.p, n_io3d + f0, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+    }
+    if (stages & REP) {
+      CU(s.out2d.ensure((size_t)nf * C * h_max * sizeof(ses3d_person2d)));
+      CU(s.n_out2d.ensure((size_t)nf * C * 4));
+      int rc = reproject_on_device(h, st, nf, h_max, s.out3d.as<ses3d_person_cov>(), s.n_out3d.as<int32_t>(),
+                                   s.out2d.as<ses3d_person2d>(), s.n_out2d.as<int32_t>());
+      if (rc) return rc;
+      CU(cudaMemcpyAsync(out2d + (size_t)f0 * C * h_max, s.out2d.p, (size_t)nf * C * h_max * sizeof(ses3d_person2d),
+                         cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(n_out2d + (size_t)f0 * C, s.n_out2d.p, (size_t)nf * C * 4, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  CU(cudaStreamSynchronize(h->slot[0].stream));
+  CU(cudaStreamSynchronize(h->slot[1].stream));
+  resolve_events(h);
+  int32_t overflow = 0;
+  CU(cudaMemcpy(&overflow, h->d_overflow.p, 4, cudaMemcpyDeviceToHost));
+  if (overflow) return fail(SES3D_E_CAPACITY, "a frame produced more hypotheses than h_max");
+  return SES3D_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void ses3d_default_params(ses3d_params* p) {
+  if (!p) return;
+  p->pose_method = SES3D_POSE_SIMPLE;
+  p->precision = SES3D_PRECISION_FP32;
+  p->lm_refine = 0;
+  p->lm_max_iters = 10;
+  p->min_num_valid_keypoints = 9;
+  p->triangulation_threshold = 0.30f;
+  p->max_epipolar_error = 0.050;
+  p->reproj_error_max_acceptable = 0.050;
+  p->max_joint_dist_to_root = 2.0;
+  p->merge_dist_thresh = 0.20;
+  p->limb_cov_offset_sigma = 0.075;
+}
+
+int ses3d_create(int32_t n_cams, const ses3d_camera* cams, const ses3d_params* params, int32_t device,
+                 ses3d_handle* out) {
+  if (!out) return fail(SES3D_E_INVALID, "out is null");
+  *out = nullptr;
+  if (!cams || n_cams < 2 || n_cams > 255) return fail(SES3D_E_INVALID, "need 2..255 cameras");  // S3D:1133-1136
+  ses3d_params prm;
+  if (params) prm = *params;
+  else ses3d_default_params(&prm);
+  if (prm.pose_method != SES3D_POSE_SIMPLE && prm.pose_method != SES3D_POSE_H36M)
+    return fail(SES3D_E_INVALID, "pose_method must be SES3D_POSE_SIMPLE or SES3D_POSE_H36M");
+  if (prm.precision != SES3D_PRECISION_FP32 && prm.precision != SES3D_PRECISION_FP64)
+    return fail(SES3D_E_INVALID, "precision must be SES3D_PRECISION_FP32 or SES3D_PRECISION_FP64");
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0)
+    return fail(SES3D_E_CUDA, std::string("no CUDA device: this library has no CPU path (") +
+                                  (e == cudaSuccess ? "device count 0" : cudaGetErrorString(e)) + ")");
+  if (device < 0 || device >= n_dev) return fail(SES3D_E_INVALID, "device ordinal out of range");
+  CU(cudaSetDevice(device));
+  ses3d_handle_s* h = new (std::nothrow) ses3d_handle_s;
+  if (!h) return fail(SES3D_E_NOMEM, "out of host memory");
+  h->device = device;
+  h->prm = prm;
+  if (!ses3d::build_host_tables(n_cams, cams, prm, &h->host)) {
+    delete h;
+    return fail(SES3D_E_INVALID, "invalid camera table (singular extrinsics or zero focal length)");
+  }
+  auto upload = [&](DevBuf& b, const void* src, size_t bytes) -> cudaError_t {
+    cudaError_t ee = b.ensure(bytes);
+    if (ee != cudaSuccess) return ee;
+    return cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice);
+  };
+  cudaError_t ue = upload(h->d_camf, h->host.camf.data(), h->host.camf.size() * sizeof(ses3d::CamF));
+  if (ue == cudaSuccess) ue = upload(h->d_camd, h->host.camd.data(), h->host.camd.size() * sizeof(ses3d::CamD));
+  if (ue == cudaSuccess) ue = upload(h->d_F, h->host.F.data(), h->host.F.size() * sizeof(float));
+  if (ue == cudaSuccess) ue = upload(h->d_frow, h->host.f_row.data(), h->host.f_row.size() * sizeof(int));
+  if (ue == cudaSuccess) ue = h->d_overflow.ensure(4);
+  for (int i = 0; i < 2 && ue == cudaSuccess; ++i) ue = cudaStreamCreateWithFlags(&h->slot[i].stream, cudaStreamNonBlocking);
+  if (ue != cudaSuccess) {
+    ses3d_destroy(h);
+    return cuda_fail(ue, "ses3d_create upload");
+  }
+  h->tb.n_cams = n_cams;
+  h->tb.camf = h->d_camf.as<ses3d::CamF>();
+  h->tb.camd = h->d_camd.as<ses3d::CamD>();
+  h->tb.F = h->d_F.as<float>();
+  h->tb.f_row = h->d_frow.as<int>();
+  h->tb.model = h->host.model;
+  h->tb.prm = prm;
+  *out = h;
+  return SES3D_OK;
+}
+
+int ses3d_destroy(ses3d_handle h) {
+  if (!h) return SES3D_OK;
+  cudaSetDevice(h->device);
+  for (Slot& s : h->slot) s.release();
+  h->d_camf.release(); h->d_camd.release(); h->d_F.release(); h->d_frow.release(); h->d_overflow.release();
+  delete h;
+  return SES3D_OK;
+}
+
+int ses3d_get_tables(ses3d_handle h, float* P, float* F) {
+  if (!h) return fail(SES3D_E_INVALID, "null handle");
+  if (P)
+    for (int i = 0; i < h->host.n_cams; ++i) std::memcpy(P + (size_t)i * 12, h->host.camf[i].P, 12 * sizeof(float));
+  if (F) std::memcpy(F, h->host.F.data(), h->host.F.size() * sizeof(float));
+  return SES3D_OK;
+}
+
+int ses3d_triangulate_batch(ses3d_handle h, int32_t n_frames, int32_t p_max, const ses3d_person2d* persons,
+                            const int32_t* n_persons, int32_t h_max, ses3d_person_cov* out, int32_t* n_out,
+                            const ses3d_assoc_dump* dump, uint32_t flags, void* stream) {
+  int rc = check_dims(h, n_frames, p_max, h_max);
+  if (rc) return rc;
+  if (n_frames > 0 && (!persons || !n_persons || !out || !n_out)) return fail(SES3D_E_INVALID, "null buffer");
+  return run_batch(h, TRI, n_frames, p_max, persons, n_persons, h_max, out, n_out, nullptr, nullptr, dump, flags, stream);
+}
+
+int ses3d_reproject_batch(ses3d_handle h, int32_t n_frames, int32_t h_max, const ses3d_person_cov* persons3d,
+                          const int32_t* n_persons3d, ses3d_person2d* out, int32_t* n_out, uint32_t flags,
+                          void* stream) {
+  int rc = check_dims(h, n_frames, 1, h_max);
+  if (rc) return rc;
+  if (n_frames > 0 && (!persons3d || !n_persons3d || !out || !n_out)) return fail(SES3D_E_INVALID, "null buffer");
+  return run_batch(h, REP, n_frames, 1, nullptr, nullptr, h_max, const_cast<ses3d_person_cov*>(persons3d),
+                   const_cast<int32_t*>(n_persons3d), out, n_out, nullptr, flags, stream);
+}
+
+int ses3d_process_batch(ses3d_handle h, int32_t n_frames, int32_t p_max, const ses3d_person2d* persons,
+                        const int32_t* n_persons, int32_t h_max, ses3d_person_cov* out3d, int32_t* n_out3d,
+                        ses3d_person2d* out2d, int32_t* n_out2d, const ses3d_assoc_dump* dump, uint32_t flags,
+                        void* stream) {
+  int rc = check_dims(h, n_frames, p_max, h_max);
+  if (rc) return rc;
+  if (n_frames > 0 && (!persons || !n_persons || !out2d || !n_out2d)) return fail(SES3D_E_INVALID, "null buffer");
+  if ((flags & SES3D_DEVICE_BUFFERS) && n_frames > 0 && (!out3d || !n_out3d))
+    return fail(SES3D_E_INVALID, "device-buffer calls need out3d/n_out3d (the PersonCov list lives there)");
+  return run_batch(h, TRI | REP, n_frames, p_max, persons, n_persons, h_max, out3d, n_out3d, out2d, n_out2d, dump,
+                   flags, stream);
+}
+
+int ses3d_reserve(ses3d_handle h, int32_t n_frames, int32_t p_max, int32_t h_max) {
+  int rc = check_dims(h, n_frames, p_max, h_max);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lock(h->mu);
+  CU(cudaSetDevice(h->device));
+  const int C = h->tb.n_cams;
+  const int nf = std::min(n_frames, kDeviceChunk);
+  bool need_nk = false;
+  ses3d::associate_smem_bytes(C, p_max, h_max, &need_nk);
+  for (Slot& s : h->slot) {
+    CU(s.sc.hyp_det.ensure((size_t)nf * h_max * C));
+    CU(s.sc.n_hyp.ensure((size_t)nf * 4));
+    CU(s.sc.n_hung.ensure((size_t)nf * 4));
+    CU(s.sc.keep.ensure((size_t)nf * h_max * 4));
+    CU(s.sc.tmp.ensure((size_t)nf * h_max * sizeof(ses3d_person_cov)));
+    if (need_nk) CU(s.sc.nk.ensure((size_t)nf * C * p_max * ses3d::NKP * 3 * sizeof(float)));
+  }
+  return SES3D_OK;
+}
+
+int64_t ses3d_launch_count(ses3d_handle h) { return h ? h->launches : 0; }
+
+int ses3d_set_profiling(ses3d_handle h, int32_t on) {
+  if (!h) return fail(SES3D_E_INVALID, "null handle");
+  h->profiling = on != 0;
+  return SES3D_OK;
+}
+
+int ses3d_last_kernel_ms(ses3d_handle h, float ms[4]) {
+  if (!h || !ms) return fail(SES3D_E_INVALID, "null argument");
+  for (int i = 0; i < 4; ++i) ms[i] = h->kernel_ms[i];
+  return SES3D_OK;
+}
+
+const char* ses3d_last_error_string(void) { return g_last_error.c_str(); }
+const char* ses3d_version(void) { return "ses3d 0.1.0 (sm_100a)"; }
+
+}  // extern "C"

@@ -1,0 +1,352 @@
+// assoc_core.h — cross-view association of one frame (kernel K2 "associate").
+//
+// Replaces, for one frame: normalize_keypoints (S3D:312-333), calcCost (S3D:335-390), the
+// Tanke-Gall iterative greedy matching loop of triangulate_persons (S3D:528-674) and the
+// Munkres solver HungarianAlgorithm::assignmentoptimal (Hungarian.cpp:60-397, called S3D:630).
+//
+// Association indices must be bit-exact with the reference, so this file keeps the
+// reference's float/double split and evaluation order and MUST be compiled without FMA
+// contraction (nvcc -fmad=false; g++ -ffp-contract=off).
+//
+// B200 mapping: one team per frame. The n_hyp x n_det cost matrix of a camera round is
+// filled in parallel (one entry per thread, each entry walks the hypothesis' observations
+// and the 17 joints); the sequential parts (ambiguity test, Munkres, hypothesis update)
+// are a few hundred integer operations run by the team leader on shared memory.
+#pragma once
+#include "common.h"
+#include "team.h"
+
+namespace ses3d {
+
+enum { SC_N_HYP = 0, SC_N_DET, SC_N_HUNG, SC_OVERFLOW, SC_CURSOR, SC_COUNT };
+
+struct AssocWs {
+  float* nk;          // [C*p_max][17][3] normalised keypoints x, y, conf ((0,0,-1) below threshold)
+  float* pscore;      // [C*p_max] Person2D.score
+  uint8_t* valid;     // [C*p_max] more than 8 valid keypoints (S3D:579,599)
+  uint8_t* hyp_nobs;  // [h_cap]
+  uint16_t* hyp_obs;  // [h_cap][C] observation list, (cam << 8) | det, in camera order
+  uint8_t* dets;      // [p_max] valid detections of the current camera
+  double* cost;       // [h_cap*p_max] column-major n_hyp x n_det (S3D:611)
+  double* dist;       // Munkres working copy
+  uint8_t *mask, *star, *prime, *nstar;  // [h_cap*p_max]
+  uint8_t *cov_r, *cov_c, *handled;      // [h_cap], [p_max], [p_max]
+  int* assignment;    // [h_cap]
+  int* scal;          // [SC_COUNT]
+};
+
+// Lays the workspace out in `base`; when nk_external != nullptr the keypoints live there
+// (global scratch for rigs whose frame does not fit in shared memory).
+template <class A>
+SES_HD void assoc_ws_layout(A& ar, int C, int p_max, int h_cap, bool nk_inside, AssocWs* ws) {
+  double* cost = ar.template take<double>((size_t)h_cap * p_max);
+  double* dist = ar.template take<double>((size_t)h_cap * p_max);
+  float* nk = nk_inside ? ar.template take<float>((size_t)C * p_max * NKP * 3) : nullptr;
+  float* pscore = ar.template take<float>((size_t)C * p_max);
+  int* assignment = ar.template take<int>(h_cap);
+  int* scal = ar.template take<int>(SC_COUNT);
+  uint16_t* hyp_obs = ar.template take<uint16_t>((size_t)h_cap * C);
+  uint8_t* valid = ar.template take<uint8_t>((size_t)C * p_max);
+  uint8_t* hyp_nobs = ar.template take<uint8_t>(h_cap);
+  uint8_t* dets = ar.template take<uint8_t>(p_max);
+  uint8_t* mask = ar.template take<uint8_t>((size_t)h_cap * p_max);
+  uint8_t* star = ar.template take<uint8_t>((size_t)h_cap * p_max);
+  uint8_t* prime = ar.template take<uint8_t>((size_t)h_cap * p_max);
+  uint8_t* nstar = ar.template take<uint8_t>((size_t)h_cap * p_max);
+  uint8_t* cov_r = ar.template take<uint8_t>(h_cap);
+  uint8_t* cov_c = ar.template take<uint8_t>(p_max);
+  uint8_t* handled = ar.template take<uint8_t>(p_max);
+  if (ws) {
+    ws->cost = cost; ws->dist = dist; if (nk_inside) ws->nk = nk; ws->pscore = pscore;
+    ws->assignment = assignment; ws->scal = scal; ws->hyp_obs = hyp_obs; ws->valid = valid;
+    ws->hyp_nobs = hyp_nobs; ws->dets = dets; ws->mask = mask; ws->star = star; ws->prime = prime;
+    ws->nstar = nstar; ws->cov_r = cov_r; ws->cov_c = cov_c; ws->handled = handled;
+  }
+}
+
+inline size_t assoc_ws_bytes(int C, int p_max, int h_cap, bool nk_inside) {
+  ArenaSizer s;
+  assoc_ws_layout(s, C, p_max, h_cap, nk_inside, nullptr);
+  return (s.used + 15) / 16 * 16;
+}
+
+// Symmetric point-to-epipolar-line distance d1 + d2 in float (S3D:355-362):
+// l1 = F (x1,y1,1), l2 = F^T (x2,y2,1), d1 = |p2.l1| / sqrt(l1x^2+l1y^2), d2 = |p1.l2| / sqrt(l2x^2+l2y^2).
+SES_HD float epipolar_symmetric(const float* F, float x1, float y1, float x2, float y2) {
+  const float l1x = sum3(F[0] * x1, F[1] * y1, F[2] * 1.0f);
+  const float l1y = sum3(F[3] * x1, F[4] * y1, F[5] * 1.0f);
+  const float l1z = sum3(F[6] * x1, F[7] * y1, F[8] * 1.0f);
+  const float l2x = sum3(F[0] * x2, F[3] * y2, F[6] * 1.0f);
+  const float l2y = sum3(F[1] * x2, F[4] * y2, F[7] * 1.0f);
+  const float l2z = sum3(F[2] * x2, F[5] * y2, F[8] * 1.0f);
+  const float d1 = ses_abs(sum3(x2 * l1x, y2 * l1y, 1.0f * l1z)) / ses_sqrt(l1x * l1x + l1y * l1y);
+  const float d2 = ses_abs(sum3(x1 * l2x, y1 * l2y, 1.0f * l2z)) / ses_sqrt(l2x * l2x + l2y * l2y);
+  return d1 + d2;
+}
+
+// Munkres on the column-major n_r x n_c matrix `in` (Hungarian.cpp:60-397). The reference's
+// mutual recursion step2a/2b/3/4/5 is unrolled into a state machine; scan orders, the
+// |x| < DBL_EPSILON zero test and the +-h updates are kept so ties resolve identically.
+SES_HD void munkres_serial(const AssocWs& ws, const double* in, int n_r, int n_c, int* assignment) {
+  const int n_e = n_r * n_c;
+  double* dist = ws.dist;
+  uint8_t *star = ws.star, *prime = ws.prime, *nstar = ws.nstar, *cov_r = ws.cov_r, *cov_c = ws.cov_c;
+  for (int i = 0; i < n_e; ++i) { dist[i] = in[i]; star[i] = 0; prime[i] = 0; nstar[i] = 0; }
+  for (int r = 0; r < n_r; ++r) { cov_r[r] = 0; assignment[r] = -1; }
+  for (int c = 0; c < n_c; ++c) cov_c[c] = 0;
+  int min_dim;
+  if (n_r <= n_c) {  // Hungarian.cpp:95-131: row reduction, row-major first-zero starring
+    min_dim = n_r;
+    for (int r = 0; r < n_r; ++r) {
+      double mn = dist[r];
+      for (int c = 1; c < n_c; ++c) { const double v = dist[r + n_r * c]; if (v < mn) mn = v; }
+      for (int c = 0; c < n_c; ++c) dist[r + n_r * c] -= mn;
+    }
+    for (int r = 0; r < n_r; ++r)
+      for (int c = 0; c < n_c; ++c)
+        if (fabs(dist[r + n_r * c]) < DBL_EPSILON && !cov_c[c]) { star[r + n_r * c] = 1; cov_c[c] = 1; break; }
+  } else {  // Hungarian.cpp:132-170: column reduction, column-major starring
+    min_dim = n_c;
+    for (int c = 0; c < n_c; ++c) {
+      double mn = dist[n_r * c];
+      for (int r = 1; r < n_r; ++r) { const double v = dist[r + n_r * c]; if (v < mn) mn = v; }
+      for (int r = 0; r < n_r; ++r) dist[r + n_r * c] -= mn;
+    }
+    for (int c = 0; c < n_c; ++c)
+      for (int r = 0; r < n_r; ++r)
+        if (fabs(dist[r + n_r * c]) < DBL_EPSILON && !cov_r[r]) {
+          star[r + n_r * c] = 1; cov_c[c] = 1; cov_r[r] = 1; break;
+        }
+    for (int r = 0; r < n_r; ++r) cov_r[r] = 0;
+  }
+  enum { S2A, S2B, S3, S4, S5, DONE };
+  int st = S2B, row4 = 0, col4 = 0;
+  while (st != DONE) {
+    if (st == S2A) {  // cover every column holding a star (Hungarian.cpp:222-242)
+      for (int c = 0; c < n_c; ++c)
+        for (int r = 0; r < n_r; ++r)
+          if (star[r + n_r * c]) { cov_c[c] = 1; break; }
+      st = S2B;
+    } else if (st == S2B) {  // Hungarian.cpp:245-266
+      int n = 0;
+      for (int c = 0; c < n_c; ++c) n += cov_c[c] ? 1 : 0;
+      st = (n == min_dim) ? DONE : S3;
+    } else if (st == S3) {  // prime uncovered zeros, column-outer scan (Hungarian.cpp:269-309)
+      bool zeros = true, to4 = false;
+      while (zeros && !to4) {
+        zeros = false;
+        for (int c = 0; c < n_c && !to4; ++c) {
+          if (cov_c[c]) continue;
+          for (int r = 0; r < n_r; ++r) {
+            if (!cov_r[r] && fabs(dist[r + n_r * c]) < DBL_EPSILON) {
+              prime[r + n_r * c] = 1;
+              int sc = 0;
+              for (; sc < n_c; ++sc)
+                if (star[r + n_r * sc]) break;
+              if (sc == n_c) { row4 = r; col4 = c; to4 = true; }
+              else { cov_r[r] = 1; cov_c[sc] = 0; zeros = true; }
+              break;
+            }
+          }
+        }
+      }
+      st = to4 ? S4 : S5;
+    } else if (st == S4) {  // augmenting path (Hungarian.cpp:312-363)
+      for (int i = 0; i < n_e; ++i) nstar[i] = star[i];
+      nstar[row4 + n_r * col4] = 1;
+      int sc = col4, sr = 0;
+      for (sr = 0; sr < n_r; ++sr)
+        if (star[sr + n_r * sc]) break;
+      while (sr < n_r) {
+        nstar[sr + n_r * sc] = 0;
+        int pc = 0;
+        for (; pc < n_c; ++pc)
+          if (prime[sr + n_r * pc]) break;
+        nstar[sr + n_r * pc] = 1;
+        sc = pc;
+        for (sr = 0; sr < n_r; ++sr)
+          if (star[sr + n_r * sc]) break;
+      }
+      for (int i = 0; i < n_e; ++i) { prime[i] = 0; star[i] = nstar[i]; }
+      for (int r = 0; r < n_r; ++r) cov_r[r] = 0;
+      st = S2A;
+    } else {  // S5: shift by the smallest uncovered element (Hungarian.cpp:366-397)
+      double h = DBL_MAX;
+      for (int r = 0; r < n_r; ++r)
+        if (!cov_r[r])
+          for (int c = 0; c < n_c; ++c)
+            if (!cov_c[c]) { const double v = dist[r + n_r * c]; if (v < h) h = v; }
+      for (int r = 0; r < n_r; ++r)
+        if (cov_r[r])
+          for (int c = 0; c < n_c; ++c) dist[r + n_r * c] += h;
+      for (int c = 0; c < n_c; ++c)
+        if (!cov_c[c])
+          for (int r = 0; r < n_r; ++r) dist[r + n_r * c] -= h;
+      st = S3;
+    }
+  }
+  for (int r = 0; r < n_r; ++r)  // buildassignmentvector (Hungarian.cpp:190-205)
+    for (int c = 0; c < n_c; ++c)
+      if (star[r + n_r * c]) { assignment[r] = c; break; }
+}
+
+// One frame. persons [C][p_max], n_persons [C]. Outputs: hyp_det [h_cap][C] (detection slot of
+// hypothesis h in camera c or -1), n_hyp, n_hungarian, overflow flag (h_cap exceeded).
+template <class Team>
+SES_HD void associate_frame(Team& tm, const Tables& tb, int p_max, int h_cap, const ses3d_person2d* persons,
+                            const int32_t* n_persons, const AssocWs& ws, int8_t* hyp_det, int32_t* n_hyp_out,
+                            int32_t* n_hung_out, int32_t* overflow_out) {
+  const int C = tb.n_cams;
+  const float thr = tb.prm.triangulation_threshold;
+  const double max_epi = tb.prm.max_epipolar_error;
+  auto np = [&](int c) { const int n = n_persons[c]; return n < 0 ? 0 : (n > p_max ? p_max : n); };
+
+  // normalize_keypoints for every detection of the frame (S3D:312-333)
+  tm.pfor(C * p_max * NKP, [&](int i) {
+    const int k = i % NKP, cd = i / NKP, c = cd / p_max, d = cd % p_max;
+    float* o = ws.nk + (size_t)i * 3;
+    o[0] = 0.f; o[1] = 0.f; o[2] = -1.f;
+    if (d < np(c)) {
+      const ses3d_keypoint2d& kp = persons[cd].keypoints[k];
+      const CamF& cm = tb.camf[c];
+      if (kp.score >= thr) {
+        o[0] = (kp.x - cm.cx) / cm.fx;
+        o[1] = (kp.y - cm.cy) / cm.fy;
+        o[2] = kp.score;
+      }
+    }
+  });
+  tm.pfor(C * p_max, [&](int cd) {
+    const int c = cd / p_max, d = cd % p_max;
+    int n_valid = 0;
+    if (d < np(c))
+      for (int k = 0; k < NKP; ++k) n_valid += ws.nk[((size_t)cd * NKP + k) * 3 + 2] >= thr ? 1 : 0;
+    ws.valid[cd] = n_valid > NKP / 2 ? 1 : 0;
+    ws.pscore[cd] = d < np(c) ? persons[cd].score : 0.f;
+  });
+
+  auto add_hyp = [&](int cam, int det) {  // push_back of a one-observation hypothesis
+    const int h = ws.scal[SC_N_HYP];
+    if (h >= h_cap) { ws.scal[SC_OVERFLOW] = 1; return; }
+    ws.hyp_obs[(size_t)h * C] = (uint16_t)((cam << 8) | det);
+    ws.hyp_nobs[h] = 1;
+    ws.scal[SC_N_HYP] = h + 1;
+  };
+
+  // cameras with detections, seed hypotheses (S3D:538-586)
+  tm.single([&] {
+    int n_with = 0;
+    for (int c = 0; c < C; ++c) n_with += np(c) > 0 ? 1 : 0;
+    ws.scal[SC_N_HYP] = 0; ws.scal[SC_N_HUNG] = 0; ws.scal[SC_OVERFLOW] = 0; ws.scal[SC_N_DET] = 0;
+    int c = C;
+    if (n_with >= 2) {
+      for (c = 0; c < C; ++c) {
+        if (np(c) == 0) continue;
+        for (int d = 0; d < np(c); ++d)
+          if (ws.valid[c * p_max + d]) add_hyp(c, d);
+        if (ws.scal[SC_N_HYP] > 0) { ++c; break; }
+      }
+    }
+    ws.scal[SC_CURSOR] = c;
+  });
+
+  for (int cam = ws.scal[SC_CURSOR]; cam < C; ++cam) {  // S3D:588-674
+    if (np(cam) == 0) continue;
+    tm.single([&] {
+      int n = 0;
+      for (int d = 0; d < np(cam); ++d)
+        if (ws.valid[cam * p_max + d]) ws.dets[n++] = (uint8_t)d;
+      ws.scal[SC_N_DET] = n;
+    });
+    const int n_det = ws.scal[SC_N_DET], n_hyp = ws.scal[SC_N_HYP];
+    if (n_det == 0) continue;
+
+    // cost matrix, one (hypothesis, detection) entry per thread: calcCost S3D:335-390
+    tm.pfor(n_hyp * n_det, [&](int e) {
+      const int h = e % n_hyp, di = e / n_hyp;
+      const float* dk = ws.nk + ((size_t)(cam * p_max + ws.dets[di]) * NKP) * 3;
+      const int n_obs = ws.hyp_nobs[h];
+      double total = 0., tmp_veto = 0.;
+      int n_used = 0;
+      const double tolerance = 1.0 - 1.0 / (2 * n_obs), veto_delta = 1.0 / n_obs;
+      for (int o = 0; o < n_obs; ++o) {
+        const int oc = ws.hyp_obs[(size_t)h * C + o] >> 8, od = ws.hyp_obs[(size_t)h * C + o] & 255;
+        const float* F = tb.F + (size_t)fundamental_idx(tb, oc, cam) * 9;
+        const float* hk = ws.nk + ((size_t)(oc * p_max + od) * NKP) * 3;
+        double cost = 0.;
+        int n_joints = 0;
+        for (int k = 0; k < NKP; ++k) {
+          if (hk[3 * k + 2] > thr && dk[3 * k + 2] > thr) {
+            cost += static_cast<double>(epipolar_symmetric(F, hk[3 * k], hk[3 * k + 1], dk[3 * k], dk[3 * k + 1]));
+            ++n_joints;
+          }
+        }
+        if (n_joints > 0) {
+          cost /= n_joints;
+          total += cost;
+          ++n_used;
+          if (cost > max_epi && (ws.pscore[oc * p_max + od] > 0.5f || n_obs == 1)) tmp_veto += veto_delta;
+        }
+      }
+      bool veto = tmp_veto > tolerance;
+      double c;
+      if (n_used > 0) c = total / n_used;
+      else { veto = true; c = MAX_COSTS; }
+      ws.cost[e] = c;  // column-major: h + n_hyp * di
+      ws.mask[e] = (!veto && c < max_epi) ? 1 : 0;
+    });
+
+    tm.single([&] {
+      // provisional assignment: the last passing detection per hypothesis (S3D:616-626)
+      for (int h = 0; h < n_hyp; ++h) ws.assignment[h] = -1;
+      bool ambiguous = false;
+      for (int d = 0; d < n_det; ++d) {
+        int col = 0;
+        for (int h = 0; h < n_hyp; ++h)
+          if (ws.mask[h + n_hyp * d]) { ws.assignment[h] = d; ++col; }
+        ambiguous = ambiguous || col > 1;
+      }
+      for (int h = 0; h < n_hyp && !ambiguous; ++h) {
+        int row = 0;
+        for (int d = 0; d < n_det; ++d) row += ws.mask[h + n_hyp * d];
+        ambiguous = row > 1;
+      }
+      if (ambiguous) {  // S3D:628-634
+        ++ws.scal[SC_N_HUNG];
+        munkres_serial(ws, ws.cost, n_hyp, n_det, ws.assignment);
+      }
+      for (int d = 0; d < n_det; ++d) ws.handled[d] = 0;
+      for (int h = 0; h < n_hyp; ++h) {  // S3D:637-660
+        const int d = ws.assignment[h];
+        if (d < 0) continue;
+        ws.handled[d] = 1;
+        if (!ws.mask[h + n_hyp * d]) add_hyp(cam, ws.dets[d]);
+        else {
+          const int o = ws.hyp_nobs[h];
+          ws.hyp_obs[(size_t)h * C + o] = (uint16_t)((cam << 8) | ws.dets[d]);
+          ws.hyp_nobs[h] = (uint8_t)(o + 1);
+        }
+      }
+      for (int d = 0; d < n_det; ++d)  // S3D:662-673
+        if (!ws.handled[d]) add_hyp(cam, ws.dets[d]);
+    });
+  }
+
+  // export the hypothesis table
+  const int n_hyp = ws.scal[SC_N_HYP];
+  tm.pfor(h_cap * C, [&](int i) { hyp_det[i] = -1; });
+  tm.pfor(n_hyp * C, [&](int i) {
+    const int h = i / C, o = i % C;
+    if (o < ws.hyp_nobs[h]) {
+      const int oc = ws.hyp_obs[(size_t)h * C + o] >> 8, od = ws.hyp_obs[(size_t)h * C + o] & 255;
+      hyp_det[h * C + oc] = (int8_t)od;
+    }
+  });
+  tm.single([&] {
+    *n_hyp_out = n_hyp;
+    if (n_hung_out) *n_hung_out = ws.scal[SC_N_HUNG];
+    if (ws.scal[SC_OVERFLOW]) *overflow_out = 1;
+  });
+}
+
+}  // namespace ses3d

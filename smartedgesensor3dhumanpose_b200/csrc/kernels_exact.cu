@@ -1,0 +1,118 @@
+// kernels_exact.cu — K2 associate, K4 finalize, K6 reproject for sm_100a.
+//
+// Compiled with -fmad=false: association indices must be bit-exact with the reference's
+// x86-64 (SSE2, no FMA) arithmetic, and finalize/reproject are FP64 paths whose results
+// then match the CPU oracle bit for bit as well. The algorithms live in *_core.h; this
+// file only binds a CTA to a frame and carves the shared-memory workspace.
+#include "assoc_core.h"
+#include "fin_core.h"
+#include "launch.h"
+#include "reproj_core.h"
+
+namespace ses3d {
+
+extern __shared__ __align__(16) unsigned char smem_raw[];
+
+__global__ void __launch_bounds__(128)
+k_associate(const Tables tb, int n_frames, int p_max, int h_cap, const ses3d_person2d* __restrict__ persons,
+            const int32_t* __restrict__ n_persons, float* nk_scratch, int8_t* __restrict__ hyp_det,
+            int32_t* __restrict__ n_hyp, int32_t* __restrict__ n_hung, int32_t* overflow, int32_t* hyp_of_dump) {
+  const int f = blockIdx.x;
+  if (f >= n_frames) return;
+  const int C = tb.n_cams;
+  Arena ar(smem_raw);
+  AssocWs ws;
+  assoc_ws_layout(ar, C, p_max, h_cap, nk_scratch == nullptr, &ws);
+  if (nk_scratch) ws.nk = nk_scratch + (size_t)f * C * p_max * NKP * 3;
+  BlockTeam tm;
+  int8_t* hd = hyp_det + (size_t)f * h_cap * C;
+  associate_frame(tm, tb, p_max, h_cap, persons + (size_t)f * C * p_max, n_persons + (size_t)f * C, ws, hd, n_hyp + f,
+                  n_hung ? n_hung + f : nullptr, overflow);
+  if (hyp_of_dump) {  // [C][p_max] hypothesis index of each detection
+    int32_t* ho = hyp_of_dump + (size_t)f * C * p_max;
+    tm.pfor(C * p_max, [&](int i) { ho[i] = -1; });
+    const int nh = ws.scal[SC_N_HYP];
+    tm.pfor(nh * C, [&](int i) {
+      const int h = i / C, c = i % C;
+      const int d = hd[h * C + c];
+      if (d >= 0) ho[c * p_max + d] = h;
+    });
+  }
+}
+
+__global__ void __launch_bounds__(64)
+k_finalize(const Tables tb, int n_frames, int h_cap, const int32_t* __restrict__ n_hyp, ses3d_person_cov* tmp,
+           const int32_t* __restrict__ keep, ses3d_person_cov* __restrict__ out, int32_t* __restrict__ n_out) {
+  const int f = blockIdx.x;
+  if (f >= n_frames) return;
+  Arena ar(smem_raw);
+  FinWs ws;
+  fin_ws_layout(ar, h_cap, &ws);
+  BlockTeam tm;
+  finalize_frame(tm, tb, h_cap, n_hyp[f], tmp + (size_t)f * h_cap, keep + (size_t)f * h_cap, ws,
+                 out + (size_t)f * h_cap, n_out + f);
+}
+
+__global__ void __launch_bounds__(128)
+k_reproject(const Tables tb, int n_frames, int h_max, int cam_tile, const ses3d_person_cov* __restrict__ persons3d,
+            const int32_t* __restrict__ n_persons3d, ses3d_person2d* __restrict__ out, int32_t* __restrict__ n_out) {
+  const int f = blockIdx.x;
+  if (f >= n_frames) return;
+  Arena ar(smem_raw);
+  ReprojWs ws;
+  reproj_ws_layout(ar, cam_tile, h_max, &ws);
+  BlockTeam tm;
+  reproject_frame(tm, tb, h_max, cam_tile, persons3d + (size_t)f * h_max, n_persons3d[f], ws,
+                  out + (size_t)f * tb.n_cams * h_max, n_out + (size_t)f * tb.n_cams);
+}
+
+static const size_t kSmemBudget = 200 * 1024;   // of the 227 KB a CTA may opt in to
+static const size_t kAssocSmemTarget = 64 * 1024;
+
+size_t associate_smem_bytes(int n_cams, int p_max, int h_cap, bool* needs_scratch) {
+  size_t b = assoc_ws_bytes(n_cams, p_max, h_cap, true);
+  bool scratch = b > kAssocSmemTarget;
+  if (scratch) b = assoc_ws_bytes(n_cams, p_max, h_cap, false);
+  if (needs_scratch) *needs_scratch = scratch;
+  return b;
+}
+
+cudaError_t launch_associate(const Tables& tb, LaunchDims d, const ses3d_person2d* persons, const int32_t* n_persons,
+                             float* nk_scratch, int8_t* hyp_det, int32_t* n_hyp, int32_t* n_hung, int32_t* overflow,
+                             int32_t* hyp_of_dump, cudaStream_t st) {
+  bool scratch;
+  const size_t smem = associate_smem_bytes(tb.n_cams, d.p_max, d.h_cap, &scratch);
+  if (smem > kSmemBudget) return cudaErrorInvalidConfiguration;
+  if (scratch && !nk_scratch) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(k_associate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int threads = (tb.n_cams * d.p_max >= 256) ? 128 : 32;
+  k_associate<<<d.n_frames, threads, smem, st>>>(tb, d.n_frames, d.p_max, d.h_cap, persons, n_persons,
+                                                 scratch ? nk_scratch : nullptr, hyp_det, n_hyp, n_hung, overflow,
+                                                 hyp_of_dump);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_finalize(const Tables& tb, LaunchDims d, const int32_t* n_hyp, ses3d_person_cov* tmp,
+                            const int32_t* keep, ses3d_person_cov* out, int32_t* n_out, cudaStream_t st) {
+  const size_t smem = fin_ws_bytes(d.h_cap);
+  if (smem > kSmemBudget) return cudaErrorInvalidConfiguration;
+  cudaError_t e = cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_finalize<<<d.n_frames, 32, smem, st>>>(tb, d.n_frames, d.h_cap, n_hyp, tmp, keep, out, n_out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_reproject(const Tables& tb, int n_frames, int h_max, const ses3d_person_cov* persons3d,
+                             const int32_t* n_persons3d, ses3d_person2d* out, int32_t* n_out, cudaStream_t st) {
+  int cam_tile = tb.n_cams;
+  while (cam_tile > 1 && reproj_ws_bytes(cam_tile, h_max) > 40 * 1024) cam_tile = (cam_tile + 1) / 2;
+  const size_t smem = reproj_ws_bytes(cam_tile, h_max);
+  if (smem > kSmemBudget) return cudaErrorInvalidConfiguration;
+  cudaError_t e = cudaFuncSetAttribute(k_reproject, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_reproject<<<n_frames, 128, smem, st>>>(tb, n_frames, h_max, cam_tile, persons3d, n_persons3d, out, n_out);
+  return cudaGetLastError();
+}
+
+}  // namespace ses3d

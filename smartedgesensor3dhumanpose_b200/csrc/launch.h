@@ -1,0 +1,31 @@
+// launch.h — host-side launchers of the four kernels (implemented in kernels_*.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "common.h"
+
+namespace ses3d {
+
+struct LaunchDims {
+  int n_frames, p_max, h_cap;
+};
+
+// K2: one CTA per frame. nk_scratch != nullptr selects the global-memory keypoint path.
+cudaError_t launch_associate(const Tables& tb, LaunchDims d, const ses3d_person2d* persons, const int32_t* n_persons,
+                             float* nk_scratch, int8_t* hyp_det, int32_t* n_hyp, int32_t* n_hung, int32_t* overflow,
+                             int32_t* hyp_of_dump, cudaStream_t st);
+size_t associate_smem_bytes(int n_cams, int p_max, int h_cap, bool* needs_scratch);
+
+// K3: one CTA per (frame, hypothesis)
+cudaError_t launch_triangulate(const Tables& tb, LaunchDims d, const ses3d_person2d* persons, const int8_t* hyp_det,
+                               ses3d_person_cov* tmp, int32_t* keep, cudaStream_t st);
+
+// K4: one CTA per frame
+cudaError_t launch_finalize(const Tables& tb, LaunchDims d, const int32_t* n_hyp, ses3d_person_cov* tmp,
+                            const int32_t* keep, ses3d_person_cov* out, int32_t* n_out, cudaStream_t st);
+
+// K6: one CTA per frame
+cudaError_t launch_reproject(const Tables& tb, int n_frames, int h_max, const ses3d_person_cov* persons3d,
+                             const int32_t* n_persons3d, ses3d_person2d* out, int32_t* n_out, cudaStream_t st);
+
+}  // namespace ses3d

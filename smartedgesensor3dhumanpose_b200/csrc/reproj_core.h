@@ -1,0 +1,138 @@
+// reproj_core.h — semantic-feedback reprojection of one frame (kernel K6 "reproject").
+//
+// Replaces fusedSkeletonCallback (REP:139-235) with draw_sigma_points (REP:62-75): per joint
+// with score > 0 the 3x3 covariance is Cholesky-factored (Eigen llt), 7 sigma points are
+// pushed through T_cam<-base and image_geometry::project3dToPixel, giving a pixel mean and
+// 2x2 covariance per camera; joints whose mean falls outside the image are skipped, the
+// bounding box is the min/max of the accepted means, and a person is emitted for a camera
+// only if it has at least one accepted joint. FP64 compute, FP32 store, like the reference.
+//
+// B200 mapping: one team per frame; one thread per (person, joint) factors the covariance once
+// and walks the cameras of the current camera tile; the tile's Person2D records are staged in
+// shared memory so that per-camera compaction ends in one coalesced copy.
+#pragma once
+#include "common.h"
+#include "team.h"
+
+namespace ses3d {
+
+struct ReprojWs {
+  ses3d_person2d* stage;  // [cc][n_p] (capacity cam_tile*h_max), dense in the frame's person count
+  uint8_t* vflag;         // [cc][n_p][17] joint accepted
+  int* slot;              // [cc][n_p] output slot or -1
+};
+
+template <class A>
+SES_HD void reproj_ws_layout(A& ar, int cam_tile, int h_max, ReprojWs* ws) {
+  ses3d_person2d* stage = ar.template take<ses3d_person2d>((size_t)cam_tile * h_max);
+  int* slot = ar.template take<int>((size_t)cam_tile * h_max);
+  uint8_t* vflag = ar.template take<uint8_t>((size_t)cam_tile * h_max * NKP);
+  if (ws) { ws->stage = stage; ws->slot = slot; ws->vflag = vflag; }
+}
+inline size_t reproj_ws_bytes(int cam_tile, int h_max) {
+  ArenaSizer s;
+  reproj_ws_layout(s, cam_tile, h_max, nullptr);
+  return (s.used + 15) / 16 * 16;
+}
+
+// persons3d [n_p] (n_p <= h_max); out [C][h_max]; n_out [C]
+template <class Team>
+SES_HD void reproject_frame(Team& tm, const Tables& tb, int h_max, int cam_tile, const ses3d_person_cov* persons3d,
+                            int n_p, const ReprojWs& ws, ses3d_person2d* out, int32_t* n_out) {
+  const int C = tb.n_cams;
+  const int words = (int)(sizeof(ses3d_person2d) / 4);  // 107
+  if (n_p > h_max) n_p = h_max;
+  if (n_p < 0) n_p = 0;
+  for (int c0 = 0; c0 < C; c0 += cam_tile) {
+    const int ncc = (C - c0) < cam_tile ? (C - c0) : cam_tile;
+    tm.pfor(ncc * n_p * words, [&](int e) { reinterpret_cast<uint32_t*>(ws.stage)[e] = 0u; });
+
+    tm.pfor(n_p * NKP, [&](int e) {
+      const int p = e / NKP, k = e % NKP;
+      const ses3d_keypoint_cov& kp = persons3d[p].keypoints[tb.model.fusion_idx[k]];
+      const bool present = kp.score > 0.0f;  // REP:181
+      double S[7][3];
+      if (present) {
+        // lower Cholesky of [[c0 c1 c2][c1 c3 c4][c2 c4 c5]] (REP:72, 184-187)
+        const double l00 = sqrt(kp.cov[0]);
+        const double l10 = kp.cov[1] / l00, l20 = kp.cov[2] / l00;
+        const double l11 = sqrt(kp.cov[3] - l10 * l10);
+        const double l21 = (kp.cov[4] - l20 * l10) / l11;
+        const double l22 = sqrt(kp.cov[5] - l20 * l20 - l21 * l21);
+        const double sp = sqrt(3.0 + 0.5);  // sqrt(DIM + kappa) REP:63,68
+        // samples: mean, mean - sp*L e_j (j=0..2), mean + sp*L e_j (REP:68-72)
+        const double col[3][3] = {{l00, l10, l20}, {0.0, l11, l21}, {0.0, 0.0, l22}};
+        S[0][0] = kp.x; S[0][1] = kp.y; S[0][2] = kp.z;
+        for (int j = 0; j < 3; ++j) {
+          S[1 + j][0] = (col[j][0] * -sp) + kp.x; S[1 + j][1] = (col[j][1] * -sp) + kp.y; S[1 + j][2] = (col[j][2] * -sp) + kp.z;
+          S[4 + j][0] = (col[j][0] * sp) + kp.x;  S[4 + j][1] = (col[j][1] * sp) + kp.y;  S[4 + j][2] = (col[j][2] * sp) + kp.z;
+        }
+      }
+      const double wden = 2.0 * (3 + 0.5);
+      const double w0 = 2 * 0.5 / wden, wi = 1.0 / wden;  // REP:65-66
+      for (int cc = 0; cc < ncc; ++cc) {
+        uint8_t ok = 0;
+        if (present) {
+          const CamD& cm = tb.camd[c0 + cc];
+          double u[7], v[7];
+          for (int s = 0; s < 7; ++s) {
+            const double X = cm.P[0] * S[s][0] + cm.P[1] * S[s][1] + cm.P[2] * S[s][2] + cm.P[3];
+            const double Y = cm.P[4] * S[s][0] + cm.P[5] * S[s][1] + cm.P[6] * S[s][2] + cm.P[7];
+            const double Z = cm.P[8] * S[s][0] + cm.P[9] * S[s][1] + cm.P[10] * S[s][2] + cm.P[11];
+            u[s] = (cm.fx * X + cm.Tx) / Z + cm.cx;  // project3dToPixel (image_geometry)
+            v[s] = (cm.fy * Y + cm.Ty) / Z + cm.cy;
+          }
+          double mu = 0, mv = 0;
+          for (int s = 0; s < 7; ++s) { const double w = s == 0 ? w0 : wi; mu += u[s] * w; mv += v[s] * w; }
+          double cxx = 0, cxy = 0, cyy = 0;
+          for (int s = 0; s < 7; ++s) {
+            const double w = s == 0 ? w0 : wi;
+            const double du = u[s] - mu, dv = v[s] - mv;
+            cxx += du * w * du; cxy += du * w * dv; cyy += dv * w * dv;
+          }
+          if (!(mu < 0 || mu > cm.width || mv < 0 || mv > cm.height)) {  // REP:207-208
+            ses3d_keypoint2d& o = ws.stage[cc * n_p + p].keypoints[k];
+            o.x = static_cast<float>(mu); o.y = static_cast<float>(mv); o.score = kp.score;
+            o.cov[0] = static_cast<float>(cxx); o.cov[1] = static_cast<float>(cxy); o.cov[2] = static_cast<float>(cyy);
+            ok = 1;
+          }
+        }
+        ws.vflag[(cc * n_p + p) * NKP + k] = ok;
+      }
+    });
+
+    // bbox + emitted flag per (camera, person) (REP:150,161-162,218-230)
+    tm.pfor(ncc * n_p, [&](int e) {
+      const int cc = e / n_p;
+      const CamD& cm = tb.camd[c0 + cc];
+      ses3d_person2d& ps = ws.stage[e];
+      float x0 = (float)cm.width, y0 = (float)cm.height, x1 = 0.f, y1 = 0.f;
+      int n_valid = 0;
+      for (int k = 0; k < NKP; ++k)
+        if (ws.vflag[e * NKP + k]) {
+          const float x = ps.keypoints[k].x, y = ps.keypoints[k].y;
+          x0 = x < x0 ? x : x0; y0 = y < y0 ? y : y0; x1 = x > x1 ? x : x1; y1 = y > y1 ? y : y1;
+          ++n_valid;
+        }
+      ps.score = 1.0f;  // REP:175
+      ps.bbox[0] = x0; ps.bbox[1] = y0; ps.bbox[2] = x1; ps.bbox[3] = y1;
+      ws.slot[e] = n_valid > 0 ? 0 : -1;
+    });
+    tm.pfor(ncc, [&](int cc) {  // per-camera push_back order = person order
+      int s = 0;
+      for (int p = 0; p < n_p; ++p)
+        if (ws.slot[cc * n_p + p] >= 0) ws.slot[cc * n_p + p] = s++;
+      n_out[c0 + cc] = s;
+    });
+    tm.pfor(ncc * n_p * words, [&](int e) {
+      const int rec = e / words, w = e % words;
+      const int s = ws.slot[rec];
+      if (s >= 0) {
+        const int cc = rec / n_p;
+        reinterpret_cast<uint32_t*>(out + (size_t)(c0 + cc) * h_max + s)[w] = reinterpret_cast<const uint32_t*>(ws.stage)[e];
+      }
+    });
+  }
+}
+
+}  // namespace ses3d

@@ -1,0 +1,59 @@
+"""ctypes loader of the C-ABI library (libses3d.so, include/ses3d.h). No fallback: if the
+library is missing or no CUDA device is present, the calls fail loudly."""
+import ctypes as C
+from pathlib import Path
+
+from .layouts import AssocDump, Params, SynthConfig
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libses3d.so"
+
+EXPORTS = ("ses3d_default_params", "ses3d_create", "ses3d_destroy", "ses3d_get_tables", "ses3d_triangulate_batch",
+           "ses3d_reproject_batch", "ses3d_process_batch", "ses3d_reserve", "ses3d_launch_count",
+           "ses3d_set_profiling", "ses3d_last_kernel_ms", "ses3d_last_error_string", "ses3d_version",
+           "ses3d_synth_frames", "ses3d_synth_frames_device")
+
+
+class Ses3dError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"ses3d error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Load libses3d.so (build it first with `python -m smartedgesensor3dhumanpose_b200.build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise FileNotFoundError(f"{LIB_PATH} not built: run `python -m smartedgesensor3dhumanpose_b200.build` "
+                                "(the CUDA library is required, there is no CPU path)")
+    L = C.CDLL(str(LIB_PATH))
+    vp, i32, u32, i64 = C.c_void_p, C.c_int32, C.c_uint32, C.c_int64
+    L.ses3d_default_params.argtypes = [C.POINTER(Params)]
+    L.ses3d_default_params.restype = None
+    L.ses3d_create.argtypes = [i32, vp, C.POINTER(Params), i32, C.POINTER(vp)]
+    L.ses3d_destroy.argtypes = [vp]
+    L.ses3d_get_tables.argtypes = [vp, vp, vp]
+    L.ses3d_triangulate_batch.argtypes = [vp, i32, i32, vp, vp, i32, vp, vp, C.POINTER(AssocDump), u32, vp]
+    L.ses3d_reproject_batch.argtypes = [vp, i32, i32, vp, vp, vp, vp, u32, vp]
+    L.ses3d_process_batch.argtypes = [vp, i32, i32, vp, vp, i32, vp, vp, vp, vp, C.POINTER(AssocDump), u32, vp]
+    L.ses3d_reserve.argtypes = [vp, i32, i32, i32]
+    L.ses3d_launch_count.argtypes = [vp]
+    L.ses3d_launch_count.restype = i64
+    L.ses3d_set_profiling.argtypes = [vp, i32]
+    L.ses3d_last_kernel_ms.argtypes = [vp, vp]
+    L.ses3d_last_error_string.restype = C.c_char_p
+    L.ses3d_version.restype = C.c_char_p
+    L.ses3d_synth_frames.argtypes = [i32, vp, C.POINTER(SynthConfig), i64, i32, vp, vp, vp, vp]
+    L.ses3d_synth_frames_device.argtypes = [i32, vp, C.POINTER(SynthConfig), i64, i32, vp, vp, vp, vp]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise Ses3dError(rc, load().ses3d_last_error_string().decode())

@@ -1,0 +1,75 @@
+"""ctypes binding of tests/hostsim/libhostsim.so — the CUDA library's device algorithms run
+serially on the CPU. Test-only; see hostsim.cpp."""
+import ctypes as C
+
+import numpy as np
+
+from smartedgesensor3dhumanpose_b200.layouts import camera_dtype, default_params, person2d_dtype, person_cov_dtype
+
+from . import build as _build
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(str(_build.build()))
+        L.hostsim_create.restype = C.c_void_p
+        L.hostsim_create.argtypes = [C.c_int32, C.c_void_p, C.c_void_p]
+        L.hostsim_destroy.argtypes = [C.c_void_p]
+        L.hostsim_get_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hostsim_triangulate_batch.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hostsim_reproject_batch.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class HostSim:
+    def __init__(self, cameras, params=None):
+        self.cameras = np.ascontiguousarray(cameras, dtype=camera_dtype)
+        self.params = params if params is not None else default_params()
+        self.n_cams = len(self.cameras)
+        self._h = lib().hostsim_create(self.n_cams, _p(self.cameras), C.byref(self.params))
+        if not self._h:
+            raise ValueError("hostsim_create failed")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().hostsim_destroy(self._h)
+            self._h = None
+
+    def tables(self):
+        P = np.zeros((self.n_cams, 12), np.float32)
+        F = np.zeros((self.n_cams * (self.n_cams - 1) // 2, 9), np.float32)
+        lib().hostsim_get_tables(self._h, _p(P), _p(F))
+        return P, F
+
+    def triangulate_batch(self, persons, n_persons, h_max):
+        persons = np.ascontiguousarray(persons, dtype=person2d_dtype)
+        n_frames, n_cams, p_max = persons.shape
+        n_persons = np.ascontiguousarray(n_persons, dtype=np.int32).reshape(n_frames, n_cams)
+        out = np.zeros((n_frames, h_max), person_cov_dtype)
+        n_out = np.zeros(n_frames, np.int32)
+        hyp_of = np.full((n_frames, n_cams, p_max), -1, np.int32)
+        n_hyp = np.zeros(n_frames, np.int32)
+        n_hung = np.zeros(n_frames, np.int32)
+        rc = lib().hostsim_triangulate_batch(self._h, n_frames, p_max, _p(persons), _p(n_persons), h_max, _p(out),
+                                             _p(n_out), _p(hyp_of), _p(n_hyp), _p(n_hung))
+        return dict(status=rc, persons3d=out, n_out=n_out, hyp_of=hyp_of, n_hyp=n_hyp, n_hungarian=n_hung)
+
+    def reproject_batch(self, persons3d, n_persons3d, cam_tile=0):
+        persons3d = np.ascontiguousarray(persons3d, dtype=person_cov_dtype)
+        n_frames, h_max = persons3d.shape
+        n_persons3d = np.ascontiguousarray(n_persons3d, dtype=np.int32)
+        out = np.zeros((n_frames, self.n_cams, h_max), person2d_dtype)
+        n_out = np.zeros((n_frames, self.n_cams), np.int32)
+        lib().hostsim_reproject_batch(self._h, n_frames, h_max, cam_tile, _p(persons3d), _p(n_persons3d), _p(out),
+                                      _p(n_out))
+        return dict(persons2d=out, n_out=n_out)

@@ -1,0 +1,118 @@
+// hostsim.cpp — TEST-ONLY serial instantiation of the device algorithms.
+//
+// The per-frame algorithms of the CUDA library (csrc/*_core.h) are __host__ __device__
+// templates over a "team". This file instantiates them with SerialTeam and the library's own
+// K0 tables so that the GPU-less container can check the *device logic* (not just the oracle)
+// against the oracle. It is built by tests/hostsim/build.py into tests/hostsim/libhostsim.so,
+// is never loaded by the product package, and is not a CPU fallback: libses3d.so has none.
+#include <cstring>
+#include <vector>
+
+#include "assoc_core.h"
+#include "fin_core.h"
+#include "host_setup.h"
+#include "reproj_core.h"
+#include "tri_core.h"
+
+using namespace ses3d;
+
+namespace {
+struct Sim {
+  HostTables host;
+  Tables tb;
+};
+}  // namespace
+
+extern "C" {
+
+void* hostsim_create(int32_t n_cams, const ses3d_camera* cams, const ses3d_params* prm) {
+  Sim* s = new Sim;
+  if (!build_host_tables(n_cams, cams, *prm, &s->host)) { delete s; return nullptr; }
+  s->tb.n_cams = n_cams;
+  s->tb.camf = s->host.camf.data();
+  s->tb.camd = s->host.camd.data();
+  s->tb.F = s->host.F.data();
+  s->tb.f_row = s->host.f_row.data();
+  s->tb.model = s->host.model;
+  s->tb.prm = *prm;
+  return s;
+}
+void hostsim_destroy(void* h) { delete static_cast<Sim*>(h); }
+
+void hostsim_get_tables(void* h, float* P, float* F) {
+  Sim* s = static_cast<Sim*>(h);
+  for (int i = 0; i < s->host.n_cams; ++i) std::memcpy(P + (size_t)i * 12, s->host.camf[i].P, 48);
+  std::memcpy(F, s->host.F.data(), s->host.F.size() * 4);
+}
+
+int hostsim_triangulate_batch(void* h, int32_t n_frames, int32_t p_max, const ses3d_person2d* persons,
+                              const int32_t* n_persons, int32_t h_max, ses3d_person_cov* out, int32_t* n_out,
+                              int32_t* hyp_of, int32_t* n_hyp_out, int32_t* n_hung_out) {
+  Sim* s = static_cast<Sim*>(h);
+  const Tables& tb = s->tb;
+  const int C = tb.n_cams;
+  std::vector<unsigned char> wsa(assoc_ws_bytes(C, p_max, h_max, true) + 64), wsf(fin_ws_bytes(h_max) + 64);
+  const bool f64 = tb.prm.precision == SES3D_PRECISION_FP64;
+  std::vector<unsigned char> wst((f64 ? tri_ws_bytes<double>(C) : tri_ws_bytes<float>(C)) + 64);
+  std::vector<int8_t> hyp_det((size_t)h_max * C);
+  std::vector<ses3d_person_cov> tmp(h_max);
+  std::vector<int32_t> keep(h_max);
+  int32_t overflow = 0;
+  SerialTeam tm;
+  for (int f = 0; f < n_frames; ++f) {
+    const ses3d_person2d* pf = persons + (size_t)f * C * p_max;
+    Arena a1(wsa.data());
+    AssocWs aws;
+    assoc_ws_layout(a1, C, p_max, h_max, true, &aws);
+    int32_t n_hyp = 0, n_hung = 0;
+    associate_frame(tm, tb, p_max, h_max, pf, n_persons + (size_t)f * C, aws, hyp_det.data(), &n_hyp, &n_hung, &overflow);
+    if (n_hyp_out) n_hyp_out[f] = n_hyp;
+    if (n_hung_out) n_hung_out[f] = n_hung;
+    if (hyp_of) {
+      int32_t* ho = hyp_of + (size_t)f * C * p_max;
+      for (int i = 0; i < C * p_max; ++i) ho[i] = -1;
+      for (int hh = 0; hh < n_hyp; ++hh)
+        for (int c = 0; c < C; ++c)
+          if (hyp_det[hh * C + c] >= 0) ho[c * p_max + hyp_det[hh * C + c]] = hh;
+    }
+    for (int hh = 0; hh < h_max; ++hh) {
+      keep[hh] = 0;
+      if (hh >= n_hyp) continue;
+      Arena a2(wst.data());
+      if (f64) {
+        TriWs<double> tws;
+        tri_ws_layout<double>(a2, C, &tws);
+        triangulate_hypothesis<double>(tm, tb, p_max, pf, hyp_det.data() + (size_t)hh * C, tws, &tmp[hh], &keep[hh]);
+      } else {
+        TriWs<float> tws;
+        tri_ws_layout<float>(a2, C, &tws);
+        triangulate_hypothesis<float>(tm, tb, p_max, pf, hyp_det.data() + (size_t)hh * C, tws, &tmp[hh], &keep[hh]);
+      }
+    }
+    Arena a3(wsf.data());
+    FinWs fws;
+    fin_ws_layout(a3, h_max, &fws);
+    finalize_frame(tm, tb, h_max, n_hyp, tmp.data(), keep.data(), fws, out + (size_t)f * h_max, n_out + f);
+  }
+  return overflow ? SES3D_E_CAPACITY : SES3D_OK;
+}
+
+int hostsim_reproject_batch(void* h, int32_t n_frames, int32_t h_max, int32_t cam_tile, const ses3d_person_cov* p3d,
+                            const int32_t* n_p3d, ses3d_person2d* out, int32_t* n_out) {
+  Sim* s = static_cast<Sim*>(h);
+  const Tables& tb = s->tb;
+  const int C = tb.n_cams;
+  if (cam_tile <= 0) cam_tile = C;
+  std::vector<unsigned char> wsr(reproj_ws_bytes(cam_tile, h_max) + 64);
+  SerialTeam tm;
+  for (int f = 0; f < n_frames; ++f) {
+    Arena a(wsr.data());
+    ReprojWs ws;
+    reproj_ws_layout(a, cam_tile, h_max, &ws);
+    reproject_frame(tm, tb, h_max, cam_tile, p3d + (size_t)f * h_max, n_p3d[f], ws, out + (size_t)f * C * h_max,
+                    n_out + (size_t)f * C);
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the multi-view geometry hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--frames B] [--workload NAME]
+
+A step = one pass of association + triangulation (+UT covariance) + plausibility/merge + reprojection
+over one batch of B synthetic frames per GPU (the reference's 16-camera hall rig,
+6 people). `value` = joints triangulated / s over the whole job with inputs resident in HBM; `e2e` = the
+same metric through the public host-buffer call (pinned host memory, H2D + D2H inside the timed region).
+`--impl reference` times the CPU oracle (reference restatement + the reference's verbatim Hungarian.cpp)
+on the host cores instead. One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "joints_triangulated_per_sec"
+UNIT = "joints/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=16384, help="frames per GPU per step")
+    ap.add_argument("--workload", default="cfg2_hall16x6")
+    ap.add_argument("--ref-frames", type=int, default=0, help="frames per step of the CPU reference arm (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary measurements (dense rig, latency)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------ flop / byte model
+def algorithmic_work(fr, res, thr=0.30):
+    """Per-frame algorithmic flops and bytes of a batch, from the survey's cost model applied to the
+    batch's actual view counts: epipolar pair 50; weighted DLT 88n+1003; unweighted 80n+1003; reprojection
+    error 32n; per joint T_w + R + (4n+1) T_u; reprojection 250 per (joint, camera). Bytes: Person2D 428 B in,
+    PersonCov 1684 B out, reprojected Person2D 428 B out (wire layouts, each byte once)."""
+    persons, n_persons, hyp_of = fr["persons"], fr["n_persons"], res["hyp_of"]
+    F, C, PM = hyp_of.shape
+    score = persons["keypoints"]["score"]                      # [F][C][PM][17]
+    slot = np.arange(PM)[None, None, :] < n_persons[:, :, None]
+    valid_kp = (score >= thr) & slot[..., None]
+    assigned = hyp_of >= 0
+    H = int(hyp_of.max()) + 1 if assigned.any() else 0
+    # views per (frame, hypothesis, joint)
+    n_views = np.zeros((F, max(H, 1), 17), np.int32)
+    n_obs = np.zeros((F, max(H, 1)), np.int32)
+    f_idx = np.broadcast_to(np.arange(F)[:, None, None], hyp_of.shape)
+    np.add.at(n_obs, (f_idx[assigned], hyp_of[assigned]), 1)
+    np.add.at(n_views, (f_idx[assigned], hyp_of[assigned]), valid_kp[assigned].astype(np.int32))
+    n = n_views[(n_obs >= 2)[..., None] & (n_views >= 2)].astype(np.float64)
+    tri_flops = ((88 * n + 1003) + 32 * n + (4 * n + 1) * (80 * n + 1003)).sum()
+    # association: every (hypothesis observation, detection) pair of later cameras, joints valid in both;
+    # approximated by the pairs of valid detections in different cameras (upper bound of what calcCost visits
+    # is data dependent; this counts each unordered cross-camera detection pair once, as the cost matrix does)
+    strict = (score > thr) & slot[..., None]
+    det_valid = (valid_kp.sum(-1) > 8)
+    v = (strict & det_valid[..., None]).astype(np.float64)     # [F][C][PM][17]
+    per_cam = v.sum(2)                                          # [F][C][17] valid joint count per camera
+    tot = per_cam.sum(1)
+    pairs = ((tot ** 2 - (per_cam ** 2).sum(1)) / 2).sum()      # sum over joints of cross-camera pairs
+    assoc_flops = 50.0 * pairs
+    joints_out = int((res["persons3d"]["keypoints"]["score"] > 0).sum())
+    rep_flops = 250.0 * joints_out * C
+    bytes_in = float(n_persons.sum()) * 428
+    bytes_out3d = float(res["n_out"].sum()) * 1684
+    bytes_out2d = float(res.get("n_out2d_total", 0)) * 428
+    return dict(tri_flops_per_frame=tri_flops / F, assoc_flops_per_frame=assoc_flops / F,
+                reproj_flops_per_frame=rep_flops / F, joints_per_frame=joints_out / F,
+                bytes_per_frame=(bytes_in + bytes_out3d + bytes_out2d) / F,
+                mean_views_per_joint=float(n.mean()) if n.size else 0.0,
+                mean_detections_per_camera=float(n_persons.mean()))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm_gbs=float(d["hbm_gbs"]), sm_max_mhz=float(d.get("sm_max_mhz", 1965.0)),
+                    sm_sustained_mhz=float(d.get("clocks_under_load", {}).get("sm_mhz_median", 1327.0)), src="measured")
+    return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, sm_sustained_mhz=1327.0, src="fallback")
+
+
+def cpu_reference_run(fr, n_frames, n_threads, steps=1, warmup=0):
+    """Time the CPU oracle (triangulation + reprojection) on n_frames frames; returns (joints/s, frames/s, ms/step)."""
+    from oracle.binding import REF_HUNGARIAN_PATH, Oracle
+    orc = Oracle(fr["cameras"], ref_hungarian=REF_HUNGARIAN_PATH.exists())
+    persons, n_persons = fr["persons"][:n_frames], fr["n_persons"][:n_frames]
+    times, joints = [], 0
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        r = orc.triangulate_batch(persons, n_persons, fr["h_max"], n_threads=n_threads)
+        orc.reproject_batch(r["persons3d"], r["n_out"], n_threads=n_threads)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+            joints = r["n_joints"]
+    t = float(np.mean(times))
+    return joints / t, n_frames / t, 1e3 * t, ("reference" if orc.ref_hungarian else "port")
+
+
+def main():
+    a = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from tests import helpers
+    rig, people, dropout, seed = helpers.CONFIGS[a.workload]
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        cores = os.cpu_count() or 1
+        pilot = helpers.make_workload(a.workload, 256)
+        _, fps, _, _ = cpu_reference_run(pilot, 256, cores)
+        n = a.ref_frames or int(min(32768, max(256, fps * 8.0)))  # ~8 s of CPU work per step
+        fr = helpers.make_workload(a.workload, n)
+        jps, fps, ms, kind = cpu_reference_run(fr, n, cores, steps=a.steps, warmup=min(a.warmup, 1))
+        line = {"metric": METRIC, "value": jps, "unit": UNIT, "impl": "reference", "n_gpus": a.gpus, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "frames_per_sec": fps,
+                "config": {"workload": a.workload, "rig": rig, "cameras": int(len(fr["cameras"])), "people": people,
+                           "dropout": dropout, "frames_per_step": n, "stages": "associate+triangulate+finalize+reproject"},
+                "cpu_baseline": {"value": jps, "unit": UNIT, "cores": cores, "kind": kind,
+                                 "sample": f"{n} frames/step of {a.workload}, frame-parallel over {cores} threads"},
+                "e2e": {"value": jps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ our arm (GPU)
+    import torch
+    import torch.distributed as dist
+    from smartedgesensor3dhumanpose_b200 import api
+    from smartedgesensor3dhumanpose_b200.layouts import person2d_dtype, person_cov_dtype
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    B = a.frames
+    fr = helpers.make_workload(a.workload, B, first_frame=rank * B)
+    cams, h_max = fr["cameras"], fr["h_max"]
+    C, PM = fr["persons"].shape[1], fr["persons"].shape[2]
+    pipe = api.GeometryPipeline(cams, device=local_rank)
+    pipe.reserve(B, PM, h_max)
+
+    def pinned(arr):
+        t = torch.from_numpy(arr.view(np.uint8).reshape(-1)).pin_memory()
+        return t, t.numpy().view(arr.dtype).reshape(arr.shape)
+
+    # host buffers (pinned) and device-resident copies
+    tp, persons_h = pinned(fr["persons"])
+    tn, n_persons_h = pinned(fr["n_persons"])
+    t3, out3d_h = pinned(np.zeros((B, h_max), person_cov_dtype))
+    tn3, n3d_h = pinned(np.zeros(B, np.int32))
+    t2, out2d_h = pinned(np.zeros((B, C, h_max), person2d_dtype))
+    tn2, n2d_h = pinned(np.zeros((B, C), np.int32))
+    d_persons, d_np = tp.to(dev), tn.to(dev)
+    d_out3d = torch.zeros(t3.numel(), dtype=torch.uint8, device=dev)
+    d_n3d = torch.zeros(B, dtype=torch.int32, device=dev)
+    d_out2d = torch.zeros(t2.numel(), dtype=torch.uint8, device=dev)
+    d_n2d = torch.zeros(B * C, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        pipe.process_device(B, PM, h_max, d_persons.data_ptr(), d_np.data_ptr(), d_out3d.data_ptr(), d_n3d.data_ptr(),
+                            d_out2d.data_ptr(), d_n2d.data_ptr(), stream=stream.cuda_stream)
+
+    bufs = dict(persons3d=out3d_h, n_out3d=n3d_h, persons2d=out2d_h, n_out2d=n2d_h)
+
+    def step_host():
+        pipe.process_batch(persons_h, n_persons_h, h_max, bufs=bufs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        evs[0].record(stream)
+        for i in range(steps):
+            fn()
+            evs[i + 1].record(stream)
+        barrier()
+        per = np.array([evs[i].elapsed_time(evs[i + 1]) for i in range(steps)])
+        total = evs[0].elapsed_time(evs[-1])
+        if world > 1:
+            t = torch.tensor([total], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total = float(t.item())
+        return total, per
+
+    # joints per step (count once from a real run; identical every step since the batch is fixed)
+    step_device()
+    torch.cuda.synchronize()
+    n3d = d_n3d.cpu().numpy()
+    out3d = d_out3d.cpu().numpy().view(person_cov_dtype).reshape(B, h_max)
+    live = np.arange(h_max)[None, :] < n3d[:, None]
+    joints_step = int(((out3d["keypoints"]["score"] > 0) & live[..., None]).sum())
+    jt = torch.tensor([joints_step], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(jt)
+    joints_all = int(jt.item())
+
+    launches0 = pipe.launch_count
+    with ClockSampler(local_rank) as clk:
+        total_ms, per_ms = timed(step_device, a.steps, a.warmup)
+    launches = (pipe.launch_count - launches0) * a.steps // (a.steps + a.warmup)
+    value = joints_all * a.steps / (total_ms * 1e-3)
+    frames_ps = B * world * a.steps / (total_ms * 1e-3)
+
+    e2e_ms, e2e_per = timed(step_host, a.steps, a.warmup)
+    e2e_value = joints_all * a.steps / (e2e_ms * 1e-3)
+    h2d = int(fr["persons"].nbytes + fr["n_persons"].nbytes)
+    d2h = int(out3d_h.nbytes + n3d_h.nbytes + out2d_h.nbytes + n2d_h.nbytes)
+
+    # per-kernel device time (CUDA events on the launching stream, inside the library), same steps
+    pipe.set_profiling(True)
+    ksum = {}
+    for _ in range(a.steps):
+        step_device()
+        for k, v in pipe.last_kernel_ms().items():
+            ksum[k] = ksum.get(k, 0.0) + v
+    pipe.set_profiling(False)
+    kernel_ms = {k: v / a.steps for k, v in ksum.items()}
+
+    # final result gather (compact xyz+score per joint), timed separately - the only collective
+    gather_ms = None
+    if world > 1:
+        kp = d_out3d.view(torch.float64).view(B, h_max, 221)[:, :, 1:211].reshape(B, h_max, 21, 10)
+        compact = torch.cat([kp[..., 0:3].float(),
+                             kp[..., 3].contiguous().view(torch.float32).view(B, h_max, 21, 2)[..., 0:1]], dim=-1).contiguous()
+        outl = [torch.empty_like(compact) for _ in range(world)] if rank == 0 else None
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        dist.gather(compact, outl, dst=0)
+        t1.record()
+        barrier()
+        gather_ms = t0.elapsed_time(t1)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ------------------------------------------------------------------ roofline of the dominant kernel
+    peaks = load_peaks()
+    sample = min(B, 2048)
+    sub = {k: (v[:sample] if isinstance(v, np.ndarray) and v.shape[:1] == (B,) else v) for k, v in fr.items()}
+    res = pipe.triangulate_batch(sub["persons"], sub["n_persons"], h_max)
+    rp = pipe.reproject_batch(res["persons3d"], res["n_out"])
+    res["n_out2d_total"] = int(rp["n_out"].sum())
+    work = algorithmic_work(sub, res)
+    fp32_peak = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12          # TFLOP/s at max clock
+    fp32_sustained = 148 * 128 * 2 * peaks["sm_sustained_mhz"] * 1e6 / 1e12
+    dom = max(kernel_ms, key=kernel_ms.get)
+    dom_flops = {"triangulate": work["tri_flops_per_frame"], "associate": work["assoc_flops_per_frame"],
+                 "reproject": work["reproj_flops_per_frame"], "finalize": 0.0}[dom] * B
+    n_launch = max(1, -(-B // 16384))
+    achieved = dom_flops / (kernel_ms[dom] * 1e-3) / 1e12
+    step_ms = total_ms / a.steps
+    roofline = {"bound": "fp32", "kernel": f"k_{dom}", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": achieved / fp32_peak, "peak_source": f"148 SM x 128 lanes x 2 x sm_max_mhz ({peaks['src']} MEASURED_PEAKS.json)",
+                "frac_of_sustained_clock_peak": achieved / fp32_sustained,
+                "launches_per_step": n_launch, "kernel_ms_per_step": kernel_ms, "kernel_share_of_step": kernel_ms[dom] / sum(kernel_ms.values()),
+                "algorithmic_flops_per_frame": {"associate": work["assoc_flops_per_frame"], "triangulate": work["tri_flops_per_frame"],
+                                                "reproject": work["reproj_flops_per_frame"]},
+                "whole_step_tflops": (work["tri_flops_per_frame"] + work["assoc_flops_per_frame"] + work["reproj_flops_per_frame"]) * B / (step_ms * 1e-3) / 1e12,
+                "hbm": {"achieved": work["bytes_per_frame"] * B / (step_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": work["bytes_per_frame"] * B / (step_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                        "algorithmic_bytes_per_frame": work["bytes_per_frame"]},
+                "traffic": None}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "frames_per_sec": frames_ps,
+            "p50_frame_latency_us": float(np.median(per_ms)) * 1e3 / B,
+            "config": {"workload": a.workload, "rig": rig, "cameras": C, "people": people, "dropout": dropout,
+                       "p_max": PM, "h_max": h_max, "frames_per_step_per_gpu": B,
+                       "stages": "associate+triangulate(+UT covariance)+finalize+reproject",
+                       "joints_per_frame": work["joints_per_frame"], "mean_views_per_joint": work["mean_views_per_joint"],
+                       "mean_detections_per_camera": work["mean_detections_per_camera"],
+                       "l2_policy": f"inputs larger than L2 ({h2d / 2**20:.0f} MiB in, {d2h / 2**20:.0f} MiB out per step)",
+                       "sharding": "frames across ranks, no data-path collective; final gather timed separately"},
+            "roofline": roofline, "clocks": clk.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / a.steps, "frames_per_sec": B * world * a.steps / (e2e_ms * 1e-3)},
+            "gpu_launches": int(launches), "gather_ms": gather_ms}
+
+    if world == 1 and not a.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        _, fps, _, _ = cpu_reference_run(fr, 256, cores)
+        n = int(min(B, max(256, fps * 12.0)))
+        jps, fps, ms, kind = cpu_reference_run(fr, n, cores)
+        _, fps1, _, _ = cpu_reference_run(fr, min(n, max(64, int(fps / cores * 3))), 1)
+        line["cpu_baseline"] = {"value": jps, "unit": UNIT, "cores": cores, "kind": kind, "frames_per_sec": fps,
+                                "single_thread_frames_per_sec": fps1,
+                                "sample": f"first {n} frames of the step's batch, frame-parallel over {cores} threads ({ms:.0f} ms)"}
+    if world == 1 and not a.no_extra:
+        # single-frame call latency (the ROS-shim use case), host buffers, wall clock
+        lat = []
+        for f in range(200):
+            t0 = time.perf_counter()
+            pipe.process_batch(persons_h[f:f + 1], n_persons_h[f:f + 1], h_max)
+            lat.append(time.perf_counter() - t0)
+        line["single_frame_call_p50_us"] = float(np.median(lat[20:])) * 1e6
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

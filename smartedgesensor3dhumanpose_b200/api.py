@@ -98,10 +98,10 @@ class GeometryPipeline:
         n_frames, n_cams, p_max = persons.shape
         n_persons = np.ascontiguousarray(n_persons, dtype=np.int32).reshape(n_frames, n_cams)
         b = bufs or {}
-        out3d = b.get("persons3d", np.zeros((n_frames, h_max), person_cov_dtype) if want_3d else None)
-        n3d = b.get("n_out3d", np.zeros(n_frames, np.int32))
-        out2d = b.get("persons2d", np.zeros((n_frames, n_cams, h_max), person2d_dtype))
-        n2d = b.get("n_out2d", np.zeros((n_frames, n_cams), np.int32))
+        out3d = b["persons3d"] if "persons3d" in b else (np.zeros((n_frames, h_max), person_cov_dtype) if want_3d else None)
+        n3d = b["n_out3d"] if "n_out3d" in b else np.zeros(n_frames, np.int32)
+        out2d = b["persons2d"] if "persons2d" in b else np.zeros((n_frames, n_cams, h_max), person2d_dtype)
+        n2d = b["n_out2d"] if "n_out2d" in b else np.zeros((n_frames, n_cams), np.int32)
         _lib.check(self._L.ses3d_process_batch(self._h, n_frames, p_max, _p(persons), _p(n_persons), h_max, _p(out3d),
                                                _p(n3d), _p(out2d), _p(n2d), None, HOST_BUFFERS, None))
         return dict(persons3d=out3d, n_out3d=n3d, persons2d=out2d, n_out2d=n2d)

@@ -48,6 +48,12 @@ def hall16():
     return make_cameras(np.array([c["T_cam_base"] for c in d["cameras"]]))
 
 
+def ring16():
+    """Dense variant of config 2: 16-camera ring in which every camera sees every person (n = 16 views per
+    joint, the case the SURVEY 8(d) flop model J(16) describes)."""
+    return ring(16, 7.0, 2.6, target=(0.0, 0.0, 1.0))
+
+
 def crowd64():
     """Config 4: two rings of 32 cameras (radii 8 m / 11 m, heights 2.5 m / 4 m)."""
     a = ring(32, 8.0, 2.5)
@@ -57,5 +63,5 @@ def crowd64():
 
 # floor areas people are placed in (x0, y0, x1, y1), chosen inside each rig's field of view
 AREAS = {"ring4": (-1.5, -1.5, 1.5, 1.5), "ring8": (-2.0, -2.0, 2.0, 2.0), "hall16": (-9.0, -4.5, 2.0, 4.5),
-         "crowd64": (-5.0, -5.0, 5.0, 5.0)}
-RIGS = {"ring4": ring4, "ring8": ring8, "hall16": hall16, "crowd64": crowd64}
+         "ring16": (-1.5, -1.5, 1.5, 1.5), "crowd64": (-5.0, -5.0, 5.0, 5.0)}
+RIGS = {"ring4": ring4, "ring8": ring8, "hall16": hall16, "ring16": ring16, "crowd64": crowd64}

@@ -1,0 +1,73 @@
+"""Shared test helpers: workloads and result comparison."""
+import numpy as np
+
+from smartedgesensor3dhumanpose_b200 import rigs, synth
+
+# name -> (rig, people, dropout, seed)  == BASELINE.json configs 1..5 at test sizes
+CONFIGS = {
+    "cfg1_ring4x1": ("ring4", 1, 0.0, 1),
+    "cfg2_hall16x6": ("hall16", 6, 0.0, 2),
+    "cfg3_hall16x6_dropout": ("hall16", 6, 0.30, 3),
+    "cfg4_crowd64x20": ("crowd64", 20, 0.10, 4),
+    "cfg5_ring8x4": ("ring8", 4, 0.05, 5),
+    "dense_ring16x6": ("ring16", 6, 0.0, 6),
+}
+
+
+def make_workload(name, n_frames, first_frame=0, **over):
+    rig, people, dropout, seed = CONFIGS[name]
+    cams = rigs.RIGS[rig]()
+    cfg = synth.synth_config(seed=over.get("seed", seed), n_people=people, dropout=over.get("dropout", dropout),
+                             noise_px=over.get("noise_px", 2.0), area=rigs.AREAS[rig])
+    fr = synth.synth_frames(cams, cfg, n_frames, first_frame)
+    fr["cameras"] = cams
+    fr["h_max"] = over.get("h_max", max(8, 2 * people + 4))
+    return fr
+
+
+def inject_outliers(fr, frac=0.05, seed=0, shift_px=150.0):
+    """Move a fraction of the confident keypoints far away (gross outliers -> rejection branches S3D:748-838)."""
+    rng = np.random.default_rng(seed)
+    kp = fr["persons"]["keypoints"]
+    m = (kp["score"] >= 0.5) & (rng.random(kp["score"].shape) < frac)
+    kp["x"][m] += shift_px * rng.choice([-1.0, 1.0], size=m.sum()).astype(np.float32)
+    kp["y"][m] += shift_px * rng.choice([-1.0, 1.0], size=m.sum()).astype(np.float32)
+    return int(m.sum())
+
+
+def compare_persons3d(ref, got, pos_tol, cov_rtol=1e-2, score_tol=2e-5):
+    """ref/got: dicts with persons3d [F][H], n_out [F]. Returns a stats dict; raises AssertionError on mismatch."""
+    assert np.array_equal(ref["n_out"], got["n_out"]), "number of output persons differs"
+    F, H = ref["persons3d"].shape
+    live = np.arange(H)[None, :] < ref["n_out"][:, None]
+    a = ref["persons3d"]["keypoints"][live]
+    b = got["persons3d"]["keypoints"][live]
+    pa, pb = a["score"] > 0, b["score"] > 0
+    assert np.array_equal(pa, pb), "set of triangulated joints differs"
+    d = np.sqrt((a["x"] - b["x"]) ** 2 + (a["y"] - b["y"]) ** 2 + (a["z"] - b["z"]) ** 2)[pa]
+    ds = np.abs(a["score"] - b["score"])[pa]
+    ca, cb = a["cov"][pa], b["cov"][pa]
+    scale = np.abs(ca).max(axis=-1, keepdims=True) + 1e-30
+    dc = (np.abs(ca - cb) / scale).max(axis=-1) if len(ca) else np.zeros(0)
+    stats = dict(n_joints=int(pa.sum()), max_pos=float(d.max()) if d.size else 0.0,
+                 max_score=float(ds.max()) if ds.size else 0.0, max_cov_rel=float(dc.max()) if dc.size else 0.0)
+    assert stats["max_pos"] <= pos_tol, f"joint position differs by {stats['max_pos']:.3e} m (tol {pos_tol})"
+    assert stats["max_score"] <= score_tol, f"score differs by {stats['max_score']:.3e}"
+    assert stats["max_cov_rel"] <= cov_rtol, f"covariance differs by {stats['max_cov_rel']:.3e} (relative)"
+    return stats
+
+
+def compare_persons2d(ref, got, px_tol=0.0):
+    """Reprojection outputs: counts exact; keypoints exact when px_tol == 0 else within px_tol pixels."""
+    assert np.array_equal(ref["n_out"], got["n_out"]), "per-camera person counts differ"
+    F, C, H = ref["persons2d"].shape
+    live = np.arange(H)[None, None, :] < ref["n_out"][:, :, None]
+    a, b = ref["persons2d"][live], got["persons2d"][live]
+    if px_tol == 0.0:
+        assert a.tobytes() == b.tobytes(), "reprojected Person2D records differ bitwise"
+        return dict(n_persons=int(live.sum()), max_px=0.0)
+    ka, kb = a["keypoints"], b["keypoints"]
+    assert np.array_equal(ka["score"] > 0, kb["score"] > 0)
+    d = max(np.abs(ka["x"] - kb["x"]).max(initial=0), np.abs(ka["y"] - kb["y"]).max(initial=0))
+    assert d <= px_tol, f"reprojected keypoints differ by {d} px"
+    return dict(n_persons=int(live.sum()), max_px=float(d))

@@ -153,7 +153,7 @@ int triangulate_on_device(ses3d_handle_s* h, Scratch& sc, cudaStream_t st, int n
     }
     {
       ProfScope ps(h, 1, st);
-      CU(ses3d::launch_triangulate(h->tb, d, pin, sc.hyp_det.as<int8_t>(), sc.tmp.as<ses3d_person_cov>(),
+      CU(ses3d::launch_triangulate(h->tb, d, pin, sc.hyp_det.as<int8_t>(), n_hyp, sc.tmp.as<ses3d_person_cov>(),
                                    sc.keep.as<int32_t>(), st));
     }
     {

@@ -16,9 +16,9 @@ cudaError_t launch_associate(const Tables& tb, LaunchDims d, const ses3d_person2
                              int32_t* hyp_of_dump, cudaStream_t st);
 size_t associate_smem_bytes(int n_cams, int p_max, int h_cap, bool* needs_scratch);
 
-// K3: one CTA per (frame, hypothesis)
+// K3: one warp per (frame, hypothesis)
 cudaError_t launch_triangulate(const Tables& tb, LaunchDims d, const ses3d_person2d* persons, const int8_t* hyp_det,
-                               ses3d_person_cov* tmp, int32_t* keep, cudaStream_t st);
+                               const int32_t* n_hyp, ses3d_person_cov* tmp, int32_t* keep, cudaStream_t st);
 
 // K4: one CTA per frame
 cudaError_t launch_finalize(const Tables& tb, LaunchDims d, const int32_t* n_hyp, ses3d_person_cov* tmp,

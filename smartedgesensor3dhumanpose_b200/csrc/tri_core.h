@@ -9,11 +9,13 @@
 // Levenberg-Marquardt refinement (not in the reference) sits behind
 // params.lm_refine.
 //
-// B200 mapping: one CTA per (frame, hypothesis). The 17 joints x (4n+1) sigma-point solves
-// of the covariance - ~98 % of the solves - are flattened into one index space and spread
-// over all threads; each thread owns a complete 4x4 eigen-solve in registers. Each sigma
-// point differs from the base system in one view only, so its normal matrix is the base
-// Gram plus a rank-<=4 update (two rows removed, two added) instead of a rebuild.
+// B200 mapping: one warp per (frame, hypothesis), several warps per CTA, no CTA-wide barrier.
+// ~95 % of the solves are the 4n+1 sigma-point triangulations of the covariance; all joints'
+// sigma points are flattened into one index space so the 32 lanes stay full, and each lane
+// owns a complete 4x4 eigen-solve in registers. A sigma point differs from the base system in
+// one view only, so its normal matrix is written in the eigenbasis of the base system
+// (diag(lambda) + a rank-<=4 update): Jacobi then starts almost diagonal (warm start) and
+// converges in 1-3 sweeps instead of 5-7.
 #pragma once
 #include "common.h"
 #include "geom.h"
@@ -22,15 +24,17 @@
 namespace ses3d {
 
 template <class T>
-struct ViewKp {  // one normalised keypoint of one observation
-  T x, y, conf, cxx, cxy, cyy;
+struct ViewKp {  // one normalised keypoint of one observation (conf = -1: below threshold)
+  T x, y, conf;
 };
+
+constexpr int Y_CHUNK = 256;  // sigma points solved per pass (bounds the shared-memory staging)
 
 template <class T>
 struct TriWs {
   uint8_t* obs_cam;   // [C]
   uint8_t* obs_det;   // [C]
-  int* scal;          // [4]: n_obs, keep, total_samples
+  int* scal;          // [4]: n_obs, keep
   ViewKp<T>* vw;      // [C][17]
   uint8_t* vlist;     // [17][C] observation indices used by joint k
   int* jn;            // [17] number of views (0 = joint not triangulated)
@@ -38,26 +42,30 @@ struct TriWs {
   T* jX;              // [17][3]
   double* jerr;       // [17]
   float* jscore;      // [17]
-  double* G0;         // [17][10] unweighted base Gram of the final view set
-  int* soff;          // [18] sample offsets
-  T* Y;               // [17*(4C+1)][3] transformed sigma points   (aliases the LOO buffers)
-  T* looX;            // [17][C][3]
-  double* looErr;     // [17][C]
+  T* V0;              // [17][16] eigenbasis of the unweighted base system
+  T* lam0;            // [17][4]  its eigenvalues
+  T* cov;             // [17][6]  running covariance sums
+  int* soff;          // [18] sample offsets (sample 0 of each joint is the base solve, already known)
+  T* Y;               // [Y_CHUNK][3] transformed sigma points of the current pass  (aliases the LOO scratch)
+  T* looX;            // [loo_cap][3]
+  double* looErr;     // [loo_cap]
+  int loo_cap;
   ses3d_keypoint_cov* kp;  // [21] the output skeleton
 };
 
 template <class T, class A>
 SES_HD void tri_ws_layout(A& ar, int C, TriWs<T>* ws) {
   double* jerr = ar.template take<double>(NKP);
-  double* G0 = ar.template take<double>(NKP * 10);
   ses3d_keypoint_cov* kp = ar.template take<ses3d_keypoint_cov>(NFUS);
-  // union { Y ; looX + looErr }
-  const size_t y_bytes = (size_t)NKP * (4 * C + 1) * 3 * sizeof(T);
-  const size_t loo_bytes = (size_t)NKP * C * (8 + 3 * sizeof(T));
-  const size_t u_bytes = (y_bytes > loo_bytes ? y_bytes : loo_bytes);
+  // union { Y[Y_CHUNK][3] ; looErr[loo_cap] + looX[loo_cap][3] }
+  const size_t u_bytes = (size_t)Y_CHUNK * 3 * sizeof(T);
+  const int loo_cap = (int)(u_bytes / (8 + 3 * sizeof(T)));
   double* u = ar.template take<double>((u_bytes + 7) / 8);
   ViewKp<T>* vw = ar.template take<ViewKp<T>>((size_t)C * NKP);
   T* jX = ar.template take<T>(NKP * 3);
+  T* V0 = ar.template take<T>(NKP * 16);
+  T* lam0 = ar.template take<T>(NKP * 4);
+  T* cov = ar.template take<T>(NKP * 6);
   float* jscore = ar.template take<float>(NKP);
   int* jn = ar.template take<int>(NKP);
   int* jflag = ar.template take<int>(NKP);
@@ -67,10 +75,10 @@ SES_HD void tri_ws_layout(A& ar, int C, TriWs<T>* ws) {
   uint8_t* obs_cam = ar.template take<uint8_t>(C);
   uint8_t* obs_det = ar.template take<uint8_t>(C);
   if (ws) {
-    ws->jerr = jerr; ws->G0 = G0; ws->kp = kp; ws->Y = reinterpret_cast<T*>(u);
-    ws->looErr = u; ws->looX = reinterpret_cast<T*>(u + (size_t)NKP * C);
-    ws->vw = vw; ws->jX = jX; ws->jscore = jscore; ws->jn = jn; ws->jflag = jflag; ws->soff = soff;
-    ws->scal = scal; ws->vlist = vlist; ws->obs_cam = obs_cam; ws->obs_det = obs_det;
+    ws->jerr = jerr; ws->kp = kp; ws->Y = reinterpret_cast<T*>(u);
+    ws->looErr = u; ws->looX = reinterpret_cast<T*>(u + loo_cap); ws->loo_cap = loo_cap;
+    ws->vw = vw; ws->jX = jX; ws->V0 = V0; ws->lam0 = lam0; ws->cov = cov; ws->jscore = jscore; ws->jn = jn;
+    ws->jflag = jflag; ws->soff = soff; ws->scal = scal; ws->vlist = vlist; ws->obs_cam = obs_cam; ws->obs_det = obs_det;
   }
 }
 
@@ -92,34 +100,60 @@ template <> struct CamSel<double> {
 // normalize_keypoints (S3D:312-333) of one raw keypoint, in T. conf = -1 when below threshold.
 SES_HD void normalize_kp(const Tables& tb, int cam, const ses3d_keypoint2d& kp, ViewKp<float>& o) {
   const CamF& cm = tb.camf[cam];
-  o.x = 0.f; o.y = 0.f; o.conf = -1.f; o.cxx = 0.f; o.cxy = 0.f; o.cyy = 0.f;
+  o.x = 0.f; o.y = 0.f; o.conf = -1.f;
   if (kp.score >= tb.prm.triangulation_threshold) {
     o.x = (kp.x - cm.cx) / cm.fx;
     o.y = (kp.y - cm.cy) / cm.fy;
     o.conf = kp.score;
-    o.cxx = kp.cov[0] / (cm.fx * cm.fx);
-    o.cxy = kp.cov[1] / (cm.fx * cm.fy);
-    o.cyy = kp.cov[2] / (cm.fy * cm.fy);
   }
 }
 SES_HD void normalize_kp(const Tables& tb, int cam, const ses3d_keypoint2d& kp, ViewKp<double>& o) {
   const CamD& cm = tb.camd[cam];
-  o.x = 0.; o.y = 0.; o.conf = -1.; o.cxx = 0.; o.cxy = 0.; o.cyy = 0.;
+  o.x = 0.; o.y = 0.; o.conf = -1.;
   if (kp.score >= tb.prm.triangulation_threshold) {
     o.x = ((double)kp.x - cm.cx) / cm.fx;
     o.y = ((double)kp.y - cm.cy) / cm.fy;
     o.conf = (double)kp.score;
-    o.cxx = (double)kp.cov[0] / (cm.fx * cm.fx);
-    o.cxy = (double)kp.cov[1] / (cm.fx * cm.fy);
-    o.cyy = (double)kp.cov[2] / (cm.fy * cm.fy);
   }
+}
+// normalised 2x2 covariance (S3D:324-327) and its Cholesky factor (mod_samples S3D:473-475)
+SES_HD void cholesky_cov(const Tables& tb, int cam, const ses3d_keypoint2d& kp, float& l11, float& l21, float& l22) {
+  const CamF& cm = tb.camf[cam];
+  const float cxx = kp.cov[0] / (cm.fx * cm.fx), cxy = kp.cov[1] / (cm.fx * cm.fy), cyy = kp.cov[2] / (cm.fy * cm.fy);
+  l11 = ses_sqrt(cxx);
+  l21 = cxy / l11;
+  l22 = ses_sqrt(cyy - l21 * l21);
+}
+SES_HD void cholesky_cov(const Tables& tb, int cam, const ses3d_keypoint2d& kp, double& l11, double& l21, double& l22) {
+  const CamD& cm = tb.camd[cam];
+  const double cxx = (double)kp.cov[0] / (cm.fx * cm.fx), cxy = (double)kp.cov[1] / (cm.fx * cm.fy),
+               cyy = (double)kp.cov[2] / (cm.fy * cm.fy);
+  l11 = sqrt(cxx);
+  l21 = cxy / l11;
+  l22 = sqrt(cyy - l21 * l21);
+}
+
+// confidence-weighted mean reprojection error, calcReprojectionError S3D:425-438
+template <class T>
+SES_HD double reproj_error(const Tables& tb, const TriWs<T>& ws, int k, const uint8_t* list, int n, int skip,
+                           const T X[3]) {
+  double avg = 0., norm = 0.;
+  for (int i = 0; i < n; ++i) {
+    if (i == skip) continue;
+    const int o = list[i];
+    const ViewKp<T>& v = ws.vw[o * NKP + k];
+    const T r = reproj_residual<T>(CamSel<T>::P(tb, ws.obs_cam[o]), X, v.x, v.y);
+    avg += static_cast<double>(v.conf * r);
+    norm += static_cast<double>(v.conf);
+  }
+  return avg / norm;
 }
 
 // Weighted DLT of joint k over the views in list[0..n) skipping index `skip` (-1 = none):
-// triangulate(..., weight_by_conf=true, &err)  S3D:440-465 + calcReprojectionError S3D:425-438.
+// triangulate(..., weight_by_conf=true, &err)  S3D:440-465.
 template <class T>
-SES_HD void solve_weighted(const Tables& tb, const TriWs<T>& ws, int C, int k, const uint8_t* list, int n, int skip,
-                           T X[3], double* err) {
+SES_HD void solve_weighted(const Tables& tb, const TriWs<T>& ws, int k, const uint8_t* list, int n, int skip, T X[3],
+                           double* err) {
   double G[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (int i = 0; i < n; ++i) {
     if (i == skip) continue;
@@ -133,18 +167,7 @@ SES_HD void solve_weighted(const Tables& tb, const TriWs<T>& ws, int C, int k, c
   T e[4];
   smallest_eigvec4<T>(G, e);
   X[0] = e[0] / e[3]; X[1] = e[1] / e[3]; X[2] = e[2] / e[3];
-  if (err) {
-    double avg = 0., norm = 0.;
-    for (int i = 0; i < n; ++i) {
-      if (i == skip) continue;
-      const int o = list[i];
-      const ViewKp<T>& v = ws.vw[o * NKP + k];
-      const T r = reproj_residual<T>(CamSel<T>::P(tb, ws.obs_cam[o]), X, v.x, v.y);
-      avg += static_cast<double>(v.conf * r);
-      norm += static_cast<double>(v.conf);
-    }
-    *err = avg / norm;
-  }
+  *err = reproj_error<T>(tb, ws, k, list, n, skip, X);
 }
 
 // LM refinement of sum conf^2 * ||hnorm(P X~) - x||^2 (self-specified, not in the reference)
@@ -240,7 +263,7 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
     return;
   }
 
-  // normalised keypoints + covariances of the hypothesis' observations
+  // normalised keypoints of the hypothesis' observations
   tm.pfor(n_obs * NKP, [&](int i) {
     const int o = i / NKP, k = i % NKP;
     const int cam = ws.obs_cam[o];
@@ -262,7 +285,7 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
     avg_score /= n;
     T X[3];
     double err;
-    solve_weighted<T>(tb, ws, C, k, list, n, -1, X, &err);
+    solve_weighted<T>(tb, ws, k, list, n, -1, X, &err);
     if (err > max_reproj && n == 3) {
       int best = -1;
       float best_dist = static_cast<float>(err * err);
@@ -286,7 +309,7 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
       if (best != -1) {
         for (int i = best; i < 2; ++i) list[i] = list[i + 1];
         n = 2;
-        solve_weighted<T>(tb, ws, C, k, list, n, -1, X, &err);
+        solve_weighted<T>(tb, ws, k, list, n, -1, X, &err);
         avg_score = ((float)ws.vw[list[0] * NKP + k].conf + (float)ws.vw[list[1] * NKP + k].conf) / 2.0f;
       }
     } else if (err > max_reproj && n >= 4) {
@@ -298,165 +321,204 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
     ws.jscore[k] = avg_score;
   });
 
-  // leave-one-out solves for joints with a large error, one (joint, left-out view) per thread (S3D:799-810)
-  tm.pfor(NKP * C, [&](int i) {
-    const int k = i / C, v = i % C;
-    if (!ws.jflag[k] || v >= ws.jn[k]) return;
-    T X[3];
-    double e;
-    solve_weighted<T>(tb, ws, C, k, ws.vlist + k * C, ws.jn[k], v, X, &e);
-    ws.looX[i * 3] = X[0]; ws.looX[i * 3 + 1] = X[1]; ws.looX[i * 3 + 2] = X[2];
-    ws.looErr[i] = e;
-  });
+  // leave-one-out (S3D:793-838), rare: joints with a large error are handled in batches that fit
+  // the scratch; one (joint, left-out view) solve per thread, then the reference's sequential selection
+  for (int k0 = 0; k0 < NKP;) {
+    tm.single([&] {  // batch [k0,k1): flagged joints whose n solves fit into loo_cap; soff = scratch offsets
+      int k1 = k0, used = 0;
+      while (k1 < NKP) {
+        const int need = ws.jflag[k1] ? ws.jn[k1] : 0;
+        if (used + need > ws.loo_cap && used > 0) break;
+        ws.soff[k1] = used;
+        used += need;
+        ++k1;
+      }
+      ws.scal[2] = k1;
+      ws.scal[3] = used;
+    });
+    const int k1 = ws.scal[2], used = ws.scal[3];
+    if (used > 0) {
+      tm.pfor(used, [&](int i) {
+        int k = k0;
+        while (!(ws.jflag[k] && i < ws.soff[k] + ws.jn[k])) ++k;
+        T X[3];
+        double e;
+        solve_weighted<T>(tb, ws, k, ws.vlist + k * C, ws.jn[k], i - ws.soff[k], X, &e);
+        ws.looX[i * 3] = X[0]; ws.looX[i * 3 + 1] = X[1]; ws.looX[i * 3 + 2] = X[2];
+        ws.looErr[i] = e;
+      });
+      tm.pfor(k1 - k0, [&](int kk) {
+        const int k = k0 + kk;
+        if (!ws.jflag[k]) return;
+        const int base = ws.soff[k];
+        const int n = ws.jn[k];
+        uint8_t* list = ws.vlist + k * C;
+        const double err = ws.jerr[k];
+        double best_err = err;
+        int best = -1;
+        float best_score = ws.jscore[k];
+        for (int i = 0; i < n; ++i) {
+          const double e_sub = ws.looErr[base + i];
+          if (best_err > e_sub && e_sub < 0.9 * err) {
+            best_err = e_sub; best = i;
+            float tmp = 0.f;
+            for (int j = 0; j < n; ++j)
+              if (j != i) tmp += (float)ws.vw[list[j] * NKP + k].conf;
+            best_score = tmp / (float)(n - 1);
+          }
+        }
+        if (best != -1) {
+          ws.jX[k * 3] = ws.looX[(base + best) * 3]; ws.jX[k * 3 + 1] = ws.looX[(base + best) * 3 + 1];
+          ws.jX[k * 3 + 2] = ws.looX[(base + best) * 3 + 2];
+          for (int i = best; i < n - 1; ++i) list[i] = list[i + 1];
+          ws.jn[k] = n - 1;
+          ws.jerr[k] = best_err;
+          ws.jscore[k] = best_score;
+        }
+      });
+    }
+    k0 = k1;
+  }
 
-  // select (S3D:811-837), optional LM, down-weight (S3D:840-844), base Gram for the sigma points
+  // optional LM, down-weight (S3D:840-844), then the unweighted base system of the final view set:
+  // its full eigen-decomposition is the warm-start basis and its smallest eigenvector is sigma point 0
   tm.pfor(NKP, [&](int k) {
-    int n = ws.jn[k];
+    const int n = ws.jn[k];
+    for (int i = 0; i < 6; ++i) ws.cov[k * 6 + i] = T(0);
     if (n < 2) return;
-    uint8_t* list = ws.vlist + k * C;
+    const uint8_t* list = ws.vlist + k * C;
     double err = ws.jerr[k];
     float avg_score = ws.jscore[k];
     T X[3] = {ws.jX[k * 3], ws.jX[k * 3 + 1], ws.jX[k * 3 + 2]};
-    if (ws.jflag[k]) {
-      double best_err = err;
-      int best = -1;
-      float best_score = avg_score;
-      for (int i = 0; i < n; ++i) {
-        const double e_sub = ws.looErr[k * C + i];
-        if (best_err > e_sub && e_sub < 0.9 * err) {
-          best_err = e_sub; best = i;
-          float tmp = 0.f;
-          for (int j = 0; j < n; ++j)
-            if (j != i) tmp += (float)ws.vw[list[j] * NKP + k].conf;
-          best_score = tmp / (float)(n - 1);
-        }
-      }
-      if (best != -1) {
-        X[0] = ws.looX[(k * C + best) * 3]; X[1] = ws.looX[(k * C + best) * 3 + 1]; X[2] = ws.looX[(k * C + best) * 3 + 2];
-        for (int i = best; i < n - 1; ++i) list[i] = list[i + 1];
-        --n;
-        err = best_err;
-        avg_score = best_score;
-      }
-    }
     if (tb.prm.lm_refine) {
       lm_refine_joint<T>(tb, ws, k, list, n, X);
-      double avg = 0., norm = 0.;
-      for (int i = 0; i < n; ++i) {
-        const ViewKp<T>& v = ws.vw[list[i] * NKP + k];
-        const T r = reproj_residual<T>(CamSel<T>::P(tb, ws.obs_cam[list[i]]), X, v.x, v.y);
-        avg += static_cast<double>(v.conf * r);
-        norm += static_cast<double>(v.conf);
-      }
-      err = avg / norm;
+      err = reproj_error<T>(tb, ws, k, list, n, -1, X);
+      ws.jX[k * 3] = X[0]; ws.jX[k * 3 + 1] = X[1]; ws.jX[k * 3 + 2] = X[2];
     }
     if (err > max_reproj) avg_score = (float)((double)avg_score * (max_reproj / err));
+    ws.jscore[k] = avg_score;
     double G[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = 0; i < n; ++i) {
       const int o = list[i];
       const ViewKp<T>& v = ws.vw[o * NKP + k];
       const T* P = CamSel<T>::P(tb, ws.obs_cam[o]);
       T r[4];
-      dlt_row<T>(P, 0, v.x, T(1), false, r); gram_add<T>(G, r, 1.0);
-      dlt_row<T>(P, 1, v.y, T(1), false, r); gram_add<T>(G, r, 1.0);
+      dlt_row_fast<T>(P, 0, v.x, r); gram_add<T>(G, r, 1.0);
+      dlt_row_fast<T>(P, 1, v.y, r); gram_add<T>(G, r, 1.0);
     }
-    for (int i = 0; i < 10; ++i) ws.G0[k * 10 + i] = G[i];
-    ws.jn[k] = n;
-    ws.jX[k * 3] = X[0]; ws.jX[k * 3 + 1] = X[1]; ws.jX[k * 3 + 2] = X[2];
-    ws.jerr[k] = err;
-    ws.jscore[k] = avg_score;
+    T e[4];
+    eig4_full<T>(G, ws.lam0 + k * 4, ws.V0 + k * 16, e);
+    // sigma point 0 (unperturbed, unweighted) contributes w0 * (y0 - m)(y0 - m)^T   (S3D:521-522)
+    const T wden = T(2) * (T(2 * n) + T(0.5));
+    const T w0 = (T(2) * T(0.5)) / wden;
+    const T d0 = e[0] / e[3] - X[0], d1 = e[1] / e[3] - X[1], d2 = e[2] / e[3] - X[2];
+    T* cv = ws.cov + k * 6;
+    cv[0] = (d0 * w0) * d0; cv[1] = (d0 * w0) * d1; cv[2] = (d0 * w0) * d2;
+    cv[3] = (d1 * w0) * d1; cv[4] = (d1 * w0) * d2; cv[5] = (d2 * w0) * d2;
   });
 
   tm.single([&] {
     int off = 0;
-    for (int k = 0; k < NKP; ++k) { ws.soff[k] = off; off += ws.jn[k] >= 2 ? 4 * ws.jn[k] + 1 : 0; }
+    for (int k = 0; k < NKP; ++k) { ws.soff[k] = off; off += ws.jn[k] >= 2 ? 4 * ws.jn[k] : 0; }
     ws.soff[NKP] = off;
   });
   const int n_samples_total = ws.soff[NKP];
 
-  // unscented sigma points (S3D:471-506): all joints x (4n+1) samples in one index space
-  tm.pfor(n_samples_total, [&](int i) {
-    int k = 0;
-    while (ws.soff[k + 1] <= i) ++k;
-    const int s = i - ws.soff[k];
-    const int n = ws.jn[k];
-    double G[10];
-    for (int j = 0; j < 10; ++j) G[j] = ws.G0[k * 10 + j];
-    if (s > 0) {
-      const int vi = (s - 1) >> 2, m = (s - 1) & 3;
+  // unscented sigma points 1..4n (S3D:471-506) of all joints in one index space, Y_CHUNK per pass
+  for (int s0 = 0; s0 < n_samples_total; s0 += Y_CHUNK) {
+    const int cnt = (n_samples_total - s0) < Y_CHUNK ? (n_samples_total - s0) : Y_CHUNK;
+    tm.pfor(cnt, [&](int ii) {
+      const int i = s0 + ii;
+      int k = 0;
+      while (ws.soff[k + 1] <= i) ++k;
+      const int s = i - ws.soff[k];
+      const int n = ws.jn[k];
+      const int vi = s >> 2, m = s & 3;
       const int o = ws.vlist[k * C + vi];
+      const int cam = ws.obs_cam[o];
       const ViewKp<T>& v = ws.vw[o * NKP + k];
-      const T* P = CamSel<T>::P(tb, ws.obs_cam[o]);
-      const T b = ses_sqrt(T(2 * n) + T(0.5));
-      const T l11 = ses_sqrt(v.cxx);         // mod_samples S3D:471-487: 2x2 Cholesky
-      const T l21 = v.cxy / l11;
-      const T l22 = ses_sqrt(v.cyy - l21 * l21);
-      T nx = v.x, ny = v.y;
+      const T* P = CamSel<T>::P(tb, cam);
+      const T* V0 = ws.V0 + k * 16;
+      T l11, l21, l22;
+      cholesky_cov(tb, cam, persons[cam * p_max + ws.obs_det[o]].keypoints[k], l11, l21, l22);
+      const T b = ses_sqrt(T(2 * n) + T(0.5));  // sqrt(dim + kappa), S3D:500
+      T nx = v.x, ny = v.y;                    // mod_samples S3D:481-486
       if (m == 0) { nx = v.x - l11 * b; ny = v.y - l21 * b; }
       else if (m == 1) { ny = v.y - l22 * b; }
       else if (m == 2) { nx = v.x + l11 * b; ny = v.y + l21 * b; }
       else { ny = v.y + l22 * b; }
+      // normal matrix in the eigenbasis of the base system: diag(lam0) - old rows + new rows
+      double G[10] = {(double)ws.lam0[k * 4], 0, 0, 0, (double)ws.lam0[k * 4 + 1], 0, 0, (double)ws.lam0[k * 4 + 2], 0,
+                      (double)ws.lam0[k * 4 + 3]};
       T r[4];
+      double q[4];
       if ((m & 1) == 0) {
-        dlt_row<T>(P, 0, v.x, T(1), false, r); gram_add<T>(G, r, -1.0);
-        dlt_row<T>(P, 0, nx, T(1), false, r); gram_add<T>(G, r, 1.0);
+        dlt_row_fast<T>(P, 0, v.x, r); to_eigenbasis<T>(V0, r, q); gram_add_d(G, q, -1.0);
+        dlt_row_fast<T>(P, 0, nx, r); to_eigenbasis<T>(V0, r, q); gram_add_d(G, q, 1.0);
       }
-      dlt_row<T>(P, 1, v.y, T(1), false, r); gram_add<T>(G, r, -1.0);
-      dlt_row<T>(P, 1, ny, T(1), false, r); gram_add<T>(G, r, 1.0);
-    }
-    T e[4];
-    smallest_eigvec4<T>(G, e);
-    ws.Y[i * 3] = e[0] / e[3]; ws.Y[i * 3 + 1] = e[1] / e[3]; ws.Y[i * 3 + 2] = e[2] / e[3];
-  });
+      dlt_row_fast<T>(P, 1, v.y, r); to_eigenbasis<T>(V0, r, q); gram_add_d(G, q, -1.0);
+      dlt_row_fast<T>(P, 1, ny, r); to_eigenbasis<T>(V0, r, q); gram_add_d(G, q, 1.0);
+      T e[4];
+      smallest_eigvec4_warm<T>(G, V0, e);
+      const T inv = T(1) / e[3];
+      ws.Y[ii * 3] = e[0] * inv; ws.Y[ii * 3 + 1] = e[1] * inv; ws.Y[ii * 3 + 2] = e[2] * inv;
+    });
+    // covariance about the weighted-DLT point, samples in the reference's order (S3D:521-522)
+    tm.pfor(NKP, [&](int k) {
+      const int n = ws.jn[k];
+      if (n < 2) return;
+      int a = ws.soff[k], b = ws.soff[k + 1];
+      a = a > s0 ? a : s0;
+      b = b < s0 + cnt ? b : s0 + cnt;
+      if (a >= b) return;
+      const T wi = T(1) / (T(2) * (T(2 * n) + T(0.5)));
+      const T m0 = ws.jX[k * 3], m1 = ws.jX[k * 3 + 1], m2 = ws.jX[k * 3 + 2];
+      T* cv = ws.cov + k * 6;
+      T c00 = cv[0], c01 = cv[1], c02 = cv[2], c11 = cv[3], c12 = cv[4], c22 = cv[5];
+      for (int i = a; i < b; ++i) {
+        const T d0 = ws.Y[(i - s0) * 3] - m0, d1 = ws.Y[(i - s0) * 3 + 1] - m1, d2 = ws.Y[(i - s0) * 3 + 2] - m2;
+        c00 += (d0 * wi) * d0; c01 += (d0 * wi) * d1; c02 += (d0 * wi) * d2;
+        c11 += (d1 * wi) * d1; c12 += (d1 * wi) * d2; c22 += (d2 * wi) * d2;
+      }
+      cv[0] = c00; cv[1] = c01; cv[2] = c02; cv[3] = c11; cv[4] = c12; cv[5] = c22;
+    });
+  }
 
-  // covariance about the weighted-DLT point (S3D:521-522) and the output keypoint (S3D:849-857)
+  // output keypoints (S3D:849-857)
   tm.pfor(NKP, [&](int k) {
-    const int n = ws.jn[k];
-    if (n < 2) return;
-    const T wden = T(2) * (T(2 * n) + T(0.5));
-    const T w0 = (T(2) * T(0.5)) / wden, wi = T(1) / wden;
-    const T m0 = ws.jX[k * 3], m1 = ws.jX[k * 3 + 1], m2 = ws.jX[k * 3 + 2];
-    T c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
-    const int base = ws.soff[k], ns = 4 * n + 1;
-    for (int s = 0; s < ns; ++s) {
-      const T w = s == 0 ? w0 : wi;
-      const T d0 = ws.Y[(base + s) * 3] - m0, d1 = ws.Y[(base + s) * 3 + 1] - m1, d2 = ws.Y[(base + s) * 3 + 2] - m2;
-      c00 += (d0 * w) * d0; c01 += (d0 * w) * d1; c02 += (d0 * w) * d2;
-      c11 += (d1 * w) * d1; c12 += (d1 * w) * d2; c22 += (d2 * w) * d2;
-    }
+    if (ws.jn[k] < 2) return;
     ses3d_keypoint_cov& o = ws.kp[tb.model.fusion_idx[k]];
-    o.x = (double)m0; o.y = (double)m1; o.z = (double)m2;
+    o.x = (double)ws.jX[k * 3]; o.y = (double)ws.jX[k * 3 + 1]; o.z = (double)ws.jX[k * 3 + 2];
     o.score = ws.jscore[k];
-    o.cov[0] = (double)c00; o.cov[1] = (double)c01; o.cov[2] = (double)c02;
-    o.cov[3] = (double)c11; o.cov[4] = (double)c12; o.cov[5] = (double)c22;
+    for (int i = 0; i < 6; ++i) o.cov[i] = (double)ws.cov[k * 6 + i];
   });
 
-  // skeleton plausibility (S3D:861-973), a few hundred flops: team leader
-  tm.single([&] {
+  // limb-length covariance inflation (S3D:861-883): each joint reads positions only, so the joints
+  // are independent except for the shoulder pair, which the RShoulder item updates alone
+  tm.pfor(NKP, [&](int k) {
     const SkeletonModel& M = tb.model;
-    int num_valid = 0;
-    for (int k = 0; k < NKP; ++k) num_valid += ws.jn[k] >= 2 ? 1 : 0;
-    for (int k = 0; k < NKP; ++k) {
-      ses3d_keypoint_cov& kp = ws.kp[M.fusion_idx[k]];
-      if (kp.score <= 0) continue;
-      const int parent = M.parent[k];
-      if (parent >= 0) {
-        const ses3d_keypoint_cov& pk = ws.kp[M.fusion_idx[parent]];
-        if (pk.score > 0 && M.limb_len[k] > 0) {
-          add_cov(kp, tb.prm.limb_cov_offset_sigma * (joint_dist(kp, pk) - M.limb_len[k]) / M.limb_sigma[k]);
-        } else if (tb.prm.pose_method == SES3D_POSE_SIMPLE && k == 6 /*RShoulder S3D:83*/) {
-          ses3d_keypoint_cov& ls = ws.kp[M.fusion_idx[5 /*LShoulder S3D:86*/]];
-          if (ls.score > 0) {
-            const double d = joint_dist(kp, ls);
-            add_cov(kp, tb.prm.limb_cov_offset_sigma * (d - 0.35) / 0.15);  // shoulderDist, shoulderSigma S3D:103
-            add_cov(ls, tb.prm.limb_cov_offset_sigma * (d - 0.35) / 0.15);
-          }
-        }
+    ses3d_keypoint_cov& kp = ws.kp[M.fusion_idx[k]];
+    if (kp.score <= 0) return;
+    const int parent = M.parent[k];
+    if (parent < 0) return;
+    const ses3d_keypoint_cov& pk = ws.kp[M.fusion_idx[parent]];
+    if (pk.score > 0 && M.limb_len[k] > 0) {
+      add_cov(kp, tb.prm.limb_cov_offset_sigma * (joint_dist(kp, pk) - M.limb_len[k]) / M.limb_sigma[k]);
+    } else if (tb.prm.pose_method == SES3D_POSE_SIMPLE && k == 6 /*RShoulder S3D:83*/) {
+      ses3d_keypoint_cov& ls = ws.kp[M.fusion_idx[5 /*LShoulder S3D:86: parent Nose, limbLength -1: no own update*/]];
+      if (ls.score > 0) {
+        const double d = joint_dist(kp, ls);
+        add_cov(kp, tb.prm.limb_cov_offset_sigma * (d - 0.35) / 0.15);  // shoulderDist, shoulderSigma S3D:103
+        add_cov(ls, tb.prm.limb_cov_offset_sigma * (d - 0.35) / 0.15);
       }
     }
+  });
+
+  // root distance / feet height / keep decision (S3D:923-973)
+  tm.single([&] {
+    const ses3d_keypoint_cov* K = ws.kp;
     ses3d_keypoint_cov root;
     zero_kp(root);
-    const ses3d_keypoint_cov* K = ws.kp;
     if (K[SES3D_FBP_MIDHIP].score > 0) root = K[SES3D_FBP_MIDHIP];
     else if (K[SES3D_FBP_LHIP].score > 0 && K[SES3D_FBP_RHIP].score > 0) {
       root.x = (K[SES3D_FBP_LHIP].x + K[SES3D_FBP_RHIP].x) / 2.;
@@ -464,16 +526,31 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
       root.z = (K[SES3D_FBP_LHIP].z + K[SES3D_FBP_RHIP].z) / 2.;
       root.score = (K[SES3D_FBP_LHIP].score + K[SES3D_FBP_RHIP].score) / 2.f;
     }
-    if (root.score > 0) {
-      for (int s = 0; s < NFUS; ++s) {
-        ses3d_keypoint_cov& kp = ws.kp[s];
-        if (kp.score > 0) {
-          if (joint_dist(root, kp) > tb.prm.max_joint_dist_to_root) { zero_kp(kp); --num_valid; }
-        } else {
-          zero_kp(kp);
-          --num_valid;
-        }
-      }
+    // root is stashed for the parallel pass below
+    ws.jerr[0] = root.x; ws.jerr[1] = root.y; ws.jerr[2] = root.z; ws.jerr[3] = (double)root.score;
+  });
+  tm.pfor(NFUS, [&](int s) {  // far-from-root joints are reset (S3D:937-953)
+    if (!(ws.jerr[3] > 0)) return;
+    ses3d_keypoint_cov& kp = ws.kp[s];
+    ses3d_keypoint_cov root;
+    root.x = ws.jerr[0]; root.y = ws.jerr[1]; root.z = ws.jerr[2];
+    if (kp.score > 0) {
+      if (joint_dist(root, kp) > tb.prm.max_joint_dist_to_root) zero_kp(kp);
+    } else {
+      zero_kp(kp);
+    }
+  });
+  tm.single([&] {
+    const ses3d_keypoint_cov* K = ws.kp;
+    int num_valid = 0;
+    for (int k = 0; k < NKP; ++k) num_valid += ws.jn[k] >= 2 ? 1 : 0;
+    if (ws.jerr[3] > 0) {
+      // every slot that is empty after the reset decrements the counter (S3D:940-951): joints reset by the
+      // distance test and the never-filled slots alike
+      for (int s = 0; s < NFUS; ++s)
+        if (!(K[s].score > 0)) --num_valid;
+      // joints that were triangulated with a non-positive score were counted once above and are removed here
+      // as "empty" exactly like the reference does (kp.score > 0 is its only test)
     }
     double feet = 0.0;
     if (K[SES3D_FBP_LANKLE].score > 0 && K[SES3D_FBP_RANKLE].score > 0)

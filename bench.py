@@ -295,17 +295,17 @@ def main():
     # final result gather (compact xyz+score per joint), timed separately - the only collective
     gather_ms = None
     if world > 1:
-        kp = d_out3d.view(torch.float64).view(B, h_max, 221)[:, :, 1:211].reshape(B, h_max, 21, 10)
-        compact = torch.cat([kp[..., 0:3].float(),
-                             kp[..., 3].contiguous().view(torch.float32).view(B, h_max, 21, 2)[..., 0:1]], dim=-1).contiguous()
-        outl = [torch.empty_like(compact) for _ in range(world)] if rank == 0 else None
+        from smartedgesensor3dhumanpose_b200 import sharding
+        compact = sharding.compact_torch(d_out3d, B, h_max)
         barrier()
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
         t0.record()
-        dist.gather(compact, outl, dst=0)
+        parts = sharding.gather_compact(compact, dst=0)
         t1.record()
         barrier()
         gather_ms = t0.elapsed_time(t1)
+        if rank == 0:
+            assert len(parts) == world and all(p.shape == compact.shape for p in parts)
 
     if rank != 0:
         if world > 1:

@@ -1,0 +1,70 @@
+#!/usr/bin/env python
+"""Generate tests/golden/golden_v1.npz: frozen outputs of the CPU oracle (with the reference's verbatim
+Hungarian.cpp from oracle/_ref) on fixed-seed synthetic frames. The reference has no golden vectors of its
+own, so these pin the oracle against regressions and give the GPU tests a fixture that does not
+need /root/reference. Run in the build container:  python scripts/make_golden.py
+"""
+import hashlib
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+from oracle.binding import Oracle  # noqa: E402
+from smartedgesensor3dhumanpose_b200.layouts import default_params  # noqa: E402
+from tests import helpers  # noqa: E402
+
+CASES = [  # name, workload, frames, outlier fraction, params
+    ("cfg1", "cfg1_ring4x1", 24, 0.0, {}),
+    ("cfg2", "cfg2_hall16x6", 12, 0.0, {}),
+    ("cfg3", "cfg3_hall16x6_dropout", 12, 0.0, {}),
+    ("cfg5_outliers", "cfg5_ring8x4", 12, 0.06, {}),
+    ("dense_outliers", "dense_ring16x6", 6, 0.05, {}),
+    ("cfg2_fp64", "cfg2_hall16x6", 8, 0.0, {"precision": 1}),
+    ("cfg5_lm", "cfg5_ring8x4", 8, 0.0, {"lm_refine": 1}),
+    ("cfg4", "cfg4_crowd64x20", 2, 0.0, {}),
+]
+H_MAX = 40
+
+
+def run_case(workload, n_frames, outliers, prm):
+    fr = helpers.make_workload(workload, n_frames, h_max=H_MAX)
+    if outliers:
+        helpers.inject_outliers(fr, outliers, seed=7)
+    orc = Oracle(fr["cameras"], default_params(**prm), ref_hungarian=True)
+    r = orc.triangulate_batch(fr["persons"], fr["n_persons"], H_MAX)
+    assert r["status"] == 0
+    p = orc.reproject_batch(r["persons3d"], r["n_out"])
+    return fr, r, p
+
+
+def main():
+    out = {}
+    for name, workload, n_frames, outliers, prm in CASES:
+        fr, r, p = run_case(workload, n_frames, outliers, prm)
+        live = np.arange(H_MAX)[None, :] < r["n_out"][:, None]
+        kp = r["persons3d"]["keypoints"][live]
+        out[f"{name}/input_sha256"] = np.frombuffer(hashlib.sha256(fr["persons"].tobytes() + fr["n_persons"].tobytes()).digest(), np.uint8)
+        out[f"{name}/hyp_of"] = r["hyp_of"].astype(np.int16)
+        out[f"{name}/n_hyp"] = r["n_hyp"]
+        out[f"{name}/n_hungarian"] = r["n_hungarian"]
+        out[f"{name}/n_out"] = r["n_out"]
+        out[f"{name}/xyz"] = np.stack([kp["x"], kp["y"], kp["z"]], -1)
+        out[f"{name}/score"] = kp["score"]
+        out[f"{name}/cov"] = kp["cov"]
+        live2 = np.arange(H_MAX)[None, None, :] < p["n_out"][:, :, None]
+        out[f"{name}/n_out2d"] = p["n_out"].astype(np.int16)
+        out[f"{name}/persons2d_sha256"] = np.frombuffer(hashlib.sha256(p["persons2d"][live2].tobytes()).digest(), np.uint8)
+        k2 = p["persons2d"][live2]["keypoints"]
+        out[f"{name}/xy2d_sum"] = np.array([k2["x"].astype(np.float64).sum(), k2["y"].astype(np.float64).sum()])
+        print(name, "frames", n_frames, "persons", int(r["n_out"].sum()), "hungarian", int(r["n_hungarian"].sum()))
+    dst = ROOT / "tests" / "golden" / "golden_v1.npz"
+    np.savez_compressed(dst, **out)
+    print("wrote", dst, dst.stat().st_size, "bytes")
+
+
+if __name__ == "__main__":
+    main()

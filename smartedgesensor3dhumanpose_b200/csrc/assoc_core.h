@@ -18,7 +18,7 @@
 
 namespace ses3d {
 
-enum { SC_N_HYP = 0, SC_N_DET, SC_N_HUNG, SC_OVERFLOW, SC_CURSOR, SC_COUNT };
+enum { SC_N_HYP = 0, SC_N_DET, SC_N_HUNG, SC_OVERFLOW, SC_CURSOR, SC_NOBS_SUM, SC_COUNT };
 
 struct AssocWs {
   float* nk;          // [C*p_max][17][3] normalised keypoints x, y, conf ((0,0,-1) below threshold)
@@ -33,7 +33,19 @@ struct AssocWs {
   uint8_t *cov_r, *cov_c, *handled;      // [h_cap], [p_max], [p_max]
   int* assignment;    // [h_cap]
   int* scal;          // [SC_COUNT]
+  // "triple mode" (small rigs): one thread per (hypothesis, observation, detection)
+  double* obs_cost;   // [triple_cap] mean epipolar distance of one observation against one detection
+  uint8_t* obs_has;   // [triple_cap] the pair shared at least one joint
+  uint8_t* r2h;       // [C*p_max] observation rank -> hypothesis
+  uint16_t* hoff;     // [h_cap+1] prefix sum of hyp_nobs
+  int triple_cap;
 };
+
+// triple mode is used when every round's (sum of observations) x (detections) fits this many entries
+SES_HD int assoc_triple_cap(int C, int p_max) {
+  const long cap = (long)C * p_max * p_max;
+  return cap <= 2048 ? (int)cap : 0;
+}
 
 // Lays the workspace out in `base`; when nk_external != nullptr the keypoints live there
 // (global scratch for rigs whose frame does not fit in shared memory).
@@ -56,7 +68,13 @@ SES_HD void assoc_ws_layout(A& ar, int C, int p_max, int h_cap, bool nk_inside, 
   uint8_t* cov_r = ar.template take<uint8_t>(h_cap);
   uint8_t* cov_c = ar.template take<uint8_t>(p_max);
   uint8_t* handled = ar.template take<uint8_t>(p_max);
+  const int tcap = assoc_triple_cap(C, p_max);
+  double* obs_cost = ar.template take<double>(tcap);
+  uint16_t* hoff = ar.template take<uint16_t>(h_cap + 1);
+  uint8_t* obs_has = ar.template take<uint8_t>(tcap);
+  uint8_t* r2h = ar.template take<uint8_t>(tcap ? (size_t)C * p_max : 0);
   if (ws) {
+    ws->obs_cost = obs_cost; ws->hoff = hoff; ws->obs_has = obs_has; ws->r2h = r2h; ws->triple_cap = tcap;
     ws->cost = cost; ws->dist = dist; if (nk_inside) ws->nk = nk; ws->pscore = pscore;
     ws->assignment = assignment; ws->scal = scal; ws->hyp_obs = hyp_obs; ws->valid = valid;
     ws->hyp_nobs = hyp_nobs; ws->dets = dets; ws->mask = mask; ws->star = star; ws->prime = prime;
@@ -257,9 +275,69 @@ SES_HD void associate_frame(Team& tm, const Tables& tb, int p_max, int h_cap, co
       for (int d = 0; d < np(cam); ++d)
         if (ws.valid[cam * p_max + d]) ws.dets[n++] = (uint8_t)d;
       ws.scal[SC_N_DET] = n;
+      int sum = 0;
+      if (ws.triple_cap > 0 && n > 0) {  // observation ranks for triple mode
+        const int nh = ws.scal[SC_N_HYP];
+        for (int h = 0; h < nh; ++h) {
+          ws.hoff[h] = (uint16_t)sum;
+          for (int o = 0; o < ws.hyp_nobs[h]; ++o) ws.r2h[sum + o] = (uint8_t)h;
+          sum += ws.hyp_nobs[h];
+        }
+        ws.hoff[nh] = (uint16_t)sum;
+      }
+      ws.scal[SC_NOBS_SUM] = sum;
     });
     const int n_det = ws.scal[SC_N_DET], n_hyp = ws.scal[SC_N_HYP];
     if (n_det == 0) continue;
+    const int S = ws.scal[SC_NOBS_SUM];
+    const bool triple_mode = ws.triple_cap > 0 && S * n_det <= ws.triple_cap && n_hyp <= 255;
+
+    if (triple_mode) {
+      // inner loop of calcCost (S3D:347-365) for one (observation, detection) pair per thread
+      tm.pfor(S * n_det, [&](int t) {
+        const int di = t / S, r = t % S;
+        const int h = ws.r2h[r], o = r - ws.hoff[h];
+        const float* dk = ws.nk + ((size_t)(cam * p_max + ws.dets[di]) * NKP) * 3;
+        const int oc = ws.hyp_obs[(size_t)h * C + o] >> 8, od = ws.hyp_obs[(size_t)h * C + o] & 255;
+        const float* F = tb.F + (size_t)fundamental_idx(tb, oc, cam) * 9;
+        const float* hk = ws.nk + ((size_t)(oc * p_max + od) * NKP) * 3;
+        double cost = 0.;
+        int n_joints = 0;
+        for (int k = 0; k < NKP; ++k) {
+          if (hk[3 * k + 2] > thr && dk[3 * k + 2] > thr) {
+            cost += static_cast<double>(epipolar_symmetric(F, hk[3 * k], hk[3 * k + 1], dk[3 * k], dk[3 * k + 1]));
+            ++n_joints;
+          }
+        }
+        if (n_joints > 0) cost /= n_joints;
+        ws.obs_cost[t] = cost;
+        ws.obs_has[t] = n_joints > 0 ? 1 : 0;
+      });
+      // outer part of calcCost (S3D:367-389): observations in order, one cost-matrix entry per thread
+      tm.pfor(n_hyp * n_det, [&](int e) {
+        const int h = e % n_hyp, di = e / n_hyp;
+        const int n_obs = ws.hyp_nobs[h];
+        double total = 0., tmp_veto = 0.;
+        int n_used = 0;
+        const double tolerance = 1.0 - 1.0 / (2 * n_obs), veto_delta = 1.0 / n_obs;
+        for (int o = 0; o < n_obs; ++o) {
+          const int t = di * S + ws.hoff[h] + o;
+          if (ws.obs_has[t]) {
+            const double cost = ws.obs_cost[t];
+            const int oc = ws.hyp_obs[(size_t)h * C + o] >> 8, od = ws.hyp_obs[(size_t)h * C + o] & 255;
+            total += cost;
+            ++n_used;
+            if (cost > max_epi && (ws.pscore[oc * p_max + od] > 0.5f || n_obs == 1)) tmp_veto += veto_delta;
+          }
+        }
+        bool veto = tmp_veto > tolerance;
+        double c;
+        if (n_used > 0) c = total / n_used;
+        else { veto = true; c = MAX_COSTS; }
+        ws.cost[e] = c;
+        ws.mask[e] = (!veto && c < max_epi) ? 1 : 0;
+      });
+    } else
 
     // cost matrix, one (hypothesis, detection) entry per thread: calcCost S3D:335-390
     tm.pfor(n_hyp * n_det, [&](int e) {

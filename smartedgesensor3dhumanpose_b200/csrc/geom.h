@@ -135,6 +135,12 @@ SES_HD void sym4_load(Sym4V<T>& m, const double g[10]) {
   m.v20 = 0; m.v21 = 0; m.v22 = 1; m.v23 = 0; m.v30 = 0; m.v31 = 0; m.v32 = 0; m.v33 = 1;
 }
 
+// NaN inputs must give NaN outputs like the reference's SVD does (e.g. a zero 2-D covariance makes the
+// sigma points NaN, S3D:473-475): Jacobi's comparisons would otherwise silently skip every rotation.
+SES_HD double nan_poison(const double g[10]) {
+  return (((g[0] + g[1]) + (g[2] + g[3])) + ((g[4] + g[5]) + (g[6] + g[7])) + (g[8] + g[9])) * 0.0;
+}
+
 template <class T>
 SES_HD void sym4_smallest(const Sym4V<T>& m, T v[4]) {
   T best = m.a00;
@@ -151,6 +157,8 @@ SES_HD void smallest_eigvec4(const double g[10], T v[4]) {
   sym4_load(m, g);
   jacobi4(m);
   sym4_smallest(m, v);
+  const T poison = (T)nan_poison(g);
+  v[0] += poison; v[1] += poison; v[2] += poison; v[3] += poison;
 }
 
 // Full decomposition g = V diag(lam) V^T; V row-major, column c = eigenvector c. Also returns
@@ -164,6 +172,9 @@ SES_HD void eig4_full(const double g[10], T lam[4], T V[16], T v[4]) {
   V[0] = m.v00; V[1] = m.v01; V[2] = m.v02; V[3] = m.v03; V[4] = m.v10; V[5] = m.v11; V[6] = m.v12; V[7] = m.v13;
   V[8] = m.v20; V[9] = m.v21; V[10] = m.v22; V[11] = m.v23; V[12] = m.v30; V[13] = m.v31; V[14] = m.v32; V[15] = m.v33;
   sym4_smallest(m, v);
+  const T poison = (T)nan_poison(g);
+  v[0] += poison; v[1] += poison; v[2] += poison; v[3] += poison;
+  lam[0] += poison;
 }
 
 // q = V^T r in double (V, r exact in double): the row expressed in the eigenbasis of the base system.
@@ -191,7 +202,9 @@ SES_HD void smallest_eigvec4_warm(const double gp[10], const T V0[16], T v[4]) {
   jacobi4(m);
   T w[4];
   sym4_smallest(m, w);
-  for (int r = 0; r < 4; ++r) v[r] = V0[r * 4] * w[0] + V0[r * 4 + 1] * w[1] + V0[r * 4 + 2] * w[2] + V0[r * 4 + 3] * w[3];
+  const T poison = (T)nan_poison(gp);
+  for (int r = 0; r < 4; ++r)
+    v[r] = V0[r * 4] * w[0] + V0[r * 4 + 1] * w[1] + V0[r * 4 + 2] * w[2] + V0[r * 4 + 3] * w[3] + poison;
 }
 
 // projection residual of one view, S3D:430-433

@@ -16,7 +16,8 @@ extern __shared__ __align__(16) unsigned char smem_raw[];
 __global__ void __launch_bounds__(128)
 k_associate(const Tables tb, int n_frames, int p_max, int h_cap, const ses3d_person2d* __restrict__ persons,
             const int32_t* __restrict__ n_persons, float* nk_scratch, int8_t* __restrict__ hyp_det,
-            int32_t* __restrict__ n_hyp, int32_t* __restrict__ n_hung, int32_t* overflow, int32_t* hyp_of_dump) {
+            int32_t* __restrict__ n_hyp, int32_t* __restrict__ n_hung, int32_t* overflow, int32_t* hyp_of_dump,
+            int32_t* __restrict__ keep, uint32_t* __restrict__ work, int32_t* work_count) {
   const int f = blockIdx.x;
   if (f >= n_frames) return;
   const int C = tb.n_cams;
@@ -28,6 +29,19 @@ k_associate(const Tables tb, int n_frames, int p_max, int h_cap, const ses3d_per
   int8_t* hd = hyp_det + (size_t)f * h_cap * C;
   associate_frame(tm, tb, p_max, h_cap, persons + (size_t)f * C * p_max, n_persons + (size_t)f * C, ws, hd, n_hyp + f,
                   n_hung ? n_hung + f : nullptr, overflow);
+  // work list for K3: every hypothesis with at least two observations (S3D:684); order is irrelevant
+  // because results are addressed by (frame, hypothesis)
+  tm.pfor(h_cap, [&](int h) { keep[(size_t)f * h_cap + h] = 0; });
+  tm.single([&] {
+    const int nh = ws.scal[SC_N_HYP];
+    int n_active = 0;
+    for (int h = 0; h < nh; ++h) n_active += ws.hyp_nobs[h] >= 2 ? 1 : 0;
+    if (n_active > 0) {
+      int at = atomicAdd(work_count, n_active);
+      for (int h = 0; h < nh; ++h)
+        if (ws.hyp_nobs[h] >= 2) work[at++] = (uint32_t)((size_t)f * h_cap + h);
+    }
+  });
   if (hyp_of_dump) {  // [C][p_max] hypothesis index of each detection
     int32_t* ho = hyp_of_dump + (size_t)f * C * p_max;
     tm.pfor(C * p_max, [&](int i) { ho[i] = -1; });
@@ -79,17 +93,19 @@ size_t associate_smem_bytes(int n_cams, int p_max, int h_cap, bool* needs_scratc
 
 cudaError_t launch_associate(const Tables& tb, LaunchDims d, const ses3d_person2d* persons, const int32_t* n_persons,
                              float* nk_scratch, int8_t* hyp_det, int32_t* n_hyp, int32_t* n_hung, int32_t* overflow,
-                             int32_t* hyp_of_dump, cudaStream_t st) {
+                             int32_t* hyp_of_dump, int32_t* keep, uint32_t* work, int32_t* work_count, cudaStream_t st) {
   bool scratch;
   const size_t smem = associate_smem_bytes(tb.n_cams, d.p_max, d.h_cap, &scratch);
   if (smem > kSmemBudget) return cudaErrorInvalidConfiguration;
   if (scratch && !nk_scratch) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(k_associate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  const int threads = (tb.n_cams * d.p_max >= 256) ? 128 : 32;
+  e = cudaMemsetAsync(work_count, 0, sizeof(int32_t), st);
+  if (e != cudaSuccess) return e;
+  const int threads = (tb.n_cams * d.p_max >= 256) ? 128 : 64;
   k_associate<<<d.n_frames, threads, smem, st>>>(tb, d.n_frames, d.p_max, d.h_cap, persons, n_persons,
                                                  scratch ? nk_scratch : nullptr, hyp_det, n_hyp, n_hung, overflow,
-                                                 hyp_of_dump);
+                                                 hyp_of_dump, keep, work, work_count);
   return cudaGetLastError();
 }
 

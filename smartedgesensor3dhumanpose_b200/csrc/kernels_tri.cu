@@ -1,6 +1,8 @@
 // kernels_tri.cu — K3 triangulate for sm_100a: one warp per (frame, hypothesis), 4 warps per CTA, FP32 or FP64.
 // The algorithm lives in tri_core.h. Joint positions are tolerance-checked against the
 // oracle (1e-3 m FP32 / 1e-4 m FP64), so FMA contraction stays on here.
+#include <algorithm>
+
 #include "launch.h"
 #include "tri_core.h"
 
@@ -12,45 +14,63 @@ constexpr int kWarpsPerCta = 4;
 
 template <class T>
 __global__ void __launch_bounds__(32 * kWarpsPerCta)
-k_triangulate(const Tables tb, int n_frames, int p_max, int h_cap, size_t ws_bytes,
-              const ses3d_person2d* __restrict__ persons, const int8_t* __restrict__ hyp_det,
-              const int32_t* __restrict__ n_hyp, ses3d_person_cov* __restrict__ tmp, int32_t* __restrict__ keep) {
+k_triangulate(const Tables tb, int p_max, int h_cap, size_t ws_bytes, const ses3d_person2d* __restrict__ persons,
+              const int8_t* __restrict__ hyp_det, const uint32_t* __restrict__ work,
+              const int32_t* __restrict__ work_count, ses3d_person_cov* __restrict__ tmp, int32_t* __restrict__ keep) {
   const int warp = (int)(threadIdx.x >> 5);
-  const size_t fh = (size_t)blockIdx.x * kWarpsPerCta + warp;  // frame * h_cap + hypothesis
-  const size_t f = fh / h_cap;
-  if (f >= (size_t)n_frames) return;
-  const int h = (int)(fh - f * h_cap);
+  const int n_work = *work_count;
+  const int total_warps = (int)gridDim.x * kWarpsPerCta;
   WarpTeam tm;
-  if (h >= n_hyp[f]) {  // empty hypothesis slot
-    tm.single([&] { keep[fh] = 0; });
-    return;
-  }
   Arena ar(smem_raw + (size_t)warp * ws_bytes);
   TriWs<T> ws;
   tri_ws_layout<T>(ar, tb.n_cams, &ws);
-  triangulate_hypothesis<T>(tm, tb, p_max, persons + f * tb.n_cams * p_max, hyp_det + fh * tb.n_cams, ws, tmp + fh,
-                            keep + fh);
+  for (int w = (int)blockIdx.x * kWarpsPerCta + warp; w < n_work; w += total_warps) {
+    const size_t fh = work[w];  // frame * h_cap + hypothesis
+    const size_t f = fh / h_cap;
+    triangulate_hypothesis<T>(tm, tb, p_max, persons + f * tb.n_cams * p_max, hyp_det + fh * tb.n_cams, ws, tmp + fh,
+                              keep + fh);
+    tm.sync();
+  }
 }
 
 cudaError_t launch_triangulate(const Tables& tb, LaunchDims d, const ses3d_person2d* persons, const int8_t* hyp_det,
-                               const int32_t* n_hyp, ses3d_person_cov* tmp, int32_t* keep, cudaStream_t st) {
+                               const uint32_t* work, const int32_t* work_count, ses3d_person_cov* tmp, int32_t* keep,
+                               cudaStream_t st) {
   const bool f64 = tb.prm.precision == SES3D_PRECISION_FP64;
   const size_t ws_bytes = f64 ? tri_ws_bytes<double>(tb.n_cams) : tri_ws_bytes<float>(tb.n_cams);
   const size_t smem = ws_bytes * kWarpsPerCta;
   if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0) n_sm = 148;
+  }
+  // persistent grid: as many CTAs as fit on the chip at the kernel's occupancy (a multiple of the SM
+  // count), never more than the work
   const size_t units = (size_t)d.n_frames * d.h_cap;
-  const unsigned grid = (unsigned)((units + kWarpsPerCta - 1) / kWarpsPerCta);
   cudaError_t e;
+  int per_sm = 0;
   if (f64) {
     e = cudaFuncSetAttribute(k_triangulate<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    k_triangulate<double><<<grid, 32 * kWarpsPerCta, smem, st>>>(tb, d.n_frames, d.p_max, d.h_cap, ws_bytes, persons,
-                                                                 hyp_det, n_hyp, tmp, keep);
+    if (e == cudaSuccess)
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_triangulate<double>, 32 * kWarpsPerCta, smem);
   } else {
     e = cudaFuncSetAttribute(k_triangulate<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    k_triangulate<float><<<grid, 32 * kWarpsPerCta, smem, st>>>(tb, d.n_frames, d.p_max, d.h_cap, ws_bytes, persons,
-                                                                hyp_det, n_hyp, tmp, keep);
+    if (e == cudaSuccess)
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_triangulate<float>, 32 * kWarpsPerCta, smem);
+  }
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((units + kWarpsPerCta - 1) / kWarpsPerCta,
+                                                                       (size_t)n_sm * per_sm));
+  if (f64) {
+    k_triangulate<double><<<grid, 32 * kWarpsPerCta, smem, st>>>(tb, d.p_max, d.h_cap, ws_bytes, persons, hyp_det, work,
+                                                                 work_count, tmp, keep);
+  } else {
+    k_triangulate<float><<<grid, 32 * kWarpsPerCta, smem, st>>>(tb, d.p_max, d.h_cap, ws_bytes, persons, hyp_det, work,
+                                                                work_count, tmp, keep);
   }
   return cudaGetLastError();
 }

@@ -166,3 +166,55 @@ def test_device_buffer_path_and_device_generator():
     got = d_out.cpu().numpy().view(person_cov_dtype).reshape(n_frames, h_max)
     live = np.arange(h_max)[None, :] < host["n_out"][:, None]
     assert got[live].tobytes() == host["persons3d"][live].tobytes()
+
+
+@pytest.mark.parametrize("case", [c[0] for c in __import__("scripts.make_golden", fromlist=["CASES"]).CASES])
+def test_gpu_against_committed_golden_vectors(case):
+    """The committed fixtures (tests/golden, made by scripts/make_golden.py from the oracle + the reference's
+    verbatim Hungarian.cpp) do not need the oracle or /root/reference at run time."""
+    import hashlib
+    from pathlib import Path
+    import scripts.make_golden as mg
+    g = np.load(Path(__file__).resolve().parent / "golden" / "golden_v1.npz")
+    name, workload, n_frames, outliers, prm = next(c for c in mg.CASES if c[0] == case)
+    fr = helpers.make_workload(workload, n_frames, h_max=mg.H_MAX)
+    if outliers:
+        helpers.inject_outliers(fr, outliers, seed=7)
+    assert hashlib.sha256(fr["persons"].tobytes() + fr["n_persons"].tobytes()).digest() == g[f"{name}/input_sha256"].tobytes()
+    gpu = api.GeometryPipeline(fr["cameras"], default_params(**prm))
+    r = gpu.triangulate_batch(fr["persons"], fr["n_persons"], mg.H_MAX)
+    assert np.array_equal(r["hyp_of"], g[f"{name}/hyp_of"])
+    assert np.array_equal(r["n_hungarian"], g[f"{name}/n_hungarian"]) and np.array_equal(r["n_hyp"], g[f"{name}/n_hyp"])
+    if outliers == 0:
+        assert np.array_equal(r["n_out"], g[f"{name}/n_out"])
+        live = np.arange(mg.H_MAX)[None, :] < r["n_out"][:, None]
+        kp = r["persons3d"]["keypoints"][live]
+        tol = POS_TOL_FP64 if prm.get("precision") else POS_TOL_FP32
+        d = np.linalg.norm(np.stack([kp["x"], kp["y"], kp["z"]], -1) - g[f"{name}/xyz"], axis=-1)
+        assert np.array_equal(kp["score"] > 0, g[f"{name}/score"] > 0) and d[kp["score"] > 0].max() <= tol
+
+
+def test_nan_trap_is_reproduced_not_hidden():
+    """Zero 2-D covariance -> NaN 3-D covariance in the reference (S3D:473-475); the library must not invent numbers."""
+    fr = helpers.make_workload("cfg5_ring8x4", 8)
+    persons = fr["persons"].copy()
+    persons["keypoints"]["cov"][5] = 0.0
+    orc = Oracle(fr["cameras"], ref_hungarian=True)
+    gpu = api.GeometryPipeline(fr["cameras"])
+    ro = orc.triangulate_batch(persons, fr["n_persons"], fr["h_max"])
+    rg = gpu.triangulate_batch(persons, fr["n_persons"], fr["h_max"])
+    assert np.array_equal(ro["n_out"], rg["n_out"]) and ro["n_out"][5] > 0
+    a = ro["persons3d"][5, :ro["n_out"][5]]["keypoints"]
+    b = rg["persons3d"][5, :rg["n_out"][5]]["keypoints"]
+    assert np.isnan(a["cov"]).any() and np.array_equal(np.isnan(a["cov"]), np.isnan(b["cov"]))
+
+
+def test_multi_chunk_batches_and_reuse_of_the_handle():
+    """More frames than one internal device chunk (16384) and than one host chunk; second call reuses scratch."""
+    fr = helpers.make_workload("cfg1_ring4x1", 20000)
+    gpu = api.GeometryPipeline(fr["cameras"])
+    a = gpu.process_batch(fr["persons"], fr["n_persons"], 4)
+    b = gpu.process_batch(fr["persons"], fr["n_persons"], 4)
+    assert a["persons3d"].tobytes() == b["persons3d"].tobytes() and a["persons2d"].tobytes() == b["persons2d"].tobytes()
+    ro = Oracle(fr["cameras"], ref_hungarian=True).triangulate_batch(fr["persons"], fr["n_persons"], 4, n_threads=8)
+    helpers.compare_persons3d(ro, dict(persons3d=a["persons3d"], n_out=a["n_out3d"]), POS_TOL_FP32)

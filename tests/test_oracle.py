@@ -1,0 +1,249 @@
+"""CPU tests of the oracle (oracle/): pinned against the reference's verbatim Hungarian.cpp, against
+independent numpy/scipy implementations, against the generator's ground truth and against the committed
+golden vectors. The reference ships no tests or golden vectors of its own."""
+import hashlib
+from pathlib import Path
+
+import numpy as np
+import pytest
+import scipy.optimize as so
+
+from oracle import binding as ob
+from oracle.binding import Oracle
+from smartedgesensor3dhumanpose_b200 import rigs
+from smartedgesensor3dhumanpose_b200.layouts import KP2FUSION_SIMPLE, default_params, person_cov_dtype
+from tests import helpers
+
+GOLDEN = Path(__file__).resolve().parent / "golden" / "golden_v1.npz"
+HAVE_REF = ob.REF_HUNGARIAN_PATH.exists()
+
+
+# ----------------------------------------------------------------------------- Munkres (a5)
+@pytest.mark.parametrize("shape", [(1, 1), (1, 5), (5, 1), (3, 3), (6, 6), (4, 7), (7, 4), (20, 20), (24, 20), (20, 31)])
+def test_munkres_restatement_matches_reference_and_scipy(shape):
+    rng = np.random.default_rng(shape[0] * 100 + shape[1])
+    for it in range(150):
+        c = rng.random(shape)
+        if it % 3 == 0:
+            c[rng.random(shape) < 0.6] = 1e6          # MAX_COSTS ties (S3D:43, 383-389)
+        if it % 5 == 0:
+            c = np.round(c * 4) / 4                   # many exact ties
+        a, total = ob.munkres(c)
+        if HAVE_REF:                                   # indices AND cost identical to Hungarian.cpp
+            a_ref, total_ref = ob.ref_munkres(c)
+            assert np.array_equal(a, a_ref) and total == total_ref
+        r, cc = so.linear_sum_assignment(c)           # optimal cost (indices may differ under ties)
+        assert abs(c[r, cc].sum() - total) <= 1e-9 * max(1.0, abs(total))
+        used = a[a >= 0]
+        assert len(set(used.tolist())) == len(used) == min(shape)
+
+
+# ----------------------------------------------------------------------------- set-up tables (a2)
+def test_fundamental_matrices_satisfy_epipolar_constraint():
+    cams = rigs.hall16()
+    P, F = Oracle(cams).tables()
+    rng = np.random.default_rng(0)
+    X = np.concatenate([rng.uniform([-9, -4, 0], [2, 4, 2], (200, 3)), np.ones((200, 1))], 1)
+    idx = 0
+    for i in range(16):
+        for j in range(i + 1, 16):
+            Pi, Pj = cams["T_cam_base"][i].reshape(3, 4), cams["T_cam_base"][j].reshape(3, 4)
+            xi, xj = (Pi @ X.T).T, (Pj @ X.T).T
+            ok = (xi[:, 2] > 0.5) & (xj[:, 2] > 0.5)
+            xi, xj = xi[ok] / xi[ok, 2:3], xj[ok] / xj[ok, 2:3]
+            Fm = F[idx].reshape(3, 3).astype(np.float64)
+            l = (Fm @ xi.T).T                          # epipolar lines in image j
+            d = np.abs((xj * l).sum(1)) / np.hypot(l[:, 0], l[:, 1])
+            assert d.max() < 1e-5, (i, j, d.max())     # get_fundamental_idx order (S3D:242-253)
+            idx += 1
+    assert idx == len(F)
+    assert np.array_equal(P, cams["T_cam_base"].astype(np.float32))
+
+
+# ----------------------------------------------------------------------------- DLT (a6, a7)
+def _random_views(rng, n):
+    cams = rigs.ring16()
+    sel = rng.choice(16, n, replace=False)
+    P = cams["T_cam_base"][sel].reshape(n, 3, 4)
+    X = rng.uniform([-2, -2, 0.2], [2, 2, 1.8])          # in front of every camera of the ring
+    x = (P @ np.append(X, 1.0)).reshape(n, 3)
+    pts = np.stack([x[:, 0] / x[:, 2] + rng.normal(0, 0.003, n), x[:, 1] / x[:, 2] + rng.normal(0, 0.003, n),
+                    rng.uniform(0.5, 1.0, n)], 1)
+    return P, pts, X
+
+
+def _numpy_dlt(P, pts, weighted):
+    rows = []
+    for Pi, (x, y, c) in zip(P, pts):
+        for r in (x * Pi[2] - Pi[0], y * Pi[2] - Pi[1]):
+            r = r / np.linalg.norm(r)
+            rows.append(r * c if weighted else r)
+    v = np.linalg.svd(np.array(rows))[2][-1]
+    return v[:3] / v[3]
+
+
+@pytest.mark.parametrize("weighted", [True, False])
+def test_dlt_matches_numpy_svd(weighted):
+    rng = np.random.default_rng(1)
+    worst32 = worst64 = 0.0
+    for _ in range(300):
+        P, pts, _ = _random_views(rng, int(rng.integers(2, 13)))
+        ref = _numpy_dlt(P, pts, weighted)
+        X64, e64 = ob.triangulate_point(P, pts, weighted, use_double=True)
+        X32, e32 = ob.triangulate_point(P, pts, weighted, use_double=False)
+        worst64 = max(worst64, np.linalg.norm(X64 - ref))
+        worst32 = max(worst32, np.linalg.norm(X32 - _numpy_dlt(P.astype(np.float32).astype(np.float64),
+                                                               pts.astype(np.float32).astype(np.float64), weighted)))
+        proj = (P @ np.append(X64, 1.0)).reshape(-1, 3)       # calcReprojectionError S3D:425-438
+        err = np.hypot(proj[:, 0] / proj[:, 2] - pts[:, 0], proj[:, 1] / proj[:, 2] - pts[:, 1])
+        assert abs((pts[:, 2] * err).sum() / pts[:, 2].sum() - e64) < 1e-12 * max(1.0, e64)
+    assert worst64 < 1e-9 and worst32 < 1e-4, (worst64, worst32)
+
+
+def test_lm_refinement_matches_scipy_least_squares():
+    rng = np.random.default_rng(2)
+    for _ in range(60):
+        P, pts, _ = _random_views(rng, int(rng.integers(3, 10)))
+        X0, _ = ob.triangulate_point(P, pts, True, use_double=True)
+
+        def resid(X):
+            x = (P @ np.append(X, 1.0)).reshape(-1, 3)
+            return np.concatenate([pts[:, 2] * (x[:, 0] / x[:, 2] - pts[:, 0]), pts[:, 2] * (x[:, 1] / x[:, 2] - pts[:, 1])])
+
+        ref = so.least_squares(resid, X0, method="lm", xtol=1e-14, ftol=1e-14).x
+        got = ob.lm_refine(P, pts, X0, max_iters=25)
+        assert np.linalg.norm(got - ref) < 1e-5
+        assert (resid(got) ** 2).sum() <= (resid(X0) ** 2).sum() + 1e-15
+
+
+def test_ut_covariance_matches_linearised_propagation():
+    """For small 2-D noise the unscented covariance (S3D:471-523) tends to J Sigma J^T of the DLT map."""
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        n = int(rng.integers(3, 9))
+        P, pts, _ = _random_views(rng, n)
+        sig = 1e-4
+        cov2d = np.tile([sig ** 2, 0.1 * sig ** 2, sig ** 2], (n, 1))
+        X0 = _numpy_dlt(P, pts, False)
+        C = ob.ut_covariance(P, pts, cov2d, X0)
+        J = np.zeros((3, 2 * n))
+        h = 1e-7
+        for i in range(n):
+            for a in range(2):
+                q = pts.copy(); q[i, a] += h
+                J[:, 2 * i + a] = (_numpy_dlt(P, q, False) - X0) / h
+        S = np.zeros((2 * n, 2 * n))
+        for i in range(n):
+            S[2 * i:2 * i + 2, 2 * i:2 * i + 2] = [[sig ** 2, 0.1 * sig ** 2], [0.1 * sig ** 2, sig ** 2]]
+        ref = J @ S @ J.T
+        assert np.allclose(C, ref, rtol=2e-2, atol=1e-3 * np.abs(ref).max())
+        assert np.allclose(C, C.T) and np.linalg.eigvalsh(C).min() > -1e-18
+
+
+# ----------------------------------------------------------------------------- whole path properties
+@pytest.mark.parametrize("name", ["cfg1_ring4x1", "cfg5_ring8x4", "dense_ring16x6"])
+def test_noise_free_frames_recover_ground_truth_and_identity(name):
+    fr = helpers.make_workload(name, 40, noise_px=0.0, dropout=0.0)
+    r = Oracle(fr["cameras"]).triangulate_batch(fr["persons"], fr["n_persons"], fr["h_max"])
+    F, C, PM = r["hyp_of"].shape
+    for f in range(F):
+        # association equals the generator's identity labels: one hypothesis per person
+        for h in range(r["n_hyp"][f]):
+            ids = fr["gt_id"][f][r["hyp_of"][f] == h]
+            assert len(set(ids.tolist())) == 1
+        assert r["n_out"][f] == fr["gt_joints"].shape[1]
+        # every output skeleton coincides with one ground-truth person to < 1e-4 m (float DLT)
+        for p in range(r["n_out"][f]):
+            kp = r["persons3d"][f, p]["keypoints"][list(KP2FUSION_SIMPLE)]
+            xyz = np.stack([kp["x"], kp["y"], kp["z"]], 1)
+            d = np.linalg.norm(fr["gt_joints"][f] - xyz[None], axis=2).max(1)
+            assert d.min() < 1e-4
+
+
+def test_person_order_permutation_permutes_association():
+    fr = helpers.make_workload("cfg5_ring8x4", 30)
+    orc = Oracle(fr["cameras"])
+    base = orc.triangulate_batch(fr["persons"], fr["n_persons"], fr["h_max"])
+    rng = np.random.default_rng(4)
+    persons = fr["persons"].copy()
+    perm = np.zeros(fr["persons"].shape[:3], np.int64)
+    for f in range(persons.shape[0]):
+        for c in range(1, persons.shape[1]):            # camera 0 seeds the hypotheses: keep its order
+            n = fr["n_persons"][f, c]
+            p = np.concatenate([rng.permutation(n), np.arange(n, persons.shape[2])])
+            persons[f, c] = fr["persons"][f, c][p]
+            perm[f, c] = p
+        perm[f, 0] = np.arange(persons.shape[2])
+    got = orc.triangulate_batch(persons, fr["n_persons"], fr["h_max"])
+    agree = 0
+    for f in range(persons.shape[0]):
+        same = all(np.array_equal(got["hyp_of"][f, c], base["hyp_of"][f, c][perm[f, c]]) for c in range(persons.shape[1]))
+        agree += same
+    assert agree >= persons.shape[0] - 2                # greedy matching may differ only on genuine ties
+
+
+def test_plausibility_counter_quirk():
+    """S3D:937-953: every empty fusion slot decrements the counter when a root exists, so a person survives only
+    with >= 16 of 17 joints triangulated (2T - f - 21 > 9)."""
+    fr = helpers.make_workload("cfg5_ring8x4", 20)
+    persons = fr["persons"].copy()
+    persons["keypoints"]["score"][:, :, :, 9:11] = 0.1     # both wrists missing in every view -> T = 15
+    r = Oracle(fr["cameras"]).triangulate_batch(persons, fr["n_persons"], fr["h_max"])
+    assert r["n_out"].sum() == 0
+    persons = fr["persons"].copy()
+    persons["keypoints"]["score"][:, :, :, 9] = 0.1        # one wrist missing -> T = 16 survives
+    r = Oracle(fr["cameras"]).triangulate_batch(persons, fr["n_persons"], fr["h_max"])
+    assert r["n_out"].sum() > 0
+
+
+def test_reprojection_closed_form_pinhole():
+    """With a tiny covariance the unscented mean is the pinhole projection (REP:193-204)."""
+    cams = rigs.ring8()
+    orc = Oracle(cams)
+    p3 = np.zeros((1, 4), person_cov_dtype)
+    rng = np.random.default_rng(5)
+    X = rng.uniform([-1, -1, 0.2], [1, 1, 1.8], (17, 3))
+    for k, slot in enumerate(KP2FUSION_SIMPLE):
+        kp = p3[0, 0]["keypoints"][slot]
+        kp["x"], kp["y"], kp["z"], kp["score"] = X[k, 0], X[k, 1], X[k, 2], 0.9
+        kp["cov"] = [1e-12, 0, 0, 1e-12, 0, 1e-12]
+    r = orc.reproject_batch(p3, np.array([1], np.int32))
+    for c in range(8):
+        T = cams["T_cam_base"][c].reshape(3, 4)
+        x = (T @ np.concatenate([X, np.ones((17, 1))], 1).T).T
+        u, v = 1000 * x[:, 0] / x[:, 2] + 640, 1000 * x[:, 1] / x[:, 2] + 360
+        inside = (u >= 0) & (u <= 1280) & (v >= 0) & (v <= 720)
+        if not inside.any():
+            assert r["n_out"][0, c] == 0
+            continue
+        got = r["persons2d"][0, c, 0]
+        assert r["n_out"][0, c] == 1 and got["score"] == 1.0
+        assert np.allclose(got["keypoints"]["x"][inside], u[inside], atol=2e-3)
+        assert np.allclose(got["keypoints"]["y"][inside], v[inside], atol=2e-3)
+        assert np.all(got["keypoints"]["score"][~inside] == 0)
+        assert np.isclose(got["bbox"][0], u[inside].min(), atol=2e-3) and np.isclose(got["bbox"][3], v[inside].max(), atol=2e-3)
+
+
+# ----------------------------------------------------------------------------- golden vectors
+def _golden_cases():
+    import scripts.make_golden as mg
+    return mg.CASES
+
+
+@pytest.mark.parametrize("case", [c[0] for c in __import__("scripts.make_golden", fromlist=["CASES"]).CASES])
+def test_oracle_reproduces_golden_vectors(case):
+    import scripts.make_golden as mg
+    g = np.load(GOLDEN)
+    name, workload, n_frames, outliers, prm = next(c for c in mg.CASES if c[0] == case)
+    fr, r, p = mg.run_case(workload, n_frames, outliers, prm)
+    digest = hashlib.sha256(fr["persons"].tobytes() + fr["n_persons"].tobytes()).digest()
+    assert digest == g[f"{name}/input_sha256"].tobytes(), "synthetic generator changed"
+    assert np.array_equal(r["hyp_of"], g[f"{name}/hyp_of"])
+    assert np.array_equal(r["n_out"], g[f"{name}/n_out"]) and np.array_equal(r["n_hungarian"], g[f"{name}/n_hungarian"])
+    live = np.arange(mg.H_MAX)[None, :] < r["n_out"][:, None]
+    kp = r["persons3d"]["keypoints"][live]
+    assert np.array_equal(np.stack([kp["x"], kp["y"], kp["z"]], -1), g[f"{name}/xyz"])
+    assert np.array_equal(kp["score"], g[f"{name}/score"]) and np.array_equal(kp["cov"], g[f"{name}/cov"])
+    live2 = np.arange(mg.H_MAX)[None, None, :] < p["n_out"][:, :, None]
+    assert np.array_equal(p["n_out"], g[f"{name}/n_out2d"])
+    assert hashlib.sha256(p["persons2d"][live2].tobytes()).digest() == g[f"{name}/persons2d_sha256"].tobytes()

@@ -168,6 +168,20 @@ int ses3d_process_batch(ses3d_handle h, int32_t n_frames, int32_t p_max,
                         ses3d_person2d* out2d, int32_t* n_out2d,
                         const ses3d_assoc_dump* dump, uint32_t flags, void* stream);
 
+/* Ragged form of ses3d_process_batch. The reference's messages are variable-length lists
+ * (Person2D[] persons, PersonCov[] persons), so only occupied records travel:
+ *   persons_dense  all detections back to back, frame-major then camera-major; n_persons [n_frames][n_cams]
+ *                  gives the run lengths (each <= p_max)
+ *   out3d          dense PersonCov records, frame-major, n_out3d [n_frames] run lengths, capacity cap3d records
+ *   out2d          dense reprojected Person2D records, frame- then camera-major, n_out2d [n_frames][n_cams],
+ *                  capacity cap2d records
+ * Offsets are the exclusive prefix sums of the count arrays; totals are returned. Synchronous. */
+int ses3d_process_batch_ragged(ses3d_handle h, int32_t n_frames, int32_t p_max,
+                               const ses3d_person2d* persons_dense, const int32_t* n_persons,
+                               int32_t h_max, ses3d_person_cov* out3d, int64_t cap3d, int32_t* n_out3d,
+                               ses3d_person2d* out2d, int64_t cap2d, int32_t* n_out2d,
+                               int64_t* total3d, int64_t* total2d, uint32_t flags);
+
 /* Pre-size the handle's device scratch (otherwise grown on first use). */
 int ses3d_reserve(ses3d_handle h, int32_t n_frames, int32_t p_max, int32_t h_max);
 

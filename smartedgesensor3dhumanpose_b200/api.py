@@ -106,6 +106,18 @@ class GeometryPipeline:
                                                _p(n3d), _p(out2d), _p(n2d), None, HOST_BUFFERS, None))
         return dict(persons3d=out3d, n_out3d=n3d, persons2d=out2d, n_out2d=n2d)
 
+    def process_batch_ragged(self, persons_dense, n_persons, p_max, h_max, out3d, n_out3d, out2d, n_out2d):
+        """Ragged form (only occupied records cross PCIe): persons_dense = all detections back to back
+        (frame-major, camera-major), n_persons [F][C] run lengths; out3d / out2d are caller-provided dense record
+        arrays (capacity = their length). Returns (total3d, total2d)."""
+        n_persons = np.ascontiguousarray(n_persons, dtype=np.int32)
+        n_frames = n_persons.shape[0]
+        t3, t2 = C.c_int64(0), C.c_int64(0)
+        _lib.check(self._L.ses3d_process_batch_ragged(self._h, n_frames, p_max, _p(persons_dense), _p(n_persons), h_max,
+                                                      _p(out3d), len(out3d), _p(n_out3d), _p(out2d), len(out2d),
+                                                      _p(n_out2d), C.byref(t3), C.byref(t2), HOST_BUFFERS))
+        return t3.value, t2.value
+
     # ----------------------------------------------------- device-buffer calls
     # Arguments are raw device addresses (e.g. torch_tensor.data_ptr()) on this handle's GPU.
     def triangulate_device(self, n_frames, p_max, h_max, persons_ptr, n_persons_ptr, out_ptr, n_out_ptr, stream=0,
@@ -123,6 +135,22 @@ class GeometryPipeline:
         _lib.check(self._L.ses3d_process_batch(self._h, n_frames, p_max, persons_ptr, n_persons_ptr, h_max, out3d_ptr,
                                                n_out3d_ptr, out2d_ptr, n_out2d_ptr, None, DEVICE_BUFFERS,
                                                stream or None))
+
+
+def to_ragged(persons, n_persons):
+    """[F][C][p_max] padded detections -> dense record array in frame-major, camera-major order."""
+    persons = np.asarray(persons, dtype=person2d_dtype)
+    live = np.arange(persons.shape[2])[None, None, :] < np.asarray(n_persons)[:, :, None]
+    return np.ascontiguousarray(persons[live])
+
+
+def from_ragged(dense, counts, cap, dtype):
+    """dense records + run lengths counts[...] -> padded array counts.shape + (cap,)."""
+    counts = np.asarray(counts)
+    out = np.zeros(counts.shape + (cap,), dtype)
+    live = np.arange(cap).reshape((1,) * counts.ndim + (cap,)) < counts[..., None]
+    out[live] = dense[:int(counts.sum())]
+    return out
 
 
 def _pack_frame(people, n_cams):

@@ -26,6 +26,7 @@ UNITS = [
     ("kernels_exact.cu", ["-fmad=false"]),
     ("kernels_tri.cu", []),
     ("synth_device.cu", ["-fmad=false"]),
+    ("kernels_pack.cu", []),
     ("api.cpp", []),
     ("host_setup.cpp", []),
     ("synth.cpp", []),

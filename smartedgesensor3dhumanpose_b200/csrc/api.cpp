@@ -68,9 +68,17 @@ struct Slot {  // one in-flight chunk of a host-buffer call
   cudaStream_t stream = nullptr;
   Scratch sc;
   DevBuf persons, n_persons, out3d, n_out3d, out2d, n_out2d, hyp_of;
+  DevBuf in_dense, in_off, off3, off2, c3d, c2d;  // ragged calls: dense staging + offsets
+  long long* totals = nullptr;                    // pinned host: {total3d, total2d} of the chunk in flight
+  cudaEvent_t done = nullptr;
   void release() {
     sc.release(); persons.release(); n_persons.release(); out3d.release(); n_out3d.release(); out2d.release();
-    n_out2d.release(); hyp_of.release();
+    n_out2d.release(); hyp_of.release(); in_dense.release(); in_off.release(); off3.release(); off2.release();
+    c3d.release(); c2d.release();
+    if (totals) cudaFreeHost(totals);
+    totals = nullptr;
+    if (done) cudaEventDestroy(done);
+    done = nullptr;
     if (stream) cudaStreamDestroy(stream);
     stream = nullptr;
   }
@@ -289,6 +297,110 @@ int run_batch(ses3d_handle_s* h, int stages, int n_frames, int p_max, const ses3
   return SES3D_OK;
 }
 
+
+// Ragged variant of process_batch (host or device buffers): dense records in, dense records out.
+int run_ragged(ses3d_handle_s* h, int n_frames, int p_max, const ses3d_person2d* persons_dense,
+               const int32_t* n_persons, int h_max, ses3d_person_cov* out3d, long long cap3d, int32_t* n_out3d,
+               ses3d_person2d* out2d, long long cap2d, int32_t* n_out2d, long long* total3d, long long* total2d,
+               uint32_t flags) {
+  std::lock_guard<std::mutex> lock(h->mu);
+  CU(cudaSetDevice(h->device));
+  const int C = h->tb.n_cams;
+  *total3d = 0;
+  *total2d = 0;
+  if (n_frames == 0) return SES3D_OK;
+  const bool dev = (flags & SES3D_DEVICE_BUFFERS) != 0;
+  const cudaMemcpyKind in_kind = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  const cudaMemcpyKind out_kind = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  if (h->profiling) for (float& m : h->kernel_ms) m = 0.f;
+  CU(cudaMemsetAsync(h->d_overflow.p, 0, 4, h->slot[0].stream));
+  CU(cudaStreamSynchronize(h->slot[0].stream));
+  // per-frame input record counts are needed on the host to cut the dense input into chunks
+  std::vector<int32_t> counts_host;
+  const int32_t* counts = n_persons;
+  if (dev) {
+    counts_host.resize((size_t)n_frames * C);
+    CU(cudaMemcpy(counts_host.data(), n_persons, counts_host.size() * 4, cudaMemcpyDeviceToHost));
+    counts = counts_host.data();
+  }
+  const int chunk = std::max(1, std::min(4096, std::max(512, (n_frames + 3) / 4)));
+  long long in_done = 0, run3 = 0, run2 = 0;
+  struct Pending { int slot; bool active; } prev{0, false};
+  int status = SES3D_OK;
+
+  auto finish = [&](const Pending& pd) -> int {  // totals known -> copy the dense results out
+    Slot& s = h->slot[pd.slot];
+    CU(cudaEventSynchronize(s.done));
+    const long long t3 = s.totals[0], t2 = s.totals[1];
+    if (run3 + t3 > cap3d || run2 + t2 > cap2d) return fail(SES3D_E_CAPACITY, "ragged output buffer too small");
+    if (t3) CU(cudaMemcpyAsync(out3d + run3, s.c3d.p, (size_t)t3 * sizeof(ses3d_person_cov), out_kind, s.stream));
+    if (t2) CU(cudaMemcpyAsync(out2d + run2, s.c2d.p, (size_t)t2 * sizeof(ses3d_person2d), out_kind, s.stream));
+    run3 += t3;
+    run2 += t2;
+    return SES3D_OK;
+  };
+
+  int ci = 0;
+  for (int f0 = 0; f0 < n_frames && status == SES3D_OK; f0 += chunk, ++ci) {
+    const int nf = std::min(chunk, n_frames - f0);
+    Slot& s = h->slot[ci & 1];
+    cudaStream_t st = s.stream;
+    long long n_in = 0;
+    for (size_t i = (size_t)f0 * C; i < (size_t)(f0 + nf) * C; ++i) n_in += std::min(std::max(counts[i], 0), p_max);
+    const size_t u_in = (size_t)nf * C;
+    CU(s.persons.ensure(u_in * p_max * sizeof(ses3d_person2d)));
+    CU(s.n_persons.ensure(u_in * 4));
+    CU(s.in_dense.ensure((size_t)std::max<long long>(n_in, 1) * sizeof(ses3d_person2d)));
+    CU(s.in_off.ensure((u_in + 1) * 8));
+    CU(s.out3d.ensure((size_t)nf * h_max * sizeof(ses3d_person_cov)));
+    CU(s.n_out3d.ensure((size_t)nf * 4));
+    CU(s.out2d.ensure(u_in * h_max * sizeof(ses3d_person2d)));
+    CU(s.n_out2d.ensure(u_in * 4));
+    CU(s.off3.ensure(((size_t)nf + 1) * 8));
+    CU(s.off2.ensure((u_in + 1) * 8));
+    CU(s.c3d.ensure((size_t)nf * h_max * sizeof(ses3d_person_cov)));
+    CU(s.c2d.ensure(u_in * h_max * sizeof(ses3d_person2d)));
+    CU(cudaMemcpyAsync(s.n_persons.p, n_persons + (size_t)f0 * C, u_in * 4, in_kind, st));
+    if (n_in) CU(cudaMemcpyAsync(s.in_dense.p, persons_dense + in_done, (size_t)n_in * sizeof(ses3d_person2d), in_kind, st));
+    in_done += n_in;
+    CU(ses3d::launch_scan_counts(s.n_persons.as<int32_t>(), (int)u_in, p_max, s.in_off.as<long long>(), st));
+    CU(ses3d::launch_move_records(1, (int)u_in, p_max, (int)sizeof(ses3d_person2d), s.n_persons.as<int32_t>(),
+                                  s.in_off.as<long long>(), s.persons.p, s.in_dense.p, st));
+    int rc = triangulate_on_device(h, s.sc, st, nf, p_max, h_max, s.persons.as<ses3d_person2d>(),
+                                   s.n_persons.as<int32_t>(), s.out3d.as<ses3d_person_cov>(), s.n_out3d.as<int32_t>(),
+                                   nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    rc = reproject_on_device(h, st, nf, h_max, s.out3d.as<ses3d_person_cov>(), s.n_out3d.as<int32_t>(),
+                             s.out2d.as<ses3d_person2d>(), s.n_out2d.as<int32_t>());
+    if (rc) return rc;
+    CU(ses3d::launch_scan_counts(s.n_out3d.as<int32_t>(), nf, h_max, s.off3.as<long long>(), st));
+    CU(ses3d::launch_move_records(0, nf, h_max, (int)sizeof(ses3d_person_cov), s.n_out3d.as<int32_t>(),
+                                  s.off3.as<long long>(), s.out3d.p, s.c3d.p, st));
+    CU(ses3d::launch_scan_counts(s.n_out2d.as<int32_t>(), (int)u_in, h_max, s.off2.as<long long>(), st));
+    CU(ses3d::launch_move_records(0, (int)u_in, h_max, (int)sizeof(ses3d_person2d), s.n_out2d.as<int32_t>(),
+                                  s.off2.as<long long>(), s.out2d.p, s.c2d.p, st));
+    h->launches += 6;
+    CU(cudaMemcpyAsync(&s.totals[0], s.off3.as<long long>() + nf, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&s.totals[1], s.off2.as<long long>() + u_in, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(n_out3d + f0, s.n_out3d.p, (size_t)nf * 4, out_kind, st));
+    CU(cudaMemcpyAsync(n_out2d + (size_t)f0 * C, s.n_out2d.p, u_in * 4, out_kind, st));
+    CU(cudaEventRecord(s.done, st));
+    if (prev.active) status = finish(prev);   // overlaps with the chunk just enqueued
+    prev = Pending{ci & 1, true};
+  }
+  if (status == SES3D_OK && prev.active) status = finish(prev);
+  CU(cudaStreamSynchronize(h->slot[0].stream));
+  CU(cudaStreamSynchronize(h->slot[1].stream));
+  resolve_events(h);
+  if (status != SES3D_OK) return status;
+  int32_t overflow = 0;
+  CU(cudaMemcpy(&overflow, h->d_overflow.p, 4, cudaMemcpyDeviceToHost));
+  if (overflow) return fail(SES3D_E_CAPACITY, "a frame produced more hypotheses than h_max");
+  *total3d = run3;
+  *total2d = run2;
+  return SES3D_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -345,7 +457,11 @@ int ses3d_create(int32_t n_cams, const ses3d_camera* cams, const ses3d_params* p
   if (ue == cudaSuccess) ue = upload(h->d_F, h->host.F.data(), h->host.F.size() * sizeof(float));
   if (ue == cudaSuccess) ue = upload(h->d_frow, h->host.f_row.data(), h->host.f_row.size() * sizeof(int));
   if (ue == cudaSuccess) ue = h->d_overflow.ensure(4);
-  for (int i = 0; i < 2 && ue == cudaSuccess; ++i) ue = cudaStreamCreateWithFlags(&h->slot[i].stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 2 && ue == cudaSuccess; ++i) {
+    ue = cudaStreamCreateWithFlags(&h->slot[i].stream, cudaStreamNonBlocking);
+    if (ue == cudaSuccess) ue = cudaMallocHost(reinterpret_cast<void**>(&h->slot[i].totals), 2 * sizeof(long long));
+    if (ue == cudaSuccess) ue = cudaEventCreateWithFlags(&h->slot[i].done, cudaEventDisableTiming);
+  }
   if (ue != cudaSuccess) {
     ses3d_destroy(h);
     return cuda_fail(ue, "ses3d_create upload");
@@ -408,6 +524,22 @@ int ses3d_process_batch(ses3d_handle h, int32_t n_frames, int32_t p_max, const s
     return fail(SES3D_E_INVALID, "device-buffer calls need out3d/n_out3d (the PersonCov list lives there)");
   return run_batch(h, TRI | REP, n_frames, p_max, persons, n_persons, h_max, out3d, n_out3d, out2d, n_out2d, dump,
                    flags, stream);
+}
+
+int ses3d_process_batch_ragged(ses3d_handle h, int32_t n_frames, int32_t p_max, const ses3d_person2d* persons_dense,
+                               const int32_t* n_persons, int32_t h_max, ses3d_person_cov* out3d, int64_t cap3d,
+                               int32_t* n_out3d, ses3d_person2d* out2d, int64_t cap2d, int32_t* n_out2d,
+                               int64_t* total3d, int64_t* total2d, uint32_t flags) {
+  int rc = check_dims(h, n_frames, p_max, h_max);
+  if (rc) return rc;
+  if (!total3d || !total2d) return fail(SES3D_E_INVALID, "null totals");
+  if (n_frames > 0 && (!n_persons || !out3d || !n_out3d || !out2d || !n_out2d)) return fail(SES3D_E_INVALID, "null buffer");
+  long long t3 = 0, t2 = 0;
+  rc = run_ragged(h, n_frames, p_max, persons_dense, n_persons, h_max, out3d, cap3d, n_out3d, out2d, cap2d, n_out2d,
+                  &t3, &t2, flags);
+  *total3d = t3;
+  *total2d = t2;
+  return rc;
 }
 
 int ses3d_reserve(ses3d_handle h, int32_t n_frames, int32_t p_max, int32_t h_max) {

@@ -29,4 +29,10 @@ cudaError_t launch_finalize(const Tables& tb, LaunchDims d, const int32_t* n_hyp
 cudaError_t launch_reproject(const Tables& tb, int n_frames, int h_max, const ses3d_person_cov* persons3d,
                              const int32_t* n_persons3d, ses3d_person2d* out, int32_t* n_out, cudaStream_t st);
 
+// ragged <-> padded record movement (kernels_pack.cu)
+cudaError_t launch_scan_counts(const int32_t* counts, int n, int cap, long long* offsets, cudaStream_t st);
+cudaError_t launch_move_records(int direction /*0 pack, 1 unpack*/, int n_units, int cap, int rec_bytes,
+                                const int32_t* counts, const long long* offsets, void* strided, void* dense,
+                                cudaStream_t st);
+
 }  // namespace ses3d

@@ -218,3 +218,32 @@ def test_multi_chunk_batches_and_reuse_of_the_handle():
     assert a["persons3d"].tobytes() == b["persons3d"].tobytes() and a["persons2d"].tobytes() == b["persons2d"].tobytes()
     ro = Oracle(fr["cameras"], ref_hungarian=True).triangulate_batch(fr["persons"], fr["n_persons"], 4, n_threads=8)
     helpers.compare_persons3d(ro, dict(persons3d=a["persons3d"], n_out=a["n_out3d"]), POS_TOL_FP32)
+
+
+def test_ragged_batch_call_equals_padded_call():
+    """ses3d_process_batch_ragged: dense records in/out, same results as the padded call, several chunks."""
+    from smartedgesensor3dhumanpose_b200.layouts import person2d_dtype, person_cov_dtype
+    fr = helpers.make_workload("cfg2_hall16x6", 3000)
+    gpu = api.GeometryPipeline(fr["cameras"])
+    h_max, p_max = fr["h_max"], fr["persons"].shape[2]
+    pad = gpu.process_batch(fr["persons"], fr["n_persons"], h_max)
+    dense_in = api.to_ragged(fr["persons"], fr["n_persons"])
+    t3e, t2e = int(pad["n_out3d"].sum()), int(pad["n_out2d"].sum())
+    out3d = np.zeros(t3e + 5, person_cov_dtype)
+    out2d = np.zeros(t2e + 5, person2d_dtype)
+    n3 = np.zeros(3000, np.int32)
+    n2 = np.zeros((3000, 16), np.int32)
+    t3, t2 = gpu.process_batch_ragged(dense_in, fr["n_persons"], p_max, h_max, out3d, n3, out2d, n2)
+    assert (t3, t2) == (t3e, t2e)
+    assert np.array_equal(n3, pad["n_out3d"]) and np.array_equal(n2, pad["n_out2d"])
+    live3 = np.arange(h_max)[None, :] < n3[:, None]
+    assert out3d[:t3].tobytes() == pad["persons3d"][live3].tobytes()
+    live2 = np.arange(h_max)[None, None, :] < n2[:, :, None]
+    assert out2d[:t2].tobytes() == pad["persons2d"][live2].tobytes()
+    back = api.from_ragged(out3d, n3, h_max, person_cov_dtype)
+    assert back[live3].tobytes() == pad["persons3d"][live3].tobytes()
+    # too-small output capacity is reported, not overrun
+    from smartedgesensor3dhumanpose_b200.lib import Ses3dError
+    with pytest.raises(Ses3dError) as ei:
+        gpu.process_batch_ragged(dense_in, fr["n_persons"], p_max, h_max, out3d[:10], n3, out2d, n2)
+    assert ei.value.code == -3

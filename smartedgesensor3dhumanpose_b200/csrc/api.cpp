@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -92,7 +93,8 @@ struct ses3d_handle_s {
   ses3d::HostTables host;
   DevBuf d_camf, d_camd, d_F, d_frow, d_overflow;
   ses3d::Tables tb;
-  Slot slot[2];
+  static constexpr int kSlots = 3;   // H2D of chunk i+1, kernels of chunk i and D2H of chunk i-1 overlap
+  Slot slot[kSlots];
   std::mutex mu;
   int64_t launches = 0;
   bool profiling = false;
@@ -201,7 +203,7 @@ int check_dims(const ses3d_handle_s* h, int n_frames, int p_max, int h_max) {
   return SES3D_OK;
 }
 
-int host_chunk_frames(int n_frames) { return std::max(1, std::min(8192, std::max(1024, (n_frames + 3) / 4))); }
+int host_chunk_frames(int n_frames) { return std::max(1, std::min(8192, std::max(1024, (n_frames + 5) / 6))); }
 
 enum Stage { TRI = 1, REP = 2 };
 
@@ -246,7 +248,7 @@ int run_batch(ses3d_handle_s* h, int stages, int n_frames, int p_max, const ses3
   int ci = 0;
   for (int f0 = 0; f0 < n_frames; f0 += chunk, ++ci) {
     const int nf = std::min(chunk, n_frames - f0);
-    Slot& s = h->slot[ci & 1];
+    Slot& s = h->slot[ci % ses3d_handle_s::kSlots];
     cudaStream_t st = s.stream;
     CU(s.out3d.ensure((size_t)nf * h_max * sizeof(ses3d_person_cov)));
     CU(s.n_out3d.ensure((size_t)nf * 4));
@@ -288,8 +290,7 @@ int run_batch(ses3d_handle_s* h, int stages, int n_frames, int p_max, const ses3
       CU(cudaMemcpyAsync(n_out2d + (size_t)f0 * C, s.n_out2d.p, (size_t)nf * C * 4, cudaMemcpyDeviceToHost, st));
     }
   }
-  CU(cudaStreamSynchronize(h->slot[0].stream));
-  CU(cudaStreamSynchronize(h->slot[1].stream));
+  for (Slot& sl : h->slot) CU(cudaStreamSynchronize(sl.stream));
   resolve_events(h);
   int32_t overflow = 0;
   CU(cudaMemcpy(&overflow, h->d_overflow.p, 4, cudaMemcpyDeviceToHost));
@@ -323,7 +324,8 @@ int run_ragged(ses3d_handle_s* h, int n_frames, int p_max, const ses3d_person2d*
     CU(cudaMemcpy(counts_host.data(), n_persons, counts_host.size() * 4, cudaMemcpyDeviceToHost));
     counts = counts_host.data();
   }
-  const int chunk = std::max(1, std::min(4096, std::max(512, (n_frames + 3) / 4)));
+  int chunk = std::max(1, std::min(4096, std::max(512, (n_frames + 7) / 8)));
+  if (const char* env = std::getenv("SES3D_RAGGED_CHUNK")) chunk = std::max(1, std::atoi(env));
   long long in_done = 0, run3 = 0, run2 = 0;
   struct Pending { int slot; bool active; } prev{0, false};
   int status = SES3D_OK;
@@ -343,7 +345,7 @@ int run_ragged(ses3d_handle_s* h, int n_frames, int p_max, const ses3d_person2d*
   int ci = 0;
   for (int f0 = 0; f0 < n_frames && status == SES3D_OK; f0 += chunk, ++ci) {
     const int nf = std::min(chunk, n_frames - f0);
-    Slot& s = h->slot[ci & 1];
+    Slot& s = h->slot[ci % ses3d_handle_s::kSlots];
     cudaStream_t st = s.stream;
     long long n_in = 0;
     for (size_t i = (size_t)f0 * C; i < (size_t)(f0 + nf) * C; ++i) n_in += std::min(std::max(counts[i], 0), p_max);
@@ -386,11 +388,10 @@ int run_ragged(ses3d_handle_s* h, int n_frames, int p_max, const ses3d_person2d*
     CU(cudaMemcpyAsync(n_out2d + (size_t)f0 * C, s.n_out2d.p, u_in * 4, out_kind, st));
     CU(cudaEventRecord(s.done, st));
     if (prev.active) status = finish(prev);   // overlaps with the chunk just enqueued
-    prev = Pending{ci & 1, true};
+    prev = Pending{ci % ses3d_handle_s::kSlots, true};
   }
   if (status == SES3D_OK && prev.active) status = finish(prev);
-  CU(cudaStreamSynchronize(h->slot[0].stream));
-  CU(cudaStreamSynchronize(h->slot[1].stream));
+  for (Slot& sl : h->slot) CU(cudaStreamSynchronize(sl.stream));
   resolve_events(h);
   if (status != SES3D_OK) return status;
   int32_t overflow = 0;
@@ -457,7 +458,7 @@ int ses3d_create(int32_t n_cams, const ses3d_camera* cams, const ses3d_params* p
   if (ue == cudaSuccess) ue = upload(h->d_F, h->host.F.data(), h->host.F.size() * sizeof(float));
   if (ue == cudaSuccess) ue = upload(h->d_frow, h->host.f_row.data(), h->host.f_row.size() * sizeof(int));
   if (ue == cudaSuccess) ue = h->d_overflow.ensure(4);
-  for (int i = 0; i < 2 && ue == cudaSuccess; ++i) {
+  for (int i = 0; i < ses3d_handle_s::kSlots && ue == cudaSuccess; ++i) {
     ue = cudaStreamCreateWithFlags(&h->slot[i].stream, cudaStreamNonBlocking);
     if (ue == cudaSuccess) ue = cudaMallocHost(reinterpret_cast<void**>(&h->slot[i].totals), 2 * sizeof(long long));
     if (ue == cudaSuccess) ue = cudaEventCreateWithFlags(&h->slot[i].done, cudaEventDisableTiming);

@@ -161,50 +161,146 @@ SES_HD void smallest_eigvec4(const double g[10], T v[4]) {
   v[0] += poison; v[1] += poison; v[2] += poison; v[3] += poison;
 }
 
-// Full decomposition g = V diag(lam) V^T; V row-major, column c = eigenvector c. Also returns
-// the smallest eigenvector (for free). Used once per joint as the basis for the warm solves.
+// ---- fast path: inverse iteration + deflated secular solve ----------------------------------------
+// The DLT normal matrix has one tiny eigenvalue (the squared residual) well separated from the other
+// three, so (a) inverse iteration finds its eigenvector in 2-3 LDL^T solves instead of 5-7 Jacobi
+// sweeps, and (b) a sigma point - the base system plus a rank-<=4 update - is solved in the basis
+// [v | Q] (v = base eigenvector, Q = Householder complement) where the matrix is [[a, b^T], [b, C]]
+// with small b: the eigenvector is (1, x), (C - lambda I) x = -b, lambda the smallest root of the
+// secular equation a - lambda - b^T (C - lambda I)^-1 b = 0 (Newton from lambda = a converges
+// monotonically because the function is concave and decreasing left of C's spectrum). Every routine
+// reports failure (non-positive pivot, no convergence, NaN) and the caller falls back to Jacobi.
+SES_HD float ses_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+  return __fdividef(1.0f, x);
+#else
+  return 1.0f / x;
+#endif
+}
+SES_HD double ses_rcp(double x) { return 1.0 / x; }
+SES_HD float ses_rsqrt(float x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrtf(x);
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+SES_HD double ses_rsqrt(double x) { return 1.0 / sqrt(x); }
+
+// Smallest eigenvector (unit length) of the symmetric PSD 4x4 matrix G by inverse iteration.
 template <class T>
-SES_HD void eig4_full(const double g[10], T lam[4], T V[16], T v[4]) {
-  Sym4V<T> m;
-  sym4_load(m, g);
-  jacobi4(m);
-  lam[0] = m.a00; lam[1] = m.a11; lam[2] = m.a22; lam[3] = m.a33;
-  V[0] = m.v00; V[1] = m.v01; V[2] = m.v02; V[3] = m.v03; V[4] = m.v10; V[5] = m.v11; V[6] = m.v12; V[7] = m.v13;
-  V[8] = m.v20; V[9] = m.v21; V[10] = m.v22; V[11] = m.v23; V[12] = m.v30; V[13] = m.v31; V[14] = m.v32; V[15] = m.v33;
-  sym4_smallest(m, v);
-  const T poison = (T)nan_poison(g);
-  v[0] += poison; v[1] += poison; v[2] += poison; v[3] += poison;
-  lam[0] += poison;
+SES_HD bool invit4(const double G[10], T v[4]) {
+  const T g00 = (T)G[0], g01 = (T)G[1], g02 = (T)G[2], g03 = (T)G[3], g11 = (T)G[4], g12 = (T)G[5], g13 = (T)G[6],
+          g22 = (T)G[7], g23 = (T)G[8], g33 = (T)G[9];
+  const T rel = sizeof(T) == 4 ? T(1e-5) : T(1e-11);     // leading pivots must stay clear of rounding noise
+  const T tol2 = sizeof(T) == 4 ? T(4e-12) : T(1e-26);   // squared change of the unit iterate
+  if (!(g00 > T(0))) return false;
+  const T i0 = ses_rcp(g00);
+  const T l10 = g01 * i0, l20 = g02 * i0, l30 = g03 * i0;
+  const T d1 = g11 - l10 * g01;
+  if (!(d1 > rel * g11)) return false;
+  const T i1 = ses_rcp(d1);
+  const T t21 = g12 - l20 * g01, t31 = g13 - l30 * g01;
+  const T l21 = t21 * i1, l31 = t31 * i1;
+  const T d2 = g22 - l20 * g02 - l21 * t21;
+  if (!(d2 > rel * g22)) return false;
+  const T i2 = ses_rcp(d2);
+  const T t32 = g23 - l30 * g02 - l31 * t21;
+  const T l32 = t32 * i2;
+  T d3 = g33 - l30 * g03 - l31 * t31 - l32 * t32;   // ~ the tiny eigenvalue; may round to <= 0, which is fine
+  const T floor3 = g33 * (sizeof(T) == 4 ? T(1e-15) : T(1e-30));
+  if (ses_abs(d3) < floor3) d3 = floor3;
+  const T i3 = ses_rcp(d3);
+  T x0 = 0, x1 = 0, x2 = 0, x3 = 1;
+  for (int it = 0; it < 6; ++it) {
+    // L z = x, z /= d, L^T y = z
+    T z0 = x0;
+    T z1 = x1 - l10 * z0;
+    T z2 = x2 - l20 * z0 - l21 * z1;
+    T z3 = x3 - l30 * z0 - l31 * z1 - l32 * z2;
+    z0 *= i0; z1 *= i1; z2 *= i2; z3 *= i3;
+    const T y3 = z3;
+    const T y2 = z2 - l32 * y3;
+    const T y1 = z1 - l21 * y2 - l31 * y3;
+    const T y0 = z0 - l10 * y1 - l20 * y2 - l30 * y3;
+    const T n2 = (y0 * y0 + y1 * y1) + (y2 * y2 + y3 * y3);
+    if (!(n2 > T(0)) || !(n2 < T(1e30))) return false;
+    T inv = ses_rsqrt(n2);
+    if ((y0 * x0 + y1 * x1) + (y2 * x2 + y3 * x3) < T(0)) inv = -inv;
+    const T w0 = y0 * inv, w1 = y1 * inv, w2 = y2 * inv, w3 = y3 * inv;
+    const T e0 = w0 - x0, e1 = w1 - x1, e2 = w2 - x2, e3 = w3 - x3;
+    x0 = w0; x1 = w1; x2 = w2; x3 = w3;
+    if ((e0 * e0 + e1 * e1) + (e2 * e2 + e3 * e3) < tol2) {
+      v[0] = x0; v[1] = x1; v[2] = x2; v[3] = x3;
+      return true;
+    }
+  }
+  return false;
 }
 
-// q = V^T r in double (V, r exact in double): the row expressed in the eigenbasis of the base system.
+// Smallest eigenvector: inverse iteration, Jacobi when it declines.
 template <class T>
-SES_HD void to_eigenbasis(const T V[16], const T r[4], double q[4]) {
-  for (int c = 0; c < 4; ++c)
-    q[c] = (double)V[c] * (double)r[0] + (double)V[4 + c] * (double)r[1] + (double)V[8 + c] * (double)r[2] +
-           (double)V[12 + c] * (double)r[3];
-}
-SES_HD void gram_add_d(double G[10], const double q[4], double sign) {
-  const double sa = sign * q[0], sb = sign * q[1], sc = sign * q[2], sd = sign * q[3];
-  G[0] += sa * q[0]; G[1] += sa * q[1]; G[2] += sa * q[2]; G[3] += sa * q[3];
-  G[4] += sb * q[1]; G[5] += sb * q[2]; G[6] += sb * q[3];
-  G[7] += sc * q[2]; G[8] += sc * q[3];
-  G[9] += sd * q[3];
+SES_HD void smallest_eigvec4_fast(const double G[10], T v[4]) {
+  if (!invit4<T>(G, v)) smallest_eigvec4<T>(G, v);
 }
 
-// Warm solve: gp is the perturbed normal matrix expressed in the eigenbasis V0 of the base
-// system (diag(lam0) + small symmetric update), so Jacobi starts almost diagonal and needs
-// 1-3 sweeps instead of 5-7. Returns the smallest eigenvector in the original basis.
+// Coordinates of a row r in the basis [v | Q]: s = r.v and p = Q^T r, with Q the Householder
+// complement of the unit vector v built around the 4th axis (u = v + sign(v3) e3, never cancels).
 template <class T>
-SES_HD void smallest_eigvec4_warm(const double gp[10], const T V0[16], T v[4]) {
-  Sym4V<T> m;
-  sym4_load(m, gp);
-  jacobi4(m);
-  T w[4];
-  sym4_smallest(m, w);
-  const T poison = (T)nan_poison(gp);
-  for (int r = 0; r < 4; ++r)
-    v[r] = V0[r * 4] * w[0] + V0[r * 4 + 1] * w[1] + V0[r * 4 + 2] * w[2] + V0[r * 4 + 3] * w[3] + poison;
+SES_HD void deflate_project(const T v[4], const T r[4], T& s, T p[3]) {
+  const T sg = v[3] >= T(0) ? T(1) : T(-1);
+  const T kappa = ses_rcp(T(1) + ses_abs(v[3]));
+  s = (r[0] * v[0] + r[1] * v[1]) + (r[2] * v[2] + r[3] * v[3]);
+  const T c = kappa * (s + sg * r[3]);
+  p[0] = r[0] - c * v[0]; p[1] = r[1] - c * v[1]; p[2] = r[2] - c * v[2];
+}
+
+// w = v + Q x  (back to the original basis)
+template <class T>
+SES_HD void deflate_expand(const T v[4], const T x[3], T w[4]) {
+  const T sg = v[3] >= T(0) ? T(1) : T(-1);
+  const T kappa = ses_rcp(T(1) + ses_abs(v[3]));
+  const T c = kappa * (x[0] * v[0] + x[1] * v[1] + x[2] * v[2]);
+  w[0] = v[0] + x[0] - c * v[0];
+  w[1] = v[1] + x[1] - c * v[1];
+  w[2] = v[2] + x[2] - c * v[2];
+  w[3] = v[3] - c * (v[3] + sg);
+}
+
+// Smallest eigenpair of [[a, b^T], [b, C]] (C: 00 01 02 11 12 22) as (1, x); see the block comment above.
+template <class T>
+SES_HD bool secular_smallest(T a, const T b[3], const T C[6], T x[3]) {
+  const T conv = sizeof(T) == 4 ? T(2e-6) : T(1e-13);
+  T lam = a;
+  for (int it = 0; it < 5; ++it) {
+    const T m00 = C[0] - lam;
+    if (!(m00 > T(0))) return false;
+    const T i0 = ses_rcp(m00);
+    const T l10 = C[1] * i0, l20 = C[2] * i0;
+    const T m11 = C[3] - lam - l10 * C[1];
+    if (!(m11 > T(0))) return false;
+    const T i1 = ses_rcp(m11);
+    const T t21 = C[4] - l20 * C[1];
+    const T l21 = t21 * i1;
+    const T m22 = C[5] - lam - l20 * C[2] - l21 * t21;
+    if (!(m22 > T(0))) return false;
+    const T i2 = ses_rcp(m22);
+    T z0 = b[0];
+    T z1 = b[1] - l10 * z0;
+    T z2 = b[2] - l20 * z0 - l21 * z1;
+    z0 *= i0; z1 *= i1; z2 *= i2;
+    const T y2 = z2;
+    const T y1 = z1 - l21 * y2;
+    const T y0 = z0 - l10 * y1 - l20 * y2;
+    x[0] = -y0; x[1] = -y1; x[2] = -y2;
+    const T f = a - lam - (b[0] * y0 + b[1] * y1 + b[2] * y2);
+    const T dl = f * ses_rcp(T(1) + (y0 * y0 + y1 * y1 + y2 * y2));
+    // x changes by ~ |y| / m_min * |dl|: stop once that is below the working precision
+    const T mmin = m00 < m11 ? (m00 < m22 ? m00 : m22) : (m11 < m22 ? m11 : m22);
+    if (ses_abs(dl) <= conv * mmin) return true;
+    lam += dl;
+  }
+  return false;
 }
 
 // projection residual of one view, S3D:430-433

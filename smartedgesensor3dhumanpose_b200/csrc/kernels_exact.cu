@@ -4,6 +4,9 @@
 // x86-64 (SSE2, no FMA) arithmetic, and finalize/reproject are FP64 paths whose results
 // then match the CPU oracle bit for bit as well. The algorithms live in *_core.h; this
 // file only binds a CTA to a frame and carves the shared-memory workspace.
+#include <algorithm>
+#include <cstdlib>
+
 #include "assoc_core.h"
 #include "fin_core.h"
 #include "launch.h"
@@ -102,7 +105,8 @@ cudaError_t launch_associate(const Tables& tb, LaunchDims d, const ses3d_person2
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(work_count, 0, sizeof(int32_t), st);
   if (e != cudaSuccess) return e;
-  const int threads = (tb.n_cams * d.p_max >= 256) ? 128 : 64;
+  int threads = (tb.n_cams * d.p_max >= 256) ? 128 : 64;
+  if (const char* env = getenv("SES3D_ASSOC_THREADS")) threads = std::max(32, std::min(128, atoi(env) / 32 * 32));
   k_associate<<<d.n_frames, threads, smem, st>>>(tb, d.n_frames, d.p_max, d.h_cap, persons, n_persons,
                                                  scratch ? nk_scratch : nullptr, hyp_det, n_hyp, n_hung, overflow,
                                                  hyp_of_dump, keep, work, work_count);

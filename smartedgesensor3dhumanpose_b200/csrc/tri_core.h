@@ -42,8 +42,7 @@ struct TriWs {
   T* jX;              // [17][3]
   double* jerr;       // [17]
   float* jscore;      // [17]
-  T* V0;              // [17][16] eigenbasis of the unweighted base system
-  T* lam0;            // [17][4]  its eigenvalues
+  T* defl;            // [17][14] deflated base system: v[4], a0, b0[3], C0[6]
   T* cov;             // [17][6]  running covariance sums
   int* soff;          // [18] sample offsets (sample 0 of each joint is the base solve, already known)
   T* Y;               // [Y_CHUNK][3] transformed sigma points of the current pass  (aliases the LOO scratch)
@@ -63,8 +62,7 @@ SES_HD void tri_ws_layout(A& ar, int C, TriWs<T>* ws) {
   double* u = ar.template take<double>((u_bytes + 7) / 8);
   ViewKp<T>* vw = ar.template take<ViewKp<T>>((size_t)C * NKP);
   T* jX = ar.template take<T>(NKP * 3);
-  T* V0 = ar.template take<T>(NKP * 16);
-  T* lam0 = ar.template take<T>(NKP * 4);
+  T* defl = ar.template take<T>(NKP * 14);
   T* cov = ar.template take<T>(NKP * 6);
   float* jscore = ar.template take<float>(NKP);
   int* jn = ar.template take<int>(NKP);
@@ -77,7 +75,7 @@ SES_HD void tri_ws_layout(A& ar, int C, TriWs<T>* ws) {
   if (ws) {
     ws->jerr = jerr; ws->kp = kp; ws->Y = reinterpret_cast<T*>(u);
     ws->looErr = u; ws->looX = reinterpret_cast<T*>(u + loo_cap); ws->loo_cap = loo_cap;
-    ws->vw = vw; ws->jX = jX; ws->V0 = V0; ws->lam0 = lam0; ws->cov = cov; ws->jscore = jscore; ws->jn = jn;
+    ws->vw = vw; ws->jX = jX; ws->defl = defl; ws->cov = cov; ws->jscore = jscore; ws->jn = jn;
     ws->jflag = jflag; ws->soff = soff; ws->scal = scal; ws->vlist = vlist; ws->obs_cam = obs_cam; ws->obs_det = obs_det;
   }
 }
@@ -165,7 +163,7 @@ SES_HD void solve_weighted(const Tables& tb, const TriWs<T>& ws, int k, const ui
     dlt_row<T>(P, 1, v.y, v.conf, true, r); gram_add<T>(G, r, 1.0);
   }
   T e[4];
-  smallest_eigvec4<T>(G, e);
+  smallest_eigvec4_fast<T>(G, e);
   X[0] = e[0] / e[3]; X[1] = e[1] / e[3]; X[2] = e[2] / e[3];
   *err = reproj_error<T>(tb, ws, k, list, n, skip, X);
 }
@@ -407,7 +405,27 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
       dlt_row_fast<T>(P, 1, v.y, r); gram_add<T>(G, r, 1.0);
     }
     T e[4];
-    eig4_full<T>(G, ws.lam0 + k * 4, ws.V0 + k * 16, e);
+    smallest_eigvec4_fast<T>(G, e);
+    // base system in the deflated basis [e | Q]: a0 = e^T G e, b0 = Q^T G e (~0), C0 = Q^T G Q
+    T a0 = 0, b0[3] = {0, 0, 0}, C0[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < n; ++i) {
+      const int o = list[i];
+      const ViewKp<T>& v = ws.vw[o * NKP + k];
+      const T* P = CamSel<T>::P(tb, ws.obs_cam[o]);
+      for (int which = 0; which < 2; ++which) {
+        T r[4], sr, p[3];
+        dlt_row_fast<T>(P, which, which == 0 ? v.x : v.y, r);
+        deflate_project<T>(e, r, sr, p);
+        a0 += sr * sr;
+        b0[0] += sr * p[0]; b0[1] += sr * p[1]; b0[2] += sr * p[2];
+        C0[0] += p[0] * p[0]; C0[1] += p[0] * p[1]; C0[2] += p[0] * p[2];
+        C0[3] += p[1] * p[1]; C0[4] += p[1] * p[2]; C0[5] += p[2] * p[2];
+      }
+    }
+    T* df = ws.defl + k * 14;
+    df[0] = e[0]; df[1] = e[1]; df[2] = e[2]; df[3] = e[3]; df[4] = a0;
+    df[5] = b0[0]; df[6] = b0[1]; df[7] = b0[2];
+    for (int i = 0; i < 6; ++i) df[8 + i] = C0[i];
     // sigma point 0 (unperturbed, unweighted) contributes w0 * (y0 - m)(y0 - m)^T   (S3D:521-522)
     const T wden = T(2) * (T(2 * n) + T(0.5));
     const T w0 = (T(2) * T(0.5)) / wden;
@@ -438,7 +456,7 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
       const int cam = ws.obs_cam[o];
       const ViewKp<T>& v = ws.vw[o * NKP + k];
       const T* P = CamSel<T>::P(tb, cam);
-      const T* V0 = ws.V0 + k * 16;
+      const T* df = ws.defl + k * 14;
       T l11, l21, l22;
       cholesky_cov(tb, cam, persons[cam * p_max + ws.obs_det[o]].keypoints[k], l11, l21, l22);
       const T b = ses_sqrt(T(2 * n) + T(0.5));  // sqrt(dim + kappa), S3D:500
@@ -447,19 +465,37 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
       else if (m == 1) { ny = v.y - l22 * b; }
       else if (m == 2) { nx = v.x + l11 * b; ny = v.y + l21 * b; }
       else { ny = v.y + l22 * b; }
-      // normal matrix in the eigenbasis of the base system: diag(lam0) - old rows + new rows
-      double G[10] = {(double)ws.lam0[k * 4], 0, 0, 0, (double)ws.lam0[k * 4 + 1], 0, 0, (double)ws.lam0[k * 4 + 2], 0,
-                      (double)ws.lam0[k * 4 + 3]};
-      T r[4];
-      double q[4];
-      if ((m & 1) == 0) {
-        dlt_row_fast<T>(P, 0, v.x, r); to_eigenbasis<T>(V0, r, q); gram_add_d(G, q, -1.0);
-        dlt_row_fast<T>(P, 0, nx, r); to_eigenbasis<T>(V0, r, q); gram_add_d(G, q, 1.0);
+      // perturbed system in the deflated basis: base +/- the rows of the one view that moved
+      T a = df[4], bb[3] = {df[5], df[6], df[7]}, Cm[6] = {df[8], df[9], df[10], df[11], df[12], df[13]};
+      auto update = [&](int which, T coord, T sign) {
+        T r[4], sr, p[3];
+        dlt_row_fast<T>(P, which, coord, r);
+        deflate_project<T>(df, r, sr, p);
+        const T ss = sign * sr;
+        a += ss * sr;
+        bb[0] += ss * p[0]; bb[1] += ss * p[1]; bb[2] += ss * p[2];
+        const T q0 = sign * p[0], q1 = sign * p[1], q2 = sign * p[2];
+        Cm[0] += q0 * p[0]; Cm[1] += q0 * p[1]; Cm[2] += q0 * p[2];
+        Cm[3] += q1 * p[1]; Cm[4] += q1 * p[2]; Cm[5] += q2 * p[2];
+      };
+      if ((m & 1) == 0) { update(0, v.x, T(-1)); update(0, nx, T(1)); }
+      update(1, v.y, T(-1));
+      update(1, ny, T(1));
+      T e[4], xs[3];
+      if (secular_smallest<T>(a, bb, Cm, xs)) {
+        deflate_expand<T>(df, xs, e);
+      } else {  // rare: rebuild the full normal matrix of this sigma point and use Jacobi
+        double G[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int i2 = 0; i2 < n; ++i2) {
+          const int o2 = ws.vlist[k * C + i2];
+          const ViewKp<T>& v2 = ws.vw[o2 * NKP + k];
+          const T* P2 = CamSel<T>::P(tb, ws.obs_cam[o2]);
+          T r[4];
+          dlt_row_fast<T>(P2, 0, i2 == vi ? nx : v2.x, r); gram_add<T>(G, r, 1.0);
+          dlt_row_fast<T>(P2, 1, i2 == vi ? ny : v2.y, r); gram_add<T>(G, r, 1.0);
+        }
+        smallest_eigvec4<T>(G, e);
       }
-      dlt_row_fast<T>(P, 1, v.y, r); to_eigenbasis<T>(V0, r, q); gram_add_d(G, q, -1.0);
-      dlt_row_fast<T>(P, 1, ny, r); to_eigenbasis<T>(V0, r, q); gram_add_d(G, q, 1.0);
-      T e[4];
-      smallest_eigvec4_warm<T>(G, V0, e);
       const T inv = T(1) / e[3];
       ws.Y[ii * 3] = e[0] * inv; ws.Y[ii * 3 + 1] = e[1] * inv; ws.Y[ii * 3 + 2] = e[2] * inv;
     });

@@ -21,7 +21,8 @@ namespace ses3d {
 enum { SC_N_HYP = 0, SC_N_DET, SC_N_HUNG, SC_OVERFLOW, SC_CURSOR, SC_NOBS_SUM, SC_COUNT };
 
 struct AssocWs {
-  float* nk;          // [C*p_max][17][3] normalised keypoints x, y, conf ((0,0,-1) below threshold)
+  float* nk;          // [C*p_max][17][2] normalised keypoints x, y
+  uint32_t* kmask;    // [C*p_max] bit k: keypoint k has score > threshold (the strict test of calcCost, S3D:354)
   float* pscore;      // [C*p_max] Person2D.score
   uint8_t* valid;     // [C*p_max] more than 8 valid keypoints (S3D:579,599)
   uint8_t* hyp_nobs;  // [h_cap]
@@ -43,7 +44,7 @@ struct AssocWs {
 
 // triple mode is used when every round's (sum of observations) x (detections) fits this many entries
 SES_HD int assoc_triple_cap(int C, int p_max) {
-  const long cap = (long)C * p_max * p_max;
+  const long cap = (long)(C - 1) * p_max * p_max;   // (observations of all hypotheses) x (detections) of one round
   return cap <= 2048 ? (int)cap : 0;
 }
 
@@ -53,7 +54,8 @@ template <class A>
 SES_HD void assoc_ws_layout(A& ar, int C, int p_max, int h_cap, bool nk_inside, AssocWs* ws) {
   double* cost = ar.template take<double>((size_t)h_cap * p_max);
   double* dist = ar.template take<double>((size_t)h_cap * p_max);
-  float* nk = nk_inside ? ar.template take<float>((size_t)C * p_max * NKP * 3) : nullptr;
+  float* nk = nk_inside ? ar.template take<float>((size_t)C * p_max * NKP * 2) : nullptr;
+  uint32_t* kmask = ar.template take<uint32_t>((size_t)C * p_max);
   float* pscore = ar.template take<float>((size_t)C * p_max);
   int* assignment = ar.template take<int>(h_cap);
   int* scal = ar.template take<int>(SC_COUNT);
@@ -75,7 +77,7 @@ SES_HD void assoc_ws_layout(A& ar, int C, int p_max, int h_cap, bool nk_inside, 
   uint8_t* r2h = ar.template take<uint8_t>(tcap ? (size_t)C * p_max : 0);
   if (ws) {
     ws->obs_cost = obs_cost; ws->hoff = hoff; ws->obs_has = obs_has; ws->r2h = r2h; ws->triple_cap = tcap;
-    ws->cost = cost; ws->dist = dist; if (nk_inside) ws->nk = nk; ws->pscore = pscore;
+    ws->cost = cost; ws->dist = dist; if (nk_inside) ws->nk = nk; ws->kmask = kmask; ws->pscore = pscore;
     ws->assignment = assignment; ws->scal = scal; ws->hyp_obs = hyp_obs; ws->valid = valid;
     ws->hyp_nobs = hyp_nobs; ws->dets = dets; ws->mask = mask; ws->star = star; ws->prime = prime;
     ws->nstar = nstar; ws->cov_r = cov_r; ws->cov_c = cov_c; ws->handled = handled;
@@ -222,24 +224,29 @@ SES_HD void associate_frame(Team& tm, const Tables& tb, int p_max, int h_cap, co
   // normalize_keypoints for every detection of the frame (S3D:312-333)
   tm.pfor(C * p_max * NKP, [&](int i) {
     const int k = i % NKP, cd = i / NKP, c = cd / p_max, d = cd % p_max;
-    float* o = ws.nk + (size_t)i * 3;
-    o[0] = 0.f; o[1] = 0.f; o[2] = -1.f;
+    float* o = ws.nk + (size_t)i * 2;
+    o[0] = 0.f; o[1] = 0.f;
     if (d < np(c)) {
       const ses3d_keypoint2d& kp = persons[cd].keypoints[k];
       const CamF& cm = tb.camf[c];
       if (kp.score >= thr) {
         o[0] = (kp.x - cm.cx) / cm.fx;
         o[1] = (kp.y - cm.cy) / cm.fy;
-        o[2] = kp.score;
       }
     }
   });
   tm.pfor(C * p_max, [&](int cd) {
     const int c = cd / p_max, d = cd % p_max;
     int n_valid = 0;
+    uint32_t strict = 0;
     if (d < np(c))
-      for (int k = 0; k < NKP; ++k) n_valid += ws.nk[((size_t)cd * NKP + k) * 3 + 2] >= thr ? 1 : 0;
+      for (int k = 0; k < NKP; ++k) {
+        const float sc = persons[cd].keypoints[k].score;
+        n_valid += sc >= thr ? 1 : 0;                 // S3D:321
+        strict |= sc > thr ? (1u << k) : 0u;          // S3D:354 (normalised conf = score when >= thr, else -1)
+      }
     ws.valid[cd] = n_valid > NKP / 2 ? 1 : 0;
+    ws.kmask[cd] = strict;
     ws.pscore[cd] = d < np(c) ? persons[cd].score : 0.f;
   });
 
@@ -297,17 +304,19 @@ SES_HD void associate_frame(Team& tm, const Tables& tb, int p_max, int h_cap, co
       tm.pfor(S * n_det, [&](int t) {
         const int di = t / S, r = t % S;
         const int h = ws.r2h[r], o = r - ws.hoff[h];
-        const float* dk = ws.nk + ((size_t)(cam * p_max + ws.dets[di]) * NKP) * 3;
+        const int dslot = cam * p_max + ws.dets[di];
+        const float* dk = ws.nk + ((size_t)dslot * NKP) * 2;
         const int oc = ws.hyp_obs[(size_t)h * C + o] >> 8, od = ws.hyp_obs[(size_t)h * C + o] & 255;
         const float* F = tb.F + (size_t)fundamental_idx(tb, oc, cam) * 9;
-        const float* hk = ws.nk + ((size_t)(oc * p_max + od) * NKP) * 3;
+        const float* hk = ws.nk + ((size_t)(oc * p_max + od) * NKP) * 2;
         double cost = 0.;
+        uint32_t m = ws.kmask[oc * p_max + od] & ws.kmask[dslot];   // joints valid in both, ascending order
         int n_joints = 0;
-        for (int k = 0; k < NKP; ++k) {
-          if (hk[3 * k + 2] > thr && dk[3 * k + 2] > thr) {
-            cost += static_cast<double>(epipolar_symmetric(F, hk[3 * k], hk[3 * k + 1], dk[3 * k], dk[3 * k + 1]));
-            ++n_joints;
-          }
+        while (m) {
+          const int k = ses_ctz(m);
+          m &= m - 1;
+          cost += static_cast<double>(epipolar_symmetric(F, hk[2 * k], hk[2 * k + 1], dk[2 * k], dk[2 * k + 1]));
+          ++n_joints;
         }
         if (n_joints > 0) cost /= n_joints;
         ws.obs_cost[t] = cost;
@@ -342,7 +351,8 @@ SES_HD void associate_frame(Team& tm, const Tables& tb, int p_max, int h_cap, co
     // cost matrix, one (hypothesis, detection) entry per thread: calcCost S3D:335-390
     tm.pfor(n_hyp * n_det, [&](int e) {
       const int h = e % n_hyp, di = e / n_hyp;
-      const float* dk = ws.nk + ((size_t)(cam * p_max + ws.dets[di]) * NKP) * 3;
+      const int dslot = cam * p_max + ws.dets[di];
+      const float* dk = ws.nk + ((size_t)dslot * NKP) * 2;
       const int n_obs = ws.hyp_nobs[h];
       double total = 0., tmp_veto = 0.;
       int n_used = 0;
@@ -350,14 +360,15 @@ SES_HD void associate_frame(Team& tm, const Tables& tb, int p_max, int h_cap, co
       for (int o = 0; o < n_obs; ++o) {
         const int oc = ws.hyp_obs[(size_t)h * C + o] >> 8, od = ws.hyp_obs[(size_t)h * C + o] & 255;
         const float* F = tb.F + (size_t)fundamental_idx(tb, oc, cam) * 9;
-        const float* hk = ws.nk + ((size_t)(oc * p_max + od) * NKP) * 3;
+        const float* hk = ws.nk + ((size_t)(oc * p_max + od) * NKP) * 2;
         double cost = 0.;
+        uint32_t m = ws.kmask[oc * p_max + od] & ws.kmask[dslot];
         int n_joints = 0;
-        for (int k = 0; k < NKP; ++k) {
-          if (hk[3 * k + 2] > thr && dk[3 * k + 2] > thr) {
-            cost += static_cast<double>(epipolar_symmetric(F, hk[3 * k], hk[3 * k + 1], dk[3 * k], dk[3 * k + 1]));
-            ++n_joints;
-          }
+        while (m) {
+          const int k = ses_ctz(m);
+          m &= m - 1;
+          cost += static_cast<double>(epipolar_symmetric(F, hk[2 * k], hk[2 * k + 1], dk[2 * k], dk[2 * k + 1]));
+          ++n_joints;
         }
         if (n_joints > 0) {
           cost /= n_joints;

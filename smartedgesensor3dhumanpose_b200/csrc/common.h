@@ -62,6 +62,13 @@ SES_HD int fundamental_idx(const Tables& tb, int i, int j) { return tb.f_row[i] 
 template <class T> SES_HD T sum3(T a, T b, T c) { return a + (b + c); }
 template <class T> SES_HD T sum4(T a, T b, T c, T d) { return (a + b) + (c + d); }
 
+SES_HD int ses_ctz(uint32_t x) {  // index of the lowest set bit (x != 0)
+#if defined(__CUDA_ARCH__)
+  return __ffs((int)x) - 1;
+#else
+  return __builtin_ctz(x);
+#endif
+}
 SES_HD float ses_sqrt(float x) { return sqrtf(x); }
 SES_HD double ses_sqrt(double x) { return sqrt(x); }
 SES_HD float ses_abs(float x) { return fabsf(x); }

@@ -27,7 +27,7 @@ k_associate(const Tables tb, int n_frames, int p_max, int h_cap, const ses3d_per
   Arena ar(smem_raw);
   AssocWs ws;
   assoc_ws_layout(ar, C, p_max, h_cap, nk_scratch == nullptr, &ws);
-  if (nk_scratch) ws.nk = nk_scratch + (size_t)f * C * p_max * NKP * 3;
+  if (nk_scratch) ws.nk = nk_scratch + (size_t)f * C * p_max * NKP * 2;
   BlockTeam tm;
   int8_t* hd = hyp_det + (size_t)f * h_cap * C;
   associate_frame(tm, tb, p_max, h_cap, persons + (size_t)f * C * p_max, n_persons + (size_t)f * C, ws, hd, n_hyp + f,

@@ -71,15 +71,16 @@ k_finalize(const Tables tb, int n_frames, int h_cap, const int32_t* __restrict__
 }
 
 __global__ void __launch_bounds__(128)
-k_reproject(const Tables tb, int n_frames, int h_max, int cam_tile, const ses3d_person_cov* __restrict__ persons3d,
+k_reproject(const Tables tb, int n_frames, int h_max, int cap_rec, int s_cap,
+            const ses3d_person_cov* __restrict__ persons3d,
             const int32_t* __restrict__ n_persons3d, ses3d_person2d* __restrict__ out, int32_t* __restrict__ n_out) {
   const int f = blockIdx.x;
   if (f >= n_frames) return;
   Arena ar(smem_raw);
   ReprojWs ws;
-  reproj_ws_layout(ar, cam_tile, h_max, &ws);
+  reproj_ws_layout(ar, cap_rec, s_cap, &ws);
   BlockTeam tm;
-  reproject_frame(tm, tb, h_max, cam_tile, persons3d + (size_t)f * h_max, n_persons3d[f], ws,
+  reproject_frame(tm, tb, h_max, cap_rec, persons3d + (size_t)f * h_max, n_persons3d[f], ws,
                   out + (size_t)f * tb.n_cams * h_max, n_out + (size_t)f * tb.n_cams);
 }
 
@@ -125,13 +126,17 @@ cudaError_t launch_finalize(const Tables& tb, LaunchDims d, const int32_t* n_hyp
 
 cudaError_t launch_reproject(const Tables& tb, int n_frames, int h_max, const ses3d_person_cov* persons3d,
                              const int32_t* n_persons3d, ses3d_person2d* out, int32_t* n_out, cudaStream_t st) {
-  int cam_tile = tb.n_cams;
-  while (cam_tile > 1 && reproj_ws_bytes(cam_tile, h_max) > 40 * 1024) cam_tile = (cam_tile + 1) / 2;
-  const size_t smem = reproj_ws_bytes(cam_tile, h_max);
+  // staging capacity in records: ~28 KB, at least one camera of h_max persons, at most the whole frame
+  int cap_rec = std::max(h_max, std::min(tb.n_cams * h_max, 64));
+  if (const char* env = getenv("SES3D_REPROJ_CAP")) cap_rec = std::max(h_max, atoi(env));
+  const int s_cap = std::min(h_max, 8);
+  const size_t smem = reproj_ws_bytes(cap_rec, s_cap);
   if (smem > kSmemBudget) return cudaErrorInvalidConfiguration;
   cudaError_t e = cudaFuncSetAttribute(k_reproject, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_reproject<<<n_frames, 128, smem, st>>>(tb, n_frames, h_max, cam_tile, persons3d, n_persons3d, out, n_out);
+  int threads = 128;
+  if (const char* env = getenv("SES3D_REPROJ_THREADS")) threads = std::max(32, std::min(128, atoi(env) / 32 * 32));
+  k_reproject<<<n_frames, threads, smem, st>>>(tb, n_frames, h_max, cap_rec, s_cap, persons3d, n_persons3d, out, n_out);
   return cudaGetLastError();
 }
 

@@ -17,42 +17,54 @@
 namespace ses3d {
 
 struct ReprojWs {
-  ses3d_person2d* stage;  // [cc][n_p] (capacity cam_tile*h_max), dense in the frame's person count
+  ses3d_person2d* stage;  // [cc][n_p] (capacity cap_rec records), dense in the frame's person count
   uint8_t* vflag;         // [cc][n_p][17] joint accepted
   int* slot;              // [cc][n_p] output slot or -1
+  double* S;              // [s_cap*17][21] sigma points of the current person batch (7 points x xyz)
+  float* sscore;          // [s_cap*17] 3-D score (0 = joint absent)
+  int s_cap;              // persons per batch
 };
 
+// cap_rec = staging capacity in Person2D records (>= h_max so that one camera always fits)
 template <class A>
-SES_HD void reproj_ws_layout(A& ar, int cam_tile, int h_max, ReprojWs* ws) {
-  ses3d_person2d* stage = ar.template take<ses3d_person2d>((size_t)cam_tile * h_max);
-  int* slot = ar.template take<int>((size_t)cam_tile * h_max);
-  uint8_t* vflag = ar.template take<uint8_t>((size_t)cam_tile * h_max * NKP);
-  if (ws) { ws->stage = stage; ws->slot = slot; ws->vflag = vflag; }
+SES_HD void reproj_ws_layout(A& ar, int cap_rec, int s_cap, ReprojWs* ws) {
+  double* S = ar.template take<double>((size_t)s_cap * NKP * 21);
+  ses3d_person2d* stage = ar.template take<ses3d_person2d>((size_t)cap_rec);
+  int* slot = ar.template take<int>((size_t)cap_rec);
+  float* sscore = ar.template take<float>((size_t)s_cap * NKP);
+  uint8_t* vflag = ar.template take<uint8_t>((size_t)cap_rec * NKP);
+  if (ws) { ws->S = S; ws->stage = stage; ws->slot = slot; ws->sscore = sscore; ws->vflag = vflag; ws->s_cap = s_cap; }
 }
-inline size_t reproj_ws_bytes(int cam_tile, int h_max) {
+inline size_t reproj_ws_bytes(int cap_rec, int s_cap) {
   ArenaSizer s;
-  reproj_ws_layout(s, cam_tile, h_max, nullptr);
+  reproj_ws_layout(s, cap_rec, s_cap, nullptr);
   return (s.used + 15) / 16 * 16;
 }
 
 // persons3d [n_p] (n_p <= h_max); out [C][h_max]; n_out [C]
 template <class Team>
-SES_HD void reproject_frame(Team& tm, const Tables& tb, int h_max, int cam_tile, const ses3d_person_cov* persons3d,
+SES_HD void reproject_frame(Team& tm, const Tables& tb, int h_max, int cap_rec, const ses3d_person_cov* persons3d,
                             int n_p, const ReprojWs& ws, ses3d_person2d* out, int32_t* n_out) {
   const int C = tb.n_cams;
   const int words = (int)(sizeof(ses3d_person2d) / 4);  // 107
   if (n_p > h_max) n_p = h_max;
   if (n_p < 0) n_p = 0;
+  // as many cameras per pass as the staging holds for this frame's person count
+  int cam_tile = n_p > 0 ? cap_rec / n_p : C;
+  cam_tile = cam_tile < 1 ? 1 : (cam_tile > C ? C : cam_tile);
   for (int c0 = 0; c0 < C; c0 += cam_tile) {
     const int ncc = (C - c0) < cam_tile ? (C - c0) : cam_tile;
     tm.pfor(ncc * n_p * words, [&](int e) { reinterpret_cast<uint32_t*>(ws.stage)[e] = 0u; });
 
-    tm.pfor(n_p * NKP, [&](int e) {
-      const int p = e / NKP, k = e % NKP;
-      const ses3d_keypoint_cov& kp = persons3d[p].keypoints[tb.model.fusion_idx[k]];
-      const bool present = kp.score > 0.0f;  // REP:181
-      double S[7][3];
-      if (present) {
+    for (int p0 = 0; p0 < n_p; p0 += ws.s_cap) {
+      const int np_b = (n_p - p0) < ws.s_cap ? (n_p - p0) : ws.s_cap;
+      // one thread per (person, joint): Cholesky of the 3x3 covariance and the 7 sigma points (REP:62-75, 184-190)
+      tm.pfor(np_b * NKP, [&](int e) {
+        const int p = p0 + e / NKP, k = e % NKP;
+        const ses3d_keypoint_cov& kp = persons3d[p].keypoints[tb.model.fusion_idx[k]];
+        const bool present = kp.score > 0.0f;  // REP:181
+        ws.sscore[e] = present ? kp.score : 0.f;
+        if (!present) return;
         // lower Cholesky of [[c0 c1 c2][c1 c3 c4][c2 c4 c5]] (REP:72, 184-187)
         const double l00 = sqrt(kp.cov[0]);
         const double l10 = kp.cov[1] / l00, l20 = kp.cov[2] / l00;
@@ -62,23 +74,32 @@ SES_HD void reproject_frame(Team& tm, const Tables& tb, int h_max, int cam_tile,
         const double sp = sqrt(3.0 + 0.5);  // sqrt(DIM + kappa) REP:63,68
         // samples: mean, mean - sp*L e_j (j=0..2), mean + sp*L e_j (REP:68-72)
         const double col[3][3] = {{l00, l10, l20}, {0.0, l11, l21}, {0.0, 0.0, l22}};
-        S[0][0] = kp.x; S[0][1] = kp.y; S[0][2] = kp.z;
+        double* S = ws.S + (size_t)e * 21;
+        S[0] = kp.x; S[1] = kp.y; S[2] = kp.z;
         for (int j = 0; j < 3; ++j) {
-          S[1 + j][0] = (col[j][0] * -sp) + kp.x; S[1 + j][1] = (col[j][1] * -sp) + kp.y; S[1 + j][2] = (col[j][2] * -sp) + kp.z;
-          S[4 + j][0] = (col[j][0] * sp) + kp.x;  S[4 + j][1] = (col[j][1] * sp) + kp.y;  S[4 + j][2] = (col[j][2] * sp) + kp.z;
+          S[(1 + j) * 3 + 0] = (col[j][0] * -sp) + kp.x; S[(1 + j) * 3 + 1] = (col[j][1] * -sp) + kp.y;
+          S[(1 + j) * 3 + 2] = (col[j][2] * -sp) + kp.z;
+          S[(4 + j) * 3 + 0] = (col[j][0] * sp) + kp.x; S[(4 + j) * 3 + 1] = (col[j][1] * sp) + kp.y;
+          S[(4 + j) * 3 + 2] = (col[j][2] * sp) + kp.z;
         }
-      }
-      const double wden = 2.0 * (3 + 0.5);
-      const double w0 = 2 * 0.5 / wden, wi = 1.0 / wden;  // REP:65-66
-      for (int cc = 0; cc < ncc; ++cc) {
+      });
+      // one thread per (person, joint, camera): project the 7 sigma points (REP:193-221)
+      tm.pfor(np_b * NKP * ncc, [&](int e2) {
+        const int cc = e2 % ncc, e = e2 / ncc;
+        const int p = p0 + e / NKP, k = e % NKP;
+        const float score = ws.sscore[e];
         uint8_t ok = 0;
-        if (present) {
+        if (score > 0.0f) {
+          const double wden = 2.0 * (3 + 0.5);
+          const double w0 = 2 * 0.5 / wden, wi = 1.0 / wden;  // REP:65-66
+          const double* S = ws.S + (size_t)e * 21;
           const CamD& cm = tb.camd[c0 + cc];
           double u[7], v[7];
           for (int s = 0; s < 7; ++s) {
-            const double X = cm.P[0] * S[s][0] + cm.P[1] * S[s][1] + cm.P[2] * S[s][2] + cm.P[3];
-            const double Y = cm.P[4] * S[s][0] + cm.P[5] * S[s][1] + cm.P[6] * S[s][2] + cm.P[7];
-            const double Z = cm.P[8] * S[s][0] + cm.P[9] * S[s][1] + cm.P[10] * S[s][2] + cm.P[11];
+            const double sx = S[s * 3], sy = S[s * 3 + 1], sz = S[s * 3 + 2];
+            const double X = cm.P[0] * sx + cm.P[1] * sy + cm.P[2] * sz + cm.P[3];
+            const double Y = cm.P[4] * sx + cm.P[5] * sy + cm.P[6] * sz + cm.P[7];
+            const double Z = cm.P[8] * sx + cm.P[9] * sy + cm.P[10] * sz + cm.P[11];
             u[s] = (cm.fx * X + cm.Tx) / Z + cm.cx;  // project3dToPixel (image_geometry)
             v[s] = (cm.fy * Y + cm.Ty) / Z + cm.cy;
           }
@@ -92,14 +113,14 @@ SES_HD void reproject_frame(Team& tm, const Tables& tb, int h_max, int cam_tile,
           }
           if (!(mu < 0 || mu > cm.width || mv < 0 || mv > cm.height)) {  // REP:207-208
             ses3d_keypoint2d& o = ws.stage[cc * n_p + p].keypoints[k];
-            o.x = static_cast<float>(mu); o.y = static_cast<float>(mv); o.score = kp.score;
+            o.x = static_cast<float>(mu); o.y = static_cast<float>(mv); o.score = score;
             o.cov[0] = static_cast<float>(cxx); o.cov[1] = static_cast<float>(cxy); o.cov[2] = static_cast<float>(cyy);
             ok = 1;
           }
         }
         ws.vflag[(cc * n_p + p) * NKP + k] = ok;
-      }
-    });
+      });
+    }
 
     // bbox + emitted flag per (camera, person) (REP:150,161-162,218-230)
     tm.pfor(ncc * n_p, [&](int e) {

@@ -102,14 +102,16 @@ int hostsim_reproject_batch(void* h, int32_t n_frames, int32_t h_max, int32_t ca
   Sim* s = static_cast<Sim*>(h);
   const Tables& tb = s->tb;
   const int C = tb.n_cams;
-  if (cam_tile <= 0) cam_tile = C;
-  std::vector<unsigned char> wsr(reproj_ws_bytes(cam_tile, h_max) + 64);
+  // cam_tile > 0 forces that many cameras per pass for a full frame; 0 = everything in one pass
+  const int cap_rec = (cam_tile <= 0 ? C : cam_tile) * h_max;
+  const int s_cap = cam_tile > 0 ? 3 : h_max;   // small person batches when a tile size is forced
+  std::vector<unsigned char> wsr(reproj_ws_bytes(cap_rec, s_cap) + 64);
   SerialTeam tm;
   for (int f = 0; f < n_frames; ++f) {
     Arena a(wsr.data());
     ReprojWs ws;
-    reproj_ws_layout(a, cam_tile, h_max, &ws);
-    reproject_frame(tm, tb, h_max, cam_tile, p3d + (size_t)f * h_max, n_p3d[f], ws, out + (size_t)f * C * h_max,
+    reproj_ws_layout(a, cap_rec, s_cap, &ws);
+    reproject_frame(tm, tb, h_max, cap_rec, p3d + (size_t)f * h_max, n_p3d[f], ws, out + (size_t)f * C * h_max,
                     n_out + (size_t)f * C);
   }
   return 0;

@@ -185,6 +185,11 @@ int ses3d_process_batch_ragged(ses3d_handle h, int32_t n_frames, int32_t p_max,
 /* Pre-size the handle's device scratch (otherwise grown on first use). */
 int ses3d_reserve(ses3d_handle h, int32_t n_frames, int32_t p_max, int32_t h_max);
 
+/* Diagnostics: n independent rows x cols assignment problems (cost [n][rows*cols], column-major like
+ * HungarianAlgorithm::assignmentoptimal, Hungarian.h:24) through the device Munkres; assignment [n][rows]. */
+int ses3d_munkres_batch(ses3d_handle h, int32_t n, int32_t rows, int32_t cols, const double* cost,
+                        int32_t* assignment);
+
 /* How many kernels the handle has launched so far (bench.py's gpu_launches). */
 int64_t ses3d_launch_count(ses3d_handle h);
 

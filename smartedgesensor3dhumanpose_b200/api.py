@@ -47,6 +47,15 @@ class GeometryPipeline:
         _lib.check(self._L.ses3d_get_tables(self._h, _p(P), _p(F)))
         return P, F
 
+    def munkres_batch(self, costs):
+        """[n][rows][cols] cost matrices -> [n][rows] assignments through the device Munkres (diagnostics)."""
+        costs = np.asarray(costs, dtype=np.float64)
+        n, rows, cols = costs.shape
+        cm = np.ascontiguousarray(np.transpose(costs, (0, 2, 1)))   # column-major per problem
+        out = np.zeros((n, rows), np.int32)
+        _lib.check(self._L.ses3d_munkres_batch(self._h, n, rows, cols, _p(cm), _p(out)))
+        return out
+
     def reserve(self, n_frames, p_max, h_max):
         _lib.check(self._L.ses3d_reserve(self._h, n_frames, p_max, h_max))
 

@@ -565,6 +565,26 @@ int ses3d_reserve(ses3d_handle h, int32_t n_frames, int32_t p_max, int32_t h_max
   return SES3D_OK;
 }
 
+int ses3d_munkres_batch(ses3d_handle h, int32_t n, int32_t rows, int32_t cols, const double* cost, int32_t* assignment) {
+  if (!h || n < 0 || !cost || !assignment) return fail(SES3D_E_INVALID, "bad argument");
+  if (n == 0) return SES3D_OK;
+  std::lock_guard<std::mutex> lock(h->mu);
+  CU(cudaSetDevice(h->device));
+  DevBuf dc, da;
+  const size_t cb = (size_t)n * rows * cols * sizeof(double), ab = (size_t)n * rows * sizeof(int32_t);
+  CU(dc.ensure(cb));
+  cudaError_t e = da.ensure(ab);
+  if (e == cudaSuccess) e = cudaMemcpy(dc.p, cost, cb, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = ses3d::launch_munkres_batch(n, rows, cols, dc.as<double>(), da.as<int32_t>(), h->slot[0].stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->slot[0].stream);
+  if (e == cudaSuccess) e = cudaMemcpy(assignment, da.p, ab, cudaMemcpyDeviceToHost);
+  dc.release();
+  da.release();
+  h->launches += 1;
+  if (e != cudaSuccess) return cuda_fail(e, "ses3d_munkres_batch");
+  return SES3D_OK;
+}
+
 int64_t ses3d_launch_count(ses3d_handle h) { return h ? h->launches : 0; }
 
 int ses3d_set_profiling(ses3d_handle h, int32_t on) {

@@ -18,7 +18,7 @@
 
 namespace ses3d {
 
-enum { SC_N_HYP = 0, SC_N_DET, SC_N_HUNG, SC_OVERFLOW, SC_CURSOR, SC_NOBS_SUM, SC_COUNT };
+enum { SC_N_HYP = 0, SC_N_DET, SC_N_HUNG, SC_OVERFLOW, SC_CURSOR, SC_NOBS_SUM, SC_AMBIG, SC_COUNT };
 
 struct AssocWs {
   float* nk;          // [C*p_max][17][2] normalised keypoints x, y
@@ -208,6 +208,116 @@ SES_HD void munkres_serial(const AssocWs& ws, const double* in, int n_r, int n_c
   for (int r = 0; r < n_r; ++r)  // buildassignmentvector (Hungarian.cpp:190-205)
     for (int c = 0; c < n_c; ++c)
       if (star[r + n_r * c]) { assignment[r] = c; break; }
+}
+
+// The same solver run cooperatively by a warp-sized team (lanes over rows / columns / entries):
+// every search of the reference ("first zero in this scan order") becomes a ballot + find-first-set over
+// the same index order, so primes, stars and covers - and therefore ties - resolve identically.
+template <class WT>
+SES_HD void munkres_coop(WT& tm, const AssocWs& ws, const double* in, int n_r, int n_c, int* assignment) {
+  const int n_e = n_r * n_c;
+  double* dist = ws.dist;
+  uint8_t *star = ws.star, *prime = ws.prime, *nstar = ws.nstar, *cov_r = ws.cov_r, *cov_c = ws.cov_c;
+  tm.pfor(n_e, [&](int i) { dist[i] = in[i]; star[i] = 0; prime[i] = 0; nstar[i] = 0; });
+  tm.pfor(n_r, [&](int r) { cov_r[r] = 0; assignment[r] = -1; });
+  tm.pfor(n_c, [&](int c) { cov_c[c] = 0; });
+  auto is_zero = [&](int r, int c) { return fabs(dist[r + n_r * c]) < DBL_EPSILON; };
+  int min_dim;
+  if (n_r <= n_c) {  // Hungarian.cpp:95-131
+    min_dim = n_r;
+    tm.pfor(n_r, [&](int r) {
+      double mn = dist[r];
+      for (int c = 1; c < n_c; ++c) { const double v = dist[r + n_r * c]; if (v < mn) mn = v; }
+      for (int c = 0; c < n_c; ++c) dist[r + n_r * c] -= mn;
+    });
+    for (int r = 0; r < n_r; ++r) {
+      const int c = tm.first(n_c, [&](int cc) { return is_zero(r, cc) && !cov_c[cc]; });
+      if (c < n_c) tm.single([&] { star[r + n_r * c] = 1; cov_c[c] = 1; });
+    }
+  } else {  // Hungarian.cpp:132-170
+    min_dim = n_c;
+    tm.pfor(n_c, [&](int c) {
+      double mn = dist[n_r * c];
+      for (int r = 1; r < n_r; ++r) { const double v = dist[r + n_r * c]; if (v < mn) mn = v; }
+      for (int r = 0; r < n_r; ++r) dist[r + n_r * c] -= mn;
+    });
+    for (int c = 0; c < n_c; ++c) {
+      const int r = tm.first(n_r, [&](int rr) { return is_zero(rr, c) && !cov_r[rr]; });
+      if (r < n_r) tm.single([&] { star[r + n_r * c] = 1; cov_c[c] = 1; cov_r[r] = 1; });
+    }
+    tm.pfor(n_r, [&](int r) { cov_r[r] = 0; });
+  }
+  enum { S2A, S2B, S3, S4, S5, DONE };
+  int st = S2B, row4 = 0, col4 = 0;
+  while (st != DONE) {
+    if (st == S2A) {  // Hungarian.cpp:222-242
+      tm.pfor(n_c, [&](int c) {
+        for (int r = 0; r < n_r; ++r)
+          if (star[r + n_r * c]) { cov_c[c] = 1; break; }
+      });
+      st = S2B;
+    } else if (st == S2B) {  // Hungarian.cpp:245-266
+      int n = 0;
+      for (int c = 0; c < n_c; ++c) n += cov_c[c] ? 1 : 0;
+      st = (n == min_dim) ? DONE : S3;
+    } else if (st == S3) {  // Hungarian.cpp:269-309: column-outer scan, rows searched by ballot
+      bool zeros = true, to4 = false;
+      while (zeros && !to4) {
+        zeros = false;
+        for (int c = 0; c < n_c && !to4; ++c) {
+          if (cov_c[c]) continue;
+          const int r = tm.first(n_r, [&](int rr) { return !cov_r[rr] && is_zero(rr, c); });
+          if (r == n_r) continue;
+          const int sc = tm.first(n_c, [&](int cc) { return star[r + n_r * cc] != 0; });
+          tm.single([&] {
+            prime[r + n_r * c] = 1;
+            if (sc < n_c) { cov_r[r] = 1; cov_c[sc] = 0; }
+          });
+          if (sc == n_c) { row4 = r; col4 = c; to4 = true; }
+          else zeros = true;
+        }
+      }
+      st = to4 ? S4 : S5;
+    } else if (st == S4) {  // Hungarian.cpp:312-363: the alternating path is a short serial chain
+      tm.pfor(n_e, [&](int i) { nstar[i] = star[i]; });
+      tm.single([&] {
+        nstar[row4 + n_r * col4] = 1;
+        int sc = col4, sr = 0;
+        for (sr = 0; sr < n_r; ++sr)
+          if (star[sr + n_r * sc]) break;
+        while (sr < n_r) {
+          nstar[sr + n_r * sc] = 0;
+          int pc = 0;
+          for (; pc < n_c; ++pc)
+            if (prime[sr + n_r * pc]) break;
+          nstar[sr + n_r * pc] = 1;
+          sc = pc;
+          for (sr = 0; sr < n_r; ++sr)
+            if (star[sr + n_r * sc]) break;
+        }
+      });
+      tm.pfor(n_e, [&](int i) { prime[i] = 0; star[i] = nstar[i]; });
+      tm.pfor(n_r, [&](int r) { cov_r[r] = 0; });
+      st = S2A;
+    } else {  // S5, Hungarian.cpp:366-397
+      const double h = tm.min(n_e, [&](int e) {
+        const int r = e % n_r, c = e / n_r;
+        return (!cov_r[r] && !cov_c[c]) ? dist[e] : DBL_MAX;
+      });
+      tm.pfor(n_e, [&](int e) {  // per entry the same sequence as the reference: + h (covered row), then - h (uncovered column)
+        const int r = e % n_r, c = e / n_r;
+        double v = dist[e];
+        if (cov_r[r]) v += h;
+        if (!cov_c[c]) v -= h;
+        dist[e] = v;
+      });
+      st = S3;
+    }
+  }
+  tm.pfor(n_r, [&](int r) {  // buildassignmentvector (Hungarian.cpp:190-205)
+    for (int c = 0; c < n_c; ++c)
+      if (star[r + n_r * c]) { assignment[r] = c; break; }
+  });
 }
 
 // One frame. persons [C][p_max], n_persons [C]. Outputs: hyp_det [h_cap][C] (detection slot of
@@ -400,10 +510,13 @@ SES_HD void associate_frame(Team& tm, const Tables& tb, int p_max, int h_cap, co
         for (int d = 0; d < n_det; ++d) row += ws.mask[h + n_hyp * d];
         ambiguous = row > 1;
       }
-      if (ambiguous) {  // S3D:628-634
-        ++ws.scal[SC_N_HUNG];
-        munkres_serial(ws, ws.cost, n_hyp, n_det, ws.assignment);
-      }
+      ws.scal[SC_AMBIG] = ambiguous ? 1 : 0;
+      if (ambiguous) ++ws.scal[SC_N_HUNG];
+    });
+    if (ws.scal[SC_AMBIG]) {  // S3D:628-634: full Munkres on the cost matrix, solved by the team's first warp
+      tm.warp0([&](auto& wt) { munkres_coop(wt, ws, ws.cost, n_hyp, n_det, ws.assignment); });
+    }
+    tm.single([&] {
       for (int d = 0; d < n_det; ++d) ws.handled[d] = 0;
       for (int h = 0; h < n_hyp; ++h) {  // S3D:637-660
         const int d = ws.assignment[h];

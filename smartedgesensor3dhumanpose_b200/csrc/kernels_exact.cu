@@ -84,6 +84,32 @@ k_reproject(const Tables tb, int n_frames, int h_max, int cap_rec, int s_cap,
                   out + (size_t)f * tb.n_cams * h_max, n_out + (size_t)f * tb.n_cams);
 }
 
+// Batch of independent assignment problems, one warp each (test / diagnostics entry: lets the tests drive the
+// warp-cooperative Munkres with adversarial tied matrices). cost: [n][rows*cols] column-major.
+__global__ void __launch_bounds__(32)
+k_munkres_batch(int n, int rows, int cols, const double* __restrict__ cost, int32_t* __restrict__ assignment) {
+  const int i = blockIdx.x;
+  if (i >= n) return;
+  Arena ar(smem_raw);
+  AssocWs ws;
+  assoc_ws_layout(ar, 1, cols, rows, false, &ws);
+  WarpTeam tm;
+  const int n_e = rows * cols;
+  tm.pfor(n_e, [&](int e) { ws.cost[e] = cost[(size_t)i * n_e + e]; });
+  munkres_coop(tm, ws, ws.cost, rows, cols, ws.assignment);
+  tm.pfor(rows, [&](int r) { assignment[(size_t)i * rows + r] = ws.assignment[r]; });
+}
+
+cudaError_t launch_munkres_batch(int n, int rows, int cols, const double* cost, int32_t* assignment, cudaStream_t st) {
+  if (rows < 1 || cols < 1 || rows > 1024 || cols > 127) return cudaErrorInvalidValue;
+  const size_t smem = assoc_ws_bytes(1, cols, rows, false);
+  if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
+  cudaError_t e = cudaFuncSetAttribute(k_munkres_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_munkres_batch<<<n, 32, smem, st>>>(n, rows, cols, cost, assignment);
+  return cudaGetLastError();
+}
+
 static const size_t kSmemBudget = 200 * 1024;   // of the 227 KB a CTA may opt in to
 static const size_t kAssocSmemTarget = 64 * 1024;
 

@@ -29,6 +29,9 @@ cudaError_t launch_finalize(const Tables& tb, LaunchDims d, const int32_t* n_hyp
 cudaError_t launch_reproject(const Tables& tb, int n_frames, int h_max, const ses3d_person_cov* persons3d,
                              const int32_t* n_persons3d, ses3d_person2d* out, int32_t* n_out, cudaStream_t st);
 
+// diagnostics: a batch of independent assignment problems through the warp-cooperative Munkres
+cudaError_t launch_munkres_batch(int n, int rows, int cols, const double* cost, int32_t* assignment, cudaStream_t st);
+
 // ragged <-> padded record movement (kernels_pack.cu)
 cudaError_t launch_scan_counts(const int32_t* counts, int n, int cap, long long* offsets, cudaStream_t st);
 cudaError_t launch_move_records(int direction /*0 pack, 1 unpack*/, int n_units, int cap, int rec_bytes,

@@ -12,9 +12,20 @@
 
 namespace ses3d {
 
+//   team.first(n, pred)   smallest i in [0,n) with pred(i) true, n if none (same value on every thread)
+//   team.min(n, f)        minimum of f(i) over [0,n) as double, DBL_MAX if empty (same value on every thread)
+//   team.warp0(f)         run f(warp_team) on the team's first warp only, then barrier (warp-cooperative
+//                         sub-algorithms such as the Munkres solver inside a CTA-wide team)
 struct SerialTeam {
   template <class F> void pfor(int n, F&& f) { for (int i = 0; i < n; ++i) f(i); }
   template <class F> void single(F&& f) { f(); }
+  template <class P> int first(int n, P&& pred) { for (int i = 0; i < n; ++i) if (pred(i)) return i; return n; }
+  template <class F> double min(int n, F&& f) {
+    double m = DBL_MAX;
+    for (int i = 0; i < n; ++i) { const double v = f(i); if (v < m) m = v; }
+    return m;
+  }
+  template <class F> void warp0(F&& f) { f(*this); }
   void sync() {}
   int rank() const { return 0; }
   int size() const { return 1; }
@@ -30,6 +41,22 @@ struct WarpTeam {
     if ((threadIdx.x & 31u) == 0) f();
     __syncwarp();
   }
+  template <class P> __device__ __forceinline__ int first(int n, P&& pred) {
+    const int lane = (int)(threadIdx.x & 31u);
+    for (int base = 0; base < n; base += 32) {
+      const int i = base + lane;
+      const unsigned b = __ballot_sync(0xffffffffu, i < n && pred(i));
+      if (b) return base + __ffs((int)b) - 1;
+    }
+    return n;
+  }
+  template <class F> __device__ __forceinline__ double min(int n, F&& f) {
+    double m = DBL_MAX;
+    for (int i = (int)(threadIdx.x & 31u); i < n; i += 32) { const double v = f(i); if (v < m) m = v; }
+    for (int off = 16; off > 0; off >>= 1) { const double o = __shfl_xor_sync(0xffffffffu, m, off); if (o < m) m = o; }
+    return m;
+  }
+  template <class F> __device__ __forceinline__ void warp0(F&& f) { f(*this); __syncwarp(); }
   __device__ __forceinline__ void sync() { __syncwarp(); }
   __device__ __forceinline__ int rank() const { return (int)(threadIdx.x & 31u); }
   __device__ __forceinline__ int size() const { return 32; }
@@ -42,6 +69,10 @@ struct BlockTeam {
   }
   template <class F> __device__ __forceinline__ void single(F&& f) {
     if (threadIdx.x == 0) f();
+    __syncthreads();
+  }
+  template <class F> __device__ __forceinline__ void warp0(F&& f) {
+    if (threadIdx.x < 32) { WarpTeam w; f(w); }
     __syncthreads();
   }
   __device__ __forceinline__ void sync() { __syncthreads(); }

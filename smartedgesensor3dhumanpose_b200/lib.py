@@ -9,7 +9,7 @@ PKG = Path(__file__).resolve().parent
 LIB_PATH = PKG / "libses3d.so"
 
 EXPORTS = ("ses3d_default_params", "ses3d_create", "ses3d_destroy", "ses3d_get_tables", "ses3d_triangulate_batch",
-           "ses3d_reproject_batch", "ses3d_process_batch", "ses3d_process_batch_ragged", "ses3d_reserve", "ses3d_launch_count",
+           "ses3d_reproject_batch", "ses3d_process_batch", "ses3d_process_batch_ragged", "ses3d_reserve", "ses3d_munkres_batch", "ses3d_launch_count",
            "ses3d_set_profiling", "ses3d_last_kernel_ms", "ses3d_last_error_string", "ses3d_version",
            "ses3d_synth_frames", "ses3d_synth_frames_device")
 
@@ -44,6 +44,7 @@ def load():
     L.ses3d_process_batch_ragged.argtypes = [vp, i32, i32, vp, vp, i32, vp, i64, vp, vp, i64, vp, C.POINTER(i64),
                                              C.POINTER(i64), u32]
     L.ses3d_reserve.argtypes = [vp, i32, i32, i32]
+    L.ses3d_munkres_batch.argtypes = [vp, i32, i32, i32, vp, vp]
     L.ses3d_launch_count.argtypes = [vp]
     L.ses3d_launch_count.restype = i64
     L.ses3d_set_profiling.argtypes = [vp, i32]

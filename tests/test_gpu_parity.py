@@ -247,3 +247,21 @@ def test_ragged_batch_call_equals_padded_call():
     with pytest.raises(Ses3dError) as ei:
         gpu.process_batch_ragged(dense_in, fr["n_persons"], p_max, h_max, out3d[:10], n3, out2d, n2)
     assert ei.value.code == -3
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (3, 3), (6, 6), (4, 7), (7, 4), (20, 20), (24, 20), (20, 31), (44, 20), (70, 33)])
+def test_device_munkres_matches_reference_indices(shape):
+    """The warp-cooperative Munkres against the reference's verbatim Hungarian.cpp, including heavily tied matrices."""
+    from oracle import binding as ob
+    from smartedgesensor3dhumanpose_b200 import rigs
+    rng = np.random.default_rng(shape[0] * 131 + shape[1])
+    costs = rng.random((200,) + shape)
+    costs[::3][rng.random((len(costs[::3]),) + shape) < 0.6] = 1e6
+    costs[::5] = np.round(costs[::5] * 4) / 4
+    costs[7] = 0.0
+    gpu = api.GeometryPipeline(rigs.ring4())
+    got = gpu.munkres_batch(costs)
+    solver = ob.ref_munkres if ob.REF_HUNGARIAN_PATH.exists() else ob.munkres
+    for i in range(len(costs)):
+        want, _ = solver(costs[i])
+        assert np.array_equal(got[i], want), (shape, i)

@@ -319,7 +319,7 @@ def main():
         barrier()
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
         t0.record()
-        parts = sharding.gather_compact(compact, dst=0)
+        parts = sharding.gather_compact(compact, dst=0, shapes=[tuple(compact.shape)] * world)
         t1.record()
         barrier()
         gather_ms = t0.elapsed_time(t1)

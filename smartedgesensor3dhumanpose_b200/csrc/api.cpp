@@ -58,23 +58,23 @@ struct DevBuf {
 };
 
 struct Scratch {  // per-slot intermediates of the triangulation path
-  DevBuf hyp_det, n_hyp, n_hung, keep, tmp, nk, work, work_count;
+  DevBuf hyp_det, n_hyp, n_hung, keep, tmp, nk, work, work_count, pairs;
   void release() {
     hyp_det.release(); n_hyp.release(); n_hung.release(); keep.release(); tmp.release(); nk.release(); work.release();
-    work_count.release();
+    work_count.release(); pairs.release();
   }
 };
 
 struct Slot {  // one in-flight chunk of a host-buffer call
   cudaStream_t stream = nullptr;
   Scratch sc;
-  DevBuf persons, n_persons, out3d, n_out3d, out2d, n_out2d, hyp_of;
+  DevBuf persons, n_persons, out3d, n_out3d, out2d, n_out2d, hyp_of, dump_nhyp, dump_nhung;
   DevBuf in_dense, in_off, off3, off2, c3d, c2d;  // ragged calls: dense staging + offsets
   long long* totals = nullptr;                    // pinned host: {total3d, total2d} of the chunk in flight
   cudaEvent_t done = nullptr;
   void release() {
     sc.release(); persons.release(); n_persons.release(); out3d.release(); n_out3d.release(); out2d.release();
-    n_out2d.release(); hyp_of.release(); in_dense.release(); in_off.release(); off3.release(); off2.release();
+    n_out2d.release(); hyp_of.release(); dump_nhyp.release(); dump_nhung.release(); in_dense.release(); in_off.release(); off3.release(); off2.release();
     c3d.release(); c2d.release();
     if (totals) cudaFreeHost(totals);
     totals = nullptr;
@@ -107,6 +107,14 @@ namespace {
 using ses3d::LaunchDims;
 
 const int kDeviceChunk = 16384;  // frames per kernel launch on the device path (bounds scratch)
+
+// frames per launch for a given rig: the per-frame pair table (n(n-1)/2 doubles, n = C*p_max) is the largest
+// scratch item; keep it under ~4 GiB per slot
+int device_chunk(int n_cams, int p_max) {
+  const size_t per_frame = ses3d::associate_pair_table_bytes(n_cams, p_max);
+  const size_t fit = std::max<size_t>(1, ((size_t)4 << 30) / std::max<size_t>(per_frame, 1));
+  return (int)std::min<size_t>(kDeviceChunk, fit);
+}
 
 struct ProfScope {  // optional CUDA-event bracket around one kernel launch
   ses3d_handle_s* h;
@@ -145,8 +153,10 @@ int triangulate_on_device(ses3d_handle_s* h, Scratch& sc, cudaStream_t st, int n
   const int C = h->tb.n_cams;
   bool need_nk = false;
   ses3d::associate_smem_bytes(C, p_max, h_max, &need_nk);
-  for (int f0 = 0; f0 < n_frames; f0 += kDeviceChunk) {
-    const int nf = std::min(kDeviceChunk, n_frames - f0);
+  const int dchunk = device_chunk(C, p_max);
+  for (int f0 = 0; f0 < n_frames; f0 += dchunk) {
+    const int nf = std::min(dchunk, n_frames - f0);
+    CU(sc.pairs.ensure((size_t)nf * ses3d::associate_pair_table_bytes(C, p_max)));
     CU(sc.hyp_det.ensure((size_t)nf * h_max * C));
     CU(sc.n_hyp.ensure((size_t)nf * 4));
     CU(sc.n_hung.ensure((size_t)nf * 4));
@@ -162,7 +172,8 @@ int triangulate_on_device(ses3d_handle_s* h, Scratch& sc, cudaStream_t st, int n
     int32_t* n_hung = n_hung_dump ? n_hung_dump + f0 : sc.n_hung.as<int32_t>();
     {
       ProfScope ps(h, 0, st);
-      CU(ses3d::launch_associate(h->tb, d, pin, nin, need_nk ? sc.nk.as<float>() : nullptr, sc.hyp_det.as<int8_t>(),
+      CU(ses3d::launch_associate(h->tb, d, pin, nin, need_nk ? sc.nk.as<float>() : nullptr, sc.pairs.as<double>(),
+                                 sc.hyp_det.as<int8_t>(),
                                  n_hyp, n_hung, h->d_overflow.as<int32_t>(),
                                  hyp_of ? hyp_of + (size_t)f0 * C * p_max : nullptr, sc.keep.as<int32_t>(),
                                  sc.work.as<uint32_t>(), sc.work_count.as<int32_t>(), st));
@@ -263,17 +274,20 @@ int run_batch(ses3d_handle_s* h, int stages, int n_frames, int p_max, const ses3
         CU(s.hyp_of.ensure((size_t)nf * C * p_max * 4));
         d_hyp_of = s.hyp_of.as<int32_t>();
       }
+      int32_t *d_nhyp = nullptr, *d_nhung = nullptr;   // a host chunk may span several device chunks
+      if (n_hyp_d) { CU(s.dump_nhyp.ensure((size_t)nf * 4)); d_nhyp = s.dump_nhyp.as<int32_t>(); }
+      if (n_hung_d) { CU(s.dump_nhung.ensure((size_t)nf * 4)); d_nhung = s.dump_nhung.as<int32_t>(); }
       int rc = triangulate_on_device(h, s.sc, st, nf, p_max, h_max, s.persons.as<ses3d_person2d>(),
                                      s.n_persons.as<int32_t>(), s.out3d.as<ses3d_person_cov>(),
-                                     s.n_out3d.as<int32_t>(), d_hyp_of, nullptr, nullptr);
+                                     s.n_out3d.as<int32_t>(), d_hyp_of, d_nhyp, d_nhung);
       if (rc) return rc;
       if (io3d) CU(cudaMemcpyAsync(io3d + (size_t)f0 * h_max, s.out3d.p, (size_t)nf * h_max * sizeof(ses3d_person_cov),
                                    cudaMemcpyDeviceToHost, st));
       if (n_io3d) CU(cudaMemcpyAsync(n_io3d + f0, s.n_out3d.p, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
       if (hyp_of) CU(cudaMemcpyAsync(hyp_of + (size_t)f0 * C * p_max, d_hyp_of, (size_t)nf * C * p_max * 4,
                                      cudaMemcpyDeviceToHost, st));
-      if (n_hyp_d) CU(cudaMemcpyAsync(n_hyp_d + f0, s.sc.n_hyp.p, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
-      if (n_hung_d) CU(cudaMemcpyAsync(n_hung_d + f0, s.sc.n_hung.p, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
+      if (n_hyp_d) CU(cudaMemcpyAsync(n_hyp_d + f0, d_nhyp, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
+      if (n_hung_d) CU(cudaMemcpyAsync(n_hung_d + f0, d_nhung, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
     } else {
       CU(cudaMemcpyAsync(s.out3d.p, io3d + (size_t)f0 * h_max, (size_t)nf * h_max * sizeof(ses3d_person_cov),
                          cudaMemcpyHostToDevice, st));
@@ -549,10 +563,11 @@ int ses3d_reserve(ses3d_handle h, int32_t n_frames, int32_t p_max, int32_t h_max
   std::lock_guard<std::mutex> lock(h->mu);
   CU(cudaSetDevice(h->device));
   const int C = h->tb.n_cams;
-  const int nf = std::min(n_frames, kDeviceChunk);
+  const int nf = std::min(n_frames, device_chunk(C, p_max));
   bool need_nk = false;
   ses3d::associate_smem_bytes(C, p_max, h_max, &need_nk);
   for (Slot& s : h->slot) {
+    CU(s.sc.pairs.ensure((size_t)nf * ses3d::associate_pair_table_bytes(C, p_max)));
     CU(s.sc.hyp_det.ensure((size_t)nf * h_max * C));
     CU(s.sc.n_hyp.ensure((size_t)nf * 4));
     CU(s.sc.n_hung.ensure((size_t)nf * 4));

@@ -8,48 +8,46 @@
 // reference's float/double split and evaluation order and MUST be compiled without FMA
 // contraction (nvcc -fmad=false; g++ -ffp-contract=off).
 //
-// B200 mapping: one team per frame. The n_hyp x n_det cost matrix of a camera round is
-// filled in parallel (one entry per thread, each entry walks the hypothesis' observations
-// and the 17 joints); the sequential parts (ambiguity test, Munkres, hypothesis update)
-// are a few hundred integer operations run by the team leader on shared memory.
+// B200 mapping: one team per frame, two phases.
+//  (1) pair table: calcCost only ever combines a detection of an earlier camera (a hypothesis
+//      observation) with a detection of a later camera, and every earlier valid detection belongs to
+//      exactly one hypothesis, so the set of (observation, detection) pairs the reference evaluates over
+//      all camera rounds is exactly "all cross-camera pairs of valid detections". Their mean epipolar
+//      distances E[a][b] (S3D:353-368) are computed up front in ONE flat parallel pass - all the
+//      floating-point work of the association, no dependency on the matching - and kept in an
+//      L2-resident table.
+//  (2) the sequential Tanke-Gall camera rounds then only gather table entries: a cost-matrix entry is
+//      the in-order mean of <= n_obs lookups; the ambiguity test, the warp-cooperative Munkres and the
+//      hypothesis update are integer work on shared memory.
 #pragma once
 #include "common.h"
 #include "team.h"
 
 namespace ses3d {
 
-enum { SC_N_HYP = 0, SC_N_DET, SC_N_HUNG, SC_OVERFLOW, SC_CURSOR, SC_NOBS_SUM, SC_AMBIG, SC_COUNT };
+enum { SC_N_HYP = 0, SC_N_DET, SC_N_HUNG, SC_OVERFLOW, SC_CURSOR, SC_N_VALID, SC_AMBIG, SC_COUNT };
 
 struct AssocWs {
-  float* nk;          // [C*p_max][17][2] normalised keypoints x, y
+  float* nk;          // [C*p_max][17][2] normalised keypoints x, y (shared memory, or global scratch for big rigs)
+  double* E;          // [n(n-1)/2], n = C*p_max: pair table in global memory, index b(b-1)/2 + a for a < b
+                      //   (compact indices of valid detections, camera-major); -1 = no joint in common
   uint32_t* kmask;    // [C*p_max] bit k: keypoint k has score > threshold (the strict test of calcCost, S3D:354)
-  float* pscore;      // [C*p_max] Person2D.score
-  uint8_t* valid;     // [C*p_max] more than 8 valid keypoints (S3D:579,599)
+  float* pscore;      // [C*p_max] Person2D.score, by compact index
+  uint16_t* vslot;    // [C*p_max] compact index -> slot (cam * p_max + det)
+  uint16_t* voff;     // [C+1] first compact index of each camera
+  uint8_t* valid;     // [C*p_max] more than 8 valid keypoints (S3D:579,599), by slot
   uint8_t* hyp_nobs;  // [h_cap]
-  uint16_t* hyp_obs;  // [h_cap][C] observation list, (cam << 8) | det, in camera order
-  uint8_t* dets;      // [p_max] valid detections of the current camera
+  uint16_t* hyp_obs;  // [h_cap][C] observation list (compact indices), in camera order
   double* cost;       // [h_cap*p_max] column-major n_hyp x n_det (S3D:611)
   double* dist;       // Munkres working copy
   uint8_t *mask, *star, *prime, *nstar;  // [h_cap*p_max]
   uint8_t *cov_r, *cov_c, *handled;      // [h_cap], [p_max], [p_max]
   int* assignment;    // [h_cap]
   int* scal;          // [SC_COUNT]
-  // "triple mode" (small rigs): one thread per (hypothesis, observation, detection)
-  double* obs_cost;   // [triple_cap] mean epipolar distance of one observation against one detection
-  uint8_t* obs_has;   // [triple_cap] the pair shared at least one joint
-  uint8_t* r2h;       // [C*p_max] observation rank -> hypothesis
-  uint16_t* hoff;     // [h_cap+1] prefix sum of hyp_nobs
-  int triple_cap;
 };
 
-// triple mode is used when every round's (sum of observations) x (detections) fits this many entries
-SES_HD int assoc_triple_cap(int C, int p_max) {
-  const long cap = (long)(C - 1) * p_max * p_max;   // (observations of all hypotheses) x (detections) of one round
-  return cap <= 2048 ? (int)cap : 0;
-}
-
-// Lays the workspace out in `base`; when nk_external != nullptr the keypoints live there
-// (global scratch for rigs whose frame does not fit in shared memory).
+// Lays the shared-memory workspace out; nk_inside = false keeps the keypoints in global scratch
+// (rigs whose frame does not fit in shared memory).
 template <class A>
 SES_HD void assoc_ws_layout(A& ar, int C, int p_max, int h_cap, bool nk_inside, AssocWs* ws) {
   double* cost = ar.template take<double>((size_t)h_cap * p_max);
@@ -60,9 +58,10 @@ SES_HD void assoc_ws_layout(A& ar, int C, int p_max, int h_cap, bool nk_inside, 
   int* assignment = ar.template take<int>(h_cap);
   int* scal = ar.template take<int>(SC_COUNT);
   uint16_t* hyp_obs = ar.template take<uint16_t>((size_t)h_cap * C);
+  uint16_t* vslot = ar.template take<uint16_t>((size_t)C * p_max);
+  uint16_t* voff = ar.template take<uint16_t>(C + 1);
   uint8_t* valid = ar.template take<uint8_t>((size_t)C * p_max);
   uint8_t* hyp_nobs = ar.template take<uint8_t>(h_cap);
-  uint8_t* dets = ar.template take<uint8_t>(p_max);
   uint8_t* mask = ar.template take<uint8_t>((size_t)h_cap * p_max);
   uint8_t* star = ar.template take<uint8_t>((size_t)h_cap * p_max);
   uint8_t* prime = ar.template take<uint8_t>((size_t)h_cap * p_max);
@@ -70,16 +69,10 @@ SES_HD void assoc_ws_layout(A& ar, int C, int p_max, int h_cap, bool nk_inside, 
   uint8_t* cov_r = ar.template take<uint8_t>(h_cap);
   uint8_t* cov_c = ar.template take<uint8_t>(p_max);
   uint8_t* handled = ar.template take<uint8_t>(p_max);
-  const int tcap = assoc_triple_cap(C, p_max);
-  double* obs_cost = ar.template take<double>(tcap);
-  uint16_t* hoff = ar.template take<uint16_t>(h_cap + 1);
-  uint8_t* obs_has = ar.template take<uint8_t>(tcap);
-  uint8_t* r2h = ar.template take<uint8_t>(tcap ? (size_t)C * p_max : 0);
   if (ws) {
-    ws->obs_cost = obs_cost; ws->hoff = hoff; ws->obs_has = obs_has; ws->r2h = r2h; ws->triple_cap = tcap;
     ws->cost = cost; ws->dist = dist; if (nk_inside) ws->nk = nk; ws->kmask = kmask; ws->pscore = pscore;
-    ws->assignment = assignment; ws->scal = scal; ws->hyp_obs = hyp_obs; ws->valid = valid;
-    ws->hyp_nobs = hyp_nobs; ws->dets = dets; ws->mask = mask; ws->star = star; ws->prime = prime;
+    ws->assignment = assignment; ws->scal = scal; ws->hyp_obs = hyp_obs; ws->vslot = vslot; ws->voff = voff;
+    ws->valid = valid; ws->hyp_nobs = hyp_nobs; ws->mask = mask; ws->star = star; ws->prime = prime;
     ws->nstar = nstar; ws->cov_r = cov_r; ws->cov_c = cov_c; ws->handled = handled;
   }
 }
@@ -88,6 +81,12 @@ inline size_t assoc_ws_bytes(int C, int p_max, int h_cap, bool nk_inside) {
   ArenaSizer s;
   assoc_ws_layout(s, C, p_max, h_cap, nk_inside, nullptr);
   return (s.used + 15) / 16 * 16;
+}
+
+// entries of the per-frame pair table
+SES_HD size_t assoc_pair_table_entries(int C, int p_max) {
+  const size_t n = (size_t)C * p_max;
+  return n * (n - 1) / 2 + 1;
 }
 
 // Symmetric point-to-epipolar-line distance d1 + d2 in float (S3D:355-362):
@@ -357,13 +356,51 @@ SES_HD void associate_frame(Team& tm, const Tables& tb, int p_max, int h_cap, co
       }
     ws.valid[cd] = n_valid > NKP / 2 ? 1 : 0;
     ws.kmask[cd] = strict;
-    ws.pscore[cd] = d < np(c) ? persons[cd].score : 0.f;
+  });
+  // compact, camera-major list of the valid detections
+  tm.single([&] {
+    int n = 0;
+    for (int c = 0; c < C; ++c) {
+      ws.voff[c] = (uint16_t)n;
+      for (int d = 0; d < np(c); ++d)
+        if (ws.valid[c * p_max + d]) { ws.vslot[n] = (uint16_t)(c * p_max + d); ++n; }
+    }
+    ws.voff[C] = (uint16_t)n;
+    ws.scal[SC_N_VALID] = n;
+  });
+  const int n_valid = ws.scal[SC_N_VALID];
+  tm.pfor(n_valid, [&](int a) { ws.pscore[a] = persons[ws.vslot[a]].score; });
+
+  // phase 1 - pair table: mean symmetric epipolar distance of every cross-camera pair of valid detections,
+  // the inner loop of calcCost (S3D:347-368), joints in ascending order, float distances summed in double
+  tm.pfor(n_valid * (n_valid - 1) / 2, [&](int e) {
+    // e -> (a, b), a < b: row b of the strictly lower triangle starts at b(b-1)/2
+    int b = (int)((1.0f + ses_sqrt(1.0f + 8.0f * (float)e)) * 0.5f);
+    while (b * (b - 1) / 2 > e) --b;
+    while ((b + 1) * b / 2 <= e) ++b;
+    const int a = e - b * (b - 1) / 2;
+    const int sa = ws.vslot[a], sb = ws.vslot[b];
+    const int ca = sa / p_max, cb = sb / p_max;
+    if (ca == cb) return;
+    const float* F = tb.F + (size_t)fundamental_idx(tb, ca, cb) * 9;
+    const float* hk = ws.nk + ((size_t)sa * NKP) * 2;
+    const float* dk = ws.nk + ((size_t)sb * NKP) * 2;
+    uint32_t m = ws.kmask[sa] & ws.kmask[sb];
+    double cost = 0.;
+    int n_joints = 0;
+    while (m) {
+      const int k = ses_ctz(m);
+      m &= m - 1;
+      cost += static_cast<double>(epipolar_symmetric(F, hk[2 * k], hk[2 * k + 1], dk[2 * k], dk[2 * k + 1]));
+      ++n_joints;
+    }
+    ws.E[e] = n_joints > 0 ? cost / n_joints : -1.0;
   });
 
-  auto add_hyp = [&](int cam, int det) {  // push_back of a one-observation hypothesis
+  auto add_hyp = [&](int a) {  // push_back of a one-observation hypothesis
     const int h = ws.scal[SC_N_HYP];
     if (h >= h_cap) { ws.scal[SC_OVERFLOW] = 1; return; }
-    ws.hyp_obs[(size_t)h * C] = (uint16_t)((cam << 8) | det);
+    ws.hyp_obs[(size_t)h * C] = (uint16_t)a;
     ws.hyp_nobs[h] = 1;
     ws.scal[SC_N_HYP] = h + 1;
   };
@@ -377,142 +414,61 @@ SES_HD void associate_frame(Team& tm, const Tables& tb, int p_max, int h_cap, co
     if (n_with >= 2) {
       for (c = 0; c < C; ++c) {
         if (np(c) == 0) continue;
-        for (int d = 0; d < np(c); ++d)
-          if (ws.valid[c * p_max + d]) add_hyp(c, d);
+        for (int a = ws.voff[c]; a < ws.voff[c + 1]; ++a) add_hyp(a);
         if (ws.scal[SC_N_HYP] > 0) { ++c; break; }
       }
     }
     ws.scal[SC_CURSOR] = c;
   });
 
-  for (int cam = ws.scal[SC_CURSOR]; cam < C; ++cam) {  // S3D:588-674
-    if (np(cam) == 0) continue;
-    tm.single([&] {
-      int n = 0;
-      for (int d = 0; d < np(cam); ++d)
-        if (ws.valid[cam * p_max + d]) ws.dets[n++] = (uint8_t)d;
-      ws.scal[SC_N_DET] = n;
-      int sum = 0;
-      if (ws.triple_cap > 0 && n > 0) {  // observation ranks for triple mode
-        const int nh = ws.scal[SC_N_HYP];
-        for (int h = 0; h < nh; ++h) {
-          ws.hoff[h] = (uint16_t)sum;
-          for (int o = 0; o < ws.hyp_nobs[h]; ++o) ws.r2h[sum + o] = (uint8_t)h;
-          sum += ws.hyp_nobs[h];
-        }
-        ws.hoff[nh] = (uint16_t)sum;
-      }
-      ws.scal[SC_NOBS_SUM] = sum;
-    });
-    const int n_det = ws.scal[SC_N_DET], n_hyp = ws.scal[SC_N_HYP];
-    if (n_det == 0) continue;
-    const int S = ws.scal[SC_NOBS_SUM];
-    const bool triple_mode = ws.triple_cap > 0 && S * n_det <= ws.triple_cap && n_hyp <= 255;
+  // phase 2 - camera rounds (S3D:588-674)
+  for (int cam = ws.scal[SC_CURSOR]; cam < C; ++cam) {
+    const int b0 = ws.voff[cam], n_det = ws.voff[cam + 1] - b0, n_hyp = ws.scal[SC_N_HYP];
+    if (n_det == 0) continue;  // covers "no person" and "no valid person" (S3D:539-541, 608-609)
 
-    if (triple_mode) {
-      // inner loop of calcCost (S3D:347-365) for one (observation, detection) pair per thread
-      tm.pfor(S * n_det, [&](int t) {
-        const int di = t / S, r = t % S;
-        const int h = ws.r2h[r], o = r - ws.hoff[h];
-        const int dslot = cam * p_max + ws.dets[di];
-        const float* dk = ws.nk + ((size_t)dslot * NKP) * 2;
-        const int oc = ws.hyp_obs[(size_t)h * C + o] >> 8, od = ws.hyp_obs[(size_t)h * C + o] & 255;
-        const float* F = tb.F + (size_t)fundamental_idx(tb, oc, cam) * 9;
-        const float* hk = ws.nk + ((size_t)(oc * p_max + od) * NKP) * 2;
-        double cost = 0.;
-        uint32_t m = ws.kmask[oc * p_max + od] & ws.kmask[dslot];   // joints valid in both, ascending order
-        int n_joints = 0;
-        while (m) {
-          const int k = ses_ctz(m);
-          m &= m - 1;
-          cost += static_cast<double>(epipolar_symmetric(F, hk[2 * k], hk[2 * k + 1], dk[2 * k], dk[2 * k + 1]));
-          ++n_joints;
-        }
-        if (n_joints > 0) cost /= n_joints;
-        ws.obs_cost[t] = cost;
-        ws.obs_has[t] = n_joints > 0 ? 1 : 0;
-      });
-      // outer part of calcCost (S3D:367-389): observations in order, one cost-matrix entry per thread
-      tm.pfor(n_hyp * n_det, [&](int e) {
-        const int h = e % n_hyp, di = e / n_hyp;
-        const int n_obs = ws.hyp_nobs[h];
-        double total = 0., tmp_veto = 0.;
-        int n_used = 0;
-        const double tolerance = 1.0 - 1.0 / (2 * n_obs), veto_delta = 1.0 / n_obs;
-        for (int o = 0; o < n_obs; ++o) {
-          const int t = di * S + ws.hoff[h] + o;
-          if (ws.obs_has[t]) {
-            const double cost = ws.obs_cost[t];
-            const int oc = ws.hyp_obs[(size_t)h * C + o] >> 8, od = ws.hyp_obs[(size_t)h * C + o] & 255;
-            total += cost;
-            ++n_used;
-            if (cost > max_epi && (ws.pscore[oc * p_max + od] > 0.5f || n_obs == 1)) tmp_veto += veto_delta;
-          }
-        }
-        bool veto = tmp_veto > tolerance;
-        double c;
-        if (n_used > 0) c = total / n_used;
-        else { veto = true; c = MAX_COSTS; }
-        ws.cost[e] = c;
-        ws.mask[e] = (!veto && c < max_epi) ? 1 : 0;
-      });
-    } else
-
-    // cost matrix, one (hypothesis, detection) entry per thread: calcCost S3D:335-390
+    // cost matrix entry = outer part of calcCost (S3D:367-389) over table lookups, observations in order
     tm.pfor(n_hyp * n_det, [&](int e) {
-      const int h = e % n_hyp, di = e / n_hyp;
-      const int dslot = cam * p_max + ws.dets[di];
-      const float* dk = ws.nk + ((size_t)dslot * NKP) * 2;
+      const int h = e % n_hyp, b = b0 + e / n_hyp;
       const int n_obs = ws.hyp_nobs[h];
       double total = 0., tmp_veto = 0.;
       int n_used = 0;
       const double tolerance = 1.0 - 1.0 / (2 * n_obs), veto_delta = 1.0 / n_obs;
+      const double* Eb = ws.E + (size_t)b * (b - 1) / 2;
       for (int o = 0; o < n_obs; ++o) {
-        const int oc = ws.hyp_obs[(size_t)h * C + o] >> 8, od = ws.hyp_obs[(size_t)h * C + o] & 255;
-        const float* F = tb.F + (size_t)fundamental_idx(tb, oc, cam) * 9;
-        const float* hk = ws.nk + ((size_t)(oc * p_max + od) * NKP) * 2;
-        double cost = 0.;
-        uint32_t m = ws.kmask[oc * p_max + od] & ws.kmask[dslot];
-        int n_joints = 0;
-        while (m) {
-          const int k = ses_ctz(m);
-          m &= m - 1;
-          cost += static_cast<double>(epipolar_symmetric(F, hk[2 * k], hk[2 * k + 1], dk[2 * k], dk[2 * k + 1]));
-          ++n_joints;
-        }
-        if (n_joints > 0) {
-          cost /= n_joints;
+        const int a = ws.hyp_obs[(size_t)h * C + o];
+        const double cost = Eb[a];
+        if (cost >= 0.0) {  // the pair shared at least one joint
           total += cost;
           ++n_used;
-          if (cost > max_epi && (ws.pscore[oc * p_max + od] > 0.5f || n_obs == 1)) tmp_veto += veto_delta;
+          if (cost > max_epi && (ws.pscore[a] > 0.5f || n_obs == 1)) tmp_veto += veto_delta;
         }
       }
       bool veto = tmp_veto > tolerance;
       double c;
       if (n_used > 0) c = total / n_used;
       else { veto = true; c = MAX_COSTS; }
-      ws.cost[e] = c;  // column-major: h + n_hyp * di
+      ws.cost[e] = c;  // column-major: h + n_hyp * d
       ws.mask[e] = (!veto && c < max_epi) ? 1 : 0;
     });
 
-    tm.single([&] {
-      // provisional assignment: the last passing detection per hypothesis (S3D:616-626)
-      for (int h = 0; h < n_hyp; ++h) ws.assignment[h] = -1;
-      bool ambiguous = false;
-      for (int d = 0; d < n_det; ++d) {
-        int col = 0;
-        for (int h = 0; h < n_hyp; ++h)
-          if (ws.mask[h + n_hyp * d]) { ws.assignment[h] = d; ++col; }
-        ambiguous = ambiguous || col > 1;
+    // provisional assignment = the last passing detection per hypothesis (S3D:616-626); the Munkres solve is
+    // needed when any row or column of the mask has more than one hit (S3D:628). One thread per row / column;
+    // the flag write is the same value from every writer.
+    tm.single([&] { ws.scal[SC_AMBIG] = 0; });
+    tm.pfor(n_hyp + n_det, [&](int i) {
+      int cnt = 0;
+      if (i < n_hyp) {
+        int last = -1;
+        for (int d = 0; d < n_det; ++d)
+          if (ws.mask[i + n_hyp * d]) { last = d; ++cnt; }
+        ws.assignment[i] = last;
+      } else {
+        const int d = i - n_hyp;
+        for (int h = 0; h < n_hyp; ++h) cnt += ws.mask[h + n_hyp * d];
       }
-      for (int h = 0; h < n_hyp && !ambiguous; ++h) {
-        int row = 0;
-        for (int d = 0; d < n_det; ++d) row += ws.mask[h + n_hyp * d];
-        ambiguous = row > 1;
-      }
-      ws.scal[SC_AMBIG] = ambiguous ? 1 : 0;
-      if (ambiguous) ++ws.scal[SC_N_HUNG];
+      if (cnt > 1) ws.scal[SC_AMBIG] = 1;
     });
+    tm.single([&] { if (ws.scal[SC_AMBIG]) ++ws.scal[SC_N_HUNG]; });
     if (ws.scal[SC_AMBIG]) {  // S3D:628-634: full Munkres on the cost matrix, solved by the team's first warp
       tm.warp0([&](auto& wt) { munkres_coop(wt, ws, ws.cost, n_hyp, n_det, ws.assignment); });
     }
@@ -522,15 +478,15 @@ SES_HD void associate_frame(Team& tm, const Tables& tb, int p_max, int h_cap, co
         const int d = ws.assignment[h];
         if (d < 0) continue;
         ws.handled[d] = 1;
-        if (!ws.mask[h + n_hyp * d]) add_hyp(cam, ws.dets[d]);
+        if (!ws.mask[h + n_hyp * d]) add_hyp(b0 + d);
         else {
           const int o = ws.hyp_nobs[h];
-          ws.hyp_obs[(size_t)h * C + o] = (uint16_t)((cam << 8) | ws.dets[d]);
+          ws.hyp_obs[(size_t)h * C + o] = (uint16_t)(b0 + d);
           ws.hyp_nobs[h] = (uint8_t)(o + 1);
         }
       }
       for (int d = 0; d < n_det; ++d)  // S3D:662-673
-        if (!ws.handled[d]) add_hyp(cam, ws.dets[d]);
+        if (!ws.handled[d]) add_hyp(b0 + d);
     });
   }
 
@@ -540,8 +496,8 @@ SES_HD void associate_frame(Team& tm, const Tables& tb, int p_max, int h_cap, co
   tm.pfor(n_hyp * C, [&](int i) {
     const int h = i / C, o = i % C;
     if (o < ws.hyp_nobs[h]) {
-      const int oc = ws.hyp_obs[(size_t)h * C + o] >> 8, od = ws.hyp_obs[(size_t)h * C + o] & 255;
-      hyp_det[h * C + oc] = (int8_t)od;
+      const int slot = ws.vslot[ws.hyp_obs[(size_t)h * C + o]];
+      hyp_det[h * C + slot / p_max] = (int8_t)(slot % p_max);
     }
   });
   tm.single([&] {

@@ -16,9 +16,9 @@ namespace ses3d {
 
 extern __shared__ __align__(16) unsigned char smem_raw[];
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_associate(const Tables tb, int n_frames, int p_max, int h_cap, const ses3d_person2d* __restrict__ persons,
-            const int32_t* __restrict__ n_persons, float* nk_scratch, int8_t* __restrict__ hyp_det,
+            const int32_t* __restrict__ n_persons, float* nk_scratch, double* pair_table, int8_t* __restrict__ hyp_det,
             int32_t* __restrict__ n_hyp, int32_t* __restrict__ n_hung, int32_t* overflow, int32_t* hyp_of_dump,
             int32_t* __restrict__ keep, uint32_t* __restrict__ work, int32_t* work_count) {
   const int f = blockIdx.x;
@@ -28,6 +28,7 @@ k_associate(const Tables tb, int n_frames, int p_max, int h_cap, const ses3d_per
   AssocWs ws;
   assoc_ws_layout(ar, C, p_max, h_cap, nk_scratch == nullptr, &ws);
   if (nk_scratch) ws.nk = nk_scratch + (size_t)f * C * p_max * NKP * 2;
+  ws.E = pair_table + (size_t)f * assoc_pair_table_entries(C, p_max);
   BlockTeam tm;
   int8_t* hd = hyp_det + (size_t)f * h_cap * C;
   associate_frame(tm, tb, p_max, h_cap, persons + (size_t)f * C * p_max, n_persons + (size_t)f * C, ws, hd, n_hyp + f,
@@ -121,9 +122,12 @@ size_t associate_smem_bytes(int n_cams, int p_max, int h_cap, bool* needs_scratc
   return b;
 }
 
+size_t associate_pair_table_bytes(int n_cams, int p_max) { return assoc_pair_table_entries(n_cams, p_max) * sizeof(double); }
+
 cudaError_t launch_associate(const Tables& tb, LaunchDims d, const ses3d_person2d* persons, const int32_t* n_persons,
-                             float* nk_scratch, int8_t* hyp_det, int32_t* n_hyp, int32_t* n_hung, int32_t* overflow,
-                             int32_t* hyp_of_dump, int32_t* keep, uint32_t* work, int32_t* work_count, cudaStream_t st) {
+                             float* nk_scratch, double* pair_table, int8_t* hyp_det, int32_t* n_hyp, int32_t* n_hung,
+                             int32_t* overflow, int32_t* hyp_of_dump, int32_t* keep, uint32_t* work,
+                             int32_t* work_count, cudaStream_t st) {
   bool scratch;
   const size_t smem = associate_smem_bytes(tb.n_cams, d.p_max, d.h_cap, &scratch);
   if (smem > kSmemBudget) return cudaErrorInvalidConfiguration;
@@ -132,11 +136,12 @@ cudaError_t launch_associate(const Tables& tb, LaunchDims d, const ses3d_person2
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(work_count, 0, sizeof(int32_t), st);
   if (e != cudaSuccess) return e;
-  int threads = (tb.n_cams * d.p_max >= 256) ? 128 : 64;
-  if (const char* env = getenv("SES3D_ASSOC_THREADS")) threads = std::max(32, std::min(128, atoi(env) / 32 * 32));
+  if (!pair_table) return cudaErrorInvalidValue;
+  int threads = scratch ? 256 : 128;   // big rigs: hundreds of thousands of detection pairs per frame
+  if (const char* env = getenv("SES3D_ASSOC_THREADS")) threads = std::max(32, std::min(256, atoi(env) / 32 * 32));
   k_associate<<<d.n_frames, threads, smem, st>>>(tb, d.n_frames, d.p_max, d.h_cap, persons, n_persons,
-                                                 scratch ? nk_scratch : nullptr, hyp_det, n_hyp, n_hung, overflow,
-                                                 hyp_of_dump, keep, work, work_count);
+                                                 scratch ? nk_scratch : nullptr, pair_table, hyp_det, n_hyp, n_hung,
+                                                 overflow, hyp_of_dump, keep, work, work_count);
   return cudaGetLastError();
 }
 

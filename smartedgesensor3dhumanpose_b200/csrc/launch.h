@@ -12,9 +12,11 @@ struct LaunchDims {
 
 // K2: one CTA per frame. nk_scratch != nullptr selects the global-memory keypoint path.
 cudaError_t launch_associate(const Tables& tb, LaunchDims d, const ses3d_person2d* persons, const int32_t* n_persons,
-                             float* nk_scratch, int8_t* hyp_det, int32_t* n_hyp, int32_t* n_hung, int32_t* overflow,
-                             int32_t* hyp_of_dump, int32_t* keep, uint32_t* work, int32_t* work_count, cudaStream_t st);
+                             float* nk_scratch, double* pair_table, int8_t* hyp_det, int32_t* n_hyp, int32_t* n_hung,
+                             int32_t* overflow, int32_t* hyp_of_dump, int32_t* keep, uint32_t* work,
+                             int32_t* work_count, cudaStream_t st);
 size_t associate_smem_bytes(int n_cams, int p_max, int h_cap, bool* needs_scratch);
+size_t associate_pair_table_bytes(int n_cams, int p_max);   // per frame
 
 // K3: one warp per (frame, hypothesis) work item, persistent grid over the work list K2 wrote
 cudaError_t launch_triangulate(const Tables& tb, LaunchDims d, const ses3d_person2d* persons, const int8_t* hyp_det,

@@ -41,15 +41,17 @@ def compact_torch(raw_u8, n_frames, h_max):
     return torch.cat([xyz, score], dim=-1).contiguous()
 
 
-def gather_compact(compact, dst=0):
-    """Gather every rank's compact tensor on `dst` (list ordered by rank) - the path's only collective."""
+def gather_compact(compact, dst=0, shapes=None):
+    """Gather every rank's compact tensor on `dst` (list ordered by rank) - the path's only collective.
+    `shapes` (one per rank) skips the shape exchange when the caller already knows them."""
     import torch
     import torch.distributed as dist
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return [compact]
     world, rank = dist.get_world_size(), dist.get_rank()
-    shapes = [None] * world
-    dist.all_gather_object(shapes, tuple(compact.shape))
+    if shapes is None:
+        shapes = [None] * world
+        dist.all_gather_object(shapes, tuple(compact.shape))
     if dist.get_backend() == "nccl":
         # NCCL gather needs equal sizes: pad the frame dimension to the largest shard
         fmax = max(s[0] for s in shapes)

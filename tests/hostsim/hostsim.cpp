@@ -55,6 +55,7 @@ int hostsim_triangulate_batch(void* h, int32_t n_frames, int32_t p_max, const se
   const bool f64 = tb.prm.precision == SES3D_PRECISION_FP64;
   std::vector<unsigned char> wst((f64 ? tri_ws_bytes<double>(C) : tri_ws_bytes<float>(C)) + 64);
   std::vector<int8_t> hyp_det((size_t)h_max * C);
+  std::vector<double> pair_table(assoc_pair_table_entries(C, p_max));
   std::vector<ses3d_person_cov> tmp(h_max);
   std::vector<int32_t> keep(h_max);
   int32_t overflow = 0;
@@ -64,6 +65,7 @@ int hostsim_triangulate_batch(void* h, int32_t n_frames, int32_t p_max, const se
     Arena a1(wsa.data());
     AssocWs aws;
     assoc_ws_layout(a1, C, p_max, h_max, true, &aws);
+    aws.E = pair_table.data();
     int32_t n_hyp = 0, n_hung = 0;
     associate_frame(tm, tb, p_max, h_max, pf, n_persons + (size_t)f * C, aws, hyp_det.data(), &n_hyp, &n_hung, &overflow);
     if (n_hyp_out) n_hyp_out[f] = n_hyp;

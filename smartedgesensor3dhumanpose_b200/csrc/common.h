@@ -38,6 +38,7 @@ struct SkeletonModel {
 struct CamF {     // float view: normalize_keypoints (S3D:314-317) + Matrix34f (S3D:1208-1211)
   float P[12];
   float fx, fy, cx, cy;
+  float inv_fx2, inv_fxfy, inv_fy2, pad_;   // 1/(fx*fx), 1/(fx*fy), 1/(fy*fy): covariance scaling of the sigma points
 };
 struct CamD {     // double view: FP64 triangulation mode and reprojection (REP:152-163, 196-197)
   double P[12];

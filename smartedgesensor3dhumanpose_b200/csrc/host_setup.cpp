@@ -107,6 +107,8 @@ bool build_host_tables(int n_cams, const ses3d_camera* cams, const ses3d_params&
     cd.width = (double)cams[i].width; cd.height = (double)cams[i].height;
     cf.fx = static_cast<float>(cams[i].fx); cf.fy = static_cast<float>(cams[i].fy);   // S3D:314-317
     cf.cx = static_cast<float>(cams[i].cx); cf.cy = static_cast<float>(cams[i].cy);
+    cf.inv_fx2 = 1.0f / (cf.fx * cf.fx); cf.inv_fxfy = 1.0f / (cf.fx * cf.fy); cf.inv_fy2 = 1.0f / (cf.fy * cf.fy);
+    cf.pad_ = 0.f;
     // camera centre: inverse of the affine transform, linear part inverted by cofactors (S3D:1191)
     const double a = T[0], b = T[1], c = T[2], d = T[4], e = T[5], f = T[6], g = T[8], h = T[9], k = T[10];
     const double A = e * k - f * h, B = -(d * k - f * g), Cc = d * h - e * g;

@@ -13,7 +13,7 @@ extern __shared__ __align__(16) unsigned char smem_raw[];
 constexpr int kWarpsPerCta = 4;
 
 template <class T>
-__global__ void __launch_bounds__(32 * kWarpsPerCta)
+__global__ void __launch_bounds__(32 * kWarpsPerCta, sizeof(T) == 4 ? 6 : 1)
 k_triangulate(const Tables tb, int p_max, int h_cap, size_t ws_bytes, const ses3d_person2d* __restrict__ persons,
               const int8_t* __restrict__ hyp_det, const uint32_t* __restrict__ work,
               const int32_t* __restrict__ work_count, ses3d_person_cov* __restrict__ tmp, int32_t* __restrict__ keep) {

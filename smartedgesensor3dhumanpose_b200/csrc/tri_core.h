@@ -45,6 +45,7 @@ struct TriWs {
   T* defl;            // [17][14] deflated base system: v[4], a0, b0[3], C0[6]
   T* cov;             // [17][6]  running covariance sums
   int* soff;          // [18] sample offsets (sample 0 of each joint is the base solve, already known)
+  uint8_t* kmap;      // [17*4*C] sample index -> joint
   T* Y;               // [Y_CHUNK][3] transformed sigma points of the current pass  (aliases the LOO scratch)
   T* looX;            // [loo_cap][3]
   double* looErr;     // [loo_cap]
@@ -55,9 +56,9 @@ struct TriWs {
 template <class T, class A>
 SES_HD void tri_ws_layout(A& ar, int C, TriWs<T>* ws) {
   double* jerr = ar.template take<double>(NKP);
-  ses3d_keypoint_cov* kp = ar.template take<ses3d_keypoint_cov>(NFUS);
-  // union { Y[Y_CHUNK][3] ; looErr[loo_cap] + looX[loo_cap][3] }
-  const size_t u_bytes = (size_t)Y_CHUNK * 3 * sizeof(T);
+  // union { Y[Y_CHUNK][3] ; looErr[loo_cap] + looX[loo_cap][3] ; kp[21] (written after the last sigma-point pass) }
+  size_t u_bytes = (size_t)Y_CHUNK * 3 * sizeof(T);
+  if (u_bytes < NFUS * sizeof(ses3d_keypoint_cov)) u_bytes = NFUS * sizeof(ses3d_keypoint_cov);
   const int loo_cap = (int)(u_bytes / (8 + 3 * sizeof(T)));
   double* u = ar.template take<double>((u_bytes + 7) / 8);
   ViewKp<T>* vw = ar.template take<ViewKp<T>>((size_t)C * NKP);
@@ -70,13 +71,14 @@ SES_HD void tri_ws_layout(A& ar, int C, TriWs<T>* ws) {
   int* soff = ar.template take<int>(NKP + 1);
   int* scal = ar.template take<int>(4);
   uint8_t* vlist = ar.template take<uint8_t>((size_t)NKP * C);
+  uint8_t* kmap = ar.template take<uint8_t>((size_t)NKP * 4 * C);
   uint8_t* obs_cam = ar.template take<uint8_t>(C);
   uint8_t* obs_det = ar.template take<uint8_t>(C);
   if (ws) {
-    ws->jerr = jerr; ws->kp = kp; ws->Y = reinterpret_cast<T*>(u);
+    ws->jerr = jerr; ws->kp = reinterpret_cast<ses3d_keypoint_cov*>(u); ws->Y = reinterpret_cast<T*>(u);
     ws->looErr = u; ws->looX = reinterpret_cast<T*>(u + loo_cap); ws->loo_cap = loo_cap;
     ws->vw = vw; ws->jX = jX; ws->defl = defl; ws->cov = cov; ws->jscore = jscore; ws->jn = jn;
-    ws->jflag = jflag; ws->soff = soff; ws->scal = scal; ws->vlist = vlist; ws->obs_cam = obs_cam; ws->obs_det = obs_det;
+    ws->jflag = jflag; ws->soff = soff; ws->scal = scal; ws->vlist = vlist; ws->kmap = kmap; ws->obs_cam = obs_cam; ws->obs_det = obs_det;
   }
 }
 
@@ -117,10 +119,21 @@ SES_HD void normalize_kp(const Tables& tb, int cam, const ses3d_keypoint2d& kp, 
 // normalised 2x2 covariance (S3D:324-327) and its Cholesky factor (mod_samples S3D:473-475)
 SES_HD void cholesky_cov(const Tables& tb, int cam, const ses3d_keypoint2d& kp, float& l11, float& l21, float& l22) {
   const CamF& cm = tb.camf[cam];
+#if defined(__CUDA_ARCH__)
+  // covariance-only path (tolerance-checked): reciprocal scaling and SFU rsqrt instead of 4 divides + 2 sqrt;
+  // a zero variance still yields NaN like the reference's 0/0 (S3D:473-475)
+  const float cxx = kp.cov[0] * cm.inv_fx2, cxy = kp.cov[1] * cm.inv_fxfy, cyy = kp.cov[2] * cm.inv_fy2;
+  const float r11 = rsqrtf(cxx);
+  l11 = cxx * r11;
+  l21 = cxy * r11;
+  const float t = cyy - l21 * l21;
+  l22 = t * rsqrtf(t);
+#else
   const float cxx = kp.cov[0] / (cm.fx * cm.fx), cxy = kp.cov[1] / (cm.fx * cm.fy), cyy = kp.cov[2] / (cm.fy * cm.fy);
   l11 = ses_sqrt(cxx);
   l21 = cxy / l11;
   l22 = ses_sqrt(cyy - l21 * l21);
+#endif
 }
 SES_HD void cholesky_cov(const Tables& tb, int cam, const ses3d_keypoint2d& kp, double& l11, double& l21, double& l22) {
   const CamD& cm = tb.camd[cam];
@@ -159,8 +172,12 @@ SES_HD void solve_weighted(const Tables& tb, const TriWs<T>& ws, int k, const ui
     const ViewKp<T>& v = ws.vw[o * NKP + k];
     const T* P = CamSel<T>::P(tb, ws.obs_cam[o]);
     T r[4];
-    dlt_row<T>(P, 0, v.x, v.conf, true, r); gram_add<T>(G, r, 1.0);
-    dlt_row<T>(P, 1, v.y, v.conf, true, r); gram_add<T>(G, r, 1.0);
+    dlt_row_fast<T>(P, 0, v.x, r);
+    r[0] *= v.conf; r[1] *= v.conf; r[2] *= v.conf; r[3] *= v.conf;   // weight_by_conf, S3D:450-453
+    gram_add<T>(G, r, 1.0);
+    dlt_row_fast<T>(P, 1, v.y, r);
+    r[0] *= v.conf; r[1] *= v.conf; r[2] *= v.conf; r[3] *= v.conf;
+    gram_add<T>(G, r, 1.0);
   }
   T e[4];
   smallest_eigvec4_fast<T>(G, e);
@@ -267,7 +284,6 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
     const int cam = ws.obs_cam[o];
     normalize_kp(tb, cam, persons[cam * p_max + ws.obs_det[o]].keypoints[k], ws.vw[i]);
   });
-  tm.pfor(NFUS, [&](int s) { zero_kp(ws.kp[s]); });
 
   // per joint: gather views, weighted DLT, 3-view epipolar rejection (S3D:718-792)
   tm.pfor(NKP, [&](int k) {
@@ -441,14 +457,16 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
     ws.soff[NKP] = off;
   });
   const int n_samples_total = ws.soff[NKP];
+  tm.pfor(NKP, [&](int k) {
+    for (int i = ws.soff[k]; i < ws.soff[k + 1]; ++i) ws.kmap[i] = (uint8_t)k;
+  });
 
   // unscented sigma points 1..4n (S3D:471-506) of all joints in one index space, Y_CHUNK per pass
   for (int s0 = 0; s0 < n_samples_total; s0 += Y_CHUNK) {
     const int cnt = (n_samples_total - s0) < Y_CHUNK ? (n_samples_total - s0) : Y_CHUNK;
     tm.pfor(cnt, [&](int ii) {
       const int i = s0 + ii;
-      int k = 0;
-      while (ws.soff[k + 1] <= i) ++k;
+      const int k = ws.kmap[i];
       const int s = i - ws.soff[k];
       const int n = ws.jn[k];
       const int vi = s >> 2, m = s & 3;
@@ -496,7 +514,7 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
         }
         smallest_eigvec4<T>(G, e);
       }
-      const T inv = T(1) / e[3];
+      const T inv = ses_rcp(e[3]);
       ws.Y[ii * 3] = e[0] * inv; ws.Y[ii * 3 + 1] = e[1] * inv; ws.Y[ii * 3 + 2] = e[2] * inv;
     });
     // covariance about the weighted-DLT point, samples in the reference's order (S3D:521-522)
@@ -520,7 +538,8 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
     });
   }
 
-  // output keypoints (S3D:849-857)
+  // output keypoints (S3D:849-857); the record shares storage with the sigma-point staging, which is done
+  tm.pfor(NFUS, [&](int s) { zero_kp(ws.kp[s]); });
   tm.pfor(NKP, [&](int k) {
     if (ws.jn[k] < 2) return;
     ses3d_keypoint_cov& o = ws.kp[tb.model.fusion_idx[k]];

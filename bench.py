@@ -73,7 +73,8 @@ def algorithmic_work(fr, res, thr=0.30):
     tot = per_cam.sum(1)
     pairs = ((tot ** 2 - (per_cam ** 2).sum(1)) / 2).sum()      # sum over joints of cross-camera pairs
     assoc_flops = 50.0 * pairs
-    joints_out = int((res["persons3d"]["keypoints"]["score"] > 0).sum())
+    live = np.arange(res["persons3d"].shape[1])[None, :] < res["n_out"][:, None]
+    joints_out = int(((res["persons3d"]["keypoints"]["score"] > 0) & live[..., None]).sum())
     rep_flops = 250.0 * joints_out * C
     bytes_in = float(n_persons.sum()) * 428
     bytes_out3d = float(res["n_out"].sum()) * 1684
@@ -358,6 +359,17 @@ def main():
                         "frac": work["bytes_per_frame"] * B / (step_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                         "algorithmic_bytes_per_frame": work["bytes_per_frame"]},
                 "traffic": None}
+    # DRAM traffic of the dominant kernel per launch from the committed ncu --set full capture of the same launch
+    # shape (scripts/profile_step.py, profiles/<round>_ncu_full_summary.json); null if no matching capture
+    try:
+        cap = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())
+        ent = cap.get(a.workload, {}).get(f"k_{dom}")
+        if ent and int(ent["frames_per_launch"]) == min(B, 16384):
+            roofline["traffic"] = {"dram_bytes_per_launch": ent["dram_bytes_read"] + ent["dram_bytes_write"],
+                                   "dram_bytes_read": ent["dram_bytes_read"], "dram_bytes_write": ent["dram_bytes_write"],
+                                   "source": ent["source"]}
+    except (OSError, ValueError, KeyError):
+        pass
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

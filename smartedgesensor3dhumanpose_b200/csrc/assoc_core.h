@@ -103,113 +103,10 @@ SES_HD float epipolar_symmetric(const float* F, float x1, float y1, float x2, fl
   return d1 + d2;
 }
 
-// Munkres on the column-major n_r x n_c matrix `in` (Hungarian.cpp:60-397). The reference's
-// mutual recursion step2a/2b/3/4/5 is unrolled into a state machine; scan orders, the
-// |x| < DBL_EPSILON zero test and the +-h updates are kept so ties resolve identically.
-SES_HD void munkres_serial(const AssocWs& ws, const double* in, int n_r, int n_c, int* assignment) {
-  const int n_e = n_r * n_c;
-  double* dist = ws.dist;
-  uint8_t *star = ws.star, *prime = ws.prime, *nstar = ws.nstar, *cov_r = ws.cov_r, *cov_c = ws.cov_c;
-  for (int i = 0; i < n_e; ++i) { dist[i] = in[i]; star[i] = 0; prime[i] = 0; nstar[i] = 0; }
-  for (int r = 0; r < n_r; ++r) { cov_r[r] = 0; assignment[r] = -1; }
-  for (int c = 0; c < n_c; ++c) cov_c[c] = 0;
-  int min_dim;
-  if (n_r <= n_c) {  // Hungarian.cpp:95-131: row reduction, row-major first-zero starring
-    min_dim = n_r;
-    for (int r = 0; r < n_r; ++r) {
-      double mn = dist[r];
-      for (int c = 1; c < n_c; ++c) { const double v = dist[r + n_r * c]; if (v < mn) mn = v; }
-      for (int c = 0; c < n_c; ++c) dist[r + n_r * c] -= mn;
-    }
-    for (int r = 0; r < n_r; ++r)
-      for (int c = 0; c < n_c; ++c)
-        if (fabs(dist[r + n_r * c]) < DBL_EPSILON && !cov_c[c]) { star[r + n_r * c] = 1; cov_c[c] = 1; break; }
-  } else {  // Hungarian.cpp:132-170: column reduction, column-major starring
-    min_dim = n_c;
-    for (int c = 0; c < n_c; ++c) {
-      double mn = dist[n_r * c];
-      for (int r = 1; r < n_r; ++r) { const double v = dist[r + n_r * c]; if (v < mn) mn = v; }
-      for (int r = 0; r < n_r; ++r) dist[r + n_r * c] -= mn;
-    }
-    for (int c = 0; c < n_c; ++c)
-      for (int r = 0; r < n_r; ++r)
-        if (fabs(dist[r + n_r * c]) < DBL_EPSILON && !cov_r[r]) {
-          star[r + n_r * c] = 1; cov_c[c] = 1; cov_r[r] = 1; break;
-        }
-    for (int r = 0; r < n_r; ++r) cov_r[r] = 0;
-  }
-  enum { S2A, S2B, S3, S4, S5, DONE };
-  int st = S2B, row4 = 0, col4 = 0;
-  while (st != DONE) {
-    if (st == S2A) {  // cover every column holding a star (Hungarian.cpp:222-242)
-      for (int c = 0; c < n_c; ++c)
-        for (int r = 0; r < n_r; ++r)
-          if (star[r + n_r * c]) { cov_c[c] = 1; break; }
-      st = S2B;
-    } else if (st == S2B) {  // Hungarian.cpp:245-266
-      int n = 0;
-      for (int c = 0; c < n_c; ++c) n += cov_c[c] ? 1 : 0;
-      st = (n == min_dim) ? DONE : S3;
-    } else if (st == S3) {  // prime uncovered zeros, column-outer scan (Hungarian.cpp:269-309)
-      bool zeros = true, to4 = false;
-      while (zeros && !to4) {
-        zeros = false;
-        for (int c = 0; c < n_c && !to4; ++c) {
-          if (cov_c[c]) continue;
-          for (int r = 0; r < n_r; ++r) {
-            if (!cov_r[r] && fabs(dist[r + n_r * c]) < DBL_EPSILON) {
-              prime[r + n_r * c] = 1;
-              int sc = 0;
-              for (; sc < n_c; ++sc)
-                if (star[r + n_r * sc]) break;
-              if (sc == n_c) { row4 = r; col4 = c; to4 = true; }
-              else { cov_r[r] = 1; cov_c[sc] = 0; zeros = true; }
-              break;
-            }
-          }
-        }
-      }
-      st = to4 ? S4 : S5;
-    } else if (st == S4) {  // augmenting path (Hungarian.cpp:312-363)
-      for (int i = 0; i < n_e; ++i) nstar[i] = star[i];
-      nstar[row4 + n_r * col4] = 1;
-      int sc = col4, sr = 0;
-      for (sr = 0; sr < n_r; ++sr)
-        if (star[sr + n_r * sc]) break;
-      while (sr < n_r) {
-        nstar[sr + n_r * sc] = 0;
-        int pc = 0;
-        for (; pc < n_c; ++pc)
-          if (prime[sr + n_r * pc]) break;
-        nstar[sr + n_r * pc] = 1;
-        sc = pc;
-        for (sr = 0; sr < n_r; ++sr)
-          if (star[sr + n_r * sc]) break;
-      }
-      for (int i = 0; i < n_e; ++i) { prime[i] = 0; star[i] = nstar[i]; }
-      for (int r = 0; r < n_r; ++r) cov_r[r] = 0;
-      st = S2A;
-    } else {  // S5: shift by the smallest uncovered element (Hungarian.cpp:366-397)
-      double h = DBL_MAX;
-      for (int r = 0; r < n_r; ++r)
-        if (!cov_r[r])
-          for (int c = 0; c < n_c; ++c)
-            if (!cov_c[c]) { const double v = dist[r + n_r * c]; if (v < h) h = v; }
-      for (int r = 0; r < n_r; ++r)
-        if (cov_r[r])
-          for (int c = 0; c < n_c; ++c) dist[r + n_r * c] += h;
-      for (int c = 0; c < n_c; ++c)
-        if (!cov_c[c])
-          for (int r = 0; r < n_r; ++r) dist[r + n_r * c] -= h;
-      st = S3;
-    }
-  }
-  for (int r = 0; r < n_r; ++r)  // buildassignmentvector (Hungarian.cpp:190-205)
-    for (int c = 0; c < n_c; ++c)
-      if (star[r + n_r * c]) { assignment[r] = c; break; }
-}
-
-// The same solver run cooperatively by a warp-sized team (lanes over rows / columns / entries):
+// Munkres on the column-major n_r x n_c matrix `in` (HungarianAlgorithm::assignmentoptimal, Hungarian.cpp:60-397).
+// The reference's mutual recursion step2a/2b/3/4/5 is unrolled into a state machine; scan orders, the
+// |x| < DBL_EPSILON zero test and the +-h updates are kept so ties resolve identically. The solver is run
+// cooperatively by a warp-sized team (lanes over rows / columns / entries):
 // every search of the reference ("first zero in this scan order") becomes a ballot + find-first-set over
 // the same index order, so primes, stars and covers - and therefore ties - resolve identically.
 template <class WT>
@@ -248,7 +145,11 @@ SES_HD void munkres_coop(WT& tm, const AssocWs& ws, const double* in, int n_r, i
   }
   enum { S2A, S2B, S3, S4, S5, DONE };
   int st = S2B, row4 = 0, col4 = 0;
-  while (st != DONE) {
+  // Every pass through S4 adds a star and every S5 uncovers a zero, so a finite matrix needs far fewer than
+  // 4 (n_r + n_c)^2 + 64 transitions; the cap only guards against non-finite costs (NaN keypoints), for which
+  // the reference's own behaviour is undefined - the kernel must never spin.
+  int budget = 4 * (n_r + n_c) * (n_r + n_c) + 64;
+  while (st != DONE && --budget > 0) {
     if (st == S2A) {  // Hungarian.cpp:222-242
       tm.pfor(n_c, [&](int c) {
         for (int r = 0; r < n_r; ++r)

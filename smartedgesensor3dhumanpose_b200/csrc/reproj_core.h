@@ -145,12 +145,15 @@ SES_HD void reproject_frame(Team& tm, const Tables& tb, int h_max, int cap_rec, 
         if (ws.slot[cc * n_p + p] >= 0) ws.slot[cc * n_p + p] = s++;
       n_out[c0 + cc] = s;
     });
-    tm.pfor(ncc * n_p * words, [&](int e) {
-      const int rec = e / words, w = e % words;
+    // coalesced copy-out, 128 word slots per record (107 used) so that the index math is shifts only
+    tm.pfor(ncc * n_p * 128, [&](int e) {
+      const int rec = e >> 7, w = e & 127;
+      if (w >= words) return;
       const int s = ws.slot[rec];
       if (s >= 0) {
         const int cc = rec / n_p;
-        reinterpret_cast<uint32_t*>(out + (size_t)(c0 + cc) * h_max + s)[w] = reinterpret_cast<const uint32_t*>(ws.stage)[e];
+        reinterpret_cast<uint32_t*>(out + (size_t)(c0 + cc) * h_max + s)[w] =
+            reinterpret_cast<const uint32_t*>(ws.stage)[rec * words + w];
       }
     });
   }

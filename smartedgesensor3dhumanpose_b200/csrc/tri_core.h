@@ -354,7 +354,7 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
     if (used > 0) {
       tm.pfor(used, [&](int i) {
         int k = k0;
-        while (!(ws.jflag[k] && i < ws.soff[k] + ws.jn[k])) ++k;
+        while (k < NKP - 1 && !(ws.jflag[k] && i < ws.soff[k] + ws.jn[k])) ++k;
         T X[3];
         double e;
         solve_weighted<T>(tb, ws, k, ws.vlist + k * C, ws.jn[k], i - ws.soff[k], X, &e);

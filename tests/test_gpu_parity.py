@@ -265,3 +265,18 @@ def test_device_munkres_matches_reference_indices(shape):
     for i in range(len(costs)):
         want, _ = solver(costs[i])
         assert np.array_equal(got[i], want), (shape, i)
+
+
+def test_non_finite_inputs_terminate():
+    """NaN / inf keypoints (undefined behaviour in the reference) must not hang the GPU; other frames are unaffected."""
+    fr = helpers.make_workload("cfg5_ring8x4", 64)
+    persons = fr["persons"].copy()
+    persons["keypoints"]["x"][3] = np.nan
+    persons["keypoints"]["y"][7, 2] = np.inf
+    persons["keypoints"]["score"][9, 1, 0, :] = np.nan
+    gpu = api.GeometryPipeline(fr["cameras"])
+    rg = gpu.process_batch(persons, fr["n_persons"], 40)
+    ro = Oracle(fr["cameras"], ref_hungarian=False).triangulate_batch(fr["persons"], fr["n_persons"], 40)
+    ok = np.ones(64, bool); ok[[3, 7, 9]] = False
+    helpers.compare_persons3d(dict(persons3d=ro["persons3d"][ok], n_out=ro["n_out"][ok]),
+                              dict(persons3d=rg["persons3d"][ok], n_out=rg["n_out3d"][ok]), POS_TOL_FP32)

@@ -99,3 +99,24 @@ def test_capacity_overflow_reported():
     fr = helpers.make_workload("cfg5_ring8x4", 8)
     rh = HostSim(fr["cameras"]).triangulate_batch(fr["persons"], fr["n_persons"], 2)
     assert rh["status"] == -3
+
+
+@pytest.mark.parametrize("prm", [dict(pose_method=1), dict(max_epipolar_error=0.045), dict(pose_method=1, precision=1),
+                                 dict(merge_dist_thresh=0.8, max_joint_dist_to_root=1.0)])
+def test_parameter_variants(prm):
+    """h36m skeleton tables (S3D:111-145), the demo launch file's max_epi_dist = 0.045, and thresholds that make the
+    merge (S3D:984-996) and root-distance (S3D:937-953) branches fire."""
+    fr, ro, rh = _pair("cfg5_ring8x4", 120, params=default_params(**prm))
+    assert np.array_equal(ro["hyp_of"], rh["hyp_of"])
+    helpers.compare_persons3d(ro, rh, 1e-4 if prm.get("precision") else 1e-3)
+
+
+def test_merge_of_close_skeletons():
+    """Two detections of the same person that the association failed to join are merged when closer than 0.20 m."""
+    fr = helpers.make_workload("cfg5_ring8x4", 60)
+    prm = default_params(max_epipolar_error=0.0005)      # almost nothing associates across > 2 cameras -> many duplicates
+    ro = Oracle(fr["cameras"], prm).triangulate_batch(fr["persons"], fr["n_persons"], 40, n_threads=4)
+    rh = HostSim(fr["cameras"], prm).triangulate_batch(fr["persons"], fr["n_persons"], 40)
+    assert np.array_equal(ro["hyp_of"], rh["hyp_of"]) and np.array_equal(ro["n_out"], rh["n_out"])
+    assert (ro["n_hyp"] > 4).any()
+    helpers.compare_persons3d(ro, rh, 1e-3, cov_rtol=5e-2)

@@ -280,3 +280,15 @@ def test_non_finite_inputs_terminate():
     ok = np.ones(64, bool); ok[[3, 7, 9]] = False
     helpers.compare_persons3d(dict(persons3d=ro["persons3d"][ok], n_out=ro["n_out"][ok]),
                               dict(persons3d=rg["persons3d"][ok], n_out=rg["n_out3d"][ok]), POS_TOL_FP32)
+
+
+@pytest.mark.parametrize("prm", [dict(pose_method=1), dict(max_epipolar_error=0.045), dict(pose_method=1, precision=1),
+                                 dict(merge_dist_thresh=0.8, max_joint_dist_to_root=1.0), dict(max_epipolar_error=0.0005)])
+def test_parameter_variants(prm):
+    """h36m tables, the demo's max_epi_dist, and thresholds that fire the merge / root-distance branches."""
+    fr, orc, gpu, ro, rg = _run_pair("cfg5_ring8x4", 400, params=default_params(**prm), h_max=40)
+    assert np.array_equal(ro["hyp_of"], rg["hyp_of"])
+    helpers.compare_persons3d(ro, rg, POS_TOL_FP64 if prm.get("precision") else POS_TOL_FP32, cov_rtol=5e-2)
+    po = orc.reproject_batch(ro["persons3d"], ro["n_out"])
+    pg = gpu.reproject_batch(ro["persons3d"], ro["n_out"])
+    helpers.compare_persons2d(po, pg, px_tol=0.0)

@@ -48,9 +48,12 @@ def _stale(out: Path, deps):
 
 
 def build(force=False, verbose=False, ptxas_info=False):
+    headers = list(CSRC.glob("*.h")) + list(INCLUDE.glob("*.h")) + [Path(__file__)]
+    sources = [CSRC / name for name, _ in UNITS if (CSRC / name).exists()]
+    if not force and not ptxas_info and not _stale(LIB, sources + headers):
+        return LIB      # up to date (e.g. the prebuilt library shipped to the GPU box without the object files)
     nvcc = _nvcc()
     BUILD.mkdir(exist_ok=True)
-    headers = list(CSRC.glob("*.h")) + list(INCLUDE.glob("*.h")) + [Path(__file__)]
     objs = []
     for name, extra in UNITS:
         src = CSRC / name

@@ -228,6 +228,34 @@ int ses3d_synth_frames_device(int32_t n_cams, const ses3d_camera* cams, const se
                               int64_t first_frame, int32_t n_frames,
                               ses3d_person2d* persons, int32_t* n_persons, int32_t* gt_id, void* stream);
 
+/* ------------------------------------------------------------- frame assembler
+ * Host-side restatement of the approximate-time synchroniser that defines what a "frame" is in live
+ * operation (my_message_filters/sync_policies/approximate_time_vec.h:170-217, 488-626;
+ * synchronizer_vec.h:147-188) plus the worker loop's gating (S3D:1029-1057). Messages are (stamp, id) pairs;
+ * the caller keeps the payloads and packs emitted frames into the batch arrays (blanked camera = 0 persons). */
+typedef struct ses3d_assembler_config {
+  int32_t n_cams;
+  uint32_t queue_size;                   /* std::max(3u, 1 + n_cams / 4)   S3D:1219 */
+  int64_t inter_message_lower_bound_ns;  /* 20 ms                          S3D:1220 */
+  double age_penalty;                    /* 2.0                            S3D:1221 */
+  int64_t max_interval_ns;               /* < 0: unlimited (ros::DURATION_MAX) */
+  double max_sync_diff_s;                /* 0.067                          S3D:64, 1051 */
+} ses3d_assembler_config;
+typedef struct ses3d_assembler_s* ses3d_assembler;
+
+int ses3d_assembler_default_config(int32_t n_cams, ses3d_assembler_config* cfg);
+int ses3d_assembler_create(const ses3d_assembler_config* cfg, ses3d_assembler* out);
+int ses3d_assembler_destroy(ses3d_assembler a);
+/* One message of camera `cam`; returns how many frames became ready (>= 0) or an error (< 0). */
+int ses3d_assembler_add(ses3d_assembler a, int32_t cam, int64_t stamp_ns, int64_t msg_id);
+/* Next ready frame: ids / stamps_ns / blank [n_cams] (blank[i] = 1: camera i lags the pivot by more than
+ * max_sync_diff_s and is replaced by an empty list, S3D:1049-1057), pivot = camera with the newest stamp.
+ * Returns 1 when a frame was written, 0 when none is ready. */
+int ses3d_assembler_pop(ses3d_assembler a, int64_t* ids, int64_t* stamps_ns, uint8_t* blank, int32_t* pivot);
+/* stats: {frames emitted, frames skipped by the backwards-time rule (S3D:1043-1046), blanked cameras,
+ * messages dropped by queue overflow, tuples signalled by the synchroniser} */
+int ses3d_assembler_stats(ses3d_assembler a, int64_t stats[5]);
+
 #ifdef __cplusplus
 }
 #endif

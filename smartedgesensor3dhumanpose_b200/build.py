@@ -30,6 +30,7 @@ UNITS = [
     ("api.cpp", []),
     ("host_setup.cpp", []),
     ("synth.cpp", []),
+    ("frame_assembler.cpp", []),
 ]
 
 

@@ -11,7 +11,9 @@ LIB_PATH = PKG / "libses3d.so"
 EXPORTS = ("ses3d_default_params", "ses3d_create", "ses3d_destroy", "ses3d_get_tables", "ses3d_triangulate_batch",
            "ses3d_reproject_batch", "ses3d_process_batch", "ses3d_process_batch_ragged", "ses3d_reserve", "ses3d_munkres_batch", "ses3d_launch_count",
            "ses3d_set_profiling", "ses3d_last_kernel_ms", "ses3d_last_error_string", "ses3d_version",
-           "ses3d_synth_frames", "ses3d_synth_frames_device")
+           "ses3d_synth_frames", "ses3d_synth_frames_device", "ses3d_assembler_default_config",
+           "ses3d_assembler_create", "ses3d_assembler_destroy", "ses3d_assembler_add", "ses3d_assembler_pop",
+           "ses3d_assembler_stats")
 
 
 class Ses3dError(RuntimeError):
@@ -53,6 +55,12 @@ def load():
     L.ses3d_version.restype = C.c_char_p
     L.ses3d_synth_frames.argtypes = [i32, vp, C.POINTER(SynthConfig), i64, i32, vp, vp, vp, vp]
     L.ses3d_synth_frames_device.argtypes = [i32, vp, C.POINTER(SynthConfig), i64, i32, vp, vp, vp, vp]
+    L.ses3d_assembler_default_config.argtypes = [i32, vp]
+    L.ses3d_assembler_create.argtypes = [vp, C.POINTER(vp)]
+    L.ses3d_assembler_destroy.argtypes = [vp]
+    L.ses3d_assembler_add.argtypes = [vp, i32, i64, i64]
+    L.ses3d_assembler_pop.argtypes = [vp, vp, vp, vp, vp]
+    L.ses3d_assembler_stats.argtypes = [vp, vp]
     _lib = L
     return L
 

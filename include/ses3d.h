@@ -256,6 +256,23 @@ int ses3d_assembler_pop(ses3d_assembler a, int64_t* ids, int64_t* stamps_ns, uin
  * messages dropped by queue overflow, tuples signalled by the synchroniser} */
 int ses3d_assembler_stats(ses3d_assembler a, int64_t stats[5]);
 
+/* ------------------------------------------------------------- wire format
+ * ROS-free (de)serialisation of the ROS 1 wire encoding of person_msgs/Person2DList and PersonCovList
+ * (person_msgs/msg, std_msgs/Header, geometry_msgs Point/Pose/Vector3): replay of recorded message bodies
+ * through the batch ABI. decode_* return the number of persons in the message (which may exceed `cap`; only
+ * the first `cap` are written) or SES3D_E_INVALID for a truncated / malformed buffer. encode_* return the
+ * encoded size; nothing is written beyond `cap` (call with buf = NULL to size the buffer). */
+int ses3d_wire_decode_person2dlist(const uint8_t* buf, size_t len, uint32_t* seq, int64_t* stamp_ns, char* frame_id,
+                                   size_t frame_id_cap, float* fb_delay, ses3d_person2d* persons, int32_t cap);
+size_t ses3d_wire_encode_person2dlist(uint32_t seq, int64_t stamp_ns, const char* frame_id, float fb_delay,
+                                      const ses3d_person2d* persons, int32_t n, uint8_t* buf, size_t cap);
+int ses3d_wire_decode_personcovlist(const uint8_t* buf, size_t len, uint32_t* seq, int64_t* stamp_ns, char* frame_id,
+                                    size_t frame_id_cap, int64_t* ts_per_cam_ns, float* fb_delay_per_cam,
+                                    int32_t cam_cap, int32_t* n_cams, ses3d_person_cov* persons, int32_t cap);
+size_t ses3d_wire_encode_personcovlist(uint32_t seq, int64_t stamp_ns, const char* frame_id, int32_t n_cams,
+                                       const int64_t* ts_per_cam_ns, const float* fb_delay_per_cam,
+                                       const ses3d_person_cov* persons, int32_t n, uint8_t* buf, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

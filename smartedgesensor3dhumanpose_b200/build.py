@@ -31,6 +31,7 @@ UNITS = [
     ("host_setup.cpp", []),
     ("synth.cpp", []),
     ("frame_assembler.cpp", []),
+    ("wire.cpp", []),
 ]
 
 

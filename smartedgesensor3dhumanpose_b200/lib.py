@@ -13,7 +13,8 @@ EXPORTS = ("ses3d_default_params", "ses3d_create", "ses3d_destroy", "ses3d_get_t
            "ses3d_set_profiling", "ses3d_last_kernel_ms", "ses3d_last_error_string", "ses3d_version",
            "ses3d_synth_frames", "ses3d_synth_frames_device", "ses3d_assembler_default_config",
            "ses3d_assembler_create", "ses3d_assembler_destroy", "ses3d_assembler_add", "ses3d_assembler_pop",
-           "ses3d_assembler_stats")
+           "ses3d_assembler_stats", "ses3d_wire_decode_person2dlist", "ses3d_wire_encode_person2dlist",
+           "ses3d_wire_decode_personcovlist", "ses3d_wire_encode_personcovlist")
 
 
 class Ses3dError(RuntimeError):
@@ -61,6 +62,13 @@ def load():
     L.ses3d_assembler_add.argtypes = [vp, i32, i64, i64]
     L.ses3d_assembler_pop.argtypes = [vp, vp, vp, vp, vp]
     L.ses3d_assembler_stats.argtypes = [vp, vp]
+    sz = C.c_size_t
+    L.ses3d_wire_decode_person2dlist.argtypes = [vp, sz, vp, vp, vp, sz, vp, vp, i32]
+    L.ses3d_wire_encode_person2dlist.argtypes = [u32, i64, C.c_char_p, C.c_float, vp, i32, vp, sz]
+    L.ses3d_wire_encode_person2dlist.restype = sz
+    L.ses3d_wire_decode_personcovlist.argtypes = [vp, sz, vp, vp, vp, sz, vp, vp, i32, vp, vp, i32]
+    L.ses3d_wire_encode_personcovlist.argtypes = [u32, i64, C.c_char_p, i32, vp, vp, vp, i32, vp, sz]
+    L.ses3d_wire_encode_personcovlist.restype = sz
     _lib = L
     return L
 

@@ -1,0 +1,32 @@
+#!/usr/bin/env python
+"""Small end-to-end run for compute-sanitizer (memcheck / racecheck / initcheck / synccheck):
+    compute-sanitizer --tool racecheck python scripts/sanitize_smoke.py
+Covers the padded, ragged and device-generator paths, outlier branches, FP64 mode and the crowd (global-scratch) rig."""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+from smartedgesensor3dhumanpose_b200 import api  # noqa: E402
+from smartedgesensor3dhumanpose_b200.layouts import default_params, person2d_dtype, person_cov_dtype  # noqa: E402
+from tests import helpers  # noqa: E402
+
+for name, n, prm, outl in [("cfg2_hall16x6", 24, {}, 0.06), ("cfg5_ring8x4", 16, {"precision": 1, "lm_refine": 1}, 0.0),
+                           ("cfg4_crowd64x20", 1, {}, 0.0)]:
+    fr = helpers.make_workload(name, n, h_max=40 if outl else None) if outl else helpers.make_workload(name, n)
+    if outl:
+        helpers.inject_outliers(fr, outl)
+    pipe = api.GeometryPipeline(fr["cameras"], default_params(**prm))
+    r = pipe.process_batch(fr["persons"], fr["n_persons"], fr["h_max"])
+    dense = api.to_ragged(fr["persons"], fr["n_persons"])
+    C = fr["persons"].shape[1]
+    o3 = np.zeros(int(r["n_out3d"].sum()) + 4, person_cov_dtype)
+    o2 = np.zeros(int(r["n_out2d"].sum()) + 4, person2d_dtype)
+    t3, t2 = pipe.process_batch_ragged(dense, fr["n_persons"], fr["persons"].shape[2], fr["h_max"], o3,
+                                       np.zeros(n, np.int32), o2, np.zeros((n, C), np.int32))
+    print(name, "persons3d", int(r["n_out3d"].sum()), "ragged totals", t3, t2)
+    pipe.close()
+print("sanitize smoke done")

@@ -263,6 +263,8 @@ int run_batch(ses3d_handle_s* h, int stages, int n_frames, int p_max, const ses3
     cudaStream_t st = s.stream;
     CU(s.out3d.ensure((size_t)nf * h_max * sizeof(ses3d_person_cov)));
     CU(s.n_out3d.ensure((size_t)nf * 4));
+    // padded outputs travel whole: unused slots are zero, never stale device memory
+    if ((stages & TRI) && io3d) CU(cudaMemsetAsync(s.out3d.p, 0, (size_t)nf * h_max * sizeof(ses3d_person_cov), st));
     if (stages & TRI) {
       CU(s.persons.ensure((size_t)nf * C * p_max * sizeof(ses3d_person2d)));
       CU(s.n_persons.ensure((size_t)nf * C * 4));
@@ -296,6 +298,7 @@ int run_batch(ses3d_handle_s* h, int stages, int n_frames, int p_max, const ses3
     if (stages & REP) {
       CU(s.out2d.ensure((size_t)nf * C * h_max * sizeof(ses3d_person2d)));
       CU(s.n_out2d.ensure((size_t)nf * C * 4));
+      CU(cudaMemsetAsync(s.out2d.p, 0, (size_t)nf * C * h_max * sizeof(ses3d_person2d), st));
       int rc = reproject_on_device(h, st, nf, h_max, s.out3d.as<ses3d_person_cov>(), s.n_out3d.as<int32_t>(),
                                    s.out2d.as<ses3d_person2d>(), s.n_out2d.as<int32_t>());
       if (rc) return rc;

@@ -46,14 +46,16 @@ struct WarpTeam {
     for (int base = 0; base < n; base += 32) {
       const int i = base + lane;
       const unsigned b = __ballot_sync(0xffffffffu, i < n && pred(i));
-      if (b) return base + __ffs((int)b) - 1;
+      if (b) { __syncwarp(); return base + __ffs((int)b) - 1; }
     }
+    __syncwarp();   // the predicate's shared-memory reads are ordered before whatever the caller writes next
     return n;
   }
   template <class F> __device__ __forceinline__ double min(int n, F&& f) {
     double m = DBL_MAX;
     for (int i = (int)(threadIdx.x & 31u); i < n; i += 32) { const double v = f(i); if (v < m) m = v; }
     for (int off = 16; off > 0; off >>= 1) { const double o = __shfl_xor_sync(0xffffffffu, m, off); if (o < m) m = o; }
+    __syncwarp();
     return m;
   }
   template <class F> __device__ __forceinline__ void warp0(F&& f) { f(*this); __syncwarp(); }

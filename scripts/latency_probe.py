@@ -1,0 +1,34 @@
+#!/usr/bin/env python
+"""Single-frame call latency (the ROS-shim use case, n_frames = 1): wall-clock p50/p90 of the host-buffer calls and
+the device time of each kernel."""
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+from smartedgesensor3dhumanpose_b200 import api  # noqa: E402
+from tests import helpers  # noqa: E402
+
+fr = helpers.make_workload("cfg2_hall16x6", 512)
+pipe = api.GeometryPipeline(fr["cameras"])
+h_max = fr["h_max"]
+for name, fn in [("triangulate_batch(1)", lambda f: pipe.triangulate_batch(fr["persons"][f:f + 1], fr["n_persons"][f:f + 1], h_max, dump=False)),
+                 ("process_batch(1)", lambda f: pipe.process_batch(fr["persons"][f:f + 1], fr["n_persons"][f:f + 1], h_max))]:
+    lat = []
+    for f in range(512):
+        t0 = time.perf_counter()
+        fn(f)
+        lat.append(time.perf_counter() - t0)
+    lat = np.array(lat[32:]) * 1e6
+    print(f"{name}: p50 {np.median(lat):.1f} us  p90 {np.percentile(lat, 90):.1f} us  min {lat.min():.1f} us")
+pipe.set_profiling(True)
+acc = {}
+for f in range(64):
+    pipe.process_batch(fr["persons"][f:f + 1], fr["n_persons"][f:f + 1], h_max)
+    for k, v in pipe.last_kernel_ms().items():
+        acc.setdefault(k, []).append(v * 1e3)
+print("kernel device time per single-frame call (us, median):", {k: round(float(np.median(v)), 1) for k, v in acc.items()})

@@ -206,6 +206,13 @@ int reproject_on_device(ses3d_handle_s* h, cudaStream_t st, int n_frames, int h_
   return SES3D_OK;
 }
 
+// The kernels only ever set the flag; it is cleared at create and again after it has been reported, so the
+// batch calls need no reset (and no extra synchronisation) on entry.
+int overflow_error(ses3d_handle_s* h) {
+  cudaMemset(h->d_overflow.p, 0, 4);
+  return fail(SES3D_E_CAPACITY, "a frame produced more hypotheses than h_max");
+}
+
 int check_dims(const ses3d_handle_s* h, int n_frames, int p_max, int h_max) {
   if (!h) return fail(SES3D_E_INVALID, "null handle");
   if (n_frames < 0) return fail(SES3D_E_INVALID, "n_frames < 0");
@@ -234,7 +241,6 @@ int run_batch(ses3d_handle_s* h, int stages, int n_frames, int p_max, const ses3
 
   if (dev) {
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->slot[0].stream;
-    CU(cudaMemsetAsync(h->d_overflow.p, 0, 4, st));
     if (stages & TRI) {
       int rc = triangulate_on_device(h, h->slot[0].sc, st, n_frames, p_max, h_max, persons, n_persons, io3d, n_io3d,
                                      hyp_of, n_hyp_d, n_hung_d);
@@ -248,14 +254,12 @@ int run_batch(ses3d_handle_s* h, int stages, int n_frames, int p_max, const ses3
     CU(cudaMemcpyAsync(&overflow, h->d_overflow.p, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     resolve_events(h);
-    if (overflow) return fail(SES3D_E_CAPACITY, "a frame produced more hypotheses than h_max");
+    if (overflow) return overflow_error(h);
     return SES3D_OK;
   }
 
   // host buffers: stream chunks through the two slots
   const int chunk = host_chunk_frames(n_frames);
-  CU(cudaMemsetAsync(h->d_overflow.p, 0, 4, h->slot[0].stream));
-  CU(cudaStreamSynchronize(h->slot[0].stream));
   int ci = 0;
   for (int f0 = 0; f0 < n_frames; f0 += chunk, ++ci) {
     const int nf = std::min(chunk, n_frames - f0);
@@ -331,8 +335,6 @@ int run_ragged(ses3d_handle_s* h, int n_frames, int p_max, const ses3d_person2d*
   const cudaMemcpyKind in_kind = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   const cudaMemcpyKind out_kind = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   if (h->profiling) for (float& m : h->kernel_ms) m = 0.f;
-  CU(cudaMemsetAsync(h->d_overflow.p, 0, 4, h->slot[0].stream));
-  CU(cudaStreamSynchronize(h->slot[0].stream));
   // per-frame input record counts are needed on the host to cut the dense input into chunks
   std::vector<int32_t> counts_host;
   const int32_t* counts = n_persons;
@@ -413,7 +415,7 @@ int run_ragged(ses3d_handle_s* h, int n_frames, int p_max, const ses3d_person2d*
   if (status != SES3D_OK) return status;
   int32_t overflow = 0;
   CU(cudaMemcpy(&overflow, h->d_overflow.p, 4, cudaMemcpyDeviceToHost));
-  if (overflow) return fail(SES3D_E_CAPACITY, "a frame produced more hypotheses than h_max");
+  if (overflow) return overflow_error(h);
   *total3d = run3;
   *total2d = run2;
   return SES3D_OK;
@@ -475,6 +477,7 @@ int ses3d_create(int32_t n_cams, const ses3d_camera* cams, const ses3d_params* p
   if (ue == cudaSuccess) ue = upload(h->d_F, h->host.F.data(), h->host.F.size() * sizeof(float));
   if (ue == cudaSuccess) ue = upload(h->d_frow, h->host.f_row.data(), h->host.f_row.size() * sizeof(int));
   if (ue == cudaSuccess) ue = h->d_overflow.ensure(4);
+  if (ue == cudaSuccess) ue = cudaMemset(h->d_overflow.p, 0, 4);
   for (int i = 0; i < ses3d_handle_s::kSlots && ue == cudaSuccess; ++i) {
     ue = cudaStreamCreateWithFlags(&h->slot[i].stream, cudaStreamNonBlocking);
     if (ue == cudaSuccess) ue = cudaMallocHost(reinterpret_cast<void**>(&h->slot[i].totals), 2 * sizeof(long long));

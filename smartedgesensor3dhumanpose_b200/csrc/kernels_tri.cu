@@ -2,6 +2,7 @@
 // The algorithm lives in tri_core.h. Joint positions are tolerance-checked against the
 // oracle (1e-3 m FP32 / 1e-4 m FP64), so FMA contraction stays on here.
 #include <algorithm>
+#include <cstdlib>
 
 #include "launch.h"
 #include "tri_core.h"
@@ -10,10 +11,8 @@ namespace ses3d {
 
 extern __shared__ __align__(16) unsigned char smem_raw[];
 
-constexpr int kWarpsPerCta = 4;
-
-template <class T>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, sizeof(T) == 4 ? 6 : 1)
+template <class T, int kWarpsPerCta>
+__global__ void __launch_bounds__(32 * kWarpsPerCta, sizeof(T) == 4 ? 24 / kWarpsPerCta : 1)
 k_triangulate(const Tables tb, int p_max, int h_cap, size_t ws_bytes, const ses3d_person2d* __restrict__ persons,
               const int8_t* __restrict__ hyp_det, const uint32_t* __restrict__ work,
               const int32_t* __restrict__ work_count, ses3d_person_cov* __restrict__ tmp, int32_t* __restrict__ keep) {
@@ -33,13 +32,30 @@ k_triangulate(const Tables tb, int p_max, int h_cap, size_t ws_bytes, const ses3
   }
 }
 
+template <class T, int W>
+static cudaError_t launch_tri_impl(const Tables& tb, LaunchDims d, const ses3d_person2d* persons, const int8_t* hyp_det,
+                                   const uint32_t* work, const int32_t* work_count, ses3d_person_cov* tmp,
+                                   int32_t* keep, int n_sm, cudaStream_t st) {
+  const size_t ws_bytes = tri_ws_bytes<T>(tb.n_cams);
+  const size_t smem = ws_bytes * W;
+  if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
+  // persistent grid: as many CTAs as fit on the chip at the kernel's occupancy (a multiple of the SM count),
+  // never more than the work
+  cudaError_t e = cudaFuncSetAttribute(k_triangulate<T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int per_sm = 0;
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_triangulate<T, W>, 32 * W, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  const size_t units = (size_t)d.n_frames * d.h_cap;
+  const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((units + W - 1) / W, (size_t)n_sm * per_sm));
+  k_triangulate<T, W><<<grid, 32 * W, smem, st>>>(tb, d.p_max, d.h_cap, ws_bytes, persons, hyp_det, work, work_count, tmp,
+                                                  keep);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_triangulate(const Tables& tb, LaunchDims d, const ses3d_person2d* persons, const int8_t* hyp_det,
                                const uint32_t* work, const int32_t* work_count, ses3d_person_cov* tmp, int32_t* keep,
                                cudaStream_t st) {
-  const bool f64 = tb.prm.precision == SES3D_PRECISION_FP64;
-  const size_t ws_bytes = f64 ? tri_ws_bytes<double>(tb.n_cams) : tri_ws_bytes<float>(tb.n_cams);
-  const size_t smem = ws_bytes * kWarpsPerCta;
-  if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
   static int n_sm = 0;
   if (n_sm == 0) {
     int dev = 0;
@@ -47,32 +63,13 @@ cudaError_t launch_triangulate(const Tables& tb, LaunchDims d, const ses3d_perso
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     if (n_sm <= 0) n_sm = 148;
   }
-  // persistent grid: as many CTAs as fit on the chip at the kernel's occupancy (a multiple of the SM
-  // count), never more than the work
-  const size_t units = (size_t)d.n_frames * d.h_cap;
-  cudaError_t e;
-  int per_sm = 0;
-  if (f64) {
-    e = cudaFuncSetAttribute(k_triangulate<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess)
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_triangulate<double>, 32 * kWarpsPerCta, smem);
-  } else {
-    e = cudaFuncSetAttribute(k_triangulate<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess)
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_triangulate<float>, 32 * kWarpsPerCta, smem);
-  }
-  if (e != cudaSuccess) return e;
-  if (per_sm < 1) per_sm = 1;
-  const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((units + kWarpsPerCta - 1) / kWarpsPerCta,
-                                                                       (size_t)n_sm * per_sm));
-  if (f64) {
-    k_triangulate<double><<<grid, 32 * kWarpsPerCta, smem, st>>>(tb, d.p_max, d.h_cap, ws_bytes, persons, hyp_det, work,
-                                                                 work_count, tmp, keep);
-  } else {
-    k_triangulate<float><<<grid, 32 * kWarpsPerCta, smem, st>>>(tb, d.p_max, d.h_cap, ws_bytes, persons, hyp_det, work,
-                                                                work_count, tmp, keep);
-  }
-  return cudaGetLastError();
+  int warps = 2;   // measured on B200 (hall16 x 6): 2 warps/CTA 0.98 ms, 4: 1.00 ms, 8: 1.10 ms per 8192 frames
+  if (const char* env = getenv("SES3D_TRI_WARPS")) warps = atoi(env);
+  if (tb.prm.precision == SES3D_PRECISION_FP64)
+    return launch_tri_impl<double, 4>(tb, d, persons, hyp_det, work, work_count, tmp, keep, n_sm, st);
+  if (warps == 2) return launch_tri_impl<float, 2>(tb, d, persons, hyp_det, work, work_count, tmp, keep, n_sm, st);
+  if (warps == 8) return launch_tri_impl<float, 8>(tb, d, persons, hyp_det, work, work_count, tmp, keep, n_sm, st);
+  return launch_tri_impl<float, 4>(tb, d, persons, hyp_det, work, work_count, tmp, keep, n_sm, st);
 }
 
 }  // namespace ses3d

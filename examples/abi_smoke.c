@@ -1,0 +1,101 @@
+/* abi_smoke.c — the C ABI used from plain C (C99): what a non-Python, non-ROS client links against.
+ *   gcc -std=c99 -Iinclude examples/abi_smoke.c -Lsmartedgesensor3dhumanpose_b200 -lses3d -o abi_smoke
+ * Exercises the host-only entry points (no GPU needed) and, when a device is present, one single-frame
+ * triangulate + reproject call on a 4-camera ring (the n_frames = 1 ROS-shim case). Exit code 0 = ok. */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "ses3d.h"
+
+static void look_at(double ex, double ey, double ez, double T[12]) {
+  /* camera at (ex,ey,ez) looking at (0,0,1), z forward, x right, y down */
+  double z[3] = {-ex, -ey, 1.0 - ez}, n = sqrt(z[0] * z[0] + z[1] * z[1] + z[2] * z[2]);
+  double x[3], y[3];
+  int i;
+  for (i = 0; i < 3; ++i) z[i] /= n;
+  x[0] = z[1] * 1.0 - z[2] * 0.0; x[1] = z[2] * 0.0 - z[0] * 1.0; x[2] = 0.0;   /* z cross up(0,0,1) */
+  n = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+  for (i = 0; i < 3; ++i) x[i] /= n;
+  y[0] = z[1] * x[2] - z[2] * x[1]; y[1] = z[2] * x[0] - z[0] * x[2]; y[2] = z[0] * x[1] - z[1] * x[0];
+  for (i = 0; i < 3; ++i) { T[i] = x[i]; T[4 + i] = y[i]; T[8 + i] = z[i]; }
+  T[3] = -(x[0] * ex + x[1] * ey + x[2] * ez);
+  T[7] = -(y[0] * ex + y[1] * ey + y[2] * ez);
+  T[11] = -(z[0] * ex + z[1] * ey + z[2] * ez);
+}
+
+int main(void) {
+  ses3d_params prm;
+  ses3d_camera cams[4];
+  ses3d_synth_config cfg;
+  ses3d_person2d persons[4 * 2];
+  int32_t n_persons[4];
+  ses3d_assembler_config acfg;
+  ses3d_assembler asmb = NULL;
+  ses3d_handle h = NULL;
+  uint8_t wire[4096];
+  size_t n;
+  int c, rc;
+
+  ses3d_default_params(&prm);
+  if (prm.min_num_valid_keypoints != 9 || prm.max_epipolar_error != 0.050) return 1;
+  printf("%s\n", ses3d_version());
+
+  for (c = 0; c < 4; ++c) {
+    const double a = 6.283185307179586 * c / 4;
+    memset(&cams[c], 0, sizeof(cams[c]));
+    look_at(5.0 * cos(a), 5.0 * sin(a), 2.5, cams[c].T_cam_base);
+    cams[c].fx = cams[c].fy = 1000.0; cams[c].cx = 640.0; cams[c].cy = 360.0;
+    cams[c].width = 1280; cams[c].height = 720;
+  }
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.seed = 1; cfg.n_people = 1; cfg.p_max = 2; cfg.noise_px = 2.0f; cfg.min_separation = 0.6f; cfg.min_visible = 5;
+  cfg.area[0] = -1.0f; cfg.area[1] = -1.0f; cfg.area[2] = 1.0f; cfg.area[3] = 1.0f;
+  if (ses3d_synth_frames(4, cams, &cfg, 0, 1, persons, n_persons, NULL, NULL) != SES3D_OK) return 2;
+  for (c = 0; c < 4; ++c) if (n_persons[c] != 1) return 3;
+
+  /* wire format round trip */
+  n = ses3d_wire_encode_person2dlist(7, 1234567890123LL, "cam_1_color_optical_frame", 0.1f, persons, n_persons[0], wire, sizeof(wire));
+  if (n != 16 + 25 + 8 + 432) return 4;
+  {
+    ses3d_person2d back[2];
+    int64_t stamp = 0;
+    if (ses3d_wire_decode_person2dlist(wire, n, NULL, &stamp, NULL, 0, NULL, back, 2) != 1) return 5;
+    if (stamp != 1234567890123LL || memcmp(&back[0], &persons[0], sizeof(back[0])) != 0) return 6;
+  }
+
+  /* frame assembler: four synchronous cameras -> one frame per tick */
+  if (ses3d_assembler_default_config(4, &acfg) != SES3D_OK || ses3d_assembler_create(&acfg, &asmb) != SES3D_OK) return 7;
+  {
+    int t, frames = 0;
+    for (t = 0; t < 10; ++t)
+      for (c = 0; c < 4; ++c) {
+        rc = ses3d_assembler_add(asmb, c, 1000000000LL + t * 40000000LL, t * 4 + c);
+        if (rc < 0) return 8;
+        frames += rc;
+      }
+    if (frames < 8) return 9;
+  }
+  ses3d_assembler_destroy(asmb);
+
+  /* the compute path needs a GPU: without one the library must say so instead of computing on the CPU */
+  rc = ses3d_create(4, cams, &prm, 0, &h);
+  if (rc != SES3D_OK) {
+    printf("no device: %s\n", ses3d_last_error_string());
+    return rc == SES3D_E_CUDA ? 0 : 10;
+  }
+  {
+    ses3d_person_cov out3d[8];
+    ses3d_person2d out2d[4 * 8];
+    int32_t n3 = 0, n2[4];
+    rc = ses3d_process_batch(h, 1, 2, persons, n_persons, 8, out3d, &n3, out2d, n2, NULL, SES3D_HOST_BUFFERS, NULL);
+    if (rc != SES3D_OK) { printf("%s\n", ses3d_last_error_string()); return 11; }
+    printf("persons3d = %d, nose = (%.3f, %.3f, %.3f), reprojected persons per camera = %d %d %d %d\n", n3,
+           out3d[0].keypoints[SES3D_FBP_NOSE].x, out3d[0].keypoints[SES3D_FBP_NOSE].y, out3d[0].keypoints[SES3D_FBP_NOSE].z,
+           n2[0], n2[1], n2[2], n2[3]);
+    if (n3 != 1 || n2[0] != 1) return 12;
+  }
+  ses3d_destroy(h);
+  return 0;
+}

@@ -273,6 +273,68 @@ size_t ses3d_wire_encode_personcovlist(uint32_t seq, int64_t stamp_ns, const cha
                                        const int64_t* ts_per_cam_ns, const float* fb_delay_per_cam,
                                        const ses3d_person_cov* persons, int32_t n, uint8_t* buf, size_t cap);
 
+/* ------------------------------------------------------------- pose_prior
+ * Replaces skeletonCallback() of pose_prior/src/pose_prior_mult_node.cpp:505-921 (bound :947) with its
+ * file-scope state (g_tracks :123, g_t_prev :58, g_next_id :59, g_frame_nr :60, g_fb_delay_buffer :54):
+ * per-person tracking (Hungarian on the velocity-normalised joint distance, :84-101, :548-580), the skeleton
+ * model fit (unary Gaussian factors :126-145, :690, :714, :732 and bone-length range factors :384-481 solved
+ * with gtsam's LevenbergMarquardtOptimizer :746-749), marginal covariances (:760-816), the constant-velocity
+ * prediction (:818-831) and the track life cycle (:191-211, :839-848, :866-903).
+ * The stage is stateful across the frames of one message stream, so the parallel unit is the *sequence*:
+ * one handle tracks n_sequences independent streams (rigs / replays); the frames of a sequence are processed in
+ * order, inside one launch when several are passed at once. Marker output is dropped (visualisation). */
+typedef struct ses3d_prior_params {
+  int32_t pose_method;          /* SES3D_POSE_SIMPLE  param pose_method   PRI:39,930 */
+  int32_t normalize_by_height;  /* 0                  param norm_height   PRI:40,931 (selects the bone table and
+                                   limb_sigma_factor 2.0 instead of 1.0, PRI:934-937) */
+  int32_t min_num_obs_track;    /* 10   PRI:66 */
+  int32_t lm_max_iterations;    /* 100  gtsam LevenbergMarquardtParams defaults (gtsam 4.0.3, README.md:22) */
+  float min_score;              /* 0.10f PRI:50 */
+  float pad_;
+  double pred_noise_sigma;      /* 0.12 PRI:47 */
+  double default_res_sigma;     /* 0.10 PRI:48 */
+  double avg_delay;             /* 0.10 PRI:51 */
+  double root_sigma_factor;     /* 100  PRI:52 */
+  double t_max_unobserved;      /* 1.0  PRI:62 */
+  double dist_threshold;        /* 5.0  PRI:63 */
+  double merge_dist_thresh;     /* 0.20 PRI:64 */
+  double lm_lambda_initial;     /* 1e-5 */
+  double lm_lambda_factor;      /* 10   */
+  double lm_lambda_upper_bound; /* 1e5  */
+  double lm_relative_error_tol; /* 1e-5 */
+  double lm_absolute_error_tol; /* 1e-5 */
+  double lm_min_model_fidelity; /* 1e-3 */
+} ses3d_prior_params;
+
+typedef struct ses3d_prior_s* ses3d_prior;
+
+void ses3d_prior_default_params(ses3d_prior_params* p);
+/* max_tracks = capacity of g_tracks per sequence (a frame that would exceed it fails with SES3D_E_CAPACITY). */
+int ses3d_prior_create(const ses3d_prior_params* params, int32_t n_sequences, int32_t max_tracks, int32_t device,
+                       ses3d_prior* out);
+int ses3d_prior_destroy(ses3d_prior p);
+int ses3d_prior_reset(ses3d_prior p); /* reset() PRI:182-189, all sequences */
+
+/* n_frames consecutive PersonCovList messages of each of n_sequences streams (sequence-major arrays):
+ *   persons  [n_sequences][n_frames][h_max]   n_persons [n_sequences][n_frames]
+ *   stamp_ns [n_sequences][n_frames]          header.stamp (t = stamp.toSec(), PRI:506)
+ *   fb_delay [n_sequences][n_frames][n_cams]  fb_delay_per_cam (PRI:513-526); NULL = no measurement (-1)
+ *   fused, pred [n_sequences][n_frames][h_max] persons3d_fused / persons3d_fused_pred (PRI:906-907), in
+ *            detection order (the reference built without OpenMP); n_out [n_sequences][n_frames]
+ *   pred_delay [n_sequences][n_frames]        the fb_delay_per_cam value stored in both outputs (PRI:531); nullable
+ *   track_of [n_sequences][n_frames][h_max]   diagnostics, nullable: track id each detection was fused into
+ * Tracker state persists in the handle between calls (streaming: n_frames = 1 per call). */
+int ses3d_prior_run(ses3d_prior p, int32_t n_sequences, int32_t n_frames, int32_t h_max,
+                    const ses3d_person_cov* persons, const int32_t* n_persons, const int64_t* stamp_ns,
+                    int32_t n_cams, const float* fb_delay, ses3d_person_cov* fused, ses3d_person_cov* pred,
+                    int32_t* n_out, float* pred_delay, int32_t* track_of, uint32_t flags, void* stream);
+
+/* Diagnostics: live tracks of one sequence (ids / num_obs [max_tracks], nullable); returns the track count or <0. */
+int ses3d_prior_get_tracks(ses3d_prior p, int32_t sequence, int32_t* ids, int32_t* num_obs);
+int64_t ses3d_prior_launch_count(ses3d_prior p);
+/* Device time (ms, CUDA events) of the most recent device-buffer ses3d_prior_run. */
+int ses3d_prior_last_kernel_ms(ses3d_prior p, float* ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,7 +18,8 @@ REF_HUNGARIAN_PATH = HERE / "_ref" / "libref_hungarian.so"
 
 def build(force=False):
     """Compile the oracle (and oracle/_ref when /root/reference is present)."""
-    if force or not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < (HERE / "ses3d_oracle.cpp").stat().st_mtime:
+    srcs = [HERE / "ses3d_oracle.cpp", HERE / "pose_prior_oracle.cpp", HERE.parent / "include" / "ses3d.h"]
+    if force or not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < max(s.stat().st_mtime for s in srcs):
         subprocess.run(["make", "-C", str(HERE), "-s"], check=True)
     elif not REF_HUNGARIAN_PATH.exists() and Path("/root/reference/skeleton_3d/src/Hungarian.cpp").exists():
         subprocess.run(["make", "-C", str(HERE), "-s", "ref"], check=True)
@@ -167,3 +168,71 @@ def ut_covariance(P, pts, cov2d, mean):
     cov = np.zeros(9)
     lib().oracle_ut_covariance(len(P), _p(P), _p(pts), _p(cov2d), _p(mean), _p(cov))
     return cov.reshape(3, 3)
+
+
+# ------------------------------------------------------------------------------------------------ pose_prior
+class PriorOracle:
+    """CPU restatement of pose_prior's skeletonCallback (pose_prior_mult_node.cpp:505-921), oracle/pose_prior_oracle.cpp."""
+
+    def __init__(self, params=None, n_sequences=1, ref_hungarian=False):
+        from smartedgesensor3dhumanpose_b200.layouts import PriorParams, default_prior_params
+        L = lib()
+        L.prior_oracle_create.restype = C.c_void_p
+        L.prior_oracle_create.argtypes = [C.POINTER(PriorParams), C.c_int32, C.c_char_p]
+        L.prior_oracle_destroy.argtypes = [C.c_void_p]
+        L.prior_oracle_reset.argtypes = [C.c_void_p]
+        L.prior_oracle_run.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 3 + [C.c_int32] + \
+            [C.c_void_p] * 6 + [C.c_int32]
+        L.prior_oracle_get_tracks.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        L.prior_oracle_stats.argtypes = [C.c_void_p, C.c_void_p]
+        self._L = L
+        self.params = params if params is not None else default_prior_params()
+        self.n_sequences = n_sequences
+        so = None
+        if ref_hungarian:
+            if not REF_HUNGARIAN_PATH.exists():
+                raise FileNotFoundError(REF_HUNGARIAN_PATH)
+            so = str(REF_HUNGARIAN_PATH).encode()
+        self._h = L.prior_oracle_create(C.byref(self.params), n_sequences, so)
+        if not self._h:
+            raise ValueError("prior_oracle_create failed")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.prior_oracle_destroy(self._h)
+            self._h = None
+
+    def reset(self):
+        self._L.prior_oracle_reset(self._h)
+
+    def run(self, persons, n_persons, stamp_ns, fb_delay=None, n_threads=1):
+        """persons [S][T][h_max], n_persons [S][T], stamp_ns [S][T], fb_delay [S][T][n_cams] or None."""
+        persons = np.ascontiguousarray(persons, dtype=person_cov_dtype)
+        S, T, H = persons.shape
+        n_persons = np.ascontiguousarray(n_persons, dtype=np.int32).reshape(S, T)
+        stamp_ns = np.ascontiguousarray(stamp_ns, dtype=np.int64).reshape(S, T)
+        n_cams = 0
+        if fb_delay is not None:
+            fb_delay = np.ascontiguousarray(fb_delay, dtype=np.float32)
+            n_cams = fb_delay.shape[-1]
+        fused = np.zeros((S, T, H), person_cov_dtype)
+        pred = np.zeros((S, T, H), person_cov_dtype)
+        n_out = np.zeros((S, T), np.int32)
+        pred_delay = np.zeros((S, T), np.float32)
+        track_of = np.full((S, T, H), -1, np.int32)
+        rc = self._L.prior_oracle_run(self._h, S, T, H, _p(persons), _p(n_persons), _p(stamp_ns), n_cams, _p(fb_delay),
+                                      _p(fused), _p(pred), _p(n_out), _p(pred_delay), _p(track_of), n_threads)
+        if rc != 0:
+            raise RuntimeError(f"prior_oracle_run -> {rc}")
+        return dict(fused=fused, pred=pred, n_out=n_out, pred_delay=pred_delay, track_of=track_of)
+
+    def tracks(self, sequence=0):
+        ids = np.zeros(1024, np.int32)
+        nobs = np.zeros(1024, np.int32)
+        n = self._L.prior_oracle_get_tracks(self._h, sequence, _p(ids), _p(nobs))
+        return ids[:n].copy(), nobs[:n].copy()
+
+    def stats(self):
+        out = np.zeros(3, np.int64)
+        self._L.prior_oracle_stats(self._h, _p(out))
+        return dict(fits=int(out[0]), lm_outer=int(out[1]), lm_inner=int(out[2]))

@@ -10,11 +10,11 @@ The CUDA library (libses3d.so) is built with `python -m smartedgesensor3dhumanpo
 from .layouts import default_params  # noqa: F401
 
 __version__ = "0.1.0"
-__all__ = ["GeometryPipeline", "Skeleton3D", "PoseReprojection", "default_params"]
+__all__ = ["GeometryPipeline", "Skeleton3D", "PoseReprojection", "PosePrior", "PriorTracker", "default_params"]
 
 
 def __getattr__(name):  # the API classes load the shared library on first use, not at import
-    if name in ("GeometryPipeline", "Skeleton3D", "PoseReprojection"):
+    if name in ("GeometryPipeline", "Skeleton3D", "PoseReprojection", "PosePrior", "PriorTracker"):
         from . import api
         return getattr(api, name)
     raise AttributeError(name)

@@ -2,6 +2,7 @@
 
     Skeleton3D.triangulate_persons(people)        <- triangulate_persons(), S3D:525-997 (called S3D:1069)
     PoseReprojection.fused_skeleton_callback(msg) <- fusedSkeletonCallback(), REP:139-235
+    PosePrior.skeleton_callback(msg)              <- skeletonCallback(), pose_prior_mult_node.cpp:505-921
 
 plus the batched calls the benchmark uses (`GeometryPipeline.*_batch`). ROS messages are
 replaced by numpy structured arrays with the person_msgs layouts (layouts.py). All compute
@@ -12,8 +13,8 @@ import ctypes as C
 import numpy as np
 
 from . import lib as _lib
-from .layouts import (DEVICE_BUFFERS, HOST_BUFFERS, AssocDump, camera_dtype, default_params, person2d_dtype,
-                      person_cov_dtype)
+from .layouts import (DEVICE_BUFFERS, HOST_BUFFERS, AssocDump, camera_dtype, default_params, default_prior_params,
+                      person2d_dtype, person_cov_dtype)
 
 
 def _p(a):
@@ -205,3 +206,97 @@ class PoseReprojection:
             return [np.zeros(0, person2d_dtype) for _ in range(self.pipe.n_cams)]
         r = self.pipe.reproject_batch(persons3d, np.array([n], np.int32))
         return [r["persons2d"][0, c, :r["n_out"][0, c]].copy() for c in range(self.pipe.n_cams)]
+
+
+class PriorTracker:
+    """pose_prior for n_sequences independent message streams on one GPU (ses3d_prior_*): tracking, skeleton-model
+    fit, marginal covariances and prediction of pose_prior_mult_node.cpp:505-921. State persists between calls."""
+
+    def __init__(self, params=None, n_sequences=1, max_tracks=32, device=0):
+        self._L = _lib.load()
+        self.params = params if params is not None else default_prior_params()
+        self.n_sequences, self.max_tracks, self.device = n_sequences, max_tracks, device
+        h = C.c_void_p()
+        _lib.check(self._L.ses3d_prior_create(C.byref(self.params), n_sequences, max_tracks, device, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.ses3d_prior_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reset(self):
+        """reset(), PRI:182-189."""
+        _lib.check(self._L.ses3d_prior_reset(self._h))
+
+    @property
+    def launch_count(self):
+        return int(self._L.ses3d_prior_launch_count(self._h))
+
+    def last_kernel_ms(self):
+        ms = C.c_float(0)
+        _lib.check(self._L.ses3d_prior_last_kernel_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def tracks(self, sequence=0):
+        ids = np.zeros(self.max_tracks, np.int32)
+        nobs = np.zeros(self.max_tracks, np.int32)
+        n = self._L.ses3d_prior_get_tracks(self._h, sequence, _p(ids), _p(nobs))
+        if n < 0:
+            _lib.check(n)
+        return ids[:n].copy(), nobs[:n].copy()
+
+    def run(self, persons, n_persons, stamp_ns, fb_delay=None, want_track_of=True):
+        """persons [S][T][h_max] PersonCov, n_persons [S][T], stamp_ns [S][T] int64, fb_delay [S][T][n_cams] float32
+        or None. Host buffers in and out."""
+        persons = np.ascontiguousarray(persons, dtype=person_cov_dtype)
+        S, T, H = persons.shape
+        n_persons = np.ascontiguousarray(n_persons, dtype=np.int32).reshape(S, T)
+        stamp_ns = np.ascontiguousarray(stamp_ns, dtype=np.int64).reshape(S, T)
+        n_cams = 0
+        if fb_delay is not None:
+            fb_delay = np.ascontiguousarray(fb_delay, dtype=np.float32).reshape(S, T, -1)
+            n_cams = fb_delay.shape[-1]
+        fused = np.zeros((S, T, H), person_cov_dtype)
+        pred = np.zeros((S, T, H), person_cov_dtype)
+        n_out = np.zeros((S, T), np.int32)
+        pred_delay = np.zeros((S, T), np.float32)
+        track_of = np.full((S, T, H), -1, np.int32) if want_track_of else None
+        _lib.check(self._L.ses3d_prior_run(self._h, S, T, H, _p(persons), _p(n_persons), _p(stamp_ns), n_cams,
+                                           _p(fb_delay), _p(fused), _p(pred), _p(n_out), _p(pred_delay), _p(track_of),
+                                           HOST_BUFFERS, None))
+        return dict(fused=fused, pred=pred, n_out=n_out, pred_delay=pred_delay, track_of=track_of)
+
+    def run_device(self, n_sequences, n_frames, h_max, persons_ptr, n_persons_ptr, stamp_ptr, n_cams, fb_delay_ptr,
+                   fused_ptr, pred_ptr, n_out_ptr, pred_delay_ptr=0, track_of_ptr=0, stream=0):
+        """Raw device addresses on this handle's GPU; stream-ordered."""
+        _lib.check(self._L.ses3d_prior_run(self._h, n_sequences, n_frames, h_max, persons_ptr, n_persons_ptr, stamp_ptr,
+                                           n_cams, fb_delay_ptr or None, fused_ptr, pred_ptr, n_out_ptr,
+                                           pred_delay_ptr or None, track_of_ptr or None, DEVICE_BUFFERS, stream or None))
+
+
+class PosePrior:
+    """pose_prior node body: skeletonCallback (PRI:505-921) for one message at a time (n_sequences = n_frames = 1)."""
+
+    def __init__(self, params=None, device=0, h_max=32, max_tracks=32):
+        self.tracker = PriorTracker(params, 1, max_tracks, device)
+        self.h_max = h_max
+
+    def skeleton_callback(self, persons3d, stamp_ns, fb_delay_per_cam=None):
+        """persons3d: PersonCov array (PersonCovList.persons), stamp_ns: header.stamp, fb_delay_per_cam: float array.
+        Returns (persons3d_fused, persons3d_fused_pred, fb_delay) as published on PRI:906-907."""
+        persons3d = np.asarray(persons3d, dtype=person_cov_dtype).reshape(-1)
+        n = len(persons3d)
+        if n > self.h_max:
+            raise ValueError(f"{n} persons exceed h_max = {self.h_max}")
+        buf = np.zeros((1, 1, self.h_max), person_cov_dtype)
+        buf[0, 0, :n] = persons3d
+        fb = None if fb_delay_per_cam is None else np.asarray(fb_delay_per_cam, np.float32).reshape(1, 1, -1)
+        r = self.tracker.run(buf, np.array([[n]], np.int32), np.array([[stamp_ns]], np.int64), fb, want_track_of=False)
+        k = int(r["n_out"][0, 0])
+        return r["fused"][0, 0, :k].copy(), r["pred"][0, 0, :k].copy(), float(r["pred_delay"][0, 0])
+
+    def reset(self):
+        self.tracker.reset()

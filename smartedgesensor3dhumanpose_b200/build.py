@@ -27,6 +27,8 @@ UNITS = [
     ("kernels_tri.cu", []),
     ("synth_device.cu", ["-fmad=false"]),
     ("kernels_pack.cu", []),
+    ("kernels_prior.cu", []),
+    ("prior_api.cpp", []),
     ("api.cpp", []),
     ("host_setup.cpp", []),
     ("synth.cpp", []),

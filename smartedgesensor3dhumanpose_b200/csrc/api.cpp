@@ -40,6 +40,13 @@ int cuda_fail(cudaError_t e, const char* what) {
     if (e_ != cudaSuccess) return cuda_fail(e_, #call);  \
   } while (0)
 
+}  // namespace
+namespace ses3d {   // shared with prior_api.cpp
+int set_error(int code, const std::string& msg) { return fail(code, msg); }
+const char* last_error() { return g_last_error.c_str(); }
+}  // namespace ses3d
+namespace {
+
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;

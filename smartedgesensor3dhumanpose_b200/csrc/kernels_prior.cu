@@ -1,0 +1,71 @@
+// kernels_prior.cu — K7 "prior" for sm_100a: one CTA per message stream, its frames walked in order; inside a
+// frame one warp per detection (skeleton fit) and warp 0 for the assignment. The algorithm lives in prior_core.h.
+// FP64 throughout (gtsam computes in double); tolerance-checked against the oracle, so FMA contraction stays on.
+#include <algorithm>
+#include <cstdlib>
+
+#include "launch.h"
+#include "prior_core.h"
+
+namespace ses3d {
+
+extern __shared__ __align__(16) unsigned char smem_raw[];
+
+__global__ void __launch_bounds__(256)
+k_prior(const PriorTables pt, int n_seq, int n_frames, int h_max, int max_tracks, size_t ws_bytes, size_t fit_bytes,
+        PriorSeqState* __restrict__ states, PriorTrack* __restrict__ tracks, uint8_t* __restrict__ order,
+        const ses3d_person_cov* __restrict__ persons, const int32_t* __restrict__ n_persons,
+        const int64_t* __restrict__ stamp_ns, int n_cams, const float* __restrict__ fb_delay,
+        ses3d_person_cov* __restrict__ fused, ses3d_person_cov* __restrict__ pred, int32_t* __restrict__ n_out,
+        float* __restrict__ pred_delay, int32_t* __restrict__ track_of) {
+  const int s = blockIdx.x;
+  if (s >= n_seq) return;
+  Arena ar(smem_raw);
+  PriorWs ws;
+  prior_ws_layout(ar, h_max, max_tracks, &ws);
+  unsigned char* fit_ws = smem_raw + ws_bytes;
+  BlockTeam tm;
+  PriorSeqState* st = states + s;
+  PriorTrack* trk = tracks + (size_t)s * max_tracks;
+  uint8_t* ord = order + (size_t)s * max_tracks;
+  for (int f = 0; f < n_frames; ++f) {
+    const size_t i = (size_t)s * n_frames + f;
+    prior_frame(tm, pt, max_tracks, h_max, st, trk, ord, ws, fit_ws, fit_bytes, stamp_ns[i], n_cams,
+                fb_delay ? fb_delay + i * n_cams : nullptr, n_persons[i], persons + i * h_max, fused + i * h_max,
+                pred + i * h_max, n_out + i, pred_delay ? pred_delay + i : nullptr,
+                track_of ? track_of + i * h_max : nullptr);
+    tm.sync();
+  }
+}
+
+__global__ void k_prior_reset(const ses3d_prior_params prm, int n_seq, PriorSeqState* states, int keep_t_prev) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n_seq) prior_state_reset(prm, states + s, keep_t_prev != 0);
+}
+
+cudaError_t launch_prior_reset(const ses3d_prior_params& prm, int n_seq, PriorSeqState* states, bool keep_t_prev,
+                               cudaStream_t st) {
+  k_prior_reset<<<(n_seq + 127) / 128, 128, 0, st>>>(prm, n_seq, states, keep_t_prev ? 1 : 0);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_prior(const PriorTables& pt, int n_seq, int n_frames, int h_max, int max_tracks,
+                         PriorSeqState* states, PriorTrack* tracks, uint8_t* order, const ses3d_person_cov* persons,
+                         const int32_t* n_persons, const int64_t* stamp_ns, int n_cams, const float* fb_delay,
+                         ses3d_person_cov* fused, ses3d_person_cov* pred, int32_t* n_out, float* pred_delay,
+                         int32_t* track_of, cudaStream_t st) {
+  int warps = std::max(1, std::min(4, h_max));   // detections of one frame fitted concurrently
+  if (const char* env = getenv("SES3D_PRIOR_WARPS")) warps = std::max(1, std::min(8, atoi(env)));
+  const size_t ws_bytes = prior_ws_bytes(h_max, max_tracks);
+  const size_t fit_bytes = prior_fit_ws_bytes();
+  const size_t smem = ws_bytes + fit_bytes * warps;
+  if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
+  cudaError_t e = cudaFuncSetAttribute(k_prior, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_prior<<<n_seq, 32 * warps, smem, st>>>(pt, n_seq, n_frames, h_max, max_tracks, ws_bytes, fit_bytes, states, tracks,
+                                            order, persons, n_persons, stamp_ns, n_cams, fb_delay, fused, pred, n_out,
+                                            pred_delay, track_of);
+  return cudaGetLastError();
+}
+
+}  // namespace ses3d

@@ -41,3 +41,15 @@ cudaError_t launch_move_records(int direction /*0 pack, 1 unpack*/, int n_units,
                                 cudaStream_t st);
 
 }  // namespace ses3d
+
+// K7 (kernels_prior.cu): pose_prior, one CTA per message stream
+#include "prior_core.h"
+namespace ses3d {
+cudaError_t launch_prior_reset(const ses3d_prior_params& prm, int n_seq, PriorSeqState* states, bool keep_t_prev,
+                               cudaStream_t st);
+cudaError_t launch_prior(const PriorTables& pt, int n_seq, int n_frames, int h_max, int max_tracks,
+                         PriorSeqState* states, PriorTrack* tracks, uint8_t* order, const ses3d_person_cov* persons,
+                         const int32_t* n_persons, const int64_t* stamp_ns, int n_cams, const float* fb_delay,
+                         ses3d_person_cov* fused, ses3d_person_cov* pred, int32_t* n_out, float* pred_delay,
+                         int32_t* track_of, cudaStream_t st);
+}  // namespace ses3d

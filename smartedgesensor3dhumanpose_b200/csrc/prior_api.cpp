@@ -1,0 +1,251 @@
+// prior_api.cpp — C ABI of the pose_prior stage (include/ses3d.h, "pose_prior" section) on top of K7.
+//
+// ses3d_prior_create  <- main() of pose_prior_mult_node.cpp (PRI:923-947: parameters, limb sigma factor)
+// ses3d_prior_run     <- skeletonCallback (PRI:505-921) for n_sequences streams x n_frames messages
+// ses3d_prior_reset   <- reset() (PRI:182-189)
+// No CPU fallback: the handle needs a CUDA device. Tracker state (tracks, counters) lives in device memory owned
+// by the handle; host-buffer calls stage the records through device buffers that grow once and are reused.
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "launch.h"
+#include "ses3d.h"
+
+namespace ses3d {
+int set_error(int code, const std::string& msg);
+}
+
+namespace {
+
+int cuda_fail(cudaError_t e, const char* what) {
+  return ses3d::set_error(SES3D_E_CUDA, std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
+}
+#define CU(call)                                         \
+  do {                                                   \
+    cudaError_t e_ = (call);                             \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #call);  \
+  } while (0)
+
+struct Buf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    const size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct ses3d_prior_s {
+  int device = 0;
+  int n_sequences = 0, max_tracks = 0;
+  ses3d::PriorTables pt;
+  Buf states, tracks, order;
+  Buf in_persons, in_n, in_stamp, in_delay, out_fused, out_pred, out_n, out_delay, out_track;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float last_ms = 0.f;
+  int64_t launches = 0;
+  std::mutex mu;
+};
+
+extern "C" {
+
+void ses3d_prior_default_params(ses3d_prior_params* p) {
+  if (!p) return;
+  std::memset(p, 0, sizeof *p);
+  p->pose_method = SES3D_POSE_SIMPLE;
+  p->normalize_by_height = 0;
+  p->min_num_obs_track = 10;
+  p->lm_max_iterations = 100;
+  p->min_score = 0.10f;
+  p->pred_noise_sigma = 0.12;
+  p->default_res_sigma = 0.10;
+  p->avg_delay = 0.10;
+  p->root_sigma_factor = 100.0;
+  p->t_max_unobserved = 1.0;
+  p->dist_threshold = 5.0;
+  p->merge_dist_thresh = 0.20;
+  p->lm_lambda_initial = 1e-5;
+  p->lm_lambda_factor = 10.0;
+  p->lm_lambda_upper_bound = 1e5;
+  p->lm_relative_error_tol = 1e-5;
+  p->lm_absolute_error_tol = 1e-5;
+  p->lm_min_model_fidelity = 1e-3;
+}
+
+int ses3d_prior_create(const ses3d_prior_params* params, int32_t n_sequences, int32_t max_tracks, int32_t device,
+                       ses3d_prior* out) {
+  if (!out) return ses3d::set_error(SES3D_E_INVALID, "ses3d_prior_create: out is NULL");
+  *out = nullptr;
+  if (n_sequences < 1) return ses3d::set_error(SES3D_E_INVALID, "ses3d_prior_create: n_sequences < 1");
+  if (max_tracks < 1 || max_tracks > ses3d::PRIOR_MAX_TRACKS)
+    return ses3d::set_error(SES3D_E_INVALID, "ses3d_prior_create: max_tracks must be in [1, 64]");
+  ses3d_prior_params prm;
+  if (params) prm = *params; else ses3d_prior_default_params(&prm);
+  if (prm.pose_method != SES3D_POSE_SIMPLE && prm.pose_method != SES3D_POSE_H36M)
+    return ses3d::set_error(SES3D_E_INVALID, "ses3d_prior_create: unknown pose_method");
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev <= 0)
+    return ses3d::set_error(SES3D_E_CUDA, "ses3d_prior_create: no CUDA device (there is no CPU path)");
+  if (device < 0 || device >= n_dev) return ses3d::set_error(SES3D_E_INVALID, "ses3d_prior_create: bad device ordinal");
+  CU(cudaSetDevice(device));
+  ses3d_prior_s* h = new ses3d_prior_s;
+  h->device = device;
+  h->n_sequences = n_sequences;
+  h->max_tracks = max_tracks;
+  h->pt.prm = prm;
+  h->pt.limb_sigma_factor = prm.normalize_by_height ? 2.0 : 1.0;   // PRI:934-937
+  auto bail = [&](cudaError_t err, const char* what) { ses3d_prior_destroy(h); return cuda_fail(err, what); };
+  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+  if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");
+  if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
+  if ((e = h->states.ensure(sizeof(ses3d::PriorSeqState) * n_sequences)) != cudaSuccess) return bail(e, "cudaMalloc states");
+  if ((e = h->tracks.ensure(sizeof(ses3d::PriorTrack) * (size_t)n_sequences * max_tracks)) != cudaSuccess) return bail(e, "cudaMalloc tracks");
+  if ((e = h->order.ensure((size_t)n_sequences * max_tracks)) != cudaSuccess) return bail(e, "cudaMalloc order");
+  if ((e = cudaMemsetAsync(h->tracks.p, 0, sizeof(ses3d::PriorTrack) * (size_t)n_sequences * max_tracks, h->stream)) != cudaSuccess) return bail(e, "cudaMemset");
+  if ((e = cudaMemsetAsync(h->order.p, 0, (size_t)n_sequences * max_tracks, h->stream)) != cudaSuccess) return bail(e, "cudaMemset");
+  if ((e = ses3d::launch_prior_reset(prm, n_sequences, h->states.as<ses3d::PriorSeqState>(), false, h->stream)) != cudaSuccess) return bail(e, "k_prior_reset");
+  if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return bail(e, "cudaStreamSynchronize");
+  ++h->launches;
+  *out = h;
+  return SES3D_OK;
+}
+
+int ses3d_prior_destroy(ses3d_prior h) {
+  if (!h) return SES3D_OK;
+  cudaSetDevice(h->device);
+  for (Buf* b : {&h->states, &h->tracks, &h->order, &h->in_persons, &h->in_n, &h->in_stamp, &h->in_delay, &h->out_fused,
+                 &h->out_pred, &h->out_n, &h->out_delay, &h->out_track})
+    b->release();
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return SES3D_OK;
+}
+
+int ses3d_prior_reset(ses3d_prior h) {
+  if (!h) return ses3d::set_error(SES3D_E_INVALID, "ses3d_prior_reset: NULL handle");
+  std::lock_guard<std::mutex> lock(h->mu);
+  CU(cudaSetDevice(h->device));
+  CU(ses3d::launch_prior_reset(h->pt.prm, h->n_sequences, h->states.as<ses3d::PriorSeqState>(), true, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  ++h->launches;
+  return SES3D_OK;
+}
+
+int ses3d_prior_run(ses3d_prior h, int32_t n_sequences, int32_t n_frames, int32_t h_max,
+                    const ses3d_person_cov* persons, const int32_t* n_persons, const int64_t* stamp_ns,
+                    int32_t n_cams, const float* fb_delay, ses3d_person_cov* fused, ses3d_person_cov* pred,
+                    int32_t* n_out, float* pred_delay, int32_t* track_of, uint32_t flags, void* stream) {
+  if (!h) return ses3d::set_error(SES3D_E_INVALID, "ses3d_prior_run: NULL handle");
+  if (n_sequences < 0 || n_sequences > h->n_sequences)
+    return ses3d::set_error(SES3D_E_INVALID, "ses3d_prior_run: n_sequences exceeds the handle's");
+  if (n_frames < 0 || h_max < 1 || h_max > 64) return ses3d::set_error(SES3D_E_INVALID, "ses3d_prior_run: bad n_frames / h_max");
+  if (n_cams < 0 || (n_cams > 0 && false)) return ses3d::set_error(SES3D_E_INVALID, "ses3d_prior_run: bad n_cams");
+  if (n_sequences == 0 || n_frames == 0) return SES3D_OK;
+  if (!persons || !n_persons || !stamp_ns || !fused || !pred || !n_out)
+    return ses3d::set_error(SES3D_E_INVALID, "ses3d_prior_run: NULL buffer");
+  std::lock_guard<std::mutex> lock(h->mu);
+  CU(cudaSetDevice(h->device));
+  const size_t n_msg = (size_t)n_sequences * n_frames;
+  const size_t rec = sizeof(ses3d_person_cov) * n_msg * h_max;
+  const bool on_device = (flags & SES3D_DEVICE_BUFFERS) != 0;
+  cudaStream_t st = (on_device && stream) ? static_cast<cudaStream_t>(stream) : h->stream;
+  auto* states = h->states.as<ses3d::PriorSeqState>();
+  auto* tracks = h->tracks.as<ses3d::PriorTrack>();
+  auto* order = h->order.as<uint8_t>();
+  if (fb_delay == nullptr) n_cams = 0;
+
+  if (on_device) {
+    CU(cudaEventRecord(h->ev0, st));
+    CU(ses3d::launch_prior(h->pt, n_sequences, n_frames, h_max, h->max_tracks, states, tracks, order, persons, n_persons,
+                           stamp_ns, n_cams, fb_delay, fused, pred, n_out, pred_delay, track_of, st));
+    CU(cudaEventRecord(h->ev1, st));
+    ++h->launches;
+    // the sticky overflow flag is checked on the host-buffer path and by ses3d_prior_get_tracks
+    return SES3D_OK;
+  }
+
+  CU(h->in_persons.ensure(rec));
+  CU(h->in_n.ensure(4 * n_msg));
+  CU(h->in_stamp.ensure(8 * n_msg));
+  CU(h->out_fused.ensure(rec));
+  CU(h->out_pred.ensure(rec));
+  CU(h->out_n.ensure(4 * n_msg));
+  CU(h->out_delay.ensure(4 * n_msg));
+  if (track_of) CU(h->out_track.ensure(4 * n_msg * h_max));
+  if (n_cams > 0) CU(h->in_delay.ensure(4 * n_msg * n_cams));
+  CU(cudaMemcpyAsync(h->in_persons.p, persons, rec, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(h->in_n.p, n_persons, 4 * n_msg, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(h->in_stamp.p, stamp_ns, 8 * n_msg, cudaMemcpyHostToDevice, st));
+  if (n_cams > 0) CU(cudaMemcpyAsync(h->in_delay.p, fb_delay, 4 * n_msg * n_cams, cudaMemcpyHostToDevice, st));
+  // unpublished slots of the outputs read as zero records
+  CU(cudaMemsetAsync(h->out_fused.p, 0, rec, st));
+  CU(cudaMemsetAsync(h->out_pred.p, 0, rec, st));
+  CU(cudaEventRecord(h->ev0, st));
+  CU(ses3d::launch_prior(h->pt, n_sequences, n_frames, h_max, h->max_tracks, states, tracks, order,
+                         h->in_persons.as<ses3d_person_cov>(), h->in_n.as<int32_t>(), h->in_stamp.as<int64_t>(), n_cams,
+                         n_cams > 0 ? h->in_delay.as<float>() : nullptr, h->out_fused.as<ses3d_person_cov>(),
+                         h->out_pred.as<ses3d_person_cov>(), h->out_n.as<int32_t>(), h->out_delay.as<float>(),
+                         track_of ? h->out_track.as<int32_t>() : nullptr, st));
+  CU(cudaEventRecord(h->ev1, st));
+  ++h->launches;
+  CU(cudaMemcpyAsync(fused, h->out_fused.p, rec, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(pred, h->out_pred.p, rec, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(n_out, h->out_n.p, 4 * n_msg, cudaMemcpyDeviceToHost, st));
+  if (pred_delay) CU(cudaMemcpyAsync(pred_delay, h->out_delay.p, 4 * n_msg, cudaMemcpyDeviceToHost, st));
+  if (track_of) CU(cudaMemcpyAsync(track_of, h->out_track.p, 4 * n_msg * h_max, cudaMemcpyDeviceToHost, st));
+  std::vector<ses3d::PriorSeqState> hs(n_sequences);
+  CU(cudaMemcpyAsync(hs.data(), states, sizeof(ses3d::PriorSeqState) * n_sequences, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  for (const auto& s : hs)
+    if (s.overflow) return ses3d::set_error(SES3D_E_CAPACITY, "ses3d_prior_run: a stream needed more than max_tracks tracks");
+  return SES3D_OK;
+}
+
+int ses3d_prior_get_tracks(ses3d_prior h, int32_t sequence, int32_t* ids, int32_t* num_obs) {
+  if (!h || sequence < 0 || sequence >= h->n_sequences) return ses3d::set_error(SES3D_E_INVALID, "ses3d_prior_get_tracks: bad argument");
+  std::lock_guard<std::mutex> lock(h->mu);
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  ses3d::PriorSeqState s;
+  CU(cudaMemcpy(&s, h->states.as<ses3d::PriorSeqState>() + sequence, sizeof s, cudaMemcpyDeviceToHost));
+  std::vector<uint8_t> ord(h->max_tracks);
+  CU(cudaMemcpy(ord.data(), h->order.as<uint8_t>() + (size_t)sequence * h->max_tracks, h->max_tracks, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < s.n_tracks; ++i) {
+    ses3d::PriorTrack t;
+    CU(cudaMemcpy(&t, h->tracks.as<ses3d::PriorTrack>() + (size_t)sequence * h->max_tracks + ord[i], sizeof t, cudaMemcpyDeviceToHost));
+    if (ids) ids[i] = t.id;
+    if (num_obs) num_obs[i] = t.num_obs;
+  }
+  if (s.overflow) return ses3d::set_error(SES3D_E_CAPACITY, "ses3d_prior_get_tracks: the stream overflowed max_tracks");
+  return s.n_tracks;
+}
+
+int64_t ses3d_prior_launch_count(ses3d_prior h) { return h ? h->launches : 0; }
+
+int ses3d_prior_last_kernel_ms(ses3d_prior h, float* ms) {
+  if (!h || !ms) return ses3d::set_error(SES3D_E_INVALID, "ses3d_prior_last_kernel_ms: bad argument");
+  std::lock_guard<std::mutex> lock(h->mu);
+  CU(cudaSetDevice(h->device));
+  CU(cudaEventSynchronize(h->ev1));
+  CU(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return SES3D_OK;
+}
+
+}  // extern "C"

@@ -16,6 +16,8 @@ namespace ses3d {
 //   team.min(n, f)        minimum of f(i) over [0,n) as double, DBL_MAX if empty (same value on every thread)
 //   team.warp0(f)         run f(warp_team) on the team's first warp only, then barrier (warp-cooperative
 //                         sub-algorithms such as the Munkres solver inside a CTA-wide team)
+//   team.sum(n, f)        sum of f(i) over [0,n) as double (same value on every thread; warp / serial teams)
+//   team.per_warp(n, f)   run f(warp_team, i) for i in [0,n), items spread over the team's warps, then barrier
 struct SerialTeam {
   template <class F> void pfor(int n, F&& f) { for (int i = 0; i < n; ++i) f(i); }
   template <class F> void single(F&& f) { f(); }
@@ -26,6 +28,8 @@ struct SerialTeam {
     return m;
   }
   template <class F> void warp0(F&& f) { f(*this); }
+  template <class F> double sum(int n, F&& f) { double s = 0.0; for (int i = 0; i < n; ++i) s += f(i); return s; }
+  template <class F> void per_warp(int n, F&& f) { for (int i = 0; i < n; ++i) f(*this, i); }
   void sync() {}
   int rank() const { return 0; }
   int size() const { return 1; }
@@ -59,6 +63,14 @@ struct WarpTeam {
     return m;
   }
   template <class F> __device__ __forceinline__ void warp0(F&& f) { f(*this); __syncwarp(); }
+  template <class F> __device__ __forceinline__ double sum(int n, F&& f) {   // same value on every lane
+    double s = 0.0;
+    for (int i = (int)(threadIdx.x & 31u); i < n; i += 32) s += f(i);
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    __syncwarp();
+    return s;
+  }
+  template <class F> __device__ __forceinline__ void per_warp(int n, F&& f) { for (int i = 0; i < n; ++i) f(*this, i); }
   __device__ __forceinline__ void sync() { __syncwarp(); }
   __device__ __forceinline__ int rank() const { return (int)(threadIdx.x & 31u); }
   __device__ __forceinline__ int size() const { return 32; }
@@ -75,6 +87,12 @@ struct BlockTeam {
   }
   template <class F> __device__ __forceinline__ void warp0(F&& f) {
     if (threadIdx.x < 32) { WarpTeam w; f(w); }
+    __syncthreads();
+  }
+  // every warp of the CTA takes items round-robin and runs f(warp_team, item); then barrier
+  template <class F> __device__ __forceinline__ void per_warp(int n, F&& f) {
+    const int nw = (int)(blockDim.x >> 5);
+    for (int i = (int)(threadIdx.x >> 5); i < n; i += nw) { WarpTeam w; f(w, i); }
     __syncthreads();
   }
   __device__ __forceinline__ void sync() { __syncthreads(); }

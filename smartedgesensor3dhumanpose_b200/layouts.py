@@ -77,3 +77,24 @@ def make_cameras(T_cam_base, fx=1000.0, fy=1000.0, cx=640.0, cy=360.0, Tx=0.0, T
     cams["width"] = width
     cams["height"] = height
     return cams
+
+
+class PriorParams(C.Structure):
+    """ses3d_prior_params: constants of pose_prior_mult_node.cpp (PRI:39-66) + gtsam's default LM parameters."""
+    _fields_ = [("pose_method", C.c_int32), ("normalize_by_height", C.c_int32), ("min_num_obs_track", C.c_int32),
+                ("lm_max_iterations", C.c_int32), ("min_score", C.c_float), ("pad_", C.c_float),
+                ("pred_noise_sigma", C.c_double), ("default_res_sigma", C.c_double), ("avg_delay", C.c_double),
+                ("root_sigma_factor", C.c_double), ("t_max_unobserved", C.c_double), ("dist_threshold", C.c_double),
+                ("merge_dist_thresh", C.c_double), ("lm_lambda_initial", C.c_double), ("lm_lambda_factor", C.c_double),
+                ("lm_lambda_upper_bound", C.c_double), ("lm_relative_error_tol", C.c_double),
+                ("lm_absolute_error_tol", C.c_double), ("lm_min_model_fidelity", C.c_double)]
+
+
+def default_prior_params(**overrides) -> PriorParams:
+    p = PriorParams(POSE_SIMPLE, 0, 10, 100, 0.10, 0.0, 0.12, 0.10, 0.10, 100.0, 1.0, 5.0, 0.20, 1e-5, 10.0, 1e5, 1e-5,
+                    1e-5, 1e-3)
+    for k, v in overrides.items():
+        if not hasattr(p, k):
+            raise AttributeError(f"ses3d_prior_params has no field {k!r}")
+        setattr(p, k, v)
+    return p

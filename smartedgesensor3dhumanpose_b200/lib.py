@@ -3,7 +3,7 @@ library is missing or no CUDA device is present, the calls fail loudly."""
 import ctypes as C
 from pathlib import Path
 
-from .layouts import AssocDump, Params, SynthConfig
+from .layouts import AssocDump, Params, PriorParams, SynthConfig
 
 PKG = Path(__file__).resolve().parent
 LIB_PATH = PKG / "libses3d.so"
@@ -14,7 +14,9 @@ EXPORTS = ("ses3d_default_params", "ses3d_create", "ses3d_destroy", "ses3d_get_t
            "ses3d_synth_frames", "ses3d_synth_frames_device", "ses3d_assembler_default_config",
            "ses3d_assembler_create", "ses3d_assembler_destroy", "ses3d_assembler_add", "ses3d_assembler_pop",
            "ses3d_assembler_stats", "ses3d_wire_decode_person2dlist", "ses3d_wire_encode_person2dlist",
-           "ses3d_wire_decode_personcovlist", "ses3d_wire_encode_personcovlist")
+           "ses3d_wire_decode_personcovlist", "ses3d_wire_encode_personcovlist", "ses3d_prior_default_params",
+           "ses3d_prior_create", "ses3d_prior_destroy", "ses3d_prior_reset", "ses3d_prior_run", "ses3d_prior_get_tracks",
+           "ses3d_prior_launch_count", "ses3d_prior_last_kernel_ms")
 
 
 class Ses3dError(RuntimeError):
@@ -69,6 +71,16 @@ def load():
     L.ses3d_wire_decode_personcovlist.argtypes = [vp, sz, vp, vp, vp, sz, vp, vp, i32, vp, vp, i32]
     L.ses3d_wire_encode_personcovlist.argtypes = [u32, i64, C.c_char_p, i32, vp, vp, vp, i32, vp, sz]
     L.ses3d_wire_encode_personcovlist.restype = sz
+    L.ses3d_prior_default_params.argtypes = [C.POINTER(PriorParams)]
+    L.ses3d_prior_default_params.restype = None
+    L.ses3d_prior_create.argtypes = [C.POINTER(PriorParams), i32, i32, i32, C.POINTER(vp)]
+    L.ses3d_prior_destroy.argtypes = [vp]
+    L.ses3d_prior_reset.argtypes = [vp]
+    L.ses3d_prior_run.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, u32, vp]
+    L.ses3d_prior_get_tracks.argtypes = [vp, i32, vp, vp]
+    L.ses3d_prior_launch_count.argtypes = [vp]
+    L.ses3d_prior_launch_count.restype = i64
+    L.ses3d_prior_last_kernel_ms.argtypes = [vp, vp]
     _lib = L
     return L
 

@@ -23,6 +23,12 @@ def lib():
                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.hostsim_reproject_batch.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.c_void_p]
+        L.hostsim_prior_create.restype = C.c_void_p
+        L.hostsim_prior_create.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+        L.hostsim_prior_destroy.argtypes = [C.c_void_p]
+        L.hostsim_prior_run.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 3 + [C.c_int32] + \
+            [C.c_void_p] * 6
+        L.hostsim_prior_get_tracks.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -73,3 +79,44 @@ class HostSim:
         lib().hostsim_reproject_batch(self._h, n_frames, h_max, cam_tile, _p(persons3d), _p(n_persons3d), _p(out),
                                       _p(n_out))
         return dict(persons2d=out, n_out=n_out)
+
+
+class PriorHostSim:
+    """prior_core.h (the device algorithm of ses3d_prior_run) instantiated with the serial team."""
+
+    def __init__(self, params=None, n_sequences=1, max_tracks=32):
+        from smartedgesensor3dhumanpose_b200.layouts import default_prior_params
+        self.params = params if params is not None else default_prior_params()
+        self.max_tracks = max_tracks
+        self._h = lib().hostsim_prior_create(C.byref(self.params), n_sequences, max_tracks)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().hostsim_prior_destroy(self._h)
+            self._h = None
+
+    def run(self, persons, n_persons, stamp_ns, fb_delay=None):
+        persons = np.ascontiguousarray(persons, dtype=person_cov_dtype)
+        S, T, H = persons.shape
+        n_persons = np.ascontiguousarray(n_persons, dtype=np.int32).reshape(S, T)
+        stamp_ns = np.ascontiguousarray(stamp_ns, dtype=np.int64).reshape(S, T)
+        n_cams = 0
+        if fb_delay is not None:
+            fb_delay = np.ascontiguousarray(fb_delay, dtype=np.float32)
+            n_cams = fb_delay.shape[-1]
+        fused = np.zeros((S, T, H), person_cov_dtype)
+        pred = np.zeros((S, T, H), person_cov_dtype)
+        n_out = np.zeros((S, T), np.int32)
+        pred_delay = np.zeros((S, T), np.float32)
+        track_of = np.full((S, T, H), -1, np.int32)
+        rc = lib().hostsim_prior_run(self._h, S, T, H, _p(persons), _p(n_persons), _p(stamp_ns), n_cams, _p(fb_delay),
+                                     _p(fused), _p(pred), _p(n_out), _p(pred_delay), _p(track_of))
+        if rc != 0:
+            raise RuntimeError(f"hostsim_prior_run -> {rc}")
+        return dict(fused=fused, pred=pred, n_out=n_out, pred_delay=pred_delay, track_of=track_of)
+
+    def tracks(self, sequence=0):
+        ids = np.zeros(self.max_tracks, np.int32)
+        nobs = np.zeros(self.max_tracks, np.int32)
+        n = lib().hostsim_prior_get_tracks(self._h, sequence, _p(ids), _p(nobs))
+        return ids[:n].copy(), nobs[:n].copy()

@@ -11,6 +11,7 @@
 #include "assoc_core.h"
 #include "fin_core.h"
 #include "host_setup.h"
+#include "prior_core.h"
 #include "reproj_core.h"
 #include "tri_core.h"
 
@@ -117,6 +118,67 @@ int hostsim_reproject_batch(void* h, int32_t n_frames, int32_t h_max, int32_t ca
                     n_out + (size_t)f * C);
   }
   return 0;
+}
+
+// ---- pose_prior (prior_core.h) with a serial team: same array shapes as ses3d_prior_run --------------------------
+struct PriorSim {
+  PriorTables pt;
+  int n_seq, max_tracks;
+  std::vector<PriorSeqState> states;
+  std::vector<PriorTrack> tracks;
+  std::vector<uint8_t> order;
+};
+
+void* hostsim_prior_create(const ses3d_prior_params* prm, int32_t n_sequences, int32_t max_tracks) {
+  PriorSim* s = new PriorSim;
+  s->pt.prm = *prm;
+  s->pt.limb_sigma_factor = prm->normalize_by_height ? 2.0 : 1.0;
+  s->n_seq = n_sequences;
+  s->max_tracks = max_tracks;
+  s->states.resize(n_sequences);
+  s->tracks.resize((size_t)n_sequences * max_tracks);
+  s->order.assign((size_t)n_sequences * max_tracks, 0);
+  std::memset(s->tracks.data(), 0, s->tracks.size() * sizeof(PriorTrack));
+  for (auto& st : s->states) prior_state_reset(*prm, &st, false);
+  return s;
+}
+void hostsim_prior_destroy(void* h) { delete static_cast<PriorSim*>(h); }
+
+int hostsim_prior_run(void* h, int32_t n_sequences, int32_t n_frames, int32_t h_max, const ses3d_person_cov* persons,
+                      const int32_t* n_persons, const int64_t* stamp_ns, int32_t n_cams, const float* fb_delay,
+                      ses3d_person_cov* fused, ses3d_person_cov* pred, int32_t* n_out, float* pred_delay,
+                      int32_t* track_of) {
+  PriorSim* s = static_cast<PriorSim*>(h);
+  if (n_sequences > s->n_seq) return SES3D_E_INVALID;
+  std::vector<unsigned char> wsb(prior_ws_bytes(h_max, s->max_tracks) + 64), fitb(prior_fit_ws_bytes() + 64);
+  SerialTeam tm;
+  int rc = 0;
+  for (int q = 0; q < n_sequences; ++q) {
+    for (int f = 0; f < n_frames; ++f) {
+      const size_t i = (size_t)q * n_frames + f;
+      Arena ar(wsb.data());
+      PriorWs ws;
+      prior_ws_layout(ar, h_max, s->max_tracks, &ws);
+      prior_frame(tm, s->pt, s->max_tracks, h_max, &s->states[q], s->tracks.data() + (size_t)q * s->max_tracks,
+                  s->order.data() + (size_t)q * s->max_tracks, ws, fitb.data(), 0, stamp_ns[i], n_cams,
+                  fb_delay ? fb_delay + i * n_cams : nullptr, n_persons[i], persons + i * h_max, fused + i * h_max,
+                  pred + i * h_max, n_out + i, pred_delay ? pred_delay + i : nullptr,
+                  track_of ? track_of + i * h_max : nullptr);
+    }
+    if (s->states[q].overflow) rc = SES3D_E_CAPACITY;
+  }
+  return rc;
+}
+
+int hostsim_prior_get_tracks(void* h, int32_t sequence, int32_t* ids, int32_t* num_obs) {
+  PriorSim* s = static_cast<PriorSim*>(h);
+  const PriorSeqState& st = s->states[sequence];
+  for (int i = 0; i < st.n_tracks; ++i) {
+    const PriorTrack& t = s->tracks[(size_t)sequence * s->max_tracks + s->order[(size_t)sequence * s->max_tracks + i]];
+    if (ids) ids[i] = t.id;
+    if (num_obs) num_obs[i] = t.num_obs;
+  }
+  return st.n_tracks;
 }
 
 }  // extern "C"

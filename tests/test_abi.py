@@ -116,3 +116,25 @@ def test_rig_fixture_matches_the_reference_launch_file():
         assert np.allclose(t[:, :3] @ t[:, :3].T, np.eye(3), atol=1e-9)
     # cam_1: base -> cam_1 translation/quaternion straight from cameras_extrinsics.launch:2
     assert np.allclose(centres[0], [1.5499999523162842, 3.0099990367889404, 2.6500000953674316], atol=1e-12)
+
+
+def test_prior_defaults_and_no_cpu_path():
+    """ses3d_prior_*: defaults are pose_prior's constants (PRI:39-66) and gtsam's default LM parameters; the handle
+    cannot be created without a GPU."""
+    p = layouts.PriorParams()
+    L.load().ses3d_prior_default_params(C.byref(p))
+    q = layouts.default_prior_params()
+    for name, _ in layouts.PriorParams._fields_:
+        assert getattr(p, name) == getattr(q, name), name
+    assert (p.min_num_obs_track, p.dist_threshold, p.merge_dist_thresh, p.t_max_unobserved) == (10, 5.0, 0.20, 1.0)
+    assert (p.pred_noise_sigma, p.default_res_sigma, p.avg_delay, p.root_sigma_factor) == (0.12, 0.10, 0.10, 100.0)
+    assert abs(p.min_score - 0.10) < 1e-8
+    assert (p.lm_lambda_initial, p.lm_lambda_factor, p.lm_lambda_upper_bound, p.lm_max_iterations) == (1e-5, 10.0, 1e5, 100)
+    assert C.sizeof(layouts.PriorParams) == 128   # 6 x 4 + 13 x 8
+    h = C.c_void_p()
+    assert L.load().ses3d_prior_create(C.byref(p), 0, 8, 0, C.byref(h)) == layouts.E_INVALID
+    assert L.load().ses3d_prior_create(C.byref(p), 1, 65, 0, C.byref(h)) == layouts.E_INVALID
+    import torch
+    if not torch.cuda.is_available():
+        assert L.load().ses3d_prior_create(C.byref(p), 1, 8, 0, C.byref(h)) == layouts.E_CUDA
+        assert b"no CPU path" in L.load().ses3d_last_error_string()

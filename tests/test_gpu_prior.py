@@ -1,0 +1,109 @@
+"""GPU parity of the pose_prior stage: ses3d_prior_run through the C ABI against the CPU oracle
+(oracle/pose_prior_oracle.cpp with the reference's verbatim Hungarian.cpp). Track assignment, ids, publication
+counts and scores: exact. Fused / predicted joints: within 1e-6 m (FP64 everywhere; the only difference is the
+elimination order — tree on the GPU, dense Cholesky in the oracle); covariances within 1e-5 relative."""
+import numpy as np
+import pytest
+
+from oracle.binding import PriorOracle
+from smartedgesensor3dhumanpose_b200 import api
+from smartedgesensor3dhumanpose_b200.layouts import default_prior_params, person_cov_dtype
+from smartedgesensor3dhumanpose_b200.sequences import synth_person_sequences
+from tests.test_pose_prior import compare_runs
+
+pytestmark = pytest.mark.gpu
+
+POS_TOL = 1e-6   # metres
+COV_RTOL = 1e-5
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(joint_dropout=0.3, person_dropout=0.1), dict(n_people=8, noise_m=0.03),
+                                dict(pose_method=1), dict(normalize_by_height=1), dict(min_num_obs_track=0),
+                                dict(pose_method=1, normalize_by_height=1, joint_dropout=0.2)])
+def test_prior_matches_oracle(kw):
+    kw = dict(kw)
+    pkw = {k: kw.pop(k) for k in ("normalize_by_height", "min_num_obs_track") if k in kw}
+    if "pose_method" in kw:
+        pkw["pose_method"] = kw["pose_method"]
+    S, T = 24, 60
+    seq = synth_person_sequences(S, T, kw.pop("n_people", 5), seed=21, **kw)
+    prm = default_prior_params(**pkw)
+    ro = PriorOracle(prm, S, ref_hungarian=True).run(seq["persons"], seq["n_persons"], seq["stamp_ns"], seq["fb_delay"],
+                                                      n_threads=8)
+    gpu = api.PriorTracker(prm, S)
+    rg = gpu.run(seq["persons"], seq["n_persons"], seq["stamp_ns"], seq["fb_delay"])
+    worst = compare_runs(ro, rg, POS_TOL, COV_RTOL)
+    assert ro["n_out"].sum() > S * 10
+    assert gpu.launch_count >= 2
+    print("max joint deviation", worst)
+
+
+def test_prior_track_tables_match_oracle():
+    S, T = 6, 45
+    seq = synth_person_sequences(S, T, 4, seed=22, person_dropout=0.15)
+    o = PriorOracle(default_prior_params(), S, ref_hungarian=True)
+    o.run(seq["persons"], seq["n_persons"], seq["stamp_ns"], seq["fb_delay"])
+    g = api.PriorTracker(default_prior_params(), S)
+    g.run(seq["persons"], seq["n_persons"], seq["stamp_ns"], seq["fb_delay"])
+    for s in range(S):
+        io, no = o.tracks(s)
+        ig, ng = g.tracks(s)
+        assert np.array_equal(io, ig) and np.array_equal(no, ng)
+
+
+def test_prior_streaming_and_node_mirror():
+    """One message per call (the ROS-shim use case) == the whole sequence in one launch; PosePrior mirrors the node."""
+    seq = synth_person_sequences(1, 40, 3, seed=23)
+    prm = default_prior_params()
+    whole = api.PriorTracker(prm, 1).run(seq["persons"], seq["n_persons"], seq["stamp_ns"], seq["fb_delay"])
+    node = api.PosePrior(prm, h_max=seq["h_max"])
+    for t in range(40):
+        n = seq["n_persons"][0, t]
+        fused, pred, delay = node.skeleton_callback(seq["persons"][0, t, :n], int(seq["stamp_ns"][0, t]),
+                                                    seq["fb_delay"][0, t])
+        k = whole["n_out"][0, t]
+        assert len(fused) == k and len(pred) == k
+        assert fused.tobytes() == whole["fused"][0, t, :k].tobytes()
+        assert pred.tobytes() == whole["pred"][0, t, :k].tobytes()
+        assert np.float32(delay) == whole["pred_delay"][0, t]
+    node.reset()
+    fused, _, _ = node.skeleton_callback(seq["persons"][0, 0, :seq["n_persons"][0, 0]], int(seq["stamp_ns"][0, 0]))
+    assert len(fused) == 0
+
+
+def test_prior_device_buffers_and_chain():
+    """Device-resident call (torch only provides the memory) fed by the triangulation stage's output layout."""
+    import torch
+    S, T = 64, 32
+    seq = synth_person_sequences(S, T, 4, seed=24)
+    prm = default_prior_params()
+    host = api.PriorTracker(prm, S).run(seq["persons"], seq["n_persons"], seq["stamp_ns"], seq["fb_delay"])
+    dev = torch.device("cuda:0")
+    H, C = seq["h_max"], seq["n_cams"]
+    tb = lambda a: torch.from_numpy(a.view(np.uint8).reshape(-1)).to(dev)
+    d_p, d_n, d_s, d_f = tb(seq["persons"]), tb(seq["n_persons"]), tb(seq["stamp_ns"]), tb(seq["fb_delay"])
+    rec = person_cov_dtype.itemsize
+    d_fused = torch.zeros(S * T * H * rec, dtype=torch.uint8, device=dev)
+    d_pred = torch.zeros_like(d_fused)
+    d_nout = torch.zeros(S * T, dtype=torch.int32, device=dev)
+    d_delay = torch.zeros(S * T, dtype=torch.float32, device=dev)
+    g = api.PriorTracker(prm, S)
+    st = torch.cuda.current_stream().cuda_stream
+    g.run_device(S, T, H, d_p.data_ptr(), d_n.data_ptr(), d_s.data_ptr(), C, d_f.data_ptr(), d_fused.data_ptr(),
+                 d_pred.data_ptr(), d_nout.data_ptr(), d_delay.data_ptr(), 0, st)
+    torch.cuda.synchronize()
+    n_out = d_nout.cpu().numpy().reshape(S, T)
+    assert np.array_equal(n_out, host["n_out"])
+    fused = d_fused.cpu().numpy().view(person_cov_dtype).reshape(S, T, H)
+    live = np.arange(H)[None, None, :] < n_out[:, :, None]
+    assert fused[live].tobytes() == host["fused"][live].tobytes()
+    assert g.last_kernel_ms() > 0
+
+
+def test_prior_capacity_error():
+    seq = synth_person_sequences(1, 3, 5, seed=25, person_dropout=0.0)
+    g = api.PriorTracker(default_prior_params(), 1, max_tracks=3)
+    from smartedgesensor3dhumanpose_b200.lib import Ses3dError
+    with pytest.raises(Ses3dError) as e:
+        g.run(seq["persons"], seq["n_persons"], seq["stamp_ns"], None)
+    assert e.value.code == -3

@@ -1,0 +1,267 @@
+"""pose_prior on the CPU: the oracle (oracle/pose_prior_oracle.cpp, a statement-by-statement
+restatement of pose_prior_mult_node.cpp:505-921 with gtsam's LM / Marginals restated densely) is pinned by independent
+scipy / numpy solutions and by tracker-semantics cases read off the reference source; the device algorithm
+(csrc/prior_core.h: tree elimination, warp-per-detection) is then checked against the oracle through the serial
+host instantiation. gtsam itself is absent here: parity unpinned at that boundary."""
+import numpy as np
+import pytest
+from scipy.optimize import least_squares
+
+from oracle.binding import PriorOracle
+from smartedgesensor3dhumanpose_b200.layouts import (POSE_H36M, default_prior_params, person_cov_dtype)
+from smartedgesensor3dhumanpose_b200.sequences import synth_person_sequences
+from tests.hostsim.binding import PriorHostSim
+
+# (joint a, joint b, length, sigma) as written in addBinaryFactors, PRI:434-479 / PRI:386-431
+BONES_ABS = [(8, 9, 0.134, 0.033), (8, 12, 0.134, 0.033), (9, 10, 0.449, 0.051), (10, 11, 0.446, 0.051),
+             (12, 13, 0.449, 0.051), (13, 14, 0.446, 0.051), (1, 0, 0.20, 0.025), (1, 2, 0.15, 0.042),
+             (1, 5, 0.15, 0.042), (2, 3, 0.28, 0.045), (3, 4, 0.25, 0.063), (5, 6, 0.28, 0.045), (6, 7, 0.25, 0.063),
+             (8, 20, 0.23846, 0.071), (20, 1, 0.25534, 0.035), (0, 19, 0.115, 0.035), (8, 1, 0.50, 0.071),
+             (0, 15, 0.05, 0.035), (0, 16, 0.05, 0.035), (15, 17, 0.10, 0.05), (16, 18, 0.10, 0.05)]
+BONES_NORM = [(8, 9, 0.17, 0.062), (8, 12, 0.17, 0.062), (9, 10, 0.694, 0.111), (10, 11, 0.708, 0.097),
+              (12, 13, 0.694, 0.111), (13, 14, 0.708, 0.097), (1, 0, 0.33, 0.050), (1, 2, 0.262, 0.092),
+              (1, 5, 0.262, 0.092), (2, 3, 0.515, 0.071), (3, 4, 0.444, 0.084), (5, 6, 0.515, 0.071),
+              (6, 7, 0.444, 0.084), (8, 20, 0.49, 0.05), (20, 1, 0.51, 0.05), (0, 19, 0.23, 0.05), (8, 1, 1.0, 0.02),
+              (0, 15, 0.085, 0.06), (0, 16, 0.085, 0.06), (15, 17, 0.167, 0.08), (16, 18, 0.167, 0.08)]
+
+
+def cov3(c):
+    return np.array([[c[0], c[1], c[2]], [c[1], c[3], c[4]], [c[2], c[4], c[5]]])
+
+
+def xyz(kp):
+    return np.array([kp["x"], kp["y"], kp["z"]], dtype=np.float64)
+
+
+def build_problem(person, h36m=False, norm_height=False):
+    """Independent python statement of the factor graph of one detection (PRI:631-737, 384-481)."""
+    kp = person["keypoints"]
+    meas, info = {}, {}
+    root, rs, neck, ns = np.zeros(3), 0.0, np.zeros(3), 0.0
+    if h36m:
+        root, rs, neck, ns = xyz(kp[8]), kp[8]["score"], xyz(kp[1]), kp[1]["score"]
+        root_cov = cov3(kp[8]["cov"])
+    else:
+        if kp[12]["score"] > 0 and kp[9]["score"] > 0:
+            root, rs = (xyz(kp[12]) + xyz(kp[9])) / 2, (kp[12]["score"] + kp[9]["score"]) / 2
+        if kp[5]["score"] > 0 and kp[2]["score"] > 0:
+            neck, ns = (xyz(kp[5]) + xyz(kp[2])) / 2, (kp[5]["score"] + kp[2]["score"]) / 2
+        root_cov = (cov3(kp[12]["cov"]) + cov3(kp[9]["cov"])) / 2
+    height = 1.0
+    if rs > 0.1:
+        if norm_height:
+            height = np.linalg.norm(neck - root) if ns > 0.1 else 0.6
+        meas[8] = np.zeros(3)
+        info[8] = np.linalg.inv(root_cov / height ** 2 / 1e4)
+    for k in range(21):
+        if k != 8 and kp[k]["score"] > 0.1:
+            meas[k] = (xyz(kp[k]) - root) / height
+            info[k] = np.linalg.inv(cov3(kp[k]["cov"]) / height ** 2)
+    if not h36m and ns > 0.1:
+        meas[1] = (neck - root) / height
+        info[1] = np.linalg.inv((cov3(kp[5]["cov"]) + cov3(kp[2]["cov"])) / 2 / height ** 2)
+    keys = sorted(meas)
+    idx = {k: i for i, k in enumerate(keys)}
+    sqrt_info = {k: np.linalg.cholesky(info[k]).T for k in keys}
+    lsf = 2.0 if norm_height else 1.0
+    bones = [(idx[a], idx[b], ln, s * lsf) for a, b, ln, s in (BONES_NORM if norm_height else BONES_ABS)
+             if a in idx and b in idx and not ((a, b) == (8, 1) and 20 in idx)]
+
+    def residuals(x):
+        x = x.reshape(-1, 3)
+        r = [sqrt_info[k] @ (x[idx[k]] - meas[k]) for k in keys]
+        r += [[(np.linalg.norm(x[b] - x[a]) - ln) / s] for a, b, ln, s in bones]
+        return np.concatenate(r)
+
+    x0 = np.concatenate([meas[k] for k in keys])
+    return keys, root, height, residuals, x0
+
+
+def check_fit_against_scipy(person, fused, pose_method=0, norm_height=False):
+    keys, root, height, res, x0 = build_problem(person, pose_method == POSE_H36M, norm_height)
+    sol = least_squares(res, x0, method="lm", xtol=1e-14, ftol=1e-14, gtol=1e-14)
+    want = sol.x.reshape(-1, 3) * height + root
+    f = fused["keypoints"]
+    got = np.stack([f["x"][keys], f["y"][keys], f["z"][keys]], -1)
+    # the reference's LM stops at a relative error decrease of 1e-5: agreement with the exact minimiser is ~1e-5 m
+    assert np.abs(got - want).max() < 1e-4
+    assert set(np.nonzero(f["score"] > 0)[0]) == set(keys)
+    # marginal covariances: blocks of (J^T J)^-1 at the returned point
+    xo = ((got - root) / height).ravel()
+    eps = 1e-7
+    J = np.stack([(res(xo + eps * e) - res(xo - eps * e)) / (2 * eps) for e in np.eye(len(xo))], 1)
+    S = np.linalg.inv(J.T @ J)
+    for i, k in enumerate(keys):
+        blk = S[3 * i:3 * i + 3, 3 * i:3 * i + 3] * height ** 2 * (1e4 if k == 8 else 1)
+        assert np.abs(blk - cov3(f["cov"][k])).max() <= 1e-6 * np.abs(blk).max()
+    return len(keys)
+
+
+@pytest.mark.parametrize("pose_method,norm_height", [(0, False), (0, True), (1, False), (1, True)])
+def test_oracle_fit_matches_scipy_and_dense_inverse(pose_method, norm_height):
+    seq = synth_person_sequences(1, 1, 6, seed=11 + pose_method, joint_dropout=0.15, person_dropout=0.0,
+                                 pose_method=pose_method)
+    if pose_method == POSE_H36M:   # h36m needs a measured MidHip (slot 8) to centre the skeleton
+        assert (seq["persons"][0, 0, :6]["keypoints"]["score"][:, 8] >= 0).all()
+    prm = default_prior_params(min_num_obs_track=0, pose_method=pose_method, normalize_by_height=int(norm_height))
+    r = PriorOracle(prm, 1).run(seq["persons"], seq["n_persons"], seq["stamp_ns"], seq["fb_delay"])
+    n = int(r["n_out"][0, 0])
+    assert n == seq["n_persons"][0, 0]
+    total = sum(check_fit_against_scipy(seq["persons"][0, 0, p], r["fused"][0, 0, p], pose_method, norm_height)
+                for p in range(n))
+    assert total > 50
+
+
+def compare_runs(a, b, pos_tol=1e-9, cov_rtol=1e-6):
+    assert np.array_equal(a["n_out"], b["n_out"])
+    assert np.array_equal(a["track_of"], b["track_of"])
+    assert np.array_equal(a["pred_delay"], b["pred_delay"])
+    H = a["fused"].shape[-1]
+    live = np.arange(H)[None, None, :] < a["n_out"][:, :, None]
+    worst = 0.0
+    for key in ("fused", "pred"):
+        ra, rb = a[key][live], b[key][live]
+        assert np.array_equal(ra["id"], rb["id"])
+        ka, kb = ra["keypoints"], rb["keypoints"]
+        assert np.array_equal(ka["score"], kb["score"])
+        d = max(np.abs(ka[c] - kb[c]).max(initial=0) for c in "xyz")
+        scale = np.abs(ka["cov"]).max(axis=-1, keepdims=True) + 1e-30
+        dc = (np.abs(ka["cov"] - kb["cov"]) / scale).max(initial=0)
+        assert d <= pos_tol, f"{key}: joints differ by {d}"
+        assert dc <= cov_rtol, f"{key}: covariances differ by {dc} (relative)"
+        worst = max(worst, d)
+    # unpublished slots stay zero records
+    assert not a["fused"][~live]["keypoints"]["score"].any() and not b["fused"][~live]["keypoints"]["score"].any()
+    return worst
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(joint_dropout=0.3, person_dropout=0.1), dict(n_people=7, noise_m=0.03),
+                                dict(pose_method=1), dict(normalize_by_height=1), dict(min_num_obs_track=0),
+                                dict(pose_method=1, normalize_by_height=1, joint_dropout=0.2)])
+def test_device_algorithm_matches_oracle(kw):
+    kw = dict(kw)
+    pkw = {k: kw.pop(k) for k in ("normalize_by_height", "min_num_obs_track") if k in kw}
+    if "pose_method" in kw:
+        pkw["pose_method"] = kw["pose_method"]
+    seq = synth_person_sequences(3, 50, kw.pop("n_people", 4), seed=5, **kw)
+    prm = default_prior_params(**pkw)
+    ro = PriorOracle(prm, 3, ref_hungarian=True).run(seq["persons"], seq["n_persons"], seq["stamp_ns"], seq["fb_delay"])
+    hs = PriorHostSim(prm, 3)
+    rh = hs.run(seq["persons"], seq["n_persons"], seq["stamp_ns"], seq["fb_delay"])
+    compare_runs(ro, rh)
+    assert ro["n_out"].sum() > 0
+
+
+def test_streaming_equals_batch():
+    """State persists across calls: one message per call == all messages in one call (device algorithm)."""
+    seq = synth_person_sequences(2, 30, 3, seed=8)
+    prm = default_prior_params()
+    whole = PriorHostSim(prm, 2).run(seq["persons"], seq["n_persons"], seq["stamp_ns"], seq["fb_delay"])
+    hs = PriorHostSim(prm, 2)
+    parts = [hs.run(seq["persons"][:, t:t + 1], seq["n_persons"][:, t:t + 1], seq["stamp_ns"][:, t:t + 1],
+                    seq["fb_delay"][:, t:t + 1]) for t in range(30)]
+    for key in ("fused", "pred", "n_out", "pred_delay", "track_of"):
+        got = np.concatenate([p[key] for p in parts], axis=1)
+        assert got.tobytes() == whole[key].tobytes(), key
+
+
+def _one_person(seed=0):
+    seq = synth_person_sequences(1, 40, 1, seed=seed, joint_dropout=0.0, person_dropout=0.0, shuffle=False)
+    return seq
+
+
+@pytest.mark.parametrize("impl", ["oracle", "hostsim"])
+def test_track_life_cycle(impl):
+    """Publication only after more than 10 observations (PRI:66, 845-848); ids count up (PRI:575-578);
+    tracks unobserved for > 1 s are dropped (PRI:62, 191-211); empty messages publish nothing (PRI:537-546)."""
+    seq = _one_person(3)
+    P, N, ST = seq["persons"].copy(), seq["n_persons"].copy(), seq["stamp_ns"].copy()
+    N[0, 20:25] = 0                       # five empty messages (track survives: 5/30 s < 1 s)
+    ST[0, 30:] += int(2e9)                # a 2 s gap: the track is dropped, a new one (id 1) starts
+    mk = (lambda: PriorOracle(default_prior_params(), 1)) if impl == "oracle" else (lambda: PriorHostSim(default_prior_params(), 1))
+    m = mk()
+    r = m.run(P, N, ST, None)
+    assert r["n_out"][0, :10].sum() == 0 and r["n_out"][0, 10] == 1        # 11th observation is the first published
+    assert (r["n_out"][0, 20:25] == 0).all() and r["n_out"][0, 25] == 1
+    assert (r["track_of"][0, :20, 0] == 0).all() and (r["track_of"][0, 25:30, 0] == 0).all()
+    # after the gap the cost (distance / (vel_sigma * delta_t)) is still small, so the detection re-uses track 0
+    # unless the track was pruned first; pruning happens at the end of a callback, so frame 30 still sees track 0
+    assert r["track_of"][0, 30, 0] == 0
+    assert (r["pred_delay"] == np.float32(0.1)).all()                      # no delay measurement -> g_avg_delay
+    ids, nobs = m.tracks(0)
+    assert list(ids) == [0] and nobs[0] == 35
+    # now a message far in the future with nobody in it prunes the track, and the next person gets id 1
+    Z = np.zeros((1, 1, P.shape[2]), person_cov_dtype)
+    m.run(Z, np.zeros((1, 1), np.int32), ST[:, -1:] + int(5e9), None)
+    assert len(m.tracks(0)[0]) == 0
+    r2 = m.run(P[:, :1], N[:, :1], ST[:, -1:] + int(6e9), None)
+    assert r2["track_of"][0, 0, 0] == 1
+
+
+@pytest.mark.parametrize("impl", ["oracle", "hostsim"])
+def test_duplicate_detection_tracks_merge(impl):
+    """Two detections of the same person start two tracks; they are closer than 0.20 m, so the later track is
+    erased and its published id re-assigned (PRI:870-903)."""
+    seq = _one_person(4)
+    P = np.zeros((1, 40, 4), person_cov_dtype)
+    P[:, :, 0] = seq["persons"][:, :, 0]
+    P[:, :, 1] = seq["persons"][:, :, 0]
+    P["keypoints"]["x"][:, :, 1] += 0.01 * (P["keypoints"]["score"][:, :, 1] > 0)
+    N = np.full((1, 40), 2, np.int32)
+    prm = default_prior_params(min_num_obs_track=0)
+    m = PriorOracle(prm, 1) if impl == "oracle" else PriorHostSim(prm, 1)
+    r = m.run(P, N, seq["stamp_ns"], None)
+    assert r["n_out"][0, 0] == 2
+    assert list(r["fused"][0, 0, :2]["id"]) == [0, 0]          # id 1 re-assigned to the surviving track 0
+    assert list(r["track_of"][0, 0, :2]) == [0, 1]             # as fused (before the merge)
+    assert list(m.tracks(0)[0]) == [0]
+    # next message: the second detection opens a new track (id 2) again
+    assert list(r["track_of"][0, 1, :2]) == [0, 2]
+
+
+@pytest.mark.parametrize("impl", ["oracle", "hostsim"])
+def test_feedback_delay_moving_average(impl):
+    """pred delay = mean over the last three frames of the mean positive per-camera delay (PRI:513-526, 531)."""
+    seq = _one_person(5)
+    fb = np.full((1, 40, 4), -1.0, np.float32)
+    fb[0, 0] = [0.2, -1, 0.4, 0.0]          # mean of positives 0.3
+    fb[0, 1] = [0.05, 0.05, 0.05, 0.05]
+    m = PriorOracle(default_prior_params(), 1) if impl == "oracle" else PriorHostSim(default_prior_params(), 1)
+    r = m.run(seq["persons"], seq["n_persons"], seq["stamp_ns"], fb)
+    f32 = np.float32
+    d0 = (np.float64(f32(0.2)) + np.float64(f32(0.4))) / 2
+    d1 = np.float64(f32(0.05)) * 4 / 4
+    assert r["pred_delay"][0, 0] == f32((d0 + 0.1 + 0.1) / 3)
+    assert r["pred_delay"][0, 1] == f32((d0 + d1 + 0.1) / 3)
+    assert r["pred_delay"][0, 2] == f32((d0 + d1 + 0.1) / 3)     # no measurement -> 0.1 into slot 2
+    assert r["pred_delay"][0, 3] == f32((0.1 + d1 + 0.1) / 3)
+
+
+def test_prediction_is_constant_velocity():
+    """pred = fused + mean velocity buffer * predicted delay, covariance + 0.12^2 on the diagonal (PRI:818-831)."""
+    seq = synth_person_sequences(1, 30, 1, seed=6, joint_dropout=0.0, person_dropout=0.0, noise_m=1e-4, jitter_s=0.0)
+    prm = default_prior_params(min_num_obs_track=0)
+    r = PriorOracle(prm, 1).run(seq["persons"], seq["n_persons"], seq["stamp_ns"], None)
+    f, p = r["fused"][0, :, 0]["keypoints"], r["pred"][0, :, 0]["keypoints"]
+    assert np.allclose(p["cov"][..., [0, 3, 5]] - f["cov"][..., [0, 3, 5]], 0.12 ** 2 * (f["score"][..., None] > 0))
+    assert np.array_equal(p["cov"][..., [1, 2, 4]], f["cov"][..., [1, 2, 4]])
+    # steady walking: predicted displacement ~ speed * 0.1 s, along the walking direction
+    k = 9
+    disp = np.stack([p[c][10:, k] - f[c][10:, k] for c in "xyz"], -1)
+    vel = np.stack([np.gradient(f[c][:, k], 1 / 30.0)[10:] for c in "xyz"], -1)
+    assert np.abs(disp - vel * 0.1).max() < 0.03
+    assert np.linalg.norm(disp[:, :2], axis=1).min() > 0.01
+    # first message of a track: no velocity yet
+    assert all(np.array_equal(p[c][0], f[c][0]) for c in "xyz")
+
+
+def test_reset_and_capacity():
+    seq = synth_person_sequences(1, 5, 3, seed=7, person_dropout=0.0)
+    o = PriorOracle(default_prior_params(), 1)
+    a = o.run(seq["persons"], seq["n_persons"], seq["stamp_ns"], None)
+    o.reset()
+    b = o.run(seq["persons"], seq["n_persons"], seq["stamp_ns"], None)
+    assert np.array_equal(a["track_of"], b["track_of"])            # ids restart at 0 (PRI:182-189)
+    hs = PriorHostSim(default_prior_params(), 1, max_tracks=2)
+    with pytest.raises(RuntimeError):                                # three people do not fit two track slots
+        hs.run(seq["persons"], seq["n_persons"], seq["stamp_ns"], None)

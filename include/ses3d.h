@@ -216,6 +216,10 @@ typedef struct ses3d_synth_config {
   float area[4];          /* x0, y0, x1, y1 of the floor area people stand in (base frame) */
   float min_separation;   /* metres between roots */
   int32_t min_visible;    /* emit a detection only if >= this many keypoints are inside the image */
+  int32_t frames_per_sequence; /* 0: every frame is an independent scene. T > 0: frames [qT, (q+1)T) form sequence q —
+                                  one scene whose people walk straight ahead (temporally coherent input for the
+                                  pose_prior stage); the 2-D noise stays independent per frame */
+  float step_m;           /* walking distance per frame in sequence mode (e.g. 1 m/s at 30 Hz = 0.0333) */
 } ses3d_synth_config;
 
 int ses3d_synth_frames(int32_t n_cams, const ses3d_camera* cams, const ses3d_synth_config* cfg,

@@ -248,9 +248,9 @@ class PriorTracker:
             _lib.check(n)
         return ids[:n].copy(), nobs[:n].copy()
 
-    def run(self, persons, n_persons, stamp_ns, fb_delay=None, want_track_of=True):
+    def run(self, persons, n_persons, stamp_ns, fb_delay=None, want_track_of=True, out=None):
         """persons [S][T][h_max] PersonCov, n_persons [S][T], stamp_ns [S][T] int64, fb_delay [S][T][n_cams] float32
-        or None. Host buffers in and out."""
+        or None. Host buffers in and out; `out` may hold caller-provided (e.g. pinned) "fused" / "pred" arrays."""
         persons = np.ascontiguousarray(persons, dtype=person_cov_dtype)
         S, T, H = persons.shape
         n_persons = np.ascontiguousarray(n_persons, dtype=np.int32).reshape(S, T)
@@ -259,8 +259,9 @@ class PriorTracker:
         if fb_delay is not None:
             fb_delay = np.ascontiguousarray(fb_delay, dtype=np.float32).reshape(S, T, -1)
             n_cams = fb_delay.shape[-1]
-        fused = np.zeros((S, T, H), person_cov_dtype)
-        pred = np.zeros((S, T, H), person_cov_dtype)
+        out = out or {}
+        fused = out["fused"] if "fused" in out else np.zeros((S, T, H), person_cov_dtype)
+        pred = out["pred"] if "pred" in out else np.zeros((S, T, H), person_cov_dtype)
         n_out = np.zeros((S, T), np.int32)
         pred_delay = np.zeros((S, T), np.float32)
         track_of = np.full((S, T, H), -1, np.int32) if want_track_of else None

@@ -11,8 +11,12 @@ namespace ses3d {
 
 extern __shared__ __align__(16) unsigned char smem_raw[];
 
+__constant__ PriorStatic c_prior_static = SES3D_PRIOR_STATIC_INIT;
+constexpr size_t kStaticBytes = (sizeof(PriorStatic) + 15) / 16 * 16;
+
 __global__ void __launch_bounds__(256)
-k_prior(const PriorTables pt, int n_seq, int n_frames, int h_max, int max_tracks, size_t ws_bytes, size_t fit_bytes,
+k_prior(const PriorTables pt_in, int n_seq, int n_frames, int h_max, int max_tracks, int group, size_t ws_bytes,
+        size_t fit_bytes,
         PriorSeqState* __restrict__ states, PriorTrack* __restrict__ tracks, uint8_t* __restrict__ order,
         const ses3d_person_cov* __restrict__ persons, const int32_t* __restrict__ n_persons,
         const int64_t* __restrict__ stamp_ns, int n_cams, const float* __restrict__ fb_delay,
@@ -20,17 +24,25 @@ k_prior(const PriorTables pt, int n_seq, int n_frames, int h_max, int max_tracks
         float* __restrict__ pred_delay, int32_t* __restrict__ track_of) {
   const int s = blockIdx.x;
   if (s >= n_seq) return;
-  Arena ar(smem_raw);
+  {  // skeleton tables: constant memory -> shared memory (lanes index them with different joints)
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_prior_static);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(smem_raw);
+    for (int i = (int)threadIdx.x; i < (int)(sizeof(PriorStatic) / 4); i += (int)blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  PriorTables pt = pt_in;
+  pt.st = reinterpret_cast<const PriorStatic*>(smem_raw);
+  Arena ar(smem_raw + kStaticBytes);
   PriorWs ws;
   prior_ws_layout(ar, h_max, max_tracks, &ws);
-  unsigned char* fit_ws = smem_raw + ws_bytes;
+  unsigned char* fit_ws = smem_raw + kStaticBytes + ws_bytes;
   BlockTeam tm;
   PriorSeqState* st = states + s;
   PriorTrack* trk = tracks + (size_t)s * max_tracks;
   uint8_t* ord = order + (size_t)s * max_tracks;
   for (int f = 0; f < n_frames; ++f) {
     const size_t i = (size_t)s * n_frames + f;
-    prior_frame(tm, pt, max_tracks, h_max, st, trk, ord, ws, fit_ws, fit_bytes, stamp_ns[i], n_cams,
+    prior_frame(tm, pt, max_tracks, h_max, group, st, trk, ord, ws, fit_ws, fit_bytes, stamp_ns[i], n_cams,
                 fb_delay ? fb_delay + i * n_cams : nullptr, n_persons[i], persons + i * h_max, fused + i * h_max,
                 pred + i * h_max, n_out + i, pred_delay ? pred_delay + i : nullptr,
                 track_of ? track_of + i * h_max : nullptr);
@@ -54,15 +66,19 @@ cudaError_t launch_prior(const PriorTables& pt, int n_seq, int n_frames, int h_m
                          const int32_t* n_persons, const int64_t* stamp_ns, int n_cams, const float* fb_delay,
                          ses3d_person_cov* fused, ses3d_person_cov* pred, int32_t* n_out, float* pred_delay,
                          int32_t* track_of, cudaStream_t st) {
-  int warps = std::max(1, std::min(4, h_max));   // detections of one frame fitted concurrently
-  if (const char* env = getenv("SES3D_PRIOR_WARPS")) warps = std::max(1, std::min(8, atoi(env)));
+  // One warp fits a group of up to `group` detections together (prior_core.h); a message with more detections is
+  // spread over the CTA's warps. Defaults measured on B200 (2048 streams x 6 people).
+  int group = std::max(1, std::min(PRIOR_GMAX, h_max));
+  if (const char* env = getenv("SES3D_PRIOR_GROUP")) group = std::max(1, std::min(PRIOR_GMAX, atoi(env)));
+  int warps = std::max(1, std::min(4, (h_max + group - 1) / group));
   const size_t ws_bytes = prior_ws_bytes(h_max, max_tracks);
-  const size_t fit_bytes = prior_fit_ws_bytes();
-  const size_t smem = ws_bytes + fit_bytes * warps;
+  const size_t fit_bytes = prior_fit_ws_bytes(group);
+  static_assert(sizeof(PriorStatic) % 4 == 0, "copied word by word");
+  const size_t smem = kStaticBytes + ws_bytes + fit_bytes * warps;
   if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
   cudaError_t e = cudaFuncSetAttribute(k_prior, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_prior<<<n_seq, 32 * warps, smem, st>>>(pt, n_seq, n_frames, h_max, max_tracks, ws_bytes, fit_bytes, states, tracks,
+  k_prior<<<n_seq, 32 * warps, smem, st>>>(pt, n_seq, n_frames, h_max, max_tracks, group, ws_bytes, fit_bytes, states, tracks,
                                             order, persons, n_persons, stamp_ns, n_cams, fb_delay, fused, pred, n_out,
                                             pred_delay, track_of);
   return cudaGetLastError();

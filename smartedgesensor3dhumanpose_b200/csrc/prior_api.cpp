@@ -109,6 +109,7 @@ int ses3d_prior_create(const ses3d_prior_params* params, int32_t n_sequences, in
   h->max_tracks = max_tracks;
   h->pt.prm = prm;
   h->pt.limb_sigma_factor = prm.normalize_by_height ? 2.0 : 1.0;   // PRI:934-937
+  h->pt.st = nullptr;   // set by the kernel (shared-memory copy of the skeleton tables)
   auto bail = [&](cudaError_t err, const char* what) { ses3d_prior_destroy(h); return cuda_fail(err, what); };
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
   if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");

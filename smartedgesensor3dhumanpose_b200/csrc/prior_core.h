@@ -49,9 +49,11 @@ struct PriorSeqState {                    // file-scope state of one node instan
   int32_t overflow;                       // sticky: a frame needed more than max_tracks tracks
 };
 
+struct PriorStatic;
 struct PriorTables {
   ses3d_prior_params prm;
   double limb_sigma_factor;               // PRI:934-937
+  const PriorStatic* st;                  // skeleton tables (shared memory on the GPU)
 };
 
 SES_HD void prior_state_reset(const ses3d_prior_params& prm, PriorSeqState* st, bool keep_t_prev) {  // reset() PRI:182-189
@@ -62,82 +64,95 @@ SES_HD void prior_state_reset(const ses3d_prior_params& prm, PriorSeqState* st, 
 }
 
 // ---- static skeleton forest (union of the bone tables PRI:384-481, rooted at MidHip) -------------------------
-SES_HD int prior_level(int k) {
-  const int8_t L[NFUS] = {3, 2, 3, 4, 5, 3, 4, 5, 0, 1, 2, 3, 1, 2, 3, 4, 4, 5, 5, 4, 1};
-  return L[k];
-}
-SES_HD int prior_static_parent(int k) {   // Neck (1): Belly (20) when measured, else MidHip (8) — PRI:464-471
-  const int8_t P[NFUS] = {1, 20, 1, 2, 3, 1, 5, 6, -1, 8, 9, 10, 8, 12, 13, 0, 0, 15, 16, 0, 8};
-  return P[k];
-}
-SES_HD int prior_child(int k, int i) {    // i-th potential child of joint k, -1 = none
-  const int8_t K[NFUS][4] = {{19, 15, 16, -1}, {0, 2, 5, -1},    {3, -1, -1, -1},  {4, -1, -1, -1},  {-1, -1, -1, -1},
-                             {6, -1, -1, -1},  {7, -1, -1, -1},  {-1, -1, -1, -1}, {9, 12, 20, 1},   {10, -1, -1, -1},
-                             {11, -1, -1, -1}, {-1, -1, -1, -1}, {13, -1, -1, -1}, {14, -1, -1, -1}, {-1, -1, -1, -1},
-                             {17, -1, -1, -1}, {18, -1, -1, -1}, {-1, -1, -1, -1}, {-1, -1, -1, -1}, {-1, -1, -1, -1},
-                             {1, -1, -1, -1}};
-  return K[k][i];
-}
-// bone between joint k and its parent: length and sigma (absolute PRI:434-479 / height-normalised PRI:386-431);
-// via_midhip selects the Simple-Baselines MidHip<->Neck bone for k = Neck
-SES_HD void prior_bone(int k, bool normalised, bool via_midhip, double* len, double* sigma) {
-  const double A[NFUS][2] = {{0.20, 0.025},  {0.25534, 0.035}, {0.15, 0.042},  {0.28, 0.045},  {0.25, 0.063},
-                             {0.15, 0.042},  {0.28, 0.045},    {0.25, 0.063},  {0.0, 1.0},     {0.134, 0.033},
-                             {0.449, 0.051}, {0.446, 0.051},   {0.134, 0.033}, {0.449, 0.051}, {0.446, 0.051},
-                             {0.05, 0.035},  {0.05, 0.035},    {0.10, 0.05},   {0.10, 0.05},   {0.11500, 0.035},
-                             {0.23846, 0.071}};
-  const double N[NFUS][2] = {{0.33, 0.050},  {0.51, 0.05},   {0.262, 0.092}, {0.515, 0.071}, {0.444, 0.084},
-                             {0.262, 0.092}, {0.515, 0.071}, {0.444, 0.084}, {0.0, 1.0},     {0.17, 0.062},
-                             {0.694, 0.111}, {0.708, 0.097}, {0.17, 0.062},  {0.694, 0.111}, {0.708, 0.097},
-                             {0.085, 0.06},  {0.085, 0.06},  {0.167, 0.08},  {0.167, 0.08},  {0.23, 0.05},
-                             {0.49, 0.05}};
-  if (k == SES3D_FBP_NECK && via_midhip) {
-    *len = normalised ? 1.000 : 0.50;
-    *sigma = normalised ? 0.02 : 0.071;
-    return;
+// One table object: a static const instance on the host, a __constant__ instance copied into shared memory at
+// kernel start on the GPU (per-lane indexed lookups would serialise in the constant cache and, as function-local
+// arrays, were rebuilt on the stack at every call).
+struct PriorStatic {
+  int8_t level[NFUS];        // depth in the forest: children are always deeper than their parent
+  int8_t parent[NFUS];       // Neck (1): Belly (20) when measured, else MidHip (8) — PRI:464-471
+  int8_t kids[NFUS][4];      // potential children, -1 padded
+  double bone[2][NFUS][2];   // [absolute PRI:434-479 | height-normalised PRI:386-431][child joint]{length, sigma}
+  double neck_midhip[2][2];  // the Simple-Baselines MidHip<->Neck bone PRI:470-471 / 422-423
+  double vel_sigma[NFUS];    // FUSION_BODY_PARTS::vel_sigmas, fusion_body_parts.h:33
+  int8_t lvl_joint[6][5];    // joints of every level (at most five), -1 padded
+};
+#define SES3D_PRIOR_STATIC_INIT                                                                                        \
+  {                                                                                                                    \
+    {3, 2, 3, 4, 5, 3, 4, 5, 0, 1, 2, 3, 1, 2, 3, 4, 4, 5, 5, 4, 1},                                                   \
+    {1, 20, 1, 2, 3, 1, 5, 6, -1, 8, 9, 10, 8, 12, 13, 0, 0, 15, 16, 0, 8},                                            \
+    {{19, 15, 16, -1}, {0, 2, 5, -1},    {3, -1, -1, -1},  {4, -1, -1, -1},  {-1, -1, -1, -1}, {6, -1, -1, -1},        \
+     {7, -1, -1, -1},  {-1, -1, -1, -1}, {9, 12, 20, 1},   {10, -1, -1, -1}, {11, -1, -1, -1}, {-1, -1, -1, -1},       \
+     {13, -1, -1, -1}, {14, -1, -1, -1}, {-1, -1, -1, -1}, {17, -1, -1, -1}, {18, -1, -1, -1}, {-1, -1, -1, -1},       \
+     {-1, -1, -1, -1}, {-1, -1, -1, -1}, {1, -1, -1, -1}},                                                             \
+    {{{0.20, 0.025},  {0.25534, 0.035}, {0.15, 0.042},  {0.28, 0.045},  {0.25, 0.063},  {0.15, 0.042},  {0.28, 0.045}, \
+      {0.25, 0.063},  {0.0, 1.0},       {0.134, 0.033}, {0.449, 0.051}, {0.446, 0.051}, {0.134, 0.033}, {0.449, 0.051},\
+      {0.446, 0.051}, {0.05, 0.035},    {0.05, 0.035},  {0.10, 0.05},   {0.10, 0.05},   {0.11500, 0.035},              \
+      {0.23846, 0.071}},                                                                                               \
+     {{0.33, 0.050},  {0.51, 0.05},   {0.262, 0.092}, {0.515, 0.071}, {0.444, 0.084}, {0.262, 0.092}, {0.515, 0.071},  \
+      {0.444, 0.084}, {0.0, 1.0},     {0.17, 0.062},  {0.694, 0.111}, {0.708, 0.097}, {0.17, 0.062},  {0.694, 0.111},  \
+      {0.708, 0.097}, {0.085, 0.06},  {0.085, 0.06},  {0.167, 0.08},  {0.167, 0.08},  {0.23, 0.05},   {0.49, 0.05}}},  \
+    {{0.50, 0.071}, {1.000, 0.02}},                                                                                    \
+    {2., 1., 1., 2., 3., 1., 2., 3., 1., 1., 2., 3., 1., 2., 3., 2., 2., 2., 2., 2., 1.},                              \
+    {{8, -1, -1, -1, -1}, {9, 12, 20, -1, -1}, {10, 13, 1, -1, -1}, {11, 14, 0, 2, 5}, {3, 6, 19, 15, 16},             \
+     {4, 7, 17, 18, -1}}                                                                                               \
   }
-  *len = normalised ? N[k][0] : A[k][0];
-  *sigma = normalised ? N[k][1] : A[k][1];
+inline const PriorStatic& prior_static_host() {
+  static const PriorStatic t = SES3D_PRIOR_STATIC_INIT;
+  return t;
 }
-SES_HD double prior_vel_sigma(int k) {    // FUSION_BODY_PARTS::vel_sigmas, fusion_body_parts.h:33
-  const double V[NFUS] = {2., 1., 1., 2., 3., 1., 2., 3., 1., 1., 2., 3., 1., 2., 3., 2., 2., 2., 2., 2., 1.};
-  return V[k];
+// bone between joint k and its parent; via_midhip selects the MidHip<->Neck bone for k = Neck
+SES_HD void prior_bone(const PriorStatic& T, int k, bool normalised, bool via_midhip, double* len, double* sigma) {
+  const double* b = (k == SES3D_FBP_NECK && via_midhip) ? T.neck_midhip[normalised ? 1 : 0] : T.bone[normalised ? 1 : 0][k];
+  *len = b[0];
+  *sigma = b[1];
 }
 
 // ---- workspaces ---------------------------------------------------------------------------------------------
-struct PriorFitWs {       // one detection's factor graph, one per warp; arrays indexed by joint
-  double *m, *x, *xn, *dl, *ub, *gu, *w, *z, *y, *pa;   // [21][3]
-  double *R, *W, *Dinv, *Sg;                            // [21][6]  (00,01,02,11,12,22)
-  double *e, *alpha, *beta;                             // [21]
-  int8_t* par;                                          // [21] parent joint of the bone, -1 none
-  uint8_t *msd, *usev;                                  // [21] measured / velocity usable
-  int* scal;                                            // [4] {measured mask, factorisation failed, -, -}
+constexpr int PRIOR_GMAX = 6;   // detections one warp fits together: 6 x 5 joints of the widest tree level = 30 lanes
+constexpr int PRIOR_LW = 5;     // widest level
+
+struct PriorFitScal {           // LM / bookkeeping state of one detection of the group
+  double lambda, error, cur_error, old_lin, height, height_prev;
+  double root[3], neck[3], root_prev[3];
+  float root_score, neck_score;
+  uint32_t mask, had;           // measured joints; joints the track's prevEstimate held
+  int32_t iterations, trials;
+  uint8_t active, lm, need_lin, fail, accept, use_marginals, pad_[2];
 };
-enum { PF_MASK = 0, PF_FAIL = 1 };
+
+struct PriorFitWs {       // the factor graphs of one group, one workspace per warp; index i = g * 21 + joint
+  double *m, *x, *dl, *w, *z;        // [G*21][3]
+  double* guy;                       // [G*21][6]: gu (gradient of the unary factor) | y = Dinv b; later the marginal Sg
+  double *W, *Dinv;                  // [G*21][6]  (00,01,02,11,12,22): information of the unary factor; block inverse
+  double *e, *alpha, *beta, *ta, *tb;  // [G*21]
+  int8_t* par;                       // [G*21] parent joint of the bone, -1 none
+  uint8_t *msd, *usev;               // [G*21] measured / velocity usable
+  PriorFitScal* sc;                  // [G]
+};
 
 template <class A>
-SES_HD void prior_fit_ws_layout(A& ar, PriorFitWs* ws) {
-  double* v3[10];
-  for (int i = 0; i < 10; ++i) v3[i] = ar.template take<double>(NFUS * 3);
-  double* v6[4];
-  for (int i = 0; i < 4; ++i) v6[i] = ar.template take<double>(NFUS * 6);
-  double* v1[3];
-  for (int i = 0; i < 3; ++i) v1[i] = ar.template take<double>(NFUS);
-  int* scal = ar.template take<int>(4);
-  int8_t* par = ar.template take<int8_t>(NFUS);
-  uint8_t* msd = ar.template take<uint8_t>(NFUS);
-  uint8_t* usev = ar.template take<uint8_t>(NFUS);
+SES_HD void prior_fit_ws_layout(A& ar, int G, PriorFitWs* ws) {
+  const size_t n = (size_t)G * NFUS;
+  double* v3[5];
+  for (int i = 0; i < 5; ++i) v3[i] = ar.template take<double>(n * 3);
+  double* v6[3];
+  for (int i = 0; i < 3; ++i) v6[i] = ar.template take<double>(n * 6);
+  double* v1[5];
+  for (int i = 0; i < 5; ++i) v1[i] = ar.template take<double>(n);
+  PriorFitScal* sc = ar.template take<PriorFitScal>(G);
+  int8_t* par = ar.template take<int8_t>(n);
+  uint8_t* msd = ar.template take<uint8_t>(n);
+  uint8_t* usev = ar.template take<uint8_t>(n);
   if (ws) {
-    ws->m = v3[0]; ws->x = v3[1]; ws->xn = v3[2]; ws->dl = v3[3]; ws->ub = v3[4]; ws->gu = v3[5]; ws->w = v3[6];
-    ws->z = v3[7]; ws->y = v3[8]; ws->pa = v3[9];
-    ws->R = v6[0]; ws->W = v6[1]; ws->Dinv = v6[2]; ws->Sg = v6[3];
-    ws->e = v1[0]; ws->alpha = v1[1]; ws->beta = v1[2];
-    ws->scal = scal; ws->par = par; ws->msd = msd; ws->usev = usev;
+    ws->m = v3[0]; ws->x = v3[1]; ws->dl = v3[2]; ws->w = v3[3]; ws->z = v3[4];
+    ws->guy = v6[0]; ws->W = v6[1]; ws->Dinv = v6[2];
+    ws->e = v1[0]; ws->alpha = v1[1]; ws->beta = v1[2]; ws->ta = v1[3]; ws->tb = v1[4];
+    ws->sc = sc; ws->par = par; ws->msd = msd; ws->usev = usev;
   }
 }
-inline size_t prior_fit_ws_bytes() {
+inline size_t prior_fit_ws_bytes(int G) {
   ArenaSizer s;
-  prior_fit_ws_layout(s, nullptr);
+  prior_fit_ws_layout(s, G, nullptr);
   return (s.used + 15) / 16 * 16;
 }
 
@@ -185,44 +200,45 @@ inline size_t prior_ws_bytes(int h_max, int max_tracks) {
 }
 
 // ---- 3x3 helpers --------------------------------------------------------------------------------------------
-// sqrt-information of noiseModel::Gaussian::Covariance(S): diagonal S -> 1/sigma; else upper Cholesky factor of S^-1.
-// S, R as (00,01,02,11,12,22); R upper triangular.
-SES_HD void prior_sqrt_information(const double S[6], double R[6]) {
+// information matrix W = R^T R of noiseModel::Gaussian::Covariance(S): diagonal S -> whitening by 1/sigma
+// (Diagonal / Isotropic), else Information(S^-1) whose Cholesky factor R satisfies R^T R = S^-1.
+// S, W as (00,01,02,11,12,22).
+SES_HD void prior_information(const double S[6], double W[6]) {
   if (S[1] == 0.0 && S[2] == 0.0 && S[4] == 0.0) {
-    R[0] = 1.0 / sqrt(S[0]); R[1] = 0.0; R[2] = 0.0; R[3] = 1.0 / sqrt(S[3]); R[4] = 0.0; R[5] = 1.0 / sqrt(S[5]);
+    const double r0 = 1.0 / sqrt(S[0]), r1 = 1.0 / sqrt(S[3]), r2 = 1.0 / sqrt(S[5]);
+    W[0] = r0 * r0; W[1] = 0.0; W[2] = 0.0; W[3] = r1 * r1; W[4] = 0.0; W[5] = r2 * r2;
     return;
   }
   const double c00 = S[3] * S[5] - S[4] * S[4], c01 = S[4] * S[2] - S[1] * S[5], c02 = S[1] * S[4] - S[3] * S[2];
   const double det = S[0] * c00 + S[1] * c01 + S[2] * c02;
   const double id = 1.0 / det;
-  const double i00 = c00 * id, i10 = c01 * id, i20 = c02 * id;
-  const double i11 = (S[0] * S[5] - S[2] * S[2]) * id, i21 = (S[1] * S[2] - S[0] * S[4]) * id;
-  const double i22 = (S[0] * S[3] - S[1] * S[1]) * id;
-  const double l00 = sqrt(i00);
-  const double l10 = i10 / l00, l20 = i20 / l00;
-  const double l11 = sqrt(i11 - l10 * l10);
-  const double l21 = (i21 - l20 * l10) / l11;
-  const double l22 = sqrt(i22 - l20 * l20 - l21 * l21);
-  R[0] = l00; R[1] = l10; R[2] = l20; R[3] = l11; R[4] = l21; R[5] = l22;
+  W[0] = c00 * id; W[1] = c01 * id; W[2] = c02 * id;
+  W[3] = (S[0] * S[5] - S[2] * S[2]) * id;
+  W[4] = (S[1] * S[2] - S[0] * S[4]) * id;
+  W[5] = (S[0] * S[3] - S[1] * S[1]) * id;
 }
 SES_HD void sym6_mul(const double A[6], const double v[3], double o[3]) {
   o[0] = A[0] * v[0] + A[1] * v[1] + A[2] * v[2];
   o[1] = A[1] * v[0] + A[3] * v[1] + A[4] * v[2];
   o[2] = A[2] * v[0] + A[4] * v[1] + A[5] * v[2];
 }
-// inverse of a symmetric positive definite 3x3; false when a Cholesky pivot is not positive / not finite
+// inverse of a symmetric positive definite 3x3 through its LDL^T factorisation (three reciprocals; the adjugate
+// formula needs one but loses ~4 digits on the ill-conditioned information blocks of elongated covariances);
+// false when a pivot is not positive / not finite
 SES_HD bool sym6_inverse_spd(const double D[6], double I[6]) {
   const double p0 = D[0];
   if (!(p0 > 0.0)) return false;
-  const double l10 = D[1] / p0, l20 = D[2] / p0;
+  const double q0 = 1.0 / p0;
+  const double l10 = D[1] * q0, l20 = D[2] * q0;
   const double p1 = D[3] - l10 * D[1];
   if (!(p1 > 0.0)) return false;
+  const double q1 = 1.0 / p1;
   const double t21 = D[4] - l20 * D[1];
-  const double l21 = t21 / p1;
+  const double l21 = t21 * q1;
   const double p2 = D[5] - l20 * D[2] - l21 * t21;
   if (!(p2 > 0.0) || !(p2 < DBL_MAX)) return false;
+  const double q2 = 1.0 / p2;
   // D = L diag(p) L^T  =>  D^-1 = L^-T diag(1/p) L^-1, L^-1 = [[1,0,0],[-l10,1,0],[l10 l21 - l20, -l21, 1]]
-  const double q0 = 1.0 / p0, q1 = 1.0 / p1, q2 = 1.0 / p2;
   const double a = l10 * l21 - l20;
   I[5] = q2;
   I[4] = -l21 * q2;
@@ -244,7 +260,7 @@ SES_HD double prior_normed_dist(const PriorTables& pt, const PriorTrack& tr, con
       const double dx = kp.x - (tr.prev[k][0] * tr.height_prev + tr.root_prev[0]);
       const double dy = kp.y - (tr.prev[k][1] * tr.height_prev + tr.root_prev[1]);
       const double dz = kp.z - (tr.prev[k][2] * tr.height_prev + tr.root_prev[2]);
-      dist += sqrt(dx * dx + dy * dy + dz * dz) / (prior_vel_sigma(k) * delta_t);
+      dist += sqrt(dx * dx + dy * dy + dz * dz) / (pt.st->vel_sigma[k] * delta_t);
       ++used;
     }
   }
@@ -322,359 +338,439 @@ SES_HD bool prior_has_measurement(const PriorTables& pt, const ses3d_person_cov&
   return false;
 }
 
-// ---- the skeleton fit of one detection (PRI:587-853), run by a warp-sized team ---------------------------------
-// unary + bone error of joint k at the point xs (NonlinearFactorGraph::error summand)
-SES_HD double prior_joint_error(const PriorTables& pt, const PriorFitWs& ws, const double* xs, int k) {
-  if (!ws.msd[k]) return 0.0;
-  const double* R = ws.R + 6 * k;
-  const double d0 = xs[3 * k] - ws.m[3 * k], d1 = xs[3 * k + 1] - ws.m[3 * k + 1], d2 = xs[3 * k + 2] - ws.m[3 * k + 2];
-  const double w0 = R[0] * d0 + R[1] * d1 + R[2] * d2, w1 = R[3] * d1 + R[4] * d2, w2 = R[5] * d2;
-  double err = 0.5 * (w0 * w0 + w1 * w1 + w2 * w2);
-  const int p = ws.par[k];
-  if (p >= 0) {
-    double len, sigma;
-    prior_bone(k, pt.prm.normalize_by_height != 0, p == SES3D_FBP_MIDHIP, &len, &sigma);
-    const double dx = xs[3 * k] - xs[3 * p], dy = xs[3 * k + 1] - xs[3 * p + 1], dz = xs[3 * k + 2] - xs[3 * p + 2];
-    const double r = sqrt(dx * dx + dy * dy + dz * dz);
-    const double e = (r - len) * (1.0 / (sigma * pt.limb_sigma_factor));   // Isotropic::whiten: v * invsigma
-    err += 0.5 * (e * e);
-  }
-  return err;
+// ---- the skeleton fits of one group of detections (PRI:587-853), run by a warp-sized team -------------------------
+// A group is up to PRIOR_GMAX detections of the same message. Dense phases run over (detection, joint) items, the
+// tree sweeps over (detection, joint-of-level) items, so the lanes of the warp stay occupied; every detection
+// carries its own LM state (lambda, errors, flags) through the same instruction stream and simply idles once
+// it has converged.
+
+// bone residual (|x_k - x_p| - len) / sigma and, optionally, the whitened direction w; xk/xp are the end points
+SES_HD double prior_bone_residual(const PriorTables& pt, int k, int p, const double* xk, const double* xp, double* w) {
+  double len, sigma;
+  prior_bone(*pt.st, k, pt.prm.normalize_by_height != 0, p == SES3D_FBP_MIDHIP, &len, &sigma);
+  const double is = 1.0 / (sigma * pt.limb_sigma_factor);   // Isotropic::whiten: v * invsigma
+  const double dx = xk[0] - xp[0], dy = xk[1] - xp[1], dz = xk[2] - xp[2];
+  const double r = sqrt(dx * dx + dy * dy + dz * dz);
+  if (w) { const double s = is / r; w[0] = dx * s; w[1] = dy * s; w[2] = dz * s; }
+  return (r - len) * is;
 }
 
-// linearise at ws.x: whitened unary residual ub, its gradient gu = R^T ub, bone direction w and residual e
+// leaf-to-root elimination of (J^T J + lambda I) for every detection with `lm` (or all active ones when
+// for_marginals, lambda = 0): per joint Dinv, z = Dinv w, y = Dinv b, alpha = w.z, beta = w.y. A block that is not
+// positive definite sets the detection's fail flag (gtsam: IndeterminantLinearSystemException).
 template <class WT>
-SES_HD void prior_linearize(WT& tm, const PriorTables& pt, const PriorFitWs& ws) {
-  tm.pfor(NFUS, [&](int k) {
-    if (!ws.msd[k]) return;
-    const double* R = ws.R + 6 * k;
-    const double* x = ws.x + 3 * k;
-    const double d0 = x[0] - ws.m[3 * k], d1 = x[1] - ws.m[3 * k + 1], d2 = x[2] - ws.m[3 * k + 2];
-    const double u0 = R[0] * d0 + R[1] * d1 + R[2] * d2, u1 = R[3] * d1 + R[4] * d2, u2 = R[5] * d2;
-    ws.ub[3 * k] = u0; ws.ub[3 * k + 1] = u1; ws.ub[3 * k + 2] = u2;
-    ws.gu[3 * k] = R[0] * u0;
-    ws.gu[3 * k + 1] = R[1] * u0 + R[3] * u1;
-    ws.gu[3 * k + 2] = R[2] * u0 + R[4] * u1 + R[5] * u2;
-    const int p = ws.par[k];
-    double w0 = 0, w1 = 0, w2 = 0, e = 0;
-    if (p >= 0) {
-      double len, sigma;
-      prior_bone(k, pt.prm.normalize_by_height != 0, p == SES3D_FBP_MIDHIP, &len, &sigma);
-      const double is = 1.0 / (sigma * pt.limb_sigma_factor);
-      const double dx = x[0] - ws.x[3 * p], dy = x[1] - ws.x[3 * p + 1], dz = x[2] - ws.x[3 * p + 2];
-      const double r = sqrt(dx * dx + dy * dy + dz * dz);
-      const double s = is / r;
-      w0 = dx * s; w1 = dy * s; w2 = dz * s;
-      e = (r - len) * is;
-    }
-    ws.w[3 * k] = w0; ws.w[3 * k + 1] = w1; ws.w[3 * k + 2] = w2;
-    ws.e[k] = e;
-  });
-}
-
-// leaf-to-root elimination of (J^T J + lambda I): per joint Dinv, z = Dinv w, y = Dinv b, alpha = w.z, beta = w.y.
-// Sets ws.scal[PF_FAIL] when a block is not positive definite (gtsam: IndeterminantLinearSystemException).
-template <class WT>
-SES_HD void prior_eliminate(WT& tm, const PriorFitWs& ws, double lambda) {
-  tm.single([&] { ws.scal[PF_FAIL] = 0; });
+SES_HD void prior_eliminate(WT& tm, const PriorTables& pt, int G, const PriorFitWs& ws, bool for_marginals) {
   for (int L = PRIOR_LEVELS - 1; L >= 0; --L) {
-    tm.pfor(NFUS, [&](int k) {
-      if (!ws.msd[k] || prior_level(k) != L) return;
-      const double* W = ws.W + 6 * k;
+    tm.pfor(G * PRIOR_LW, [&](int it) {
+      const int g = it / PRIOR_LW, k = pt.st->lvl_joint[L][it % PRIOR_LW];
+      if (k < 0) return;
+      PriorFitScal& sc = ws.sc[g];
+      if (!(for_marginals ? sc.active : sc.lm)) return;
+      const int i = g * NFUS + k;
+      if (!ws.msd[i]) return;
+      const double lambda = for_marginals ? 0.0 : sc.lambda;
+      const double* W = ws.W + 6 * i;
       double D[6] = {W[0] + lambda, W[1], W[2], W[3] + lambda, W[4], W[5] + lambda};
-      double b[3] = {-ws.gu[3 * k], -ws.gu[3 * k + 1], -ws.gu[3 * k + 2]};
-      if (ws.par[k] >= 0) {
-        const double* w = ws.w + 3 * k;
-        const double e = ws.e[k];
+      double b[3] = {-ws.guy[6 * i], -ws.guy[6 * i + 1], -ws.guy[6 * i + 2]};
+      const double* w = ws.w + 3 * i;
+      if (ws.par[i] >= 0) {
+        const double e = ws.e[i];
         D[0] += w[0] * w[0]; D[1] += w[0] * w[1]; D[2] += w[0] * w[2];
         D[3] += w[1] * w[1]; D[4] += w[1] * w[2]; D[5] += w[2] * w[2];
         b[0] -= w[0] * e; b[1] -= w[1] * e; b[2] -= w[2] * e;
       }
-      for (int i = 0; i < 4; ++i) {
-        const int c = prior_child(k, i);
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const int c = pt.st->kids[k][c4];
         if (c < 0) break;
-        if (!ws.msd[c] || ws.par[c] != k) continue;
-        const double* w = ws.w + 3 * c;
-        const double f = 1.0 - ws.alpha[c];        // bone term w w^T minus the child's Schur complement alpha w w^T
-        const double g = ws.e[c] + ws.beta[c];     // -(-w e) from the bone gradient, + beta w from the elimination
-        D[0] += f * w[0] * w[0]; D[1] += f * w[0] * w[1]; D[2] += f * w[0] * w[2];
-        D[3] += f * w[1] * w[1]; D[4] += f * w[1] * w[2]; D[5] += f * w[2] * w[2];
-        b[0] += g * w[0]; b[1] += g * w[1]; b[2] += g * w[2];
+        const int ic = g * NFUS + c;
+        if (!ws.msd[ic] || ws.par[ic] != k) continue;
+        const double* wc = ws.w + 3 * ic;
+        const double f = 1.0 - ws.alpha[ic];        // bone term w w^T minus the child's Schur complement alpha w w^T
+        const double q = ws.e[ic] + ws.beta[ic];    // -(-w e) from the bone gradient, + beta w from the elimination
+        D[0] += f * wc[0] * wc[0]; D[1] += f * wc[0] * wc[1]; D[2] += f * wc[0] * wc[2];
+        D[3] += f * wc[1] * wc[1]; D[4] += f * wc[1] * wc[2]; D[5] += f * wc[2] * wc[2];
+        b[0] += q * wc[0]; b[1] += q * wc[1]; b[2] += q * wc[2];
       }
-      double* I = ws.Dinv + 6 * k;
+      double* I = ws.Dinv + 6 * i;
       if (!sym6_inverse_spd(D, I)) {
-        ws.scal[PF_FAIL] = 1;
+        sc.fail = 1;
         I[0] = I[3] = I[5] = 1.0; I[1] = I[2] = I[4] = 0.0;
       }
-      sym6_mul(I, ws.w + 3 * k, ws.z + 3 * k);
-      sym6_mul(I, b, ws.y + 3 * k);
-      const double* w = ws.w + 3 * k;
-      ws.alpha[k] = w[0] * ws.z[3 * k] + w[1] * ws.z[3 * k + 1] + w[2] * ws.z[3 * k + 2];
-      ws.beta[k] = w[0] * ws.y[3 * k] + w[1] * ws.y[3 * k + 1] + w[2] * ws.y[3 * k + 2];
+      double* z = ws.z + 3 * i;
+      double* y = ws.guy + 6 * i + 3;
+      sym6_mul(I, w, z);
+      sym6_mul(I, b, y);
+      ws.alpha[i] = w[0] * z[0] + w[1] * z[1] + w[2] * z[2];
+      ws.beta[i] = w[0] * y[0] + w[1] * y[1] + w[2] * y[2];
     });
   }
 }
 
 // root-to-leaf back-substitution: delta_k = y_k + z_k (w_k . delta_parent)
 template <class WT>
-SES_HD void prior_backsubstitute(WT& tm, const PriorFitWs& ws) {
+SES_HD void prior_backsubstitute(WT& tm, const PriorTables& pt, int G, const PriorFitWs& ws) {
   for (int L = 0; L < PRIOR_LEVELS; ++L) {
-    tm.pfor(NFUS, [&](int k) {
-      if (!ws.msd[k] || prior_level(k) != L) return;
+    tm.pfor(G * PRIOR_LW, [&](int it) {
+      const int g = it / PRIOR_LW, k = pt.st->lvl_joint[L][it % PRIOR_LW];
+      if (k < 0 || !ws.sc[g].lm || ws.sc[g].fail) return;
+      const int i = g * NFUS + k;
+      if (!ws.msd[i]) return;
       double s = 0.0;
-      const int p = ws.par[k];
-      if (p >= 0) s = ws.w[3 * k] * ws.dl[3 * p] + ws.w[3 * k + 1] * ws.dl[3 * p + 1] + ws.w[3 * k + 2] * ws.dl[3 * p + 2];
-      for (int i = 0; i < 3; ++i) ws.dl[3 * k + i] = ws.y[3 * k + i] + ws.z[3 * k + i] * s;
+      const int p = ws.par[i];
+      if (p >= 0) {
+        const double* dp = ws.dl + 3 * (g * NFUS + p);
+        s = ws.w[3 * i] * dp[0] + ws.w[3 * i + 1] * dp[1] + ws.w[3 * i + 2] * dp[2];
+      }
+      const double* y = ws.guy + 6 * i + 3;
+      for (int a = 0; a < 3; ++a) ws.dl[3 * i + a] = y[a] + ws.z[3 * i + a] * s;
     });
   }
 }
 
-// marginal covariances after prior_eliminate(lambda = 0): Sigma_k = Dinv_k + (w_k^T Sigma_p w_k) z_k z_k^T
+// marginal covariances after prior_eliminate(for_marginals): Sigma_k = Dinv_k + (w_k^T Sigma_p w_k) z_k z_k^T,
+// written over gu | y (no longer needed)
 template <class WT>
-SES_HD void prior_marginals(WT& tm, const PriorFitWs& ws) {
+SES_HD void prior_marginals(WT& tm, const PriorTables& pt, int G, const PriorFitWs& ws) {
   for (int L = 0; L < PRIOR_LEVELS; ++L) {
-    tm.pfor(NFUS, [&](int k) {
-      if (!ws.msd[k] || prior_level(k) != L) return;
-      const double* I = ws.Dinv + 6 * k;
-      double* S = ws.Sg + 6 * k;
-      double g = 0.0;
-      const int p = ws.par[k];
+    tm.pfor(G * PRIOR_LW, [&](int it) {
+      const int g = it / PRIOR_LW, k = pt.st->lvl_joint[L][it % PRIOR_LW];
+      if (k < 0 || !ws.sc[g].active || !ws.sc[g].use_marginals) return;
+      const int i = g * NFUS + k;
+      if (!ws.msd[i]) return;
+      const double* I = ws.Dinv + 6 * i;
+      double* S = ws.guy + 6 * i;
+      double q = 0.0;
+      const int p = ws.par[i];
       if (p >= 0) {
         double t[3];
-        sym6_mul(ws.Sg + 6 * p, ws.w + 3 * k, t);
-        g = ws.w[3 * k] * t[0] + ws.w[3 * k + 1] * t[1] + ws.w[3 * k + 2] * t[2];
+        sym6_mul(ws.guy + 6 * (g * NFUS + p), ws.w + 3 * i, t);
+        q = ws.w[3 * i] * t[0] + ws.w[3 * i + 1] * t[1] + ws.w[3 * i + 2] * t[2];
       }
-      const double* z = ws.z + 3 * k;
-      S[0] = I[0] + g * z[0] * z[0]; S[1] = I[1] + g * z[0] * z[1]; S[2] = I[2] + g * z[0] * z[2];
-      S[3] = I[3] + g * z[1] * z[1]; S[4] = I[4] + g * z[1] * z[2]; S[5] = I[5] + g * z[2] * z[2];
+      const double* z = ws.z + 3 * i;
+      S[0] = I[0] + q * z[0] * z[0]; S[1] = I[1] + q * z[0] * z[1]; S[2] = I[2] + q * z[0] * z[2];
+      S[3] = I[3] + q * z[1] * z[1]; S[4] = I[4] + q * z[1] * z[2]; S[5] = I[5] + q * z[2] * z[2];
     });
   }
 }
 
-// GaussianFactorGraph::error(delta) of the undamped linearised system
+// linearise at x for the detections selected by `which` (0: lm && need_lin, 1: all active): gradient gu = W d of the
+// unary factor, bone direction w and residual e; ta = the joint's share of linear.error(0)
 template <class WT>
-SES_HD double prior_linear_error(WT& tm, const PriorFitWs& ws, bool at_zero) {
-  return tm.sum(NFUS, [&](int k) -> double {
-    if (!ws.msd[k]) return 0.0;
-    double u0 = ws.ub[3 * k], u1 = ws.ub[3 * k + 1], u2 = ws.ub[3 * k + 2], e = ws.e[k];
-    if (!at_zero) {
-      const double* R = ws.R + 6 * k;
-      const double* d = ws.dl + 3 * k;
-      u0 += R[0] * d[0] + R[1] * d[1] + R[2] * d[2];
-      u1 += R[3] * d[1] + R[4] * d[2];
-      u2 += R[5] * d[2];
-      const int p = ws.par[k];
-      if (p >= 0) {
-        const double* w = ws.w + 3 * k;
-        e += w[0] * (d[0] - ws.dl[3 * p]) + w[1] * (d[1] - ws.dl[3 * p + 1]) + w[2] * (d[2] - ws.dl[3 * p + 2]);
-      }
+SES_HD void prior_linearize(WT& tm, const PriorTables& pt, int G, const PriorFitWs& ws, int which) {
+  tm.pfor(G * NFUS, [&](int i) {
+    const int g = i / NFUS, k = i % NFUS;
+    const PriorFitScal& sc = ws.sc[g];
+    if (!(which ? sc.active : (sc.lm && sc.need_lin)) || !ws.msd[i]) return;
+    const double* x = ws.x + 3 * i;
+    const double d[3] = {x[0] - ws.m[3 * i], x[1] - ws.m[3 * i + 1], x[2] - ws.m[3 * i + 2]};
+    double* gu = ws.guy + 6 * i;
+    sym6_mul(ws.W + 6 * i, d, gu);
+    double err = 0.5 * (d[0] * gu[0] + d[1] * gu[1] + d[2] * gu[2]);
+    const int p = ws.par[i];
+    double e = 0.0;
+    double* w = ws.w + 3 * i;
+    w[0] = w[1] = w[2] = 0.0;
+    if (p >= 0) {
+      e = prior_bone_residual(pt, k, p, x, ws.x + 3 * (g * NFUS + p), w);
+      err += 0.5 * (e * e);
     }
-    return 0.5 * (u0 * u0 + u1 * u1 + u2 * u2) + 0.5 * (e * e);
+    ws.e[i] = e;
+    ws.ta[i] = err;
   });
 }
 
-// One detection. tr = its track (exclusively owned by this team during the call). fused / pred may be null
-// (track not published yet, PRI:845-848). Returns false when the detection has no usable joint (PRI:739-741).
+SES_HD double prior_sum_terms(const PriorFitWs& ws, const double* t, int g) {
+  double s = 0.0;
+  for (int k = 0; k < NFUS; ++k)
+    if (ws.msd[g * NFUS + k]) s += t[g * NFUS + k];
+  return s;
+}
+
+// G detections persons[0..G) of one message; slot[g] = track slot (-1: skip), out_idx[g] = position in the
+// published list (-1: not published, PRI:845-848). Tracks are exclusively owned by this team during the call.
 template <class WT>
-SES_HD bool prior_fit_person(WT& tm, const PriorTables& pt, const ses3d_person_cov& person, PriorTrack& tr, double t,
-                             double t_prev_global, int frame_nr, double pred_delta_t, const PriorFitWs& ws,
-                             ses3d_person_cov* fused, ses3d_person_cov* pred) {
+SES_HD void prior_fit_group(WT& tm, const PriorTables& pt, int G, const ses3d_person_cov* persons, PriorTrack* tracks,
+                            const int* slot, const int* out_idx, ses3d_person_cov* fused, ses3d_person_cov* pred,
+                            double t, double t_prev_global, int frame_nr, double pred_delta_t, const PriorFitWs& ws) {
   const ses3d_prior_params& q = pt.prm;
-  const PriorRootNeck rn = prior_root_neck(pt, person);
-  const double height = rn.height;
   const bool simple = q.pose_method == SES3D_POSE_SIMPLE;
 
-  // measurements and their sqrt-information (PRI:658-737)
-  tm.pfor(NFUS, [&](int k) {
-    bool ms = false;
-    double c[6], mk[3] = {0.0, 0.0, 0.0};
-    if (k == SES3D_FBP_MIDHIP) {
-      if (rn.root_score > q.min_score) {
-        ms = true;
-        if (simple) {
-          const double* a = person.keypoints[SES3D_FBP_LHIP].cov;
-          const double* b = person.keypoints[SES3D_FBP_RHIP].cov;
-          for (int i = 0; i < 6; ++i) c[i] = (a[i] + b[i]) / 2.0;
-        } else {
-          for (int i = 0; i < 6; ++i) c[i] = person.keypoints[SES3D_FBP_MIDHIP].cov[i];
-        }
-        for (int i = 0; i < 6; ++i) c[i] = c[i] / (height * height) / (q.root_sigma_factor * q.root_sigma_factor);
-      }
-    } else {
-      const ses3d_keypoint_cov& kp = person.keypoints[k];
-      if (kp.score > q.min_score) {
-        ms = true;
-        for (int i = 0; i < 6; ++i) c[i] = kp.cov[i] / (height * height);
-        mk[0] = (kp.x - rn.root[0]) / height; mk[1] = (kp.y - rn.root[1]) / height; mk[2] = (kp.z - rn.root[2]) / height;
-      }
-      if (k == SES3D_FBP_NECK && simple && rn.neck_score > q.min_score) {
-        ms = true;
-        const double* a = person.keypoints[SES3D_FBP_LSHOULDER].cov;
-        const double* b = person.keypoints[SES3D_FBP_RSHOULDER].cov;
-        for (int i = 0; i < 6; ++i) c[i] = (a[i] + b[i]) / 2.0 / (height * height);
-        for (int i = 0; i < 3; ++i) mk[i] = (rn.neck[i] - rn.root[i]) / height;
-      }
-    }
-    ws.msd[k] = ms ? 1 : 0;
-    if (ms) {
-      double* R = ws.R + 6 * k;
-      prior_sqrt_information(c, R);
-      double* W = ws.W + 6 * k;                     // R^T R, constant over the LM iterations
-      W[0] = R[0] * R[0]; W[1] = R[0] * R[1]; W[2] = R[0] * R[2];
-      W[3] = R[1] * R[1] + R[3] * R[3]; W[4] = R[1] * R[2] + R[3] * R[4];
-      W[5] = R[2] * R[2] + R[4] * R[4] + R[5] * R[5];
-      ws.m[3 * k] = mk[0]; ws.m[3 * k + 1] = mk[1]; ws.m[3 * k + 2] = mk[2];
-    }
-  });
-  tm.single([&] {
-    int mask = 0;
-    for (int k = 0; k < NFUS; ++k) mask |= ws.msd[k] ? (1 << k) : 0;
-    ws.scal[PF_MASK] = mask;
-    if (tr.height_prev < 0.0) {  // PRI:699-702
-      tr.height_prev = height;
+  // root / neck / height of every detection (PRI:631-668), first-observation initialisation (PRI:699-702)
+  tm.pfor(G, [&](int g) {
+    PriorFitScal& sc = ws.sc[g];
+    sc.active = 0; sc.lm = 0; sc.need_lin = 0; sc.fail = 0; sc.accept = 0; sc.use_marginals = 0;
+    sc.mask = 0u; sc.had = 0u; sc.iterations = 0; sc.trials = 0;
+    if (slot[g] < 0) return;
+    const PriorRootNeck rn = prior_root_neck(pt, persons[g]);
+    for (int a = 0; a < 3; ++a) { sc.root[a] = rn.root[a]; sc.neck[a] = rn.neck[a]; }
+    sc.root_score = rn.root_score; sc.neck_score = rn.neck_score; sc.height = rn.height;
+    PriorTrack& tr = tracks[slot[g]];
+    if (tr.height_prev < 0.0) {
+      tr.height_prev = rn.height;
       tr.root_prev[0] = rn.root[0]; tr.root_prev[1] = rn.root[1]; tr.root_prev[2] = rn.root[2];
     }
+    sc.height_prev = tr.height_prev;
+    for (int a = 0; a < 3; ++a) sc.root_prev[a] = tr.root_prev[a];
+    sc.had = tr.exists;
+    sc.active = 1;   // provisional: cleared below when the detection has no usable joint
   });
-  const uint32_t mask = (uint32_t)ws.scal[PF_MASK];
-  if (mask == 0) return false;
+
+  // measurements and their information matrices (PRI:658-737)
+  tm.pfor(G * NFUS, [&](int i) {
+    const int g = i / NFUS, k = i % NFUS;
+    const PriorFitScal& sc = ws.sc[g];
+    bool ms = false;
+    double c[6], mk[3] = {0.0, 0.0, 0.0};
+    if (sc.active) {
+      const ses3d_person_cov& person = persons[g];
+      const double height = sc.height;
+      if (k == SES3D_FBP_MIDHIP) {
+        if (sc.root_score > q.min_score) {
+          ms = true;
+          if (simple) {
+            const double* a = person.keypoints[SES3D_FBP_LHIP].cov;
+            const double* b = person.keypoints[SES3D_FBP_RHIP].cov;
+            for (int j = 0; j < 6; ++j) c[j] = (a[j] + b[j]) / 2.0;
+          } else {
+            for (int j = 0; j < 6; ++j) c[j] = person.keypoints[SES3D_FBP_MIDHIP].cov[j];
+          }
+          for (int j = 0; j < 6; ++j) c[j] = c[j] / (height * height) / (q.root_sigma_factor * q.root_sigma_factor);
+        }
+      } else {
+        const ses3d_keypoint_cov& kp = person.keypoints[k];
+        if (kp.score > q.min_score) {
+          ms = true;
+          for (int j = 0; j < 6; ++j) c[j] = kp.cov[j] / (height * height);
+          mk[0] = (kp.x - sc.root[0]) / height; mk[1] = (kp.y - sc.root[1]) / height; mk[2] = (kp.z - sc.root[2]) / height;
+        }
+        if (k == SES3D_FBP_NECK && simple && sc.neck_score > q.min_score) {
+          ms = true;
+          const double* a = person.keypoints[SES3D_FBP_LSHOULDER].cov;
+          const double* b = person.keypoints[SES3D_FBP_RSHOULDER].cov;
+          for (int j = 0; j < 6; ++j) c[j] = (a[j] + b[j]) / 2.0 / (height * height);
+          for (int j = 0; j < 3; ++j) mk[j] = (sc.neck[j] - sc.root[j]) / height;
+        }
+      }
+    }
+    ws.msd[i] = ms ? 1 : 0;
+    if (ms) {
+      prior_information(c, ws.W + 6 * i);
+      ws.m[3 * i] = mk[0]; ws.m[3 * i + 1] = mk[1]; ws.m[3 * i + 2] = mk[2];
+    }
+  });
+  tm.pfor(G, [&](int g) {
+    PriorFitScal& sc = ws.sc[g];
+    uint32_t mask = 0;
+    for (int k = 0; k < NFUS; ++k) mask |= ws.msd[g * NFUS + k] ? (1u << k) : 0u;
+    sc.mask = mask;
+    if (mask == 0u) sc.active = 0;   // num_meas == 0: continue (PRI:739-741)
+  });
 
   // setInitialState (PRI:483-503) + bone parents (addBinaryFactors PRI:384-481)
-  const uint32_t had = tr.exists;
-  const double height_prev = tr.height_prev;
-  const double root_prev[3] = {tr.root_prev[0], tr.root_prev[1], tr.root_prev[2]};
-  tm.pfor(NFUS, [&](int k) {
-    const bool ex = (had >> k) & 1u, ms = (mask >> k) & 1u;
+  tm.pfor(G * NFUS, [&](int i) {
+    const int g = i / NFUS, k = i % NFUS;
+    const PriorFitScal& sc = ws.sc[g];
+    ws.usev[i] = 0;
+    ws.par[i] = -1;
+    if (!sc.active) return;
+    PriorTrack& tr = tracks[slot[g]];
+    const bool ex = (sc.had >> k) & 1u, ms = (sc.mask >> k) & 1u;
     if (ex && !ms)
       for (int b = 0; b < PRIOR_NAVG; ++b) tr.vel[k][b][0] = tr.vel[k][b][1] = tr.vel[k][b][2] = 0.0;
-    ws.usev[k] = (ex && ms) ? 1 : 0;
-    int par = -1;
-    if (ms) {
-      for (int i = 0; i < 3; ++i) {
-        const double v = ex ? tr.prev[k][i] : ws.m[3 * k + i];
-        ws.x[3 * k + i] = v;
-        ws.pa[3 * k + i] = v * height_prev + root_prev[i];   // previous absolute position (velocity, PRI:820-821)
-      }
-      par = prior_static_parent(k);
-      if (k == SES3D_FBP_NECK && !((mask >> SES3D_FBP_BELLY) & 1u)) par = SES3D_FBP_MIDHIP;
-      if (par >= 0 && !((mask >> par) & 1u)) par = -1;
-    }
-    ws.par[k] = (int8_t)par;
+    if (!ms) return;
+    ws.usev[i] = ex ? 1 : 0;
+    for (int a = 0; a < 3; ++a) ws.x[3 * i + a] = ex ? tr.prev[k][a] : ws.m[3 * i + a];
+    int par = pt.st->parent[k];
+    if (k == SES3D_FBP_NECK && !((sc.mask >> SES3D_FBP_BELLY) & 1u)) par = SES3D_FBP_MIDHIP;
+    if (par >= 0 && !((sc.mask >> par) & 1u)) par = -1;
+    ws.par[i] = (int8_t)par;
   });
 
-  // LevenbergMarquardtOptimizer(graph, prevEstimate).optimize(), default parameters
-  double error = tm.sum(NFUS, [&](int k) { return prior_joint_error(pt, ws, ws.x, k); });
-  double lambda = q.lm_lambda_initial;
-  int iterations = 0;
-  if (error > 0.0 && iterations < q.lm_max_iterations) {
-    for (int guard = 0; guard < 4 * q.lm_max_iterations + 64; ++guard) {
-      const double current_error = error;
-      prior_linearize(tm, pt, ws);
-      const double old_lin = prior_linear_error(tm, ws, true);
-      for (;;) {  // tryLambda until it reports "stop"
-        bool step_ok = false, stop_searching = false;
-        double new_error = DBL_MAX;
-        prior_eliminate(tm, ws, lambda);
-        if (!ws.scal[PF_FAIL]) {
-          prior_backsubstitute(tm, ws);
-          const double new_lin = prior_linear_error(tm, ws, false);
-          const double lin_change = old_lin - new_lin;
-          if (lin_change >= 0) {
-            tm.pfor(NFUS * 3, [&](int i) { if (ws.msd[i / 3]) ws.xn[i] = ws.x[i] + ws.dl[i]; });
-            new_error = tm.sum(NFUS, [&](int k) { return prior_joint_error(pt, ws, ws.xn, k); });
-            const double cost_change = error - new_error;
-            if (lin_change > 1e-20) step_ok = (cost_change / lin_change) > q.lm_min_model_fidelity;
-            if (fabs(cost_change) < q.lm_relative_error_tol * error) stop_searching = true;
-          }
-        }
-        tm.sync();
-        if (step_ok) {
-          tm.pfor(NFUS * 3, [&](int i) { if (ws.msd[i / 3]) ws.x[i] = ws.xn[i]; });
-          error = new_error;
-          lambda = lambda / q.lm_lambda_factor;
-          if (lambda < 0.0) lambda = 0.0;
-          ++iterations;
-          break;
-        } else if (!stop_searching) {
-          lambda *= q.lm_lambda_factor;
-          if (lambda >= q.lm_lambda_upper_bound) break;
-        } else {
-          break;
-        }
-      }
-      bool converged;
-      if (error <= 0.0) converged = true;
-      else {
-        const double abs_dec = current_error - error;
-        const double rel_dec = abs_dec / current_error;
-        converged = (q.lm_relative_error_tol != 0.0 && rel_dec <= q.lm_relative_error_tol) ||
-                    abs_dec <= q.lm_absolute_error_tol;
-      }
-      if (!(iterations < q.lm_max_iterations && !converged && current_error < DBL_MAX && current_error == current_error))
-        break;
+  // LevenbergMarquardtOptimizer(graph, prevEstimate).optimize(), default parameters, all detections in lock step
+  tm.pfor(G * NFUS, [&](int i) {   // graph.error(initial)
+    const int g = i / NFUS, k = i % NFUS;
+    if (!ws.sc[g].active || !ws.msd[i]) return;
+    const double* x = ws.x + 3 * i;
+    const double d[3] = {x[0] - ws.m[3 * i], x[1] - ws.m[3 * i + 1], x[2] - ws.m[3 * i + 2]};
+    double wd[3];
+    sym6_mul(ws.W + 6 * i, d, wd);
+    double err = 0.5 * (d[0] * wd[0] + d[1] * wd[1] + d[2] * wd[2]);
+    const int p = ws.par[i];
+    if (p >= 0) {
+      const double e = prior_bone_residual(pt, k, p, x, ws.x + 3 * (g * NFUS + p), nullptr);
+      err += 0.5 * (e * e);
     }
+    ws.ta[i] = err;
+  });
+  tm.pfor(G, [&](int g) {
+    PriorFitScal& sc = ws.sc[g];
+    if (!sc.active) return;
+    sc.error = prior_sum_terms(ws, ws.ta, g);
+    sc.lambda = q.lm_lambda_initial;
+    sc.lm = (sc.error > 0.0 && q.lm_max_iterations > 0) ? 1 : 0;   // errorTol = 0, maxIterations
+    sc.need_lin = 1;
+  });
+  const int trial_cap = 4 * q.lm_max_iterations + 64;
+  for (int round = 0; round < trial_cap; ++round) {
+    if (tm.first(G, [&](int g) { return ws.sc[g].lm != 0; }) == G) break;
+    prior_linearize(tm, pt, G, ws, 0);
+    tm.pfor(G, [&](int g) {
+      PriorFitScal& sc = ws.sc[g];
+      sc.fail = 0;
+      if (!sc.lm || !sc.need_lin) return;
+      sc.old_lin = prior_sum_terms(ws, ws.ta, g);   // linear.error(0)
+      sc.cur_error = sc.error;                      // currentError = error(); iterate();
+      sc.need_lin = 0;
+    });
+    prior_eliminate(tm, pt, G, ws, false);
+    prior_backsubstitute(tm, pt, G, ws);
+    tm.pfor(G * NFUS, [&](int i) {   // linear.error(delta) and graph.error(x + delta), joint by joint
+      const int g = i / NFUS, k = i % NFUS;
+      const PriorFitScal& sc = ws.sc[g];
+      if (!sc.lm || sc.fail || !ws.msd[i]) return;
+      const double* x = ws.x + 3 * i;
+      const double* dl = ws.dl + 3 * i;
+      const double xn[3] = {x[0] + dl[0], x[1] + dl[1], x[2] + dl[2]};
+      const double d[3] = {xn[0] - ws.m[3 * i], xn[1] - ws.m[3 * i + 1], xn[2] - ws.m[3 * i + 2]};
+      double wd[3];
+      sym6_mul(ws.W + 6 * i, d, wd);
+      const double unary = 0.5 * (d[0] * wd[0] + d[1] * wd[1] + d[2] * wd[2]);   // linear in x: same in both errors
+      double lin = unary, nonlin = unary;
+      const int p = ws.par[i];
+      if (p >= 0) {
+        const int ip = g * NFUS + p;
+        const double* xp = ws.x + 3 * ip;
+        const double* dp = ws.dl + 3 * ip;
+        const double* w = ws.w + 3 * i;
+        const double el = ws.e[i] + w[0] * (dl[0] - dp[0]) + w[1] * (dl[1] - dp[1]) + w[2] * (dl[2] - dp[2]);
+        lin += 0.5 * (el * el);
+        const double xpn[3] = {xp[0] + dp[0], xp[1] + dp[1], xp[2] + dp[2]};
+        const double en = prior_bone_residual(pt, k, p, xn, xpn, nullptr);
+        nonlin += 0.5 * (en * en);
+      }
+      ws.ta[i] = lin;
+      ws.tb[i] = nonlin;
+    });
+    tm.pfor(G, [&](int g) {   // tryLambda() + the outer loop's convergence test, per detection
+      PriorFitScal& sc = ws.sc[g];
+      sc.accept = 0;
+      if (!sc.lm) return;
+      bool step_ok = false, stop_searching = false;
+      double new_error = DBL_MAX;
+      if (!sc.fail) {
+        const double new_lin = prior_sum_terms(ws, ws.ta, g);
+        const double lin_change = sc.old_lin - new_lin;
+        if (lin_change >= 0) {
+          new_error = prior_sum_terms(ws, ws.tb, g);
+          const double cost_change = sc.error - new_error;
+          if (lin_change > 1e-20) step_ok = (cost_change / lin_change) > q.lm_min_model_fidelity;
+          if (fabs(cost_change) < q.lm_relative_error_tol * sc.error) stop_searching = true;
+        }
+      }
+      bool end_iterate = true;
+      if (step_ok) {
+        sc.accept = 1;
+        sc.error = new_error;
+        sc.lambda = sc.lambda / q.lm_lambda_factor;
+        if (sc.lambda < 0.0) sc.lambda = 0.0;
+        ++sc.iterations;
+      } else if (!stop_searching) {
+        sc.lambda *= q.lm_lambda_factor;
+        end_iterate = sc.lambda >= q.lm_lambda_upper_bound;
+      }
+      if (end_iterate) {
+        bool converged;
+        if (sc.error <= 0.0) converged = true;
+        else {
+          const double abs_dec = sc.cur_error - sc.error;
+          const double rel_dec = abs_dec / sc.cur_error;
+          converged = (q.lm_relative_error_tol != 0.0 && rel_dec <= q.lm_relative_error_tol) ||
+                      abs_dec <= q.lm_absolute_error_tol;
+        }
+        const bool finite = sc.cur_error < DBL_MAX && sc.cur_error == sc.cur_error;
+        if (sc.iterations < q.lm_max_iterations && !converged && finite) sc.need_lin = 1;
+        else sc.lm = 0;
+      }
+      if (++sc.trials >= trial_cap) sc.lm = 0;
+    });
+    tm.pfor(G * NFUS, [&](int i) {
+      if (!ws.sc[i / NFUS].accept || !ws.msd[i]) return;
+      for (int a = 0; a < 3; ++a) ws.x[3 * i + a] += ws.dl[3 * i + a];
+    });
   }
 
   // Marginals(graph, result) (PRI:760-767)
-  prior_linearize(tm, pt, ws);
-  prior_eliminate(tm, ws, 0.0);
-  const bool use_marginals = !ws.scal[PF_FAIL];
-  if (use_marginals) prior_marginals(tm, ws);
+  tm.pfor(G, [&](int g) { ws.sc[g].fail = 0; ws.sc[g].lm = 0; });
+  prior_linearize(tm, pt, G, ws, 1);
+  prior_eliminate(tm, pt, G, ws, true);
+  tm.pfor(G, [&](int g) { ws.sc[g].use_marginals = (ws.sc[g].active && !ws.sc[g].fail) ? 1 : 0; });
+  prior_marginals(tm, pt, G, ws);
 
   // outputs (PRI:770-837) and the track update (PRI:839-843)
-  if (fused) {
-    double* fz = reinterpret_cast<double*>(fused);
-    double* pz = reinterpret_cast<double*>(pred);
-    tm.pfor((int)(sizeof(ses3d_person_cov) / 8), [&](int i) { fz[i] = 0.0; pz[i] = 0.0; });
-  }
+  const int rec_words = (int)(sizeof(ses3d_person_cov) / 8);
+  tm.pfor(G * rec_words, [&](int i) {
+    const int g = i / rec_words;
+    if (!ws.sc[g].active || out_idx[g] < 0) return;
+    reinterpret_cast<double*>(fused + out_idx[g])[i % rec_words] = 0.0;
+    reinterpret_cast<double*>(pred + out_idx[g])[i % rec_words] = 0.0;
+  });
   const double dtg = t - t_prev_global;
   const int vslot = frame_nr % PRIOR_NAVG;
-  tm.pfor(NFUS, [&](int k) {
-    if (!((mask >> k) & 1u)) return;
+  tm.pfor(G * NFUS, [&](int i) {
+    const int g = i / NFUS, k = i % NFUS;
+    const PriorFitScal& sc = ws.sc[g];
+    if (!sc.active || !ws.msd[i]) return;
+    PriorTrack& tr = tracks[slot[g]];
+    const double height = sc.height;
     double jf[3], jp[3];
-    for (int i = 0; i < 3; ++i) jf[i] = ws.x[3 * k + i] * height + rn.root[i];
-    for (int i = 0; i < 3; ++i) jp[i] = jf[i];
-    if (ws.usev[k]) {
-      for (int i = 0; i < 3; ++i) tr.vel[k][vslot][i] = (jf[i] - ws.pa[3 * k + i]) / dtg;
-      for (int i = 0; i < 3; ++i) {
+    for (int a = 0; a < 3; ++a) jf[a] = ws.x[3 * i + a] * height + sc.root[a];
+    for (int a = 0; a < 3; ++a) jp[a] = jf[a];
+    if (ws.usev[i]) {
+      for (int a = 0; a < 3; ++a)
+        tr.vel[k][vslot][a] = (jf[a] - (tr.prev[k][a] * sc.height_prev + sc.root_prev[a])) / dtg;
+      for (int a = 0; a < 3; ++a) {
         double acc = 0.0;
-        for (int b = 0; b < PRIOR_NAVG; ++b) acc += tr.vel[k][b][i];
-        jp[i] += acc / PRIOR_NAVG * pred_delta_t;
+        for (int b = 0; b < PRIOR_NAVG; ++b) acc += tr.vel[k][b][a];
+        jp[a] += acc / PRIOR_NAVG * pred_delta_t;
       }
     }
-    for (int i = 0; i < 3; ++i) tr.prev[k][i] = ws.x[3 * k + i];
-    if (!fused) return;
+    for (int a = 0; a < 3; ++a) tr.prev[k][a] = ws.x[3 * i + a];
+    const int oi = out_idx[g];
+    if (oi < 0) return;
     float score;
-    if (k == SES3D_FBP_MIDHIP) score = rn.root_score;
-    else if (k == SES3D_FBP_NECK) score = rn.neck_score;
-    else score = person.keypoints[k].score;
+    if (k == SES3D_FBP_MIDHIP) score = sc.root_score;
+    else if (k == SES3D_FBP_NECK) score = sc.neck_score;
+    else score = persons[g].keypoints[k].score;
     if (!(score > q.min_score)) score = q.min_score;   // std::max(g_min_score, score)
     double cv[6];
-    if (use_marginals) {
-      for (int i = 0; i < 6; ++i) cv[i] = ws.Sg[6 * k + i] * height * height;
+    if (sc.use_marginals) {
+      for (int a = 0; a < 6; ++a) cv[a] = ws.guy[6 * i + a] * height * height;
     } else {
       const double d = q.default_res_sigma * q.default_res_sigma;
       cv[0] = d; cv[1] = 0; cv[2] = 0; cv[3] = d; cv[4] = 0; cv[5] = d;
     }
     if (k == SES3D_FBP_MIDHIP)
-      for (int i = 0; i < 6; ++i) cv[i] *= (q.root_sigma_factor * q.root_sigma_factor);
-    ses3d_keypoint_cov& o = fused->keypoints[k];
+      for (int a = 0; a < 6; ++a) cv[a] *= (q.root_sigma_factor * q.root_sigma_factor);
+    ses3d_keypoint_cov& o = fused[oi].keypoints[k];
     o.x = jf[0]; o.y = jf[1]; o.z = jf[2]; o.score = score;
-    for (int i = 0; i < 6; ++i) o.cov[i] = cv[i];
-    ses3d_keypoint_cov& po = pred->keypoints[k];
+    for (int a = 0; a < 6; ++a) o.cov[a] = cv[a];
+    ses3d_keypoint_cov& po = pred[oi].keypoints[k];
     po.x = jp[0]; po.y = jp[1]; po.z = jp[2]; po.score = score;
     const double pn = q.pred_noise_sigma * q.pred_noise_sigma;
     po.cov[0] = cv[0] + pn; po.cov[1] = cv[1]; po.cov[2] = cv[2]; po.cov[3] = cv[3] + pn; po.cov[4] = cv[4];
     po.cov[5] = cv[5] + pn;
   });
-  tm.single([&] {
+  tm.pfor(G, [&](int g) {
+    const PriorFitScal& sc = ws.sc[g];
+    if (!sc.active) return;
+    PriorTrack& tr = tracks[slot[g]];
     tr.t_prev = t;
-    tr.exists = mask;
-    tr.height_prev = height;
-    tr.root_prev[0] = rn.root[0]; tr.root_prev[1] = rn.root[1]; tr.root_prev[2] = rn.root[2];
+    tr.exists = sc.mask;
+    tr.height_prev = sc.height;
+    tr.root_prev[0] = sc.root[0]; tr.root_prev[1] = sc.root[1]; tr.root_prev[2] = sc.root[2];
     ++tr.num_obs;
-    if (fused) { fused->id = (uint32_t)tr.id; pred->id = (uint32_t)tr.id; }
+    if (out_idx[g] >= 0) { fused[out_idx[g]].id = (uint32_t)tr.id; pred[out_idx[g]].id = (uint32_t)tr.id; }
   });
-  return true;
 }
 
 // remove_old_tracks (PRI:191-211): compact the order list, free the slots. Leader only.
@@ -689,9 +785,10 @@ SES_HD void prior_remove_old(const PriorTables& pt, PriorSeqState* st, const Pri
 }
 
 // One message of one stream: skeletonCallback PRI:505-921. tm = the stream's team (CTA / serial).
-// persons [n_det], fused / pred [h_max]; fit_ws = base of the per-warp fit workspaces (fit_ws_stride bytes apart).
+// persons [n_det], fused / pred [h_max]; fit_ws = base of the per-warp fit workspaces (fit_ws_stride bytes apart,
+// each sized for `group` detections fitted together).
 template <class Team>
-SES_HD void prior_frame(Team& tm, const PriorTables& pt, int max_tracks, int h_max, PriorSeqState* st,
+SES_HD void prior_frame(Team& tm, const PriorTables& pt, int max_tracks, int h_max, int group, PriorSeqState* st,
                         PriorTrack* tracks, uint8_t* order, const PriorWs& ws, unsigned char* fit_ws, size_t fit_ws_stride,
                         int64_t stamp_ns, int n_cams, const float* fb_delay, int n_det_in,
                         const ses3d_person_cov* persons, ses3d_person_cov* fused, ses3d_person_cov* pred,
@@ -787,17 +884,17 @@ SES_HD void prior_frame(Team& tm, const PriorTables& pt, int max_tracks, int h_m
   const double t_prev_global = st->t_prev;
   const int frame_nr = st->frame_nr;
 
-  // the skeleton fits: one warp per detection (PRI:587-853)
-  tm.per_warp(n_det, [&](auto& w, int p) {
-    const int s = ws.slot[p];
-    if (s < 0) return;
+  // the skeleton fits: one warp per group of up to `group` detections (PRI:587-853)
+  const int n_groups = (n_det + group - 1) / group;
+  tm.per_warp(n_groups, [&](auto& w, int gi) {
     const int wid = w.size() == 1 ? 0 : (tm.rank() / 32);   // serial build: one workspace
     Arena ar(fit_ws + (size_t)wid * fit_ws_stride);
     PriorFitWs fws;
-    prior_fit_ws_layout(ar, &fws);
-    const int oi = ws.out_idx[p];
-    prior_fit_person(w, pt, persons[p], tracks[s], t, t_prev_global, frame_nr, pred_delta_t, fws,
-                     oi >= 0 ? fused + oi : nullptr, oi >= 0 ? pred + oi : nullptr);
+    prior_fit_ws_layout(ar, group, &fws);
+    const int p0 = gi * group;
+    const int G = n_det - p0 < group ? n_det - p0 : group;
+    prior_fit_group(w, pt, G, persons + p0, tracks, ws.slot + p0, ws.out_idx + p0, fused, pred, t, t_prev_global,
+                    frame_nr, pred_delta_t, fws);
   });
 
   // track life cycle: prune, then merge close tracks (PRI:866-903)

@@ -70,8 +70,12 @@ struct Scene {          // per-frame people: root (x, y) and yaw (cos, sin)
 #define SES3D_SYNTH_MAX_PEOPLE 64
 
 // Place n_people roots with >= min_separation by rejection sampling (at most 64 attempts each).
-SES_HD void make_scene(const ses3d_synth_config& cfg, uint64_t frame, Scene& sc) {
+SES_HD void make_scene(const ses3d_synth_config& cfg, uint64_t frame_in, Scene& sc) {
   const uint32_t k0 = (uint32_t)cfg.seed, k1 = (uint32_t)(cfg.seed >> 32);
+  // sequence mode: the scene is drawn once per sequence and then moves (people walk along their heading)
+  const uint64_t T = cfg.frames_per_sequence > 0 ? (uint64_t)cfg.frames_per_sequence : 0;
+  const uint64_t frame = T ? frame_in / T : frame_in;
+  const float walked = T ? cfg.step_m * (float)(frame_in % T) : 0.0f;
   const uint32_t f0 = (uint32_t)frame, f1 = (uint32_t)(frame >> 32);
   const float sep2 = cfg.min_separation * cfg.min_separation;
   for (int p = 0; p < cfg.n_people; ++p) {
@@ -92,6 +96,8 @@ SES_HD void make_scene(const ses3d_synth_config& cfg, uint64_t frame, Scene& sc)
     }
     sc.x[p] = px; sc.y[p] = py; sc.c[p] = pc; sc.s[p] = ps;
   }
+  if (T)
+    for (int p = 0; p < cfg.n_people; ++p) { sc.x[p] += sc.c[p] * walked; sc.y[p] += sc.s[p] * walked; }
 }
 
 SES_HD void world_joint(const Scene& sc, int p, int k, double X[3]) {

@@ -62,7 +62,7 @@ class AssocDump(C.Structure):
 class SynthConfig(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("n_people", C.c_int32), ("p_max", C.c_int32), ("dropout", C.c_float),
                 ("noise_px", C.c_float), ("area", C.c_float * 4), ("min_separation", C.c_float),
-                ("min_visible", C.c_int32)]
+                ("min_visible", C.c_int32), ("frames_per_sequence", C.c_int32), ("step_m", C.c_float)]
 
 
 def make_cameras(T_cam_base, fx=1000.0, fy=1000.0, cx=640.0, cy=360.0, Tx=0.0, Ty=0.0, width=1280, height=720):

@@ -61,32 +61,41 @@ def synth_person_sequences(n_sequences, n_frames, n_people, seed=0, h_max=None, 
     drop = rng.random((S, P, T, 17)) < joint_dropout
     present = rng.random((S, P, T)) >= person_dropout
 
+    # all records [S][T][P], then per message: shuffle, drop absent people, pad to h_max
+    full = np.zeros((S, T, P), person_cov_dtype)
+    keep = np.transpose(~drop, (0, 2, 1, 3))                                  # [S][T][P][17]
+    Xt = np.transpose(X, (0, 2, 1, 3, 4))
+    ct = np.transpose(cov, (0, 2, 1, 3, 4, 5))
+    sc = np.transpose(score, (0, 2, 1, 3)) * keep
+    kp = full["keypoints"]
+    for name, axis in (("x", 0), ("y", 1), ("z", 2)):
+        v = np.zeros((S, T, P, 21))
+        v[..., fus] = Xt[..., axis] * keep
+        kp[name] = v
+    v = np.zeros((S, T, P, 21), np.float32)
+    v[..., fus] = sc
+    kp["score"] = v
+    c6 = np.stack([ct[..., 0, 0], ct[..., 0, 1], ct[..., 0, 2], ct[..., 1, 1], ct[..., 1, 2], ct[..., 2, 2]], -1)
+    v = np.zeros((S, T, P, 21, 6))
+    v[..., fus, :] = c6 * keep[..., None]
+    kp["cov"] = v
+    full["keypoints"] = kp
+    full["score"] = (sc.sum(-1) / np.maximum(keep.sum(-1), 1)).astype(np.float32)
+    rank = np.argsort(rng.random((S, T, P)), axis=-1) if shuffle else np.broadcast_to(np.arange(P), (S, T, P))
+    pres = np.transpose(present, (0, 2, 1))                                   # [S][T][P]
+    key = ~np.take_along_axis(pres, rank, -1)
+    # position list: people in `rank` order, absent ones last
+    pos = np.take_along_axis(rank, np.argsort(key, axis=-1, kind="stable"), -1)
+    n_persons = np.minimum(pres.sum(-1), h_max).astype(np.int32)
+    take = min(P, h_max)
     persons = np.zeros((S, T, h_max), person_cov_dtype)
-    n_persons = np.zeros((S, T), np.int32)
+    persons[:, :, :take] = np.take_along_axis(full, pos[:, :, :take], axis=2)
+    live = np.arange(h_max)[None, None, :] < n_persons[:, :, None]
+    persons[~live] = np.zeros((), person_cov_dtype)
     gt = np.full((S, T, h_max), -1, np.int32)
-    order = np.argsort(rng.random((S, T, P)), axis=-1) if shuffle else np.broadcast_to(np.arange(P), (S, T, P))
-    for si in range(S):
-        for ti in range(T):
-            n = 0
-            for p in order[si, ti]:
-                if not present[si, p, ti] or n >= h_max:
-                    continue
-                rec = persons[si, ti, n]
-                kp = rec["keypoints"]
-                keep = ~drop[si, p, ti]
-                slots = fus[keep]
-                kp["x"][slots] = X[si, p, ti, keep, 0]
-                kp["y"][slots] = X[si, p, ti, keep, 1]
-                kp["z"][slots] = X[si, p, ti, keep, 2]
-                kp["score"][slots] = score[si, p, ti, keep]
-                cm = cov[si, p, ti, keep]
-                kp["cov"][slots] = np.stack([cm[:, 0, 0], cm[:, 0, 1], cm[:, 0, 2], cm[:, 1, 1], cm[:, 1, 2],
-                                             cm[:, 2, 2]], -1)
-                rec["score"] = score[si, p, ti, keep].mean() if keep.any() else 0.0
-                rec["id"] = n
-                gt[si, ti, n] = p
-                n += 1
-            n_persons[si, ti] = n
+    gt[:, :, :take] = pos[:, :, :take]
+    gt[~live] = -1
+    persons["id"] = np.where(live, np.arange(h_max)[None, None, :], 0)
     t = t0_s + np.arange(T) * dt + rng.normal(0, jitter_s, (S, T))
     t = np.maximum.accumulate(t, axis=1)
     stamp_ns = np.round(t * 1e9).astype(np.int64)

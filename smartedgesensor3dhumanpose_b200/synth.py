@@ -8,9 +8,11 @@ from .layouts import SynthConfig, camera_dtype, person2d_dtype
 
 
 def synth_config(seed, n_people, p_max=None, dropout=0.0, noise_px=2.0, area=(-2, -2, 2, 2), min_separation=0.6,
-                 min_visible=5):
+                 min_visible=5, frames_per_sequence=0, step_m=1.0 / 30.0):
+    """frames_per_sequence = T > 0: frames [qT, (q+1)T) are one scene whose people walk step_m per frame."""
     return SynthConfig(seed, n_people, p_max if p_max is not None else n_people, dropout, noise_px,
-                       (C.c_float * 4)(*[float(a) for a in area]), min_separation, min_visible)
+                       (C.c_float * 4)(*[float(a) for a in area]), min_separation, min_visible, frames_per_sequence,
+                       step_m)
 
 
 def synth_frames(cameras, cfg: SynthConfig, n_frames, first_frame=0, want_gt=True):

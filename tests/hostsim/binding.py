@@ -27,7 +27,7 @@ def lib():
         L.hostsim_prior_create.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
         L.hostsim_prior_destroy.argtypes = [C.c_void_p]
         L.hostsim_prior_run.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 3 + [C.c_int32] + \
-            [C.c_void_p] * 6
+            [C.c_void_p] * 6 + [C.c_int32]
         L.hostsim_prior_get_tracks.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
@@ -84,10 +84,11 @@ class HostSim:
 class PriorHostSim:
     """prior_core.h (the device algorithm of ses3d_prior_run) instantiated with the serial team."""
 
-    def __init__(self, params=None, n_sequences=1, max_tracks=32):
+    def __init__(self, params=None, n_sequences=1, max_tracks=32, group=6):
         from smartedgesensor3dhumanpose_b200.layouts import default_prior_params
         self.params = params if params is not None else default_prior_params()
         self.max_tracks = max_tracks
+        self.group = group   # detections fitted together by one warp on the GPU
         self._h = lib().hostsim_prior_create(C.byref(self.params), n_sequences, max_tracks)
 
     def __del__(self):
@@ -110,7 +111,7 @@ class PriorHostSim:
         pred_delay = np.zeros((S, T), np.float32)
         track_of = np.full((S, T, H), -1, np.int32)
         rc = lib().hostsim_prior_run(self._h, S, T, H, _p(persons), _p(n_persons), _p(stamp_ns), n_cams, _p(fb_delay),
-                                     _p(fused), _p(pred), _p(n_out), _p(pred_delay), _p(track_of))
+                                     _p(fused), _p(pred), _p(n_out), _p(pred_delay), _p(track_of), self.group)
         if rc != 0:
             raise RuntimeError(f"hostsim_prior_run -> {rc}")
         return dict(fused=fused, pred=pred, n_out=n_out, pred_delay=pred_delay, track_of=track_of)

@@ -133,6 +133,7 @@ void* hostsim_prior_create(const ses3d_prior_params* prm, int32_t n_sequences, i
   PriorSim* s = new PriorSim;
   s->pt.prm = *prm;
   s->pt.limb_sigma_factor = prm->normalize_by_height ? 2.0 : 1.0;
+  s->pt.st = &prior_static_host();
   s->n_seq = n_sequences;
   s->max_tracks = max_tracks;
   s->states.resize(n_sequences);
@@ -147,10 +148,10 @@ void hostsim_prior_destroy(void* h) { delete static_cast<PriorSim*>(h); }
 int hostsim_prior_run(void* h, int32_t n_sequences, int32_t n_frames, int32_t h_max, const ses3d_person_cov* persons,
                       const int32_t* n_persons, const int64_t* stamp_ns, int32_t n_cams, const float* fb_delay,
                       ses3d_person_cov* fused, ses3d_person_cov* pred, int32_t* n_out, float* pred_delay,
-                      int32_t* track_of) {
+                      int32_t* track_of, int32_t group) {
   PriorSim* s = static_cast<PriorSim*>(h);
   if (n_sequences > s->n_seq) return SES3D_E_INVALID;
-  std::vector<unsigned char> wsb(prior_ws_bytes(h_max, s->max_tracks) + 64), fitb(prior_fit_ws_bytes() + 64);
+  std::vector<unsigned char> wsb(prior_ws_bytes(h_max, s->max_tracks) + 64), fitb(prior_fit_ws_bytes(group) + 64);
   SerialTeam tm;
   int rc = 0;
   for (int q = 0; q < n_sequences; ++q) {
@@ -159,7 +160,7 @@ int hostsim_prior_run(void* h, int32_t n_sequences, int32_t n_frames, int32_t h_
       Arena ar(wsb.data());
       PriorWs ws;
       prior_ws_layout(ar, h_max, s->max_tracks, &ws);
-      prior_frame(tm, s->pt, s->max_tracks, h_max, &s->states[q], s->tracks.data() + (size_t)q * s->max_tracks,
+      prior_frame(tm, s->pt, s->max_tracks, h_max, group, &s->states[q], s->tracks.data() + (size_t)q * s->max_tracks,
                   s->order.data() + (size_t)q * s->max_tracks, ws, fitb.data(), 0, stamp_ns[i], n_cams,
                   fb_delay ? fb_delay + i * n_cams : nullptr, n_persons[i], persons + i * h_max, fused + i * h_max,
                   pred + i * h_max, n_out + i, pred_delay ? pred_delay + i : nullptr,

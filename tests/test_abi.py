@@ -33,7 +33,7 @@ def test_pod_layouts_match_person_msgs():
     assert layouts.person_cov_dtype.itemsize == 1768      # 8 + 21*80 + 56 + 24
     assert layouts.person_cov_dtype.fields["keypoints"][1] == 8
     assert layouts.person2d_dtype.fields["bbox"][1] == 412
-    assert C.sizeof(layouts.Params) == 64 and C.sizeof(layouts.SynthConfig) == 48
+    assert C.sizeof(layouts.Params) == 64 and C.sizeof(layouts.SynthConfig) == 56
     assert layouts.KP2FUSION_SIMPLE == (0, 16, 15, 18, 17, 5, 2, 6, 3, 7, 4, 12, 9, 13, 10, 14, 11)   # S3D:139-142
     assert layouts.KP2FUSION_H36M == (0, 19, 1, 20, 8, 5, 2, 6, 3, 7, 4, 12, 9, 13, 10, 14, 11)       # S3D:143-145
 

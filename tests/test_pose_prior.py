@@ -152,6 +152,17 @@ def test_device_algorithm_matches_oracle(kw):
     assert ro["n_out"].sum() > 0
 
 
+@pytest.mark.parametrize("group", [1, 2, 4])
+def test_group_size_does_not_change_results(group):
+    """On the GPU one warp fits up to `group` detections in lock step; the grouping must not matter."""
+    seq = synth_person_sequences(2, 25, 7, seed=9, joint_dropout=0.2, h_max=10)
+    prm = default_prior_params(min_num_obs_track=0)
+    a = PriorHostSim(prm, 2, group=6).run(seq["persons"], seq["n_persons"], seq["stamp_ns"], seq["fb_delay"])
+    b = PriorHostSim(prm, 2, group=group).run(seq["persons"], seq["n_persons"], seq["stamp_ns"], seq["fb_delay"])
+    for key in ("fused", "pred", "n_out", "track_of"):
+        assert a[key].tobytes() == b[key].tobytes(), key
+
+
 def test_streaming_equals_batch():
     """State persists across calls: one message per call == all messages in one call (device algorithm)."""
     seq = synth_person_sequences(2, 30, 3, seed=8)

@@ -66,11 +66,13 @@ cudaError_t launch_prior(const PriorTables& pt, int n_seq, int n_frames, int h_m
                          const int32_t* n_persons, const int64_t* stamp_ns, int n_cams, const float* fb_delay,
                          ses3d_person_cov* fused, ses3d_person_cov* pred, int32_t* n_out, float* pred_delay,
                          int32_t* track_of, cudaStream_t st) {
-  // One warp fits a group of up to `group` detections together (prior_core.h); a message with more detections is
-  // spread over the CTA's warps. Defaults measured on B200 (2048 streams x 6 people).
-  int group = std::max(1, std::min(PRIOR_GMAX, h_max));
+  // One warp fits a group of up to `group` detections together (prior_core.h); the groups of a message are spread
+  // over the CTA's warps. Measured on B200 (2048 streams x 32 messages x 6 people, ms per launch): group 6 / 1 warp
+  // 37.0, 6 / 2 37.1, 3 / 2 23.2, 3 / 4 23.2, 2 / 4 23.0, 1 / 4 27.0 - shared memory per CTA (occupancy) decides.
+  int group = std::max(1, std::min(3, h_max));
   if (const char* env = getenv("SES3D_PRIOR_GROUP")) group = std::max(1, std::min(PRIOR_GMAX, atoi(env)));
   int warps = std::max(1, std::min(4, (h_max + group - 1) / group));
+  if (const char* env = getenv("SES3D_PRIOR_WARPS")) warps = std::max(1, std::min(8, atoi(env)));
   const size_t ws_bytes = prior_ws_bytes(h_max, max_tracks);
   const size_t fit_bytes = prior_fit_ws_bytes(group);
   static_assert(sizeof(PriorStatic) % 4 == 0, "copied word by word");

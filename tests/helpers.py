@@ -71,3 +71,29 @@ def compare_persons2d(ref, got, px_tol=0.0):
     d = max(np.abs(ka["x"] - kb["x"]).max(initial=0), np.abs(ka["y"] - kb["y"]).max(initial=0))
     assert d <= px_tol, f"reprojected keypoints differ by {d} px"
     return dict(n_persons=int(live.sum()), max_px=float(d))
+
+
+def make_sequence_workload(rig, n_sequences, n_frames, n_people, seed=7, fps=30.0, step_m=1.0 / 30.0, **over):
+    """Temporally coherent 2-D detections (synthetic generator in sequence mode): frames [q T, (q+1) T) are stream q.
+    Returns the frame arrays plus the per-message stamps of the demo chain skeleton_3d -> pose_prior -> reprojection."""
+    cams = rigs.RIGS[rig]()
+    cfg = synth.synth_config(seed=seed, n_people=n_people, dropout=over.get("dropout", 0.0),
+                             noise_px=over.get("noise_px", 2.0), area=over.get("area", rigs.AREAS[rig]),
+                             frames_per_sequence=n_frames, step_m=step_m)
+    fr = synth.synth_frames(cams, cfg, n_sequences * n_frames)
+    fr["cameras"] = cams
+    fr["h_max"] = over.get("h_max", max(8, 2 * n_people + 4))
+    t = 1000.0 + np.arange(n_frames) / fps
+    fr["stamp_ns"] = np.broadcast_to(np.round(t * 1e9).astype(np.int64), (n_sequences, n_frames)).copy()
+    fr["n_sequences"], fr["n_frames_per_sequence"] = n_sequences, n_frames
+    return fr
+
+
+def run_demo_chain(tri, prior, fr):
+    """The demo wiring (pose_prior/launch/pose_triangulate_demo.launch): persons_3d -> pose_prior ->
+    persons3d_fused_pred -> pose_reprojection. tri needs triangulate_batch / reproject_batch, prior needs run."""
+    S, T, H = fr["n_sequences"], fr["n_frames_per_sequence"], fr["h_max"]
+    r3 = tri.triangulate_batch(fr["persons"], fr["n_persons"], H)
+    rp = prior.run(r3["persons3d"].reshape(S, T, H), r3["n_out"].reshape(S, T), fr["stamp_ns"], None)
+    r2 = tri.reproject_batch(rp["pred"].reshape(S * T, H), rp["n_out"].reshape(S * T))
+    return r3, rp, r2

@@ -1,0 +1,107 @@
+"""The whole demo chain of the reference (pose_prior/launch/pose_triangulate_demo.launch):
+2-D detections -> skeleton_3d -> pose_prior -> pose_reprojection (semantic feedback), on temporally coherent
+synthetic streams. CPU: the device algorithms (serial host instantiation) against the oracle chain, plus physical
+sanity of the result (tracks follow people, fused joints near the ground truth, the predicted skeletons re-project
+next to the next frame's detections)."""
+import numpy as np
+import pytest
+
+from oracle.binding import Oracle, PriorOracle
+from smartedgesensor3dhumanpose_b200.layouts import KP2FUSION_SIMPLE, default_prior_params
+from tests import helpers
+from tests.hostsim.binding import HostSim, PriorHostSim
+
+
+def _chain_pair(rig="ring8", S=3, T=26, P=3, **kw):
+    fr = helpers.make_sequence_workload(rig, S, T, P, **kw)
+    prm = default_prior_params()
+    ref = helpers.run_demo_chain(Oracle(fr["cameras"], ref_hungarian=True), PriorOracle(prm, S, ref_hungarian=True), fr)
+    dev = helpers.run_demo_chain(HostSim(fr["cameras"]), PriorHostSim(prm, S), fr)
+    return fr, ref, dev
+
+
+def check_chain_parity(fr, ref, dev, pos_tol=1e-3, px_tol=1.0):
+    (r3, rp, r2), (d3, dp, d2) = ref, dev
+    helpers.compare_persons3d(r3, d3, pos_tol)
+    assert np.array_equal(rp["n_out"], dp["n_out"]) and np.array_equal(rp["track_of"], dp["track_of"])
+    H = rp["fused"].shape[-1]
+    live = np.arange(H)[None, None, :] < rp["n_out"][:, :, None]
+    for key in ("fused", "pred"):
+        a, b = rp[key][live], dp[key][live]
+        assert np.array_equal(a["id"], b["id"])
+        ka, kb = a["keypoints"], b["keypoints"]
+        assert np.array_equal(ka["score"] > 0, kb["score"] > 0)
+        d = max(np.abs(ka[c] - kb[c]).max(initial=0) for c in "xyz")
+        assert d <= pos_tol, f"{key} joints differ by {d} m"
+    helpers.compare_persons2d(r2, d2, px_tol=px_tol)
+    assert rp["n_out"].sum() > 0 and r2["n_out"].sum() > 0
+
+
+def check_chain_physics(fr, res):
+    r3, rp, r2 = res
+    S, T, H = fr["n_sequences"], fr["n_frames_per_sequence"], fr["h_max"]
+    gt = fr["gt_joints"].reshape(S, T, -1, 17, 3)
+    fus = np.array(KP2FUSION_SIMPLE)
+    # every published fused skeleton lies on one ground-truth person (< 6 cm mean joint error) and a track id
+    # sticks to that person for the whole stream
+    owner = {}
+    n_checked = 0
+    for s in range(S):
+        for t in range(T):
+            for i in range(rp["n_out"][s, t]):
+                kp = rp["fused"][s, t, i]["keypoints"]
+                ok = kp["score"][fus] > 0
+                X = np.stack([kp["x"][fus], kp["y"][fus], kp["z"][fus]], -1)
+                err = np.linalg.norm(X[None] - gt[s, t], axis=-1)[:, ok].mean(axis=1)
+                p = int(err.argmin())
+                assert err[p] < 0.06, f"fused skeleton {err[p]:.3f} m from the nearest person"
+                key = (s, int(rp["fused"][s, t, i]["id"]))
+                assert owner.setdefault(key, p) == p, "track id switched person"
+                n_checked += 1
+    assert n_checked > S * (T - 11)
+    # semantic feedback: the predicted skeleton of message t, re-projected, lies near the detections of message t + 3
+    # (prediction horizon 0.1 s = 3 frames at 30 Hz) - within a few pixels of noise, closer than the unpredicted one
+    C = len(fr["cameras"])
+    det = fr["persons"].reshape(S, T, C, -1)
+    ndet = fr["n_persons"].reshape(S, T, C)
+    rep = r2["persons2d"].reshape(S, T, C, -1)
+    nrep = r2["n_out"].reshape(S, T, C)
+    dists = []
+    for s in range(S):
+        for t in range(12, T - 3):
+            for c in range(C):
+                for i in range(nrep[s, t, c]):
+                    a = rep[s, t, c, i]["keypoints"]
+                    best = np.inf
+                    for j in range(ndet[s, t + 3, c]):
+                        b = det[s, t + 3, c, j]["keypoints"]
+                        both = (a["score"] > 0) & (b["score"] >= 0.5)
+                        if both.sum() >= 8:
+                            best = min(best, np.hypot(a["x"] - b["x"], a["y"] - b["y"])[both].mean())
+                    if np.isfinite(best):
+                        dists.append(best)
+    assert len(dists) > 20 and np.median(dists) < 8.0, f"median feedback error {np.median(dists):.1f} px"
+
+
+def test_demo_chain_device_algorithms_match_oracle():
+    fr, ref, dev = _chain_pair()
+    check_chain_parity(fr, ref, dev)
+
+
+def test_demo_chain_physics():
+    fr = helpers.make_sequence_workload("ring8", 2, 30, 3)
+    res = helpers.run_demo_chain(Oracle(fr["cameras"], ref_hungarian=True),
+                                 PriorOracle(default_prior_params(), 2, ref_hungarian=True), fr)
+    check_chain_physics(fr, res)
+
+
+def test_sequence_mode_generator():
+    """Sequence mode: one scene per stream, people walk step_m per frame along their heading; frame noise independent."""
+    fr = helpers.make_sequence_workload("ring8", 2, 10, 3)
+    g = fr["gt_joints"].reshape(2, 10, 3, 17, 3)
+    step = np.linalg.norm(np.diff(g[:, :, :, 0, :2], axis=1), axis=-1)
+    assert np.allclose(step, 1.0 / 30.0, atol=1e-5)
+    assert np.abs(g[0, 0] - g[1, 0]).max() > 0.1            # different scenes per stream
+    assert np.allclose(np.diff(g[..., 2], axis=1), 0)       # heights unchanged
+    plain = helpers.make_workload("cfg5_ring8x4", 4)          # frames_per_sequence = 0 keeps the old behaviour
+    assert plain["gt_joints"].shape == (4, 4, 17, 3)

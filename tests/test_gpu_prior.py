@@ -107,3 +107,17 @@ def test_prior_capacity_error():
     with pytest.raises(Ses3dError) as e:
         g.run(seq["persons"], seq["n_persons"], seq["stamp_ns"], None)
     assert e.value.code == -3
+
+
+def test_demo_chain_on_gpu():
+    """2-D detections -> skeleton_3d -> pose_prior -> pose_reprojection through the C ABI against the oracle chain."""
+    from oracle.binding import Oracle
+    from tests import helpers
+    from tests.test_demo_chain import check_chain_parity, check_chain_physics
+    S, T = 6, 28
+    fr = helpers.make_sequence_workload("hall16", S, T, 4)
+    prm = default_prior_params()
+    ref = helpers.run_demo_chain(Oracle(fr["cameras"], ref_hungarian=True), PriorOracle(prm, S, ref_hungarian=True), fr)
+    dev = helpers.run_demo_chain(api.GeometryPipeline(fr["cameras"]), api.PriorTracker(prm, S), fr)
+    check_chain_parity(fr, ref, dev)
+    check_chain_physics(fr, dev)

@@ -151,7 +151,14 @@ n_mean = float((seq["persons"]["keypoints"]["score"] > 0.1).sum() / max(n_fits, 
 trials = (cpu["lm_stats"]["lm_inner"] / max(cpu["lm_stats"]["fits"], 1)) if cpu else 4.5
 flops_fit = n_mean * (trials * 266.0 + 300.0)
 fp64_peak = 148 * 64 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12   # 64 FP64 FMA lanes / SM / clk (B200), TFLOP/s
-bytes_fit = 3 * 1684.0                                         # PersonCov in, fused + pred out (wire size)
+bytes_fit = 1684.0 * (1.0 + 2.0 * n_pub / max(n_fits, 1))      # PersonCov in; fused + pred out for published tracks (wire size)
+traffic = None
+tp = ROOT / "profiles" / "ncu_traffic.json"
+if tp.exists():
+    ent = json.loads(tp.read_text()).get("pose_prior", {}).get("k_prior")
+    if ent and ent["frames_per_launch"] == S * T:
+        traffic = {"dram_bytes_per_launch": ent["dram_bytes_read"] + ent["dram_bytes_write"],
+                   "algorithmic_bytes_per_launch": n_fits * bytes_fit, "source": ent["source"]}
 out = {
     "metric": "skeleton_fits_per_sec", "value": n_fits / (ms * 1e-3), "unit": "fits/s", "n_gpus": 1, "steps": a.steps,
     "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "dtype": "f64", "data": "synthetic",
@@ -168,7 +175,7 @@ out = {
                  "hbm": {"achieved": n_fits * bytes_fit / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": n_fits * bytes_fit / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                          "algorithmic_bytes_per_fit": bytes_fit},
-                 "traffic": None},
+                 "traffic": traffic},
     "clocks": clk.summary(),
     "e2e": {"value": n_fits / (e2e_ms * 1e-3), "unit": "fits/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": d2h, "call": "ses3d_prior_run, pinned host buffers"},

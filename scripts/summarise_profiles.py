@@ -71,6 +71,10 @@ if summ:
     traffic = {workload: {k: {"dram_bytes_read": to_bytes(v["dram__bytes_read.sum"]), "dram_bytes_write": to_bytes(v["dram__bytes_write.sum"]),
                               "frames_per_launch": frames, "source": f"profiles/{tag}_ncu_full_summary.json"}
                           for k, v in summ.items() if "dram__bytes_read.sum" in v}}
+    if "k_prior" in traffic[workload]:   # captured with scripts/bench_prior.py --profile-only (2048 streams x 32 messages)
+        kp = traffic[workload].pop("k_prior")
+        kp["frames_per_launch"] = 2048 * 32
+        traffic["pose_prior"] = {"k_prior": kp}
     (P / "ncu_traffic.json").write_text(json.dumps(traffic, indent=1))
 for name in (f"bench_{tag}.json", f"bench_{tag}_reference.json", f"bench_{tag}_dense.json", f"configs_{tag}.json"):
     if (G / name).exists():

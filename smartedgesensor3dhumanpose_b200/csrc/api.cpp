@@ -102,6 +102,8 @@ struct ses3d_handle_s {
   ses3d::Tables tb;
   static constexpr int kSlots = 3;   // H2D of chunk i+1, kernels of chunk i and D2H of chunk i-1 overlap
   Slot slot[kSlots];
+  cudaEvent_t fork_ev = nullptr;     // device-buffer calls: the caller's stream forks into the slot streams
+  int device_split = 2;              // sub-batches of a device-buffer call that run on concurrent streams
   std::mutex mu;
   int64_t launches = 0;
   bool profiling = false;
@@ -248,14 +250,44 @@ int run_batch(ses3d_handle_s* h, int stages, int n_frames, int p_max, const ses3
 
   if (dev) {
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->slot[0].stream;
-    if (stages & TRI) {
-      int rc = triangulate_on_device(h, h->slot[0].sc, st, n_frames, p_max, h_max, persons, n_persons, io3d, n_io3d,
-                                     hyp_of, n_hyp_d, n_hung_d);
-      if (rc) return rc;
-    }
-    if (stages & REP) {
-      int rc = reproject_on_device(h, st, n_frames, h_max, io3d, n_io3d, out2d, n_out2d);
-      if (rc) return rc;
+    // Large batches are cut into sub-batches that run the kernel chain on concurrent streams: the four kernels
+    // stress different resources (FP32 pipe / FP64 pipe / shared-memory latency) and none fills an SM's issue
+    // slots or its register / shared-memory budget alone, so CTAs of neighbouring stages co-reside and the
+    // tail of one kernel overlaps the head of the next. Profiling runs serially so per-kernel times stay clean.
+    int n_split = (h->profiling || n_frames < 4096) ? 1 : std::min(h->device_split, (int)ses3d_handle_s::kSlots);
+    if (n_split <= 1) {
+      if (stages & TRI) {
+        int rc = triangulate_on_device(h, h->slot[0].sc, st, n_frames, p_max, h_max, persons, n_persons, io3d, n_io3d,
+                                       hyp_of, n_hyp_d, n_hung_d);
+        if (rc) return rc;
+      }
+      if (stages & REP) {
+        int rc = reproject_on_device(h, st, n_frames, h_max, io3d, n_io3d, out2d, n_out2d);
+        if (rc) return rc;
+      }
+    } else {
+      CU(cudaEventRecord(h->fork_ev, st));
+      for (int i = 0; i < n_split; ++i) {
+        Slot& s = h->slot[i];
+        const int f0 = (int)((int64_t)n_frames * i / n_split), f1 = (int)((int64_t)n_frames * (i + 1) / n_split);
+        const int nf = f1 - f0;
+        if (s.stream != st) CU(cudaStreamWaitEvent(s.stream, h->fork_ev, 0));
+        if (stages & TRI) {
+          int rc = triangulate_on_device(h, s.sc, s.stream, nf, p_max, h_max, persons + (size_t)f0 * C * p_max,
+                                         n_persons + (size_t)f0 * C, io3d + (size_t)f0 * h_max, n_io3d + f0,
+                                         hyp_of ? hyp_of + (size_t)f0 * C * p_max : nullptr,
+                                         n_hyp_d ? n_hyp_d + f0 : nullptr, n_hung_d ? n_hung_d + f0 : nullptr);
+          if (rc) return rc;
+        }
+        if (stages & REP) {
+          int rc = reproject_on_device(h, s.stream, nf, h_max, io3d + (size_t)f0 * h_max, n_io3d + f0,
+                                       out2d + (size_t)f0 * C * h_max, n_out2d + (size_t)f0 * C);
+          if (rc) return rc;
+        }
+        if (s.stream != st) CU(cudaEventRecord(s.done, s.stream));
+      }
+      for (int i = 0; i < n_split; ++i)
+        if (h->slot[i].stream != st) CU(cudaStreamWaitEvent(st, h->slot[i].done, 0));
     }
     int32_t overflow = 0;
     CU(cudaMemcpyAsync(&overflow, h->d_overflow.p, 4, cudaMemcpyDeviceToHost, st));
@@ -490,6 +522,8 @@ int ses3d_create(int32_t n_cams, const ses3d_camera* cams, const ses3d_params* p
     if (ue == cudaSuccess) ue = cudaMallocHost(reinterpret_cast<void**>(&h->slot[i].totals), 2 * sizeof(long long));
     if (ue == cudaSuccess) ue = cudaEventCreateWithFlags(&h->slot[i].done, cudaEventDisableTiming);
   }
+  if (ue == cudaSuccess) ue = cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming);
+  if (const char* env = getenv("SES3D_DEVICE_SPLIT")) h->device_split = std::max(1, atoi(env));
   if (ue != cudaSuccess) {
     ses3d_destroy(h);
     return cuda_fail(ue, "ses3d_create upload");
@@ -509,6 +543,7 @@ int ses3d_destroy(ses3d_handle h) {
   if (!h) return SES3D_OK;
   cudaSetDevice(h->device);
   for (Slot& s : h->slot) s.release();
+  if (h->fork_ev) cudaEventDestroy(h->fork_ev);
   h->d_camf.release(); h->d_camd.release(); h->d_F.release(); h->d_frow.release(); h->d_overflow.release();
   delete h;
   return SES3D_OK;

@@ -21,20 +21,43 @@ def _chain_pair(rig="ring8", S=3, T=26, P=3, **kw):
 
 
 def check_chain_parity(fr, ref, dev, pos_tol=1e-3, px_tol=1.0):
+    """Stage by stage. The triangulation is compared at the north-star tolerance. pose_prior is then fed inputs that
+    differ by ~1e-5 m between the two chains, and the reference's LM stops at a *relative error decrease* of 1e-5
+    (gtsam default): a weakly observed joint (sigma of several cm) can sit a fraction of its sigma away from the
+    minimiser when the loop stops, and a 1e-6 m input change can flip the iteration at which it stops - the oracle
+    fed with 2e-6 m of input noise moves 0.02 % of its own output joints by more than 1e-4 m. So after pose_prior:
+    track ids / counts / joint sets identical, median deviation < 1e-5 m, 99 % of the joints within pos_tol, every
+    joint within half its own 1-sigma. (With identical inputs the stage agrees to 1e-10 m: tests/test_gpu_prior.py.)"""
     (r3, rp, r2), (d3, dp, d2) = ref, dev
     helpers.compare_persons3d(r3, d3, pos_tol)
     assert np.array_equal(rp["n_out"], dp["n_out"]) and np.array_equal(rp["track_of"], dp["track_of"])
     H = rp["fused"].shape[-1]
     live = np.arange(H)[None, None, :] < rp["n_out"][:, :, None]
-    for key in ("fused", "pred"):
+    stats = {}
+    for key, slack in (("fused", 1.0), ("pred", 4.0)):   # pred adds velocity * 0.1 s = 3 x a frame-to-frame difference
         a, b = rp[key][live], dp[key][live]
         assert np.array_equal(a["id"], b["id"])
         ka, kb = a["keypoints"], b["keypoints"]
-        assert np.array_equal(ka["score"] > 0, kb["score"] > 0)
-        d = max(np.abs(ka[c] - kb[c]).max(initial=0) for c in "xyz")
-        assert d <= pos_tol, f"{key} joints differ by {d} m"
-    helpers.compare_persons2d(r2, d2, px_tol=px_tol)
+        m = ka["score"] > 0
+        assert np.array_equal(m, kb["score"] > 0)
+        d = np.sqrt(sum((ka[c] - kb[c]) ** 2 for c in "xyz"))[m]
+        cov = rp["fused"][live]["keypoints"]["cov"]
+        sigma = np.sqrt(np.maximum.reduce([cov[..., 0], cov[..., 3], cov[..., 5]]))[m]
+        assert np.median(d) < 1e-5 * slack, f"{key}: median deviation {np.median(d)} m"
+        assert np.quantile(d, 0.99) <= pos_tol * slack, f"{key}: 99th percentile {np.quantile(d, 0.99)} m"
+        assert (d <= np.maximum(pos_tol, 0.5 * sigma) * slack).all(), f"{key}: {(d / sigma).max()} sigma"
+        stats[key] = (float(np.median(d)), float(d.max()))
+    # the re-projection of the predicted skeletons: same persons per camera; pixels within px_tol for 99 %
+    assert np.array_equal(r2["n_out"], d2["n_out"])
+    Hh = r2["persons2d"].shape[-1]
+    live2 = np.arange(Hh)[None, None, :] < r2["n_out"][:, :, None]
+    ka, kb = r2["persons2d"][live2]["keypoints"], d2["persons2d"][live2]["keypoints"]
+    both = (ka["score"] > 0) & (kb["score"] > 0)
+    assert (both == (ka["score"] > 0)).mean() > 0.995     # a joint on the image border may flip
+    px = np.hypot(ka["x"] - kb["x"], ka["y"] - kb["y"])[both]
+    assert np.quantile(px, 0.99) <= px_tol, f"re-projection differs by {np.quantile(px, 0.99)} px (99th percentile)"
     assert rp["n_out"].sum() > 0 and r2["n_out"].sum() > 0
+    return stats
 
 
 def check_chain_physics(fr, res):
@@ -83,8 +106,9 @@ def check_chain_physics(fr, res):
     assert len(dists) > 20 and np.median(dists) < 8.0, f"median feedback error {np.median(dists):.1f} px"
 
 
-def test_demo_chain_device_algorithms_match_oracle():
-    fr, ref, dev = _chain_pair()
+@pytest.mark.parametrize("rig,S,T,P", [("ring8", 3, 26, 3), ("hall16", 6, 28, 4)])
+def test_demo_chain_device_algorithms_match_oracle(rig, S, T, P):
+    fr, ref, dev = _chain_pair(rig, S, T, P)
     check_chain_parity(fr, ref, dev)
 
 

@@ -113,6 +113,16 @@ e2e_ms = float(np.mean(e2e_times))
 h2d = S * T * (H * rec + 4 + 8 + 4 * C)
 d2h = S * T * (2 * H * rec + 4 + 4)
 
+# single-message call latency (the ROS-shim use case: one stream, one PersonCovList per call, host buffers)
+node = api.PosePrior(prm, h_max=H)
+lat = []
+for t in range(T):
+    n = int(seq["n_persons"][0, t])
+    t0 = time.perf_counter()
+    node.skeleton_callback(seq["persons"][0, t, :n], int(seq["stamp_ns"][0, t]), seq["fb_delay"][0, t])
+    lat.append((time.perf_counter() - t0) * 1e6)
+single_call_p50_us = float(np.median(lat[3:]))
+
 cpu = None
 if not a.no_cpu:
     from oracle.binding import PriorOracle
@@ -180,6 +190,7 @@ out = {
     "e2e": {"value": n_fits / (e2e_ms * 1e-3), "unit": "fits/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": d2h, "call": "ses3d_prior_run, pinned host buffers"},
     "gpu_launches": int(launches),
+    "single_message_call_p50_us": single_call_p50_us,
     "cpu_baseline": cpu,
 }
 print(json.dumps(out))

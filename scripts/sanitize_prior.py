@@ -1,0 +1,25 @@
+#!/usr/bin/env python
+"""Small pose_prior run for compute-sanitizer (memcheck / racecheck / initcheck / synccheck):
+    compute-sanitizer --tool racecheck python scripts/sanitize_prior.py
+Covers track creation / pruning / merging, drop-outs, more detections than one fit group, both pose methods."""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+from smartedgesensor3dhumanpose_b200 import api  # noqa: E402
+from smartedgesensor3dhumanpose_b200.layouts import default_prior_params  # noqa: E402
+from smartedgesensor3dhumanpose_b200.sequences import synth_person_sequences  # noqa: E402
+
+for pm, nh, people in [(0, 0, 7), (1, 1, 3)]:
+    seq = synth_person_sequences(3, 14, people, seed=41 + pm, joint_dropout=0.2, person_dropout=0.15, pose_method=pm,
+                                 h_max=10)
+    seq["stamp_ns"][2, 8:] += int(3e9)          # a gap: tracks of stream 2 are pruned and re-created
+    trk = api.PriorTracker(default_prior_params(pose_method=pm, normalize_by_height=nh, min_num_obs_track=2), 3)
+    r = trk.run(seq["persons"], seq["n_persons"], seq["stamp_ns"], seq["fb_delay"])
+    print("pose_method", pm, "published", int(r["n_out"].sum()), "tracks", [len(trk.tracks(s)[0]) for s in range(3)])
+    trk.close()
+print("sanitize prior done")

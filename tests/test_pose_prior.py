@@ -276,3 +276,27 @@ def test_reset_and_capacity():
     hs = PriorHostSim(default_prior_params(), 1, max_tracks=2)
     with pytest.raises(RuntimeError):                                # three people do not fit two track slots
         hs.run(seq["persons"], seq["n_persons"], seq["stamp_ns"], None)
+
+
+@pytest.mark.parametrize("impl", ["oracle", "hostsim"])
+def test_degenerate_inputs_terminate(impl):
+    """NaN joints, zero / non-SPD covariances and coincident joints (zero bone length: division by zero in the range
+    factor) must neither hang nor crash; detections that are fine in the same message are fitted as usual."""
+    seq = synth_person_sequences(1, 6, 3, seed=12, joint_dropout=0.0, person_dropout=0.0, shuffle=False)
+    P = seq["persons"].copy()
+    if impl == "hostsim":   # a NaN joint poisons the cost matrix: the reference's Munkres (and the oracle's) may never
+        P["keypoints"]["x"][0, 2, 0, 5] = np.nan   # return on it; the device algorithm bounds every loop
+    P["keypoints"]["cov"][0, 3, 0, 6] = 0.0                        # zero covariance
+    P["keypoints"]["cov"][0, 4, 0, 7] = [1e-4, 2e-4, 0, 1e-4, 0, 1e-4]   # not positive definite
+    for c in "xyz":
+        P["keypoints"][c][0, 5, 0, 3] = P["keypoints"][c][0, 5, 0, 2]   # elbow on top of the shoulder
+    prm = default_prior_params(min_num_obs_track=0)
+    m = PriorOracle(prm, 1) if impl == "oracle" else PriorHostSim(prm, 1)
+    r = m.run(P, seq["n_persons"], seq["stamp_ns"], None)
+    assert (r["n_out"] == 3).all()
+    # the untouched person 2 is unaffected by its neighbours' degenerate data
+    clean = (PriorOracle(prm, 1) if impl == "oracle" else PriorHostSim(prm, 1)).run(
+        seq["persons"], seq["n_persons"], seq["stamp_ns"], None)
+    for t in range(6):
+        a, b = r["fused"][0, t, 2]["keypoints"], clean["fused"][0, t, 2]["keypoints"]
+        assert np.array_equal(a["x"], b["x"]) and np.array_equal(a["cov"], b["cov"])

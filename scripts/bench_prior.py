@@ -3,6 +3,10 @@
 messages, P people each.
 
     python scripts/bench_prior.py [--sequences 2048 --frames 32 --people 6 --steps 10 --warmup 3] [--profile-only]
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 scripts/bench_prior.py   (weak scaling)
+
+Streams are independent node instances, so rank g of N owns its own 2048 streams (different seeds) and the data
+path has no collective; the timed region is bracketed by a barrier and the maximum over ranks is reported.
 
 Prints one JSON line in the same spirit as bench.py: `value` = skeleton fits (detections fused) per second with the
 inputs resident in HBM, CUDA events on the launching stream; `e2e` = the same through ses3d_prior_run with pinned
@@ -40,11 +44,27 @@ ap.add_argument("--profile-only", action="store_true", help="device-resident ste
 ap.add_argument("--no-cpu", action="store_true")
 a = ap.parse_args()
 
+rank = int(os.environ.get("RANK", "0"))
+local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+world = int(os.environ.get("WORLD_SIZE", "1"))
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+torch.cuda.set_device(local_rank)
+
+
+def barrier():
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+
+
 S, T, P = a.sequences, a.frames, a.people
-seq = synth_person_sequences(S, T, P, seed=31)
+seq = synth_person_sequences(S, T, P, seed=31 + rank)
 H, C = seq["h_max"], seq["n_cams"]
 prm = default_prior_params()
-dev = torch.device("cuda:0")
+dev = torch.device(f"cuda:{local_rank}")
 rec = person_cov_dtype.itemsize
 n_fits = int(seq["n_persons"].sum())
 
@@ -54,7 +74,7 @@ d_fused = torch.zeros(S * T * H * rec, dtype=torch.uint8, device=dev)
 d_pred = torch.zeros_like(d_fused)
 d_nout = torch.zeros(S * T, dtype=torch.int32, device=dev)
 d_delay = torch.zeros(S * T, dtype=torch.float32, device=dev)
-trk = api.PriorTracker(prm, S)
+trk = api.PriorTracker(prm, S, device=local_rank)
 torch.cuda.set_stream(torch.cuda.Stream())     # a real stream: 0 would select the handle's own stream, unseen by torch events
 stream = torch.cuda.current_stream().cuda_stream
 
@@ -78,43 +98,60 @@ for _ in range(a.warmup):
 torch.cuda.synchronize()
 l0 = trk.launch_count
 times = []
-with ClockSampler(0) as clk:
+with ClockSampler(local_rank) as clk:
     time.sleep(0.6)
     for _ in range(a.steps):
         trk.reset()     # not timed: the reference's reset(), outside the per-message path
-        torch.cuda.synchronize()
+        barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         device_step()
         e1.record()
-        torch.cuda.synchronize()
+        barrier()
         times.append(e0.elapsed_time(e1))
     time.sleep(0.3)
 launches = trk.launch_count - l0 - a.steps   # minus the reset launches
 kernel_ms = trk.last_kernel_ms()
 ms = float(np.mean(times))
 n_pub = int(d_nout.sum().item())
+n_fits_all = n_fits
+if world > 1:   # device time = max over ranks; work = sum over ranks
+    tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt.item())
+    nn = torch.tensor([n_fits], device=dev, dtype=torch.int64)
+    dist.all_reduce(nn)
+    n_fits_all = int(nn.item())
 
 # e2e through the host-buffer call
 pin = lambda x: torch.from_numpy(np.ascontiguousarray(x).view(np.uint8).reshape(-1)).pin_memory().numpy()
 hp = pin(seq["persons"]).view(person_cov_dtype).reshape(S, T, H)
 outb = dict(fused=pin(np.zeros((S, T, H), person_cov_dtype)).view(person_cov_dtype).reshape(S, T, H),
             pred=pin(np.zeros((S, T, H), person_cov_dtype)).view(person_cov_dtype).reshape(S, T, H))
-trk2 = api.PriorTracker(prm, S)
+trk2 = api.PriorTracker(prm, S, device=local_rank)
 e2e_times = []
 for i in range(2 + min(a.steps, 5)):
     trk2.reset()
+    barrier()
     t0 = time.perf_counter()
     r = trk2.run(hp, seq["n_persons"], seq["stamp_ns"], seq["fb_delay"], want_track_of=False, out=outb)
+    barrier()
     dt = time.perf_counter() - t0
     if i >= 2:
         e2e_times.append(dt * 1e3)
 e2e_ms = float(np.mean(e2e_times))
+if world > 1:
+    tt = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e_ms = float(tt.item())
+    if rank != 0:
+        dist.destroy_process_group()
+        sys.exit(0)
 h2d = S * T * (H * rec + 4 + 8 + 4 * C)
 d2h = S * T * (2 * H * rec + 4 + 4)
 
 # single-message call latency (the ROS-shim use case: one stream, one PersonCovList per call, host buffers)
-node = api.PosePrior(prm, h_max=H)
+node = api.PosePrior(prm, device=local_rank, h_max=H)
 lat = []
 for t in range(T):
     n = int(seq["n_persons"][0, t])
@@ -124,7 +161,7 @@ for t in range(T):
 single_call_p50_us = float(np.median(lat[3:]))
 
 cpu = None
-if not a.no_cpu:
+if not a.no_cpu and world == 1:
     from oracle.binding import PriorOracle
     ref = (ROOT / "oracle" / "_ref" / "libref_hungarian.so").exists()
     cs = min(S, a.cpu_sequences)
@@ -170,11 +207,12 @@ if tp.exists():
         traffic = {"dram_bytes_per_launch": ent["dram_bytes_read"] + ent["dram_bytes_write"],
                    "algorithmic_bytes_per_launch": n_fits * bytes_fit, "source": ent["source"]}
 out = {
-    "metric": "skeleton_fits_per_sec", "value": n_fits / (ms * 1e-3), "unit": "fits/s", "n_gpus": 1, "steps": a.steps,
-    "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "dtype": "f64", "data": "synthetic",
-    "frames_per_sec": S * T / (ms * 1e-3),
+    "metric": "skeleton_fits_per_sec", "value": n_fits_all / (ms * 1e-3), "unit": "fits/s", "n_gpus": world,
+    "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+    "dtype": "f64", "data": "synthetic", "frames_per_sec": S * T * world / (ms * 1e-3),
     "config": {"workload": "pose_prior", "streams": S, "messages_per_stream": T, "people": P, "h_max": H,
-               "fits_per_step": n_fits, "published_per_step": n_pub,
+               "fits_per_step_per_gpu": n_fits, "published_per_step_per_gpu": n_pub,
+               "sharding": "streams across ranks (independent trackers), no collective",
                "l2_policy": f"inputs larger than L2 ({S * T * H * rec / 2**20:.0f} MiB in, {2 * S * T * H * rec / 2**20:.0f} MiB out per step)"},
     "roofline": {"bound": "fp64", "kernel": "k_prior", "achieved": n_fits * flops_fit / (ms * 1e-3) / 1e12,
                  "peak": fp64_peak, "unit": "TFLOP/s", "frac": n_fits * flops_fit / (ms * 1e-3) / 1e12 / fp64_peak,
@@ -187,10 +225,13 @@ out = {
                          "algorithmic_bytes_per_fit": bytes_fit},
                  "traffic": traffic},
     "clocks": clk.summary(),
-    "e2e": {"value": n_fits / (e2e_ms * 1e-3), "unit": "fits/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+    "e2e": {"value": n_fits_all / (e2e_ms * 1e-3), "unit": "fits/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": d2h, "call": "ses3d_prior_run, pinned host buffers"},
     "gpu_launches": int(launches),
     "single_message_call_p50_us": single_call_p50_us,
     "cpu_baseline": cpu,
 }
 print(json.dumps(out))
+
+if world > 1:
+    dist.destroy_process_group()

@@ -74,3 +74,50 @@ def test_compact_torch_matches_numpy():
     raw = torch.from_numpy(p3.view(np.uint8).reshape(-1).copy())
     got = sharding.compact_torch(raw, p3.shape[0], p3.shape[1]).numpy()
     assert np.array_equal(got, sharding.compact_numpy(p3, r["n_out"]))
+
+
+# ---- pose_prior: message streams sharded across ranks (independent trackers), final gather of the fused skeletons
+N_STREAMS, N_MSG = 5, 14   # ragged split: 2 + 3 streams
+
+
+def _prior_worker(rank, world, port, q):
+    from smartedgesensor3dhumanpose_b200.layouts import default_prior_params
+    from smartedgesensor3dhumanpose_b200.sequences import synth_person_sequences
+    from tests.hostsim.binding import PriorHostSim
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = sharding.shard_range(N_STREAMS, rank, world)
+    seq = synth_person_sequences(N_STREAMS, N_MSG, 3, seed=51)          # every rank cuts its streams out of the same set
+    prm = default_prior_params(min_num_obs_track=2)
+    r = PriorHostSim(prm, hi - lo).run(seq["persons"][lo:hi], seq["n_persons"][lo:hi], seq["stamp_ns"][lo:hi],
+                                       seq["fb_delay"][lo:hi])
+    H = r["fused"].shape[-1]
+    compact = torch.from_numpy(sharding.compact_numpy(r["fused"].reshape(-1, H), r["n_out"].reshape(-1)))
+    parts = sharding.gather_compact(compact, dst=0)
+    if rank == 0:
+        q.put(torch.cat(parts).numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharded_prior_streams_equal_single_process():
+    from smartedgesensor3dhumanpose_b200.layouts import default_prior_params
+    from smartedgesensor3dhumanpose_b200.sequences import synth_person_sequences
+    from tests.hostsim.binding import PriorHostSim
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_prior_worker, args=(r, WORLD, port, q)) for r in range(WORLD)]
+    for p in procs:
+        p.start()
+    gathered = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    seq = synth_person_sequences(N_STREAMS, N_MSG, 3, seed=51)
+    r = PriorHostSim(default_prior_params(min_num_obs_track=2), N_STREAMS).run(seq["persons"], seq["n_persons"],
+                                                                               seq["stamp_ns"], seq["fb_delay"])
+    H = r["fused"].shape[-1]
+    want = sharding.compact_numpy(r["fused"].reshape(-1, H), r["n_out"].reshape(-1))
+    assert gathered.shape == want.shape and np.array_equal(gathered, want)
+    assert (want[..., 3] > 0).sum() > 100

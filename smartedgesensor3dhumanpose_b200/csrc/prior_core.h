@@ -117,7 +117,7 @@ struct PriorFitScal {           // LM / bookkeeping state of one detection of th
   float root_score, neck_score;
   uint32_t mask, had;           // measured joints; joints the track's prevEstimate held
   int32_t iterations, trials;
-  uint8_t active, lm, need_lin, fail, accept, use_marginals, pad_[2];
+  uint8_t active, lm, need_lin, fail, accept, use_marginals, fresh, pad_[1];
 };
 
 struct PriorFitWs {       // the factor graphs of one group, one workspace per warp; index i = g * 21 + joint
@@ -498,14 +498,15 @@ SES_HD void prior_fit_group(WT& tm, const PriorTables& pt, int G, const ses3d_pe
   // root / neck / height of every detection (PRI:631-668), first-observation initialisation (PRI:699-702)
   tm.pfor(G, [&](int g) {
     PriorFitScal& sc = ws.sc[g];
-    sc.active = 0; sc.lm = 0; sc.need_lin = 0; sc.fail = 0; sc.accept = 0; sc.use_marginals = 0;
+    sc.active = 0; sc.lm = 0; sc.need_lin = 0; sc.fail = 0; sc.accept = 0; sc.use_marginals = 0; sc.fresh = 0;
     sc.mask = 0u; sc.had = 0u; sc.iterations = 0; sc.trials = 0;
     if (slot[g] < 0) return;
     const PriorRootNeck rn = prior_root_neck(pt, persons[g]);
     for (int a = 0; a < 3; ++a) { sc.root[a] = rn.root[a]; sc.neck[a] = rn.neck[a]; }
     sc.root_score = rn.root_score; sc.neck_score = rn.neck_score; sc.height = rn.height;
     PriorTrack& tr = tracks[slot[g]];
-    if (tr.height_prev < 0.0) {
+    sc.fresh = tr.height_prev < 0.0 ? 1 : 0;   // first message of the track: its velocity buffer starts at zero
+    if (sc.fresh) {
       tr.height_prev = rn.height;
       tr.root_prev[0] = rn.root[0]; tr.root_prev[1] = rn.root[1]; tr.root_prev[2] = rn.root[2];
     }
@@ -572,11 +573,12 @@ SES_HD void prior_fit_group(WT& tm, const PriorTables& pt, int G, const ses3d_pe
     const PriorFitScal& sc = ws.sc[g];
     ws.usev[i] = 0;
     ws.par[i] = -1;
-    if (!sc.active) return;
+    if (slot[g] < 0) return;
     PriorTrack& tr = tracks[slot[g]];
     const bool ex = (sc.had >> k) & 1u, ms = (sc.mask >> k) & 1u;
-    if (ex && !ms)
+    if (sc.fresh || (sc.active && ex && !ms))   // TrackingHypothesis ctor (PRI:80) / setInitialState (PRI:492)
       for (int b = 0; b < PRIOR_NAVG; ++b) tr.vel[k][b][0] = tr.vel[k][b][1] = tr.vel[k][b][2] = 0.0;
+    if (!sc.active) return;
     if (!ms) return;
     ws.usev[i] = ex ? 1 : 0;
     for (int a = 0; a < 3; ++a) ws.x[3 * i + a] = ex ? tr.prev[k][a] : ws.m[3 * i + a];
@@ -795,27 +797,42 @@ SES_HD void prior_frame(Team& tm, const PriorTables& pt, int max_tracks, int h_m
                         int32_t* n_out, float* pred_delay, int32_t* track_of) {
   const ses3d_prior_params& q = pt.prm;
   const int n_det = n_det_in < 0 ? 0 : (n_det_in > h_max ? h_max : n_det_in);
-  tm.single([&] {
-    const double t = prior_stamp_to_sec(stamp_ns);
-    double curr = 0.0;  // PRI:513-526
+  // Four barrier-separated phases per message: (1) cost matrix in parallel, (2) everything serial about the
+  // tracker on the first warp, (3) the fits, (4) track life cycle on the first warp.
+  const double t = prior_stamp_to_sec(stamp_ns);   // pure function of the stamp: every thread evaluates it
+  const int n_trk = st->n_tracks;                   // unchanged until phase 2
+  const double t_prev_global = st->t_prev;          // unchanged until phase 4
+  const int frame_nr = st->frame_nr;
+
+  // ---- phase 1: association costs (PRI:554-559), one thread per (detection, track); the leader also does the
+  // feedback-delay moving average (PRI:513-526)
+  tm.pfor(n_det * n_trk + h_max + 1, [&](int e) {
+    if (e < n_det * n_trk) {
+      const int p = e % n_det, tr = e / n_det;
+      ws.cost[e] = prior_normed_dist(pt, tracks[order[tr]], persons[p], t);
+      return;
+    }
+    e -= n_det * n_trk;
+    if (e < h_max) {
+      if (track_of) track_of[e] = -1;
+      if (e < n_det) ws.has[e] = prior_has_measurement(pt, persons[e]) ? 1 : 0;
+      return;
+    }
+    double curr = 0.0;
     int n_valid = 0;
     for (int c = 0; c < n_cams; ++c) {
       const float d = fb_delay ? fb_delay[c] : -1.0f;
       if (d > 0.0f) { curr += (double)d; ++n_valid; }
     }
     if (n_valid > 0) curr /= n_valid; else curr = q.avg_delay;
-    st->delay_buf[st->frame_nr % PRIOR_NAVG] = curr;
+    st->delay_buf[frame_nr % PRIOR_NAVG] = curr;
     double acc = 0.0;
     for (int i = 0; i < PRIOR_NAVG; ++i) acc += st->delay_buf[i];
-    ws.dscal[PW_T] = t;
     ws.dscal[PW_PDT] = acc / PRIOR_NAVG;
     if (pred_delay) *pred_delay = (float)ws.dscal[PW_PDT];
-    ws.scal[PS_NTRK] = st->n_tracks;
     ws.scal[PS_NPUB] = 0;
   });
-  const double t = ws.dscal[PW_T], pred_delta_t = ws.dscal[PW_PDT];
-  const int n_trk = ws.scal[PS_NTRK];
-  if (track_of) tm.pfor(h_max, [&](int i) { track_of[i] = -1; });
+  const double pred_delta_t = ws.dscal[PW_PDT];
 
   if (n_det == 0) {  // PRI:537-546
     tm.single([&] {
@@ -826,65 +843,51 @@ SES_HD void prior_frame(Team& tm, const PriorTables& pt, int max_tracks, int h_m
     return;
   }
 
-  // association of detections to tracks (PRI:548-568)
-  if (n_trk > 0) {
-    tm.pfor(n_det * n_trk, [&](int e) {
-      const int p = e % n_det, tr = e / n_det;
-      ws.cost[e] = prior_normed_dist(pt, tracks[order[tr]], persons[p], t);
-    });
-    tm.warp0([&](auto& w) {
+  // ---- phase 2 (first warp): assignment (PRI:561-567), new tracks (PRI:570-580), publication slots (PRI:845-848)
+  tm.warp0([&](auto& w) {
+    if (n_trk > 0) {
       AssocWs aws;
       aws.dist = ws.dist; aws.star = ws.star; aws.prime = ws.prime; aws.nstar = ws.nstar; aws.cov_r = ws.cov_r;
       aws.cov_c = ws.cov_c;
       munkres_coop(w, aws, ws.cost, n_det, n_trk, ws.assignment);
-    });
-    tm.pfor(n_det, [&](int p) {
-      const int a = ws.assignment[p];
-      if (a >= 0 && ws.cost[p + n_det * a] > q.dist_threshold) ws.assignment[p] = -1;
-    });
-  } else {
-    tm.pfor(n_det, [&](int p) { ws.assignment[p] = -1; });
-  }
-
-  // new tracks for unassigned detections, in detection order (PRI:570-580)
-  tm.single([&] {
-    for (int p = 0; p < n_det; ++p) {
-      ws.isnew[p] = 0;
-      if (ws.assignment[p] >= 0) { ws.slot[p] = order[ws.assignment[p]]; continue; }
-      int s = -1;
-      for (int i = 0; i < max_tracks; ++i)
-        if (!((st->used >> i) & 1ull)) { s = i; break; }
-      if (s < 0 || st->n_tracks >= max_tracks) { st->overflow = 1; ws.slot[p] = -1; continue; }
-      st->used |= 1ull << s;
-      order[st->n_tracks++] = (uint8_t)s;
-      PriorTrack& tr = tracks[s];
-      tr.t_prev = -DBL_MAX;      // "never observed" (the reference leaves t_prev uninitialised, PRI:79-82)
-      tr.height_prev = -1.0;
-      tr.root_prev[0] = tr.root_prev[1] = tr.root_prev[2] = 0.0;
-      tr.exists = 0u; tr.num_obs = 0; tr.id = st->next_id++;
-      ws.slot[p] = s;
-      ws.isnew[p] = 1;
+      w.pfor(n_det, [&](int p) {
+        const int a = ws.assignment[p];
+        if (a >= 0 && ws.cost[p + n_det * a] > q.dist_threshold) ws.assignment[p] = -1;
+      });
+    } else {
+      w.pfor(n_det, [&](int p) { ws.assignment[p] = -1; });
     }
-  });
-  tm.pfor(n_det * NFUS * PRIOR_NAVG * 3, [&](int i) {
-    const int p = i / (NFUS * PRIOR_NAVG * 3);
-    if (ws.isnew[p]) (&tracks[ws.slot[p]].vel[0][0][0])[i % (NFUS * PRIOR_NAVG * 3)] = 0.0;
-  });
-  tm.pfor(n_det, [&](int p) { ws.has[p] = prior_has_measurement(pt, persons[p]) ? 1 : 0; });
-  tm.single([&] {  // persons are published in detection order once their track has enough observations (PRI:845-848)
-    int n_pub = 0;
-    for (int p = 0; p < n_det; ++p) {
-      const int s = ws.slot[p];
-      ws.out_idx[p] = (s >= 0 && ws.has[p] && tracks[s].num_obs + 1 > q.min_num_obs_track) ? n_pub++ : -1;
-      if (track_of && s >= 0) track_of[p] = tracks[s].id;
-    }
-    ws.scal[PS_NPUB] = n_pub;
+    w.single([&] {
+      int n_pub = 0;
+      for (int p = 0; p < n_det; ++p) {
+        int s = -1;
+        if (ws.assignment[p] >= 0) {
+          s = order[ws.assignment[p]];
+        } else {  // new track, in detection order
+          for (int i = 0; i < max_tracks; ++i)
+            if (!((st->used >> i) & 1ull)) { s = i; break; }
+          if (s < 0 || st->n_tracks >= max_tracks) { st->overflow = 1; s = -1; }
+          else {
+            st->used |= 1ull << s;
+            order[st->n_tracks++] = (uint8_t)s;
+            PriorTrack& tr = tracks[s];
+            tr.t_prev = -DBL_MAX;      // "never observed" (the reference leaves t_prev uninitialised, PRI:79-82)
+            tr.height_prev = -1.0;     // also tells the fit that the velocity buffer has to be zeroed
+            tr.root_prev[0] = tr.root_prev[1] = tr.root_prev[2] = 0.0;
+            tr.exists = 0u; tr.num_obs = 0; tr.id = st->next_id++;
+          }
+        }
+        ws.slot[p] = s;
+        // persons are published in detection order once their track has enough observations
+        ws.out_idx[p] = (s >= 0 && ws.has[p] && tracks[s].num_obs + 1 > q.min_num_obs_track) ? n_pub++ : -1;
+        if (track_of && s >= 0) track_of[p] = tracks[s].id;
+      }
+      ws.scal[PS_NPUB] = n_pub;
+    });
   });
   const int n_pub = ws.scal[PS_NPUB];
-  const double t_prev_global = st->t_prev;
-  const int frame_nr = st->frame_nr;
 
-  // the skeleton fits: one warp per group of up to `group` detections (PRI:587-853)
+  // ---- phase 3: the skeleton fits, one warp per group of up to `group` detections (PRI:587-853)
   const int n_groups = (n_det + group - 1) / group;
   tm.per_warp(n_groups, [&](auto& w, int gi) {
     const int wid = w.size() == 1 ? 0 : (tm.rank() / 32);   // serial build: one workspace
@@ -897,40 +900,44 @@ SES_HD void prior_frame(Team& tm, const PriorTables& pt, int max_tracks, int h_m
                     frame_nr, pred_delta_t, fws);
   });
 
-  // track life cycle: prune, then merge close tracks (PRI:866-903)
-  tm.single([&] { prior_remove_old(pt, st, tracks, order, t); });
-  const int n = st->n_tracks;
-  tm.pfor(n * n, [&](int e) {
-    const int i = e / n, j = e % n;
-    if (i < j) ws.D[e] = prior_track_dist(tracks[order[i]], tracks[order[j]]);
-  });
-  tm.single([&] {
-    // positions refer to the list at entry; the merge loop erases entries but never modifies a track
-    int live[PRIOR_MAX_TRACKS];
-    int m = n;
-    for (int i = 0; i < n; ++i) live[i] = i;
-    for (int i = 0; i < m; ++i) {
-      for (int j = i + 1; j < m;) {
-        if (ws.D[live[i] * n + live[j]] < q.merge_dist_thresh) {
-          const int sj = order[live[j]], si = order[live[i]];
-          const uint32_t id_to_remove = (uint32_t)tracks[sj].id, id_keep = (uint32_t)tracks[si].id;
-          st->used &= ~(1ull << sj);
-          for (int k = j; k + 1 < m; ++k) live[k] = live[k + 1];
-          --m;
-          for (int k = 0; k < n_pub; ++k)
-            if (fused[k].id == id_to_remove) { fused[k].id = id_keep; pred[k].id = id_keep; }
-        } else {
-          ++j;
+  // ---- phase 4 (first warp): prune (PRI:867), then merge close tracks (PRI:870-903)
+  tm.warp0([&](auto& w) {
+    w.single([&] { prior_remove_old(pt, st, tracks, order, t); });
+    const int n = st->n_tracks;
+    w.pfor(n * n, [&](int e) {
+      const int i = e / n, j = e % n;
+      if (i < j) ws.D[e] = prior_track_dist(tracks[order[i]], tracks[order[j]]);
+    });
+    w.single([&] {
+      // positions refer to the list at entry; the merge loop erases entries but never modifies a track
+      int live[PRIOR_MAX_TRACKS];
+      int m = n;
+      for (int i = 0; i < n; ++i) live[i] = i;
+      for (int i = 0; i < m; ++i) {
+        for (int j = i + 1; j < m;) {
+          if (ws.D[live[i] * n + live[j]] < q.merge_dist_thresh) {
+            const int sj = order[live[j]], si = order[live[i]];
+            const uint32_t id_to_remove = (uint32_t)tracks[sj].id, id_keep = (uint32_t)tracks[si].id;
+            st->used &= ~(1ull << sj);
+            for (int k = j; k + 1 < m; ++k) live[k] = live[k + 1];
+            --m;
+            for (int k = 0; k < n_pub; ++k)
+              if (fused[k].id == id_to_remove) { fused[k].id = id_keep; pred[k].id = id_keep; }
+          } else {
+            ++j;
+          }
         }
       }
-    }
-    uint8_t tmp[PRIOR_MAX_TRACKS];
-    for (int i = 0; i < m; ++i) tmp[i] = order[live[i]];
-    for (int i = 0; i < m; ++i) order[i] = tmp[i];
-    st->n_tracks = m;
-    *n_out = n_pub;
-    st->t_prev = t;   // PRI:909-910
-    ++st->frame_nr;
+      if (m != n) {
+        uint8_t tmp[PRIOR_MAX_TRACKS];
+        for (int i = 0; i < m; ++i) tmp[i] = order[live[i]];
+        for (int i = 0; i < m; ++i) order[i] = tmp[i];
+        st->n_tracks = m;
+      }
+      *n_out = n_pub;
+      st->t_prev = t;   // PRI:909-910
+      ++st->frame_nr;
+    });
   });
 }
 

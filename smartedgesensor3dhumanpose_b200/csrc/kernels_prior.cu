@@ -32,10 +32,10 @@ k_prior(const PriorTables pt_in, int n_seq, int n_frames, int h_max, int max_tra
   __syncthreads();
   PriorTables pt = pt_in;
   pt.st = reinterpret_cast<const PriorStatic*>(smem_raw);
-  Arena ar(smem_raw + kStaticBytes);
+  unsigned char* fit_ws = smem_raw + kStaticBytes + ws_bytes;   // fit workspaces, shared with the tracker's big arrays
+  Arena ar(smem_raw + kStaticBytes), tr(fit_ws);
   PriorWs ws;
-  prior_ws_layout(ar, h_max, max_tracks, &ws);
-  unsigned char* fit_ws = smem_raw + kStaticBytes + ws_bytes;
+  prior_ws_layout(ar, tr, h_max, max_tracks, &ws);
   BlockTeam tm;
   PriorSeqState* st = states + s;
   PriorTrack* trk = tracks + (size_t)s * max_tracks;
@@ -67,16 +67,19 @@ cudaError_t launch_prior(const PriorTables& pt, int n_seq, int n_frames, int h_m
                          ses3d_person_cov* fused, ses3d_person_cov* pred, int32_t* n_out, float* pred_delay,
                          int32_t* track_of, cudaStream_t st) {
   // One warp fits a group of up to `group` detections together (prior_core.h); the groups of a message are spread
-  // over the CTA's warps. Measured on B200 (2048 streams x 32 messages x 6 people, ms per launch): group 6 / 1 warp
-  // 37.0, 6 / 2 37.1, 3 / 2 23.2, 3 / 4 23.2, 2 / 4 23.0, 1 / 4 27.0 - shared memory per CTA (occupancy) decides.
+  // over the CTA's warps. Measured on B200 (2048 streams x 32 messages x 6 people, h_max 8, ms per launch):
+  // group/warps 3/1 23.6, 3/2 19.0, 3/3 22.7, 2/2 22.7, 2/3 19.6, 2/4 22.5, 4/2 24.5 - just enough warps to fit a
+  // typical message in one round, and as little shared memory per CTA as possible (occupancy decides).
   int group = std::max(1, std::min(3, h_max));
   if (const char* env = getenv("SES3D_PRIOR_GROUP")) group = std::max(1, std::min(PRIOR_GMAX, atoi(env)));
-  int warps = std::max(1, std::min(4, (h_max + group - 1) / group));
+  const int typical = std::max(1, (3 * h_max + 3) / 4);    // messages rarely fill all h_max slots
+  int warps = std::max(1, std::min(4, (typical + group - 1) / group));
   if (const char* env = getenv("SES3D_PRIOR_WARPS")) warps = std::max(1, std::min(8, atoi(env)));
-  const size_t ws_bytes = prior_ws_bytes(h_max, max_tracks);
+  size_t ws_bytes = 0, transient_bytes = 0;
+  prior_ws_bytes(h_max, max_tracks, &ws_bytes, &transient_bytes);
   const size_t fit_bytes = prior_fit_ws_bytes(group);
   static_assert(sizeof(PriorStatic) % 4 == 0, "copied word by word");
-  const size_t smem = kStaticBytes + ws_bytes + fit_bytes * warps;
+  const size_t smem = kStaticBytes + ws_bytes + std::max(fit_bytes * warps, transient_bytes);
   if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
   cudaError_t e = cudaFuncSetAttribute(k_prior, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

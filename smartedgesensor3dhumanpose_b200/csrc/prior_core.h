@@ -121,10 +121,12 @@ struct PriorFitScal {           // LM / bookkeeping state of one detection of th
 };
 
 struct PriorFitWs {       // the factor graphs of one group, one workspace per warp; index i = g * 21 + joint
-  double *m, *x, *dl, *w, *z;        // [G*21][3]
-  double* guy;                       // [G*21][6]: gu (gradient of the unary factor) | y = Dinv b; later the marginal Sg
+  double *m, *x, *w, *z;             // [G*21][3]
+  double* guy;                       // [G*21][6]: gu (gradient of the unary factor) | y = Dinv b, overwritten in place
+                                     //            by delta in the back-substitution; later the marginal Sg
   double *W, *Dinv;                  // [G*21][6]  (00,01,02,11,12,22): information of the unary factor; block inverse
-  double *e, *alpha, *beta, *ta, *tb;  // [G*21]
+  double *e, *alpha, *beta;          // [G*21]
+  double *ta, *tb;                   // [G*21] per-joint error terms; alias alpha / beta (never live together)
   int8_t* par;                       // [G*21] parent joint of the bone, -1 none
   uint8_t *msd, *usev;               // [G*21] measured / velocity usable
   PriorFitScal* sc;                  // [G]
@@ -133,20 +135,20 @@ struct PriorFitWs {       // the factor graphs of one group, one workspace per w
 template <class A>
 SES_HD void prior_fit_ws_layout(A& ar, int G, PriorFitWs* ws) {
   const size_t n = (size_t)G * NFUS;
-  double* v3[5];
-  for (int i = 0; i < 5; ++i) v3[i] = ar.template take<double>(n * 3);
+  double* v3[4];
+  for (int i = 0; i < 4; ++i) v3[i] = ar.template take<double>(n * 3);
   double* v6[3];
   for (int i = 0; i < 3; ++i) v6[i] = ar.template take<double>(n * 6);
-  double* v1[5];
-  for (int i = 0; i < 5; ++i) v1[i] = ar.template take<double>(n);
+  double* v1[3];
+  for (int i = 0; i < 3; ++i) v1[i] = ar.template take<double>(n);
   PriorFitScal* sc = ar.template take<PriorFitScal>(G);
   int8_t* par = ar.template take<int8_t>(n);
   uint8_t* msd = ar.template take<uint8_t>(n);
   uint8_t* usev = ar.template take<uint8_t>(n);
   if (ws) {
-    ws->m = v3[0]; ws->x = v3[1]; ws->dl = v3[2]; ws->w = v3[3]; ws->z = v3[4];
+    ws->m = v3[0]; ws->x = v3[1]; ws->w = v3[2]; ws->z = v3[3];
     ws->guy = v6[0]; ws->W = v6[1]; ws->Dinv = v6[2];
-    ws->e = v1[0]; ws->alpha = v1[1]; ws->beta = v1[2]; ws->ta = v1[3]; ws->tb = v1[4];
+    ws->e = v1[0]; ws->alpha = v1[1]; ws->beta = v1[2]; ws->ta = v1[1]; ws->tb = v1[2];
     ws->sc = sc; ws->par = par; ws->msd = msd; ws->usev = usev;
   }
 }
@@ -164,39 +166,41 @@ struct PriorWs {          // per-stream frame workspace (shared memory of the CT
   int* assignment;        // [h_max]
   int* slot;              // [h_max] track slot of each detection, -1 = none (capacity)
   int* out_idx;           // [h_max] position in the published list or -1
-  uint8_t *isnew, *has;   // [h_max]
+  uint8_t* has;           // [h_max]
   int* scal;              // [4] {n_trk at frame start, n_pub}
 };
 enum { PW_T = 0, PW_PDT = 1 };
 enum { PS_NTRK = 0, PS_NPUB = 1 };
 
-template <class A>
-SES_HD void prior_ws_layout(A& ar, int h_max, int max_tracks, PriorWs* ws) {
-  double* cost = ar.template take<double>((size_t)h_max * max_tracks);
-  double* dist = ar.template take<double>((size_t)h_max * max_tracks);
-  double* D = ar.template take<double>((size_t)max_tracks * max_tracks);
+// The small arrays live for the whole message; the big ones (cost / Munkres tables, pair distances) are only used
+// while no fit is running and therefore share memory with the fit workspaces (`tr` arena).
+template <class A, class B>
+SES_HD void prior_ws_layout(A& ar, B& tr, int h_max, int max_tracks, PriorWs* ws) {
   double* dscal = ar.template take<double>(4);
   int* assignment = ar.template take<int>(h_max);
   int* slot = ar.template take<int>(h_max);
   int* out_idx = ar.template take<int>(h_max);
   int* scal = ar.template take<int>(4);
-  uint8_t* star = ar.template take<uint8_t>((size_t)h_max * max_tracks);
-  uint8_t* prime = ar.template take<uint8_t>((size_t)h_max * max_tracks);
-  uint8_t* nstar = ar.template take<uint8_t>((size_t)h_max * max_tracks);
-  uint8_t* cov_r = ar.template take<uint8_t>(h_max);
-  uint8_t* cov_c = ar.template take<uint8_t>(max_tracks);
-  uint8_t* isnew = ar.template take<uint8_t>(h_max);
   uint8_t* has = ar.template take<uint8_t>(h_max);
+  double* cost = tr.template take<double>((size_t)h_max * max_tracks);
+  double* dist = tr.template take<double>((size_t)h_max * max_tracks);
+  double* D = tr.template take<double>((size_t)max_tracks * max_tracks);
+  uint8_t* star = tr.template take<uint8_t>((size_t)h_max * max_tracks);
+  uint8_t* prime = tr.template take<uint8_t>((size_t)h_max * max_tracks);
+  uint8_t* nstar = tr.template take<uint8_t>((size_t)h_max * max_tracks);
+  uint8_t* cov_r = tr.template take<uint8_t>(h_max);
+  uint8_t* cov_c = tr.template take<uint8_t>(max_tracks);
   if (ws) {
     ws->cost = cost; ws->dist = dist; ws->D = D; ws->dscal = dscal; ws->assignment = assignment; ws->slot = slot;
     ws->out_idx = out_idx; ws->scal = scal; ws->star = star; ws->prime = prime; ws->nstar = nstar; ws->cov_r = cov_r;
-    ws->cov_c = cov_c; ws->isnew = isnew; ws->has = has;
+    ws->cov_c = cov_c; ws->has = has;
   }
 }
-inline size_t prior_ws_bytes(int h_max, int max_tracks) {
-  ArenaSizer s;
-  prior_ws_layout(s, h_max, max_tracks, nullptr);
-  return (s.used + 15) / 16 * 16;
+inline void prior_ws_bytes(int h_max, int max_tracks, size_t* persistent, size_t* transient) {
+  ArenaSizer a, b;
+  prior_ws_layout(a, b, h_max, max_tracks, nullptr);
+  *persistent = (a.used + 15) / 16 * 16;
+  *transient = (b.used + 15) / 16 * 16;
 }
 
 // ---- 3x3 helpers --------------------------------------------------------------------------------------------
@@ -418,11 +422,11 @@ SES_HD void prior_backsubstitute(WT& tm, const PriorTables& pt, int G, const Pri
       double s = 0.0;
       const int p = ws.par[i];
       if (p >= 0) {
-        const double* dp = ws.dl + 3 * (g * NFUS + p);
+        const double* dp = ws.guy + 6 * (g * NFUS + p) + 3;
         s = ws.w[3 * i] * dp[0] + ws.w[3 * i + 1] * dp[1] + ws.w[3 * i + 2] * dp[2];
       }
-      const double* y = ws.guy + 6 * i + 3;
-      for (int a = 0; a < 3; ++a) ws.dl[3 * i + a] = y[a] + ws.z[3 * i + a] * s;
+      double* y = ws.guy + 6 * i + 3;   // delta overwrites y
+      for (int a = 0; a < 3; ++a) y[a] = y[a] + ws.z[3 * i + a] * s;
     });
   }
 }
@@ -631,7 +635,7 @@ SES_HD void prior_fit_group(WT& tm, const PriorTables& pt, int G, const ses3d_pe
       const PriorFitScal& sc = ws.sc[g];
       if (!sc.lm || sc.fail || !ws.msd[i]) return;
       const double* x = ws.x + 3 * i;
-      const double* dl = ws.dl + 3 * i;
+      const double* dl = ws.guy + 6 * i + 3;
       const double xn[3] = {x[0] + dl[0], x[1] + dl[1], x[2] + dl[2]};
       const double d[3] = {xn[0] - ws.m[3 * i], xn[1] - ws.m[3 * i + 1], xn[2] - ws.m[3 * i + 2]};
       double wd[3];
@@ -642,7 +646,7 @@ SES_HD void prior_fit_group(WT& tm, const PriorTables& pt, int G, const ses3d_pe
       if (p >= 0) {
         const int ip = g * NFUS + p;
         const double* xp = ws.x + 3 * ip;
-        const double* dp = ws.dl + 3 * ip;
+        const double* dp = ws.guy + 6 * ip + 3;
         const double* w = ws.w + 3 * i;
         const double el = ws.e[i] + w[0] * (dl[0] - dp[0]) + w[1] * (dl[1] - dp[1]) + w[2] * (dl[2] - dp[2]);
         lin += 0.5 * (el * el);
@@ -697,7 +701,7 @@ SES_HD void prior_fit_group(WT& tm, const PriorTables& pt, int G, const ses3d_pe
     });
     tm.pfor(G * NFUS, [&](int i) {
       if (!ws.sc[i / NFUS].accept || !ws.msd[i]) return;
-      for (int a = 0; a < 3; ++a) ws.x[3 * i + a] += ws.dl[3 * i + a];
+      for (int a = 0; a < 3; ++a) ws.x[3 * i + a] += ws.guy[6 * i + 3 + a];
     });
   }
 

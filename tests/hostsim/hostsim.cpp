@@ -5,6 +5,7 @@
 // K0 tables so that the GPU-less container can check the *device logic* (not just the oracle)
 // against the oracle. It is built by tests/hostsim/build.py into tests/hostsim/libhostsim.so,
 // is never loaded by the product package, and is not a CPU fallback: libses3d.so has none.
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -151,15 +152,17 @@ int hostsim_prior_run(void* h, int32_t n_sequences, int32_t n_frames, int32_t h_
                       int32_t* track_of, int32_t group) {
   PriorSim* s = static_cast<PriorSim*>(h);
   if (n_sequences > s->n_seq) return SES3D_E_INVALID;
-  std::vector<unsigned char> wsb(prior_ws_bytes(h_max, s->max_tracks) + 64), fitb(prior_fit_ws_bytes(group) + 64);
+  size_t pers = 0, trans = 0;
+  prior_ws_bytes(h_max, s->max_tracks, &pers, &trans);
+  std::vector<unsigned char> wsb(pers + 64), fitb(std::max(prior_fit_ws_bytes(group), trans) + 64);
   SerialTeam tm;
   int rc = 0;
   for (int q = 0; q < n_sequences; ++q) {
     for (int f = 0; f < n_frames; ++f) {
       const size_t i = (size_t)q * n_frames + f;
-      Arena ar(wsb.data());
+      Arena ar(wsb.data()), tr(fitb.data());   // the tracker's big arrays share memory with the fit workspace
       PriorWs ws;
-      prior_ws_layout(ar, h_max, s->max_tracks, &ws);
+      prior_ws_layout(ar, tr, h_max, s->max_tracks, &ws);
       prior_frame(tm, s->pt, s->max_tracks, h_max, group, &s->states[q], s->tracks.data() + (size_t)q * s->max_tracks,
                   s->order.data() + (size_t)q * s->max_tracks, ws, fitb.data(), 0, stamp_ns[i], n_cams,
                   fb_delay ? fb_delay + i * n_cams : nullptr, n_persons[i], persons + i * h_max, fused + i * h_max,

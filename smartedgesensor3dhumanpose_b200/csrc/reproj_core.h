@@ -41,6 +41,35 @@ inline size_t reproj_ws_bytes(int cap_rec, int s_cap) {
   return (s.used + 15) / 16 * 16;
 }
 
+// Conservative single-precision pre-test of REP:207-208. A person is in view of only a few cameras, so most
+// (joint, camera) pairs end in "mean pixel outside the image -> skip". When all seven sigma points lie at least
+// 0.5 m in front of the camera, within 100 m of the origin and within 1e4 px of the principal point, the float
+// evaluation of the mean pixel is within ~1.1 px of the FP64 one (coordinate rounding 100 m x 2^-24 x 4 terms ->
+// 2.4e-5 m; fx dX / Z <= 0.05 px; |u - cx| dZ / Z <= 0.5 px; float mean / division rounding <= 0.01 px each of
+// the seven terms). If that estimate is more than 16 px outside the image the exact mean is outside too and the
+// FP64 projections (fourteen IEEE divisions) are skipped; everything else takes the exact path unchanged.
+SES_HD bool reproj_certainly_outside(const double* S, const CamF& cf, const CamD& cm) {
+  const float fx = cf.fx, fy = cf.fy, cx = cf.cx, cy = cf.cy, Tx = (float)cm.Tx, Ty = (float)cm.Ty;
+  const float w0 = (float)(2 * 0.5 / (2.0 * 3.5)), wi = (float)(1.0 / (2.0 * 3.5));
+  float mu = 0.f, mv = 0.f;
+  bool tame = true;
+  for (int s = 0; s < 7; ++s) {
+    const float sx = (float)S[s * 3], sy = (float)S[s * 3 + 1], sz = (float)S[s * 3 + 2];
+    const float X = cf.P[0] * sx + cf.P[1] * sy + cf.P[2] * sz + cf.P[3];
+    const float Y = cf.P[4] * sx + cf.P[5] * sy + cf.P[6] * sz + cf.P[7];
+    const float Z = cf.P[8] * sx + cf.P[9] * sy + cf.P[10] * sz + cf.P[11];
+    const float du = (fx * X + Tx) / Z, dv = (fy * Y + Ty) / Z;
+    tame = tame && Z >= 0.5f && ses_abs(sx) < 100.f && ses_abs(sy) < 100.f && ses_abs(sz) < 100.f &&
+           ses_abs(du) < 1e4f && ses_abs(dv) < 1e4f;
+    const float w = s == 0 ? w0 : wi;
+    mu += (du + cx) * w;
+    mv += (dv + cy) * w;
+  }
+  if (!tame) return false;   // also false for NaN / Inf inputs: every comparison above fails
+  const float m = 16.f;
+  return mu < -m || mu > (float)cm.width + m || mv < -m || mv > (float)cm.height + m;
+}
+
 // persons3d [n_p] (n_p <= h_max); out [C][h_max]; n_out [C]
 template <class Team>
 SES_HD void reproject_frame(Team& tm, const Tables& tb, int h_max, int cap_rec, const ses3d_person_cov* persons3d,
@@ -94,6 +123,10 @@ SES_HD void reproject_frame(Team& tm, const Tables& tb, int h_max, int cap_rec, 
           const double w0 = 2 * 0.5 / wden, wi = 1.0 / wden;  // REP:65-66
           const double* S = ws.S + (size_t)e * 21;
           const CamD& cm = tb.camd[c0 + cc];
+          if (reproj_certainly_outside(S, tb.camf[c0 + cc], cm)) {   // most (joint, camera) pairs: not in view
+            ws.vflag[(cc * n_p + p) * NKP + k] = 0;
+            return;
+          }
           double u[7], v[7];
           for (int s = 0; s < 7; ++s) {
             const double sx = S[s * 3], sy = S[s * 3 + 1], sz = S[s * 3 + 2];

@@ -120,3 +120,37 @@ def test_merge_of_close_skeletons():
     assert np.array_equal(ro["hyp_of"], rh["hyp_of"]) and np.array_equal(ro["n_out"], rh["n_out"])
     assert (ro["n_hyp"] > 4).any()
     helpers.compare_persons3d(ro, rh, 1e-3, cov_rtol=5e-2)
+
+
+def test_reprojection_prefilter_is_exact_near_borders_and_behind_cameras():
+    """The single-precision "certainly outside the image" pre-test (reproj_core.h) must never change a record:
+    skeletons scattered all over (and outside) the hall, near the image borders, behind and very close to cameras,
+    with covariances from millimetres to metres, NaNs and a non-SPD covariance - bitwise equal to the oracle."""
+    from smartedgesensor3dhumanpose_b200.layouts import KP2FUSION_SIMPLE, person_cov_dtype
+    from smartedgesensor3dhumanpose_b200.sequences import TEMPLATE
+    rng = np.random.default_rng(77)
+    for rig in ("hall16", "ring8"):
+        cams = helpers.rigs.RIGS[rig]()
+        F, H = 120, 6
+        p3 = np.zeros((F, H), person_cov_dtype)
+        n3 = np.full(F, H, np.int32)
+        fus = np.array(KP2FUSION_SIMPLE)
+        pos = rng.uniform(-12, 12, (F, H, 1, 3)) * [1, 1, 0.2]
+        X = TEMPLATE[None, None] * rng.uniform(0.3, 3.0, (F, H, 1, 1)) + pos
+        kp = p3["keypoints"]
+        for i, c in enumerate("xyz"):
+            v = np.zeros((F, H, 21)); v[..., fus] = X[..., i]; kp[c] = v
+        sc = np.zeros((F, H, 21), np.float32); sc[..., fus] = rng.uniform(0.05, 1.0, (F, H, 17)); kp["score"] = sc
+        A = rng.normal(0, 1, (F, H, 21, 3, 3)) * 10.0 ** rng.uniform(-3, 0.3, (F, H, 21, 1, 1))
+        S = A @ np.swapaxes(A, -1, -2) + 1e-12 * np.eye(3)
+        kp["cov"] = np.stack([S[..., 0, 0], S[..., 0, 1], S[..., 0, 2], S[..., 1, 1], S[..., 1, 2], S[..., 2, 2]], -1)
+        p3["keypoints"] = kp
+        p3["keypoints"]["x"][3, 1, 5] = np.nan
+        p3["keypoints"]["cov"][4, 2, 6] = [1e-4, 5e-4, 0, 1e-4, 0, 1e-4]      # not positive definite -> NaN sigma points
+        p3["keypoints"]["cov"][5, 0, 2] = 0.0
+        po = Oracle(cams).reproject_batch(p3, n3)
+        ph = HostSim(cams).reproject_batch(p3, n3)
+        assert np.array_equal(po["n_out"], ph["n_out"])
+        live = np.arange(H)[None, None, :] < po["n_out"][:, :, None]
+        assert po["persons2d"][live].tobytes() == ph["persons2d"][live].tobytes()
+        assert po["n_out"].sum() > 100

@@ -79,7 +79,7 @@ k_reproject(const Tables tb, int n_frames, int h_max, int cap_rec, int s_cap,
   if (f >= n_frames) return;
   Arena ar(smem_raw);
   ReprojWs ws;
-  reproj_ws_layout(ar, cap_rec, s_cap, &ws);
+  reproj_ws_layout(ar, tb.n_cams, cap_rec, s_cap, &ws);
   BlockTeam tm;
   reproject_frame(tm, tb, h_max, cap_rec, persons3d + (size_t)f * h_max, n_persons3d[f], ws,
                   out + (size_t)f * tb.n_cams * h_max, n_out + (size_t)f * tb.n_cams);
@@ -160,8 +160,8 @@ cudaError_t launch_reproject(const Tables& tb, int n_frames, int h_max, const se
   // staging capacity in records: ~28 KB, at least one camera of h_max persons, at most the whole frame
   int cap_rec = std::max(h_max, std::min(tb.n_cams * h_max, 64));
   if (const char* env = getenv("SES3D_REPROJ_CAP")) cap_rec = std::max(h_max, atoi(env));
-  const int s_cap = std::min(h_max, 8);
-  const size_t smem = reproj_ws_bytes(cap_rec, s_cap);
+  const int s_cap = reproj_s_cap(tb.n_cams, h_max, 6);
+  const size_t smem = reproj_ws_bytes(tb.n_cams, cap_rec, s_cap);
   if (smem > kSmemBudget) return cudaErrorInvalidConfiguration;
   cudaError_t e = cudaFuncSetAttribute(k_reproject, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

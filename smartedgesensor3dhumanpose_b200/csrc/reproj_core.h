@@ -22,52 +22,65 @@ struct ReprojWs {
   int* slot;              // [cc][n_p] output slot or -1
   double* S;              // [s_cap*17][21] sigma points of the current person batch (7 points x xyz)
   float* sscore;          // [s_cap*17] 3-D score (0 = joint absent)
+  float* ctr;             // [s_cap*17][4] single-precision joint centre x, y, z and the sigma-point radius
+  uint16_t* list;         // [s_cap*17*C] (joint, camera) items that need the exact projection
+  int* cnt;               // [1] length of list
   int s_cap;              // persons per batch
+  int n_cams;
 };
 
 // cap_rec = staging capacity in Person2D records (>= h_max so that one camera always fits)
 template <class A>
-SES_HD void reproj_ws_layout(A& ar, int cap_rec, int s_cap, ReprojWs* ws) {
+SES_HD void reproj_ws_layout(A& ar, int n_cams, int cap_rec, int s_cap, ReprojWs* ws) {
   double* S = ar.template take<double>((size_t)s_cap * NKP * 21);
   ses3d_person2d* stage = ar.template take<ses3d_person2d>((size_t)cap_rec);
   int* slot = ar.template take<int>((size_t)cap_rec);
   float* sscore = ar.template take<float>((size_t)s_cap * NKP);
+  float* ctr = ar.template take<float>((size_t)s_cap * NKP * 4);
+  int* cnt = ar.template take<int>(1);
+  uint16_t* list = ar.template take<uint16_t>((size_t)s_cap * NKP * n_cams);
   uint8_t* vflag = ar.template take<uint8_t>((size_t)cap_rec * NKP);
-  if (ws) { ws->S = S; ws->stage = stage; ws->slot = slot; ws->sscore = sscore; ws->vflag = vflag; ws->s_cap = s_cap; }
+  if (ws) {
+    ws->S = S; ws->stage = stage; ws->slot = slot; ws->sscore = sscore; ws->vflag = vflag; ws->s_cap = s_cap;
+    ws->ctr = ctr; ws->cnt = cnt; ws->list = list; ws->n_cams = n_cams;
+  }
 }
-inline size_t reproj_ws_bytes(int cap_rec, int s_cap) {
+inline size_t reproj_ws_bytes(int n_cams, int cap_rec, int s_cap) {
   ArenaSizer s;
-  reproj_ws_layout(s, cap_rec, s_cap, nullptr);
+  reproj_ws_layout(s, n_cams, cap_rec, s_cap, nullptr);
   return (s.used + 15) / 16 * 16;
+}
+// items per person batch must be addressable by the 16-bit work list
+inline int reproj_s_cap(int n_cams, int h_max, int want) {
+  int s = want < h_max ? want : h_max;
+  while (s > 1 && (long long)s * NKP * n_cams > 65535) --s;
+  return s < 1 ? 1 : s;
 }
 
 // Conservative single-precision pre-test of REP:207-208. A person is in view of only a few cameras, so most
-// (joint, camera) pairs end in "mean pixel outside the image -> skip". When all seven sigma points lie at least
-// 0.5 m in front of the camera, within 100 m of the origin and within 1e4 px of the principal point, the float
-// evaluation of the mean pixel is within ~1.1 px of the FP64 one (coordinate rounding 100 m x 2^-24 x 4 terms ->
-// 2.4e-5 m; fx dX / Z <= 0.05 px; |u - cx| dZ / Z <= 0.5 px; float mean / division rounding <= 0.01 px each of
-// the seven terms). If that estimate is more than 16 px outside the image the exact mean is outside too and the
-// FP64 projections (fourteen IEEE divisions) are skipped; everything else takes the exact path unchanged.
-SES_HD bool reproj_certainly_outside(const double* S, const CamF& cf, const CamD& cm) {
-  const float fx = cf.fx, fy = cf.fy, cx = cf.cx, cy = cf.cy, Tx = (float)cm.Tx, Ty = (float)cm.Ty;
-  const float w0 = (float)(2 * 0.5 / (2.0 * 3.5)), wi = (float)(1.0 / (2.0 * 3.5));
-  float mu = 0.f, mv = 0.f;
-  bool tame = true;
-  for (int s = 0; s < 7; ++s) {
-    const float sx = (float)S[s * 3], sy = (float)S[s * 3 + 1], sz = (float)S[s * 3 + 2];
-    const float X = cf.P[0] * sx + cf.P[1] * sy + cf.P[2] * sz + cf.P[3];
-    const float Y = cf.P[4] * sx + cf.P[5] * sy + cf.P[6] * sz + cf.P[7];
-    const float Z = cf.P[8] * sx + cf.P[9] * sy + cf.P[10] * sz + cf.P[11];
-    const float du = (fx * X + Tx) / Z, dv = (fy * Y + Ty) / Z;
-    tame = tame && Z >= 0.5f && ses_abs(sx) < 100.f && ses_abs(sy) < 100.f && ses_abs(sz) < 100.f &&
-           ses_abs(du) < 1e4f && ses_abs(dv) < 1e4f;
-    const float w = s == 0 ? w0 : wi;
-    mu += (du + cx) * w;
-    mv += (dv + cy) * w;
-  }
-  if (!tame) return false;   // also false for NaN / Inf inputs: every comparison above fails
-  const float m = 16.f;
-  return mu < -m || mu > (float)cm.width + m || mv < -m || mv > (float)cm.height + m;
+// (joint, camera) pairs end in "mean pixel outside the image -> skip". With the joint centre x0 at depth Z0 and all
+// seven sigma points within radius r of it (r = sqrt(3.5) x the largest column norm of the Cholesky factor), every
+// sigma point has depth >= Z0 - r and its pixel lies within B = (f (Z0 + |X0|) + |T|) r / (Z0 (Z0 - r)) of the centre's
+// pixel, and so does their weighted mean (weights are positive and sum to one). If the centre's pixel is more than
+// B + 16 px outside the image, the exact FP64 mean is outside as well and the fourteen IEEE divisions of the exact
+// path are skipped. Conditions that keep single precision trustworthy (else the exact path runs): Z0 - r >= 0.5 m,
+// |x0| < 100 m, centre within 1e4 px of the principal point -> float evaluation error < 1.1 px (coordinate rounding
+// 2.4e-5 m, f dX / Z <= 0.05 px, |u - cx| dZ / Z <= 0.5 px), well inside the 16 px margin. NaN / Inf fail every test.
+SES_HD bool reproj_certainly_outside(const float* c4, const CamF& cf, const CamD& cm) {
+  const float sx = c4[0], sy = c4[1], sz = c4[2], r = c4[3];
+  const float X = cf.P[0] * sx + cf.P[1] * sy + cf.P[2] * sz + cf.P[3];
+  const float Y = cf.P[4] * sx + cf.P[5] * sy + cf.P[6] * sz + cf.P[7];
+  const float Z = cf.P[8] * sx + cf.P[9] * sy + cf.P[10] * sz + cf.P[11];
+  const float zr = Z - r;
+  if (!(zr >= 0.5f) || !(ses_abs(sx) < 100.f) || !(ses_abs(sy) < 100.f) || !(ses_abs(sz) < 100.f)) return false;
+  const float iz = 1.0f / Z;
+  const float du = (cf.fx * X + (float)cm.Tx) * iz, dv = (cf.fy * Y + (float)cm.Ty) * iz;
+  if (!(ses_abs(du) < 1e4f) || !(ses_abs(dv) < 1e4f)) return false;
+  const float k = r / zr * iz * 1.001f;                      // r / (Z0 (Z0 - r)), rounded up
+  const float bu = (cf.fx * (Z + ses_abs(X)) + ses_abs((float)cm.Tx)) * k + 16.f;
+  const float bv = (cf.fy * (Z + ses_abs(Y)) + ses_abs((float)cm.Ty)) * k + 16.f;
+  const float u = du + cf.cx, v = dv + cf.cy;
+  return u < -bu || u > (float)cm.width + bu || v < -bv || v > (float)cm.height + bv;
 }
 
 // persons3d [n_p] (n_p <= h_max); out [C][h_max]; n_out [C]
@@ -104,6 +117,13 @@ SES_HD void reproject_frame(Team& tm, const Tables& tb, int h_max, int cap_rec, 
         // samples: mean, mean - sp*L e_j (j=0..2), mean + sp*L e_j (REP:68-72)
         const double col[3][3] = {{l00, l10, l20}, {0.0, l11, l21}, {0.0, 0.0, l22}};
         double* S = ws.S + (size_t)e * 21;
+        {  // single-precision centre and sigma-point radius for the "certainly outside" pre-test
+          const double n0 = l00 * l00 + l10 * l10 + l20 * l20, n1 = l11 * l11 + l21 * l21, n2 = l22 * l22;
+          const double nm = n0 > n1 ? (n0 > n2 ? n0 : n2) : (n1 > n2 ? n1 : n2);
+          float* c4 = ws.ctr + (size_t)e * 4;
+          c4[0] = (float)kp.x; c4[1] = (float)kp.y; c4[2] = (float)kp.z;
+          c4[3] = (float)(sp * sqrt(nm)) * 1.001f + 1e-6f;   // NaN (non-SPD covariance) disables the pre-test
+        }
         S[0] = kp.x; S[1] = kp.y; S[2] = kp.z;
         for (int j = 0; j < 3; ++j) {
           S[(1 + j) * 3 + 0] = (col[j][0] * -sp) + kp.x; S[(1 + j) * 3 + 1] = (col[j][1] * -sp) + kp.y;
@@ -112,46 +132,49 @@ SES_HD void reproject_frame(Team& tm, const Tables& tb, int h_max, int cap_rec, 
           S[(4 + j) * 3 + 2] = (col[j][2] * sp) + kp.z;
         }
       });
-      // one thread per (person, joint, camera): project the 7 sigma points (REP:193-221)
+      // (joint, camera) pairs: cheap single-precision cull, then the exact projection of the survivors with all
+      // lanes busy (REP:193-221)
+      tm.single([&] { *ws.cnt = 0; });
       tm.pfor(np_b * NKP * ncc, [&](int e2) {
         const int cc = e2 % ncc, e = e2 / ncc;
         const int p = p0 + e / NKP, k = e % NKP;
+        ws.vflag[(cc * n_p + p) * NKP + k] = 0;
+        if (!(ws.sscore[e] > 0.0f)) return;
+        if (reproj_certainly_outside(ws.ctr + (size_t)e * 4, tb.camf[c0 + cc], tb.camd[c0 + cc])) return;
+        ws.list[team_append(ws.cnt)] = (uint16_t)e2;
+      });
+      tm.pfor(*ws.cnt, [&](int li) {
+        const int e2 = ws.list[li];
+        const int cc = e2 % ncc, e = e2 / ncc;
+        const int p = p0 + e / NKP, k = e % NKP;
         const float score = ws.sscore[e];
-        uint8_t ok = 0;
-        if (score > 0.0f) {
-          const double wden = 2.0 * (3 + 0.5);
-          const double w0 = 2 * 0.5 / wden, wi = 1.0 / wden;  // REP:65-66
-          const double* S = ws.S + (size_t)e * 21;
-          const CamD& cm = tb.camd[c0 + cc];
-          if (reproj_certainly_outside(S, tb.camf[c0 + cc], cm)) {   // most (joint, camera) pairs: not in view
-            ws.vflag[(cc * n_p + p) * NKP + k] = 0;
-            return;
-          }
-          double u[7], v[7];
-          for (int s = 0; s < 7; ++s) {
-            const double sx = S[s * 3], sy = S[s * 3 + 1], sz = S[s * 3 + 2];
-            const double X = cm.P[0] * sx + cm.P[1] * sy + cm.P[2] * sz + cm.P[3];
-            const double Y = cm.P[4] * sx + cm.P[5] * sy + cm.P[6] * sz + cm.P[7];
-            const double Z = cm.P[8] * sx + cm.P[9] * sy + cm.P[10] * sz + cm.P[11];
-            u[s] = (cm.fx * X + cm.Tx) / Z + cm.cx;  // project3dToPixel (image_geometry)
-            v[s] = (cm.fy * Y + cm.Ty) / Z + cm.cy;
-          }
-          double mu = 0, mv = 0;
-          for (int s = 0; s < 7; ++s) { const double w = s == 0 ? w0 : wi; mu += u[s] * w; mv += v[s] * w; }
-          double cxx = 0, cxy = 0, cyy = 0;
-          for (int s = 0; s < 7; ++s) {
-            const double w = s == 0 ? w0 : wi;
-            const double du = u[s] - mu, dv = v[s] - mv;
-            cxx += du * w * du; cxy += du * w * dv; cyy += dv * w * dv;
-          }
-          if (!(mu < 0 || mu > cm.width || mv < 0 || mv > cm.height)) {  // REP:207-208
-            ses3d_keypoint2d& o = ws.stage[cc * n_p + p].keypoints[k];
-            o.x = static_cast<float>(mu); o.y = static_cast<float>(mv); o.score = score;
-            o.cov[0] = static_cast<float>(cxx); o.cov[1] = static_cast<float>(cxy); o.cov[2] = static_cast<float>(cyy);
-            ok = 1;
-          }
+        const double wden = 2.0 * (3 + 0.5);
+        const double w0 = 2 * 0.5 / wden, wi = 1.0 / wden;  // REP:65-66
+        const double* S = ws.S + (size_t)e * 21;
+        const CamD& cm = tb.camd[c0 + cc];
+        double u[7], v[7];
+        for (int s = 0; s < 7; ++s) {
+          const double sx = S[s * 3], sy = S[s * 3 + 1], sz = S[s * 3 + 2];
+          const double X = cm.P[0] * sx + cm.P[1] * sy + cm.P[2] * sz + cm.P[3];
+          const double Y = cm.P[4] * sx + cm.P[5] * sy + cm.P[6] * sz + cm.P[7];
+          const double Z = cm.P[8] * sx + cm.P[9] * sy + cm.P[10] * sz + cm.P[11];
+          u[s] = (cm.fx * X + cm.Tx) / Z + cm.cx;  // project3dToPixel (image_geometry)
+          v[s] = (cm.fy * Y + cm.Ty) / Z + cm.cy;
         }
-        ws.vflag[(cc * n_p + p) * NKP + k] = ok;
+        double mu = 0, mv = 0;
+        for (int s = 0; s < 7; ++s) { const double w = s == 0 ? w0 : wi; mu += u[s] * w; mv += v[s] * w; }
+        double cxx = 0, cxy = 0, cyy = 0;
+        for (int s = 0; s < 7; ++s) {
+          const double w = s == 0 ? w0 : wi;
+          const double du = u[s] - mu, dv = v[s] - mv;
+          cxx += du * w * du; cxy += du * w * dv; cyy += dv * w * dv;
+        }
+        if (!(mu < 0 || mu > cm.width || mv < 0 || mv > cm.height)) {  // REP:207-208
+          ses3d_keypoint2d& o = ws.stage[cc * n_p + p].keypoints[k];
+          o.x = static_cast<float>(mu); o.y = static_cast<float>(mv); o.score = score;
+          o.cov[0] = static_cast<float>(cxx); o.cov[1] = static_cast<float>(cxy); o.cov[2] = static_cast<float>(cyy);
+          ws.vflag[(cc * n_p + p) * NKP + k] = 1;
+        }
       });
     }
 

@@ -35,6 +35,15 @@ struct SerialTeam {
   int size() const { return 1; }
 };
 
+// Reserve the next slot of a list shared by the team's threads (order is unspecified on the GPU).
+SES_HD int team_append(int* counter) {
+#if defined(__CUDA_ARCH__)
+  return atomicAdd(counter, 1);
+#else
+  return (*counter)++;
+#endif
+}
+
 #if defined(__CUDACC__)
 struct WarpTeam {
   template <class F> __device__ __forceinline__ void pfor(int n, F&& f) {

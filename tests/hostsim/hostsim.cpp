@@ -108,13 +108,13 @@ int hostsim_reproject_batch(void* h, int32_t n_frames, int32_t h_max, int32_t ca
   const int C = tb.n_cams;
   // cam_tile > 0 forces that many cameras per pass for a full frame; 0 = everything in one pass
   const int cap_rec = (cam_tile <= 0 ? C : cam_tile) * h_max;
-  const int s_cap = cam_tile > 0 ? 3 : h_max;   // small person batches when a tile size is forced
-  std::vector<unsigned char> wsr(reproj_ws_bytes(cap_rec, s_cap) + 64);
+  const int s_cap = reproj_s_cap(C, h_max, cam_tile > 0 ? 3 : h_max);   // small person batches when a tile size is forced
+  std::vector<unsigned char> wsr(reproj_ws_bytes(C, cap_rec, s_cap) + 64);
   SerialTeam tm;
   for (int f = 0; f < n_frames; ++f) {
     Arena a(wsr.data());
     ReprojWs ws;
-    reproj_ws_layout(a, cap_rec, s_cap, &ws);
+    reproj_ws_layout(a, C, cap_rec, s_cap, &ws);
     reproject_frame(tm, tb, h_max, cap_rec, p3d + (size_t)f * h_max, n_p3d[f], ws, out + (size_t)f * C * h_max,
                     n_out + (size_t)f * C);
   }

@@ -95,6 +95,31 @@ int main(void) {
            out3d[0].keypoints[SES3D_FBP_NOSE].x, out3d[0].keypoints[SES3D_FBP_NOSE].y, out3d[0].keypoints[SES3D_FBP_NOSE].z,
            n2[0], n2[1], n2[2], n2[3]);
     if (n3 != 1 || n2[0] != 1) return 12;
+
+    /* pose_prior: feed the same skeleton as 12 consecutive 30 Hz messages; it is published from the 11th on */
+    {
+      ses3d_prior_params pp;
+      ses3d_prior pr = NULL;
+      ses3d_person_cov fused[8], pred[8];
+      int32_t n_in = n3, n_pub = 0, ids[8], nobs[8];
+      float delay = 0.f;
+      int t;
+      ses3d_prior_default_params(&pp);
+      if (pp.min_num_obs_track != 10 || pp.dist_threshold != 5.0) return 13;
+      if (ses3d_prior_create(&pp, 1, 8, 0, &pr) != SES3D_OK) { printf("%s\n", ses3d_last_error_string()); return 14; }
+      for (t = 0; t < 12; ++t) {
+        const int64_t stamp = 1000000000000LL + (int64_t)t * 33333333LL;
+        rc = ses3d_prior_run(pr, 1, 1, 8, out3d, &n_in, &stamp, 0, NULL, fused, pred, &n_pub, &delay, NULL,
+                             SES3D_HOST_BUFFERS, NULL);
+        if (rc != SES3D_OK) { printf("%s\n", ses3d_last_error_string()); return 15; }
+        if ((t < 10) != (n_pub == 0)) return 16;
+      }
+      if (ses3d_prior_get_tracks(pr, 0, ids, nobs) != 1 || ids[0] != 0 || nobs[0] != 12) return 17;
+      printf("pose_prior: track %d, %d observations, fused nose = (%.3f, %.3f, %.3f), predicted delay %.3f s\n", ids[0],
+             nobs[0], fused[0].keypoints[SES3D_FBP_NOSE].x, fused[0].keypoints[SES3D_FBP_NOSE].y,
+             fused[0].keypoints[SES3D_FBP_NOSE].z, delay);
+      ses3d_prior_destroy(pr);
+    }
   }
   ses3d_destroy(h);
   return 0;

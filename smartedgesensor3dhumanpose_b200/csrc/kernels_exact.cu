@@ -158,9 +158,11 @@ cudaError_t launch_finalize(const Tables& tb, LaunchDims d, const int32_t* n_hyp
 cudaError_t launch_reproject(const Tables& tb, int n_frames, int h_max, const ses3d_person_cov* persons3d,
                              const int32_t* n_persons3d, ses3d_person2d* out, int32_t* n_out, cudaStream_t st) {
   // staging capacity in records: ~28 KB, at least one camera of h_max persons, at most the whole frame
-  int cap_rec = std::max(h_max, std::min(tb.n_cams * h_max, 64));
+  int cap_rec = std::max(h_max, std::min(tb.n_cams * h_max, 48));   // B200, hall16 x 6: 16 -> 1.25 ms, 32 -> 1.02, 48 -> 0.97, 64 -> 1.10, 96 -> 1.28
   if (const char* env = getenv("SES3D_REPROJ_CAP")) cap_rec = std::max(h_max, atoi(env));
-  const int s_cap = reproj_s_cap(tb.n_cams, h_max, 6);
+  int s_want = 6;
+  if (const char* env = getenv("SES3D_REPROJ_SCAP")) s_want = std::max(1, atoi(env));
+  const int s_cap = reproj_s_cap(tb.n_cams, h_max, s_want);
   const size_t smem = reproj_ws_bytes(tb.n_cams, cap_rec, s_cap);
   if (smem > kSmemBudget) return cudaErrorInvalidConfiguration;
   cudaError_t e = cudaFuncSetAttribute(k_reproject, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

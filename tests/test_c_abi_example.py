@@ -30,3 +30,4 @@ def test_c_client_single_frame_call_on_gpu(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "persons3d = 1" in r.stdout
+    assert "pose_prior: track 0, 12 observations" in r.stdout

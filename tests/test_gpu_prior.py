@@ -121,3 +121,13 @@ def test_demo_chain_on_gpu():
     dev = helpers.run_demo_chain(api.GeometryPipeline(fr["cameras"]), api.PriorTracker(prm, S), fr)
     check_chain_parity(fr, ref, dev)
     check_chain_physics(fr, dev)
+
+
+@pytest.mark.parametrize("case", [c[0] for c in __import__("scripts.make_golden_prior", fromlist=["CASES"]).CASES])
+def test_prior_against_committed_golden_vectors(case):
+    """The committed fixtures (tests/golden/golden_prior_v1.npz) through the C ABI: nothing here needs /root/reference."""
+    from tests.test_pose_prior import _prior_golden
+    mg, g = _prior_golden()
+    c = next(x for x in mg.CASES if x[0] == case)
+    seq, r = mg.run_case(c, make=lambda prm, S: api.PriorTracker(prm, S))
+    mg.compare(g, case, seq, r, POS_TOL, COV_RTOL)

@@ -300,3 +300,22 @@ def test_degenerate_inputs_terminate(impl):
     for t in range(6):
         a, b = r["fused"][0, t, 2]["keypoints"], clean["fused"][0, t, 2]["keypoints"]
         assert np.array_equal(a["x"], b["x"]) and np.array_equal(a["cov"], b["cov"])
+
+
+# ----------------------------------------------------------------------------- golden vectors
+def _prior_golden():
+    import scripts.make_golden_prior as mg
+    from pathlib import Path
+    return mg, np.load(Path(__file__).resolve().parent / "golden" / "golden_prior_v1.npz")
+
+
+@pytest.mark.parametrize("case", [c[0] for c in __import__("scripts.make_golden_prior", fromlist=["CASES"]).CASES])
+def test_oracle_and_device_algorithm_against_committed_golden_vectors(case):
+    """tests/golden/golden_prior_v1.npz (made by scripts/make_golden_prior.py): the oracle must reproduce it (same
+    compiler flags: within 1e-12 m) and so must the device algorithm (tree elimination: 1e-9 m)."""
+    mg, g = _prior_golden()
+    c = next(x for x in mg.CASES if x[0] == case)
+    seq, r = mg.run_case(c)
+    mg.compare(g, case, seq, r, 1e-12, 1e-9)
+    seq, r = mg.run_case(c, make=PriorHostSim)
+    mg.compare(g, case, seq, r, 1e-9, 1e-6)

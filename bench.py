@@ -359,6 +359,16 @@ def main():
                         "frac": work["bytes_per_frame"] * B / (step_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                         "algorithmic_bytes_per_frame": work["bytes_per_frame"]},
                 "traffic": None}
+    # the FMA pipe measured live on this GPU (micro-benchmark inside the library): the formula above assumes the
+    # maximum clock, the micro-benchmark shows what the pipe sustains on this box
+    try:
+        from smartedgesensor3dhumanpose_b200 import lib as _l
+        m = _l.measure_fma_peak(local_rank, fp64=False)
+        roofline["peak_measured_fma_microbench"] = m
+        roofline["frac_of_measured_fma_peak"] = achieved / m if m > 0 else None
+    except Exception as e:   # diagnostics only
+        roofline["peak_measured_fma_microbench"] = None
+        roofline["peak_measured_error"] = str(e)
     # DRAM traffic of the dominant kernel per launch from the committed ncu --set full capture of the same launch
     # shape (scripts/profile_step.py, profiles/<round>_ncu_full_summary.json); null if no matching capture
     try:

@@ -202,6 +202,11 @@ int ses3d_last_kernel_ms(ses3d_handle h, float ms[4]);
 const char* ses3d_last_error_string(void);
 const char* ses3d_version(void);
 
+/* Diagnostics: measured peak of the CUDA-core FMA pipe of `device` in TFLOP/s (fp64 = 0: FP32, 1: FP64), a
+ * micro-benchmark of independent FMA chains. The benchmarks use it as the measured roofline denominator of the
+ * FP32 / FP64 kernels (MEASURED_PEAKS.json holds HBM and tensor-core figures only). */
+int ses3d_measure_fma_peak(int32_t device, int32_t fp64, double* tflops);
+
 /* ------------------------------------------------- synthetic frame generator
  * Test/bench input source; not part of the reference. Counter
  * based (Philox4x32-10), IEEE-only arithmetic, so host and device variants are

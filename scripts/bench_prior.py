@@ -197,7 +197,10 @@ peaks = load_peaks()
 n_mean = float((seq["persons"]["keypoints"]["score"] > 0.1).sum() / max(n_fits, 1)) + 2.0   # + MidHip, Neck
 trials = (cpu["lm_stats"]["lm_inner"] / max(cpu["lm_stats"]["fits"], 1)) if cpu else 4.5
 flops_fit = n_mean * (trials * 266.0 + 300.0)
-fp64_peak = 148 * 64 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12   # 64 FP64 FMA lanes / SM / clk (B200), TFLOP/s
+fp64_nominal = 148 * 64 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12   # 64 FP64 FMA lanes / SM / clk (B200), TFLOP/s
+from smartedgesensor3dhumanpose_b200 import lib as _l  # noqa: E402
+fp64_measured = _l.measure_fma_peak(local_rank, fp64=True)       # measured on the box
+fp64_peak = fp64_measured if fp64_measured > 0 else fp64_nominal
 bytes_fit = 1684.0 * (1.0 + 2.0 * n_pub / max(n_fits, 1))      # PersonCov in; fused + pred out for published tracks (wire size)
 traffic = None
 tp = ROOT / "profiles" / "ncu_traffic.json"
@@ -216,7 +219,8 @@ out = {
                "l2_policy": f"inputs larger than L2 ({S * T * H * rec / 2**20:.0f} MiB in, {2 * S * T * H * rec / 2**20:.0f} MiB out per step)"},
     "roofline": {"bound": "fp64", "kernel": "k_prior", "achieved": n_fits * flops_fit / (ms * 1e-3) / 1e12,
                  "peak": fp64_peak, "unit": "TFLOP/s", "frac": n_fits * flops_fit / (ms * 1e-3) / 1e12 / fp64_peak,
-                 "peak_source": "148 SM x 64 FP64 lanes x 2 x sm_max_mhz (MEASURED_PEAKS.json clock)",
+                 "peak_source": "FP64 FMA micro-benchmark on this GPU (ses3d_measure_fma_peak)",
+                 "peak_nominal": fp64_nominal,
                  "algorithmic_flops_per_fit": flops_fit, "mean_variables_per_fit": n_mean, "lm_trials_per_fit": trials,
                  "kernel_ms_last_launch": kernel_ms,
                  "note": "small dependent FP64 chains: latency / issue bound, not pipe bound",

@@ -28,6 +28,7 @@ UNITS = [
     ("synth_device.cu", ["-fmad=false"]),
     ("kernels_pack.cu", []),
     ("kernels_prior.cu", []),
+    ("kernels_peak.cu", []),
     ("prior_api.cpp", []),
     ("api.cpp", []),
     ("host_setup.cpp", []),

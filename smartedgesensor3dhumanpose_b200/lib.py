@@ -16,7 +16,7 @@ EXPORTS = ("ses3d_default_params", "ses3d_create", "ses3d_destroy", "ses3d_get_t
            "ses3d_assembler_stats", "ses3d_wire_decode_person2dlist", "ses3d_wire_encode_person2dlist",
            "ses3d_wire_decode_personcovlist", "ses3d_wire_encode_personcovlist", "ses3d_prior_default_params",
            "ses3d_prior_create", "ses3d_prior_destroy", "ses3d_prior_reset", "ses3d_prior_run", "ses3d_prior_get_tracks",
-           "ses3d_prior_launch_count", "ses3d_prior_last_kernel_ms")
+           "ses3d_prior_launch_count", "ses3d_prior_last_kernel_ms", "ses3d_measure_fma_peak")
 
 
 class Ses3dError(RuntimeError):
@@ -81,8 +81,16 @@ def load():
     L.ses3d_prior_launch_count.argtypes = [vp]
     L.ses3d_prior_launch_count.restype = i64
     L.ses3d_prior_last_kernel_ms.argtypes = [vp, vp]
+    L.ses3d_measure_fma_peak.argtypes = [i32, i32, C.POINTER(C.c_double)]
     _lib = L
     return L
+
+
+def measure_fma_peak(device=0, fp64=False):
+    """Measured FMA-pipe peak of the GPU in TFLOP/s (micro-benchmark inside libses3d.so)."""
+    v = C.c_double(0)
+    check(load().ses3d_measure_fma_peak(device, int(fp64), C.byref(v)))
+    return v.value
 
 
 def check(rc):

@@ -344,6 +344,25 @@ int64_t ses3d_prior_launch_count(ses3d_prior p);
 /* Device time (ms, CUDA events) of the most recent device-buffer ses3d_prior_run. */
 int ses3d_prior_last_kernel_ms(ses3d_prior p, float* ms);
 
+/* ------------------------------------------------------------- visualisation
+ * The numeric content of the reference's rviz markers; message assembly (headers, colours, lifetimes) stays in the node.
+ *   ellipsoids [n_frames][h_max][21]  covariance ellipsoid of every joint with score > 0 (setMarkerPose S3D:279-310 ==
+ *                                     PRI:237-254): orientation quaternion + axis lengths 2 x 2.7955 x sqrt(eigenvalue);
+ *                                     all-zero for absent joints
+ *   segments   [n_frames][h_max][22][2][3]  LINE_LIST end points of the skeleton marker, n_segments [n_frames][h_max];
+ *              style 0 = skeleton_3d (S3D:898-916), 1 = pose_prior (addJointToSkeleton PRI:273-382);
+ *              segment_slot [n_frames][h_max][22] (nullable) = fusion slot whose colour the segment carries
+ * ellipsoids or segments may be NULL. */
+typedef struct ses3d_ellipsoid {
+  double qw, qx, qy, qz; /* marker.pose.orientation */
+  double sx, sy, sz;     /* marker.scale */
+} ses3d_ellipsoid;
+enum { SES3D_MARKERS_SKELETON3D = 0, SES3D_MARKERS_POSE_PRIOR = 1 };
+#define SES3D_MARKER_MAX_SEGMENTS 22
+int ses3d_markers_batch(ses3d_handle h, int32_t n_frames, int32_t h_max, const ses3d_person_cov* persons3d,
+                        const int32_t* n_persons3d, int32_t style, ses3d_ellipsoid* ellipsoids, double* segments,
+                        int32_t* n_segments, int8_t* segment_slot, uint32_t flags, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -128,6 +128,21 @@ class GeometryPipeline:
                                                       _p(n_out2d), C.byref(t3), C.byref(t2), HOST_BUFFERS))
         return t3.value, t2.value
 
+    def markers_batch(self, persons3d, n_persons3d, style=0):
+        """Numeric content of the rviz markers: covariance ellipsoids [F][H][21] (setMarkerPose
+        S3D:279-310) and skeleton LINE_LIST segments [F][H][22][2][3]; style 0 = skeleton_3d, 1 = pose_prior."""
+        from .layouts import ellipsoid_dtype
+        persons3d = np.ascontiguousarray(persons3d, dtype=person_cov_dtype)
+        F, H = persons3d.shape
+        n_persons3d = np.ascontiguousarray(n_persons3d, dtype=np.int32).reshape(F)
+        ell = np.zeros((F, H, 21), ellipsoid_dtype)
+        seg = np.zeros((F, H, 22, 2, 3), np.float64)
+        n_seg = np.zeros((F, H), np.int32)
+        slot = np.zeros((F, H, 22), np.int8)
+        _lib.check(self._L.ses3d_markers_batch(self._h, F, H, _p(persons3d), _p(n_persons3d), style, _p(ell), _p(seg),
+                                               _p(n_seg), _p(slot), HOST_BUFFERS, None))
+        return dict(ellipsoids=ell, segments=seg, n_segments=n_seg, segment_slot=slot)
+
     # ----------------------------------------------------- device-buffer calls
     # Arguments are raw device addresses (e.g. torch_tensor.data_ptr()) on this handle's GPU.
     def triangulate_device(self, n_frames, p_max, h_max, persons_ptr, n_persons_ptr, out_ptr, n_out_ptr, stream=0,

@@ -29,6 +29,7 @@ UNITS = [
     ("kernels_pack.cu", []),
     ("kernels_prior.cu", []),
     ("kernels_peak.cu", []),
+    ("kernels_markers.cu", []),
     ("prior_api.cpp", []),
     ("api.cpp", []),
     ("host_setup.cpp", []),

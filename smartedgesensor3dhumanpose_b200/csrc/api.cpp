@@ -606,6 +606,55 @@ int ses3d_process_batch_ragged(ses3d_handle h, int32_t n_frames, int32_t p_max, 
   return rc;
 }
 
+int ses3d_markers_batch(ses3d_handle h, int32_t n_frames, int32_t h_max, const ses3d_person_cov* persons3d,
+                        const int32_t* n_persons3d, int32_t style, ses3d_ellipsoid* ellipsoids, double* segments,
+                        int32_t* n_segments, int8_t* segment_slot, uint32_t flags, void* stream) {
+  if (!h) return fail(SES3D_E_INVALID, "null handle");
+  if (n_frames < 0 || h_max < 1 || h_max > 1024) return fail(SES3D_E_INVALID, "bad n_frames / h_max");
+  if (style != SES3D_MARKERS_SKELETON3D && style != SES3D_MARKERS_POSE_PRIOR) return fail(SES3D_E_INVALID, "unknown marker style");
+  if (n_frames == 0) return SES3D_OK;
+  if (!persons3d || !n_persons3d || (segments && !n_segments)) return fail(SES3D_E_INVALID, "NULL buffer");
+  std::lock_guard<std::mutex> lock(h->mu);
+  CU(cudaSetDevice(h->device));
+  const size_t units = (size_t)n_frames * h_max;
+  if (flags & SES3D_DEVICE_BUFFERS) {
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->slot[0].stream;
+    CU(ses3d::launch_markers(h->tb.model, n_frames, h_max, style, persons3d, n_persons3d, ellipsoids, segments,
+                             n_segments, segment_slot, st));
+    ++h->launches;
+    return SES3D_OK;
+  }
+  Slot& s = h->slot[0];
+  cudaStream_t st = s.stream;
+  // staging: the person records in out3d / n_out3d, the results in out2d (one allocation, carved below)
+  const size_t b_ell = ellipsoids ? units * ses3d::NFUS * sizeof(ses3d_ellipsoid) : 0;
+  const size_t b_seg = segments ? units * SES3D_MARKER_MAX_SEGMENTS * 6 * sizeof(double) : 0;
+  const size_t b_n = segments ? units * 4 : 0;
+  const size_t b_slot = (segments && segment_slot) ? (units * SES3D_MARKER_MAX_SEGMENTS + 7) / 8 * 8 : 0;
+  CU(s.out3d.ensure(units * sizeof(ses3d_person_cov)));
+  CU(s.n_out3d.ensure((size_t)n_frames * 4));
+  CU(s.out2d.ensure(b_ell + b_seg + b_n + b_slot + 64));
+  unsigned char* base = s.out2d.as<unsigned char>();
+  ses3d_ellipsoid* d_ell = ellipsoids ? reinterpret_cast<ses3d_ellipsoid*>(base) : nullptr;
+  double* d_seg = segments ? reinterpret_cast<double*>(base + b_ell) : nullptr;
+  int8_t* d_slot = b_slot ? reinterpret_cast<int8_t*>(base + b_ell + b_seg) : nullptr;
+  int32_t* d_n = segments ? reinterpret_cast<int32_t*>(base + b_ell + b_seg + b_slot) : nullptr;
+  CU(cudaMemcpyAsync(s.out3d.p, persons3d, units * sizeof(ses3d_person_cov), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(s.n_out3d.p, n_persons3d, (size_t)n_frames * 4, cudaMemcpyHostToDevice, st));
+  if (b_seg) CU(cudaMemsetAsync(base + b_ell, 0, b_seg + b_slot, st));   // unused segment slots arrive as zeros
+  CU(ses3d::launch_markers(h->tb.model, n_frames, h_max, style, s.out3d.as<ses3d_person_cov>(), s.n_out3d.as<int32_t>(),
+                           d_ell, d_seg, d_n, d_slot, st));
+  ++h->launches;
+  if (ellipsoids) CU(cudaMemcpyAsync(ellipsoids, d_ell, b_ell, cudaMemcpyDeviceToHost, st));
+  if (segments) {
+    CU(cudaMemcpyAsync(segments, d_seg, b_seg, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(n_segments, d_n, b_n, cudaMemcpyDeviceToHost, st));
+    if (segment_slot) CU(cudaMemcpyAsync(segment_slot, d_slot, units * SES3D_MARKER_MAX_SEGMENTS, cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaStreamSynchronize(st));
+  return SES3D_OK;
+}
+
 int ses3d_reserve(ses3d_handle h, int32_t n_frames, int32_t p_max, int32_t h_max) {
   int rc = check_dims(h, n_frames, p_max, h_max);
   if (rc) return rc;

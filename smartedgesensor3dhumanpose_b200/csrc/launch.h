@@ -53,3 +53,10 @@ cudaError_t launch_prior(const PriorTables& pt, int n_seq, int n_frames, int h_m
                          ses3d_person_cov* fused, ses3d_person_cov* pred, int32_t* n_out, float* pred_delay,
                          int32_t* track_of, cudaStream_t st);
 }  // namespace ses3d
+
+// K8 (kernels_markers.cu): visualisation content, one warp per (frame, person)
+namespace ses3d {
+cudaError_t launch_markers(const SkeletonModel& model, int n_frames, int h_max, int style,
+                           const ses3d_person_cov* persons3d, const int32_t* n_persons3d, ses3d_ellipsoid* ell,
+                           double* seg, int32_t* n_seg, int8_t* seg_slot, cudaStream_t st);
+}  // namespace ses3d

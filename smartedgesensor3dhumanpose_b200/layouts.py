@@ -20,6 +20,11 @@ person_cov_dtype = np.dtype([("id", "<u4"), ("score", "<f4"), ("keypoints", keyp
 camera_dtype = np.dtype([("T_cam_base", "<f8", (12,)), ("fx", "<f8"), ("fy", "<f8"), ("cx", "<f8"), ("cy", "<f8"),
                          ("Tx", "<f8"), ("Ty", "<f8"), ("width", "<u4"), ("height", "<u4")])
 
+ellipsoid_dtype = np.dtype([("qw", "<f8"), ("qx", "<f8"), ("qy", "<f8"), ("qz", "<f8"), ("sx", "<f8"), ("sy", "<f8"),
+                            ("sz", "<f8")])   # ses3d_ellipsoid: marker orientation + scale
+MARKERS_SKELETON3D, MARKERS_POSE_PRIOR = 0, 1
+MARKER_MAX_SEGMENTS = 22
+
 assert keypoint2d_dtype.itemsize == 24
 assert person2d_dtype.itemsize == 428
 assert keypoint_cov_dtype.itemsize == 80

@@ -23,6 +23,7 @@ def lib():
                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.hostsim_reproject_batch.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.c_void_p]
+        L.hostsim_markers.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 4
         L.hostsim_prior_create.restype = C.c_void_p
         L.hostsim_prior_create.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
         L.hostsim_prior_destroy.argtypes = [C.c_void_p]
@@ -79,6 +80,24 @@ class HostSim:
         lib().hostsim_reproject_batch(self._h, n_frames, h_max, cam_tile, _p(persons3d), _p(n_persons3d), _p(out),
                                       _p(n_out))
         return dict(persons2d=out, n_out=n_out)
+
+
+def _markers(call, persons3d, n_out, style):
+    from smartedgesensor3dhumanpose_b200.layouts import ellipsoid_dtype
+    persons3d = np.ascontiguousarray(persons3d, dtype=person_cov_dtype)
+    F, H = persons3d.shape
+    n_out = np.ascontiguousarray(n_out, dtype=np.int32).reshape(F)
+    ell = np.zeros((F, H, 21), ellipsoid_dtype)
+    seg = np.zeros((F, H, 22, 2, 3), np.float64)
+    n_seg = np.zeros((F, H), np.int32)
+    slot = np.zeros((F, H, 22), np.int8)
+    call(F, H, persons3d, n_out, style, ell, seg, n_seg, slot)
+    return dict(ellipsoids=ell, segments=seg, n_segments=n_seg, segment_slot=slot)
+
+
+def hostsim_markers(sim, persons3d, n_out, style=0):
+    return _markers(lambda F, H, p, n, st, e, s, ns, sl: lib().hostsim_markers(sim._h, F, H, _p(p), _p(n), st, _p(e), _p(s),
+                                                                              _p(ns), _p(sl)), persons3d, n_out, style)
 
 
 class PriorHostSim:

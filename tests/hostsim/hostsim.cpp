@@ -12,6 +12,7 @@
 #include "assoc_core.h"
 #include "fin_core.h"
 #include "host_setup.h"
+#include "markers_core.h"
 #include "prior_core.h"
 #include "reproj_core.h"
 #include "tri_core.h"
@@ -119,6 +120,24 @@ int hostsim_reproject_batch(void* h, int32_t n_frames, int32_t h_max, int32_t ca
                     n_out + (size_t)f * C);
   }
   return 0;
+}
+
+// ---- visualisation content (markers_core.h), same array shapes as ses3d_markers_batch
+void hostsim_markers(void* h, int32_t n_frames, int32_t h_max, const ses3d_person_cov* p3d, const int32_t* n_p3d,
+                     int32_t style, ses3d_ellipsoid* ell, double* seg, int32_t* n_seg, int8_t* seg_slot) {
+  Sim* s = static_cast<Sim*>(h);
+  for (int f = 0; f < n_frames; ++f)
+    for (int p = 0; p < h_max; ++p) {
+      const size_t unit = (size_t)f * h_max + p;
+      const bool live = p < n_p3d[f];
+      for (int k = 0; k < NFUS; ++k) {
+        ses3d_ellipsoid e = {0, 0, 0, 0, 0, 0, 0};
+        if (live && p3d[unit].keypoints[k].score > 0.0f) covariance_ellipsoid(p3d[unit].keypoints[k].cov, &e);
+        ell[unit * NFUS + k] = e;
+      }
+      n_seg[unit] = live ? skeleton_segments(s->tb.model, style, p3d[unit], seg + unit * MARKER_MAX_SEGMENTS * 6,
+                                             seg_slot + unit * MARKER_MAX_SEGMENTS) : 0;
+    }
 }
 
 // ---- pose_prior (prior_core.h) with a serial team: same array shapes as ses3d_prior_run --------------------------

@@ -65,8 +65,13 @@ cudaError_t launch_triangulate(const Tables& tb, LaunchDims d, const ses3d_perso
   }
   int warps = 2;   // measured on B200 (hall16 x 6): 2 warps/CTA 0.98 ms, 4: 1.00 ms, 8: 1.10 ms per 8192 frames
   if (const char* env = getenv("SES3D_TRI_WARPS")) warps = atoi(env);
-  if (tb.prm.precision == SES3D_PRECISION_FP64)
+  if (tb.prm.precision == SES3D_PRECISION_FP64) {
+    int w64 = 4;
+    if (const char* env = getenv("SES3D_TRI_WARPS_F64")) w64 = atoi(env);
+    if (w64 == 2) return launch_tri_impl<double, 2>(tb, d, persons, hyp_det, work, work_count, tmp, keep, n_sm, st);
+    if (w64 == 8) return launch_tri_impl<double, 8>(tb, d, persons, hyp_det, work, work_count, tmp, keep, n_sm, st);
     return launch_tri_impl<double, 4>(tb, d, persons, hyp_det, work, work_count, tmp, keep, n_sm, st);
+  }
   if (warps == 2) return launch_tri_impl<float, 2>(tb, d, persons, hyp_det, work, work_count, tmp, keep, n_sm, st);
   if (warps == 8) return launch_tri_impl<float, 8>(tb, d, persons, hyp_det, work, work_count, tmp, keep, n_sm, st);
   return launch_tri_impl<float, 4>(tb, d, persons, hyp_det, work, work_count, tmp, keep, n_sm, st);

@@ -411,6 +411,7 @@ def main():
         _, fps1, _, _ = cpu_reference_run(fr, min(n, max(64, int(fps / cores * 3))), 1)
         line["cpu_baseline"] = {"value": jps, "unit": UNIT, "cores": cores, "kind": kind, "frames_per_sec": fps,
                                 "single_thread_frames_per_sec": fps1,
+                                "single_thread_mean_frame_latency_ms": 1e3 / fps1 if fps1 > 0 else None,
                                 "sample": f"first {n} frames of the step's batch, frame-parallel over {cores} threads ({ms:.0f} ms)"}
     if world == 1 and not a.no_extra:
         # single-frame call latency (the ROS-shim use case), host buffers, wall clock

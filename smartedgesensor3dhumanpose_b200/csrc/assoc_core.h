@@ -322,13 +322,17 @@ SES_HD void associate_frame(Team& tm, const Tables& tb, int p_max, int h_cap, co
     ws.scal[SC_CURSOR] = c;
   });
 
-  // phase 2 - camera rounds (S3D:588-674)
+  // phase 2 - camera rounds (S3D:588-674). The rounds are sequential and, for ordinary rigs, tiny (a handful of
+  // hypotheses x detections per camera): five barriers per round on the whole CTA cost more than the work between
+  // them, so frames with few detections run all rounds on the team's first warp (warp-level barriers only); crowd
+  // rigs keep the CTA-wide version.
+  auto rounds = [&](auto& t) {
   for (int cam = ws.scal[SC_CURSOR]; cam < C; ++cam) {
     const int b0 = ws.voff[cam], n_det = ws.voff[cam + 1] - b0, n_hyp = ws.scal[SC_N_HYP];
     if (n_det == 0) continue;  // covers "no person" and "no valid person" (S3D:539-541, 608-609)
 
     // cost matrix entry = outer part of calcCost (S3D:367-389) over table lookups, observations in order
-    tm.pfor(n_hyp * n_det, [&](int e) {
+    t.pfor(n_hyp * n_det, [&](int e) {
       const int h = e % n_hyp, b = b0 + e / n_hyp;
       const int n_obs = ws.hyp_nobs[h];
       double total = 0., tmp_veto = 0.;
@@ -355,8 +359,8 @@ SES_HD void associate_frame(Team& tm, const Tables& tb, int p_max, int h_cap, co
     // provisional assignment = the last passing detection per hypothesis (S3D:616-626); the Munkres solve is
     // needed when any row or column of the mask has more than one hit (S3D:628). One thread per row / column;
     // the flag write is the same value from every writer.
-    tm.single([&] { ws.scal[SC_AMBIG] = 0; });
-    tm.pfor(n_hyp + n_det, [&](int i) {
+    t.single([&] { ws.scal[SC_AMBIG] = 0; });
+    t.pfor(n_hyp + n_det, [&](int i) {
       int cnt = 0;
       if (i < n_hyp) {
         int last = -1;
@@ -369,11 +373,11 @@ SES_HD void associate_frame(Team& tm, const Tables& tb, int p_max, int h_cap, co
       }
       if (cnt > 1) ws.scal[SC_AMBIG] = 1;
     });
-    tm.single([&] { if (ws.scal[SC_AMBIG]) ++ws.scal[SC_N_HUNG]; });
+    t.single([&] { if (ws.scal[SC_AMBIG]) ++ws.scal[SC_N_HUNG]; });
     if (ws.scal[SC_AMBIG]) {  // S3D:628-634: full Munkres on the cost matrix, solved by the team's first warp
-      tm.warp0([&](auto& wt) { munkres_coop(wt, ws, ws.cost, n_hyp, n_det, ws.assignment); });
+      t.warp0([&](auto& wt) { munkres_coop(wt, ws, ws.cost, n_hyp, n_det, ws.assignment); });
     }
-    tm.single([&] {
+    t.single([&] {
       for (int d = 0; d < n_det; ++d) ws.handled[d] = 0;
       for (int h = 0; h < n_hyp; ++h) {  // S3D:637-660
         const int d = ws.assignment[h];
@@ -390,6 +394,9 @@ SES_HD void associate_frame(Team& tm, const Tables& tb, int p_max, int h_cap, co
         if (!ws.handled[d]) add_hyp(b0 + d);
     });
   }
+  };
+  if (n_valid <= 96) tm.warp0([&](auto& w) { rounds(w); });
+  else rounds(tm);
 
   // export the hypothesis table
   const int n_hyp = ws.scal[SC_N_HYP];

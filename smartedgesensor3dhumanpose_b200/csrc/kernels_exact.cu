@@ -137,7 +137,9 @@ cudaError_t launch_associate(const Tables& tb, LaunchDims d, const ses3d_person2
   e = cudaMemsetAsync(work_count, 0, sizeof(int32_t), st);
   if (e != cudaSuccess) return e;
   if (!pair_table) return cudaErrorInvalidValue;
-  int threads = scratch ? 256 : 128;   // big rigs: hundreds of thousands of detection pairs per frame
+  // big rigs: hundreds of thousands of detection pairs per frame -> 256 threads; ordinary rigs (B200, hall16 x 6,
+  // ms per 16384 frames): 32 -> 1.66, 64 -> 1.41, 96 -> 1.37, 128 -> 1.42, 192 -> 1.67
+  int threads = scratch ? 256 : 96;
   if (const char* env = getenv("SES3D_ASSOC_THREADS")) threads = std::max(32, std::min(256, atoi(env) / 32 * 32));
   k_associate<<<d.n_frames, threads, smem, st>>>(tb, d.n_frames, d.p_max, d.h_cap, persons, n_persons,
                                                  scratch ? nk_scratch : nullptr, pair_table, hyp_det, n_hyp, n_hung,

@@ -350,11 +350,19 @@ int run_batch(ses3d_handle_s* h, int stages, int n_frames, int p_max, const ses3
       CU(cudaMemcpyAsync(n_out2d + (size_t)f0 * C, s.n_out2d.p, (size_t)nf * C * 4, cudaMemcpyDeviceToHost, st));
     }
   }
-  for (Slot& sl : h->slot) CU(cudaStreamSynchronize(sl.stream));
+  // the sticky overflow flag rides at the end of every used stream (pinned word per slot): no extra blocking copy
+  const int used = std::min(ci, (int)ses3d_handle_s::kSlots);
+  for (int i = 0; i < used; ++i) {
+    h->slot[i].totals[0] = 0;
+    CU(cudaMemcpyAsync(&h->slot[i].totals[0], h->d_overflow.p, 4, cudaMemcpyDeviceToHost, h->slot[i].stream));
+  }
+  long long overflow = 0;
+  for (int i = 0; i < used; ++i) {
+    CU(cudaStreamSynchronize(h->slot[i].stream));
+    overflow |= h->slot[i].totals[0];
+  }
   resolve_events(h);
-  int32_t overflow = 0;
-  CU(cudaMemcpy(&overflow, h->d_overflow.p, 4, cudaMemcpyDeviceToHost));
-  if (overflow) return fail(SES3D_E_CAPACITY, "a frame produced more hypotheses than h_max");
+  if (overflow) return overflow_error(h);
   return SES3D_OK;
 }
 

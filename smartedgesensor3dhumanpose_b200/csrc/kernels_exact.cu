@@ -140,6 +140,7 @@ cudaError_t launch_associate(const Tables& tb, LaunchDims d, const ses3d_person2
   // big rigs: hundreds of thousands of detection pairs per frame -> 256 threads; ordinary rigs (B200, hall16 x 6,
   // ms per 16384 frames): 32 -> 1.66, 64 -> 1.41, 96 -> 1.37, 128 -> 1.42, 192 -> 1.67
   int threads = scratch ? 256 : 96;
+  if (d.n_frames <= 296) threads = 256;   // fewer frames than two per SM: latency mode (single-frame call 75 -> 60 us)
   if (const char* env = getenv("SES3D_ASSOC_THREADS")) threads = std::max(32, std::min(256, atoi(env) / 32 * 32));
   k_associate<<<d.n_frames, threads, smem, st>>>(tb, d.n_frames, d.p_max, d.h_cap, persons, n_persons,
                                                  scratch ? nk_scratch : nullptr, pair_table, hyp_det, n_hyp, n_hung,

@@ -23,6 +23,7 @@ def lib():
                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.hostsim_reproject_batch.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.c_void_p]
+        L.hostsim_set_big_rig_path.argtypes = [C.c_int32]
         L.hostsim_markers.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 4
         L.hostsim_prior_create.restype = C.c_void_p
         L.hostsim_prior_create.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
@@ -80,6 +81,11 @@ class HostSim:
         lib().hostsim_reproject_batch(self._h, n_frames, h_max, cam_tile, _p(persons3d), _p(n_persons3d), _p(out),
                                       _p(n_out))
         return dict(persons2d=out, n_out=n_out)
+
+
+def set_big_rig_path(on):
+    """Run the association the way the kernel does for rigs whose frame does not fit shared memory."""
+    lib().hostsim_set_big_rig_path(int(on))
 
 
 def _markers(call, persons3d, n_out, style):

@@ -26,7 +26,11 @@ struct Sim {
 };
 }  // namespace
 
+static bool g_big_rig_path = false;   // association as the kernel runs it for rigs that do not fit shared memory
+
 extern "C" {
+
+void hostsim_set_big_rig_path(int32_t on) { g_big_rig_path = on != 0; }
 
 void* hostsim_create(int32_t n_cams, const ses3d_camera* cams, const ses3d_params* prm) {
   Sim* s = new Sim;
@@ -54,7 +58,9 @@ int hostsim_triangulate_batch(void* h, int32_t n_frames, int32_t p_max, const se
   Sim* s = static_cast<Sim*>(h);
   const Tables& tb = s->tb;
   const int C = tb.n_cams;
-  std::vector<unsigned char> wsa(assoc_ws_bytes(C, p_max, h_max, true) + 64), wsf(fin_ws_bytes(h_max) + 64);
+  const bool big = g_big_rig_path;   // keypoints in "global scratch", camera-pair tiled pair table
+  std::vector<unsigned char> wsa(assoc_ws_bytes(C, p_max, h_max, !big) + 64), wsf(fin_ws_bytes(h_max) + 64);
+  std::vector<float> nk_scratch(big ? (size_t)C * p_max * NKP * 2 : 0);
   const bool f64 = tb.prm.precision == SES3D_PRECISION_FP64;
   std::vector<unsigned char> wst((f64 ? tri_ws_bytes<double>(C) : tri_ws_bytes<float>(C)) + 64);
   std::vector<int8_t> hyp_det((size_t)h_max * C);
@@ -67,7 +73,8 @@ int hostsim_triangulate_batch(void* h, int32_t n_frames, int32_t p_max, const se
     const ses3d_person2d* pf = persons + (size_t)f * C * p_max;
     Arena a1(wsa.data());
     AssocWs aws;
-    assoc_ws_layout(a1, C, p_max, h_max, true, &aws);
+    assoc_ws_layout(a1, C, p_max, h_max, !big, &aws);
+    if (big) aws.nk = nk_scratch.data();
     aws.E = pair_table.data();
     int32_t n_hyp = 0, n_hung = 0;
     associate_frame(tm, tb, p_max, h_max, pf, n_persons + (size_t)f * C, aws, hyp_det.data(), &n_hyp, &n_hung, &overflow);

@@ -154,3 +154,22 @@ def test_reprojection_prefilter_is_exact_near_borders_and_behind_cameras():
         live = np.arange(H)[None, None, :] < po["n_out"][:, :, None]
         assert po["persons2d"][live].tobytes() == ph["persons2d"][live].tobytes()
         assert po["n_out"].sum() > 100
+
+
+@pytest.mark.parametrize("name,n_frames", [("cfg4_crowd64x20", 3), ("cfg2_hall16x6", 80), ("cfg3_hall16x6_dropout", 80)])
+def test_big_rig_association_path_bit_exact(name, n_frames):
+    """Rigs that do not fit shared memory use global-scratch keypoints and a camera-pair tiled pair table with hoisted
+    epipolar lines; the table (hence every association index) must be identical to the flat pass and to the oracle."""
+    from tests.hostsim import binding
+    fr = helpers.make_workload(name, n_frames)
+    ro = Oracle(fr["cameras"], ref_hungarian=True).triangulate_batch(fr["persons"], fr["n_persons"], fr["h_max"])
+    flat = HostSim(fr["cameras"]).triangulate_batch(fr["persons"], fr["n_persons"], fr["h_max"])
+    binding.set_big_rig_path(True)
+    try:
+        tiled = HostSim(fr["cameras"]).triangulate_batch(fr["persons"], fr["n_persons"], fr["h_max"])
+    finally:
+        binding.set_big_rig_path(False)
+    for key in ("hyp_of", "n_hyp", "n_hungarian", "n_out"):
+        assert np.array_equal(ro[key], tiled[key]), key
+        assert np.array_equal(flat[key], tiled[key]), key
+    assert flat["persons3d"].tobytes() == tiled["persons3d"].tobytes()

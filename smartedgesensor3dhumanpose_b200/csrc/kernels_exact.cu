@@ -26,7 +26,7 @@ k_associate(const Tables tb, int n_frames, int p_max, int h_cap, const ses3d_per
   const int C = tb.n_cams;
   Arena ar(smem_raw);
   AssocWs ws;
-  assoc_ws_layout(ar, C, p_max, h_cap, nk_scratch == nullptr, &ws);
+  assoc_ws_layout(ar, C, p_max, h_cap, nk_scratch == nullptr, &ws, (int)(blockDim.x >> 5));
   if (nk_scratch) ws.nk = nk_scratch + (size_t)f * C * p_max * NKP * 2;
   ws.E = pair_table + (size_t)f * assoc_pair_table_entries(C, p_max);
   BlockTeam tm;
@@ -114,10 +114,10 @@ cudaError_t launch_munkres_batch(int n, int rows, int cols, const double* cost, 
 static const size_t kSmemBudget = 200 * 1024;   // of the 227 KB a CTA may opt in to
 static const size_t kAssocSmemTarget = 64 * 1024;
 
-size_t associate_smem_bytes(int n_cams, int p_max, int h_cap, bool* needs_scratch) {
+size_t associate_smem_bytes(int n_cams, int p_max, int h_cap, bool* needs_scratch, int n_warps) {
   size_t b = assoc_ws_bytes(n_cams, p_max, h_cap, true);
   bool scratch = b > kAssocSmemTarget;
-  if (scratch) b = assoc_ws_bytes(n_cams, p_max, h_cap, false);
+  if (scratch) b = assoc_ws_bytes(n_cams, p_max, h_cap, false, n_warps);   // + one epipolar-line tile per warp
   if (needs_scratch) *needs_scratch = scratch;
   return b;
 }
@@ -129,7 +129,14 @@ cudaError_t launch_associate(const Tables& tb, LaunchDims d, const ses3d_person2
                              int32_t* overflow, int32_t* hyp_of_dump, int32_t* keep, uint32_t* work,
                              int32_t* work_count, cudaStream_t st) {
   bool scratch;
-  const size_t smem = associate_smem_bytes(tb.n_cams, d.p_max, d.h_cap, &scratch);
+  associate_smem_bytes(tb.n_cams, d.p_max, d.h_cap, &scratch, 1);
+  // big rigs: hundreds of thousands of detection pairs per frame, one warp per camera-pair tile -> 128 threads
+  // (shared memory per warp decides); ordinary rigs (B200, hall16 x 6, ms per 16384 frames): 32 -> 1.66, 64 -> 1.41,
+  // 96 -> 1.37, 128 -> 1.42, 192 -> 1.67
+  int threads = scratch ? 128 : 96;
+  if (!scratch && d.n_frames <= 296) threads = 256;   // fewer frames than two per SM: latency mode (single-frame call 75 -> 60 us)
+  if (const char* env = getenv("SES3D_ASSOC_THREADS")) threads = std::max(32, std::min(256, atoi(env) / 32 * 32));
+  const size_t smem = associate_smem_bytes(tb.n_cams, d.p_max, d.h_cap, &scratch, threads / 32);
   if (smem > kSmemBudget) return cudaErrorInvalidConfiguration;
   if (scratch && !nk_scratch) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(k_associate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -137,11 +144,6 @@ cudaError_t launch_associate(const Tables& tb, LaunchDims d, const ses3d_person2
   e = cudaMemsetAsync(work_count, 0, sizeof(int32_t), st);
   if (e != cudaSuccess) return e;
   if (!pair_table) return cudaErrorInvalidValue;
-  // big rigs: hundreds of thousands of detection pairs per frame -> 256 threads; ordinary rigs (B200, hall16 x 6,
-  // ms per 16384 frames): 32 -> 1.66, 64 -> 1.41, 96 -> 1.37, 128 -> 1.42, 192 -> 1.67
-  int threads = scratch ? 256 : 96;
-  if (d.n_frames <= 296) threads = 256;   // fewer frames than two per SM: latency mode (single-frame call 75 -> 60 us)
-  if (const char* env = getenv("SES3D_ASSOC_THREADS")) threads = std::max(32, std::min(256, atoi(env) / 32 * 32));
   k_associate<<<d.n_frames, threads, smem, st>>>(tb, d.n_frames, d.p_max, d.h_cap, persons, n_persons,
                                                  scratch ? nk_scratch : nullptr, pair_table, hyp_det, n_hyp, n_hung,
                                                  overflow, hyp_of_dump, keep, work, work_count);
@@ -161,7 +163,7 @@ cudaError_t launch_finalize(const Tables& tb, LaunchDims d, const int32_t* n_hyp
 cudaError_t launch_reproject(const Tables& tb, int n_frames, int h_max, const ses3d_person_cov* persons3d,
                              const int32_t* n_persons3d, ses3d_person2d* out, int32_t* n_out, cudaStream_t st) {
   // staging capacity in records: ~28 KB, at least one camera of h_max persons, at most the whole frame
-  int cap_rec = std::max(h_max, std::min(tb.n_cams * h_max, 48));   // B200, hall16 x 6: 16 -> 1.25 ms, 32 -> 1.02, 48 -> 0.97, 64 -> 1.10, 96 -> 1.28
+  int cap_rec = std::max(h_max, std::min(tb.n_cams * h_max, std::max(48, 2 * h_max)));   // B200, hall16 x 6: 16 -> 1.25 ms, 32 -> 1.02, 48 -> 0.97, 64 -> 1.10, 96 -> 1.28
   if (const char* env = getenv("SES3D_REPROJ_CAP")) cap_rec = std::max(h_max, atoi(env));
   int s_want = 6;
   if (const char* env = getenv("SES3D_REPROJ_SCAP")) s_want = std::max(1, atoi(env));

@@ -44,14 +44,12 @@ struct AssocWs {
   uint8_t *cov_r, *cov_c, *handled;      // [h_cap], [p_max], [p_max]
   int* assignment;    // [h_cap]
   int* scal;          // [SC_COUNT]
-  float* lines;       // [n_warps][2][p_max][17][4] epipolar lines (x, y, z, norm) of the camera pair a warp is working
-                      //   on; nullptr = flat pass
 };
 
 // Lays the shared-memory workspace out; nk_inside = false keeps the keypoints in global scratch
 // (rigs whose frame does not fit in shared memory).
 template <class A>
-SES_HD void assoc_ws_layout(A& ar, int C, int p_max, int h_cap, bool nk_inside, AssocWs* ws, int n_warps = 1) {
+SES_HD void assoc_ws_layout(A& ar, int C, int p_max, int h_cap, bool nk_inside, AssocWs* ws) {
   double* cost = ar.template take<double>((size_t)h_cap * p_max);
   double* dist = ar.template take<double>((size_t)h_cap * p_max);
   float* nk = nk_inside ? ar.template take<float>((size_t)C * p_max * NKP * 2) : nullptr;
@@ -71,9 +69,7 @@ SES_HD void assoc_ws_layout(A& ar, int C, int p_max, int h_cap, bool nk_inside, 
   uint8_t* cov_r = ar.template take<uint8_t>(h_cap);
   uint8_t* cov_c = ar.template take<uint8_t>(p_max);
   uint8_t* handled = ar.template take<uint8_t>(p_max);
-  float* lines = nk_inside ? nullptr : ar.template take<float>((size_t)n_warps * 2 * p_max * NKP * 4);   // big rigs only
   if (ws) {
-    ws->lines = lines;
     ws->cost = cost; ws->dist = dist; if (nk_inside) ws->nk = nk; ws->kmask = kmask; ws->pscore = pscore;
     ws->assignment = assignment; ws->scal = scal; ws->hyp_obs = hyp_obs; ws->vslot = vslot; ws->voff = voff;
     ws->valid = valid; ws->hyp_nobs = hyp_nobs; ws->mask = mask; ws->star = star; ws->prime = prime;
@@ -81,9 +77,9 @@ SES_HD void assoc_ws_layout(A& ar, int C, int p_max, int h_cap, bool nk_inside, 
   }
 }
 
-inline size_t assoc_ws_bytes(int C, int p_max, int h_cap, bool nk_inside, int n_warps = 1) {
+inline size_t assoc_ws_bytes(int C, int p_max, int h_cap, bool nk_inside) {
   ArenaSizer s;
-  assoc_ws_layout(s, C, p_max, h_cap, nk_inside, nullptr, n_warps);
+  assoc_ws_layout(s, C, p_max, h_cap, nk_inside, nullptr);
   return (s.used + 15) / 16 * 16;
 }
 
@@ -277,68 +273,7 @@ SES_HD void associate_frame(Team& tm, const Tables& tb, int p_max, int h_cap, co
   tm.pfor(n_valid, [&](int a) { ws.pscore[a] = persons[ws.vslot[a]].score; });
 
   // phase 1 - pair table: mean symmetric epipolar distance of every cross-camera pair of valid detections,
-  // the inner loop of calcCost (S3D:347-368), joints in ascending order, float distances summed in double.
-  if (ws.lines) {
-    // Big rigs (hundreds of thousands of pairs per frame): camera pair by camera pair, one warp per camera pair (no
-    // CTA barrier). The epipolar line of a keypoint in the other camera, l1 = F p1 (resp. l2 = F^T p2), and its norm
-    // depend on one detection and the camera pair only, so they are computed once per (detection, joint) and reused
-    // by all p_max partners: ~33 instead of ~85 instructions per joint pair, the same operations in the same order
-    // (bit-identical table).
-    tm.per_warp(C * (C - 1) / 2, [&](auto& w, int cp) {
-      // cp -> (ca, cb), ca < cb: row cb of the strictly lower triangle starts at cb(cb-1)/2
-      int cb = (int)((1.0f + ses_sqrt(1.0f + 8.0f * (float)cp)) * 0.5f);
-      while (cb * (cb - 1) / 2 > cp) --cb;
-      while ((cb + 1) * cb / 2 <= cp) ++cb;
-      const int ca = cp - cb * (cb - 1) / 2;
-      const int a0 = ws.voff[ca], nA = ws.voff[ca + 1] - a0;
-      const int b0 = ws.voff[cb], nB = ws.voff[cb + 1] - b0;
-      if (nA == 0 || nB == 0) return;
-      const int wid = w.size() == 1 ? 0 : (tm.rank() / 32);
-      float* lines = ws.lines + (size_t)wid * 2 * p_max * NKP * 4;
-      const float* F = tb.F + (size_t)fundamental_idx(tb, ca, cb) * 9;
-      w.pfor((nA + nB) * NKP, [&](int it) {
-        const int k = it % NKP, i = it / NKP;
-        const bool sideA = i < nA;
-        const int s = ws.vslot[sideA ? a0 + i : b0 + (i - nA)];
-        if (!((ws.kmask[s] >> k) & 1u)) return;
-        const float x = ws.nk[((size_t)s * NKP + k) * 2], y = ws.nk[((size_t)s * NKP + k) * 2 + 1];
-        float lx, ly, lz;
-        if (sideA) {
-          lx = sum3(F[0] * x, F[1] * y, F[2] * 1.0f); ly = sum3(F[3] * x, F[4] * y, F[5] * 1.0f);
-          lz = sum3(F[6] * x, F[7] * y, F[8] * 1.0f);
-        } else {
-          lx = sum3(F[0] * x, F[3] * y, F[6] * 1.0f); ly = sum3(F[1] * x, F[4] * y, F[7] * 1.0f);
-          lz = sum3(F[2] * x, F[5] * y, F[8] * 1.0f);
-        }
-        float* L = lines + ((size_t)((sideA ? 0 : p_max) + (sideA ? i : i - nA)) * NKP + k) * 4;
-        L[0] = lx; L[1] = ly; L[2] = lz; L[3] = ses_sqrt(lx * lx + ly * ly);
-      });
-      w.pfor(nA * nB, [&](int it) {
-        const int i = it % nA, j = it / nA;
-        const int a = a0 + i, b = b0 + j;
-        const int sa = ws.vslot[a], sb = ws.vslot[b];
-        const float* hk = ws.nk + ((size_t)sa * NKP) * 2;
-        const float* dk = ws.nk + ((size_t)sb * NKP) * 2;
-        const float* L1 = lines + (size_t)i * NKP * 4;
-        const float* L2 = lines + (size_t)(p_max + j) * NKP * 4;
-        uint32_t m = ws.kmask[sa] & ws.kmask[sb];
-        double cost = 0.;
-        int n_joints = 0;
-        while (m) {
-          const int k = ses_ctz(m);
-          m &= m - 1;
-          const float x1 = hk[2 * k], y1 = hk[2 * k + 1], x2 = dk[2 * k], y2 = dk[2 * k + 1];
-          const float* l1 = L1 + k * 4;
-          const float* l2 = L2 + k * 4;
-          const float d1 = ses_abs(sum3(x2 * l1[0], y2 * l1[1], 1.0f * l1[2])) / l1[3];
-          const float d2 = ses_abs(sum3(x1 * l2[0], y1 * l2[1], 1.0f * l2[2])) / l2[3];
-          cost += static_cast<double>(d1 + d2);
-          ++n_joints;
-        }
-        ws.E[(size_t)b * (b - 1) / 2 + a] = n_joints > 0 ? cost / n_joints : -1.0;
-      });
-    });
-  } else
+  // the inner loop of calcCost (S3D:347-368), joints in ascending order, float distances summed in double
   tm.pfor(n_valid * (n_valid - 1) / 2, [&](int e) {
     // e -> (a, b), a < b: row b of the strictly lower triangle starts at b(b-1)/2
     int b = (int)((1.0f + ses_sqrt(1.0f + 8.0f * (float)e)) * 0.5f);

@@ -26,7 +26,7 @@ k_associate(const Tables tb, int n_frames, int p_max, int h_cap, const ses3d_per
   const int C = tb.n_cams;
   Arena ar(smem_raw);
   AssocWs ws;
-  assoc_ws_layout(ar, C, p_max, h_cap, nk_scratch == nullptr, &ws, (int)(blockDim.x >> 5));
+  assoc_ws_layout(ar, C, p_max, h_cap, nk_scratch == nullptr, &ws);
   if (nk_scratch) ws.nk = nk_scratch + (size_t)f * C * p_max * NKP * 2;
   ws.E = pair_table + (size_t)f * assoc_pair_table_entries(C, p_max);
   BlockTeam tm;
@@ -114,10 +114,10 @@ cudaError_t launch_munkres_batch(int n, int rows, int cols, const double* cost, 
 static const size_t kSmemBudget = 200 * 1024;   // of the 227 KB a CTA may opt in to
 static const size_t kAssocSmemTarget = 64 * 1024;
 
-size_t associate_smem_bytes(int n_cams, int p_max, int h_cap, bool* needs_scratch, int n_warps) {
+size_t associate_smem_bytes(int n_cams, int p_max, int h_cap, bool* needs_scratch) {
   size_t b = assoc_ws_bytes(n_cams, p_max, h_cap, true);
   bool scratch = b > kAssocSmemTarget;
-  if (scratch) b = assoc_ws_bytes(n_cams, p_max, h_cap, false, n_warps);   // + one epipolar-line tile per warp
+  if (scratch) b = assoc_ws_bytes(n_cams, p_max, h_cap, false);
   if (needs_scratch) *needs_scratch = scratch;
   return b;
 }
@@ -129,15 +129,13 @@ cudaError_t launch_associate(const Tables& tb, LaunchDims d, const ses3d_person2
                              int32_t* overflow, int32_t* hyp_of_dump, int32_t* keep, uint32_t* work,
                              int32_t* work_count, cudaStream_t st) {
   bool scratch;
-  associate_smem_bytes(tb.n_cams, d.p_max, d.h_cap, &scratch, 1);
-  // big rigs: hundreds of thousands of detection pairs per frame, one warp per camera-pair tile -> 128 threads
-  // (shared memory per warp decides); ordinary rigs (B200, hall16 x 6, ms per 16384 frames): 32 -> 1.66, 64 -> 1.41,
-  // 96 -> 1.37, 128 -> 1.42, 192 -> 1.67
-  int threads = scratch ? 128 : 96;
-  if (!scratch && d.n_frames <= 296) threads = 256;   // fewer frames than two per SM: latency mode (single-frame call 75 -> 60 us)
-  if (const char* env = getenv("SES3D_ASSOC_THREADS")) threads = std::max(32, std::min(256, atoi(env) / 32 * 32));
-  const size_t smem = associate_smem_bytes(tb.n_cams, d.p_max, d.h_cap, &scratch, threads / 32);
+  const size_t smem = associate_smem_bytes(tb.n_cams, d.p_max, d.h_cap, &scratch);
   if (smem > kSmemBudget) return cudaErrorInvalidConfiguration;
+  // big rigs: hundreds of thousands of detection pairs per frame -> 256 threads; ordinary rigs (B200, hall16 x 6,
+  // ms per 16384 frames): 32 -> 1.66, 64 -> 1.41, 96 -> 1.37, 128 -> 1.42, 192 -> 1.67
+  int threads = scratch ? 256 : 96;
+  if (d.n_frames <= 296) threads = 256;   // fewer frames than two per SM: latency mode (single-frame call 75 -> 60 us)
+  if (const char* env = getenv("SES3D_ASSOC_THREADS")) threads = std::max(32, std::min(256, atoi(env) / 32 * 32));
   if (scratch && !nk_scratch) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(k_associate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

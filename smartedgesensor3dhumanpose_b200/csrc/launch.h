@@ -15,7 +15,7 @@ cudaError_t launch_associate(const Tables& tb, LaunchDims d, const ses3d_person2
                              float* nk_scratch, double* pair_table, int8_t* hyp_det, int32_t* n_hyp, int32_t* n_hung,
                              int32_t* overflow, int32_t* hyp_of_dump, int32_t* keep, uint32_t* work,
                              int32_t* work_count, cudaStream_t st);
-size_t associate_smem_bytes(int n_cams, int p_max, int h_cap, bool* needs_scratch, int n_warps = 8);
+size_t associate_smem_bytes(int n_cams, int p_max, int h_cap, bool* needs_scratch);
 size_t associate_pair_table_bytes(int n_cams, int p_max);   // per frame
 
 // K3: one warp per (frame, hypothesis) work item, persistent grid over the work list K2 wrote

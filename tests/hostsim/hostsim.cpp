@@ -58,7 +58,7 @@ int hostsim_triangulate_batch(void* h, int32_t n_frames, int32_t p_max, const se
   Sim* s = static_cast<Sim*>(h);
   const Tables& tb = s->tb;
   const int C = tb.n_cams;
-  const bool big = g_big_rig_path;   // keypoints in "global scratch", camera-pair tiled pair table
+  const bool big = g_big_rig_path;   // keypoints in "global scratch"
   std::vector<unsigned char> wsa(assoc_ws_bytes(C, p_max, h_max, !big) + 64), wsf(fin_ws_bytes(h_max) + 64);
   std::vector<float> nk_scratch(big ? (size_t)C * p_max * NKP * 2 : 0);
   const bool f64 = tb.prm.precision == SES3D_PRECISION_FP64;

@@ -158,8 +158,8 @@ def test_reprojection_prefilter_is_exact_near_borders_and_behind_cameras():
 
 @pytest.mark.parametrize("name,n_frames", [("cfg4_crowd64x20", 3), ("cfg2_hall16x6", 80), ("cfg3_hall16x6_dropout", 80)])
 def test_big_rig_association_path_bit_exact(name, n_frames):
-    """Rigs that do not fit shared memory use global-scratch keypoints and a camera-pair tiled pair table with hoisted
-    epipolar lines; the table (hence every association index) must be identical to the flat pass and to the oracle."""
+    """Rigs that do not fit shared memory keep the normalised keypoints in global scratch; every association index and
+    record must be identical to the shared-memory path and to the oracle."""
     from tests.hostsim import binding
     fr = helpers.make_workload(name, n_frames)
     ro = Oracle(fr["cameras"], ref_hungarian=True).triangulate_batch(fr["persons"], fr["n_persons"], fr["h_max"])

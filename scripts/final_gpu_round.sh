@@ -13,3 +13,7 @@ import json
 for f in ['bench_r01_reference','bench_r01','bench_r01_dense']:
     d=json.load(open('gpurun_out/'+f+'.json')); print(f, d['value'], d.get('frames_per_sec'), d.get('ms_per_step'), d.get('e2e',{}).get('value'))
 "
+python scripts/run_configs.py --out gpurun_out/configs_r01.json > gpurun_out/configs_log.txt 2>&1; tail -2 gpurun_out/configs_log.txt
+python scripts/bench_prior.py > gpurun_out/bench_prior_r01.json 2>gpurun_out/bench_prior_err.log
+python scripts/bench_chain.py > gpurun_out/bench_chain_r01.json 2>gpurun_out/err_chain.log
+python scripts/latency_probe.py > gpurun_out/latency_r01.txt 2>&1; tail -3 gpurun_out/latency_r01.txt

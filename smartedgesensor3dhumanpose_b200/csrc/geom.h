@@ -12,6 +12,9 @@
 
 namespace ses3d {
 
+SES_HD double ses_rsqrt(double x);
+SES_HD double ses_rcp(double x);
+
 // order of the 10 unique entries of a symmetric 4x4: 00 01 02 03 11 12 13 22 23 33
 template <class T>
 SES_HD void dlt_row(const T* P, int which /*0: x-row, 1: y-row*/, T m, T weight, bool weighted, T r[4]) {
@@ -22,8 +25,16 @@ SES_HD void dlt_row(const T* P, int which /*0: x-row, 1: y-row*/, T m, T weight,
   r[3] = m * P[11] - P[which * 4 + 3];
   const T z = sum4(r[0] * r[0], r[1] * r[1], r[2] * r[2], r[3] * r[3]);
   if (z > T(0)) {
-    const T nrm = ses_sqrt(z);
-    r[0] /= nrm; r[1] /= nrm; r[2] /= nrm; r[3] /= nrm;
+#if defined(__CUDA_ARCH__)
+    if (sizeof(T) == 8) {   // FP64 mode (tolerance-checked): one refined reciprocal square root instead of sqrt + 4 divides
+      const T inv = (T)ses_rsqrt((double)z);
+      r[0] *= inv; r[1] *= inv; r[2] *= inv; r[3] *= inv;
+    } else
+#endif
+    {
+      const T nrm = ses_sqrt(z);
+      r[0] /= nrm; r[1] /= nrm; r[2] /= nrm; r[3] /= nrm;
+    }
   }
   if (weighted) { r[0] *= weight; r[1] *= weight; r[2] *= weight; r[3] *= weight; }
 }
@@ -177,7 +188,21 @@ SES_HD float ses_rcp(float x) {
   return 1.0f / x;
 #endif
 }
-SES_HD double ses_rcp(double x) { return 1.0 / x; }
+// FP64 mode on the GPU: an IEEE double division / square root expands to ~20 instructions with a long dependency chain.
+// A single-precision SFU seed refined by two Newton steps in double is accurate to ~1 ulp (seed error 2e-7 ->
+// 6e-14 -> 1e-16) at a third of the cost; arguments outside the comfortable float range take the exact path.
+SES_HD double ses_rcp(double x) {
+#if defined(__CUDA_ARCH__)
+  const double ax = fabs(x);
+  if (ax > 1e-30 && ax < 1e30) {
+    double y = (double)__frcp_rn((float)x);
+    y = y * (2.0 - x * y);
+    y = y * (2.0 - x * y);
+    return y;
+  }
+#endif
+  return 1.0 / x;
+}
 SES_HD float ses_rsqrt(float x) {
 #if defined(__CUDA_ARCH__)
   return rsqrtf(x);
@@ -185,7 +210,17 @@ SES_HD float ses_rsqrt(float x) {
   return 1.0f / sqrtf(x);
 #endif
 }
-SES_HD double ses_rsqrt(double x) { return 1.0 / sqrt(x); }
+SES_HD double ses_rsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+  if (x > 1e-30 && x < 1e30) {
+    double y = (double)rsqrtf((float)x);
+    y = y * (1.5 - 0.5 * x * y * y);
+    y = y * (1.5 - 0.5 * x * y * y);
+    return y;
+  }
+#endif
+  return 1.0 / sqrt(x);
+}
 
 // Smallest eigenvector (unit length) of the symmetric PSD 4x4 matrix G by inverse iteration.
 template <class T>

@@ -197,7 +197,8 @@ SES_HD void lm_refine_joint(const Tables& tb, const TriWs<T>& ws, int k, const u
       const T a = P[0] * Y[0] + P[1] * Y[1] + P[2] * Y[2] + P[3];
       const T b = P[4] * Y[0] + P[5] * Y[1] + P[6] * Y[2] + P[7];
       const T c = P[8] * Y[0] + P[9] * Y[1] + P[10] * Y[2] + P[11];
-      const T rx = v.conf * (a / c - v.x), ry = v.conf * (b / c - v.y);
+      const T ic = ses_rcp(c);
+      const T rx = v.conf * (a * ic - v.x), ry = v.conf * (b * ic - v.y);
       f += rx * rx + ry * ry;
     }
     return f;
@@ -213,7 +214,7 @@ SES_HD void lm_refine_joint(const Tables& tb, const TriWs<T>& ws, int k, const u
       const T a = P[0] * X[0] + P[1] * X[1] + P[2] * X[2] + P[3];
       const T b = P[4] * X[0] + P[5] * X[1] + P[6] * X[2] + P[7];
       const T c = P[8] * X[0] + P[9] * X[1] + P[10] * X[2] + P[11];
-      const T ic = T(1) / c, u = a * ic, vv = b * ic;
+      const T ic = ses_rcp(c), u = a * ic, vv = b * ic;
       const T rx = v.conf * (u - v.x), ry = v.conf * (vv - v.y);
       const T jx0 = v.conf * ic * (P[0] - u * P[8]), jx1 = v.conf * ic * (P[1] - u * P[9]),
               jx2 = v.conf * ic * (P[2] - u * P[10]);

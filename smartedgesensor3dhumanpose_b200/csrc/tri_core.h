@@ -137,11 +137,23 @@ SES_HD void cholesky_cov(const Tables& tb, int cam, const ses3d_keypoint2d& kp, 
 }
 SES_HD void cholesky_cov(const Tables& tb, int cam, const ses3d_keypoint2d& kp, double& l11, double& l21, double& l22) {
   const CamD& cm = tb.camd[cam];
+#if defined(__CUDA_ARCH__)
+  // covariance-only path (tolerance-checked): refined reciprocals instead of 4 IEEE divides + 2 square roots;
+  // a zero variance still yields NaN like the reference's 0/0 (S3D:473-475)
+  const double ifx = ses_rcp(cm.fx), ify = ses_rcp(cm.fy);
+  const double cxx = (double)kp.cov[0] * (ifx * ifx), cxy = (double)kp.cov[1] * (ifx * ify), cyy = (double)kp.cov[2] * (ify * ify);
+  const double r11 = ses_rsqrt(cxx);
+  l11 = cxx * r11;
+  l21 = cxy * r11;
+  const double t = cyy - l21 * l21;
+  l22 = t * ses_rsqrt(t);
+#else
   const double cxx = (double)kp.cov[0] / (cm.fx * cm.fx), cxy = (double)kp.cov[1] / (cm.fx * cm.fy),
                cyy = (double)kp.cov[2] / (cm.fy * cm.fy);
   l11 = sqrt(cxx);
   l21 = cxy / l11;
   l22 = sqrt(cyy - l21 * l21);
+#endif
 }
 
 // confidence-weighted mean reprojection error, calcReprojectionError S3D:425-438
@@ -181,7 +193,8 @@ SES_HD void solve_weighted(const Tables& tb, const TriWs<T>& ws, int k, const ui
   }
   T e[4];
   smallest_eigvec4_fast<T>(G, e);
-  X[0] = e[0] / e[3]; X[1] = e[1] / e[3]; X[2] = e[2] / e[3];
+  const T ie3 = ses_rcp(e[3]);   // hnormalized(), S3D:459
+  X[0] = e[0] * ie3; X[1] = e[1] * ie3; X[2] = e[2] * ie3;
   *err = reproj_error<T>(tb, ws, k, list, n, skip, X);
 }
 
@@ -446,7 +459,8 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
     // sigma point 0 (unperturbed, unweighted) contributes w0 * (y0 - m)(y0 - m)^T   (S3D:521-522)
     const T wden = T(2) * (T(2 * n) + T(0.5));
     const T w0 = (T(2) * T(0.5)) / wden;
-    const T d0 = e[0] / e[3] - X[0], d1 = e[1] / e[3] - X[1], d2 = e[2] / e[3] - X[2];
+    const T ie3 = ses_rcp(e[3]);
+    const T d0 = e[0] * ie3 - X[0], d1 = e[1] * ie3 - X[1], d2 = e[2] * ie3 - X[2];
     T* cv = ws.cov + k * 6;
     cv[0] = (d0 * w0) * d0; cv[1] = (d0 * w0) * d1; cv[2] = (d0 * w0) * d2;
     cv[3] = (d1 * w0) * d1; cv[4] = (d1 * w0) * d2; cv[5] = (d2 * w0) * d2;

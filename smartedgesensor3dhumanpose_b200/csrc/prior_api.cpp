@@ -157,7 +157,7 @@ int ses3d_prior_run(ses3d_prior h, int32_t n_sequences, int32_t n_frames, int32_
   if (n_sequences < 0 || n_sequences > h->n_sequences)
     return ses3d::set_error(SES3D_E_INVALID, "ses3d_prior_run: n_sequences exceeds the handle's");
   if (n_frames < 0 || h_max < 1 || h_max > 64) return ses3d::set_error(SES3D_E_INVALID, "ses3d_prior_run: bad n_frames / h_max");
-  if (n_cams < 0 || (n_cams > 0 && false)) return ses3d::set_error(SES3D_E_INVALID, "ses3d_prior_run: bad n_cams");
+  if (n_cams < 0) return ses3d::set_error(SES3D_E_INVALID, "ses3d_prior_run: n_cams < 0");
   if (n_sequences == 0 || n_frames == 0) return SES3D_OK;
   if (!persons || !n_persons || !stamp_ns || !fused || !pred || !n_out)
     return ses3d::set_error(SES3D_E_INVALID, "ses3d_prior_run: NULL buffer");

@@ -124,7 +124,8 @@ struct PriorFitWs {       // the factor graphs of one group, one workspace per w
   double *m, *x, *w, *z;             // [G*21][3]
   double* guy;                       // [G*21][6]: gu (gradient of the unary factor) | y = Dinv b, overwritten in place
                                      //            by delta in the back-substitution; later the marginal Sg
-  double *W, *Dinv;                  // [G*21][6]  (00,01,02,11,12,22): information of the unary factor; block inverse
+  double* W;                         // [G*21][6]  (00,01,02,11,12,22): information of the unary factor; the marginal
+                                     //            elimination overwrites it with the block inverse D^-1
   double *e, *alpha, *beta;          // [G*21]
   double *ta, *tb;                   // [G*21] per-joint error terms; alias alpha / beta (never live together)
   int8_t* par;                       // [G*21] parent joint of the bone, -1 none
@@ -137,8 +138,8 @@ SES_HD void prior_fit_ws_layout(A& ar, int G, PriorFitWs* ws) {
   const size_t n = (size_t)G * NFUS;
   double* v3[4];
   for (int i = 0; i < 4; ++i) v3[i] = ar.template take<double>(n * 3);
-  double* v6[3];
-  for (int i = 0; i < 3; ++i) v6[i] = ar.template take<double>(n * 6);
+  double* v6[2];
+  for (int i = 0; i < 2; ++i) v6[i] = ar.template take<double>(n * 6);
   double* v1[3];
   for (int i = 0; i < 3; ++i) v1[i] = ar.template take<double>(n);
   PriorFitScal* sc = ar.template take<PriorFitScal>(G);
@@ -147,7 +148,7 @@ SES_HD void prior_fit_ws_layout(A& ar, int G, PriorFitWs* ws) {
   uint8_t* usev = ar.template take<uint8_t>(n);
   if (ws) {
     ws->m = v3[0]; ws->x = v3[1]; ws->w = v3[2]; ws->z = v3[3];
-    ws->guy = v6[0]; ws->W = v6[1]; ws->Dinv = v6[2];
+    ws->guy = v6[0]; ws->W = v6[1];
     ws->e = v1[0]; ws->alpha = v1[1]; ws->beta = v1[2]; ws->ta = v1[1]; ws->tb = v1[2];
     ws->sc = sc; ws->par = par; ws->msd = msd; ws->usev = usev;
   }
@@ -395,11 +396,13 @@ SES_HD void prior_eliminate(WT& tm, const PriorTables& pt, int G, const PriorFit
         D[3] += f * wc[1] * wc[1]; D[4] += f * wc[1] * wc[2]; D[5] += f * wc[2] * wc[2];
         b[0] += q * wc[0]; b[1] += q * wc[1]; b[2] += q * wc[2];
       }
-      double* I = ws.Dinv + 6 * i;
+      double I[6];
       if (!sym6_inverse_spd(D, I)) {
         sc.fail = 1;
         I[0] = I[3] = I[5] = 1.0; I[1] = I[2] = I[4] = 0.0;
       }
+      if (for_marginals)   // W is dead after this point of the marginal pass: keep D^-1 in its place
+        for (int a = 0; a < 6; ++a) ws.W[6 * i + a] = I[a];
       double* z = ws.z + 3 * i;
       double* y = ws.guy + 6 * i + 3;
       sym6_mul(I, w, z);
@@ -441,7 +444,7 @@ SES_HD void prior_marginals(WT& tm, const PriorTables& pt, int G, const PriorFit
       if (k < 0 || !ws.sc[g].active || !ws.sc[g].use_marginals) return;
       const int i = g * NFUS + k;
       if (!ws.msd[i]) return;
-      const double* I = ws.Dinv + 6 * i;
+      const double* I = ws.W + 6 * i;   // D^-1, stored by the marginal elimination
       double* S = ws.guy + 6 * i;
       double q = 0.0;
       const int p = ws.par[i];

@@ -121,9 +121,9 @@ struct PriorFitScal {           // LM / bookkeeping state of one detection of th
 };
 
 struct PriorFitWs {       // the factor graphs of one group, one workspace per warp; index i = g * 21 + joint
-  double *m, *x, *w, *z;             // [G*21][3]
-  double* guy;                       // [G*21][6]: gu (gradient of the unary factor) | y = Dinv b, overwritten in place
-                                     //            by delta in the back-substitution; later the marginal Sg
+  double *x, *w, *z;                 // [G*21][3]
+  double* my;                        // [G*21][6]: measurement m | y = Dinv b, overwritten in place by delta in the
+                                     //            back-substitution; the marginal pass ends by writing Sigma over both
   double* W;                         // [G*21][6]  (00,01,02,11,12,22): information of the unary factor; the marginal
                                      //            elimination overwrites it with the block inverse D^-1
   double *e, *alpha, *beta;          // [G*21]
@@ -136,8 +136,8 @@ struct PriorFitWs {       // the factor graphs of one group, one workspace per w
 template <class A>
 SES_HD void prior_fit_ws_layout(A& ar, int G, PriorFitWs* ws) {
   const size_t n = (size_t)G * NFUS;
-  double* v3[4];
-  for (int i = 0; i < 4; ++i) v3[i] = ar.template take<double>(n * 3);
+  double* v3[3];
+  for (int i = 0; i < 3; ++i) v3[i] = ar.template take<double>(n * 3);
   double* v6[2];
   for (int i = 0; i < 2; ++i) v6[i] = ar.template take<double>(n * 6);
   double* v1[3];
@@ -147,8 +147,8 @@ SES_HD void prior_fit_ws_layout(A& ar, int G, PriorFitWs* ws) {
   uint8_t* msd = ar.template take<uint8_t>(n);
   uint8_t* usev = ar.template take<uint8_t>(n);
   if (ws) {
-    ws->m = v3[0]; ws->x = v3[1]; ws->w = v3[2]; ws->z = v3[3];
-    ws->guy = v6[0]; ws->W = v6[1];
+    ws->x = v3[0]; ws->w = v3[1]; ws->z = v3[2];
+    ws->my = v6[0]; ws->W = v6[1];
     ws->e = v1[0]; ws->alpha = v1[1]; ws->beta = v1[2]; ws->ta = v1[1]; ws->tb = v1[2];
     ws->sc = sc; ws->par = par; ws->msd = msd; ws->usev = usev;
   }
@@ -376,7 +376,13 @@ SES_HD void prior_eliminate(WT& tm, const PriorTables& pt, int G, const PriorFit
       const double lambda = for_marginals ? 0.0 : sc.lambda;
       const double* W = ws.W + 6 * i;
       double D[6] = {W[0] + lambda, W[1], W[2], W[3] + lambda, W[4], W[5] + lambda};
-      double b[3] = {-ws.guy[6 * i], -ws.guy[6 * i + 1], -ws.guy[6 * i + 2]};
+      double b[3];
+      {  // minus the gradient of the unary factor, W (x - m), recomputed here (9 FMAs) instead of being stored
+        const double* x = ws.x + 3 * i;
+        const double d[3] = {x[0] - ws.my[6 * i], x[1] - ws.my[6 * i + 1], x[2] - ws.my[6 * i + 2]};
+        sym6_mul(W, d, b);
+        b[0] = -b[0]; b[1] = -b[1]; b[2] = -b[2];
+      }
       const double* w = ws.w + 3 * i;
       if (ws.par[i] >= 0) {
         const double e = ws.e[i];
@@ -404,7 +410,7 @@ SES_HD void prior_eliminate(WT& tm, const PriorTables& pt, int G, const PriorFit
       if (for_marginals)   // W is dead after this point of the marginal pass: keep D^-1 in its place
         for (int a = 0; a < 6; ++a) ws.W[6 * i + a] = I[a];
       double* z = ws.z + 3 * i;
-      double* y = ws.guy + 6 * i + 3;
+      double* y = ws.my + 6 * i + 3;
       sym6_mul(I, w, z);
       sym6_mul(I, b, y);
       ws.alpha[i] = w[0] * z[0] + w[1] * z[1] + w[2] * z[2];
@@ -425,17 +431,17 @@ SES_HD void prior_backsubstitute(WT& tm, const PriorTables& pt, int G, const Pri
       double s = 0.0;
       const int p = ws.par[i];
       if (p >= 0) {
-        const double* dp = ws.guy + 6 * (g * NFUS + p) + 3;
+        const double* dp = ws.my + 6 * (g * NFUS + p) + 3;
         s = ws.w[3 * i] * dp[0] + ws.w[3 * i + 1] * dp[1] + ws.w[3 * i + 2] * dp[2];
       }
-      double* y = ws.guy + 6 * i + 3;   // delta overwrites y
+      double* y = ws.my + 6 * i + 3;   // delta overwrites y
       for (int a = 0; a < 3; ++a) y[a] = y[a] + ws.z[3 * i + a] * s;
     });
   }
 }
 
 // marginal covariances after prior_eliminate(for_marginals): Sigma_k = Dinv_k + (w_k^T Sigma_p w_k) z_k z_k^T,
-// written over gu | y (no longer needed)
+// written over m | y (no longer needed)
 template <class WT>
 SES_HD void prior_marginals(WT& tm, const PriorTables& pt, int G, const PriorFitWs& ws) {
   for (int L = 0; L < PRIOR_LEVELS; ++L) {
@@ -445,12 +451,12 @@ SES_HD void prior_marginals(WT& tm, const PriorTables& pt, int G, const PriorFit
       const int i = g * NFUS + k;
       if (!ws.msd[i]) return;
       const double* I = ws.W + 6 * i;   // D^-1, stored by the marginal elimination
-      double* S = ws.guy + 6 * i;
+      double* S = ws.my + 6 * i;
       double q = 0.0;
       const int p = ws.par[i];
       if (p >= 0) {
         double t[3];
-        sym6_mul(ws.guy + 6 * (g * NFUS + p), ws.w + 3 * i, t);
+        sym6_mul(ws.my + 6 * (g * NFUS + p), ws.w + 3 * i, t);
         q = ws.w[3 * i] * t[0] + ws.w[3 * i + 1] * t[1] + ws.w[3 * i + 2] * t[2];
       }
       const double* z = ws.z + 3 * i;
@@ -460,8 +466,8 @@ SES_HD void prior_marginals(WT& tm, const PriorTables& pt, int G, const PriorFit
   }
 }
 
-// linearise at x for the detections selected by `which` (0: lm && need_lin, 1: all active): gradient gu = W d of the
-// unary factor, bone direction w and residual e; ta = the joint's share of linear.error(0)
+// linearise at x for the detections selected by `which` (0: lm && need_lin, 1: all active): bone direction w and
+// residual e; ta = the joint's share of linear.error(0)
 template <class WT>
 SES_HD void prior_linearize(WT& tm, const PriorTables& pt, int G, const PriorFitWs& ws, int which) {
   tm.pfor(G * NFUS, [&](int i) {
@@ -469,8 +475,8 @@ SES_HD void prior_linearize(WT& tm, const PriorTables& pt, int G, const PriorFit
     const PriorFitScal& sc = ws.sc[g];
     if (!(which ? sc.active : (sc.lm && sc.need_lin)) || !ws.msd[i]) return;
     const double* x = ws.x + 3 * i;
-    const double d[3] = {x[0] - ws.m[3 * i], x[1] - ws.m[3 * i + 1], x[2] - ws.m[3 * i + 2]};
-    double* gu = ws.guy + 6 * i;
+    const double d[3] = {x[0] - ws.my[6 * i], x[1] - ws.my[6 * i + 1], x[2] - ws.my[6 * i + 2]};
+    double gu[3];
     sym6_mul(ws.W + 6 * i, d, gu);
     double err = 0.5 * (d[0] * gu[0] + d[1] * gu[1] + d[2] * gu[2]);
     const int p = ws.par[i];
@@ -563,7 +569,7 @@ SES_HD void prior_fit_group(WT& tm, const PriorTables& pt, int G, const ses3d_pe
     ws.msd[i] = ms ? 1 : 0;
     if (ms) {
       prior_information(c, ws.W + 6 * i);
-      ws.m[3 * i] = mk[0]; ws.m[3 * i + 1] = mk[1]; ws.m[3 * i + 2] = mk[2];
+      ws.my[6 * i] = mk[0]; ws.my[6 * i + 1] = mk[1]; ws.my[6 * i + 2] = mk[2];
     }
   });
   tm.pfor(G, [&](int g) {
@@ -588,7 +594,7 @@ SES_HD void prior_fit_group(WT& tm, const PriorTables& pt, int G, const ses3d_pe
     if (!sc.active) return;
     if (!ms) return;
     ws.usev[i] = ex ? 1 : 0;
-    for (int a = 0; a < 3; ++a) ws.x[3 * i + a] = ex ? tr.prev[k][a] : ws.m[3 * i + a];
+    for (int a = 0; a < 3; ++a) ws.x[3 * i + a] = ex ? tr.prev[k][a] : ws.my[6 * i + a];
     int par = pt.st->parent[k];
     if (k == SES3D_FBP_NECK && !((sc.mask >> SES3D_FBP_BELLY) & 1u)) par = SES3D_FBP_MIDHIP;
     if (par >= 0 && !((sc.mask >> par) & 1u)) par = -1;
@@ -600,7 +606,7 @@ SES_HD void prior_fit_group(WT& tm, const PriorTables& pt, int G, const ses3d_pe
     const int g = i / NFUS, k = i % NFUS;
     if (!ws.sc[g].active || !ws.msd[i]) return;
     const double* x = ws.x + 3 * i;
-    const double d[3] = {x[0] - ws.m[3 * i], x[1] - ws.m[3 * i + 1], x[2] - ws.m[3 * i + 2]};
+    const double d[3] = {x[0] - ws.my[6 * i], x[1] - ws.my[6 * i + 1], x[2] - ws.my[6 * i + 2]};
     double wd[3];
     sym6_mul(ws.W + 6 * i, d, wd);
     double err = 0.5 * (d[0] * wd[0] + d[1] * wd[1] + d[2] * wd[2]);
@@ -638,9 +644,9 @@ SES_HD void prior_fit_group(WT& tm, const PriorTables& pt, int G, const ses3d_pe
       const PriorFitScal& sc = ws.sc[g];
       if (!sc.lm || sc.fail || !ws.msd[i]) return;
       const double* x = ws.x + 3 * i;
-      const double* dl = ws.guy + 6 * i + 3;
+      const double* dl = ws.my + 6 * i + 3;
       const double xn[3] = {x[0] + dl[0], x[1] + dl[1], x[2] + dl[2]};
-      const double d[3] = {xn[0] - ws.m[3 * i], xn[1] - ws.m[3 * i + 1], xn[2] - ws.m[3 * i + 2]};
+      const double d[3] = {xn[0] - ws.my[6 * i], xn[1] - ws.my[6 * i + 1], xn[2] - ws.my[6 * i + 2]};
       double wd[3];
       sym6_mul(ws.W + 6 * i, d, wd);
       const double unary = 0.5 * (d[0] * wd[0] + d[1] * wd[1] + d[2] * wd[2]);   // linear in x: same in both errors
@@ -649,7 +655,7 @@ SES_HD void prior_fit_group(WT& tm, const PriorTables& pt, int G, const ses3d_pe
       if (p >= 0) {
         const int ip = g * NFUS + p;
         const double* xp = ws.x + 3 * ip;
-        const double* dp = ws.guy + 6 * ip + 3;
+        const double* dp = ws.my + 6 * ip + 3;
         const double* w = ws.w + 3 * i;
         const double el = ws.e[i] + w[0] * (dl[0] - dp[0]) + w[1] * (dl[1] - dp[1]) + w[2] * (dl[2] - dp[2]);
         lin += 0.5 * (el * el);
@@ -704,7 +710,7 @@ SES_HD void prior_fit_group(WT& tm, const PriorTables& pt, int G, const ses3d_pe
     });
     tm.pfor(G * NFUS, [&](int i) {
       if (!ws.sc[i / NFUS].accept || !ws.msd[i]) return;
-      for (int a = 0; a < 3; ++a) ws.x[3 * i + a] += ws.guy[6 * i + 3 + a];
+      for (int a = 0; a < 3; ++a) ws.x[3 * i + a] += ws.my[6 * i + 3 + a];
     });
   }
 
@@ -753,7 +759,7 @@ SES_HD void prior_fit_group(WT& tm, const PriorTables& pt, int G, const ses3d_pe
     if (!(score > q.min_score)) score = q.min_score;   // std::max(g_min_score, score)
     double cv[6];
     if (sc.use_marginals) {
-      for (int a = 0; a < 6; ++a) cv[a] = ws.guy[6 * i + a] * height * height;
+      for (int a = 0; a < 6; ++a) cv[a] = ws.my[6 * i + a] * height * height;
     } else {
       const double d = q.default_res_sigma * q.default_res_sigma;
       cv[0] = d; cv[1] = 0; cv[2] = 0; cv[3] = d; cv[4] = 0; cv[5] = d;

@@ -20,8 +20,7 @@ struct ReprojWs {
   ses3d_person2d* stage;  // [cc][n_p] (capacity cap_rec records), dense in the frame's person count
   uint8_t* vflag;         // [cc][n_p][17] joint accepted
   int* slot;              // [cc][n_p] output slot or -1
-  double* S;              // [s_cap*17][9] joint centre x, y, z and the six non-zero entries of its Cholesky factor
-                          //   (l00 l10 l20 l11 l21 l22): the seven sigma points are rebuilt from them on the fly
+  double* S;              // [s_cap*17][21] sigma points of the current person batch (7 points x xyz)
   float* sscore;          // [s_cap*17] 3-D score (0 = joint absent)
   float* ctr;             // [s_cap*17][4] single-precision joint centre x, y, z and the sigma-point radius
   uint16_t* list;         // [s_cap*17*C] (joint, camera) items that need the exact projection
@@ -33,7 +32,7 @@ struct ReprojWs {
 // cap_rec = staging capacity in Person2D records (>= h_max so that one camera always fits)
 template <class A>
 SES_HD void reproj_ws_layout(A& ar, int n_cams, int cap_rec, int s_cap, ReprojWs* ws) {
-  double* S = ar.template take<double>((size_t)s_cap * NKP * 9);
+  double* S = ar.template take<double>((size_t)s_cap * NKP * 21);
   ses3d_person2d* stage = ar.template take<ses3d_person2d>((size_t)cap_rec);
   int* slot = ar.template take<int>((size_t)cap_rec);
   float* sscore = ar.template take<float>((size_t)s_cap * NKP);
@@ -115,7 +114,9 @@ SES_HD void reproject_frame(Team& tm, const Tables& tb, int h_max, int cap_rec, 
         const double l21 = (kp.cov[4] - l20 * l10) / l11;
         const double l22 = sqrt(kp.cov[5] - l20 * l20 - l21 * l21);
         const double sp = sqrt(3.0 + 0.5);  // sqrt(DIM + kappa) REP:63,68
-        double* S = ws.S + (size_t)e * 9;
+        // samples: mean, mean - sp*L e_j (j=0..2), mean + sp*L e_j (REP:68-72)
+        const double col[3][3] = {{l00, l10, l20}, {0.0, l11, l21}, {0.0, 0.0, l22}};
+        double* S = ws.S + (size_t)e * 21;
         {  // single-precision centre and sigma-point radius for the "certainly outside" pre-test
           const double n0 = l00 * l00 + l10 * l10 + l20 * l20, n1 = l11 * l11 + l21 * l21, n2 = l22 * l22;
           const double nm = n0 > n1 ? (n0 > n2 ? n0 : n2) : (n1 > n2 ? n1 : n2);
@@ -124,7 +125,12 @@ SES_HD void reproject_frame(Team& tm, const Tables& tb, int h_max, int cap_rec, 
           c4[3] = (float)(sp * sqrt(nm)) * 1.001f + 1e-6f;   // NaN (non-SPD covariance) disables the pre-test
         }
         S[0] = kp.x; S[1] = kp.y; S[2] = kp.z;
-        S[3] = l00; S[4] = l10; S[5] = l20; S[6] = l11; S[7] = l21; S[8] = l22;
+        for (int j = 0; j < 3; ++j) {
+          S[(1 + j) * 3 + 0] = (col[j][0] * -sp) + kp.x; S[(1 + j) * 3 + 1] = (col[j][1] * -sp) + kp.y;
+          S[(1 + j) * 3 + 2] = (col[j][2] * -sp) + kp.z;
+          S[(4 + j) * 3 + 0] = (col[j][0] * sp) + kp.x; S[(4 + j) * 3 + 1] = (col[j][1] * sp) + kp.y;
+          S[(4 + j) * 3 + 2] = (col[j][2] * sp) + kp.z;
+        }
       });
       // (joint, camera) pairs: cheap single-precision cull, then the exact projection of the survivors with all
       // lanes busy (REP:193-221)
@@ -144,19 +150,11 @@ SES_HD void reproject_frame(Team& tm, const Tables& tb, int h_max, int cap_rec, 
         const float score = ws.sscore[e];
         const double wden = 2.0 * (3 + 0.5);
         const double w0 = 2 * 0.5 / wden, wi = 1.0 / wden;  // REP:65-66
-        const double* S = ws.S + (size_t)e * 9;
+        const double* S = ws.S + (size_t)e * 21;
         const CamD& cm = tb.camd[c0 + cc];
-        // samples: mean, mean - sp*L e_j (j=0..2), mean + sp*L e_j (REP:68-72), rebuilt with the reference's expression
-        const double sp = sqrt(3.0 + 0.5);  // sqrt(DIM + kappa) REP:63,68
-        const double col[3][3] = {{S[3], S[4], S[5]}, {0.0, S[6], S[7]}, {0.0, 0.0, S[8]}};
         double u[7], v[7];
         for (int s = 0; s < 7; ++s) {
-          double sx = S[0], sy = S[1], sz = S[2];
-          if (s > 0) {
-            const int j = (s - 1) % 3;
-            const double f = s <= 3 ? -sp : sp;
-            sx = (col[j][0] * f) + S[0]; sy = (col[j][1] * f) + S[1]; sz = (col[j][2] * f) + S[2];
-          }
+          const double sx = S[s * 3], sy = S[s * 3 + 1], sz = S[s * 3 + 2];
           const double X = cm.P[0] * sx + cm.P[1] * sy + cm.P[2] * sz + cm.P[3];
           const double Y = cm.P[4] * sx + cm.P[5] * sy + cm.P[6] * sz + cm.P[7];
           const double Z = cm.P[8] * sx + cm.P[9] * sy + cm.P[10] * sz + cm.P[11];

@@ -20,7 +20,11 @@
 //   LevenbergMarquardtOptimizer, default LevenbergMarquardtParams: lambdaInitial 1e-5, lambdaFactor 10,
 //     lambdaUpperBound 1e5, lambdaLowerBound 0, useFixedLambdaFactor, no diagonal damping (damped system =
 //     J^T J + lambda I), minModelFidelity 1e-3, maxIterations 100, relativeErrorTol = absoluteErrorTol = 1e-5,
-//     errorTol 0; inner loop tryLambda(), outer loop NonlinearOptimizer::defaultOptimize() + checkConvergence()
+//     errorTol 0; inner loop tryLambda(), outer loop NonlinearOptimizer::defaultOptimize() + checkConvergence().
+//     One detail differs between gtsam releases and cannot be checked offline: a trial step counts only when the
+//     linearised cost change exceeds 1e-20 (4.0.x as remembered) resp. epsilon x the old linearised error (later
+//     releases). Both thresholds are only reached at machine-precision convergence, where the relative-tolerance
+//     test of the same function ends the search anyway; 1e-20 is used here and in the kernel.
 //   Marginals(graph, x).marginalCovariance(k) -> the k-th 3x3 diagonal block of (J^T J)^-1 at x;
 //     IndeterminantLinearSystemException when the Cholesky factorisation meets a non-positive pivot
 // gtsam is absent from this image and the reference has no tests => PARITY UNPINNED at this boundary; the fit is

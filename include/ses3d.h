@@ -338,6 +338,17 @@ int ses3d_prior_run(ses3d_prior p, int32_t n_sequences, int32_t n_frames, int32_
                     int32_t n_cams, const float* fb_delay, ses3d_person_cov* fused, ses3d_person_cov* pred,
                     int32_t* n_out, float* pred_delay, int32_t* track_of, uint32_t flags, void* stream);
 
+/* Ragged form of ses3d_prior_run (host buffers): the messages are variable-length lists (PersonCov[] persons,
+ * PersonCovList.msg:4), so only occupied records cross PCIe.
+ *   persons_dense  all input records back to back, stream-major then message-major; n_persons [n_sequences][n_frames]
+ *                  gives the run lengths (each <= h_max)
+ *   fused_dense / pred_dense  the published records back to back in the same order, capacity `cap` records each;
+ *                  n_out [n_sequences][n_frames] run lengths, *total = records written to each of the two arrays. */
+int ses3d_prior_run_ragged(ses3d_prior p, int32_t n_sequences, int32_t n_frames, int32_t h_max,
+                           const ses3d_person_cov* persons_dense, const int32_t* n_persons, const int64_t* stamp_ns,
+                           int32_t n_cams, const float* fb_delay, ses3d_person_cov* fused_dense,
+                           ses3d_person_cov* pred_dense, int64_t cap, int32_t* n_out, float* pred_delay, int64_t* total);
+
 /* Diagnostics: live tracks of one sequence (ids / num_obs [max_tracks], nullable); returns the track count or <0. */
 int ses3d_prior_get_tracks(ses3d_prior p, int32_t sequence, int32_t* ids, int32_t* num_obs);
 int64_t ses3d_prior_launch_count(ses3d_prior p);

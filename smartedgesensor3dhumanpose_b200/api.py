@@ -285,6 +285,26 @@ class PriorTracker:
                                            HOST_BUFFERS, None))
         return dict(fused=fused, pred=pred, n_out=n_out, pred_delay=pred_delay, track_of=track_of)
 
+    def run_ragged(self, persons_dense, n_persons, stamp_ns, h_max, fused_dense, pred_dense, fb_delay=None):
+        """Ragged form (only occupied records cross PCIe): persons_dense = all input records back to back
+        (stream-major, message-major), n_persons [S][T] run lengths; fused_dense / pred_dense are caller-provided record
+        arrays (capacity = their length). Returns (n_out [S][T], pred_delay [S][T], total)."""
+        n_persons = np.ascontiguousarray(n_persons, dtype=np.int32)
+        S, T = n_persons.shape
+        stamp_ns = np.ascontiguousarray(stamp_ns, dtype=np.int64).reshape(S, T)
+        n_cams = 0
+        if fb_delay is not None:
+            fb_delay = np.ascontiguousarray(fb_delay, dtype=np.float32).reshape(S, T, -1)
+            n_cams = fb_delay.shape[-1]
+        n_out = np.zeros((S, T), np.int32)
+        pred_delay = np.zeros((S, T), np.float32)
+        total = C.c_int64(0)
+        _lib.check(self._L.ses3d_prior_run_ragged(self._h, S, T, h_max, _p(persons_dense), _p(n_persons), _p(stamp_ns),
+                                                  n_cams, _p(fb_delay), _p(fused_dense), _p(pred_dense),
+                                                  min(len(fused_dense), len(pred_dense)), _p(n_out), _p(pred_delay),
+                                                  C.byref(total)))
+        return n_out, pred_delay, total.value
+
     def run_device(self, n_sequences, n_frames, h_max, persons_ptr, n_persons_ptr, stamp_ptr, n_cams, fb_delay_ptr,
                    fused_ptr, pred_ptr, n_out_ptr, pred_delay_ptr=0, track_of_ptr=0, stream=0):
         """Raw device addresses on this handle's GPU; stream-ordered."""

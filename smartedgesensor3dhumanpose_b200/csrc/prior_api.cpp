@@ -7,6 +7,7 @@
 // by the handle; host-buffer calls stage the records through device buffers that grow once and are reused.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -54,6 +55,7 @@ struct ses3d_prior_s {
   ses3d::PriorTables pt;
   Buf states, tracks, order;
   Buf in_persons, in_n, in_stamp, in_delay, out_fused, out_pred, out_n, out_delay, out_track;
+  Buf dense_in, dense_fused, dense_pred, off_in, off_out;   // ragged call
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   float last_ms = 0.f;
@@ -130,7 +132,8 @@ int ses3d_prior_destroy(ses3d_prior h) {
   if (!h) return SES3D_OK;
   cudaSetDevice(h->device);
   for (Buf* b : {&h->states, &h->tracks, &h->order, &h->in_persons, &h->in_n, &h->in_stamp, &h->in_delay, &h->out_fused,
-                 &h->out_pred, &h->out_n, &h->out_delay, &h->out_track})
+                 &h->out_pred, &h->out_n, &h->out_delay, &h->out_track, &h->dense_in, &h->dense_fused, &h->dense_pred,
+                 &h->off_in, &h->off_out})
     b->release();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -216,6 +219,80 @@ int ses3d_prior_run(ses3d_prior h, int32_t n_sequences, int32_t n_frames, int32_
   CU(cudaStreamSynchronize(st));
   for (const auto& s : hs)
     if (s.overflow) return ses3d::set_error(SES3D_E_CAPACITY, "ses3d_prior_run: a stream needed more than max_tracks tracks");
+  return SES3D_OK;
+}
+
+int ses3d_prior_run_ragged(ses3d_prior h, int32_t n_sequences, int32_t n_frames, int32_t h_max,
+                           const ses3d_person_cov* persons_dense, const int32_t* n_persons, const int64_t* stamp_ns,
+                           int32_t n_cams, const float* fb_delay, ses3d_person_cov* fused_dense,
+                           ses3d_person_cov* pred_dense, int64_t cap, int32_t* n_out, float* pred_delay, int64_t* total) {
+  if (!h) return ses3d::set_error(SES3D_E_INVALID, "ses3d_prior_run_ragged: NULL handle");
+  if (total) *total = 0;
+  if (n_sequences < 0 || n_sequences > h->n_sequences)
+    return ses3d::set_error(SES3D_E_INVALID, "ses3d_prior_run_ragged: n_sequences exceeds the handle's");
+  if (n_frames < 0 || h_max < 1 || h_max > 64 || n_cams < 0 || cap < 0)
+    return ses3d::set_error(SES3D_E_INVALID, "ses3d_prior_run_ragged: bad n_frames / h_max / n_cams / cap");
+  if (n_sequences == 0 || n_frames == 0) return SES3D_OK;
+  if (!n_persons || !stamp_ns || !n_out || !total || (cap > 0 && (!fused_dense || !pred_dense)))
+    return ses3d::set_error(SES3D_E_INVALID, "ses3d_prior_run_ragged: NULL buffer");
+  std::lock_guard<std::mutex> lock(h->mu);
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const size_t n_msg = (size_t)n_sequences * n_frames;
+  const size_t rec = sizeof(ses3d_person_cov);
+  long long n_in = 0;
+  for (size_t i = 0; i < n_msg; ++i) n_in += std::min(std::max(n_persons[i], 0), h_max);
+  if (n_in > 0 && !persons_dense) return ses3d::set_error(SES3D_E_INVALID, "ses3d_prior_run_ragged: NULL persons_dense");
+  if (fb_delay == nullptr) n_cams = 0;
+  CU(h->in_persons.ensure(rec * n_msg * h_max));
+  CU(h->in_n.ensure(4 * n_msg));
+  CU(h->in_stamp.ensure(8 * n_msg));
+  CU(h->out_fused.ensure(rec * n_msg * h_max));
+  CU(h->out_pred.ensure(rec * n_msg * h_max));
+  CU(h->out_n.ensure(4 * n_msg));
+  CU(h->out_delay.ensure(4 * n_msg));
+  CU(h->dense_in.ensure(rec * (size_t)std::max<long long>(n_in, 1)));
+  CU(h->dense_fused.ensure(rec * (size_t)std::max<long long>(n_in, 1)));   // published <= fitted
+  CU(h->dense_pred.ensure(rec * (size_t)std::max<long long>(n_in, 1)));
+  CU(h->off_in.ensure(8 * (n_msg + 1)));
+  CU(h->off_out.ensure(8 * (n_msg + 1)));
+  if (n_cams > 0) CU(h->in_delay.ensure(4 * n_msg * n_cams));
+  CU(cudaMemcpyAsync(h->in_n.p, n_persons, 4 * n_msg, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(h->in_stamp.p, stamp_ns, 8 * n_msg, cudaMemcpyHostToDevice, st));
+  if (n_in) CU(cudaMemcpyAsync(h->dense_in.p, persons_dense, rec * (size_t)n_in, cudaMemcpyHostToDevice, st));
+  if (n_cams > 0) CU(cudaMemcpyAsync(h->in_delay.p, fb_delay, 4 * n_msg * n_cams, cudaMemcpyHostToDevice, st));
+  CU(ses3d::launch_scan_counts(h->in_n.as<int32_t>(), (int)n_msg, h_max, h->off_in.as<long long>(), st));
+  CU(ses3d::launch_move_records(1, (int)n_msg, h_max, (int)rec, h->in_n.as<int32_t>(), h->off_in.as<long long>(),
+                                h->in_persons.p, h->dense_in.p, st));
+  CU(cudaEventRecord(h->ev0, st));
+  CU(ses3d::launch_prior(h->pt, n_sequences, n_frames, h_max, h->max_tracks, h->states.as<ses3d::PriorSeqState>(),
+                         h->tracks.as<ses3d::PriorTrack>(), h->order.as<uint8_t>(), h->in_persons.as<ses3d_person_cov>(),
+                         h->in_n.as<int32_t>(), h->in_stamp.as<int64_t>(), n_cams,
+                         n_cams > 0 ? h->in_delay.as<float>() : nullptr, h->out_fused.as<ses3d_person_cov>(),
+                         h->out_pred.as<ses3d_person_cov>(), h->out_n.as<int32_t>(), h->out_delay.as<float>(), nullptr, st));
+  CU(cudaEventRecord(h->ev1, st));
+  CU(ses3d::launch_scan_counts(h->out_n.as<int32_t>(), (int)n_msg, h_max, h->off_out.as<long long>(), st));
+  CU(ses3d::launch_move_records(0, (int)n_msg, h_max, (int)rec, h->out_n.as<int32_t>(), h->off_out.as<long long>(),
+                                h->out_fused.p, h->dense_fused.p, st));
+  CU(ses3d::launch_move_records(0, (int)n_msg, h_max, (int)rec, h->out_n.as<int32_t>(), h->off_out.as<long long>(),
+                                h->out_pred.p, h->dense_pred.p, st));
+  h->launches += 6;
+  long long n_pub = 0;
+  CU(cudaMemcpyAsync(&n_pub, h->off_out.as<long long>() + n_msg, 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(n_out, h->out_n.p, 4 * n_msg, cudaMemcpyDeviceToHost, st));
+  if (pred_delay) CU(cudaMemcpyAsync(pred_delay, h->out_delay.p, 4 * n_msg, cudaMemcpyDeviceToHost, st));
+  std::vector<ses3d::PriorSeqState> hs(n_sequences);
+  CU(cudaMemcpyAsync(hs.data(), h->states.p, sizeof(ses3d::PriorSeqState) * n_sequences, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  for (const auto& s : hs)
+    if (s.overflow) return ses3d::set_error(SES3D_E_CAPACITY, "ses3d_prior_run_ragged: a stream needed more than max_tracks tracks");
+  if (n_pub > cap) return ses3d::set_error(SES3D_E_CAPACITY, "ses3d_prior_run_ragged: output capacity too small");
+  if (n_pub) {
+    CU(cudaMemcpyAsync(fused_dense, h->dense_fused.p, rec * (size_t)n_pub, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(pred_dense, h->dense_pred.p, rec * (size_t)n_pub, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  *total = n_pub;
   return SES3D_OK;
 }
 

@@ -16,7 +16,7 @@ EXPORTS = ("ses3d_default_params", "ses3d_create", "ses3d_destroy", "ses3d_get_t
            "ses3d_assembler_stats", "ses3d_wire_decode_person2dlist", "ses3d_wire_encode_person2dlist",
            "ses3d_wire_decode_personcovlist", "ses3d_wire_encode_personcovlist", "ses3d_prior_default_params",
            "ses3d_prior_create", "ses3d_prior_destroy", "ses3d_prior_reset", "ses3d_prior_run", "ses3d_prior_get_tracks",
-           "ses3d_prior_launch_count", "ses3d_prior_last_kernel_ms", "ses3d_measure_fma_peak", "ses3d_markers_batch")
+           "ses3d_prior_launch_count", "ses3d_prior_last_kernel_ms", "ses3d_measure_fma_peak", "ses3d_markers_batch", "ses3d_prior_run_ragged")
 
 
 class Ses3dError(RuntimeError):
@@ -78,6 +78,7 @@ def load():
     L.ses3d_prior_reset.argtypes = [vp]
     L.ses3d_prior_run.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, u32, vp]
     L.ses3d_prior_get_tracks.argtypes = [vp, i32, vp, vp]
+    L.ses3d_prior_run_ragged.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, i64, vp, vp, C.POINTER(i64)]
     L.ses3d_prior_launch_count.argtypes = [vp]
     L.ses3d_prior_launch_count.restype = i64
     L.ses3d_prior_last_kernel_ms.argtypes = [vp, vp]

@@ -131,3 +131,29 @@ def test_prior_against_committed_golden_vectors(case):
     c = next(x for x in mg.CASES if x[0] == case)
     seq, r = mg.run_case(c, make=lambda prm, S: api.PriorTracker(prm, S))
     mg.compare(g, case, seq, r, POS_TOL, COV_RTOL)
+
+
+def test_prior_ragged_call_equals_padded():
+    """ses3d_prior_run_ragged (dense records in and out) == ses3d_prior_run on the same streams."""
+    S, T = 12, 30
+    seq = synth_person_sequences(S, T, 5, seed=26, person_dropout=0.2)
+    prm = default_prior_params(min_num_obs_track=3)
+    H = seq["h_max"]
+    padded = api.PriorTracker(prm, S).run(seq["persons"], seq["n_persons"], seq["stamp_ns"], seq["fb_delay"])
+    live_in = np.arange(H)[None, None, :] < seq["n_persons"][:, :, None]
+    dense_in = np.ascontiguousarray(seq["persons"][live_in])
+    cap = int(seq["n_persons"].sum())
+    fused = np.zeros(cap, person_cov_dtype)
+    pred = np.zeros(cap, person_cov_dtype)
+    n_out, delay, total = api.PriorTracker(prm, S).run_ragged(dense_in, seq["n_persons"], seq["stamp_ns"], H, fused, pred,
+                                                              seq["fb_delay"])
+    assert np.array_equal(n_out, padded["n_out"]) and np.array_equal(delay, padded["pred_delay"])
+    assert total == padded["n_out"].sum() and total > S * 10
+    live = np.arange(H)[None, None, :] < padded["n_out"][:, :, None]
+    assert fused[:total].tobytes() == padded["fused"][live].tobytes()
+    assert pred[:total].tobytes() == padded["pred"][live].tobytes()
+    # capacity error: an output array that is too small
+    from smartedgesensor3dhumanpose_b200.lib import Ses3dError
+    with pytest.raises(Ses3dError) as e:
+        api.PriorTracker(prm, S).run_ragged(dense_in, seq["n_persons"], seq["stamp_ns"], H, fused[:5], pred[:5], seq["fb_delay"])
+    assert e.value.code == -3

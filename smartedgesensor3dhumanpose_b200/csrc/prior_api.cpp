@@ -49,13 +49,30 @@ struct Buf {
 
 }  // namespace
 
+struct PriorSlot {   // one in-flight chunk of streams of a ragged call
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  long long* total = nullptr;   // pinned
+  Buf persons, n, stamp, delay, fused, pred, n_out, delay_out, dense_in, dense_fused, dense_pred, off_in, off_out;
+  void release() {
+    for (Buf* b : {&persons, &n, &stamp, &delay, &fused, &pred, &n_out, &delay_out, &dense_in, &dense_fused, &dense_pred,
+                   &off_in, &off_out})
+      b->release();
+    if (total) cudaFreeHost(total);
+    if (done) cudaEventDestroy(done);
+    if (stream) cudaStreamDestroy(stream);
+    total = nullptr; done = nullptr; stream = nullptr;
+  }
+};
+
 struct ses3d_prior_s {
   int device = 0;
   int n_sequences = 0, max_tracks = 0;
   ses3d::PriorTables pt;
   Buf states, tracks, order;
   Buf in_persons, in_n, in_stamp, in_delay, out_fused, out_pred, out_n, out_delay, out_track;
-  Buf dense_in, dense_fused, dense_pred, off_in, off_out;   // ragged call
+  static constexpr int kSlots = 3;   // ragged call: H2D of chunk i+1, kernel of chunk i and D2H of chunk i-1 overlap
+  PriorSlot rs[kSlots];
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   float last_ms = 0.f;
@@ -116,6 +133,11 @@ int ses3d_prior_create(const ses3d_prior_params* params, int32_t n_sequences, in
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
   if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");
   if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
+  for (PriorSlot& sl : h->rs) {
+    if ((e = cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaMallocHost(reinterpret_cast<void**>(&sl.total), sizeof(long long))) != cudaSuccess) return bail(e, "cudaMallocHost");
+  }
   if ((e = h->states.ensure(sizeof(ses3d::PriorSeqState) * n_sequences)) != cudaSuccess) return bail(e, "cudaMalloc states");
   if ((e = h->tracks.ensure(sizeof(ses3d::PriorTrack) * (size_t)n_sequences * max_tracks)) != cudaSuccess) return bail(e, "cudaMalloc tracks");
   if ((e = h->order.ensure((size_t)n_sequences * max_tracks)) != cudaSuccess) return bail(e, "cudaMalloc order");
@@ -132,9 +154,9 @@ int ses3d_prior_destroy(ses3d_prior h) {
   if (!h) return SES3D_OK;
   cudaSetDevice(h->device);
   for (Buf* b : {&h->states, &h->tracks, &h->order, &h->in_persons, &h->in_n, &h->in_stamp, &h->in_delay, &h->out_fused,
-                 &h->out_pred, &h->out_n, &h->out_delay, &h->out_track, &h->dense_in, &h->dense_fused, &h->dense_pred,
-                 &h->off_in, &h->off_out})
+                 &h->out_pred, &h->out_n, &h->out_delay, &h->out_track})
     b->release();
+  for (PriorSlot& sl : h->rs) sl.release();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -237,62 +259,87 @@ int ses3d_prior_run_ragged(ses3d_prior h, int32_t n_sequences, int32_t n_frames,
     return ses3d::set_error(SES3D_E_INVALID, "ses3d_prior_run_ragged: NULL buffer");
   std::lock_guard<std::mutex> lock(h->mu);
   CU(cudaSetDevice(h->device));
-  cudaStream_t st = h->stream;
-  const size_t n_msg = (size_t)n_sequences * n_frames;
+  CU(cudaStreamSynchronize(h->stream));   // earlier padded / reset work on the handle's own stream
   const size_t rec = sizeof(ses3d_person_cov);
-  long long n_in = 0;
-  for (size_t i = 0; i < n_msg; ++i) n_in += std::min(std::max(n_persons[i], 0), h_max);
-  if (n_in > 0 && !persons_dense) return ses3d::set_error(SES3D_E_INVALID, "ses3d_prior_run_ragged: NULL persons_dense");
   if (fb_delay == nullptr) n_cams = 0;
-  CU(h->in_persons.ensure(rec * n_msg * h_max));
-  CU(h->in_n.ensure(4 * n_msg));
-  CU(h->in_stamp.ensure(8 * n_msg));
-  CU(h->out_fused.ensure(rec * n_msg * h_max));
-  CU(h->out_pred.ensure(rec * n_msg * h_max));
-  CU(h->out_n.ensure(4 * n_msg));
-  CU(h->out_delay.ensure(4 * n_msg));
-  CU(h->dense_in.ensure(rec * (size_t)std::max<long long>(n_in, 1)));
-  CU(h->dense_fused.ensure(rec * (size_t)std::max<long long>(n_in, 1)));   // published <= fitted
-  CU(h->dense_pred.ensure(rec * (size_t)std::max<long long>(n_in, 1)));
-  CU(h->off_in.ensure(8 * (n_msg + 1)));
-  CU(h->off_out.ensure(8 * (n_msg + 1)));
-  if (n_cams > 0) CU(h->in_delay.ensure(4 * n_msg * n_cams));
-  CU(cudaMemcpyAsync(h->in_n.p, n_persons, 4 * n_msg, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(h->in_stamp.p, stamp_ns, 8 * n_msg, cudaMemcpyHostToDevice, st));
-  if (n_in) CU(cudaMemcpyAsync(h->dense_in.p, persons_dense, rec * (size_t)n_in, cudaMemcpyHostToDevice, st));
-  if (n_cams > 0) CU(cudaMemcpyAsync(h->in_delay.p, fb_delay, 4 * n_msg * n_cams, cudaMemcpyHostToDevice, st));
-  CU(ses3d::launch_scan_counts(h->in_n.as<int32_t>(), (int)n_msg, h_max, h->off_in.as<long long>(), st));
-  CU(ses3d::launch_move_records(1, (int)n_msg, h_max, (int)rec, h->in_n.as<int32_t>(), h->off_in.as<long long>(),
-                                h->in_persons.p, h->dense_in.p, st));
-  CU(cudaEventRecord(h->ev0, st));
-  CU(ses3d::launch_prior(h->pt, n_sequences, n_frames, h_max, h->max_tracks, h->states.as<ses3d::PriorSeqState>(),
-                         h->tracks.as<ses3d::PriorTrack>(), h->order.as<uint8_t>(), h->in_persons.as<ses3d_person_cov>(),
-                         h->in_n.as<int32_t>(), h->in_stamp.as<int64_t>(), n_cams,
-                         n_cams > 0 ? h->in_delay.as<float>() : nullptr, h->out_fused.as<ses3d_person_cov>(),
-                         h->out_pred.as<ses3d_person_cov>(), h->out_n.as<int32_t>(), h->out_delay.as<float>(), nullptr, st));
-  CU(cudaEventRecord(h->ev1, st));
-  CU(ses3d::launch_scan_counts(h->out_n.as<int32_t>(), (int)n_msg, h_max, h->off_out.as<long long>(), st));
-  CU(ses3d::launch_move_records(0, (int)n_msg, h_max, (int)rec, h->out_n.as<int32_t>(), h->off_out.as<long long>(),
-                                h->out_fused.p, h->dense_fused.p, st));
-  CU(ses3d::launch_move_records(0, (int)n_msg, h_max, (int)rec, h->out_n.as<int32_t>(), h->off_out.as<long long>(),
-                                h->out_pred.p, h->dense_pred.p, st));
-  h->launches += 6;
-  long long n_pub = 0;
-  CU(cudaMemcpyAsync(&n_pub, h->off_out.as<long long>() + n_msg, 8, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(n_out, h->out_n.p, 4 * n_msg, cudaMemcpyDeviceToHost, st));
-  if (pred_delay) CU(cudaMemcpyAsync(pred_delay, h->out_delay.p, 4 * n_msg, cudaMemcpyDeviceToHost, st));
-  std::vector<ses3d::PriorSeqState> hs(n_sequences);
-  CU(cudaMemcpyAsync(hs.data(), h->states.p, sizeof(ses3d::PriorSeqState) * n_sequences, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
-  for (const auto& s : hs)
-    if (s.overflow) return ses3d::set_error(SES3D_E_CAPACITY, "ses3d_prior_run_ragged: a stream needed more than max_tracks tracks");
-  if (n_pub > cap) return ses3d::set_error(SES3D_E_CAPACITY, "ses3d_prior_run_ragged: output capacity too small");
-  if (n_pub) {
-    CU(cudaMemcpyAsync(fused_dense, h->dense_fused.p, rec * (size_t)n_pub, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(pred_dense, h->dense_pred.p, rec * (size_t)n_pub, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+  // chunks of streams (streams are independent): three slots keep H2D, the kernel and D2H of neighbouring chunks busy
+  const int chunk = std::max(1, std::min(n_sequences, std::max(64, (n_sequences + 7) / 8)));
+  long long in_done = 0, out_done = 0;
+  struct Pending { int slot; size_t m0, n_msg; bool active; } prev{0, 0, 0, false};
+  int status = SES3D_OK;
+  auto finish = [&](const Pending& pd) -> int {   // total known -> copy the dense results out
+    PriorSlot& sl = h->rs[pd.slot];
+    CU(cudaEventSynchronize(sl.done));
+    const long long t = *sl.total;
+    if (out_done + t > cap) return ses3d::set_error(SES3D_E_CAPACITY, "ses3d_prior_run_ragged: output capacity too small");
+    if (t) {
+      CU(cudaMemcpyAsync(fused_dense + out_done, sl.dense_fused.p, rec * (size_t)t, cudaMemcpyDeviceToHost, sl.stream));
+      CU(cudaMemcpyAsync(pred_dense + out_done, sl.dense_pred.p, rec * (size_t)t, cudaMemcpyDeviceToHost, sl.stream));
+    }
+    out_done += t;
+    return SES3D_OK;
+  };
+  int ci = 0;
+  for (int s0 = 0; s0 < n_sequences && status == SES3D_OK; s0 += chunk, ++ci) {
+    const int ns = std::min(chunk, n_sequences - s0);
+    PriorSlot& sl = h->rs[ci % ses3d_prior_s::kSlots];
+    cudaStream_t st = sl.stream;
+    const size_t m0 = (size_t)s0 * n_frames, n_msg = (size_t)ns * n_frames;
+    long long n_in = 0;
+    for (size_t i = m0; i < m0 + n_msg; ++i) n_in += std::min(std::max(n_persons[i], 0), h_max);
+    if (n_in > 0 && !persons_dense) return ses3d::set_error(SES3D_E_INVALID, "ses3d_prior_run_ragged: NULL persons_dense");
+    CU(cudaEventSynchronize(sl.done));   // the slot's previous chunk (its copies included) has left the buffers
+    CU(sl.persons.ensure(rec * n_msg * h_max));
+    CU(sl.n.ensure(4 * n_msg));
+    CU(sl.stamp.ensure(8 * n_msg));
+    CU(sl.fused.ensure(rec * n_msg * h_max));
+    CU(sl.pred.ensure(rec * n_msg * h_max));
+    CU(sl.n_out.ensure(4 * n_msg));
+    CU(sl.delay_out.ensure(4 * n_msg));
+    CU(sl.dense_in.ensure(rec * (size_t)std::max<long long>(n_in, 1)));
+    CU(sl.dense_fused.ensure(rec * (size_t)std::max<long long>(n_in, 1)));   // published <= fitted
+    CU(sl.dense_pred.ensure(rec * (size_t)std::max<long long>(n_in, 1)));
+    CU(sl.off_in.ensure(8 * (n_msg + 1)));
+    CU(sl.off_out.ensure(8 * (n_msg + 1)));
+    if (n_cams > 0) CU(sl.delay.ensure(4 * n_msg * n_cams));
+    CU(cudaMemcpyAsync(sl.n.p, n_persons + m0, 4 * n_msg, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(sl.stamp.p, stamp_ns + m0, 8 * n_msg, cudaMemcpyHostToDevice, st));
+    if (n_in) CU(cudaMemcpyAsync(sl.dense_in.p, persons_dense + in_done, rec * (size_t)n_in, cudaMemcpyHostToDevice, st));
+    in_done += n_in;
+    if (n_cams > 0) CU(cudaMemcpyAsync(sl.delay.p, fb_delay + m0 * n_cams, 4 * n_msg * n_cams, cudaMemcpyHostToDevice, st));
+    CU(ses3d::launch_scan_counts(sl.n.as<int32_t>(), (int)n_msg, h_max, sl.off_in.as<long long>(), st));
+    CU(ses3d::launch_move_records(1, (int)n_msg, h_max, (int)rec, sl.n.as<int32_t>(), sl.off_in.as<long long>(),
+                                  sl.persons.p, sl.dense_in.p, st));
+    CU(ses3d::launch_prior(h->pt, ns, n_frames, h_max, h->max_tracks, h->states.as<ses3d::PriorSeqState>() + s0,
+                           h->tracks.as<ses3d::PriorTrack>() + (size_t)s0 * h->max_tracks,
+                           h->order.as<uint8_t>() + (size_t)s0 * h->max_tracks, sl.persons.as<ses3d_person_cov>(),
+                           sl.n.as<int32_t>(), sl.stamp.as<int64_t>(), n_cams, n_cams > 0 ? sl.delay.as<float>() : nullptr,
+                           sl.fused.as<ses3d_person_cov>(), sl.pred.as<ses3d_person_cov>(), sl.n_out.as<int32_t>(),
+                           sl.delay_out.as<float>(), nullptr, st));
+    CU(ses3d::launch_scan_counts(sl.n_out.as<int32_t>(), (int)n_msg, h_max, sl.off_out.as<long long>(), st));
+    CU(ses3d::launch_move_records(0, (int)n_msg, h_max, (int)rec, sl.n_out.as<int32_t>(), sl.off_out.as<long long>(),
+                                  sl.fused.p, sl.dense_fused.p, st));
+    CU(ses3d::launch_move_records(0, (int)n_msg, h_max, (int)rec, sl.n_out.as<int32_t>(), sl.off_out.as<long long>(),
+                                  sl.pred.p, sl.dense_pred.p, st));
+    h->launches += 6;
+    CU(cudaMemcpyAsync(sl.total, sl.off_out.as<long long>() + n_msg, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(n_out + m0, sl.n_out.p, 4 * n_msg, cudaMemcpyDeviceToHost, st));
+    if (pred_delay) CU(cudaMemcpyAsync(pred_delay + m0, sl.delay_out.p, 4 * n_msg, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(sl.done, st));
+    if (prev.active) status = finish(prev);   // overlaps with the chunk just enqueued
+    prev = Pending{ci % ses3d_prior_s::kSlots, m0, n_msg, true};
   }
-  *total = n_pub;
+  if (status == SES3D_OK && prev.active) status = finish(prev);
+  for (PriorSlot& sl : h->rs) {
+    CU(cudaEventRecord(sl.done, sl.stream));   // covers the result copies: the slot is free once this has passed
+    CU(cudaStreamSynchronize(sl.stream));
+  }
+  if (status != SES3D_OK) return status;
+  std::vector<ses3d::PriorSeqState> hs(n_sequences);
+  CU(cudaMemcpy(hs.data(), h->states.p, sizeof(ses3d::PriorSeqState) * n_sequences, cudaMemcpyDeviceToHost));
+  for (const auto& st : hs)
+    if (st.overflow) return ses3d::set_error(SES3D_E_CAPACITY, "ses3d_prior_run_ragged: a stream needed more than max_tracks tracks");
+  *total = out_done;
   return SES3D_OK;
 }
 

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -262,8 +263,12 @@ int ses3d_prior_run_ragged(ses3d_prior h, int32_t n_sequences, int32_t n_frames,
   CU(cudaStreamSynchronize(h->stream));   // earlier padded / reset work on the handle's own stream
   const size_t rec = sizeof(ses3d_person_cov);
   if (fb_delay == nullptr) n_cams = 0;
-  // chunks of streams (streams are independent): three slots keep H2D, the kernel and D2H of neighbouring chunks busy
-  const int chunk = std::max(1, std::min(n_sequences, std::max(64, (n_sequences + 7) / 8)));
+  // chunks of streams (streams are independent): three slots keep H2D, the kernel and D2H of neighbouring chunks busy.
+  // The kernel walks the messages of a stream one after the other, so a launch takes about n_frames x the per-message
+  // latency however few streams it holds: chunks stay large (B200, 2048 streams x 32 messages, ms per call:
+  // 1 chunk 43.5, 8 chunks 58.8)
+  int chunk = std::max(1, std::min(n_sequences, std::max(592, (n_sequences + 2) / 3)));
+  if (const char* env = getenv("SES3D_PRIOR_RAGGED_CHUNK")) chunk = std::max(1, std::min(n_sequences, atoi(env)));
   long long in_done = 0, out_done = 0;
   struct Pending { int slot; size_t m0, n_msg; bool active; } prev{0, 0, 0, false};
   int status = SES3D_OK;

@@ -54,12 +54,24 @@ struct PriorSlot {   // one in-flight chunk of streams of a ragged call
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
   long long* total = nullptr;   // pinned
+  unsigned char* h_stage = nullptr;   // pinned staging of the chunk's n_out / pred_delay (the caller's arrays may be pageable,
+  size_t h_stage_cap = 0;             //   and an async copy into pageable memory blocks the host until the kernel is done)
+  cudaError_t ensure_stage(size_t bytes) {
+    if (bytes <= h_stage_cap) return cudaSuccess;
+    if (h_stage) cudaFreeHost(h_stage);
+    h_stage = nullptr; h_stage_cap = 0;
+    cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&h_stage), bytes + bytes / 8 + 256);
+    if (e == cudaSuccess) h_stage_cap = bytes + bytes / 8 + 256;
+    return e;
+  }
   Buf persons, n, stamp, delay, fused, pred, n_out, delay_out, dense_in, dense_fused, dense_pred, off_in, off_out;
   void release() {
     for (Buf* b : {&persons, &n, &stamp, &delay, &fused, &pred, &n_out, &delay_out, &dense_in, &dense_fused, &dense_pred,
                    &off_in, &off_out})
       b->release();
     if (total) cudaFreeHost(total);
+    if (h_stage) cudaFreeHost(h_stage);
+    h_stage = nullptr; h_stage_cap = 0;
     if (done) cudaEventDestroy(done);
     if (stream) cudaStreamDestroy(stream);
     total = nullptr; done = nullptr; stream = nullptr;
@@ -276,6 +288,8 @@ int ses3d_prior_run_ragged(ses3d_prior h, int32_t n_sequences, int32_t n_frames,
     PriorSlot& sl = h->rs[pd.slot];
     CU(cudaEventSynchronize(sl.done));
     const long long t = *sl.total;
+    std::memcpy(n_out + pd.m0, sl.h_stage, 4 * pd.n_msg);
+    if (pred_delay) std::memcpy(pred_delay + pd.m0, sl.h_stage + 4 * pd.n_msg, 4 * pd.n_msg);
     if (out_done + t > cap) return ses3d::set_error(SES3D_E_CAPACITY, "ses3d_prior_run_ragged: output capacity too small");
     if (t) {
       CU(cudaMemcpyAsync(fused_dense + out_done, sl.dense_fused.p, rec * (size_t)t, cudaMemcpyDeviceToHost, sl.stream));
@@ -307,6 +321,7 @@ int ses3d_prior_run_ragged(ses3d_prior h, int32_t n_sequences, int32_t n_frames,
     CU(sl.off_in.ensure(8 * (n_msg + 1)));
     CU(sl.off_out.ensure(8 * (n_msg + 1)));
     if (n_cams > 0) CU(sl.delay.ensure(4 * n_msg * n_cams));
+    CU(sl.ensure_stage(8 * n_msg));
     CU(cudaMemcpyAsync(sl.n.p, n_persons + m0, 4 * n_msg, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(sl.stamp.p, stamp_ns + m0, 8 * n_msg, cudaMemcpyHostToDevice, st));
     if (n_in) CU(cudaMemcpyAsync(sl.dense_in.p, persons_dense + in_done, rec * (size_t)n_in, cudaMemcpyHostToDevice, st));
@@ -328,8 +343,8 @@ int ses3d_prior_run_ragged(ses3d_prior h, int32_t n_sequences, int32_t n_frames,
                                   sl.pred.p, sl.dense_pred.p, st));
     h->launches += 6;
     CU(cudaMemcpyAsync(sl.total, sl.off_out.as<long long>() + n_msg, 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(n_out + m0, sl.n_out.p, 4 * n_msg, cudaMemcpyDeviceToHost, st));
-    if (pred_delay) CU(cudaMemcpyAsync(pred_delay + m0, sl.delay_out.p, 4 * n_msg, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(sl.h_stage, sl.n_out.p, 4 * n_msg, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(sl.h_stage + 4 * n_msg, sl.delay_out.p, 4 * n_msg, cudaMemcpyDeviceToHost, st));
     CU(cudaEventRecord(sl.done, st));
     if (prev.active) status = finish(prev);   // overlaps with the chunk just enqueued
     prev = Pending{ci % ses3d_prior_s::kSlots, m0, n_msg, true};

@@ -22,4 +22,19 @@ for pm, nh, people in [(0, 0, 7), (1, 1, 3)]:
     r = trk.run(seq["persons"], seq["n_persons"], seq["stamp_ns"], seq["fb_delay"])
     print("pose_method", pm, "published", int(r["n_out"].sum()), "tracks", [len(trk.tracks(s)[0]) for s in range(3)])
     trk.close()
+    # ragged call (pack / unpack kernels, pipelined slots)
+    from smartedgesensor3dhumanpose_b200.layouts import person_cov_dtype
+    H = seq["h_max"]
+    live = np.arange(H)[None, None, :] < seq["n_persons"][:, :, None]
+    dense = np.ascontiguousarray(seq["persons"][live])
+    fused, pred = np.zeros(len(dense), person_cov_dtype), np.zeros(len(dense), person_cov_dtype)
+    trk = api.PriorTracker(default_prior_params(pose_method=pm, normalize_by_height=nh, min_num_obs_track=2), 3)
+    n_out, _, total = trk.run_ragged(dense, seq["n_persons"], seq["stamp_ns"], H, fused, pred, seq["fb_delay"])
+    assert total == r["n_out"].sum() and np.array_equal(n_out, r["n_out"])
+    trk.close()
+# visualisation kernel on fused skeletons
+from smartedgesensor3dhumanpose_b200 import rigs  # noqa: E402
+pipe = api.GeometryPipeline(rigs.ring8())
+m = pipe.markers_batch(r["fused"].reshape(-1, r["fused"].shape[-1]), r["n_out"].reshape(-1), 1)
+print("markers: segments", int(m["n_segments"].sum()))
 print("sanitize prior done")

@@ -11,15 +11,17 @@
 // in order; the tracker state lives in HBM/L2 between launches. Inside a frame
 //  * the track/detection cost matrix is filled one thread per entry, the assignment is solved by the
 //    warp-cooperative Munkres of assoc_core.h (same scan order as the reference's Hungarian.cpp);
-//  * every detection is fitted by ONE WARP, lane k = skeleton joint k. The factor graph of a skeleton is a
-//    forest (one bone per joint to its parent), and a range factor's Hessian block is rank one:
-//    H_child,parent = -w w^T with w = (x_c - x_p) / (|x_c - x_p| sigma). The damped normal equations
-//    (J^T J + lambda I) delta = -J^T e are therefore solved exactly by leaf-to-root elimination of 3x3 blocks
-//    (no fill-in, each Schur complement is the scalar alpha = w^T D^-1 w times w w^T) and a root-to-leaf
-//    back-substitution: 6 tree levels up, 6 down, all joints of a level in parallel, instead of a dense 57 x 57
-//    Cholesky per LM trial. The marginal covariances follow from the same factorisation by the downward
-//    recursion Sigma_c = D_c^-1 + (w^T Sigma_p w) z z^T, z = D_c^-1 w (no dense inverse);
-//  * track pruning / merging is integer work by the leader on a pair-distance table computed in parallel.
+//  * the detections of a message are fitted in groups of up to three by one warp each, all detections of a group in
+//    lock step. The factor graph of a skeleton is a forest (one bone per joint to its parent), and a range factor's
+//    Hessian block is rank one: H_child,parent = -w w^T with w = (x_c - x_p) / (|x_c - x_p| sigma). The damped
+//    normal equations (J^T J + lambda I) delta = -J^T e are therefore solved exactly by leaf-to-root elimination of
+//    3x3 blocks (no fill-in, each Schur complement is the scalar alpha = w^T D^-1 w times w w^T) and a root-to-leaf
+//    back-substitution: 6 tree levels up, 6 down, the (detection, joint-of-level) items of a level in parallel,
+//    instead of a dense 57 x 57 Cholesky per LM trial. The marginal covariances follow from the same factorisation by
+//    the downward recursion Sigma_c = D_c^-1 + (w^T Sigma_p w) z z^T, z = D_c^-1 w (no dense inverse). Every
+//    detection carries its own LM state (lambda, errors, flags) and idles once it has converged;
+//  * a message costs four CTA barriers: costs in parallel; Munkres, new tracks and publication slots on the first
+//    warp; the fits; pruning, the pair-distance table and the merge loop on the first warp.
 // Everything is FP64 like gtsam; results are tolerance-checked against the oracle (different elimination order).
 #pragma once
 #include "assoc_core.h"

@@ -378,3 +378,31 @@ def test_translation_and_time_shift_invariance():
         d = np.stack([np.abs(kb[c][m] - ka[c][m] - shift[i]) for i, c in enumerate("xyz")])
         assert d.max() < 1e-4 and np.median(d) < 1e-9
         assert np.allclose(ka["cov"], kb["cov"], rtol=1e-2, atol=1e-10)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_randomised_differential_device_algorithm_vs_oracle(seed):
+    """Random stream shapes, parameters, drop-out rates and time gaps: the device algorithm against the oracle."""
+    rng = np.random.default_rng(100 + seed)
+    pose_method = int(rng.integers(0, 2))
+    prm = default_prior_params(pose_method=pose_method, normalize_by_height=int(rng.integers(0, 2)),
+                               min_num_obs_track=int(rng.integers(0, 12)),
+                               dist_threshold=float(rng.choice([5.0, 2.0, 0.5])),
+                               t_max_unobserved=float(rng.choice([1.0, 0.2])))
+    S, T, P = int(rng.integers(1, 4)), int(rng.integers(5, 45)), int(rng.integers(1, 8))
+    seq = synth_person_sequences(S, T, P, seed=200 + seed, pose_method=pose_method, h_max=max(8, P + 1),
+                                 joint_dropout=float(rng.uniform(0, 0.5)), person_dropout=float(rng.uniform(0, 0.4)),
+                                 noise_m=float(rng.choice([0.005, 0.02, 0.06])), area=float(rng.choice([2.0, 6.0])))
+    for s in range(S):                                    # a gap (tracks pruned) and a stall (tiny delta t)
+        g = int(rng.integers(1, T))
+        seq["stamp_ns"][s, g:] += int(rng.choice([3e8, 1.5e9]))
+    ro = PriorOracle(prm, S, ref_hungarian=True).run(seq["persons"], seq["n_persons"], seq["stamp_ns"], seq["fb_delay"])
+    rh = PriorHostSim(prm, S, group=int(rng.integers(1, 7))).run(seq["persons"], seq["n_persons"], seq["stamp_ns"],
+                                                                 seq["fb_delay"])
+    # the bulk agrees to rounding; single weakly observed joints may sit one LM iteration apart (see RESULTS.md)
+    compare_runs(ro, rh, pos_tol=2e-4, cov_rtol=0.2)
+    live = np.arange(ro["fused"].shape[-1])[None, None, :] < ro["n_out"][:, :, None]
+    ka, kb = ro["fused"][live]["keypoints"], rh["fused"][live]["keypoints"]
+    if ka.size:
+        d = np.sqrt(sum((ka[c] - kb[c]) ** 2 for c in "xyz"))[ka["score"] > 0]
+        assert np.median(d) < 1e-9

@@ -42,6 +42,10 @@ def lib():
         L.oracle_triangulate_batch.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                C.c_int32]
+        L.oracle_triangulate_batch_ex.argtypes = L.oracle_triangulate_batch.argtypes + [C.c_void_p]
+        L.oracle_set_svd_variant.argtypes = [C.c_void_p, C.c_int32]
+        L.oracle_triangulate_point_v.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                                 C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_reproject_batch.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_void_p, C.c_int32]
         L.oracle_triangulate_point.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
@@ -59,13 +63,15 @@ def _p(a):
 class Oracle:
     """CPU restatement of triangulate_persons (S3D:525-997) + fusedSkeletonCallback (REP:139-235)."""
 
-    def __init__(self, cameras, params=None, ref_hungarian=False):
+    def __init__(self, cameras, params=None, ref_hungarian=False, svd_variant=0):
         self.cameras = np.ascontiguousarray(cameras, dtype=camera_dtype)
         self.params = params if params is not None else default_params()
         self.n_cams = len(self.cameras)
         self._h = lib().oracle_create(self.n_cams, _p(self.cameras), C.byref(self.params))
         if not self._h:
             raise ValueError("oracle_create failed")
+        # 0 = one-sided Hestenes Jacobi (primary oracle), 1 = Eigen 3.3 JacobiSVD restatement (S3D:456)
+        lib().oracle_set_svd_variant(self._h, int(svd_variant))
         self.ref_hungarian = False
         if ref_hungarian:
             if not REF_HUNGARIAN_PATH.exists():
@@ -86,7 +92,9 @@ class Oracle:
         lib().oracle_get_tables(self._h, _p(P), _p(F))
         return P, F
 
-    def triangulate_batch(self, persons, n_persons, h_max, n_threads=1):
+    def triangulate_batch(self, persons, n_persons, h_max, n_threads=1, diag=False):
+        """diag=True adds per-frame 'margin' (smallest relative distance of a floating-point branch decision of the
+        frame to its threshold) and 'cond' (largest sigma_1/sigma_3 of a weighted DLT system of the frame)."""
         persons = np.ascontiguousarray(persons, dtype=person2d_dtype)
         n_frames, n_cams, p_max = persons.shape
         assert n_cams == self.n_cams
@@ -97,10 +105,15 @@ class Oracle:
         n_hyp = np.zeros(n_frames, np.int32)
         n_hung = np.zeros(n_frames, np.int32)
         n_joints = np.zeros(1, np.int64)
-        rc = lib().oracle_triangulate_batch(self._h, n_frames, p_max, _p(persons), _p(n_persons), h_max, _p(out),
-                                            _p(n_out), _p(hyp_of), _p(n_hyp), _p(n_hung), _p(n_joints), n_threads)
-        return dict(status=rc, persons3d=out, n_out=n_out, hyp_of=hyp_of, n_hyp=n_hyp, n_hungarian=n_hung,
-                    n_joints=int(n_joints[0]))
+        dg = np.zeros((n_frames, 2), np.float64) if diag else None
+        rc = lib().oracle_triangulate_batch_ex(self._h, n_frames, p_max, _p(persons), _p(n_persons), h_max, _p(out),
+                                               _p(n_out), _p(hyp_of), _p(n_hyp), _p(n_hung), _p(n_joints), n_threads,
+                                               _p(dg))
+        r = dict(status=rc, persons3d=out, n_out=n_out, hyp_of=hyp_of, n_hyp=n_hyp, n_hungarian=n_hung,
+                 n_joints=int(n_joints[0]))
+        if diag:
+            r["margin"], r["cond"] = dg[:, 0].copy(), dg[:, 1].copy()
+        return r
 
     def reproject_batch(self, persons3d, n_persons3d, n_threads=1):
         persons3d = np.ascontiguousarray(persons3d, dtype=person_cov_dtype)
@@ -150,6 +163,16 @@ def triangulate_point(P, pts, weighted=True, use_double=False):
     e = np.zeros(1)
     lib().oracle_triangulate_point(len(P), _p(P), _p(pts), int(weighted), int(use_double), _p(X), _p(e))
     return X, float(e[0])
+
+
+def triangulate_point_v(P, pts, weighted=True, use_double=False, svd_variant=0):
+    """Single DLT solve with the chosen SVD variant; returns (X, reprojection error, singular values descending)."""
+    P = np.ascontiguousarray(P, np.float64).reshape(-1, 12)
+    pts = np.ascontiguousarray(pts, np.float64).reshape(-1, 3)
+    X, e, sv = np.zeros(3), np.zeros(1), np.zeros(4)
+    lib().oracle_triangulate_point_v(len(P), _p(P), _p(pts), int(weighted), int(use_double), int(svd_variant), _p(X),
+                                     _p(e), _p(sv))
+    return X, float(e[0]), sv
 
 
 def lm_refine(P, pts, X0, max_iters=10):

@@ -125,6 +125,194 @@ void onesided_jacobi(T* B, int rows, int cols, T* W) {
   }
 }
 
+// ----------------------------------------------------------------------------
+// Second SVD variant: restatement of Eigen 3.3 JacobiSVD<Matrix<T,-1,4>, ColPivHouseholderQRPreconditioner>
+// ::compute(A, ComputeThinV) as triangulate() calls it (S3D:456). Eigen is absent from this image, so this follows
+// the published algorithm of Eigen 3.3.x (Ubuntu 18.04 / ROS melodic ships 3.3.4):
+//   JacobiSVD.h   compute(): scale by max|a_ij|; rows != cols -> R-SVD step (column-pivoting Householder QR, work
+//                 matrix = upper-triangular R, V = column permutation); two-sided Jacobi sweeps p = 1..3, q = 0..p-1
+//                 with threshold max(min_normal, 2 eps * maxDiagEntry); real_2x2_jacobi_svd; singular values = |diag|,
+//                 sorted descending with column swaps of V.
+//   ColPivHouseholderQR.h computeInPlace(): pivot = first column of largest updated norm, LAPACK xGEQPF norm down-date.
+//   Householder.h makeHouseholder() / applyHouseholderOnTheLeft(), Jacobi.h makeJacobi() / rotation products.
+// What cannot be restated offline: Eigen's vectorised reduction orders for dynamic-size columns (SSE packets,
+// alignment dependent) - sums over a column run sequentially here. The variant therefore tracks the reference's
+// algorithm (pivoting, rotation order, thresholds), not its last bit. It is used to QUANTIFY how far the primary
+// oracle (one-sided Hestenes Jacobi above) can sit from the reference's arithmetic at S3D:456: see DESIGN.md 2 and
+// tests/test_oracle.py::test_svd_variants_agree.
+// ----------------------------------------------------------------------------
+template <class T>
+struct JRot { T c, s; };
+
+template <class T>
+inline JRot<T> jrot_mul(const JRot<T>& a, const JRot<T>& b) {   // JacobiRotation::operator*
+  return {a.c * b.c - a.s * b.s, a.c * b.s + a.s * b.c};
+}
+
+// JacobiRotation::makeJacobi(x, y, z) for the symmetric 2x2 [[x, y], [y, z]]
+template <class T>
+inline JRot<T> make_jacobi(T x, T y, T z) {
+  const T deno = T(2) * std::fabs(y);
+  if (deno < std::numeric_limits<T>::min()) return {T(1), T(0)};
+  const T tau = (x - z) / deno;
+  const T w = std::sqrt(tau * tau + T(1));
+  const T t = tau > T(0) ? T(1) / (tau + w) : T(1) / (tau - w);
+  const T sign_t = t > T(0) ? T(1) : T(-1);
+  const T n = T(1) / std::sqrt(t * t + T(1));
+  return {n, -sign_t * (y / std::fabs(y)) * std::fabs(t) * n};
+}
+
+// A: rows x 4 row-major (rows >= 4). V: 4x4 row-major, columns ordered by descending singular value; sv[4].
+template <class T>
+void eigen_jacobi_svd_thinV(const T* A, int rows, T* V, T* sv) {
+  const int n = 4;
+  const T tiny = std::numeric_limits<T>::min();
+  T scale = T(0);
+  for (int i = 0; i < rows * n; ++i) { const T a = std::fabs(A[i]); if (a > scale) scale = a; }   // cwiseAbs().maxCoeff()
+  if (scale == T(0)) scale = T(1);
+  T W[16];  // work matrix, row-major W[r*4+c]
+  for (int i = 0; i < 16; ++i) V[i] = T(0);
+  if (rows != n) {
+    // ---- R-SVD step: ColPivHouseholderQR of A / scale
+    std::vector<T> M((size_t)rows * n);   // column-major M[c*rows + r]
+    for (int r = 0; r < rows; ++r)
+      for (int c = 0; c < n; ++c) M[(size_t)c * rows + r] = A[(size_t)r * n + c] / scale;
+    T norm_upd[4], norm_dir[4];
+    int transp[4];
+    for (int k = 0; k < n; ++k) {
+      T s2 = T(0);
+      for (int r = 0; r < rows; ++r) s2 += M[(size_t)k * rows + r] * M[(size_t)k * rows + r];
+      norm_dir[k] = norm_upd[k] = std::sqrt(s2);
+    }
+    const T downdate_thr = std::sqrt(std::numeric_limits<T>::epsilon());
+    for (int k = 0; k < n; ++k) {
+      int big = k;
+      for (int j = k + 1; j < n; ++j)
+        if (norm_upd[j] > norm_upd[big]) big = j;      // first maximum
+      transp[k] = big;
+      if (big != k) {
+        for (int r = 0; r < rows; ++r) std::swap(M[(size_t)k * rows + r], M[(size_t)big * rows + r]);
+        std::swap(norm_upd[k], norm_upd[big]);
+        std::swap(norm_dir[k], norm_dir[big]);
+      }
+      // makeHouseholderInPlace on M(k.., k)
+      T tail2 = T(0);
+      for (int r = k + 1; r < rows; ++r) tail2 += M[(size_t)k * rows + r] * M[(size_t)k * rows + r];
+      const T c0 = M[(size_t)k * rows + k];
+      T tau, beta;
+      if (tail2 <= tiny) {
+        tau = T(0);
+        beta = c0;
+        for (int r = k + 1; r < rows; ++r) M[(size_t)k * rows + r] = T(0);
+      } else {
+        beta = std::sqrt(c0 * c0 + tail2);
+        if (c0 >= T(0)) beta = -beta;
+        for (int r = k + 1; r < rows; ++r) M[(size_t)k * rows + r] /= (c0 - beta);
+        tau = (beta - c0) / beta;
+      }
+      M[(size_t)k * rows + k] = beta;
+      // applyHouseholderOnTheLeft on the bottom-right corner (rows-k) x (n-k-1)
+      if (rows - k == 1) {
+        for (int j = k + 1; j < n; ++j) M[(size_t)j * rows + k] *= T(1) - tau;
+      } else if (tau != T(0)) {
+        for (int j = k + 1; j < n; ++j) {
+          T tmp = T(0);
+          for (int r = k + 1; r < rows; ++r) tmp += M[(size_t)k * rows + r] * M[(size_t)j * rows + r];
+          tmp += M[(size_t)j * rows + k];
+          M[(size_t)j * rows + k] -= tau * tmp;
+          for (int r = k + 1; r < rows; ++r) M[(size_t)j * rows + r] -= (tau * M[(size_t)k * rows + r]) * tmp;
+        }
+      }
+      // norm down-date (LAPACK xGEQPF)
+      for (int j = k + 1; j < n; ++j) {
+        if (norm_upd[j] != T(0)) {
+          T temp = std::fabs(M[(size_t)j * rows + k]) / norm_upd[j];
+          temp = (T(1) + temp) * (T(1) - temp);
+          temp = temp < T(0) ? T(0) : temp;
+          const T q = norm_upd[j] / norm_dir[j];
+          const T temp2 = temp * (q * q);
+          if (temp2 <= downdate_thr) {
+            T s2 = T(0);
+            for (int r = k + 1; r < rows; ++r) s2 += M[(size_t)j * rows + r] * M[(size_t)j * rows + r];
+            norm_dir[j] = norm_upd[j] = std::sqrt(s2);
+          } else {
+            norm_upd[j] *= std::sqrt(temp);
+          }
+        }
+      }
+    }
+    int perm[4] = {0, 1, 2, 3};
+    for (int k = 0; k < n; ++k) std::swap(perm[k], perm[transp[k]]);   // applyTranspositionOnTheRight
+    for (int r = 0; r < n; ++r)
+      for (int c = 0; c < n; ++c) W[r * n + c] = c >= r ? M[(size_t)c * rows + r] : T(0);   // triangularView<Upper>
+    for (int j = 0; j < n; ++j) V[perm[j] * n + j] = T(1);   // m_matrixV = colsPermutation
+  } else {
+    for (int i = 0; i < 16; ++i) W[i] = A[i] / scale;
+    for (int i = 0; i < n; ++i) V[i * n + i] = T(1);
+  }
+  // ---- two-sided Jacobi sweeps
+  const T precision = T(2) * std::numeric_limits<T>::epsilon();
+  T max_diag = T(0);
+  for (int i = 0; i < n; ++i) max_diag = std::max(max_diag, std::fabs(W[i * n + i]));
+  bool finished = false;
+  int guard = 0;
+  while (!finished && ++guard < 1000) {
+    finished = true;
+    for (int p = 1; p < n; ++p)
+      for (int q = 0; q < p; ++q) {
+        const T threshold = std::max(tiny, precision * max_diag);
+        if (std::fabs(W[p * n + q]) > threshold || std::fabs(W[q * n + p]) > threshold) {
+          finished = false;
+          // real_2x2_jacobi_svd
+          T m00 = W[p * n + p], m01 = W[p * n + q], m10 = W[q * n + p], m11 = W[q * n + q];
+          JRot<T> rot1;
+          const T t = m00 + m11, d = m10 - m01;
+          if (std::fabs(d) < tiny) {
+            rot1 = {T(1), T(0)};
+          } else {
+            const T u = t / d;
+            const T tmp = std::sqrt(T(1) + u * u);
+            rot1 = {u / tmp, T(1) / tmp};
+          }
+          {  // m.applyOnTheLeft(0, 1, rot1)
+            const T x0 = m00, y0 = m10, x1 = m01, y1 = m11;
+            m00 = rot1.c * x0 + rot1.s * y0; m10 = -rot1.s * x0 + rot1.c * y0;
+            m01 = rot1.c * x1 + rot1.s * y1; m11 = -rot1.s * x1 + rot1.c * y1;
+          }
+          const JRot<T> j_right = make_jacobi<T>(m00, m01, m11);
+          const JRot<T> j_left = jrot_mul<T>(rot1, JRot<T>{j_right.c, -j_right.s});
+          for (int i = 0; i < n; ++i) {  // applyOnTheLeft(p, q, j_left): rows p, q
+            const T x = W[p * n + i], y = W[q * n + i];
+            W[p * n + i] = j_left.c * x + j_left.s * y;
+            W[q * n + i] = -j_left.s * x + j_left.c * y;
+          }
+          for (int i = 0; i < n; ++i) {  // applyOnTheRight(p, q, j_right): columns p, q with the transposed rotation
+            const T x = W[i * n + p], y = W[i * n + q];
+            W[i * n + p] = j_right.c * x - j_right.s * y;
+            W[i * n + q] = j_right.s * x + j_right.c * y;
+          }
+          for (int i = 0; i < n; ++i) {
+            const T x = V[i * n + p], y = V[i * n + q];
+            V[i * n + p] = j_right.c * x - j_right.s * y;
+            V[i * n + q] = j_right.s * x + j_right.c * y;
+          }
+          max_diag = std::max(max_diag, std::max(std::fabs(W[p * n + p]), std::fabs(W[q * n + q])));
+        }
+      }
+  }
+  for (int i = 0; i < n; ++i) sv[i] = std::fabs(W[i * n + i]) * scale;
+  for (int i = 0; i < n; ++i) {   // descending order, column swaps of V
+    int pos = i;
+    for (int j = i + 1; j < n; ++j)
+      if (sv[j] > sv[pos]) pos = j;
+    if (sv[pos] == T(0)) break;
+    if (pos != i) {
+      std::swap(sv[i], sv[pos]);
+      for (int r = 0; r < n; ++r) std::swap(V[r * n + i], V[r * n + pos]);
+    }
+  }
+}
+
 // pseudo_inv34d S3D:236-240: pinv of a 3x4 (row-major M[12]) -> 4x3 (row-major out[12]).
 void pseudo_inv34(const double* M, double* out) {
   // SVD of M^T (4x3): M^T = Q diag(s) W^T  =>  M = W diag(s) Q^T,  pinv(M) = Q diag(1/s) W^T
@@ -173,6 +361,7 @@ struct Tables {
   std::vector<float> Pf;   // [C][12] cast to float (camera_matrices S3D:1208-1211)
   std::vector<float> F;    // [C(C-1)/2][9] row-major float (S3D:1195-1204)
   std::vector<ses3d_camera> cams;
+  int svd_variant = 0;     // 0: Hestenes one-sided Jacobi (primary), 1: Eigen JacobiSVD restatement
   void* ref_hungarian_lib = nullptr;
   void (*ref_hungarian)(int*, double*, double*, int, int) = nullptr;
 };
@@ -564,8 +753,11 @@ double reprojection_error(const T X[3], const std::vector<View<T>>& v) {
 }
 
 // triangulate S3D:440-465
+// svd_variant 0: one-sided Hestenes Jacobi (primary oracle); 1: the Eigen JacobiSVD restatement above.
+// sv_out (optional): the four singular values of A in descending order.
 template <class T>
-void triangulate(const std::vector<View<T>>& v, bool weight_by_conf, T X[3], double* reproj_error) {
+void triangulate(const std::vector<View<T>>& v, bool weight_by_conf, T X[3], double* reproj_error, int svd_variant = 0,
+                 T* sv_out = nullptr) {
   const int n = (int)v.size();
   std::vector<T> A((size_t)2 * n * 4);
   for (int i = 0; i < n; ++i) {
@@ -580,13 +772,26 @@ void triangulate(const std::vector<View<T>>& v, bool weight_by_conf, T X[3], dou
     }
   }
   T W[16];
-  onesided_jacobi<T>(A.data(), 2 * n, 4, W);
   int best = 0;
-  T best_s = std::numeric_limits<T>::max();
-  for (int c = 0; c < 4; ++c) {
-    T s = 0;
-    for (int r = 0; r < 2 * n; ++r) s += A[(size_t)r * 4 + c] * A[(size_t)r * 4 + c];
-    if (s < best_s) { best_s = s; best = c; }
+  if (svd_variant == 1) {
+    T sv[4];
+    eigen_jacobi_svd_thinV<T>(A.data(), 2 * n, W, sv);
+    best = 3;   // matrixV().col(3), S3D:456
+    if (sv_out) for (int c = 0; c < 4; ++c) sv_out[c] = sv[c];
+  } else {
+    onesided_jacobi<T>(A.data(), 2 * n, 4, W);
+    T best_s = std::numeric_limits<T>::max();
+    T col2[4];
+    for (int c = 0; c < 4; ++c) {
+      T s = 0;
+      for (int r = 0; r < 2 * n; ++r) s += A[(size_t)r * 4 + c] * A[(size_t)r * 4 + c];
+      col2[c] = s;
+      if (s < best_s) { best_s = s; best = c; }
+    }
+    if (sv_out) {
+      std::sort(col2, col2 + 4, [](T a, T b) { return a > b; });
+      for (int c = 0; c < 4; ++c) sv_out[c] = std::sqrt(col2[c]);
+    }
   }
   const T w = W[3 * 4 + best];
   X[0] = W[0 * 4 + best] / w;
@@ -661,7 +866,7 @@ void lm_refine(const std::vector<View<T>>& v, int max_iters, T X[3]) {
 
 // calc_covariance S3D:508-523 with draw_sigma_points S3D:489-506 and mod_samples S3D:471-487
 template <class T>
-void ut_covariance(const T mean[3], const std::vector<View<T>>& v, T cov[9]) {
+void ut_covariance(const T mean[3], const std::vector<View<T>>& v, T cov[9], int svd_variant = 0) {
   const int n = (int)v.size();
   const int dim = 2 * n;
   const T kappa = T(0.5);
@@ -671,7 +876,7 @@ void ut_covariance(const T mean[3], const std::vector<View<T>>& v, T cov[9]) {
   const T b = std::sqrt(T(dim) + kappa);
   std::vector<T> Y((size_t)n_samples * 3);
   std::vector<View<T>> s(v);
-  auto solve = [&](int sample) { triangulate<T>(s, false, &Y[(size_t)sample * 3], nullptr); };
+  auto solve = [&](int sample) { triangulate<T>(s, false, &Y[(size_t)sample * 3], nullptr, svd_variant); };
   solve(0);
   for (int c = 0; c < n; ++c) {
     const T l11 = std::sqrt(v[c].cxx);
@@ -700,9 +905,25 @@ inline void add_cov(ses3d_keypoint_cov& kp, double sigma) {  // addToKeypointCov
   kp.cov[0] += sigma * sigma; kp.cov[3] += sigma * sigma; kp.cov[5] += sigma * sigma;
 }
 
+// Diagnostics of one frame for the parity tests (not part of the reference's outputs):
+//   margin  smallest relative distance of any data-dependent floating-point branch of the frame to its threshold
+//           (S3D:748/793 err > 0.05; S3D:775 d < bestDist; S3D:813 best > e_sub && e_sub < 0.9 err; S3D:943 root
+//           distance > 2 m; S3D:964 |feet| > 0.5; S3D:988 merge distance < 0.2). Two correct float implementations
+//           of the SVD may legitimately take different sides when the margin is at rounding level.
+//   cond    largest sigma_1 / sigma_3 of a weighted DLT system of the frame (conditioning of the triangulated point)
+struct FrameDiag {
+  double margin = 1e300;
+  double cond = 0.0;
+  void branch(double value, double threshold, double scale) {
+    const double m = std::fabs(value - threshold) / (std::fabs(scale) > 0 ? std::fabs(scale) : 1.0);
+    if (m < margin) margin = m;
+  }
+};
+
 // per-hypothesis body of the OpenMP loop, S3D:681-975. Returns true if the person is kept.
 template <class T>
-bool triangulate_hypothesis(const Tables& tb, const Hypothesis& hyp, ses3d_person_cov& person) {
+bool triangulate_hypothesis(const Tables& tb, const Hypothesis& hyp, ses3d_person_cov& person, FrameDiag* dg = nullptr) {
+  const int sv_var = tb.svd_variant;
   const SkeletonModel& M = *tb.model;
   const float thrf = tb.prm.triangulation_threshold;
   const double max_reproj = tb.prm.reproj_error_max_acceptable;
@@ -743,7 +964,13 @@ bool triangulate_hypothesis(const Tables& tb, const Hypothesis& hyp, ses3d_perso
 
     double err;
     T X[3];
-    triangulate<T>(views, true, X, &err);  // S3D:746
+    T sv[4];
+    triangulate<T>(views, true, X, &err, sv_var, sv);  // S3D:746
+    if (dg) {
+      if (n >= 3) dg->branch(err, max_reproj, max_reproj);
+      const double c = (double)sv[0] / (double)sv[2];
+      if (c > dg->cond || c != c) dg->cond = c;
+    }
 
     if (err > max_reproj && n == 3) {  // S3D:748-792
       int best = -1;
@@ -762,11 +989,12 @@ bool triangulate_hypothesis(const Tables& tb, const Hypothesis& hyp, ses3d_perso
         const float n1 = sum3(x2 * l1x, y2 * l1y, 1.0f * l1z);
         const float n2 = sum3(x1 * l2x, y1 * l2y, 1.0f * l2z);
         const float d = n1 * n1 / (l1x * l1x + l1y * l1y) + n2 * n2 / (l2x * l2x + l2y * l2y);
+        if (dg) dg->branch(d, best_dist, best_dist);
         if (d < best_dist) { best_dist = d; best = i; }
       }
       if (best != -1) {
         views.erase(views.begin() + best);
-        triangulate<T>(views, true, X, &err);
+        triangulate<T>(views, true, X, &err, sv_var);
         avg_score = ((float)views[0].conf + (float)views[1].conf) / 2.0f;
         n = 2;
       }
@@ -780,7 +1008,8 @@ bool triangulate_hypothesis(const Tables& tb, const Hypothesis& hyp, ses3d_perso
         sub.erase(sub.begin() + i);
         double e_sub;
         T Xs[3];
-        triangulate<T>(sub, true, Xs, &e_sub);
+        triangulate<T>(sub, true, Xs, &e_sub, sv_var);
+        if (dg) { dg->branch(e_sub, best_err, err); dg->branch(e_sub, 0.9 * err, err); }
         if (best_err > e_sub && e_sub < 0.9 * err) {
           best_err = e_sub; best = i;
           bestX[0] = Xs[0]; bestX[1] = Xs[1]; bestX[2] = Xs[2];
@@ -806,7 +1035,7 @@ bool triangulate_hypothesis(const Tables& tb, const Hypothesis& hyp, ses3d_perso
     if (err > max_reproj) avg_score *= (max_reproj / err);  // S3D:840-844
 
     T cov[9];
-    ut_covariance<T>(X, views, cov);  // S3D:846-847
+    ut_covariance<T>(X, views, cov, sv_var);  // S3D:846-847
 
     ses3d_keypoint_cov& out = person.keypoints[M.fusion_idx[k]];  // S3D:849-857
     out.x = static_cast<double>(X[0]); out.y = static_cast<double>(X[1]); out.z = static_cast<double>(X[2]);
@@ -852,6 +1081,7 @@ bool triangulate_hypothesis(const Tables& tb, const Hypothesis& hyp, ses3d_perso
     for (int s = 0; s < NFUS; ++s) {
       ses3d_keypoint_cov& kp = person.keypoints[s];
       if (kp.score > 0) {
+        if (dg) dg->branch(joint_dist(root, kp), tb.prm.max_joint_dist_to_root, tb.prm.max_joint_dist_to_root);
         if (joint_dist(root, kp) > tb.prm.max_joint_dist_to_root) { std::memset(&kp, 0, sizeof(kp)); --num_valid; }
       } else {
         std::memset(&kp, 0, sizeof(kp));
@@ -864,6 +1094,7 @@ bool triangulate_hypothesis(const Tables& tb, const Hypothesis& hyp, ses3d_perso
   if (K[SES3D_FBP_LANKLE].score > 0 && K[SES3D_FBP_RANKLE].score > 0) feet = (K[SES3D_FBP_LANKLE].z + K[SES3D_FBP_RANKLE].z) / 2.0;
   else if (K[SES3D_FBP_LANKLE].score > 0) feet = K[SES3D_FBP_LANKLE].z;
   else if (K[SES3D_FBP_RANKLE].score > 0) feet = K[SES3D_FBP_RANKLE].z;
+  if (dg && feet != 0.0) dg->branch(std::fabs(feet), 0.50, 0.50);
   if (std::fabs(feet) > 0.50) num_valid = 0;
   return num_valid > tb.prm.min_num_valid_keypoints;  // S3D:968
 }
@@ -903,7 +1134,8 @@ void merge_into(ses3d_person_cov& a, const ses3d_person_cov& b) {
 // identical in both variants. *n_joints accumulates the output joints (score > 0).
 template <class T>
 int triangulate_frame(const Tables& tb, int p_max, const ses3d_person2d* persons, const int32_t* n_persons, int h_max,
-                      ses3d_person_cov* out, int32_t* hyp_of, int32_t* n_hyp, int32_t* n_hung, int64_t* n_joints) {
+                      ses3d_person_cov* out, int32_t* hyp_of, int32_t* n_hyp, int32_t* n_hung, int64_t* n_joints,
+                      FrameDiag* dg = nullptr) {
   AssocResult ar;
   associate(tb, p_max, persons, n_persons, ar);
   if (hyp_of) {
@@ -916,10 +1148,11 @@ int triangulate_frame(const Tables& tb, int p_max, const ses3d_person2d* persons
   std::vector<ses3d_person_cov> kept;
   for (size_t h = 0; h < ar.H.size(); ++h) {  // hypothesis order = the reference built without OpenMP
     ses3d_person_cov person;
-    if (triangulate_hypothesis<T>(tb, ar.H[h], person)) kept.push_back(person);
+    if (triangulate_hypothesis<T>(tb, ar.H[h], person, dg)) kept.push_back(person);
   }
   for (size_t i = 0; i < kept.size(); ++i)  // S3D:984-996
     for (size_t j = i + 1; j < kept.size();) {
+      if (dg) dg->branch(dist3d(kept[i], kept[j]), tb.prm.merge_dist_thresh, tb.prm.merge_dist_thresh);
       if (dist3d(kept[i], kept[j]) < tb.prm.merge_dist_thresh) { merge_into(kept[i], kept[j]); kept.erase(kept.begin() + j); }
       else ++j;
     }
@@ -957,11 +1190,24 @@ void reproject_frame(const Tables& tb, int h_max, const ses3d_person_cov* person
       if (kp.score <= 0.0f) continue;  // REP:181
       // llt of the symmetric 3x3 (lower Cholesky) REP:72, 184-187
       const double a00 = kp.cov[0], a10 = kp.cov[1], a20 = kp.cov[2], a11 = kp.cov[3], a21 = kp.cov[4], a22 = kp.cov[5];
-      const double l00 = std::sqrt(a00);
-      const double l10 = a10 / l00, l20 = a20 / l00;
-      const double l11 = std::sqrt(a11 - l10 * l10);
-      const double l21 = (a21 - l20 * l10) / l11;
-      const double l22 = std::sqrt(a22 - l20 * l20 - l21 * l21);
+      // Eigen 3.3 LLT.h llt_inplace<double, Lower>::unblocked (a 3x3 never takes the blocked path): a non-positive
+      // pivot x <= 0 stops the factorisation and the remaining lower-triangle entries keep their current values;
+      // cov.llt().matrixL() (REP:72) reads that lower triangle without checking info(). A NaN pivot compares false
+      // and continues into sqrt(NaN), as in Eigen.
+      double l00 = a00, l10 = a10, l20 = a20, l11 = a11, l21 = a21, l22 = a22;
+      do {
+        if (l00 <= 0.0) break;
+        l00 = std::sqrt(l00);
+        l10 /= l00; l20 /= l00;
+        double x = l11 - l10 * l10;            // x -= A10.squaredNorm()
+        if (x <= 0.0) break;
+        l11 = x = std::sqrt(x);
+        l21 -= l20 * l10;                      // A21 -= A20 * A10^T
+        l21 /= x;
+        x = l22 - (l20 * l20 + l21 * l21);
+        if (x <= 0.0) break;
+        l22 = std::sqrt(x);
+      } while (false);
       const double L[3][3] = {{l00, 0, 0}, {l10, l11, 0}, {l20, l21, l22}};
       double S[7][3];  // mean, three minus, three plus (REP:68-72)
       for (int s = 0; s < 7; ++s) {
@@ -1068,11 +1314,14 @@ void oracle_munkres(int* assignment, double* cost, const double* dist, int n_row
   munkres(assignment, cost, dist, n_rows, n_cols);
 }
 
-// double-precision variant flag: precision taken from params at create
-int oracle_triangulate_batch(void* h, int32_t n_frames, int32_t p_max, const ses3d_person2d* persons,
-                             const int32_t* n_persons, int32_t h_max, ses3d_person_cov* out, int32_t* n_out,
-                             int32_t* hyp_of, int32_t* n_hyp, int32_t* n_hung, int64_t* n_joints_total,
-                             int32_t n_threads) {
+void oracle_set_svd_variant(void* h, int32_t variant) { static_cast<Tables*>(h)->svd_variant = variant == 1 ? 1 : 0; }
+
+// double-precision variant flag: precision taken from params at create.
+// diag (optional) [n_frames][2]: FrameDiag margin, cond.
+int oracle_triangulate_batch_ex(void* h, int32_t n_frames, int32_t p_max, const ses3d_person2d* persons,
+                                const int32_t* n_persons, int32_t h_max, ses3d_person_cov* out, int32_t* n_out,
+                                int32_t* hyp_of, int32_t* n_hyp, int32_t* n_hung, int64_t* n_joints_total,
+                                int32_t n_threads, double* diag) {
   Tables* tb = static_cast<Tables*>(h);
   const int C = tb->n_cams;
   std::vector<int64_t> joints((size_t)std::max(1, n_threads), 0);
@@ -1085,12 +1334,16 @@ int oracle_triangulate_batch(void* h, int32_t n_frames, int32_t p_max, const ses
       const int32_t* nf = n_persons + (size_t)f * C;
       int32_t* ho = hyp_of ? hyp_of + (size_t)f * C * p_max : nullptr;
       int r;
+      FrameDiag dg;
       if (tb->prm.precision == SES3D_PRECISION_FP64)
         r = triangulate_frame<double>(*tb, p_max, pf, nf, h_max, out + (size_t)f * h_max, ho,
-                                      n_hyp ? n_hyp + f : nullptr, n_hung ? n_hung + f : nullptr, &joints[t]);
+                                      n_hyp ? n_hyp + f : nullptr, n_hung ? n_hung + f : nullptr, &joints[t],
+                                      diag ? &dg : nullptr);
       else
         r = triangulate_frame<float>(*tb, p_max, pf, nf, h_max, out + (size_t)f * h_max, ho,
-                                     n_hyp ? n_hyp + f : nullptr, n_hung ? n_hung + f : nullptr, &joints[t]);
+                                     n_hyp ? n_hyp + f : nullptr, n_hung ? n_hung + f : nullptr, &joints[t],
+                                     diag ? &dg : nullptr);
+      if (diag) { diag[(size_t)f * 2] = dg.margin; diag[(size_t)f * 2 + 1] = dg.cond; }
       if (r < 0) { status[t] = SES3D_E_CAPACITY; n_out[f] = 0; }
       else n_out[f] = r;
     }
@@ -1110,6 +1363,14 @@ int oracle_triangulate_batch(void* h, int32_t n_frames, int32_t p_max, const ses
   return st;
 }
 
+int oracle_triangulate_batch(void* h, int32_t n_frames, int32_t p_max, const ses3d_person2d* persons,
+                             const int32_t* n_persons, int32_t h_max, ses3d_person_cov* out, int32_t* n_out,
+                             int32_t* hyp_of, int32_t* n_hyp, int32_t* n_hung, int64_t* n_joints_total,
+                             int32_t n_threads) {
+  return oracle_triangulate_batch_ex(h, n_frames, p_max, persons, n_persons, h_max, out, n_out, hyp_of, n_hyp, n_hung,
+                                     n_joints_total, n_threads, nullptr);
+}
+
 int oracle_reproject_batch(void* h, int32_t n_frames, int32_t h_max, const ses3d_person_cov* persons3d,
                            const int32_t* n_persons3d, ses3d_person2d* out, int32_t* n_out, int32_t n_threads) {
   Tables* tb = static_cast<Tables*>(h);
@@ -1123,6 +1384,28 @@ int oracle_reproject_batch(void* h, int32_t n_frames, int32_t h_max, const ses3d
 }
 
 // Single DLT solve exposed for the numpy.linalg.svd cross-check: P [n][12], pts [n][3] (x,y,conf)
+void oracle_triangulate_point_v(int32_t n, const double* P, const double* pts, int32_t weighted, int32_t use_double,
+                                int32_t svd_variant, double X[3], double* reproj, double sv[4]) {
+  if (use_double) {
+    std::vector<double> Pd(P, P + (size_t)n * 12);
+    std::vector<View<double>> v(n);
+    for (int i = 0; i < n; ++i) { v[i] = {pts[i * 3], pts[i * 3 + 1], pts[i * 3 + 2], 0, 0, 0, &Pd[(size_t)i * 12], i}; }
+    double Xd[3];
+    triangulate<double>(v, weighted != 0, Xd, reproj, svd_variant, sv);
+    X[0] = Xd[0]; X[1] = Xd[1]; X[2] = Xd[2];
+  } else {
+    std::vector<float> Pf((size_t)n * 12);
+    for (size_t i = 0; i < Pf.size(); ++i) Pf[i] = (float)P[i];
+    std::vector<View<float>> v(n);
+    for (int i = 0; i < n; ++i)
+      v[i] = {(float)pts[i * 3], (float)pts[i * 3 + 1], (float)pts[i * 3 + 2], 0, 0, 0, &Pf[(size_t)i * 12], i};
+    float Xf[3], svf[4];
+    triangulate<float>(v, weighted != 0, Xf, reproj, svd_variant, svf);
+    X[0] = Xf[0]; X[1] = Xf[1]; X[2] = Xf[2];
+    if (sv) for (int i = 0; i < 4; ++i) sv[i] = svf[i];
+  }
+}
+
 void oracle_triangulate_point(int32_t n, const double* P, const double* pts, int32_t weighted, int32_t use_double,
                               double X[3], double* reproj) {
   if (use_double) {

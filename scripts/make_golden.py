@@ -17,25 +17,32 @@ from oracle.binding import Oracle  # noqa: E402
 from smartedgesensor3dhumanpose_b200.layouts import default_params  # noqa: E402
 from tests import helpers  # noqa: E402
 
-CASES = [  # name, workload, frames, outlier fraction, params
-    ("cfg1", "cfg1_ring4x1", 24, 0.0, {}),
-    ("cfg2", "cfg2_hall16x6", 12, 0.0, {}),
-    ("cfg3", "cfg3_hall16x6_dropout", 12, 0.0, {}),
-    ("cfg5_outliers", "cfg5_ring8x4", 12, 0.06, {}),
-    ("dense_outliers", "dense_ring16x6", 6, 0.05, {}),
-    ("cfg2_fp64", "cfg2_hall16x6", 8, 0.0, {"precision": 1}),
-    ("cfg5_lm", "cfg5_ring8x4", 8, 0.0, {"lm_refine": 1}),
-    ("cfg4", "cfg4_crowd64x20", 2, 0.0, {}),
+CASES = [  # name, workload, frames, outlier fraction, params, first frame
+    ("cfg1", "cfg1_ring4x1", 24, 0.0, {}, 0),
+    ("cfg2", "cfg2_hall16x6", 12, 0.0, {}, 0),
+    ("cfg3", "cfg3_hall16x6_dropout", 12, 0.0, {}, 0),
+    ("cfg5_outliers", "cfg5_ring8x4", 12, 0.06, {}, 0),
+    ("dense_outliers", "dense_ring16x6", 6, 0.05, {}, 0),
+    ("cfg2_fp64", "cfg2_hall16x6", 8, 0.0, {"precision": 1}, 0),
+    ("cfg5_lm", "cfg5_ring8x4", 8, 0.0, {"lm_refine": 1}, 0),
+    ("cfg4", "cfg4_crowd64x20", 2, 0.0, {}, 0),
+    # frames of the round-1 parity soak in which the FP32 path left the 1e-3 m tolerance: mismatched / nearly parallel
+    # views put a joint hundreds of metres away, where X = v_xyz / v_w amplifies the last bits of any float SVD
+    ("cfg3_far_6958", "cfg3_hall16x6_dropout", 2, 0.0, {}, 6958),
+    ("cfg3_far_24017", "cfg3_hall16x6_dropout", 2, 0.0, {}, 24017),
+    ("cfg3_far_27427", "cfg3_hall16x6_dropout", 2, 0.0, {}, 27427),
+    ("cfg3_far_36792", "cfg3_hall16x6_dropout", 2, 0.0, {}, 36792),
 ]
 H_MAX = 40
+MARGIN_EPS = 1e-4   # frames with a branch decision closer than this (relative) to its threshold may legitimately differ
 
 
-def run_case(workload, n_frames, outliers, prm):
-    fr = helpers.make_workload(workload, n_frames, h_max=H_MAX)
+def run_case(workload, n_frames, outliers, prm, first_frame=0):
+    fr = helpers.make_workload(workload, n_frames, first_frame=first_frame, h_max=H_MAX)
     if outliers:
         helpers.inject_outliers(fr, outliers, seed=7)
     orc = Oracle(fr["cameras"], default_params(**prm), ref_hungarian=True)
-    r = orc.triangulate_batch(fr["persons"], fr["n_persons"], H_MAX)
+    r = orc.triangulate_batch(fr["persons"], fr["n_persons"], H_MAX, diag=True)
     assert r["status"] == 0
     p = orc.reproject_batch(r["persons3d"], r["n_out"])
     return fr, r, p
@@ -43,8 +50,8 @@ def run_case(workload, n_frames, outliers, prm):
 
 def main():
     out = {}
-    for name, workload, n_frames, outliers, prm in CASES:
-        fr, r, p = run_case(workload, n_frames, outliers, prm)
+    for name, workload, n_frames, outliers, prm, first in CASES:
+        fr, r, p = run_case(workload, n_frames, outliers, prm, first)
         live = np.arange(H_MAX)[None, :] < r["n_out"][:, None]
         kp = r["persons3d"]["keypoints"][live]
         out[f"{name}/input_sha256"] = np.frombuffer(hashlib.sha256(fr["persons"].tobytes() + fr["n_persons"].tobytes()).digest(), np.uint8)
@@ -55,6 +62,7 @@ def main():
         out[f"{name}/xyz"] = np.stack([kp["x"], kp["y"], kp["z"]], -1)
         out[f"{name}/score"] = kp["score"]
         out[f"{name}/cov"] = kp["cov"]
+        out[f"{name}/margin"] = r["margin"]
         live2 = np.arange(H_MAX)[None, None, :] < p["n_out"][:, :, None]
         out[f"{name}/n_out2d"] = p["n_out"].astype(np.int16)
         out[f"{name}/persons2d_sha256"] = np.frombuffer(hashlib.sha256(p["persons2d"][live2].tobytes()).digest(), np.uint8)

@@ -75,6 +75,23 @@ SES_HD double ses_sqrt(double x) { return sqrt(x); }
 SES_HD float ses_abs(float x) { return fabsf(x); }
 SES_HD double ses_abs(double x) { return fabs(x); }
 
+// Single-precision operations that are never contracted into FMAs, for the code paths that must reproduce the
+// reference's x86-64 (SSE2, no FMA) arithmetic bit for bit inside translation units compiled with FMA contraction on.
+// Host builds are compiled with -ffp-contract=off, where the plain operators already mean this.
+#if defined(__CUDA_ARCH__)
+SES_HD float xmul(float a, float b) { return __fmul_rn(a, b); }
+SES_HD float xadd(float a, float b) { return __fadd_rn(a, b); }
+SES_HD float xsub(float a, float b) { return __fsub_rn(a, b); }
+SES_HD float xdiv(float a, float b) { return __fdiv_rn(a, b); }
+SES_HD float xsqrt(float a) { return __fsqrt_rn(a); }
+#else
+SES_HD float xmul(float a, float b) { return a * b; }
+SES_HD float xadd(float a, float b) { return a + b; }
+SES_HD float xsub(float a, float b) { return a - b; }
+SES_HD float xdiv(float a, float b) { return a / b; }
+SES_HD float xsqrt(float a) { return sqrtf(a); }
+#endif
+
 // carve typed arrays out of a byte workspace (shared memory on the GPU)
 struct Arena {
   unsigned char* p;

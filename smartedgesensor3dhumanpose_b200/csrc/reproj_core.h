@@ -107,12 +107,25 @@ SES_HD void reproject_frame(Team& tm, const Tables& tb, int h_max, int cap_rec, 
         const bool present = kp.score > 0.0f;  // REP:181
         ws.sscore[e] = present ? kp.score : 0.f;
         if (!present) return;
-        // lower Cholesky of [[c0 c1 c2][c1 c3 c4][c2 c4 c5]] (REP:72, 184-187)
-        const double l00 = sqrt(kp.cov[0]);
-        const double l10 = kp.cov[1] / l00, l20 = kp.cov[2] / l00;
-        const double l11 = sqrt(kp.cov[3] - l10 * l10);
-        const double l21 = (kp.cov[4] - l20 * l10) / l11;
-        const double l22 = sqrt(kp.cov[5] - l20 * l20 - l21 * l21);
+        // lower Cholesky of [[c0 c1 c2][c1 c3 c4][c2 c4 c5]] as cov.llt().matrixL() evaluates it (REP:72, 184-187):
+        // Eigen's unblocked LLT stops at the first non-positive pivot and leaves the rest of the lower triangle as it
+        // is at that moment; matrixL() is read without checking info(). So a zero or indefinite covariance gives
+        // finite sigma points (all equal to the mean for cov = 0), not NaN. A NaN pivot fails `x <= 0` and
+        // propagates through sqrt like in Eigen.
+        double l00 = kp.cov[0], l10 = kp.cov[1], l20 = kp.cov[2], l11 = kp.cov[3], l21 = kp.cov[4], l22 = kp.cov[5];
+        do {
+          if (l00 <= 0.0) break;
+          l00 = sqrt(l00);
+          l10 /= l00; l20 /= l00;
+          double x = l11 - l10 * l10;
+          if (x <= 0.0) break;
+          l11 = x = sqrt(x);
+          l21 -= l20 * l10;
+          l21 /= x;
+          x = l22 - (l20 * l20 + l21 * l21);
+          if (x <= 0.0) break;
+          l22 = sqrt(x);
+        } while (false);
         const double sp = sqrt(3.0 + 0.5);  // sqrt(DIM + kappa) REP:63,68
         // samples: mean, mean - sp*L e_j (j=0..2), mean + sp*L e_j (REP:68-72)
         const double col[3][3] = {{l00, l10, l20}, {0.0, l11, l21}, {0.0, 0.0, l22}};
@@ -122,7 +135,7 @@ SES_HD void reproject_frame(Team& tm, const Tables& tb, int h_max, int cap_rec, 
           const double nm = n0 > n1 ? (n0 > n2 ? n0 : n2) : (n1 > n2 ? n1 : n2);
           float* c4 = ws.ctr + (size_t)e * 4;
           c4[0] = (float)kp.x; c4[1] = (float)kp.y; c4[2] = (float)kp.z;
-          c4[3] = (float)(sp * sqrt(nm)) * 1.001f + 1e-6f;   // NaN (non-SPD covariance) disables the pre-test
+          c4[3] = (float)(sp * sqrt(nm)) * 1.001f + 1e-6f;   // NaN entries disable the pre-test
         }
         S[0] = kp.x; S[1] = kp.y; S[2] = kp.z;
         for (int j = 0; j < 3; ++j) {

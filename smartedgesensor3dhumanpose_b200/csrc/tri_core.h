@@ -198,6 +198,97 @@ SES_HD void solve_weighted(const Tables& tb, const TriWs<T>& ws, int k, const ui
   *err = reproj_error<T>(tb, ws, k, list, n, skip, X);
 }
 
+// ---- far points: exact re-solve in the oracle's operation order ----------------------------------------------
+// The DLT returns a homogeneous vector v and the joint is X = v_xyz / v_w (hnormalized, S3D:459). For a point at
+// distance |X| from the rig origin v_w ~ 1/|X|, so a rounding error dv of the unit vector moves X by ~ dv |X|^2: two
+// nearly parallel rays that "meet" hundreds of metres away (mismatched views, gross outliers) land wherever the last
+// bits of the particular float SVD put them. Measured (scripts/soak_hostsim.py): inside 15 m the Gram / inverse
+// iteration path is within 5e-5 m of the oracle, beyond 50 m it can be 1e-2 m off - and so is any other float SVD
+// (the oracle's two SVD variants differ by the same amount there). Such joints are therefore re-solved exactly as
+// the reference's data flow is restated in the oracle: rows of A built without FMA contraction, one-sided Jacobi
+// on the 2n x 4 matrix with sequential column sums, same rotation formulas, same column selection - bit for bit,
+// so they carry no tolerance at all. A holds 2n x 4 floats in the warp's sigma-point staging area (idle at this point).
+constexpr float FAR_POINT_R2 = 20.0f * 20.0f;
+
+template <class Team>
+SES_HD void exact_weighted_resolve(Team& tm, const Tables& tb, const TriWs<float>& ws, int k, const uint8_t* list, int n) {
+  float* B = ws.Y;           // [2n][4] row-major, as the oracle holds A
+  float* W = B + 8 * n;      // [4][4] accumulated right rotations
+  const int rows = 2 * n;
+  tm.pfor(rows, [&](int r) {   // triangulate(), S3D:444-454, weight_by_conf = true
+    const int o = list[r >> 1], half = r & 1;
+    const ViewKp<float>& v = ws.vw[o * NKP + k];
+    const float* P = tb.camf[ws.obs_cam[o]].P;
+    const float m = half ? v.y : v.x;
+    float row[4];
+    for (int c = 0; c < 4; ++c) row[c] = xsub(xmul(m, P[8 + c]), P[half * 4 + c]);
+    const float z = xadd(xadd(xmul(row[0], row[0]), xmul(row[1], row[1])), xadd(xmul(row[2], row[2]), xmul(row[3], row[3])));
+    if (z > 0.f) {
+      const float nrm = xsqrt(z);
+      for (int c = 0; c < 4; ++c) row[c] = xdiv(row[c], nrm);
+    }
+    for (int c = 0; c < 4; ++c) B[r * 4 + c] = xmul(row[c], v.conf);
+  });
+  tm.pfor(16, [&](int i) { W[i] = (i >> 2) == (i & 3) ? 1.f : 0.f; });
+  const float eps = 1.1920929e-7f;
+  for (int sweep = 0; sweep < 60; ++sweep) {   // every thread evaluates the same sums -> the same decisions
+    bool rotated = false;
+    for (int p = 0; p < 3; ++p)
+      for (int q = p + 1; q < 4; ++q) {
+        float alpha = 0.f, beta = 0.f, gamma = 0.f;
+        for (int r = 0; r < rows; ++r) {
+          const float bp = B[r * 4 + p], bq = B[r * 4 + q];
+          alpha = xadd(alpha, xmul(bp, bp));
+          beta = xadd(beta, xmul(bq, bq));
+          gamma = xadd(gamma, xmul(bp, bq));
+        }
+        tm.sync();   // all reads of B done before anybody rotates its rows
+        if (ses_abs(gamma) <= xmul(eps, xsqrt(xmul(alpha, beta))) || gamma == 0.f) continue;
+        rotated = true;
+        const float zeta = xdiv(xsub(beta, alpha), xmul(2.f, gamma));
+        const float t = xdiv(zeta >= 0.f ? 1.f : -1.f, xadd(ses_abs(zeta), xsqrt(xadd(1.f, xmul(zeta, zeta)))));
+        const float c = xdiv(1.f, xsqrt(xadd(1.f, xmul(t, t))));
+        const float sn = xmul(c, t);
+        tm.pfor(rows + 4, [&](int r) {
+          float* row = r < rows ? B + r * 4 : W + (r - rows) * 4;
+          const float bp = row[p], bq = row[q];
+          row[p] = xsub(xmul(c, bp), xmul(sn, bq));
+          row[q] = xadd(xmul(sn, bp), xmul(c, bq));
+        });
+      }
+    if (!rotated) break;
+  }
+  int best = 0;
+  float best_s = FLT_MAX;
+  for (int c = 0; c < 4; ++c) {
+    float sq = 0.f;
+    for (int r = 0; r < rows; ++r) sq = xadd(sq, xmul(B[r * 4 + c], B[r * 4 + c]));
+    if (sq < best_s) { best_s = sq; best = c; }
+  }
+  const float w = W[12 + best];
+  const float X[3] = {xdiv(W[best], w), xdiv(W[4 + best], w), xdiv(W[8 + best], w)};
+  double avg = 0., norm = 0.;   // calcReprojectionError, S3D:425-438
+  for (int i = 0; i < n; ++i) {
+    const int o = list[i];
+    const ViewKp<float>& v = ws.vw[o * NKP + k];
+    const float* P = tb.camf[ws.obs_cam[o]].P;
+    const float a = xadd(xadd(xmul(P[0], X[0]), xmul(P[1], X[1])), xadd(xmul(P[2], X[2]), xmul(P[3], 1.f)));
+    const float b = xadd(xadd(xmul(P[4], X[0]), xmul(P[5], X[1])), xadd(xmul(P[6], X[2]), xmul(P[7], 1.f)));
+    const float cc = xadd(xadd(xmul(P[8], X[0]), xmul(P[9], X[1])), xadd(xmul(P[10], X[2]), xmul(P[11], 1.f)));
+    const float dx = xsub(xdiv(a, cc), v.x), dy = xsub(xdiv(b, cc), v.y);
+    const float e = xsqrt(xadd(xmul(dx, dx), xmul(dy, dy)));
+    avg += static_cast<double>(xmul(v.conf, e));
+    norm += static_cast<double>(v.conf);
+  }
+  tm.sync();
+  tm.single([&] {
+    ws.jX[k * 3] = X[0]; ws.jX[k * 3 + 1] = X[1]; ws.jX[k * 3 + 2] = X[2];
+    ws.jerr[k] = avg / norm;
+  });
+}
+template <class Team>
+SES_HD void exact_weighted_resolve(Team&, const Tables&, const TriWs<double>&, int, const uint8_t*, int) {}
+
 // LM refinement of sum conf^2 * ||hnorm(P X~) - x||^2 (self-specified, not in the reference)
 template <class T>
 SES_HD void lm_refine_joint(const Tables& tb, const TriWs<T>& ws, int k, const uint8_t* list, int n, T X[3]) {
@@ -406,6 +497,21 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
       });
     }
     k0 = k1;
+  }
+
+  // far points and high-residual joints (FP32 mode): exact re-solve of the final view set, see exact_weighted_resolve
+  if (sizeof(T) == 4) {
+    const int cap_n = (int)((size_t)Y_CHUNK * 3 - 16) / 8;
+    for (int k = 0; k < NKP; ++k) {
+      const int n = ws.jn[k];
+      if (n < 2 || n > cap_n) continue;
+      const T x = ws.jX[k * 3], y = ws.jX[k * 3 + 1], z = ws.jX[k * 3 + 2];
+      // second trigger: a residual above the acceptance threshold (gross outlier left in the view set). The large
+      // smallest singular value narrows the gap to the next one, which amplifies rounding the same way, and the
+      // residual scales the published score (S3D:840-844) - solved exactly, both match the oracle to the last bit.
+      if (!(x * x + y * y + z * z > T(FAR_POINT_R2)) && !(ws.jerr[k] > max_reproj)) continue;
+      exact_weighted_resolve(tm, tb, ws, k, ws.vlist + k * C, n);
+    }
   }
 
   // optional LM, down-weight (S3D:840-844), then the unweighted base system of the final view set:

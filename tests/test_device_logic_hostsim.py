@@ -46,18 +46,37 @@ def test_fp64_mode():
     helpers.compare_persons3d(ro, rh, 1e-4, cov_rtol=1e-6, score_tol=1e-6)
 
 
-@pytest.mark.parametrize("name,n_frames", [("cfg5_ring8x4", 150), ("dense_ring16x6", 40)])
+MARGIN_EPS = 1e-4
+
+
+@pytest.mark.parametrize("name,n_frames", [("cfg5_ring8x4", 400), ("dense_ring16x6", 60)])
 def test_outlier_rejection_branches(name, n_frames):
-    fr, ro, rh = _pair(name, n_frames, outliers=0.06, h_max=40)
+    """Frames whose closest branch decision is inside the eps-band around its threshold are excluded (the oracle's
+    'margin' diagnostic); every other frame must agree completely (see tests/test_gpu_parity.py)."""
+    fr = helpers.make_workload(name, n_frames, h_max=40)
+    helpers.inject_outliers(fr, 0.06)
+    ro = Oracle(fr["cameras"]).triangulate_batch(fr["persons"], fr["n_persons"], 40, n_threads=4, diag=True)
+    rh = HostSim(fr["cameras"]).triangulate_batch(fr["persons"], fr["n_persons"], 40)
     assert np.array_equal(ro["hyp_of"], rh["hyp_of"])
-    bad = 0
-    for f in range(n_frames):
-        sub = lambda r: dict(persons3d=r["persons3d"][f:f + 1], n_out=r["n_out"][f:f + 1])
-        try:
-            helpers.compare_persons3d(sub(ro), sub(rh), 1e-3, cov_rtol=5e-2)
-        except AssertionError:
-            bad += 1
-    assert bad <= max(1, n_frames // 100)
+    keep = ro["margin"] >= MARGIN_EPS
+    assert (~keep).sum() <= n_frames // 50
+    sub = lambda r: dict(persons3d=r["persons3d"][keep], n_out=r["n_out"][keep])
+    helpers.compare_persons3d(sub(ro), sub(rh), 1e-3, cov_rtol=1e-2)
+
+
+@pytest.mark.parametrize("first", [6958, 24017, 27427, 36792])
+def test_far_points_are_resolved_exactly(first):
+    """Soak offenders of round 1 (cfg3): a joint triangulated hundreds of metres away. The device algorithm re-solves
+    such joints in the oracle's operation order (tri_core.h::exact_weighted_resolve): bit-identical position and score."""
+    fr = helpers.make_workload("cfg3_hall16x6_dropout", 2, first_frame=first, h_max=40)
+    ro = Oracle(fr["cameras"]).triangulate_batch(fr["persons"], fr["n_persons"], 40)
+    rh = HostSim(fr["cameras"]).triangulate_batch(fr["persons"], fr["n_persons"], 40)
+    helpers.compare_persons3d(ro, rh, 1e-3)
+    ka, kb = ro["persons3d"]["keypoints"], rh["persons3d"]["keypoints"]
+    far = (ka["score"] > 0) & (ka["x"] ** 2 + ka["y"] ** 2 + ka["z"] ** 2 > 21.0 ** 2)
+    assert far.any()
+    for c in ("x", "y", "z", "score"):
+        assert np.array_equal(ka[c][far], kb[c][far])
 
 
 def test_lm_refinement():

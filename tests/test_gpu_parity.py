@@ -48,21 +48,73 @@ def test_joints_fp64_mode(name, n_frames):
     helpers.compare_persons3d(ro, rg, POS_TOL_FP64, cov_rtol=1e-6, score_tol=1e-6)
 
 
-@pytest.mark.parametrize("name,n_frames", [("cfg5_ring8x4", 600), ("dense_ring16x6", 200), ("cfg2_hall16x6", 600)])
+MARGIN_EPS = 1e-4  # relative half-width of the band around a branch threshold inside which two float SVDs may disagree
+
+
+@pytest.mark.parametrize("name,n_frames", [("cfg5_ring8x4", 1500), ("dense_ring16x6", 300), ("cfg2_hall16x6", 1500)])
 def test_outlier_rejection_branches(name, n_frames):
-    """Gross 2-D outliers exercise the 3-view epipolar and >=4-view leave-one-out branches (S3D:748-838)."""
-    fr, orc, gpu, ro, rg = _run_pair(name, n_frames, outliers=0.06, h_max=40)
+    """Gross 2-D outliers exercise the 3-view epipolar and >=4-view leave-one-out branches (S3D:748-838).
+
+    Branch decisions compare floating-point results with thresholds (S3D:748/793 err > 0.05, S3D:775 d < bestDist,
+    S3D:813 e_sub vs best / 0.9 err, S3D:943, 964, 988). The oracle reports for every frame how close its closest
+    decision came to its threshold (relative); frames inside the band MARGIN_EPS are excluded - two correct float
+    implementations may take different sides there - and the excluded fraction is printed. EVERY other frame must
+    agree: same persons, same joints, positions within 1e-3 m, scores within 2e-5, covariances within 1 %."""
+    fr = helpers.make_workload(name, n_frames, h_max=40)
+    helpers.inject_outliers(fr, 0.06)
+    orc = Oracle(fr["cameras"], ref_hungarian=True)
+    gpu = api.GeometryPipeline(fr["cameras"])
+    ro = orc.triangulate_batch(fr["persons"], fr["n_persons"], 40, n_threads=8, diag=True)
+    rg = gpu.triangulate_batch(fr["persons"], fr["n_persons"], 40)
     assert np.array_equal(ro["hyp_of"], rg["hyp_of"])
-    # near-threshold branch decisions may legitimately differ between two float SVD algorithms:
-    # compare frame by frame and require the mismatching fraction to be tiny
-    bad = 0
-    for f in range(n_frames):
-        sub = lambda r: dict(persons3d=r["persons3d"][f:f + 1], n_out=r["n_out"][f:f + 1])
-        try:
-            helpers.compare_persons3d(sub(ro), sub(rg), POS_TOL_FP32, cov_rtol=5e-2)
-        except AssertionError:
-            bad += 1
-    assert bad <= max(1, n_frames // 200), f"{bad} of {n_frames} frames differ"
+    keep = ro["margin"] >= MARGIN_EPS
+    excluded = int((~keep).sum())
+    print(f"{name}: {excluded} of {n_frames} frames ({100.0 * excluded / n_frames:.2f} %) inside the eps-band {MARGIN_EPS:g}")
+    assert excluded <= n_frames // 50
+    sub = lambda r: dict(persons3d=r["persons3d"][keep], n_out=r["n_out"][keep])
+    st = helpers.compare_persons3d(sub(ro), sub(rg), POS_TOL_FP32, cov_rtol=1e-2)
+    assert st["n_joints"] > 1000
+
+
+def _outlier_chunk(name, f0, n, seed_chunk=20000, frac=0.05):
+    """Frames [f0, f0+n) of the soak's outlier runs: scripts/soak_parity.py injects outliers per 20000-frame chunk with
+    the chunk's first frame as seed, so the chunk is rebuilt and sliced."""
+    c0 = f0 // seed_chunk * seed_chunk
+    fr = helpers.make_workload(name, seed_chunk, first_frame=c0, h_max=40)
+    helpers.inject_outliers(fr, frac, seed=c0)
+    sl = slice(f0 - c0, f0 - c0 + n)
+    return dict(fr, persons=fr["persons"][sl].copy(), n_persons=fr["n_persons"][sl].copy())
+
+
+@pytest.mark.parametrize("name,f0,n,outliers", [
+    ("cfg3_hall16x6_dropout", 6900, 120, False), ("cfg3_hall16x6_dropout", 24000, 60, False),
+    ("cfg3_hall16x6_dropout", 27400, 60, False), ("cfg3_hall16x6_dropout", 36760, 60, False),
+    ("cfg5_ring8x4", 4650, 120, True), ("cfg5_ring8x4", 17300, 300, True), ("cfg5_ring8x4", 18100, 100, True),
+    ("cfg5_ring8x4", 19740, 80, True), ("cfg5_ring8x4", 40480, 60, True), ("cfg5_ring8x4", 53400, 60, True)])
+def test_soak_offender_slices_have_zero_frames_over_tolerance(name, f0, n, outliers):
+    """Fixed slices of the parity soak that contain the frames in which round 1's FP32 path left the 1e-3 m tolerance
+    (cfg3: frames 6958, 24017, 27427, 36792; ring8 + 5 % outliers: 4714, 17544, 18149, 19780, 40502, 53434, ...): joints
+    hundreds of metres away from mismatched / nearly parallel views, and high-residual joints. These are now re-solved
+    in the oracle's operation order (tri_core.h::exact_weighted_resolve), so outside the eps-band NO frame may differ."""
+    if outliers:
+        fr = _outlier_chunk(name, f0, n)
+    else:
+        fr = helpers.make_workload(name, n, first_frame=f0, h_max=40)
+    orc = Oracle(fr["cameras"], ref_hungarian=True)
+    gpu = api.GeometryPipeline(fr["cameras"])
+    ro = orc.triangulate_batch(fr["persons"], fr["n_persons"], 40, n_threads=8, diag=True)
+    rg = gpu.triangulate_batch(fr["persons"], fr["n_persons"], 40)
+    assert np.array_equal(ro["hyp_of"], rg["hyp_of"])
+    keep = ro["margin"] >= MARGIN_EPS
+    assert keep.sum() >= n - 3
+    sub = lambda r: dict(persons3d=r["persons3d"][keep], n_out=r["n_out"][keep])
+    helpers.compare_persons3d(sub(ro), sub(rg), POS_TOL_FP32, cov_rtol=1e-2)
+    # joints beyond the far-point radius (20 m) are exact, not merely within tolerance
+    ka, kb = ro["persons3d"]["keypoints"][keep], rg["persons3d"]["keypoints"][keep]
+    far = (ka["score"] > 0) & (ka["x"] ** 2 + ka["y"] ** 2 + ka["z"] ** 2 > 21.0 ** 2)
+    for c in "xyz":
+        assert np.array_equal(ka[c][far], kb[c][far])
+    assert np.array_equal(ka["score"][far], kb["score"][far])
 
 
 def test_lm_refinement_matches_oracle():
@@ -176,8 +228,8 @@ def test_gpu_against_committed_golden_vectors(case):
     from pathlib import Path
     import scripts.make_golden as mg
     g = np.load(Path(__file__).resolve().parent / "golden" / "golden_v1.npz")
-    name, workload, n_frames, outliers, prm = next(c for c in mg.CASES if c[0] == case)
-    fr = helpers.make_workload(workload, n_frames, h_max=mg.H_MAX)
+    name, workload, n_frames, outliers, prm, first = next(c for c in mg.CASES if c[0] == case)
+    fr = helpers.make_workload(workload, n_frames, first_frame=first, h_max=mg.H_MAX)
     if outliers:
         helpers.inject_outliers(fr, outliers, seed=7)
     assert hashlib.sha256(fr["persons"].tobytes() + fr["n_persons"].tobytes()).digest() == g[f"{name}/input_sha256"].tobytes()
@@ -185,13 +237,17 @@ def test_gpu_against_committed_golden_vectors(case):
     r = gpu.triangulate_batch(fr["persons"], fr["n_persons"], mg.H_MAX)
     assert np.array_equal(r["hyp_of"], g[f"{name}/hyp_of"])
     assert np.array_equal(r["n_hungarian"], g[f"{name}/n_hungarian"]) and np.array_equal(r["n_hyp"], g[f"{name}/n_hyp"])
-    if outliers == 0:
-        assert np.array_equal(r["n_out"], g[f"{name}/n_out"])
-        live = np.arange(mg.H_MAX)[None, :] < r["n_out"][:, None]
-        kp = r["persons3d"]["keypoints"][live]
-        tol = POS_TOL_FP64 if prm.get("precision") else POS_TOL_FP32
-        d = np.linalg.norm(np.stack([kp["x"], kp["y"], kp["z"]], -1) - g[f"{name}/xyz"], axis=-1)
-        assert np.array_equal(kp["score"] > 0, g[f"{name}/score"] > 0) and d[kp["score"] > 0].max() <= tol
+    # positions are checked in every case, outlier cases included; only frames whose closest branch decision lies inside
+    # the eps-band recorded with the fixture are exempt (none in the committed fixture: asserted)
+    keep = g[f"{name}/margin"] >= mg.MARGIN_EPS
+    assert keep.all(), "a golden frame sits inside the eps-band: pick another seed for the fixture"
+    assert np.array_equal(r["n_out"], g[f"{name}/n_out"])
+    live = np.arange(mg.H_MAX)[None, :] < r["n_out"][:, None]
+    kp = r["persons3d"]["keypoints"][live]
+    tol = POS_TOL_FP64 if prm.get("precision") else POS_TOL_FP32
+    d = np.linalg.norm(np.stack([kp["x"], kp["y"], kp["z"]], -1) - g[f"{name}/xyz"], axis=-1)
+    assert np.array_equal(kp["score"] > 0, g[f"{name}/score"] > 0) and d[kp["score"] > 0].max() <= tol
+    assert np.abs(kp["score"] - g[f"{name}/score"]).max() <= 2e-5
 
 
 def test_nan_trap_is_reproduced_not_hidden():

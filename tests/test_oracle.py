@@ -224,6 +224,100 @@ def test_reprojection_closed_form_pinhole():
         assert np.isclose(got["bbox"][0], u[inside].min(), atol=2e-3) and np.isclose(got["bbox"][3], v[inside].max(), atol=2e-3)
 
 
+def _eigen_llt_lower(A):
+    """Independent statement of Eigen 3.3 llt_inplace<.., Lower>::unblocked on a copy of A: stop at the first
+    non-positive pivot, leaving the rest of the lower triangle as it is (LLT.h); returns the lower triangle."""
+    M = np.array(A, np.float64)
+    n = len(M)
+    for k in range(n):
+        x = M[k, k] - float(np.dot(M[k, :k], M[k, :k]))
+        if x <= 0:
+            break
+        M[k, k] = x = np.sqrt(x)
+        if k + 1 < n:
+            M[k + 1:, k] -= M[k + 1:, :k] @ M[k, :k]
+            M[k + 1:, k] /= x
+    return np.tril(M)
+
+
+@pytest.mark.parametrize("cov6,what", [([0, 0, 0, 0, 0, 0], "zero covariance (Nose without limb inflation)"),
+                                       ([1e-4, 5e-4, 0, 1e-4, 0, 1e-4], "indefinite: second pivot negative"),
+                                       ([4e-4, 0, 0, 1e-4, 1e-4, 1e-4], "semi-definite: third pivot zero"),
+                                       ([-1e-4, 1e-5, 2e-5, 1e-4, 0, 1e-4], "negative first pivot")])
+def test_reprojection_llt_follows_eigen_on_degenerate_covariances(cov6, what):
+    """REP:72 `cov.llt().matrixL()`: Eigen's LLT does not produce NaNs for a matrix that is not positive definite, it
+    stops and matrixL() returns the partially factored lower triangle, so the reference publishes FINITE pixels (for
+    cov = 0: the plain pinhole projection with zero 2-D covariance). Checked against a numpy statement of LLT.h."""
+    cams = rigs.ring8()
+    orc = Oracle(cams)
+    p3 = np.zeros((1, 2), person_cov_dtype)
+    X = np.array([0.1, -0.2, 1.1])
+    slot = KP2FUSION_SIMPLE[0]
+    kp = p3[0, 0]["keypoints"][slot]
+    kp["x"], kp["y"], kp["z"], kp["score"] = X[0], X[1], X[2], 0.8
+    kp["cov"] = cov6
+    r = orc.reproject_batch(p3, np.array([1], np.int32))
+    c0, c1, c2, c3, c4, c5 = cov6
+    L = _eigen_llt_lower([[c0, c1, c2], [c1, c3, c4], [c2, c4, c5]])
+    sp = np.sqrt(3.5)
+    S = np.stack([X] + [X - sp * L[:, j] for j in range(3)] + [X + sp * L[:, j] for j in range(3)])
+    w = np.array([1.0] + [1.0] * 6) / 7.0
+    seen = 0
+    for c in range(8):
+        T = cams["T_cam_base"][c].reshape(3, 4)
+        x = (T @ np.concatenate([S, np.ones((7, 1))], 1).T).T
+        u, v = 1000 * x[:, 0] / x[:, 2] + 640, 1000 * x[:, 1] / x[:, 2] + 360
+        mu, mv = (u * w).sum(), (v * w).sum()
+        if not (0 <= mu <= 1280 and 0 <= mv <= 720):
+            continue
+        assert r["n_out"][0, c] == 1, what
+        got = r["persons2d"][0, c, 0]["keypoints"][0]
+        assert np.isfinite([got["x"], got["y"]]).all() and np.isfinite(got["cov"]).all(), what
+        assert abs(got["x"] - mu) < 2e-3 and abs(got["y"] - mv) < 2e-3, what
+        cxx = (w * (u - mu) ** 2).sum()
+        assert abs(got["cov"][0] - cxx) <= 1e-3 * max(cxx, 1e-9) + 1e-9, what
+        seen += 1
+    assert seen >= 4
+
+
+def test_svd_variants_agree():
+    """The primary oracle solves S3D:456 with a one-sided Hestenes Jacobi; the second variant restates Eigen 3.3's
+    JacobiSVD (column-pivoting QR preconditioner + two-sided 2x2 sweeps). In double they must agree to rounding on
+    singular values and on the point (validates the restatement); in float their spread IS the size of the unpinned
+    risk at the Eigen boundary - it must stay far inside the 1e-3 m tolerance for points inside a 15 m hall."""
+    rng = np.random.default_rng(11)
+    cams = rigs.hall16()
+    worst_f = 0.0
+    for trial in range(1500):
+        n = int(rng.integers(2, 10))
+        idx = rng.choice(16, n, replace=False)
+        X = np.array([rng.uniform(-4, 4), rng.uniform(-4, 4), rng.uniform(0, 2)])
+        P = np.stack([cams["T_cam_base"][i].reshape(3, 4) for i in idx])
+        h = P @ np.append(X, 1)
+        pts = np.stack([h[:, 0] / h[:, 2] + rng.normal(0, 2e-3, n), h[:, 1] / h[:, 2] + rng.normal(0, 2e-3, n),
+                        rng.uniform(0.5, 1, n)], 1)
+        Xd0, e0, sv0 = ob.triangulate_point_v(P.reshape(n, 12), pts, True, True, 0)
+        Xd1, e1, sv1 = ob.triangulate_point_v(P.reshape(n, 12), pts, True, True, 1)
+        assert np.linalg.norm(Xd0 - Xd1) < 1e-9 and np.allclose(sv0, sv1, rtol=1e-10, atol=1e-14)
+        assert np.all(np.diff(sv1) <= 0)                      # Eigen sorts descending; col(3) is the smallest
+        Xf0, _, _ = ob.triangulate_point_v(P.reshape(n, 12), pts, True, False, 0)
+        Xf1, _, _ = ob.triangulate_point_v(P.reshape(n, 12), pts, True, False, 1)
+        worst_f = max(worst_f, float(np.linalg.norm(Xf0 - Xf1)))
+        assert np.linalg.norm(Xf0 - Xd0) < 2e-4
+    assert worst_f < 2e-4
+
+
+def test_frame_diagnostics_flag_near_threshold_branches():
+    """diag=True: 'margin' is the smallest relative distance of a branch decision to its threshold. A frame built so
+    that a leave-one-out sub-error sits on the 0.9 err boundary must report a tiny margin; clean frames a large one."""
+    fr = helpers.make_workload("cfg5_ring8x4", 200)
+    r = Oracle(fr["cameras"]).triangulate_batch(fr["persons"], fr["n_persons"], fr["h_max"], diag=True)
+    assert (r["margin"] > 0.3).mean() > 0.95 and np.all(r["cond"] > 1.0)
+    helpers.inject_outliers(fr, 0.06, seed=3)
+    r2 = Oracle(fr["cameras"]).triangulate_batch(fr["persons"], fr["n_persons"], fr["h_max"], diag=True)
+    assert np.median(r2["margin"]) < np.median(r["margin"])    # outliers bring the rejection branches into play
+
+
 # ----------------------------------------------------------------------------- golden vectors
 def _golden_cases():
     import scripts.make_golden as mg
@@ -234,8 +328,8 @@ def _golden_cases():
 def test_oracle_reproduces_golden_vectors(case):
     import scripts.make_golden as mg
     g = np.load(GOLDEN)
-    name, workload, n_frames, outliers, prm = next(c for c in mg.CASES if c[0] == case)
-    fr, r, p = mg.run_case(workload, n_frames, outliers, prm)
+    name, workload, n_frames, outliers, prm, first = next(c for c in mg.CASES if c[0] == case)
+    fr, r, p = mg.run_case(workload, n_frames, outliers, prm, first)
     digest = hashlib.sha256(fr["persons"].tobytes() + fr["n_persons"].tobytes()).digest()
     assert digest == g[f"{name}/input_sha256"].tobytes(), "synthetic generator changed"
     assert np.array_equal(r["hyp_of"], g[f"{name}/hyp_of"])

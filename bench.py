@@ -205,6 +205,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
+    # host placement: this rank's thread (and therefore the pinned buffers it allocates next) on the GPU's NUMA node
+    from smartedgesensor3dhumanpose_b200 import lib as _libmod
+    numa_node = _libmod.bind_thread_to_device_numa(local_rank)
     B = a.frames
     fr = helpers.make_workload(a.workload, B, first_frame=rank * B)
     cams, h_max = fr["cameras"], fr["h_max"]
@@ -391,7 +394,8 @@ def main():
                        "joints_per_frame": work["joints_per_frame"], "mean_views_per_joint": work["mean_views_per_joint"],
                        "mean_detections_per_camera": work["mean_detections_per_camera"],
                        "l2_policy": f"inputs larger than L2 ({h2d / 2**20:.0f} MiB in, {d2h / 2**20:.0f} MiB out per step)",
-                       "sharding": "frames across ranks, no data-path collective; final gather timed separately"},
+                       "sharding": "frames across ranks, no data-path collective; final gather timed separately",
+                       "host_numa_node_rank0": numa_node},
             "roofline": roofline, "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / a.steps, "frames_per_sec": B * world * a.steps / (e2e_ms * 1e-3),

@@ -135,6 +135,9 @@ int ses3d_create(int32_t n_cams, const ses3d_camera* cams, const ses3d_params* p
                  int32_t device, ses3d_handle* out);
 int ses3d_destroy(ses3d_handle h);
 
+/* Number of cameras the handle was created with. */
+int32_t ses3d_n_cams(ses3d_handle h);
+
 /* Read back the constant tables (host memory): P [n_cams][12] float row-major,
  * F [n_cams*(n_cams-1)/2][9] float row-major in get_fundamental_idx order (S3D:242-253). */
 int ses3d_get_tables(ses3d_handle h, float* P, float* F);
@@ -145,8 +148,13 @@ int ses3d_get_tables(ses3d_handle h, float* P, float* F);
  * Output persons are in hypothesis-index order (the reference built without
  * OpenMP), after plausibility checks and merge. Fewer than two cameras with
  * detections is not an error (n_out = 0, S3D:557-560).
- * stream: a cudaStream_t cast to void* (NULL = the handle's own stream); the
- * call is synchronous for host buffers and stream-ordered for device buffers. */
+ * stream: a cudaStream_t cast to void*, used by device-buffer calls only. NULL means the legacy default stream
+ * (stream 0), exactly as a NULL cudaStream_t does in the CUDA runtime.
+ * Host-buffer calls are synchronous. Device-buffer calls are STREAM-ORDERED: the kernels are enqueued on `stream`
+ * and the call returns without waiting, so the caller can enqueue the next batch, or its own consumers, behind
+ * it. A capacity overflow (more hypotheses than h_max in some frame) of such a call is reported by ses3d_check()
+ * or by the next batch call on the handle, whichever comes first. One handle owns one set of device scratch: calls
+ * issued on different streams are serialised on the device in call order. */
 int ses3d_triangulate_batch(ses3d_handle h, int32_t n_frames, int32_t p_max,
                             const ses3d_person2d* persons, const int32_t* n_persons,
                             int32_t h_max, ses3d_person_cov* out, int32_t* n_out,
@@ -175,12 +183,48 @@ int ses3d_process_batch(ses3d_handle h, int32_t n_frames, int32_t p_max,
  *   out3d          dense PersonCov records, frame-major, n_out3d [n_frames] run lengths, capacity cap3d records
  *   out2d          dense reprojected Person2D records, frame- then camera-major, n_out2d [n_frames][n_cams],
  *                  capacity cap2d records
- * Offsets are the exclusive prefix sums of the count arrays; totals are returned. Synchronous. */
+ * Offsets are the exclusive prefix sums of the count arrays; totals are returned. Synchronous.
+ * When out3d / out2d are device memory or pinned (page-locked) host memory the results are written straight into
+ * them by the pack kernels - for pinned memory as posted writes over PCIe, no staging copy and no host round trip
+ * between the internal chunks; pageable host outputs are staged on the device and copied. */
 int ses3d_process_batch_ragged(ses3d_handle h, int32_t n_frames, int32_t p_max,
                                const ses3d_person2d* persons_dense, const int32_t* n_persons,
                                int32_t h_max, ses3d_person_cov* out3d, int64_t cap3d, int32_t* n_out3d,
                                ses3d_person2d* out2d, int64_t cap2d, int32_t* n_out2d,
                                int64_t* total3d, int64_t* total2d, uint32_t flags);
+
+/* Wait for the handle's outstanding stream-ordered (device-buffer) work and report its status: SES3D_OK, or
+ * SES3D_E_CAPACITY if a frame of those calls exceeded h_max (results of that call are then incomplete). */
+int ses3d_check(ses3d_handle h);
+
+/* Pin the calling host thread to the CPUs of the NUMA node `device` hangs off (read from sysfs; a no-op where that
+ * information is not available). Call it before allocating the pinned buffers of a rank: on multi-socket boxes the
+ * host<->device copies of the batch calls then stay on the GPU's own PCIe root. numa_node (nullable) receives the
+ * node number or -1. */
+int ses3d_bind_thread_to_device_numa(int32_t device, int32_t* numa_node);
+
+/* ---------------------------------------------------------- single-process multi-GPU
+ * One handle per device of the list (n_devices = 0 / devices = NULL: every visible device). A batch is cut into
+ * contiguous frame ranges, range g = [g N / G, (g+1) N / G) runs on device g from its own host thread (bound to the
+ * GPU's NUMA node); there is no data-path collective. Host buffers only (pinned recommended). */
+typedef struct ses3d_multi_s* ses3d_multi;
+int ses3d_create_multi(int32_t n_cams, const ses3d_camera* cams, const ses3d_params* params, int32_t n_devices,
+                       const int32_t* devices, ses3d_multi* out);
+int ses3d_multi_destroy(ses3d_multi m);
+int32_t ses3d_multi_device_count(ses3d_multi m);
+ses3d_handle ses3d_multi_handle(ses3d_multi m, int32_t i);   /* the i-th device's handle (e.g. for ses3d_reserve) */
+/* ses3d_process_batch over all devices; same argument meaning, host buffers. */
+int ses3d_multi_process_batch(ses3d_multi m, int32_t n_frames, int32_t p_max, const ses3d_person2d* persons,
+                              const int32_t* n_persons, int32_t h_max, ses3d_person_cov* out3d, int32_t* n_out3d,
+                              ses3d_person2d* out2d, int32_t* n_out2d, const ses3d_assoc_dump* dump);
+/* ses3d_process_batch_ragged over all devices. The dense outputs come back as one segment per device: device g
+ * writes its records from index seg[2g] on (= cap * first_frame_g / n_frames: its proportional share of the
+ * buffer) and seg[2g+1] receives how many it wrote; frames stay in order inside a segment, segments are in device
+ * order. seg3d / seg2d: [n_devices][2]. */
+int ses3d_multi_process_batch_ragged(ses3d_multi m, int32_t n_frames, int32_t p_max, const ses3d_person2d* persons_dense,
+                                     const int32_t* n_persons, int32_t h_max, ses3d_person_cov* out3d, int64_t cap3d,
+                                     int32_t* n_out3d, ses3d_person2d* out2d, int64_t cap2d, int32_t* n_out2d,
+                                     int64_t* seg3d, int64_t* seg2d);
 
 /* Pre-size the handle's device scratch (otherwise grown on first use). */
 int ses3d_reserve(ses3d_handle h, int32_t n_frames, int32_t p_max, int32_t h_max);

@@ -144,7 +144,13 @@ class GeometryPipeline:
         return dict(ellipsoids=ell, segments=seg, n_segments=n_seg, segment_slot=slot)
 
     # ----------------------------------------------------- device-buffer calls
-    # Arguments are raw device addresses (e.g. torch_tensor.data_ptr()) on this handle's GPU.
+    # Arguments are raw device addresses (e.g. torch_tensor.data_ptr()) on this handle's GPU. These calls are
+    # STREAM-ORDERED: they enqueue on `stream` (0 = the legacy default stream) and return without waiting. A capacity
+    # overflow is raised by check() or by the next call on the handle.
+    def check(self):
+        """Wait for outstanding stream-ordered work of this handle and raise if a frame exceeded h_max (ses3d_check)."""
+        _lib.check(self._L.ses3d_check(self._h))
+
     def triangulate_device(self, n_frames, p_max, h_max, persons_ptr, n_persons_ptr, out_ptr, n_out_ptr, stream=0,
                            hyp_of_ptr=0, n_hyp_ptr=0, n_hung_ptr=0):
         d = AssocDump(hyp_of_ptr or None, n_hyp_ptr or None, n_hung_ptr or None)
@@ -160,6 +166,66 @@ class GeometryPipeline:
         _lib.check(self._L.ses3d_process_batch(self._h, n_frames, p_max, persons_ptr, n_persons_ptr, h_max, out3d_ptr,
                                                n_out3d_ptr, out2d_ptr, n_out2d_ptr, None, DEVICE_BUFFERS,
                                                stream or None))
+
+
+class MultiPipeline:
+    """One rig on several GPUs from one process (ses3d_create_multi): frames are cut into contiguous ranges, one per
+    device, each driven by its own host thread bound to the GPU's NUMA node; no data-path collective."""
+
+    def __init__(self, cameras, params=None, devices=None):
+        self._L = _lib.load()
+        self.cameras = np.ascontiguousarray(cameras, dtype=camera_dtype)
+        self.n_cams = len(self.cameras)
+        self.params = params if params is not None else default_params()
+        dev = None if devices is None else np.ascontiguousarray(devices, dtype=np.int32)
+        h = C.c_void_p()
+        _lib.check(self._L.ses3d_create_multi(self.n_cams, _p(self.cameras), C.byref(self.params),
+                                              0 if dev is None else len(dev), _p(dev), C.byref(h)))
+        self._h = h
+        self.n_devices = int(self._L.ses3d_multi_device_count(h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.ses3d_multi_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reserve(self, n_frames_per_device, p_max, h_max):
+        for i in range(self.n_devices):
+            _lib.check(self._L.ses3d_reserve(self._L.ses3d_multi_handle(self._h, i), n_frames_per_device, p_max, h_max))
+
+    def process_batch(self, persons, n_persons, h_max, bufs=None, dump=False):
+        persons = np.ascontiguousarray(persons, dtype=person2d_dtype)
+        n_frames, n_cams, p_max = persons.shape
+        n_persons = np.ascontiguousarray(n_persons, dtype=np.int32).reshape(n_frames, n_cams)
+        b = bufs or {}
+        out3d = b["persons3d"] if "persons3d" in b else np.zeros((n_frames, h_max), person_cov_dtype)
+        n3d = b["n_out3d"] if "n_out3d" in b else np.zeros(n_frames, np.int32)
+        out2d = b["persons2d"] if "persons2d" in b else np.zeros((n_frames, n_cams, h_max), person2d_dtype)
+        n2d = b["n_out2d"] if "n_out2d" in b else np.zeros((n_frames, n_cams), np.int32)
+        res = dict(persons3d=out3d, n_out3d=n3d, persons2d=out2d, n_out2d=n2d)
+        d = None
+        if dump:
+            res["hyp_of"] = np.full((n_frames, n_cams, p_max), -1, np.int32)
+            res["n_hyp"] = np.zeros(n_frames, np.int32)
+            res["n_hungarian"] = np.zeros(n_frames, np.int32)
+            d = AssocDump(res["hyp_of"].ctypes.data, res["n_hyp"].ctypes.data, res["n_hungarian"].ctypes.data)
+        _lib.check(self._L.ses3d_multi_process_batch(self._h, n_frames, p_max, _p(persons), _p(n_persons), h_max, _p(out3d),
+                                                     _p(n3d), _p(out2d), _p(n2d), C.byref(d) if d else None))
+        return res
+
+    def process_batch_ragged(self, persons_dense, n_persons, p_max, h_max, out3d, n_out3d, out2d, n_out2d):
+        """Dense records in; dense records out as one segment per device. Returns (seg3d, seg2d), each [n_devices][2] =
+        (first record index, record count) of the device's segment in out3d / out2d."""
+        n_persons = np.ascontiguousarray(n_persons, dtype=np.int32)
+        n_frames = n_persons.shape[0]
+        seg3 = np.zeros((self.n_devices, 2), np.int64)
+        seg2 = np.zeros((self.n_devices, 2), np.int64)
+        _lib.check(self._L.ses3d_multi_process_batch_ragged(self._h, n_frames, p_max, _p(persons_dense), _p(n_persons),
+                                                            h_max, _p(out3d), len(out3d), _p(n_out3d), _p(out2d),
+                                                            len(out2d), _p(n_out2d), _p(seg3), _p(seg2)))
+        return seg3, seg2
 
 
 def to_ragged(persons, n_persons):

@@ -32,6 +32,7 @@ UNITS = [
     ("kernels_markers.cu", []),
     ("prior_api.cpp", []),
     ("api.cpp", []),
+    ("multi.cpp", []),
     ("host_setup.cpp", []),
     ("synth.cpp", []),
     ("frame_assembler.cpp", []),

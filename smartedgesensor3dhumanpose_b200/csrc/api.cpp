@@ -104,6 +104,18 @@ struct ses3d_handle_s {
   Slot slot[kSlots];
   cudaEvent_t fork_ev = nullptr;     // device-buffer calls: the caller's stream forks into the slot streams
   int device_split = 2;              // sub-batches of a device-buffer call that run on concurrent streams
+  ses3d::LaunchCfg cfg;              // SM count + tuning overrides, fixed at create
+  int ragged_chunk_env = 0;          // SES3D_RAGGED_CHUNK
+  int ragged_direct = 1;             // SES3D_RAGGED_DIRECT=0: always stage dense results on the device first
+  // ragged calls: running output totals {3-D records, 2-D records} live on the device and are carried from chunk to
+  // chunk by the scan kernels; scan_ev orders the scans of consecutive chunks across the slot streams
+  DevBuf d_run;
+  cudaEvent_t scan_ev[kSlots] = {nullptr, nullptr, nullptr};
+  // pinned host words: [0..1] totals of the last ragged call, [2] overflow flag snapshot of the last device-buffer call
+  long long* h_words = nullptr;
+  // device-buffer calls return without synchronising; dev_done marks the end of the last one on its stream
+  cudaEvent_t dev_done = nullptr;
+  bool dev_pending = false;
   std::mutex mu;
   int64_t launches = 0;
   bool profiling = false;
@@ -181,7 +193,7 @@ int triangulate_on_device(ses3d_handle_s* h, Scratch& sc, cudaStream_t st, int n
     int32_t* n_hung = n_hung_dump ? n_hung_dump + f0 : sc.n_hung.as<int32_t>();
     {
       ProfScope ps(h, 0, st);
-      CU(ses3d::launch_associate(h->tb, d, pin, nin, need_nk ? sc.nk.as<float>() : nullptr, sc.pairs.as<double>(),
+      CU(ses3d::launch_associate(h->cfg, h->tb, d, pin, nin, need_nk ? sc.nk.as<float>() : nullptr, sc.pairs.as<double>(),
                                  sc.hyp_det.as<int8_t>(),
                                  n_hyp, n_hung, h->d_overflow.as<int32_t>(),
                                  hyp_of ? hyp_of + (size_t)f0 * C * p_max : nullptr, sc.keep.as<int32_t>(),
@@ -189,7 +201,7 @@ int triangulate_on_device(ses3d_handle_s* h, Scratch& sc, cudaStream_t st, int n
     }
     {
       ProfScope ps(h, 1, st);
-      CU(ses3d::launch_triangulate(h->tb, d, pin, sc.hyp_det.as<int8_t>(), sc.work.as<uint32_t>(),
+      CU(ses3d::launch_triangulate(h->cfg, h->tb, d, pin, sc.hyp_det.as<int8_t>(), sc.work.as<uint32_t>(),
                                    sc.work_count.as<int32_t>(), sc.tmp.as<ses3d_person_cov>(), sc.keep.as<int32_t>(), st));
     }
     {
@@ -208,7 +220,7 @@ int reproject_on_device(ses3d_handle_s* h, cudaStream_t st, int n_frames, int h_
   for (int f0 = 0; f0 < n_frames; f0 += kDeviceChunk) {
     const int nf = std::min(kDeviceChunk, n_frames - f0);
     ProfScope ps(h, 3, st);
-    CU(ses3d::launch_reproject(h->tb, nf, h_max, persons3d + (size_t)f0 * h_max, n_persons3d + f0,
+    CU(ses3d::launch_reproject(h->cfg, h->tb, nf, h_max, persons3d + (size_t)f0 * h_max, n_persons3d + f0,
                                out + (size_t)f0 * C * h_max, n_out + (size_t)f0 * C, st));
     h->launches += 1;
   }
@@ -220,6 +232,34 @@ int reproject_on_device(ses3d_handle_s* h, cudaStream_t st, int n_frames, int h_
 int overflow_error(ses3d_handle_s* h) {
   cudaMemset(h->d_overflow.p, 0, 4);
   return fail(SES3D_E_CAPACITY, "a frame produced more hypotheses than h_max");
+}
+
+// Device-buffer calls are stream-ordered: they enqueue their kernels plus a 4-byte snapshot of the sticky overflow
+// flag into pinned memory and return. collect_device_status(wait = true) blocks until that work has finished
+// (ses3d_check); with wait = false it only looks (start of the next call) - either way a pending capacity overflow is
+// reported exactly once.
+int collect_device_status(ses3d_handle_s* h, bool wait) {
+  if (!h->dev_pending) return SES3D_OK;
+  if (wait) {
+    CU(cudaEventSynchronize(h->dev_done));
+  } else {
+    const cudaError_t q = cudaEventQuery(h->dev_done);
+    if (q == cudaErrorNotReady) return SES3D_OK;
+    if (q != cudaSuccess) return cuda_fail(q, "cudaEventQuery(dev_done)");
+  }
+  h->dev_pending = false;
+  if (h->h_words[2]) {
+    h->h_words[2] = 0;
+    return overflow_error(h);
+  }
+  return SES3D_OK;
+}
+
+// Work that is about to be enqueued on `st` shares the handle's scratch with the last device-buffer call: order it
+// behind that call on the device (no host wait).
+cudaError_t order_after_device_work(ses3d_handle_s* h, cudaStream_t st) {
+  if (!h->dev_pending) return cudaSuccess;
+  return cudaStreamWaitEvent(st, h->dev_done, 0);
 }
 
 int check_dims(const ses3d_handle_s* h, int n_frames, int p_max, int h_max) {
@@ -248,8 +288,15 @@ int run_batch(ses3d_handle_s* h, int stages, int n_frames, int p_max, const ses3
   int32_t* n_hyp_d = dump ? dump->n_hyp : nullptr;
   int32_t* n_hung_d = dump ? dump->n_hungarian : nullptr;
 
+  {  // an overflow left behind by an earlier stream-ordered call is reported now (no waiting)
+    const int rc0 = collect_device_status(h, false);
+    if (rc0) return rc0;
+  }
   if (dev) {
-    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->slot[0].stream;
+    // NULL = the legacy default stream, exactly as a NULL cudaStream_t means in the CUDA runtime: the kernels are
+    // ordered with the caller's producers and consumers on that stream
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CU(order_after_device_work(h, st));
     // Large batches are cut into sub-batches that run the kernel chain on concurrent streams: the four kernels
     // stress different resources (FP32 pipe / FP64 pipe / shared-memory latency) and none fills an SM's issue
     // slots or its register / shared-memory budget alone, so CTAs of neighbouring stages co-reside and the
@@ -289,15 +336,19 @@ int run_batch(ses3d_handle_s* h, int stages, int n_frames, int p_max, const ses3
       for (int i = 0; i < n_split; ++i)
         if (h->slot[i].stream != st) CU(cudaStreamWaitEvent(st, h->slot[i].done, 0));
     }
-    int32_t overflow = 0;
-    CU(cudaMemcpyAsync(&overflow, h->d_overflow.p, 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    resolve_events(h);
-    if (overflow) return overflow_error(h);
-    return SES3D_OK;
+    CU(cudaMemcpyAsync(&h->h_words[2], h->d_overflow.p, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(h->dev_done, st));
+    h->dev_pending = true;
+    if (h->profiling) {   // per-kernel timing needs the events resolved: profiling calls are synchronous
+      const int rc1 = collect_device_status(h, true);
+      resolve_events(h);
+      return rc1;
+    }
+    return SES3D_OK;   // stream-ordered: no host synchronisation (ses3d_check / the next call report an overflow)
   }
 
-  // host buffers: stream chunks through the two slots
+  // host buffers: stream chunks through the slots
+  for (Slot& sl : h->slot) CU(order_after_device_work(h, sl.stream));
   const int chunk = host_chunk_frames(n_frames);
   int ci = 0;
   for (int f0 = 0; f0 < n_frames; f0 += chunk, ++ci) {
@@ -367,16 +418,58 @@ int run_batch(ses3d_handle_s* h, int stages, int n_frames, int p_max, const ses3
 }
 
 
+// Can a kernel on this device write to `p` directly? True for device memory and for pinned / registered host memory
+// (unified addressing: the mapped device pointer is returned in *dev_ptr). Pageable host memory -> false.
+bool device_accessible(const void* p, void** dev_ptr) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  if ((at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged) && at.devicePointer) {
+    *dev_ptr = at.devicePointer;
+    return true;
+  }
+  return false;
+}
+
 // Ragged variant of process_batch (host or device buffers): dense records in, dense records out.
+//
+// Direct mode (outputs in device memory or in pinned host memory, i.e. whenever a kernel can address them): the
+// running output offsets stay on the device - every chunk's scan kernels start from the totals the previous chunk
+// left in d_run (ordered by one event per chunk) - and the pack kernels write the occupied records straight to their
+// final position in the caller's buffers, for pinned host memory as posted writes over PCIe. No staging copy, no
+// host round trip between chunks; the host synchronises once at the end. Staged mode (pageable host outputs): the
+// dense results are packed on the device and copied out once the host knows the chunk totals.
+int run_ragged_impl(ses3d_handle_s* h, int n_frames, int p_max, const ses3d_person2d* persons_dense,
+                    const int32_t* n_persons, int h_max, ses3d_person_cov* out3d, long long cap3d, int32_t* n_out3d,
+                    ses3d_person2d* out2d, long long cap2d, int32_t* n_out2d, long long* total3d, long long* total2d,
+                    uint32_t flags);
+
 int run_ragged(ses3d_handle_s* h, int n_frames, int p_max, const ses3d_person2d* persons_dense,
                const int32_t* n_persons, int h_max, ses3d_person_cov* out3d, long long cap3d, int32_t* n_out3d,
                ses3d_person2d* out2d, long long cap2d, int32_t* n_out2d, long long* total3d, long long* total2d,
                uint32_t flags) {
   std::lock_guard<std::mutex> lock(h->mu);
   CU(cudaSetDevice(h->device));
+  const int rc = run_ragged_impl(h, n_frames, p_max, persons_dense, n_persons, h_max, out3d, cap3d, n_out3d, out2d, cap2d,
+                                 n_out2d, total3d, total2d, flags);
+  if (rc != SES3D_OK) {   // nothing may still be writing into the caller's buffers when a failed call returns
+    const std::string msg = g_last_error;
+    for (Slot& sl : h->slot) cudaStreamSynchronize(sl.stream);
+    g_last_error = msg;
+  }
+  return rc;
+}
+
+int run_ragged_impl(ses3d_handle_s* h, int n_frames, int p_max, const ses3d_person2d* persons_dense,
+                    const int32_t* n_persons, int h_max, ses3d_person_cov* out3d, long long cap3d, int32_t* n_out3d,
+                    ses3d_person2d* out2d, long long cap2d, int32_t* n_out2d, long long* total3d, long long* total2d,
+                    uint32_t flags) {
   const int C = h->tb.n_cams;
   *total3d = 0;
   *total2d = 0;
+  {
+    const int rc0 = collect_device_status(h, true);   // a ragged call is synchronous anyway
+    if (rc0) return rc0;
+  }
   if (n_frames == 0) return SES3D_OK;
   const bool dev = (flags & SES3D_DEVICE_BUFFERS) != 0;
   const cudaMemcpyKind in_kind = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
@@ -390,14 +483,17 @@ int run_ragged(ses3d_handle_s* h, int n_frames, int p_max, const ses3d_person2d*
     CU(cudaMemcpy(counts_host.data(), n_persons, counts_host.size() * 4, cudaMemcpyDeviceToHost));
     counts = counts_host.data();
   }
+  void *d3 = out3d, *d2 = out2d;
+  bool direct = h->ragged_direct != 0;
+  if (direct && !dev) direct = device_accessible(out3d, &d3) && device_accessible(out2d, &d2);
   // B200, 16384 frames of hall16 x 6 (ms per call): chunk 1024 -> 10.2, 1536 -> 10.3, 2048 -> 10.4, 3072 -> 10.8
   int chunk = std::max(1, std::min(4096, std::max(512, (n_frames + 15) / 16)));
-  if (const char* env = std::getenv("SES3D_RAGGED_CHUNK")) chunk = std::max(1, std::atoi(env));
+  if (h->ragged_chunk_env > 0) chunk = h->ragged_chunk_env;
   long long in_done = 0, run3 = 0, run2 = 0;
   struct Pending { int slot; bool active; } prev{0, false};
   int status = SES3D_OK;
 
-  auto finish = [&](const Pending& pd) -> int {  // totals known -> copy the dense results out
+  auto finish = [&](const Pending& pd) -> int {  // staged mode: totals known -> copy the dense results out
     Slot& s = h->slot[pd.slot];
     CU(cudaEventSynchronize(s.done));
     const long long t3 = s.totals[0], t2 = s.totals[1];
@@ -409,10 +505,15 @@ int run_ragged(ses3d_handle_s* h, int n_frames, int p_max, const ses3d_person2d*
     return SES3D_OK;
   };
 
+  if (direct) {
+    CU(h->d_run.ensure(16));
+    CU(cudaMemsetAsync(h->d_run.p, 0, 16, h->slot[0].stream));
+  }
   int ci = 0;
   for (int f0 = 0; f0 < n_frames && status == SES3D_OK; f0 += chunk, ++ci) {
     const int nf = std::min(chunk, n_frames - f0);
-    Slot& s = h->slot[ci % ses3d_handle_s::kSlots];
+    const int si = ci % ses3d_handle_s::kSlots;
+    Slot& s = h->slot[si];
     cudaStream_t st = s.stream;
     long long n_in = 0;
     for (size_t i = (size_t)f0 * C; i < (size_t)(f0 + nf) * C; ++i) n_in += std::min(std::max(counts[i], 0), p_max);
@@ -427,27 +528,45 @@ int run_ragged(ses3d_handle_s* h, int n_frames, int p_max, const ses3d_person2d*
     CU(s.n_out2d.ensure(u_in * 4));
     CU(s.off3.ensure(((size_t)nf + 1) * 8));
     CU(s.off2.ensure((u_in + 1) * 8));
-    CU(s.c3d.ensure((size_t)nf * h_max * sizeof(ses3d_person_cov)));
-    CU(s.c2d.ensure(u_in * h_max * sizeof(ses3d_person2d)));
+    if (!direct) {
+      CU(s.c3d.ensure((size_t)nf * h_max * sizeof(ses3d_person_cov)));
+      CU(s.c2d.ensure(u_in * h_max * sizeof(ses3d_person2d)));
+    }
     CU(cudaMemcpyAsync(s.n_persons.p, n_persons + (size_t)f0 * C, u_in * 4, in_kind, st));
     if (n_in) CU(cudaMemcpyAsync(s.in_dense.p, persons_dense + in_done, (size_t)n_in * sizeof(ses3d_person2d), in_kind, st));
     in_done += n_in;
-    CU(ses3d::launch_scan_counts(s.n_persons.as<int32_t>(), (int)u_in, p_max, s.in_off.as<long long>(), st));
+    CU(ses3d::launch_scan_counts(s.n_persons.as<int32_t>(), (int)u_in, p_max, s.in_off.as<long long>(), nullptr, st));
     CU(ses3d::launch_move_records(1, (int)u_in, p_max, (int)sizeof(ses3d_person2d), s.n_persons.as<int32_t>(),
-                                  s.in_off.as<long long>(), s.persons.p, s.in_dense.p, st));
+                                  s.in_off.as<long long>(), s.persons.p, s.in_dense.p, -1, st));
     int rc = triangulate_on_device(h, s.sc, st, nf, p_max, h_max, s.persons.as<ses3d_person2d>(),
                                    s.n_persons.as<int32_t>(), s.out3d.as<ses3d_person_cov>(), s.n_out3d.as<int32_t>(),
                                    nullptr, nullptr, nullptr);
-    if (rc) return rc;
+    if (rc) { status = rc; break; }
     rc = reproject_on_device(h, st, nf, h_max, s.out3d.as<ses3d_person_cov>(), s.n_out3d.as<int32_t>(),
                              s.out2d.as<ses3d_person2d>(), s.n_out2d.as<int32_t>());
-    if (rc) return rc;
-    CU(ses3d::launch_scan_counts(s.n_out3d.as<int32_t>(), nf, h_max, s.off3.as<long long>(), st));
+    if (rc) { status = rc; break; }
+    if (direct) {
+      // the scans continue the running totals of the previous chunk (which ran on another slot's stream)
+      if (ci > 0) CU(cudaStreamWaitEvent(st, h->scan_ev[(ci - 1) % ses3d_handle_s::kSlots], 0));
+      long long* run = h->d_run.as<long long>();
+      CU(ses3d::launch_scan_counts(s.n_out3d.as<int32_t>(), nf, h_max, s.off3.as<long long>(), run, st));
+      CU(ses3d::launch_scan_counts(s.n_out2d.as<int32_t>(), (int)u_in, h_max, s.off2.as<long long>(), run + 1, st));
+      CU(cudaEventRecord(h->scan_ev[si], st));
+      CU(ses3d::launch_move_records(0, nf, h_max, (int)sizeof(ses3d_person_cov), s.n_out3d.as<int32_t>(),
+                                    s.off3.as<long long>(), s.out3d.p, d3, cap3d, st));
+      CU(ses3d::launch_move_records(0, (int)u_in, h_max, (int)sizeof(ses3d_person2d), s.n_out2d.as<int32_t>(),
+                                    s.off2.as<long long>(), s.out2d.p, d2, cap2d, st));
+      h->launches += 6;
+      CU(cudaMemcpyAsync(n_out3d + f0, s.n_out3d.p, (size_t)nf * 4, out_kind, st));
+      CU(cudaMemcpyAsync(n_out2d + (size_t)f0 * C, s.n_out2d.p, u_in * 4, out_kind, st));
+      continue;
+    }
+    CU(ses3d::launch_scan_counts(s.n_out3d.as<int32_t>(), nf, h_max, s.off3.as<long long>(), nullptr, st));
     CU(ses3d::launch_move_records(0, nf, h_max, (int)sizeof(ses3d_person_cov), s.n_out3d.as<int32_t>(),
-                                  s.off3.as<long long>(), s.out3d.p, s.c3d.p, st));
-    CU(ses3d::launch_scan_counts(s.n_out2d.as<int32_t>(), (int)u_in, h_max, s.off2.as<long long>(), st));
+                                  s.off3.as<long long>(), s.out3d.p, s.c3d.p, -1, st));
+    CU(ses3d::launch_scan_counts(s.n_out2d.as<int32_t>(), (int)u_in, h_max, s.off2.as<long long>(), nullptr, st));
     CU(ses3d::launch_move_records(0, (int)u_in, h_max, (int)sizeof(ses3d_person2d), s.n_out2d.as<int32_t>(),
-                                  s.off2.as<long long>(), s.out2d.p, s.c2d.p, st));
+                                  s.off2.as<long long>(), s.out2d.p, s.c2d.p, -1, st));
     h->launches += 6;
     CU(cudaMemcpyAsync(&s.totals[0], s.off3.as<long long>() + nf, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(&s.totals[1], s.off2.as<long long>() + u_in, 8, cudaMemcpyDeviceToHost, st));
@@ -455,15 +574,25 @@ int run_ragged(ses3d_handle_s* h, int n_frames, int p_max, const ses3d_person2d*
     CU(cudaMemcpyAsync(n_out2d + (size_t)f0 * C, s.n_out2d.p, u_in * 4, out_kind, st));
     CU(cudaEventRecord(s.done, st));
     if (prev.active) status = finish(prev);   // overlaps with the chunk just enqueued
-    prev = Pending{ci % ses3d_handle_s::kSlots, true};
+    prev = Pending{si, true};
   }
-  if (status == SES3D_OK && prev.active) status = finish(prev);
+  if (!direct && status == SES3D_OK && prev.active) status = finish(prev);
+  if (direct && status == SES3D_OK && ci > 0) {
+    // totals + overflow flag ride at the end of the last chunk's stream, which is ordered behind every scan
+    cudaStream_t st = h->slot[(ci - 1) % ses3d_handle_s::kSlots].stream;
+    CU(cudaMemcpyAsync(&h->h_words[0], h->d_run.p, 16, cudaMemcpyDeviceToHost, st));
+  }
   for (Slot& sl : h->slot) CU(cudaStreamSynchronize(sl.stream));
   resolve_events(h);
   if (status != SES3D_OK) return status;
   int32_t overflow = 0;
   CU(cudaMemcpy(&overflow, h->d_overflow.p, 4, cudaMemcpyDeviceToHost));
   if (overflow) return overflow_error(h);
+  if (direct) {
+    run3 = h->h_words[0];
+    run2 = h->h_words[1];
+    if (run3 > cap3d || run2 > cap2d) return fail(SES3D_E_CAPACITY, "ragged output buffer too small");
+  }
   *total3d = run3;
   *total2d = run2;
   return SES3D_OK;
@@ -532,7 +661,17 @@ int ses3d_create(int32_t n_cams, const ses3d_camera* cams, const ses3d_params* p
     if (ue == cudaSuccess) ue = cudaEventCreateWithFlags(&h->slot[i].done, cudaEventDisableTiming);
   }
   if (ue == cudaSuccess) ue = cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming);
+  if (ue == cudaSuccess) ue = cudaEventCreateWithFlags(&h->dev_done, cudaEventDisableTiming);
+  for (int i = 0; i < ses3d_handle_s::kSlots && ue == cudaSuccess; ++i)
+    ue = cudaEventCreateWithFlags(&h->scan_ev[i], cudaEventDisableTiming);
+  if (ue == cudaSuccess) ue = cudaMallocHost(reinterpret_cast<void**>(&h->h_words), 4 * sizeof(long long));
+  if (ue == cudaSuccess) { h->h_words[0] = h->h_words[1] = h->h_words[2] = h->h_words[3] = 0; }
+  if (ue == cudaSuccess) ue = h->d_run.ensure(16);
+  if (ue == cudaSuccess) ue = ses3d::init_kernels(&h->cfg, device);
+  // tuning overrides are read here, once; nothing on the per-batch path touches the environment
   if (const char* env = getenv("SES3D_DEVICE_SPLIT")) h->device_split = std::max(1, atoi(env));
+  if (const char* env = getenv("SES3D_RAGGED_CHUNK")) h->ragged_chunk_env = std::max(1, atoi(env));
+  if (const char* env = getenv("SES3D_RAGGED_DIRECT")) h->ragged_direct = atoi(env);
   if (ue != cudaSuccess) {
     ses3d_destroy(h);
     return cuda_fail(ue, "ses3d_create upload");
@@ -553,10 +692,16 @@ int ses3d_destroy(ses3d_handle h) {
   cudaSetDevice(h->device);
   for (Slot& s : h->slot) s.release();
   if (h->fork_ev) cudaEventDestroy(h->fork_ev);
+  if (h->dev_done) { cudaEventSynchronize(h->dev_done); cudaEventDestroy(h->dev_done); }
+  for (cudaEvent_t& e : h->scan_ev) if (e) cudaEventDestroy(e);
+  if (h->h_words) cudaFreeHost(h->h_words);
+  h->d_run.release();
   h->d_camf.release(); h->d_camd.release(); h->d_F.release(); h->d_frow.release(); h->d_overflow.release();
   delete h;
   return SES3D_OK;
 }
+
+int32_t ses3d_n_cams(ses3d_handle h) { return h ? h->tb.n_cams : 0; }
 
 int ses3d_get_tables(ses3d_handle h, float* P, float* F) {
   if (!h) return fail(SES3D_E_INVALID, "null handle");
@@ -626,7 +771,7 @@ int ses3d_markers_batch(ses3d_handle h, int32_t n_frames, int32_t h_max, const s
   CU(cudaSetDevice(h->device));
   const size_t units = (size_t)n_frames * h_max;
   if (flags & SES3D_DEVICE_BUFFERS) {
-    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->slot[0].stream;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);   // NULL = legacy default stream
     CU(ses3d::launch_markers(h->tb.model, n_frames, h_max, style, persons3d, n_persons3d, ellipsoids, segments,
                              n_segments, segment_slot, st));
     ++h->launches;
@@ -661,6 +806,13 @@ int ses3d_markers_batch(ses3d_handle h, int32_t n_frames, int32_t h_max, const s
   }
   CU(cudaStreamSynchronize(st));
   return SES3D_OK;
+}
+
+int ses3d_check(ses3d_handle h) {
+  if (!h) return fail(SES3D_E_INVALID, "null handle");
+  std::lock_guard<std::mutex> lock(h->mu);
+  CU(cudaSetDevice(h->device));
+  return collect_device_status(h, true);
 }
 
 int ses3d_reserve(ses3d_handle h, int32_t n_frames, int32_t p_max, int32_t h_max) {

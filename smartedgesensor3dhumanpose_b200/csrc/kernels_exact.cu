@@ -101,18 +101,17 @@ k_munkres_batch(int n, int rows, int cols, const double* __restrict__ cost, int3
   tm.pfor(rows, [&](int r) { assignment[(size_t)i * rows + r] = ws.assignment[r]; });
 }
 
+static const size_t kSmemBudget = 200 * 1024;   // of the 227 KB a CTA may opt in to
+static const size_t kAssocSmemTarget = 64 * 1024;
+
 cudaError_t launch_munkres_batch(int n, int rows, int cols, const double* cost, int32_t* assignment, cudaStream_t st) {
   if (rows < 1 || cols < 1 || rows > 1024 || cols > 127) return cudaErrorInvalidValue;
   const size_t smem = assoc_ws_bytes(1, cols, rows, false);
   if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
-  cudaError_t e = cudaFuncSetAttribute(k_munkres_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
   k_munkres_batch<<<n, 32, smem, st>>>(n, rows, cols, cost, assignment);
   return cudaGetLastError();
 }
 
-static const size_t kSmemBudget = 200 * 1024;   // of the 227 KB a CTA may opt in to
-static const size_t kAssocSmemTarget = 64 * 1024;
 
 size_t associate_smem_bytes(int n_cams, int p_max, int h_cap, bool* needs_scratch) {
   size_t b = assoc_ws_bytes(n_cams, p_max, h_cap, true);
@@ -124,7 +123,36 @@ size_t associate_smem_bytes(int n_cams, int p_max, int h_cap, bool* needs_scratc
 
 size_t associate_pair_table_bytes(int n_cams, int p_max) { return assoc_pair_table_entries(n_cams, p_max) * sizeof(double); }
 
-cudaError_t launch_associate(const Tables& tb, LaunchDims d, const ses3d_person2d* persons, const int32_t* n_persons,
+static int env_int(const char* name, int fallback) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : fallback;
+}
+
+// Once per handle (ses3d_create): SM count, environment overrides, and the opt-in to large dynamic shared memory for
+// every kernel of this translation unit. The attribute is a ceiling, not a reservation: occupancy still follows the
+// bytes each launch actually asks for.
+cudaError_t init_kernels_tri(int device);
+cudaError_t init_kernels(LaunchCfg* cfg, int device) {
+  cfg->device = device;
+  cudaError_t e = cudaDeviceGetAttribute(&cfg->n_sm, cudaDevAttrMultiProcessorCount, device);
+  if (e != cudaSuccess) return e;
+  if (cfg->n_sm <= 0) cfg->n_sm = 148;
+  cfg->assoc_threads = env_int("SES3D_ASSOC_THREADS", 0);
+  if (cfg->assoc_threads) cfg->assoc_threads = std::max(32, std::min(256, cfg->assoc_threads / 32 * 32));
+  cfg->reproj_cap = env_int("SES3D_REPROJ_CAP", 0);
+  cfg->reproj_scap = std::max(1, env_int("SES3D_REPROJ_SCAP", 6));
+  cfg->reproj_threads = std::max(32, std::min(128, env_int("SES3D_REPROJ_THREADS", 128) / 32 * 32));
+  cfg->tri_warps = env_int("SES3D_TRI_WARPS", 2);
+  cfg->tri_warps_f64 = env_int("SES3D_TRI_WARPS_F64", 4);
+  const int budget = (int)kSmemBudget;
+  if ((e = cudaFuncSetAttribute(k_associate, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_reproject, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_munkres_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
+  return init_kernels_tri(device);
+}
+
+cudaError_t launch_associate(const LaunchCfg& cfg, const Tables& tb, LaunchDims d, const ses3d_person2d* persons, const int32_t* n_persons,
                              float* nk_scratch, double* pair_table, int8_t* hyp_det, int32_t* n_hyp, int32_t* n_hung,
                              int32_t* overflow, int32_t* hyp_of_dump, int32_t* keep, uint32_t* work,
                              int32_t* work_count, cudaStream_t st) {
@@ -135,11 +163,9 @@ cudaError_t launch_associate(const Tables& tb, LaunchDims d, const ses3d_person2
   // ms per 16384 frames): 32 -> 1.66, 64 -> 1.41, 96 -> 1.37, 128 -> 1.42, 192 -> 1.67
   int threads = scratch ? 256 : 96;
   if (d.n_frames <= 296) threads = 256;   // fewer frames than two per SM: latency mode (single-frame call 75 -> 60 us)
-  if (const char* env = getenv("SES3D_ASSOC_THREADS")) threads = std::max(32, std::min(256, atoi(env) / 32 * 32));
+  if (cfg.assoc_threads) threads = cfg.assoc_threads;
   if (scratch && !nk_scratch) return cudaErrorInvalidValue;
-  cudaError_t e = cudaFuncSetAttribute(k_associate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(work_count, 0, sizeof(int32_t), st);
+  cudaError_t e = cudaMemsetAsync(work_count, 0, sizeof(int32_t), st);
   if (e != cudaSuccess) return e;
   if (!pair_table) return cudaErrorInvalidValue;
   k_associate<<<d.n_frames, threads, smem, st>>>(tb, d.n_frames, d.p_max, d.h_cap, persons, n_persons,
@@ -152,26 +178,20 @@ cudaError_t launch_finalize(const Tables& tb, LaunchDims d, const int32_t* n_hyp
                             const int32_t* keep, ses3d_person_cov* out, int32_t* n_out, cudaStream_t st) {
   const size_t smem = fin_ws_bytes(d.h_cap);
   if (smem > kSmemBudget) return cudaErrorInvalidConfiguration;
-  cudaError_t e = cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
   k_finalize<<<d.n_frames, 32, smem, st>>>(tb, d.n_frames, d.h_cap, n_hyp, tmp, keep, out, n_out);
   return cudaGetLastError();
 }
 
-cudaError_t launch_reproject(const Tables& tb, int n_frames, int h_max, const ses3d_person_cov* persons3d,
-                             const int32_t* n_persons3d, ses3d_person2d* out, int32_t* n_out, cudaStream_t st) {
+cudaError_t launch_reproject(const LaunchCfg& cfg, const Tables& tb, int n_frames, int h_max,
+                             const ses3d_person_cov* persons3d, const int32_t* n_persons3d, ses3d_person2d* out,
+                             int32_t* n_out, cudaStream_t st) {
   // staging capacity in records: ~28 KB, at least one camera of h_max persons, at most the whole frame
   int cap_rec = std::max(h_max, std::min(tb.n_cams * h_max, std::max(48, 2 * h_max)));   // B200, hall16 x 6: 16 -> 1.25 ms, 32 -> 1.02, 48 -> 0.97, 64 -> 1.10, 96 -> 1.28
-  if (const char* env = getenv("SES3D_REPROJ_CAP")) cap_rec = std::max(h_max, atoi(env));
-  int s_want = 6;
-  if (const char* env = getenv("SES3D_REPROJ_SCAP")) s_want = std::max(1, atoi(env));
-  const int s_cap = reproj_s_cap(tb.n_cams, h_max, s_want);
+  if (cfg.reproj_cap) cap_rec = std::max(h_max, cfg.reproj_cap);
+  const int s_cap = reproj_s_cap(tb.n_cams, h_max, cfg.reproj_scap);
   const size_t smem = reproj_ws_bytes(tb.n_cams, cap_rec, s_cap);
   if (smem > kSmemBudget) return cudaErrorInvalidConfiguration;
-  cudaError_t e = cudaFuncSetAttribute(k_reproject, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  int threads = 128;
-  if (const char* env = getenv("SES3D_REPROJ_THREADS")) threads = std::max(32, std::min(128, atoi(env) / 32 * 32));
+  const int threads = cfg.reproj_threads;
   k_reproject<<<n_frames, threads, smem, st>>>(tb, n_frames, h_max, cap_rec, s_cap, persons3d, n_persons3d, out, n_out);
   return cudaGetLastError();
 }

@@ -61,6 +61,14 @@ cudaError_t launch_prior_reset(const ses3d_prior_params& prm, int n_seq, PriorSe
   return cudaGetLastError();
 }
 
+// tuning overrides, read once per handle creation (ses3d_prior_create -> init_prior_kernels), never per launch
+static int g_prior_group_env = 0, g_prior_warps_env = 0;
+cudaError_t init_prior_kernels(int) {
+  if (const char* env = getenv("SES3D_PRIOR_GROUP")) g_prior_group_env = atoi(env);
+  if (const char* env = getenv("SES3D_PRIOR_WARPS")) g_prior_warps_env = atoi(env);
+  return cudaFuncSetAttribute(k_prior, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+
 cudaError_t launch_prior(const PriorTables& pt, int n_seq, int n_frames, int h_max, int max_tracks,
                          PriorSeqState* states, PriorTrack* tracks, uint8_t* order, const ses3d_person_cov* persons,
                          const int32_t* n_persons, const int64_t* stamp_ns, int n_cams, const float* fb_delay,
@@ -71,19 +79,17 @@ cudaError_t launch_prior(const PriorTables& pt, int n_seq, int n_frames, int h_m
   // group/warps 3/1 23.6, 3/2 19.0, 3/3 22.7, 2/2 22.7, 2/3 19.6, 2/4 22.5, 4/2 24.5 - just enough warps to fit a
   // typical message in one round, and as little shared memory per CTA as possible (occupancy decides).
   int group = std::max(1, std::min(3, h_max));
-  if (const char* env = getenv("SES3D_PRIOR_GROUP")) group = std::max(1, std::min(PRIOR_GMAX, atoi(env)));
+  if (g_prior_group_env > 0) group = std::max(1, std::min(PRIOR_GMAX, g_prior_group_env));
   // two warps per stream whatever h_max is: a fuller message simply takes more rounds of groups, and the smaller CTA
   // keeps eight streams resident per SM (demo chain, h_max 16, 2048 streams: 40.8 ms with 4 warps -> 36.3 ms with 2)
   int warps = std::max(1, std::min(2, (h_max + group - 1) / group));
-  if (const char* env = getenv("SES3D_PRIOR_WARPS")) warps = std::max(1, std::min(8, atoi(env)));
+  if (g_prior_warps_env > 0) warps = std::max(1, std::min(8, g_prior_warps_env));
   size_t ws_bytes = 0, transient_bytes = 0;
   prior_ws_bytes(h_max, max_tracks, &ws_bytes, &transient_bytes);
   const size_t fit_bytes = prior_fit_ws_bytes(group);
   static_assert(sizeof(PriorStatic) % 4 == 0, "copied word by word");
   const size_t smem = kStaticBytes + ws_bytes + std::max(fit_bytes * warps, transient_bytes);
   if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
-  cudaError_t e = cudaFuncSetAttribute(k_prior, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
   k_prior<<<n_seq, 32 * warps, smem, st>>>(pt, n_seq, n_frames, h_max, max_tracks, group, ws_bytes, fit_bytes, states, tracks,
                                             order, persons, n_persons, stamp_ns, n_cams, fb_delay, fused, pred, n_out,
                                             pred_delay, track_of);

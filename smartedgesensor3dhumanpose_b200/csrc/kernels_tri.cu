@@ -33,48 +33,53 @@ k_triangulate(const Tables tb, int p_max, int h_cap, size_t ws_bytes, const ses3
 }
 
 template <class T, int W>
-static cudaError_t launch_tri_impl(const Tables& tb, LaunchDims d, const ses3d_person2d* persons, const int8_t* hyp_det,
-                                   const uint32_t* work, const int32_t* work_count, ses3d_person_cov* tmp,
-                                   int32_t* keep, int n_sm, cudaStream_t st) {
+static cudaError_t launch_tri_impl(LaunchCfg& cfg, const Tables& tb, LaunchDims d, const ses3d_person2d* persons,
+                                   const int8_t* hyp_det, const uint32_t* work, const int32_t* work_count,
+                                   ses3d_person_cov* tmp, int32_t* keep, cudaStream_t st) {
   const size_t ws_bytes = tri_ws_bytes<T>(tb.n_cams);
   const size_t smem = ws_bytes * W;
   if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
   // persistent grid: as many CTAs as fit on the chip at the kernel's occupancy (a multiple of the SM count),
-  // never more than the work
-  cudaError_t e = cudaFuncSetAttribute(k_triangulate<T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // never more than the work. The occupancy query is cached per (kernel, shared-memory size).
+  const void* fn = reinterpret_cast<const void*>(&k_triangulate<T, W>);
   int per_sm = 0;
-  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_triangulate<T, W>, 32 * W, smem);
-  if (e != cudaSuccess) return e;
-  if (per_sm < 1) per_sm = 1;
+  for (int i = 0; i < cfg.n_occ; ++i)
+    if (cfg.occ[i].fn == fn && cfg.occ[i].smem == smem) per_sm = cfg.occ[i].per_sm;
+  if (per_sm == 0) {
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_triangulate<T, W>, 32 * W, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    if (cfg.n_occ < 8) cfg.occ[cfg.n_occ++] = {fn, smem, per_sm};
+  }
   const size_t units = (size_t)d.n_frames * d.h_cap;
-  const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((units + W - 1) / W, (size_t)n_sm * per_sm));
+  const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((units + W - 1) / W, (size_t)cfg.n_sm * per_sm));
   k_triangulate<T, W><<<grid, 32 * W, smem, st>>>(tb, d.p_max, d.h_cap, ws_bytes, persons, hyp_det, work, work_count, tmp,
                                                   keep);
   return cudaGetLastError();
 }
 
-cudaError_t launch_triangulate(const Tables& tb, LaunchDims d, const ses3d_person2d* persons, const int8_t* hyp_det,
-                               const uint32_t* work, const int32_t* work_count, ses3d_person_cov* tmp, int32_t* keep,
-                               cudaStream_t st) {
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (n_sm <= 0) n_sm = 148;
-  }
-  int warps = 2;   // measured on B200 (hall16 x 6): 2 warps/CTA 0.98 ms, 4: 1.00 ms, 8: 1.10 ms per 8192 frames
-  if (const char* env = getenv("SES3D_TRI_WARPS")) warps = atoi(env);
+cudaError_t init_kernels_tri(int) {
+  const int budget = 200 * 1024;
+  cudaError_t e;
+#define SES_ATTR(T, W)                                                                                                  \
+  if ((e = cudaFuncSetAttribute(k_triangulate<T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
+  SES_ATTR(float, 2) SES_ATTR(float, 4) SES_ATTR(float, 8) SES_ATTR(double, 2) SES_ATTR(double, 4) SES_ATTR(double, 8)
+#undef SES_ATTR
+  return cudaSuccess;
+}
+
+cudaError_t launch_triangulate(LaunchCfg& cfg, const Tables& tb, LaunchDims d, const ses3d_person2d* persons,
+                               const int8_t* hyp_det, const uint32_t* work, const int32_t* work_count,
+                               ses3d_person_cov* tmp, int32_t* keep, cudaStream_t st) {
+  // measured on B200 (hall16 x 6): 2 warps/CTA 0.98 ms, 4: 1.00 ms, 8: 1.10 ms per 8192 frames
   if (tb.prm.precision == SES3D_PRECISION_FP64) {
-    int w64 = 4;
-    if (const char* env = getenv("SES3D_TRI_WARPS_F64")) w64 = atoi(env);
-    if (w64 == 2) return launch_tri_impl<double, 2>(tb, d, persons, hyp_det, work, work_count, tmp, keep, n_sm, st);
-    if (w64 == 8) return launch_tri_impl<double, 8>(tb, d, persons, hyp_det, work, work_count, tmp, keep, n_sm, st);
-    return launch_tri_impl<double, 4>(tb, d, persons, hyp_det, work, work_count, tmp, keep, n_sm, st);
+    if (cfg.tri_warps_f64 == 2) return launch_tri_impl<double, 2>(cfg, tb, d, persons, hyp_det, work, work_count, tmp, keep, st);
+    if (cfg.tri_warps_f64 == 8) return launch_tri_impl<double, 8>(cfg, tb, d, persons, hyp_det, work, work_count, tmp, keep, st);
+    return launch_tri_impl<double, 4>(cfg, tb, d, persons, hyp_det, work, work_count, tmp, keep, st);
   }
-  if (warps == 2) return launch_tri_impl<float, 2>(tb, d, persons, hyp_det, work, work_count, tmp, keep, n_sm, st);
-  if (warps == 8) return launch_tri_impl<float, 8>(tb, d, persons, hyp_det, work, work_count, tmp, keep, n_sm, st);
-  return launch_tri_impl<float, 4>(tb, d, persons, hyp_det, work, work_count, tmp, keep, n_sm, st);
+  if (cfg.tri_warps == 2) return launch_tri_impl<float, 2>(cfg, tb, d, persons, hyp_det, work, work_count, tmp, keep, st);
+  if (cfg.tri_warps == 8) return launch_tri_impl<float, 8>(cfg, tb, d, persons, hyp_det, work, work_count, tmp, keep, st);
+  return launch_tri_impl<float, 4>(cfg, tb, d, persons, hyp_det, work, work_count, tmp, keep, st);
 }
 
 }  // namespace ses3d

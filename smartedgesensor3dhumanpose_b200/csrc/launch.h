@@ -10,8 +10,26 @@ struct LaunchDims {
   int n_frames, p_max, h_cap;
 };
 
+// Per-handle launch configuration, fixed at ses3d_create: the device's SM count, the tuning overrides from the
+// environment (SES3D_*: read once, never on the per-batch path) and a small cache of occupancy queries. The kernels'
+// dynamic shared-memory ceilings are raised once per device by init_kernels().
+struct LaunchCfg {
+  int device = 0;
+  int n_sm = 148;
+  int assoc_threads = 0;       // 0 = automatic
+  int reproj_cap = 0;          // 0 = automatic
+  int reproj_scap = 6;
+  int reproj_threads = 128;
+  int tri_warps = 2, tri_warps_f64 = 4;
+  struct OccEntry { const void* fn; size_t smem; int per_sm; };
+  OccEntry occ[8] = {};
+  int n_occ = 0;
+};
+cudaError_t init_kernels(LaunchCfg* cfg, int device);
+cudaError_t init_prior_kernels(int device);
+
 // K2: one CTA per frame. nk_scratch != nullptr selects the global-memory keypoint path.
-cudaError_t launch_associate(const Tables& tb, LaunchDims d, const ses3d_person2d* persons, const int32_t* n_persons,
+cudaError_t launch_associate(const LaunchCfg& cfg, const Tables& tb, LaunchDims d, const ses3d_person2d* persons, const int32_t* n_persons,
                              float* nk_scratch, double* pair_table, int8_t* hyp_det, int32_t* n_hyp, int32_t* n_hung,
                              int32_t* overflow, int32_t* hyp_of_dump, int32_t* keep, uint32_t* work,
                              int32_t* work_count, cudaStream_t st);
@@ -19,7 +37,7 @@ size_t associate_smem_bytes(int n_cams, int p_max, int h_cap, bool* needs_scratc
 size_t associate_pair_table_bytes(int n_cams, int p_max);   // per frame
 
 // K3: one warp per (frame, hypothesis) work item, persistent grid over the work list K2 wrote
-cudaError_t launch_triangulate(const Tables& tb, LaunchDims d, const ses3d_person2d* persons, const int8_t* hyp_det,
+cudaError_t launch_triangulate(LaunchCfg& cfg, const Tables& tb, LaunchDims d, const ses3d_person2d* persons, const int8_t* hyp_det,
                                const uint32_t* work, const int32_t* work_count, ses3d_person_cov* tmp, int32_t* keep,
                                cudaStream_t st);
 
@@ -28,17 +46,18 @@ cudaError_t launch_finalize(const Tables& tb, LaunchDims d, const int32_t* n_hyp
                             const int32_t* keep, ses3d_person_cov* out, int32_t* n_out, cudaStream_t st);
 
 // K6: one CTA per frame
-cudaError_t launch_reproject(const Tables& tb, int n_frames, int h_max, const ses3d_person_cov* persons3d,
+cudaError_t launch_reproject(const LaunchCfg& cfg, const Tables& tb, int n_frames, int h_max, const ses3d_person_cov* persons3d,
                              const int32_t* n_persons3d, ses3d_person2d* out, int32_t* n_out, cudaStream_t st);
 
 // diagnostics: a batch of independent assignment problems through the warp-cooperative Munkres
 cudaError_t launch_munkres_batch(int n, int rows, int cols, const double* cost, int32_t* assignment, cudaStream_t st);
 
 // ragged <-> padded record movement (kernels_pack.cu)
-cudaError_t launch_scan_counts(const int32_t* counts, int n, int cap, long long* offsets, cudaStream_t st);
+cudaError_t launch_scan_counts(const int32_t* counts, int n, int cap, long long* offsets, long long* running,
+                               cudaStream_t st);
 cudaError_t launch_move_records(int direction /*0 pack, 1 unpack*/, int n_units, int cap, int rec_bytes,
                                 const int32_t* counts, const long long* offsets, void* strided, void* dense,
-                                cudaStream_t st);
+                                long long dense_limit, cudaStream_t st);
 
 }  // namespace ses3d
 

@@ -19,6 +19,7 @@
 
 namespace ses3d {
 int set_error(int code, const std::string& msg);
+const char* last_error();
 }
 
 namespace {
@@ -88,10 +89,25 @@ struct ses3d_prior_s {
   PriorSlot rs[kSlots];
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int ragged_chunk_env = 0;       // SES3D_PRIOR_RAGGED_CHUNK, read at create
+  bool dev_run_pending = false;   // a device-buffer run was enqueued on a caller's stream; ev1 marks its end
   float last_ms = 0.f;
   int64_t launches = 0;
   std::mutex mu;
 };
+
+// Device-buffer runs are enqueued on the caller's stream and return at once. Every other entry point that reads or
+// rewrites the tracker state (host-buffer runs, reset, get_tracks, a device run on another stream) first orders itself
+// behind the last such run.
+static cudaError_t wait_for_device_runs(ses3d_prior_s* h, cudaStream_t st) {
+  if (!h->dev_run_pending) return cudaSuccess;
+  return cudaStreamWaitEvent(st, h->ev1, 0);
+}
+
+static int prior_run_ragged_impl(ses3d_prior h, int32_t n_sequences, int32_t n_frames, int32_t h_max,
+                                 const ses3d_person_cov* persons_dense, const int32_t* n_persons, const int64_t* stamp_ns,
+                                 int32_t n_cams, const float* fb_delay, ses3d_person_cov* fused_dense,
+                                 ses3d_person_cov* pred_dense, int64_t cap, int32_t* n_out, float* pred_delay, int64_t* total);
 
 extern "C" {
 
@@ -135,8 +151,10 @@ int ses3d_prior_create(const ses3d_prior_params* params, int32_t n_sequences, in
     return ses3d::set_error(SES3D_E_CUDA, "ses3d_prior_create: no CUDA device (there is no CPU path)");
   if (device < 0 || device >= n_dev) return ses3d::set_error(SES3D_E_INVALID, "ses3d_prior_create: bad device ordinal");
   CU(cudaSetDevice(device));
+  CU(ses3d::init_prior_kernels(device));
   ses3d_prior_s* h = new ses3d_prior_s;
   h->device = device;
+  if (const char* env = getenv("SES3D_PRIOR_RAGGED_CHUNK")) h->ragged_chunk_env = atoi(env);
   h->n_sequences = n_sequences;
   h->max_tracks = max_tracks;
   h->pt.prm = prm;
@@ -181,6 +199,7 @@ int ses3d_prior_reset(ses3d_prior h) {
   if (!h) return ses3d::set_error(SES3D_E_INVALID, "ses3d_prior_reset: NULL handle");
   std::lock_guard<std::mutex> lock(h->mu);
   CU(cudaSetDevice(h->device));
+  CU(wait_for_device_runs(h, h->stream));
   CU(ses3d::launch_prior_reset(h->pt.prm, h->n_sequences, h->states.as<ses3d::PriorSeqState>(), true, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   ++h->launches;
@@ -204,17 +223,23 @@ int ses3d_prior_run(ses3d_prior h, int32_t n_sequences, int32_t n_frames, int32_
   const size_t n_msg = (size_t)n_sequences * n_frames;
   const size_t rec = sizeof(ses3d_person_cov) * n_msg * h_max;
   const bool on_device = (flags & SES3D_DEVICE_BUFFERS) != 0;
-  cudaStream_t st = (on_device && stream) ? static_cast<cudaStream_t>(stream) : h->stream;
+  // device buffers: the kernel is ordered on the caller's stream; NULL means the legacy default stream (0), exactly
+  // as a NULL cudaStream_t does in the CUDA runtime, so producers / consumers on that stream are ordered with it
+  cudaStream_t st = on_device ? static_cast<cudaStream_t>(stream) : h->stream;
+  if (!on_device) CU(wait_for_device_runs(h, h->stream));
   auto* states = h->states.as<ses3d::PriorSeqState>();
   auto* tracks = h->tracks.as<ses3d::PriorTrack>();
   auto* order = h->order.as<uint8_t>();
   if (fb_delay == nullptr) n_cams = 0;
 
   if (on_device) {
+    CU(cudaStreamSynchronize(h->stream));   // host-path / reset work of earlier calls (normally idle)
+    CU(wait_for_device_runs(h, st));        // a previous device run on a different stream
     CU(cudaEventRecord(h->ev0, st));
     CU(ses3d::launch_prior(h->pt, n_sequences, n_frames, h_max, h->max_tracks, states, tracks, order, persons, n_persons,
                            stamp_ns, n_cams, fb_delay, fused, pred, n_out, pred_delay, track_of, st));
     CU(cudaEventRecord(h->ev1, st));
+    h->dev_run_pending = true;   // later entry points wait on ev1 before they touch the tracker state
     ++h->launches;
     // the sticky overflow flag is checked on the host-buffer path and by ses3d_prior_get_tracks
     return SES3D_OK;
@@ -272,15 +297,41 @@ int ses3d_prior_run_ragged(ses3d_prior h, int32_t n_sequences, int32_t n_frames,
     return ses3d::set_error(SES3D_E_INVALID, "ses3d_prior_run_ragged: NULL buffer");
   std::lock_guard<std::mutex> lock(h->mu);
   CU(cudaSetDevice(h->device));
-  CU(cudaStreamSynchronize(h->stream));   // earlier padded / reset work on the handle's own stream
+  const int rc = prior_run_ragged_impl(h, n_sequences, n_frames, h_max, persons_dense, n_persons, stamp_ns, n_cams, fb_delay,
+                                       fused_dense, pred_dense, cap, n_out, pred_delay, total);
+  if (rc != SES3D_OK) {
+    // a failed call may have copies into the caller's buffers in flight: nothing may be written after we return
+    const std::string msg = ses3d::last_error();
+    for (PriorSlot& sl : h->rs) cudaStreamSynchronize(sl.stream);
+    cudaStreamSynchronize(h->stream);
+    ses3d::set_error(rc, msg);
+  }
+  return rc;
+}
+
+}  // extern "C"
+
+static int prior_run_ragged_impl(ses3d_prior h, int32_t n_sequences, int32_t n_frames, int32_t h_max,
+                                 const ses3d_person_cov* persons_dense, const int32_t* n_persons, const int64_t* stamp_ns,
+                                 int32_t n_cams, const float* fb_delay, ses3d_person_cov* fused_dense,
+                                 ses3d_person_cov* pred_dense, int64_t cap, int32_t* n_out, float* pred_delay, int64_t* total) {
+  CU(wait_for_device_runs(h, h->stream));
+  CU(cudaStreamSynchronize(h->stream));   // earlier padded / reset / device-buffer work
   const size_t rec = sizeof(ses3d_person_cov);
   if (fb_delay == nullptr) n_cams = 0;
+  {  // validate everything before the first launch: a failed call must not advance the tracker state
+    long long n_in_total = 0;
+    for (size_t i = 0; i < (size_t)n_sequences * n_frames; ++i) n_in_total += std::min(std::max(n_persons[i], 0), h_max);
+    if (n_in_total > 0 && !persons_dense) return ses3d::set_error(SES3D_E_INVALID, "ses3d_prior_run_ragged: NULL persons_dense");
+    // every published record stems from one input record, so cap >= the input count can never overflow; a smaller
+    // capacity is accepted and checked against the actual totals chunk by chunk (the state then has advanced: documented)
+  }
   // chunks of streams (streams are independent): three slots keep H2D, the kernel and D2H of neighbouring chunks busy.
   // The kernel walks the messages of a stream one after the other, so a launch takes about n_frames x the per-message
   // latency however few streams it holds: chunks stay large (B200, 2048 streams x 32 messages, ms per call:
   // 1 chunk 43.5, 8 chunks 58.8)
   int chunk = std::max(1, std::min(n_sequences, std::max(592, (n_sequences + 2) / 3)));
-  if (const char* env = getenv("SES3D_PRIOR_RAGGED_CHUNK")) chunk = std::max(1, std::min(n_sequences, atoi(env)));
+  if (h->ragged_chunk_env > 0) chunk = std::max(1, std::min(n_sequences, h->ragged_chunk_env));
   long long in_done = 0, out_done = 0;
   struct Pending { int slot; size_t m0, n_msg; bool active; } prev{0, 0, 0, false};
   int status = SES3D_OK;
@@ -306,7 +357,6 @@ int ses3d_prior_run_ragged(ses3d_prior h, int32_t n_sequences, int32_t n_frames,
     const size_t m0 = (size_t)s0 * n_frames, n_msg = (size_t)ns * n_frames;
     long long n_in = 0;
     for (size_t i = m0; i < m0 + n_msg; ++i) n_in += std::min(std::max(n_persons[i], 0), h_max);
-    if (n_in > 0 && !persons_dense) return ses3d::set_error(SES3D_E_INVALID, "ses3d_prior_run_ragged: NULL persons_dense");
     CU(cudaEventSynchronize(sl.done));   // the slot's previous chunk (its copies included) has left the buffers
     CU(sl.persons.ensure(rec * n_msg * h_max));
     CU(sl.n.ensure(4 * n_msg));
@@ -327,20 +377,20 @@ int ses3d_prior_run_ragged(ses3d_prior h, int32_t n_sequences, int32_t n_frames,
     if (n_in) CU(cudaMemcpyAsync(sl.dense_in.p, persons_dense + in_done, rec * (size_t)n_in, cudaMemcpyHostToDevice, st));
     in_done += n_in;
     if (n_cams > 0) CU(cudaMemcpyAsync(sl.delay.p, fb_delay + m0 * n_cams, 4 * n_msg * n_cams, cudaMemcpyHostToDevice, st));
-    CU(ses3d::launch_scan_counts(sl.n.as<int32_t>(), (int)n_msg, h_max, sl.off_in.as<long long>(), st));
+    CU(ses3d::launch_scan_counts(sl.n.as<int32_t>(), (int)n_msg, h_max, sl.off_in.as<long long>(), nullptr, st));
     CU(ses3d::launch_move_records(1, (int)n_msg, h_max, (int)rec, sl.n.as<int32_t>(), sl.off_in.as<long long>(),
-                                  sl.persons.p, sl.dense_in.p, st));
+                                  sl.persons.p, sl.dense_in.p, -1, st));
     CU(ses3d::launch_prior(h->pt, ns, n_frames, h_max, h->max_tracks, h->states.as<ses3d::PriorSeqState>() + s0,
                            h->tracks.as<ses3d::PriorTrack>() + (size_t)s0 * h->max_tracks,
                            h->order.as<uint8_t>() + (size_t)s0 * h->max_tracks, sl.persons.as<ses3d_person_cov>(),
                            sl.n.as<int32_t>(), sl.stamp.as<int64_t>(), n_cams, n_cams > 0 ? sl.delay.as<float>() : nullptr,
                            sl.fused.as<ses3d_person_cov>(), sl.pred.as<ses3d_person_cov>(), sl.n_out.as<int32_t>(),
                            sl.delay_out.as<float>(), nullptr, st));
-    CU(ses3d::launch_scan_counts(sl.n_out.as<int32_t>(), (int)n_msg, h_max, sl.off_out.as<long long>(), st));
+    CU(ses3d::launch_scan_counts(sl.n_out.as<int32_t>(), (int)n_msg, h_max, sl.off_out.as<long long>(), nullptr, st));
     CU(ses3d::launch_move_records(0, (int)n_msg, h_max, (int)rec, sl.n_out.as<int32_t>(), sl.off_out.as<long long>(),
-                                  sl.fused.p, sl.dense_fused.p, st));
+                                  sl.fused.p, sl.dense_fused.p, -1, st));
     CU(ses3d::launch_move_records(0, (int)n_msg, h_max, (int)rec, sl.n_out.as<int32_t>(), sl.off_out.as<long long>(),
-                                  sl.pred.p, sl.dense_pred.p, st));
+                                  sl.pred.p, sl.dense_pred.p, -1, st));
     h->launches += 6;
     CU(cudaMemcpyAsync(sl.total, sl.off_out.as<long long>() + n_msg, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(sl.h_stage, sl.n_out.p, 4 * n_msg, cudaMemcpyDeviceToHost, st));
@@ -363,10 +413,13 @@ int ses3d_prior_run_ragged(ses3d_prior h, int32_t n_sequences, int32_t n_frames,
   return SES3D_OK;
 }
 
+extern "C" {
+
 int ses3d_prior_get_tracks(ses3d_prior h, int32_t sequence, int32_t* ids, int32_t* num_obs) {
   if (!h || sequence < 0 || sequence >= h->n_sequences) return ses3d::set_error(SES3D_E_INVALID, "ses3d_prior_get_tracks: bad argument");
   std::lock_guard<std::mutex> lock(h->mu);
   CU(cudaSetDevice(h->device));
+  CU(wait_for_device_runs(h, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   ses3d::PriorSeqState s;
   CU(cudaMemcpy(&s, h->states.as<ses3d::PriorSeqState>() + sequence, sizeof s, cudaMemcpyDeviceToHost));

@@ -210,28 +210,20 @@ SES_HD void solve_weighted(const Tables& tb, const TriWs<T>& ws, int k, const ui
 // so they carry no tolerance at all. A holds 2n x 4 floats in the warp's sigma-point staging area (idle at this point).
 constexpr float FAR_POINT_R2 = 20.0f * 20.0f;
 
-template <class Team>
-SES_HD void exact_weighted_resolve(Team& tm, const Tables& tb, const TriWs<float>& ws, int k, const uint8_t* list, int n) {
-  float* B = ws.Y;           // [2n][4] row-major, as the oracle holds A
-  float* W = B + 8 * n;      // [4][4] accumulated right rotations
-  const int rows = 2 * n;
-  tm.pfor(rows, [&](int r) {   // triangulate(), S3D:444-454, weight_by_conf = true
-    const int o = list[r >> 1], half = r & 1;
-    const ViewKp<float>& v = ws.vw[o * NKP + k];
-    const float* P = tb.camf[ws.obs_cam[o]].P;
-    const float m = half ? v.y : v.x;
+// One DLT solve in the oracle's arithmetic. build_row(r, row) fills row r of A (already normalised / weighted, built
+// with the non-contracting x-ops); B [rows][4] and W [4][4] live in shared memory; every thread of the team evaluates
+// the same column sums sequentially (read-only), so all threads take the same decisions and end with the same X.
+template <class Team, class RowFn>
+SES_HD void exact_dlt(Team& tm, float* B, int rows, RowFn&& build_row, float X[3]) {
+  float* W = B + 4 * rows;
+  tm.pfor(rows, [&](int r) {
     float row[4];
-    for (int c = 0; c < 4; ++c) row[c] = xsub(xmul(m, P[8 + c]), P[half * 4 + c]);
-    const float z = xadd(xadd(xmul(row[0], row[0]), xmul(row[1], row[1])), xadd(xmul(row[2], row[2]), xmul(row[3], row[3])));
-    if (z > 0.f) {
-      const float nrm = xsqrt(z);
-      for (int c = 0; c < 4; ++c) row[c] = xdiv(row[c], nrm);
-    }
-    for (int c = 0; c < 4; ++c) B[r * 4 + c] = xmul(row[c], v.conf);
+    build_row(r, row);
+    for (int c = 0; c < 4; ++c) B[r * 4 + c] = row[c];
   });
   tm.pfor(16, [&](int i) { W[i] = (i >> 2) == (i & 3) ? 1.f : 0.f; });
   const float eps = 1.1920929e-7f;
-  for (int sweep = 0; sweep < 60; ++sweep) {   // every thread evaluates the same sums -> the same decisions
+  for (int sweep = 0; sweep < 60; ++sweep) {
     bool rotated = false;
     for (int p = 0; p < 3; ++p)
       for (int q = p + 1; q < 4; ++q) {
@@ -249,8 +241,8 @@ SES_HD void exact_weighted_resolve(Team& tm, const Tables& tb, const TriWs<float
         const float t = xdiv(zeta >= 0.f ? 1.f : -1.f, xadd(ses_abs(zeta), xsqrt(xadd(1.f, xmul(zeta, zeta)))));
         const float c = xdiv(1.f, xsqrt(xadd(1.f, xmul(t, t))));
         const float sn = xmul(c, t);
-        tm.pfor(rows + 4, [&](int r) {
-          float* row = r < rows ? B + r * 4 : W + (r - rows) * 4;
+        tm.pfor(rows + 4, [&](int r) {   // rows of A and of W are rotated alike
+          float* row = B + r * 4;
           const float bp = row[p], bq = row[q];
           row[p] = xsub(xmul(c, bp), xmul(sn, bq));
           row[q] = xadd(xmul(sn, bp), xmul(c, bq));
@@ -266,7 +258,30 @@ SES_HD void exact_weighted_resolve(Team& tm, const Tables& tb, const TriWs<float
     if (sq < best_s) { best_s = sq; best = c; }
   }
   const float w = W[12 + best];
-  const float X[3] = {xdiv(W[best], w), xdiv(W[4 + best], w), xdiv(W[8 + best], w)};
+  X[0] = xdiv(W[best], w); X[1] = xdiv(W[4 + best], w); X[2] = xdiv(W[8 + best], w);
+  tm.sync();   // B may be rebuilt by the next solve
+}
+
+// row r of A for view list[r / 2] with the keypoint at (x, y): triangulate(), S3D:444-454
+SES_HD void exact_row(const float* P, int half, float m, float conf, bool weighted, float row[4]) {
+  for (int c = 0; c < 4; ++c) row[c] = xsub(xmul(m, P[8 + c]), P[half * 4 + c]);
+  const float z = xadd(xadd(xmul(row[0], row[0]), xmul(row[1], row[1])), xadd(xmul(row[2], row[2]), xmul(row[3], row[3])));
+  if (z > 0.f) {
+    const float nrm = xsqrt(z);
+    for (int c = 0; c < 4; ++c) row[c] = xdiv(row[c], nrm);
+  }
+  if (weighted)
+    for (int c = 0; c < 4; ++c) row[c] = xmul(row[c], conf);
+}
+
+template <class Team>
+SES_HD void exact_weighted_resolve(Team& tm, const Tables& tb, const TriWs<float>& ws, int k, const uint8_t* list, int n) {
+  float X[3];
+  exact_dlt(tm, ws.Y, 2 * n, [&](int r, float* row) {
+    const int o = list[r >> 1], half = r & 1;
+    const ViewKp<float>& v = ws.vw[o * NKP + k];
+    exact_row(tb.camf[ws.obs_cam[o]].P, half, half ? v.y : v.x, v.conf, true, row);
+  }, X);
   double avg = 0., norm = 0.;   // calcReprojectionError, S3D:425-438
   for (int i = 0; i < n; ++i) {
     const int o = list[i];
@@ -280,7 +295,6 @@ SES_HD void exact_weighted_resolve(Team& tm, const Tables& tb, const TriWs<float
     avg += static_cast<double>(xmul(v.conf, e));
     norm += static_cast<double>(v.conf);
   }
-  tm.sync();
   tm.single([&] {
     ws.jX[k * 3] = X[0]; ws.jX[k * 3 + 1] = X[1]; ws.jX[k * 3 + 2] = X[2];
     ws.jerr[k] = avg / norm;
@@ -288,6 +302,59 @@ SES_HD void exact_weighted_resolve(Team& tm, const Tables& tb, const TriWs<float
 }
 template <class Team>
 SES_HD void exact_weighted_resolve(Team&, const Tables&, const TriWs<double>&, int, const uint8_t*, int) {}
+
+// Unscented covariance of a far joint, sample by sample in the oracle's arithmetic (calc_covariance S3D:508-523 with
+// draw_sigma_points S3D:489-506 and mod_samples S3D:471-487). For a point hundreds of metres away the sigma points
+// straddle the pole of X = v_xyz / v_w, so anything but the same arithmetic gives an unrelated (equally meaningless)
+// covariance. 4n + 1 sequential solves - affordable because such joints are a few in 10^5.
+template <class Team>
+SES_HD void exact_far_covariance(Team& tm, const Tables& tb, int p_max, const ses3d_person2d* persons,
+                                 const TriWs<float>& ws, int k, const uint8_t* list, int n) {
+  const float dimk = xadd((float)(2 * n), 0.5f);          // T(dim) + kappa
+  const float wden = xmul(2.f, dimk);
+  const float w0 = xdiv(xmul(2.f, 0.5f), wden), wi = xdiv(1.f, wden);
+  const float b = xsqrt(dimk);
+  const float m0 = ws.jX[k * 3], m1 = ws.jX[k * 3 + 1], m2 = ws.jX[k * 3 + 2];
+  float c00 = 0.f, c01 = 0.f, c02 = 0.f, c11 = 0.f, c12 = 0.f, c22 = 0.f;
+  for (int s = 0; s <= 4 * n; ++s) {
+    const int vi = s > 0 ? (s - 1) >> 2 : -1, m = (s - 1) & 3;
+    float px = 0.f, py = 0.f;   // the perturbed keypoint of view vi
+    if (vi >= 0) {
+      const int o = list[vi], cam = ws.obs_cam[o];
+      const ses3d_keypoint2d& kp = persons[cam * p_max + ws.obs_det[o]].keypoints[k];
+      const CamF& cm = tb.camf[cam];
+      const ViewKp<float>& v = ws.vw[o * NKP + k];
+      const float cxx = xdiv(kp.cov[0], xmul(cm.fx, cm.fx)), cxy = xdiv(kp.cov[1], xmul(cm.fx, cm.fy)),
+                  cyy = xdiv(kp.cov[2], xmul(cm.fy, cm.fy));            // normalize_keypoints S3D:324-327
+      const float l11 = xsqrt(cxx), l21 = xdiv(cxy, l11);
+      const float l22 = xsqrt(xsub(cyy, xmul(l21, l21)));
+      const float dx1 = xmul(l11, b), dy1 = xmul(l21, b), dy2 = xmul(l22, b);
+      px = v.x; py = v.y;
+      if (m == 0) { px = xsub(v.x, dx1); py = xsub(v.y, dy1); }
+      else if (m == 1) { py = xsub(v.y, dy2); }
+      else if (m == 2) { px = xadd(v.x, dx1); py = xadd(v.y, dy1); }
+      else { py = xadd(v.y, dy2); }
+    }
+    float Y[3];
+    exact_dlt(tm, ws.Y, 2 * n, [&](int r, float* row) {
+      const int i = r >> 1, o = list[i], half = r & 1;
+      const ViewKp<float>& v = ws.vw[o * NKP + k];
+      const float coord = i == vi ? (half ? py : px) : (half ? v.y : v.x);
+      exact_row(tb.camf[ws.obs_cam[o]].P, half, coord, 1.f, false, row);
+    }, Y);
+    const float w = s == 0 ? w0 : wi;
+    const float d0 = xsub(Y[0], m0), d1 = xsub(Y[1], m1), d2 = xsub(Y[2], m2);
+    c00 = xadd(c00, xmul(xmul(d0, w), d0)); c01 = xadd(c01, xmul(xmul(d0, w), d1)); c02 = xadd(c02, xmul(xmul(d0, w), d2));
+    c11 = xadd(c11, xmul(xmul(d1, w), d1)); c12 = xadd(c12, xmul(xmul(d1, w), d2)); c22 = xadd(c22, xmul(xmul(d2, w), d2));
+  }
+  tm.single([&] {
+    float* cv = ws.cov + k * 6;
+    cv[0] = c00; cv[1] = c01; cv[2] = c02; cv[3] = c11; cv[4] = c12; cv[5] = c22;
+  });
+}
+template <class Team>
+SES_HD void exact_far_covariance(Team&, const Tables&, int, const ses3d_person2d*, const TriWs<double>&, int,
+                                 const uint8_t*, int) {}
 
 // LM refinement of sum conf^2 * ||hnorm(P X~) - x||^2 (self-specified, not in the reference)
 template <class T>
@@ -499,18 +566,22 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
     k0 = k1;
   }
 
-  // far points and high-residual joints (FP32 mode): exact re-solve of the final view set, see exact_weighted_resolve
+  // far points and high-residual joints (FP32 mode): exact re-solve of the final view set, see exact_weighted_resolve.
+  // jflag (the leave-one-out marks are spent) now marks the far joints: their covariance is solved exactly as well.
+  tm.pfor(NKP, [&](int k) { ws.jflag[k] = 0; });
   if (sizeof(T) == 4) {
     const int cap_n = (int)((size_t)Y_CHUNK * 3 - 16) / 8;
     for (int k = 0; k < NKP; ++k) {
       const int n = ws.jn[k];
       if (n < 2 || n > cap_n) continue;
       const T x = ws.jX[k * 3], y = ws.jX[k * 3 + 1], z = ws.jX[k * 3 + 2];
+      const bool far = x * x + y * y + z * z > T(FAR_POINT_R2);
       // second trigger: a residual above the acceptance threshold (gross outlier left in the view set). The large
       // smallest singular value narrows the gap to the next one, which amplifies rounding the same way, and the
       // residual scales the published score (S3D:840-844) - solved exactly, both match the oracle to the last bit.
-      if (!(x * x + y * y + z * z > T(FAR_POINT_R2)) && !(ws.jerr[k] > max_reproj)) continue;
+      if (!far && !(ws.jerr[k] > max_reproj)) continue;
       exact_weighted_resolve(tm, tb, ws, k, ws.vlist + k * C, n);
+      if (far) tm.single([&] { ws.jflag[k] = 2; });
     }
   }
 
@@ -531,6 +602,7 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
     }
     if (err > max_reproj) avg_score = (float)((double)avg_score * (max_reproj / err));
     ws.jscore[k] = avg_score;
+    if (ws.jflag[k] == 2) return;   // far joint: covariance by exact_far_covariance below
     double G[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = 0; i < n; ++i) {
       const int o = list[i];
@@ -574,7 +646,7 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
 
   tm.single([&] {
     int off = 0;
-    for (int k = 0; k < NKP; ++k) { ws.soff[k] = off; off += ws.jn[k] >= 2 ? 4 * ws.jn[k] : 0; }
+    for (int k = 0; k < NKP; ++k) { ws.soff[k] = off; off += (ws.jn[k] >= 2 && ws.jflag[k] != 2) ? 4 * ws.jn[k] : 0; }
     ws.soff[NKP] = off;
   });
   const int n_samples_total = ws.soff[NKP];
@@ -641,7 +713,7 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
     // covariance about the weighted-DLT point, samples in the reference's order (S3D:521-522)
     tm.pfor(NKP, [&](int k) {
       const int n = ws.jn[k];
-      if (n < 2) return;
+      if (n < 2 || ws.jflag[k] == 2) return;
       int a = ws.soff[k], b = ws.soff[k + 1];
       a = a > s0 ? a : s0;
       b = b < s0 + cnt ? b : s0 + cnt;
@@ -658,6 +730,9 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
       cv[0] = c00; cv[1] = c01; cv[2] = c02; cv[3] = c11; cv[4] = c12; cv[5] = c22;
     });
   }
+
+  for (int k = 0; k < NKP; ++k)
+    if (ws.jflag[k] == 2) exact_far_covariance(tm, tb, p_max, persons, ws, k, ws.vlist + k * C, ws.jn[k]);
 
   // output keypoints (S3D:849-857); the record shares storage with the sigma-point staging, which is done
   tm.pfor(NFUS, [&](int s) { zero_kp(ws.kp[s]); });

@@ -128,18 +128,20 @@ int ses3d_wire_decode_personcovlist(const uint8_t* buf, size_t len, uint32_t* se
   Reader r{buf, len};
   if (!read_header(r, seq, stamp_ns, frame_id, frame_id_cap)) return SES3D_E_INVALID;
   const uint32_t nt = r.get<uint32_t>();
+  if (!r.ok || r.left < (size_t)nt * 8) return SES3D_E_INVALID;   // counts come from untrusted bytes: check before looping
   for (uint32_t i = 0; i < nt; ++i) {
     const uint32_t sec = r.get<uint32_t>(), nsec = r.get<uint32_t>();
     if (ts_per_cam_ns && (int32_t)i < cam_cap) ts_per_cam_ns[i] = (int64_t)sec * 1000000000LL + nsec;
   }
   const uint32_t nf = r.get<uint32_t>();
+  if (!r.ok || r.left < (size_t)nf * 4) return SES3D_E_INVALID;
   for (uint32_t i = 0; i < nf; ++i) {
     const float v = r.get<float>();
     if (fb_delay_per_cam && (int32_t)i < cam_cap) fb_delay_per_cam[i] = v;
   }
-  if (n_cams) *n_cams = (int32_t)nt;
   const uint32_t n = r.get<uint32_t>();
   if (!r.ok) return SES3D_E_INVALID;
+  if (n_cams) *n_cams = (int32_t)nt;   // only once the header part has been validated
   for (uint32_t i = 0; i < n; ++i) {
     ses3d_person_cov p;
     std::memset(&p, 0, sizeof(p));

@@ -16,7 +16,10 @@ EXPORTS = ("ses3d_default_params", "ses3d_create", "ses3d_destroy", "ses3d_get_t
            "ses3d_assembler_stats", "ses3d_wire_decode_person2dlist", "ses3d_wire_encode_person2dlist",
            "ses3d_wire_decode_personcovlist", "ses3d_wire_encode_personcovlist", "ses3d_prior_default_params",
            "ses3d_prior_create", "ses3d_prior_destroy", "ses3d_prior_reset", "ses3d_prior_run", "ses3d_prior_get_tracks",
-           "ses3d_prior_launch_count", "ses3d_prior_last_kernel_ms", "ses3d_measure_fma_peak", "ses3d_markers_batch", "ses3d_prior_run_ragged")
+           "ses3d_prior_launch_count", "ses3d_prior_last_kernel_ms", "ses3d_measure_fma_peak", "ses3d_markers_batch", "ses3d_prior_run_ragged",
+           "ses3d_n_cams", "ses3d_check", "ses3d_bind_thread_to_device_numa", "ses3d_create_multi", "ses3d_multi_destroy",
+           "ses3d_multi_device_count", "ses3d_multi_handle", "ses3d_multi_process_batch",
+           "ses3d_multi_process_batch_ragged")
 
 
 class Ses3dError(RuntimeError):
@@ -84,6 +87,16 @@ def load():
     L.ses3d_prior_last_kernel_ms.argtypes = [vp, vp]
     L.ses3d_measure_fma_peak.argtypes = [i32, i32, C.POINTER(C.c_double)]
     L.ses3d_markers_batch.argtypes = [vp, i32, i32, vp, vp, i32, vp, vp, vp, vp, u32, vp]
+    L.ses3d_n_cams.argtypes = [vp]
+    L.ses3d_check.argtypes = [vp]
+    L.ses3d_bind_thread_to_device_numa.argtypes = [i32, C.POINTER(i32)]
+    L.ses3d_create_multi.argtypes = [i32, vp, C.POINTER(Params), i32, vp, C.POINTER(vp)]
+    L.ses3d_multi_destroy.argtypes = [vp]
+    L.ses3d_multi_device_count.argtypes = [vp]
+    L.ses3d_multi_handle.argtypes = [vp, i32]
+    L.ses3d_multi_handle.restype = vp
+    L.ses3d_multi_process_batch.argtypes = [vp, i32, i32, vp, vp, i32, vp, vp, vp, vp, C.POINTER(AssocDump)]
+    L.ses3d_multi_process_batch_ragged.argtypes = [vp, i32, i32, vp, vp, i32, vp, i64, vp, vp, i64, vp, vp, vp]
     _lib = L
     return L
 
@@ -93,6 +106,13 @@ def measure_fma_peak(device=0, fp64=False):
     v = C.c_double(0)
     check(load().ses3d_measure_fma_peak(device, int(fp64), C.byref(v)))
     return v.value
+
+
+def bind_thread_to_device_numa(device=0):
+    """Pin the calling thread to the CPUs of the GPU's NUMA node (no-op without sysfs); returns the node or -1."""
+    node = C.c_int32(-1)
+    check(load().ses3d_bind_thread_to_device_numa(device, C.byref(node)))
+    return node.value
 
 
 def check(rc):

@@ -59,7 +59,7 @@ def test_outlier_rejection_branches(name, n_frames):
     rh = HostSim(fr["cameras"]).triangulate_batch(fr["persons"], fr["n_persons"], 40)
     assert np.array_equal(ro["hyp_of"], rh["hyp_of"])
     keep = ro["margin"] >= MARGIN_EPS
-    assert (~keep).sum() <= n_frames // 50
+    assert (~keep).sum() <= n_frames // 20
     sub = lambda r: dict(persons3d=r["persons3d"][keep], n_out=r["n_out"][keep])
     helpers.compare_persons3d(sub(ro), sub(rh), 1e-3, cov_rtol=1e-2)
 

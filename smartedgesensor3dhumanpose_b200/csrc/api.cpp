@@ -65,10 +65,10 @@ struct DevBuf {
 };
 
 struct Scratch {  // per-slot intermediates of the triangulation path
-  DevBuf hyp_det, n_hyp, n_hung, keep, tmp, nk, work, work_count, pairs;
+  DevBuf hyp_det, n_hyp, n_hung, keep, tmp, nk, work, work_count, pairs, far;
   void release() {
     hyp_det.release(); n_hyp.release(); n_hung.release(); keep.release(); tmp.release(); nk.release(); work.release();
-    work_count.release(); pairs.release();
+    work_count.release(); pairs.release(); far.release();
   }
 };
 
@@ -184,7 +184,8 @@ int triangulate_on_device(ses3d_handle_s* h, Scratch& sc, cudaStream_t st, int n
     CU(sc.keep.ensure((size_t)nf * h_max * 4));
     CU(sc.tmp.ensure((size_t)nf * h_max * sizeof(ses3d_person_cov)));
     CU(sc.work.ensure((size_t)nf * h_max * 4));
-    CU(sc.work_count.ensure(4));
+    CU(sc.work_count.ensure(8));
+    if (h->prm.precision == SES3D_PRECISION_FP32) CU(sc.far.ensure(ses3d::triangulate_far_scratch_bytes(h->cfg)));
     if (need_nk) CU(sc.nk.ensure((size_t)nf * C * p_max * ses3d::NKP * 3 * sizeof(float)));
     LaunchDims d{nf, p_max, h_max};
     const ses3d_person2d* pin = persons + (size_t)f0 * C * p_max;
@@ -202,7 +203,8 @@ int triangulate_on_device(ses3d_handle_s* h, Scratch& sc, cudaStream_t st, int n
     {
       ProfScope ps(h, 1, st);
       CU(ses3d::launch_triangulate(h->cfg, h->tb, d, pin, sc.hyp_det.as<int8_t>(), sc.work.as<uint32_t>(),
-                                   sc.work_count.as<int32_t>(), sc.tmp.as<ses3d_person_cov>(), sc.keep.as<int32_t>(), st));
+                                   sc.work_count.as<int32_t>(), sc.tmp.as<ses3d_person_cov>(), sc.keep.as<int32_t>(),
+                                   sc.far.as<float>(), sc.far.cap, st));
     }
     {
       ProfScope ps(h, 2, st);
@@ -832,7 +834,8 @@ int ses3d_reserve(ses3d_handle h, int32_t n_frames, int32_t p_max, int32_t h_max
     CU(s.sc.keep.ensure((size_t)nf * h_max * 4));
     CU(s.sc.tmp.ensure((size_t)nf * h_max * sizeof(ses3d_person_cov)));
     CU(s.sc.work.ensure((size_t)nf * h_max * 4));
-    CU(s.sc.work_count.ensure(4));
+    CU(s.sc.work_count.ensure(8));
+    if (h->prm.precision == SES3D_PRECISION_FP32) CU(s.sc.far.ensure(ses3d::triangulate_far_scratch_bytes(h->cfg)));
     if (need_nk) CU(s.sc.nk.ensure((size_t)nf * C * p_max * ses3d::NKP * 3 * sizeof(float)));
   }
   return SES3D_OK;

@@ -14,10 +14,10 @@
 
 #if defined(__CUDACC__)
 #define SES_HD __host__ __device__ __forceinline__
-#define SES_HDN __host__ __device__ __noinline__
+#define SES_HDN __host__ __device__ __noinline__ inline
 #else
 #define SES_HD inline
-#define SES_HDN
+#define SES_HDN inline
 #endif
 
 namespace ses3d {

@@ -165,7 +165,7 @@ cudaError_t launch_associate(const LaunchCfg& cfg, const Tables& tb, LaunchDims 
   if (d.n_frames <= 296) threads = 256;   // fewer frames than two per SM: latency mode (single-frame call 75 -> 60 us)
   if (cfg.assoc_threads) threads = cfg.assoc_threads;
   if (scratch && !nk_scratch) return cudaErrorInvalidValue;
-  cudaError_t e = cudaMemsetAsync(work_count, 0, sizeof(int32_t), st);
+  cudaError_t e = cudaMemsetAsync(work_count, 0, 2 * sizeof(int32_t), st);   // [0] item count, [1] K3's claim counter
   if (e != cudaSuccess) return e;
   if (!pair_table) return cudaErrorInvalidValue;
   k_associate<<<d.n_frames, threads, smem, st>>>(tb, d.n_frames, d.p_max, d.h_cap, persons, n_persons,

@@ -36,10 +36,13 @@ cudaError_t launch_associate(const LaunchCfg& cfg, const Tables& tb, LaunchDims 
 size_t associate_smem_bytes(int n_cams, int p_max, int h_cap, bool* needs_scratch);
 size_t associate_pair_table_bytes(int n_cams, int p_max);   // per frame
 
-// K3: one warp per (frame, hypothesis) work item, persistent grid over the work list K2 wrote
-cudaError_t launch_triangulate(LaunchCfg& cfg, const Tables& tb, LaunchDims d, const ses3d_person2d* persons, const int8_t* hyp_det,
-                               const uint32_t* work, const int32_t* work_count, ses3d_person_cov* tmp, int32_t* keep,
-                               cudaStream_t st);
+// K3: one warp per (frame, hypothesis) work item, persistent grid over the work list K2 wrote; work_count[0] = number
+// of items, work_count[1] = next unclaimed item (both zeroed by launch_associate). far_scratch: global workspace of
+// triangulate_far_scratch_bytes() for the exact covariance of far joints (nullptr / too small: approximate path).
+cudaError_t launch_triangulate(LaunchCfg& cfg, const Tables& tb, LaunchDims d, const ses3d_person2d* persons,
+                               const int8_t* hyp_det, const uint32_t* work, int32_t* work_count, ses3d_person_cov* tmp,
+                               int32_t* keep, float* far_scratch, size_t far_scratch_bytes, cudaStream_t st);
+size_t triangulate_far_scratch_bytes(const LaunchCfg& cfg);
 
 // K4: one CTA per frame
 cudaError_t launch_finalize(const Tables& tb, LaunchDims d, const int32_t* n_hyp, ses3d_person_cov* tmp,

@@ -51,6 +51,8 @@ struct TriWs {
   double* looErr;     // [loo_cap]
   int loo_cap;
   ses3d_keypoint_cov* kp;  // [21] the output skeleton
+  float* far_scratch;      // [team size][FAR_COV_STRIDE] private solve copies for exact_far_covariance (not carved
+                           // from the arena: global memory on the GPU; nullptr disables the exact covariance)
 };
 
 template <class T, class A>
@@ -75,6 +77,7 @@ SES_HD void tri_ws_layout(A& ar, int C, TriWs<T>* ws) {
   uint8_t* obs_cam = ar.template take<uint8_t>(C);
   uint8_t* obs_det = ar.template take<uint8_t>(C);
   if (ws) {
+    ws->far_scratch = nullptr;
     ws->jerr = jerr; ws->kp = reinterpret_cast<ses3d_keypoint_cov*>(u); ws->Y = reinterpret_cast<T*>(u);
     ws->looErr = u; ws->looX = reinterpret_cast<T*>(u + loo_cap); ws->loo_cap = loo_cap;
     ws->vw = vw; ws->jX = jX; ws->defl = defl; ws->cov = cov; ws->jscore = jscore; ws->jn = jn;
@@ -303,20 +306,67 @@ SES_HD void exact_weighted_resolve(Team& tm, const Tables& tb, const TriWs<float
 template <class Team>
 SES_HD void exact_weighted_resolve(Team&, const Tables&, const TriWs<double>&, int, const uint8_t*, int) {}
 
-// Unscented covariance of a far joint, sample by sample in the oracle's arithmetic (calc_covariance S3D:508-523 with
-// draw_sigma_points S3D:489-506 and mod_samples S3D:471-487). For a point hundreds of metres away the sigma points
-// straddle the pole of X = v_xyz / v_w, so anything but the same arithmetic gives an unrelated (equally meaningless)
-// covariance. 4n + 1 sequential solves - affordable because such joints are a few in 10^5.
+// The same solve run by ONE thread on its own copy of A (B: rows x 4 followed by the 4 x 4 rotation accumulator):
+// the oracle's onesided_jacobi statement for statement. Used where many independent solves exist at once (the sigma
+// points of a far joint), one per lane.
+SES_HDN void exact_dlt_serial(float* B, int rows, float X[3]) {
+  float* W = B + 4 * rows;
+  for (int i = 0; i < 16; ++i) W[i] = (i >> 2) == (i & 3) ? 1.f : 0.f;
+  const float eps = 1.1920929e-7f;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    bool rotated = false;
+    for (int p = 0; p < 3; ++p)
+      for (int q = p + 1; q < 4; ++q) {
+        float alpha = 0.f, beta = 0.f, gamma = 0.f;
+        for (int r = 0; r < rows; ++r) {
+          const float bp = B[r * 4 + p], bq = B[r * 4 + q];
+          alpha = xadd(alpha, xmul(bp, bp));
+          beta = xadd(beta, xmul(bq, bq));
+          gamma = xadd(gamma, xmul(bp, bq));
+        }
+        if (ses_abs(gamma) <= xmul(eps, xsqrt(xmul(alpha, beta))) || gamma == 0.f) continue;
+        rotated = true;
+        const float zeta = xdiv(xsub(beta, alpha), xmul(2.f, gamma));
+        const float t = xdiv(zeta >= 0.f ? 1.f : -1.f, xadd(ses_abs(zeta), xsqrt(xadd(1.f, xmul(zeta, zeta)))));
+        const float c = xdiv(1.f, xsqrt(xadd(1.f, xmul(t, t))));
+        const float sn = xmul(c, t);
+        for (int r = 0; r < rows + 4; ++r) {
+          float* row = B + r * 4;
+          const float bp = row[p], bq = row[q];
+          row[p] = xsub(xmul(c, bp), xmul(sn, bq));
+          row[q] = xadd(xmul(sn, bp), xmul(c, bq));
+        }
+      }
+    if (!rotated) break;
+  }
+  int best = 0;
+  float best_s = FLT_MAX;
+  for (int c = 0; c < 4; ++c) {
+    float sq = 0.f;
+    for (int r = 0; r < rows; ++r) sq = xadd(sq, xmul(B[r * 4 + c], B[r * 4 + c]));
+    if (sq < best_s) { best_s = sq; best = c; }
+  }
+  const float w = W[12 + best];
+  X[0] = xdiv(W[best], w); X[1] = xdiv(W[4 + best], w); X[2] = xdiv(W[8 + best], w);
+}
+
+// Unscented covariance of a far joint in the oracle's arithmetic (calc_covariance S3D:508-523 with draw_sigma_points
+// S3D:489-506 and mod_samples S3D:471-487). For a point hundreds of metres away the sigma points straddle the pole
+// of X = v_xyz / v_w, so anything but the same arithmetic gives an unrelated (equally meaningless) covariance.
+// The 4n + 1 solves are independent: one per lane, each on a private copy of A in the workspace `scratch`
+// ([team size][FAR_COV_MAX_VIEWS * 8 + 16] floats, global memory on the GPU); the transformed points are staged in
+// the (idle) sigma-point buffer and folded in sample order like the reference does.
+constexpr int FAR_COV_MAX_VIEWS = 16;
+constexpr int FAR_COV_STRIDE = FAR_COV_MAX_VIEWS * 8 + 16;
 template <class Team>
 SES_HD void exact_far_covariance(Team& tm, const Tables& tb, int p_max, const ses3d_person2d* persons,
-                                 const TriWs<float>& ws, int k, const uint8_t* list, int n) {
+                                 const TriWs<float>& ws, int k, const uint8_t* list, int n, float* scratch) {
   const float dimk = xadd((float)(2 * n), 0.5f);          // T(dim) + kappa
   const float wden = xmul(2.f, dimk);
   const float w0 = xdiv(xmul(2.f, 0.5f), wden), wi = xdiv(1.f, wden);
   const float b = xsqrt(dimk);
-  const float m0 = ws.jX[k * 3], m1 = ws.jX[k * 3 + 1], m2 = ws.jX[k * 3 + 2];
-  float c00 = 0.f, c01 = 0.f, c02 = 0.f, c11 = 0.f, c12 = 0.f, c22 = 0.f;
-  for (int s = 0; s <= 4 * n; ++s) {
+  const int n_samples = 4 * n + 1;   // <= 65 <= Y_CHUNK
+  tm.pfor(n_samples, [&](int s) {
     const int vi = s > 0 ? (s - 1) >> 2 : -1, m = (s - 1) & 3;
     float px = 0.f, py = 0.f;   // the perturbed keypoint of view vi
     if (vi >= 0) {
@@ -335,26 +385,31 @@ SES_HD void exact_far_covariance(Team& tm, const Tables& tb, int p_max, const se
       else if (m == 2) { px = xadd(v.x, dx1); py = xadd(v.y, dy1); }
       else { py = xadd(v.y, dy2); }
     }
-    float Y[3];
-    exact_dlt(tm, ws.Y, 2 * n, [&](int r, float* row) {
+    float* B = scratch + (size_t)(s % tm.size()) * FAR_COV_STRIDE;
+    for (int r = 0; r < 2 * n; ++r) {
       const int i = r >> 1, o = list[i], half = r & 1;
       const ViewKp<float>& v = ws.vw[o * NKP + k];
       const float coord = i == vi ? (half ? py : px) : (half ? v.y : v.x);
-      exact_row(tb.camf[ws.obs_cam[o]].P, half, coord, 1.f, false, row);
-    }, Y);
-    const float w = s == 0 ? w0 : wi;
-    const float d0 = xsub(Y[0], m0), d1 = xsub(Y[1], m1), d2 = xsub(Y[2], m2);
-    c00 = xadd(c00, xmul(xmul(d0, w), d0)); c01 = xadd(c01, xmul(xmul(d0, w), d1)); c02 = xadd(c02, xmul(xmul(d0, w), d2));
-    c11 = xadd(c11, xmul(xmul(d1, w), d1)); c12 = xadd(c12, xmul(xmul(d1, w), d2)); c22 = xadd(c22, xmul(xmul(d2, w), d2));
-  }
+      exact_row(tb.camf[ws.obs_cam[o]].P, half, coord, 1.f, false, B + r * 4);
+    }
+    exact_dlt_serial(B, 2 * n, ws.Y + s * 3);
+  });
   tm.single([&] {
+    const float m0 = ws.jX[k * 3], m1 = ws.jX[k * 3 + 1], m2 = ws.jX[k * 3 + 2];
+    float c00 = 0.f, c01 = 0.f, c02 = 0.f, c11 = 0.f, c12 = 0.f, c22 = 0.f;
+    for (int s = 0; s < n_samples; ++s) {
+      const float w = s == 0 ? w0 : wi;
+      const float d0 = xsub(ws.Y[s * 3], m0), d1 = xsub(ws.Y[s * 3 + 1], m1), d2 = xsub(ws.Y[s * 3 + 2], m2);
+      c00 = xadd(c00, xmul(xmul(d0, w), d0)); c01 = xadd(c01, xmul(xmul(d0, w), d1)); c02 = xadd(c02, xmul(xmul(d0, w), d2));
+      c11 = xadd(c11, xmul(xmul(d1, w), d1)); c12 = xadd(c12, xmul(xmul(d1, w), d2)); c22 = xadd(c22, xmul(xmul(d2, w), d2));
+    }
     float* cv = ws.cov + k * 6;
     cv[0] = c00; cv[1] = c01; cv[2] = c02; cv[3] = c11; cv[4] = c12; cv[5] = c22;
   });
 }
 template <class Team>
 SES_HD void exact_far_covariance(Team&, const Tables&, int, const ses3d_person2d*, const TriWs<double>&, int,
-                                 const uint8_t*, int) {}
+                                 const uint8_t*, int, float*) {}
 
 // LM refinement of sum conf^2 * ||hnorm(P X~) - x||^2 (self-specified, not in the reference)
 template <class T>
@@ -571,17 +626,42 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
   tm.pfor(NKP, [&](int k) { ws.jflag[k] = 0; });
   if (sizeof(T) == 4) {
     const int cap_n = (int)((size_t)Y_CHUNK * 3 - 16) / 8;
+    // Most far joints belong to garbage hypotheses and never reach the output: when the skeleton's root (MidHip, else
+    // the mean of both hips, S3D:924-935) lies inside the far-point radius, a joint more than 3 m beyond that radius
+    // is certainly further than max_joint_dist_to_root from it and is reset (S3D:937-953) whatever its last digits
+    // are - no exact solve needed. (Its approximate position still feeds a child's limb-length inflation; at these
+    // distances that term changes by parts in 1e5.)
+    bool root_near = false;
+    if (tb.prm.max_joint_dist_to_root <= 2.5) {
+      auto near = [&](int slot) {
+        for (int k = 0; k < NKP; ++k)
+          if (tb.model.fusion_idx[k] == slot) {
+            const T x = ws.jX[k * 3], y = ws.jX[k * 3 + 1], z = ws.jX[k * 3 + 2];
+            return ws.jn[k] >= 2 && x * x + y * y + z * z <= T(FAR_POINT_R2);
+          }
+        return false;
+      };
+      auto present = [&](int slot) {
+        for (int k = 0; k < NKP; ++k)
+          if (tb.model.fusion_idx[k] == slot) return ws.jn[k] >= 2;
+        return false;
+      };
+      root_near = present(SES3D_FBP_MIDHIP) ? near(SES3D_FBP_MIDHIP) : (near(SES3D_FBP_LHIP) && near(SES3D_FBP_RHIP));
+    }
+    const T r_skip = T(23.0 * 23.0);
     for (int k = 0; k < NKP; ++k) {
       const int n = ws.jn[k];
       if (n < 2 || n > cap_n) continue;
       const T x = ws.jX[k * 3], y = ws.jX[k * 3 + 1], z = ws.jX[k * 3 + 2];
-      const bool far = x * x + y * y + z * z > T(FAR_POINT_R2);
+      const T r2 = x * x + y * y + z * z;
+      if (root_near && r2 > r_skip && r2 < T(1e30)) continue;   // will be reset by the root-distance rule
+      const bool far = r2 > T(FAR_POINT_R2);
       // second trigger: a residual above the acceptance threshold (gross outlier left in the view set). The large
       // smallest singular value narrows the gap to the next one, which amplifies rounding the same way, and the
       // residual scales the published score (S3D:840-844) - solved exactly, both match the oracle to the last bit.
       if (!far && !(ws.jerr[k] > max_reproj)) continue;
       exact_weighted_resolve(tm, tb, ws, k, ws.vlist + k * C, n);
-      if (far) tm.single([&] { ws.jflag[k] = 2; });
+      if (far && n <= FAR_COV_MAX_VIEWS && ws.far_scratch) tm.single([&] { ws.jflag[k] = 2; });
     }
   }
 
@@ -732,7 +812,7 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
   }
 
   for (int k = 0; k < NKP; ++k)
-    if (ws.jflag[k] == 2) exact_far_covariance(tm, tb, p_max, persons, ws, k, ws.vlist + k * C, ws.jn[k]);
+    if (ws.jflag[k] == 2) exact_far_covariance(tm, tb, p_max, persons, ws, k, ws.vlist + k * C, ws.jn[k], ws.far_scratch);
 
   // output keypoints (S3D:849-857); the record shares storage with the sigma-point staging, which is done
   tm.pfor(NFUS, [&](int s) { zero_kp(ws.kp[s]); });

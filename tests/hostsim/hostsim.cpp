@@ -64,6 +64,7 @@ int hostsim_triangulate_batch(void* h, int32_t n_frames, int32_t p_max, const se
   const bool f64 = tb.prm.precision == SES3D_PRECISION_FP64;
   std::vector<unsigned char> wst((f64 ? tri_ws_bytes<double>(C) : tri_ws_bytes<float>(C)) + 64);
   std::vector<int8_t> hyp_det((size_t)h_max * C);
+  std::vector<float> far_scratch(FAR_COV_STRIDE);   // serial team: one private solve copy
   std::vector<double> pair_table(assoc_pair_table_entries(C, p_max));
   std::vector<ses3d_person_cov> tmp(h_max);
   std::vector<int32_t> keep(h_max);
@@ -98,6 +99,7 @@ int hostsim_triangulate_batch(void* h, int32_t n_frames, int32_t p_max, const se
       } else {
         TriWs<float> tws;
         tri_ws_layout<float>(a2, C, &tws);
+        tws.far_scratch = far_scratch.data();
         triangulate_hypothesis<float>(tm, tb, p_max, pf, hyp_det.data() + (size_t)hh * C, tws, &tmp[hh], &keep[hh]);
       }
     }

@@ -65,10 +65,10 @@ struct DevBuf {
 };
 
 struct Scratch {  // per-slot intermediates of the triangulation path
-  DevBuf hyp_det, n_hyp, n_hung, keep, tmp, nk, work, work_count, pairs, far;
+  DevBuf hyp_det, n_hyp, n_hung, keep, tmp, nk, work, work_count, pairs, far, meta;
   void release() {
     hyp_det.release(); n_hyp.release(); n_hung.release(); keep.release(); tmp.release(); nk.release(); work.release();
-    work_count.release(); pairs.release(); far.release();
+    work_count.release(); pairs.release(); far.release(); meta.release();
   }
 };
 
@@ -167,10 +167,12 @@ void resolve_events(ses3d_handle_s* h) {
   h->pending_events.clear();
 }
 
-// K2 -> K3 -> K4 on device pointers, stream-ordered, no synchronisation.
+// K2a -> K2b -> K3 -> K4 on device pointers, stream-ordered, no synchronisation. With out2d != nullptr the last step
+// is the fused K4 + K6 kernel (finalize + reproject): four launches per device chunk for the whole path.
 int triangulate_on_device(ses3d_handle_s* h, Scratch& sc, cudaStream_t st, int n_frames, int p_max, int h_max,
                           const ses3d_person2d* persons, const int32_t* n_persons, ses3d_person_cov* out,
-                          int32_t* n_out, int32_t* hyp_of, int32_t* n_hyp_dump, int32_t* n_hung_dump) {
+                          int32_t* n_out, int32_t* hyp_of, int32_t* n_hyp_dump, int32_t* n_hung_dump,
+                          ses3d_person2d* out2d = nullptr, int32_t* n_out2d = nullptr) {
   const int C = h->tb.n_cams;
   bool need_nk = false;
   ses3d::associate_smem_bytes(C, p_max, h_max, &need_nk);
@@ -178,6 +180,7 @@ int triangulate_on_device(ses3d_handle_s* h, Scratch& sc, cudaStream_t st, int n
   for (int f0 = 0; f0 < n_frames; f0 += dchunk) {
     const int nf = std::min(dchunk, n_frames - f0);
     CU(sc.pairs.ensure((size_t)nf * ses3d::associate_pair_table_bytes(C, p_max)));
+    CU(sc.meta.ensure((size_t)nf * ses3d::associate_meta_bytes(C, p_max)));
     CU(sc.hyp_det.ensure((size_t)nf * h_max * C));
     CU(sc.n_hyp.ensure((size_t)nf * 4));
     CU(sc.n_hung.ensure((size_t)nf * 4));
@@ -195,7 +198,7 @@ int triangulate_on_device(ses3d_handle_s* h, Scratch& sc, cudaStream_t st, int n
     {
       ProfScope ps(h, 0, st);
       CU(ses3d::launch_associate(h->cfg, h->tb, d, pin, nin, need_nk ? sc.nk.as<float>() : nullptr, sc.pairs.as<double>(),
-                                 sc.hyp_det.as<int8_t>(),
+                                 sc.meta.as<unsigned char>(), sc.hyp_det.as<int8_t>(),
                                  n_hyp, n_hung, h->d_overflow.as<int32_t>(),
                                  hyp_of ? hyp_of + (size_t)f0 * C * p_max : nullptr, sc.keep.as<int32_t>(),
                                  sc.work.as<uint32_t>(), sc.work_count.as<int32_t>(), st));
@@ -206,12 +209,17 @@ int triangulate_on_device(ses3d_handle_s* h, Scratch& sc, cudaStream_t st, int n
                                    sc.work_count.as<int32_t>(), sc.tmp.as<ses3d_person_cov>(), sc.keep.as<int32_t>(),
                                    sc.far.as<float>(), sc.far.cap, st));
     }
-    {
+    if (out2d) {
+      ProfScope ps(h, 3, st);
+      CU(ses3d::launch_finproj(h->cfg, h->tb, d, n_hyp, sc.tmp.as<ses3d_person_cov>(), sc.keep.as<int32_t>(),
+                               out + (size_t)f0 * h_max, n_out + f0, out2d + (size_t)f0 * C * h_max,
+                               n_out2d + (size_t)f0 * C, st));
+    } else {
       ProfScope ps(h, 2, st);
       CU(ses3d::launch_finalize(h->tb, d, n_hyp, sc.tmp.as<ses3d_person_cov>(), sc.keep.as<int32_t>(),
                                 out + (size_t)f0 * h_max, n_out + f0, st));
     }
-    h->launches += 3;
+    h->launches += 4;
   }
   return SES3D_OK;
 }
@@ -305,12 +313,13 @@ int run_batch(ses3d_handle_s* h, int stages, int n_frames, int p_max, const ses3
     // tail of one kernel overlaps the head of the next. Profiling runs serially so per-kernel times stay clean.
     int n_split = (h->profiling || n_frames < 4096) ? 1 : std::min(h->device_split, (int)ses3d_handle_s::kSlots);
     if (n_split <= 1) {
+      const bool fused = (stages & TRI) && (stages & REP);
       if (stages & TRI) {
         int rc = triangulate_on_device(h, h->slot[0].sc, st, n_frames, p_max, h_max, persons, n_persons, io3d, n_io3d,
-                                       hyp_of, n_hyp_d, n_hung_d);
+                                       hyp_of, n_hyp_d, n_hung_d, fused ? out2d : nullptr, fused ? n_out2d : nullptr);
         if (rc) return rc;
       }
-      if (stages & REP) {
+      if ((stages & REP) && !fused) {
         int rc = reproject_on_device(h, st, n_frames, h_max, io3d, n_io3d, out2d, n_out2d);
         if (rc) return rc;
       }
@@ -321,14 +330,17 @@ int run_batch(ses3d_handle_s* h, int stages, int n_frames, int p_max, const ses3
         const int f0 = (int)((int64_t)n_frames * i / n_split), f1 = (int)((int64_t)n_frames * (i + 1) / n_split);
         const int nf = f1 - f0;
         if (s.stream != st) CU(cudaStreamWaitEvent(s.stream, h->fork_ev, 0));
+        const bool fused = (stages & TRI) && (stages & REP);
         if (stages & TRI) {
           int rc = triangulate_on_device(h, s.sc, s.stream, nf, p_max, h_max, persons + (size_t)f0 * C * p_max,
                                          n_persons + (size_t)f0 * C, io3d + (size_t)f0 * h_max, n_io3d + f0,
                                          hyp_of ? hyp_of + (size_t)f0 * C * p_max : nullptr,
-                                         n_hyp_d ? n_hyp_d + f0 : nullptr, n_hung_d ? n_hung_d + f0 : nullptr);
+                                         n_hyp_d ? n_hyp_d + f0 : nullptr, n_hung_d ? n_hung_d + f0 : nullptr,
+                                         fused ? out2d + (size_t)f0 * C * h_max : nullptr,
+                                         fused ? n_out2d + (size_t)f0 * C : nullptr);
           if (rc) return rc;
         }
-        if (stages & REP) {
+        if ((stages & REP) && !fused) {
           int rc = reproject_on_device(h, s.stream, nf, h_max, io3d + (size_t)f0 * h_max, n_io3d + f0,
                                        out2d + (size_t)f0 * C * h_max, n_out2d + (size_t)f0 * C);
           if (rc) return rc;
@@ -361,6 +373,12 @@ int run_batch(ses3d_handle_s* h, int stages, int n_frames, int p_max, const ses3
     CU(s.n_out3d.ensure((size_t)nf * 4));
     // padded outputs travel whole: unused slots are zero, never stale device memory
     if ((stages & TRI) && io3d) CU(cudaMemsetAsync(s.out3d.p, 0, (size_t)nf * h_max * sizeof(ses3d_person_cov), st));
+    const bool fused = (stages & TRI) && (stages & REP);
+    if (stages & REP) {
+      CU(s.out2d.ensure((size_t)nf * C * h_max * sizeof(ses3d_person2d)));
+      CU(s.n_out2d.ensure((size_t)nf * C * 4));
+      CU(cudaMemsetAsync(s.out2d.p, 0, (size_t)nf * C * h_max * sizeof(ses3d_person2d), st));
+    }
     if (stages & TRI) {
       CU(s.persons.ensure((size_t)nf * C * p_max * sizeof(ses3d_person2d)));
       CU(s.n_persons.ensure((size_t)nf * C * 4));
@@ -377,7 +395,9 @@ int run_batch(ses3d_handle_s* h, int stages, int n_frames, int p_max, const ses3
       if (n_hung_d) { CU(s.dump_nhung.ensure((size_t)nf * 4)); d_nhung = s.dump_nhung.as<int32_t>(); }
       int rc = triangulate_on_device(h, s.sc, st, nf, p_max, h_max, s.persons.as<ses3d_person2d>(),
                                      s.n_persons.as<int32_t>(), s.out3d.as<ses3d_person_cov>(),
-                                     s.n_out3d.as<int32_t>(), d_hyp_of, d_nhyp, d_nhung);
+                                     s.n_out3d.as<int32_t>(), d_hyp_of, d_nhyp, d_nhung,
+                                     fused ? s.out2d.as<ses3d_person2d>() : nullptr,
+                                     fused ? s.n_out2d.as<int32_t>() : nullptr);
       if (rc) return rc;
       if (io3d) CU(cudaMemcpyAsync(io3d + (size_t)f0 * h_max, s.out3d.p, (size_t)nf * h_max * sizeof(ses3d_person_cov),
                                    cudaMemcpyDeviceToHost, st));
@@ -392,12 +412,11 @@ int run_batch(ses3d_handle_s* h, int stages, int n_frames, int p_max, const ses3
       CU(cudaMemcpyAsync(s.n_out3d.p, n_io3d + f0, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
     }
     if (stages & REP) {
-      CU(s.out2d.ensure((size_t)nf * C * h_max * sizeof(ses3d_person2d)));
-      CU(s.n_out2d.ensure((size_t)nf * C * 4));
-      CU(cudaMemsetAsync(s.out2d.p, 0, (size_t)nf * C * h_max * sizeof(ses3d_person2d), st));
-      int rc = reproject_on_device(h, st, nf, h_max, s.out3d.as<ses3d_person_cov>(), s.n_out3d.as<int32_t>(),
-                                   s.out2d.as<ses3d_person2d>(), s.n_out2d.as<int32_t>());
-      if (rc) return rc;
+      if (!fused) {
+        int rc = reproject_on_device(h, st, nf, h_max, s.out3d.as<ses3d_person_cov>(), s.n_out3d.as<int32_t>(),
+                                     s.out2d.as<ses3d_person2d>(), s.n_out2d.as<int32_t>());
+        if (rc) return rc;
+      }
       CU(cudaMemcpyAsync(out2d + (size_t)f0 * C * h_max, s.out2d.p, (size_t)nf * C * h_max * sizeof(ses3d_person2d),
                          cudaMemcpyDeviceToHost, st));
       CU(cudaMemcpyAsync(n_out2d + (size_t)f0 * C, s.n_out2d.p, (size_t)nf * C * 4, cudaMemcpyDeviceToHost, st));
@@ -542,10 +561,7 @@ int run_ragged_impl(ses3d_handle_s* h, int n_frames, int p_max, const ses3d_pers
                                   s.in_off.as<long long>(), s.persons.p, s.in_dense.p, -1, st));
     int rc = triangulate_on_device(h, s.sc, st, nf, p_max, h_max, s.persons.as<ses3d_person2d>(),
                                    s.n_persons.as<int32_t>(), s.out3d.as<ses3d_person_cov>(), s.n_out3d.as<int32_t>(),
-                                   nullptr, nullptr, nullptr);
-    if (rc) { status = rc; break; }
-    rc = reproject_on_device(h, st, nf, h_max, s.out3d.as<ses3d_person_cov>(), s.n_out3d.as<int32_t>(),
-                             s.out2d.as<ses3d_person2d>(), s.n_out2d.as<int32_t>());
+                                   nullptr, nullptr, nullptr, s.out2d.as<ses3d_person2d>(), s.n_out2d.as<int32_t>());
     if (rc) { status = rc; break; }
     if (direct) {
       // the scans continue the running totals of the previous chunk (which ran on another slot's stream)
@@ -685,6 +701,8 @@ int ses3d_create(int32_t n_cams, const ses3d_camera* cams, const ses3d_params* p
   h->tb.f_row = h->d_frow.as<int>();
   h->tb.model = h->host.model;
   h->tb.prm = prm;
+  h->tb.exact_mode = 3;
+  if (const char* env = getenv("SES3D_TRI_EXACT")) h->tb.exact_mode = atoi(env);
   *out = h;
   return SES3D_OK;
 }
@@ -828,6 +846,7 @@ int ses3d_reserve(ses3d_handle h, int32_t n_frames, int32_t p_max, int32_t h_max
   ses3d::associate_smem_bytes(C, p_max, h_max, &need_nk);
   for (Slot& s : h->slot) {
     CU(s.sc.pairs.ensure((size_t)nf * ses3d::associate_pair_table_bytes(C, p_max)));
+    CU(s.sc.meta.ensure((size_t)nf * ses3d::associate_meta_bytes(C, p_max)));
     CU(s.sc.hyp_det.ensure((size_t)nf * h_max * C));
     CU(s.sc.n_hyp.ensure((size_t)nf * 4));
     CU(s.sc.n_hung.ensure((size_t)nf * 4));

@@ -8,17 +8,21 @@
 // reference's float/double split and evaluation order and MUST be compiled without FMA
 // contraction (nvcc -fmad=false; g++ -ffp-contract=off).
 //
-// B200 mapping: one team per frame, two phases.
-//  (1) pair table: calcCost only ever combines a detection of an earlier camera (a hypothesis
-//      observation) with a detection of a later camera, and every earlier valid detection belongs to
-//      exactly one hypothesis, so the set of (observation, detection) pairs the reference evaluates over
-//      all camera rounds is exactly "all cross-camera pairs of valid detections". Their mean epipolar
-//      distances E[a][b] (S3D:353-368) are computed up front in ONE flat parallel pass - all the
-//      floating-point work of the association, no dependency on the matching - and kept in an
-//      L2-resident table.
-//  (2) the sequential Tanke-Gall camera rounds then only gather table entries: a cost-matrix entry is
-//      the in-order mean of <= n_obs lookups; the ambiguity test, the warp-cooperative Munkres and the
-//      hypothesis update are integer work on shared memory.
+// B200 mapping: two kernels, because the two halves of the association want opposite things from an SM.
+//  (1) pair table (pairs_frame, kernel K2a, one CTA per frame): calcCost only ever combines a detection of an
+//      earlier camera (a hypothesis observation) with a detection of a later camera, and every earlier valid
+//      detection belongs to exactly one hypothesis, so the set of (observation, detection) pairs the reference
+//      evaluates over all camera rounds is exactly "all cross-camera pairs of valid detections". Their mean epipolar
+//      distances E[a][b] (S3D:353-368) are computed up front in ONE flat parallel pass - all the floating-point work
+//      of the association, no dependency on the matching - into an L2-resident table. Throughput-bound: wide CTAs,
+//      the frame's normalised keypoints in shared memory (13 KB at 16 x 6).
+//  (2) camera rounds (rounds_frame, kernel K2b, one WARP per frame): the sequential Tanke-Gall rounds only gather
+//      table entries - a cost-matrix entry is the in-order mean of <= n_obs lookups - then the ambiguity test, the
+//      warp-cooperative Munkres and the hypothesis update: integer work on a few KB of shared memory, latency-bound.
+//      With the keypoints gone a warp needs ~3 KB, so dozens of frames are in flight per SM and hide each other's
+//      latency (in round 1 both phases shared one CTA: two of three warps idled through the rounds while the CTA
+//      kept 17 KB of shared memory).
+//  The compact list of valid detections (FrameMeta) travels from (1) to (2) through global memory.
 #pragma once
 #include "common.h"
 #include "team.h"
@@ -27,15 +31,45 @@ namespace ses3d {
 
 enum { SC_N_HYP = 0, SC_N_DET, SC_N_HUNG, SC_OVERFLOW, SC_CURSOR, SC_N_VALID, SC_AMBIG, SC_COUNT };
 
+// Per-frame hand-over from the pair kernel to the rounds kernel (global memory):
+//   int32 n_valid | uint16 voff[C+1] | uint16 vslot[n_max] | (pad to 4) | float pscore[n_max]      n_max = C * p_max
+struct FrameMeta {
+  int32_t* n_valid;
+  uint16_t* voff;     // [C+1] first compact index of each camera
+  uint16_t* vslot;    // [n_max] compact index -> slot (cam * p_max + det)
+  float* pscore;      // [n_max] Person2D.score, by compact index
+};
+SES_HD size_t frame_meta_bytes(int C, int p_max) {
+  size_t b = 4 + 2 * (size_t)(C + 1) + 2 * (size_t)C * p_max;
+  b = (b + 3) / 4 * 4;
+  return (b + 4 * (size_t)C * p_max + 15) / 16 * 16;
+}
+SES_HD FrameMeta frame_meta_at(void* base, int C, int p_max) {
+  unsigned char* p = static_cast<unsigned char*>(base);
+  FrameMeta m;
+  m.n_valid = reinterpret_cast<int32_t*>(p);
+  m.voff = reinterpret_cast<uint16_t*>(p + 4);
+  m.vslot = m.voff + (C + 1);
+  size_t b = 4 + 2 * (size_t)(C + 1) + 2 * (size_t)C * p_max;
+  b = (b + 3) / 4 * 4;
+  m.pscore = reinterpret_cast<float*>(p + b);
+  return m;
+}
+
 struct AssocWs {
+  // ---- pair kernel
   float* nk;          // [C*p_max][17][2] normalised keypoints x, y (shared memory, or global scratch for big rigs)
+  uint32_t* kmask;    // [C*p_max] bit k: keypoint k has score > threshold (the strict test of calcCost, S3D:354)
+  uint8_t* valid;     // [C*p_max] more than 8 valid keypoints (S3D:579,599), by slot
+  uint32_t* pstart;   // [C*p_max+1] cross-camera pairs before compact detection b (b pairs with every earlier camera's)
+  // ---- both
   double* E;          // [n(n-1)/2], n = C*p_max: pair table in global memory, index b(b-1)/2 + a for a < b
                       //   (compact indices of valid detections, camera-major); -1 = no joint in common
-  uint32_t* kmask;    // [C*p_max] bit k: keypoint k has score > threshold (the strict test of calcCost, S3D:354)
-  float* pscore;      // [C*p_max] Person2D.score, by compact index
-  uint16_t* vslot;    // [C*p_max] compact index -> slot (cam * p_max + det)
-  uint16_t* voff;     // [C+1] first compact index of each camera
-  uint8_t* valid;     // [C*p_max] more than 8 valid keypoints (S3D:579,599), by slot
+  float* pscore;      // [C*p_max] Person2D.score, by compact index          (FrameMeta)
+  uint16_t* vslot;    // [C*p_max] compact index -> slot (cam * p_max + det)  (FrameMeta)
+  uint16_t* voff;     // [C+1] first compact index of each camera             (FrameMeta)
+  int* scal;          // [SC_COUNT]
+  // ---- rounds kernel
   uint8_t* hyp_nobs;  // [h_cap]
   uint16_t* hyp_obs;  // [h_cap][C] observation list (compact indices), in camera order
   double* cost;       // [h_cap*p_max] column-major n_hyp x n_det (S3D:611)
@@ -43,24 +77,39 @@ struct AssocWs {
   uint8_t *mask, *star, *prime, *nstar;  // [h_cap*p_max]
   uint8_t *cov_r, *cov_c, *handled;      // [h_cap], [p_max], [p_max]
   int* assignment;    // [h_cap]
-  int* scal;          // [SC_COUNT]
 };
 
-// Lays the shared-memory workspace out; nk_inside = false keeps the keypoints in global scratch
-// (rigs whose frame does not fit in shared memory).
+// Shared-memory workspace of the pair kernel; nk_inside = false keeps the keypoints in global scratch
+// (rigs whose frame does not fit in shared memory). vslot / voff / pscore are staged here and copied to FrameMeta.
 template <class A>
-SES_HD void assoc_ws_layout(A& ar, int C, int p_max, int h_cap, bool nk_inside, AssocWs* ws) {
-  double* cost = ar.template take<double>((size_t)h_cap * p_max);
-  double* dist = ar.template take<double>((size_t)h_cap * p_max);
+SES_HD void pair_ws_layout(A& ar, int C, int p_max, bool nk_inside, AssocWs* ws) {
   float* nk = nk_inside ? ar.template take<float>((size_t)C * p_max * NKP * 2) : nullptr;
   uint32_t* kmask = ar.template take<uint32_t>((size_t)C * p_max);
-  float* pscore = ar.template take<float>((size_t)C * p_max);
-  int* assignment = ar.template take<int>(h_cap);
+  uint32_t* pstart = ar.template take<uint32_t>((size_t)C * p_max + 1);
   int* scal = ar.template take<int>(SC_COUNT);
-  uint16_t* hyp_obs = ar.template take<uint16_t>((size_t)h_cap * C);
   uint16_t* vslot = ar.template take<uint16_t>((size_t)C * p_max);
   uint16_t* voff = ar.template take<uint16_t>(C + 1);
   uint8_t* valid = ar.template take<uint8_t>((size_t)C * p_max);
+  if (ws) {
+    if (nk_inside) ws->nk = nk;
+    ws->kmask = kmask; ws->pstart = pstart; ws->scal = scal; ws->vslot = vslot; ws->voff = voff; ws->valid = valid;
+  }
+}
+inline size_t pair_ws_bytes(int C, int p_max, bool nk_inside) {
+  ArenaSizer s;
+  pair_ws_layout(s, C, p_max, nk_inside, nullptr);
+  return (s.used + 15) / 16 * 16;
+}
+
+// Shared-memory workspace of one frame in the rounds kernel (per warp). The compact detection list is read from
+// FrameMeta in global memory (L1-resident, a few hundred bytes).
+template <class A>
+SES_HD void round_ws_layout(A& ar, int C, int p_max, int h_cap, AssocWs* ws) {
+  double* cost = ar.template take<double>((size_t)h_cap * p_max);
+  double* dist = ar.template take<double>((size_t)h_cap * p_max);
+  int* assignment = ar.template take<int>(h_cap);
+  int* scal = ar.template take<int>(SC_COUNT);
+  uint16_t* hyp_obs = ar.template take<uint16_t>((size_t)h_cap * C);
   uint8_t* hyp_nobs = ar.template take<uint8_t>(h_cap);
   uint8_t* mask = ar.template take<uint8_t>((size_t)h_cap * p_max);
   uint8_t* star = ar.template take<uint8_t>((size_t)h_cap * p_max);
@@ -70,16 +119,14 @@ SES_HD void assoc_ws_layout(A& ar, int C, int p_max, int h_cap, bool nk_inside, 
   uint8_t* cov_c = ar.template take<uint8_t>(p_max);
   uint8_t* handled = ar.template take<uint8_t>(p_max);
   if (ws) {
-    ws->cost = cost; ws->dist = dist; if (nk_inside) ws->nk = nk; ws->kmask = kmask; ws->pscore = pscore;
-    ws->assignment = assignment; ws->scal = scal; ws->hyp_obs = hyp_obs; ws->vslot = vslot; ws->voff = voff;
-    ws->valid = valid; ws->hyp_nobs = hyp_nobs; ws->mask = mask; ws->star = star; ws->prime = prime;
-    ws->nstar = nstar; ws->cov_r = cov_r; ws->cov_c = cov_c; ws->handled = handled;
+    ws->cost = cost; ws->dist = dist; ws->assignment = assignment; ws->scal = scal; ws->hyp_obs = hyp_obs;
+    ws->hyp_nobs = hyp_nobs; ws->mask = mask; ws->star = star; ws->prime = prime; ws->nstar = nstar;
+    ws->cov_r = cov_r; ws->cov_c = cov_c; ws->handled = handled;
   }
 }
-
-inline size_t assoc_ws_bytes(int C, int p_max, int h_cap, bool nk_inside) {
+inline size_t round_ws_bytes(int C, int p_max, int h_cap) {
   ArenaSizer s;
-  assoc_ws_layout(s, C, p_max, h_cap, nk_inside, nullptr);
+  round_ws_layout(s, C, p_max, h_cap, nullptr);
   return (s.used + 15) / 16 * 16;
 }
 
@@ -220,15 +267,13 @@ SES_HD void munkres_coop(WT& tm, const AssocWs& ws, const double* in, int n_r, i
   });
 }
 
-// One frame. persons [C][p_max], n_persons [C]. Outputs: hyp_det [h_cap][C] (detection slot of
-// hypothesis h in camera c or -1), n_hyp, n_hungarian, overflow flag (h_cap exceeded).
+// K2a, one frame. persons [C][p_max], n_persons [C]. Outputs: the pair table ws.E and the compact detection list
+// (meta). ws = pair_ws_layout.
 template <class Team>
-SES_HD void associate_frame(Team& tm, const Tables& tb, int p_max, int h_cap, const ses3d_person2d* persons,
-                            const int32_t* n_persons, const AssocWs& ws, int8_t* hyp_det, int32_t* n_hyp_out,
-                            int32_t* n_hung_out, int32_t* overflow_out) {
+SES_HD void pairs_frame(Team& tm, const Tables& tb, int p_max, const ses3d_person2d* persons, const int32_t* n_persons,
+                        const AssocWs& ws, const FrameMeta& meta) {
   const int C = tb.n_cams;
   const float thr = tb.prm.triangulation_threshold;
-  const double max_epi = tb.prm.max_epipolar_error;
   auto np = [&](int c) { const int n = n_persons[c]; return n < 0 ? 0 : (n > p_max ? p_max : n); };
 
   // normalize_keypoints for every detection of the frame (S3D:312-333)
@@ -258,31 +303,42 @@ SES_HD void associate_frame(Team& tm, const Tables& tb, int p_max, int h_cap, co
     ws.valid[cd] = n_valid > NKP / 2 ? 1 : 0;
     ws.kmask[cd] = strict;
   });
-  // compact, camera-major list of the valid detections
+  // compact, camera-major list of the valid detections; pstart[b] = cross-camera pairs (a, b'), b' < b
   tm.single([&] {
     int n = 0;
+    uint32_t pairs = 0;
     for (int c = 0; c < C; ++c) {
       ws.voff[c] = (uint16_t)n;
+      const int before = n;   // every detection of an earlier camera pairs with each detection of camera c
       for (int d = 0; d < np(c); ++d)
-        if (ws.valid[c * p_max + d]) { ws.vslot[n] = (uint16_t)(c * p_max + d); ++n; }
+        if (ws.valid[c * p_max + d]) {
+          ws.vslot[n] = (uint16_t)(c * p_max + d);
+          ws.pstart[n] = pairs;
+          pairs += (uint32_t)before;
+          ++n;
+        }
     }
     ws.voff[C] = (uint16_t)n;
+    ws.pstart[n] = pairs;
     ws.scal[SC_N_VALID] = n;
+    *meta.n_valid = n;
   });
   const int n_valid = ws.scal[SC_N_VALID];
-  tm.pfor(n_valid, [&](int a) { ws.pscore[a] = persons[ws.vslot[a]].score; });
+  tm.pfor(n_valid, [&](int a) { meta.vslot[a] = ws.vslot[a]; meta.pscore[a] = persons[ws.vslot[a]].score; });
+  tm.pfor(C + 1, [&](int c) { meta.voff[c] = ws.voff[c]; });
 
-  // phase 1 - pair table: mean symmetric epipolar distance of every cross-camera pair of valid detections,
-  // the inner loop of calcCost (S3D:347-368), joints in ascending order, float distances summed in double
-  tm.pfor(n_valid * (n_valid - 1) / 2, [&](int e) {
-    // e -> (a, b), a < b: row b of the strictly lower triangle starts at b(b-1)/2
-    int b = (int)((1.0f + ses_sqrt(1.0f + 8.0f * (float)e)) * 0.5f);
-    while (b * (b - 1) / 2 > e) --b;
-    while ((b + 1) * b / 2 <= e) ++b;
-    const int a = e - b * (b - 1) / 2;
+  // pair table: mean symmetric epipolar distance of every cross-camera pair of valid detections, the inner loop of
+  // calcCost (S3D:347-368), joints in ascending order, float distances summed in double
+  tm.pfor((int)ws.pstart[n_valid], [&](int e) {
+    // e -> (a, b): b = the detection whose pair range contains e (binary search), a = offset inside it
+    int lo = 0, hi = n_valid;   // invariant: pstart[lo] <= e < pstart[hi]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (ws.pstart[mid] <= (uint32_t)e) lo = mid; else hi = mid;
+    }
+    const int b = lo, a = e - (int)ws.pstart[b];
     const int sa = ws.vslot[a], sb = ws.vslot[b];
     const int ca = sa / p_max, cb = sb / p_max;
-    if (ca == cb) return;
     const float* F = tb.F + (size_t)fundamental_idx(tb, ca, cb) * 9;
     const float* hk = ws.nk + ((size_t)sa * NKP) * 2;
     const float* dk = ws.nk + ((size_t)sb * NKP) * 2;
@@ -295,8 +351,21 @@ SES_HD void associate_frame(Team& tm, const Tables& tb, int p_max, int h_cap, co
       cost += static_cast<double>(epipolar_symmetric(F, hk[2 * k], hk[2 * k + 1], dk[2 * k], dk[2 * k + 1]));
       ++n_joints;
     }
-    ws.E[e] = n_joints > 0 ? cost / n_joints : -1.0;
+    ws.E[(size_t)b * (b - 1) / 2 + a] = n_joints > 0 ? cost / n_joints : -1.0;
   });
+}
+
+// K2b, one frame: the Tanke-Gall camera rounds over the pair table. ws = round_ws_layout + E + the FrameMeta
+// pointers (pscore, vslot, voff). Outputs: hyp_det [h_cap][C] (detection slot of hypothesis h in camera c or -1),
+// n_hyp, n_hungarian, overflow flag (h_cap exceeded).
+template <class Team>
+SES_HD void rounds_frame(Team& tm, const Tables& tb, int p_max, int h_cap, const int32_t* n_persons, int n_valid,
+                         const AssocWs& ws, int8_t* hyp_det, int32_t* n_hyp_out, int32_t* n_hung_out,
+                         int32_t* overflow_out) {
+  const int C = tb.n_cams;
+  const double max_epi = tb.prm.max_epipolar_error;
+  auto np = [&](int c) { const int n = n_persons[c]; return n < 0 ? 0 : (n > p_max ? p_max : n); };
+  (void)n_valid;
 
   auto add_hyp = [&](int a) {  // push_back of a one-observation hypothesis
     const int h = ws.scal[SC_N_HYP];
@@ -322,17 +391,13 @@ SES_HD void associate_frame(Team& tm, const Tables& tb, int p_max, int h_cap, co
     ws.scal[SC_CURSOR] = c;
   });
 
-  // phase 2 - camera rounds (S3D:588-674). The rounds are sequential and, for ordinary rigs, tiny (a handful of
-  // hypotheses x detections per camera): five barriers per round on the whole CTA cost more than the work between
-  // them, so frames with few detections run all rounds on the team's first warp (warp-level barriers only); crowd
-  // rigs keep the CTA-wide version.
-  auto rounds = [&](auto& t) {
+  // camera rounds (S3D:588-674)
   for (int cam = ws.scal[SC_CURSOR]; cam < C; ++cam) {
     const int b0 = ws.voff[cam], n_det = ws.voff[cam + 1] - b0, n_hyp = ws.scal[SC_N_HYP];
     if (n_det == 0) continue;  // covers "no person" and "no valid person" (S3D:539-541, 608-609)
 
     // cost matrix entry = outer part of calcCost (S3D:367-389) over table lookups, observations in order
-    t.pfor(n_hyp * n_det, [&](int e) {
+    tm.pfor(n_hyp * n_det, [&](int e) {
       const int h = e % n_hyp, b = b0 + e / n_hyp;
       const int n_obs = ws.hyp_nobs[h];
       double total = 0., tmp_veto = 0.;
@@ -359,8 +424,8 @@ SES_HD void associate_frame(Team& tm, const Tables& tb, int p_max, int h_cap, co
     // provisional assignment = the last passing detection per hypothesis (S3D:616-626); the Munkres solve is
     // needed when any row or column of the mask has more than one hit (S3D:628). One thread per row / column;
     // the flag write is the same value from every writer.
-    t.single([&] { ws.scal[SC_AMBIG] = 0; });
-    t.pfor(n_hyp + n_det, [&](int i) {
+    tm.single([&] { ws.scal[SC_AMBIG] = 0; });
+    tm.pfor(n_hyp + n_det, [&](int i) {
       int cnt = 0;
       if (i < n_hyp) {
         int last = -1;
@@ -373,11 +438,11 @@ SES_HD void associate_frame(Team& tm, const Tables& tb, int p_max, int h_cap, co
       }
       if (cnt > 1) ws.scal[SC_AMBIG] = 1;
     });
-    t.single([&] { if (ws.scal[SC_AMBIG]) ++ws.scal[SC_N_HUNG]; });
-    if (ws.scal[SC_AMBIG]) {  // S3D:628-634: full Munkres on the cost matrix, solved by the team's first warp
-      t.warp0([&](auto& wt) { munkres_coop(wt, ws, ws.cost, n_hyp, n_det, ws.assignment); });
+    tm.single([&] { if (ws.scal[SC_AMBIG]) ++ws.scal[SC_N_HUNG]; });
+    if (ws.scal[SC_AMBIG]) {  // S3D:628-634: full Munkres on the cost matrix
+      tm.warp0([&](auto& wt) { munkres_coop(wt, ws, ws.cost, n_hyp, n_det, ws.assignment); });
     }
-    t.single([&] {
+    tm.single([&] {
       for (int d = 0; d < n_det; ++d) ws.handled[d] = 0;
       for (int h = 0; h < n_hyp; ++h) {  // S3D:637-660
         const int d = ws.assignment[h];
@@ -394,9 +459,6 @@ SES_HD void associate_frame(Team& tm, const Tables& tb, int p_max, int h_cap, co
         if (!ws.handled[d]) add_hyp(b0 + d);
     });
   }
-  };
-  if (n_valid <= 96) tm.warp0([&](auto& w) { rounds(w); });
-  else rounds(tm);
 
   // export the hypothesis table
   const int n_hyp = ws.scal[SC_N_HYP];

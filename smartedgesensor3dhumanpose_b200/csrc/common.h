@@ -55,6 +55,8 @@ struct Tables {
   const int* f_row;   // [C]: start index of row i in F (sum_{ii<i} (C-ii-1)), so idx(i,j) = f_row[i] + j-i-1
   SkeletonModel model;
   ses3d_params prm;
+  int exact_mode;     // bit 0: exact re-solve of far / high-residual joints, bit 1: exact covariance of far joints
+                      // (3 = default; SES3D_TRI_EXACT overrides it for A/B measurements only)
 };
 
 SES_HD int fundamental_idx(const Tables& tb, int i, int j) { return tb.f_row[i] + j - i - 1; }  // S3D:242-253, i<j

@@ -16,23 +16,44 @@ namespace ses3d {
 
 extern __shared__ __align__(16) unsigned char smem_raw[];
 
+// K2a: pair table + compact detection list of one frame per CTA (assoc_core.h::pairs_frame)
 __global__ void __launch_bounds__(256)
-k_associate(const Tables tb, int n_frames, int p_max, int h_cap, const ses3d_person2d* __restrict__ persons,
-            const int32_t* __restrict__ n_persons, float* nk_scratch, double* pair_table, int8_t* __restrict__ hyp_det,
-            int32_t* __restrict__ n_hyp, int32_t* __restrict__ n_hung, int32_t* overflow, int32_t* hyp_of_dump,
-            int32_t* __restrict__ keep, uint32_t* __restrict__ work, int32_t* work_count) {
+k_pairs(const Tables tb, int n_frames, int p_max, const ses3d_person2d* __restrict__ persons,
+        const int32_t* __restrict__ n_persons, float* nk_scratch, double* pair_table, unsigned char* meta_base,
+        size_t meta_stride) {
   const int f = blockIdx.x;
   if (f >= n_frames) return;
   const int C = tb.n_cams;
   Arena ar(smem_raw);
   AssocWs ws;
-  assoc_ws_layout(ar, C, p_max, h_cap, nk_scratch == nullptr, &ws);
+  pair_ws_layout(ar, C, p_max, nk_scratch == nullptr, &ws);
   if (nk_scratch) ws.nk = nk_scratch + (size_t)f * C * p_max * NKP * 2;
   ws.E = pair_table + (size_t)f * assoc_pair_table_entries(C, p_max);
   BlockTeam tm;
+  pairs_frame(tm, tb, p_max, persons + (size_t)f * C * p_max, n_persons + (size_t)f * C, ws,
+              frame_meta_at(meta_base + (size_t)f * meta_stride, C, p_max));
+}
+
+// K2b: the sequential camera rounds, one WARP per frame (assoc_core.h::rounds_frame), plus the K3 work list
+__global__ void __launch_bounds__(128)
+k_rounds(const Tables tb, int n_frames, int p_max, int h_cap, size_t ws_bytes, const int32_t* __restrict__ n_persons,
+         const double* pair_table, unsigned char* meta_base, size_t meta_stride, int8_t* __restrict__ hyp_det,
+         int32_t* __restrict__ n_hyp, int32_t* __restrict__ n_hung, int32_t* overflow, int32_t* hyp_of_dump,
+         int32_t* __restrict__ keep, uint32_t* __restrict__ work, int32_t* work_count, int32_t* __restrict__ n_out_zero) {
+  const int warp = (int)(threadIdx.x >> 5);
+  const int f = (int)blockIdx.x * (int)(blockDim.x >> 5) + warp;
+  if (f >= n_frames) return;
+  const int C = tb.n_cams;
+  Arena ar(smem_raw + (size_t)warp * ws_bytes);
+  AssocWs ws;
+  round_ws_layout(ar, C, p_max, h_cap, &ws);
+  const FrameMeta meta = frame_meta_at(meta_base + (size_t)f * meta_stride, C, p_max);
+  ws.voff = meta.voff; ws.vslot = meta.vslot; ws.pscore = meta.pscore;
+  ws.E = const_cast<double*>(pair_table) + (size_t)f * assoc_pair_table_entries(C, p_max);
+  WarpTeam tm;
   int8_t* hd = hyp_det + (size_t)f * h_cap * C;
-  associate_frame(tm, tb, p_max, h_cap, persons + (size_t)f * C * p_max, n_persons + (size_t)f * C, ws, hd, n_hyp + f,
-                  n_hung ? n_hung + f : nullptr, overflow);
+  rounds_frame(tm, tb, p_max, h_cap, n_persons + (size_t)f * C, *meta.n_valid, ws, hd, n_hyp + f,
+               n_hung ? n_hung + f : nullptr, overflow);
   // work list for K3: every hypothesis with at least two observations (S3D:684); order is irrelevant
   // because results are addressed by (frame, hypothesis)
   tm.pfor(h_cap, [&](int h) { keep[(size_t)f * h_cap + h] = 0; });
@@ -45,6 +66,7 @@ k_associate(const Tables tb, int n_frames, int p_max, int h_cap, const ses3d_per
       for (int h = 0; h < nh; ++h)
         if (ws.hyp_nobs[h] >= 2) work[at++] = (uint32_t)((size_t)f * h_cap + h);
     }
+    if (n_out_zero) n_out_zero[f] = 0;
   });
   if (hyp_of_dump) {  // [C][p_max] hypothesis index of each detection
     int32_t* ho = hyp_of_dump + (size_t)f * C * p_max;
@@ -85,6 +107,32 @@ k_reproject(const Tables tb, int n_frames, int h_max, int cap_rec, int s_cap,
                   out + (size_t)f * tb.n_cams * h_max, n_out + (size_t)f * tb.n_cams);
 }
 
+// K4 + K6 fused (process calls): the CTA first compacts / merges the frame's skeletons into the PersonCovList
+// (finalize_frame), then re-projects that list into every camera (reproject_frame). The two steps use the shared
+// memory one after the other (aliased workspaces); the list is read back through L1 / L2, it never waits for DRAM.
+__global__ void __launch_bounds__(128)
+k_finproj(const Tables tb, int n_frames, int h_max, int cap_rec, int s_cap, const int32_t* __restrict__ n_hyp,
+          ses3d_person_cov* tmp, const int32_t* __restrict__ keep, ses3d_person_cov* out3d, int32_t* n_out3d,
+          ses3d_person2d* __restrict__ out2d, int32_t* __restrict__ n_out2d) {
+  const int f = blockIdx.x;
+  if (f >= n_frames) return;
+  BlockTeam tm;
+  {
+    Arena ar(smem_raw);
+    FinWs ws;
+    fin_ws_layout(ar, h_max, &ws);
+    finalize_frame(tm, tb, h_max, n_hyp[f], tmp + (size_t)f * h_max, keep + (size_t)f * h_max, ws,
+                   out3d + (size_t)f * h_max, n_out3d + f);
+  }
+  __threadfence_block();
+  tm.sync();
+  Arena ar(smem_raw);
+  ReprojWs ws;
+  reproj_ws_layout(ar, tb.n_cams, cap_rec, s_cap, &ws);
+  reproject_frame(tm, tb, h_max, cap_rec, out3d + (size_t)f * h_max, n_out3d[f], ws,
+                  out2d + (size_t)f * tb.n_cams * h_max, n_out2d + (size_t)f * tb.n_cams);
+}
+
 // Batch of independent assignment problems, one warp each (test / diagnostics entry: lets the tests drive the
 // warp-cooperative Munkres with adversarial tied matrices). cost: [n][rows*cols] column-major.
 __global__ void __launch_bounds__(32)
@@ -93,7 +141,7 @@ k_munkres_batch(int n, int rows, int cols, const double* __restrict__ cost, int3
   if (i >= n) return;
   Arena ar(smem_raw);
   AssocWs ws;
-  assoc_ws_layout(ar, 1, cols, rows, false, &ws);
+  round_ws_layout(ar, 1, cols, rows, &ws);
   WarpTeam tm;
   const int n_e = rows * cols;
   tm.pfor(n_e, [&](int e) { ws.cost[e] = cost[(size_t)i * n_e + e]; });
@@ -106,7 +154,7 @@ static const size_t kAssocSmemTarget = 64 * 1024;
 
 cudaError_t launch_munkres_batch(int n, int rows, int cols, const double* cost, int32_t* assignment, cudaStream_t st) {
   if (rows < 1 || cols < 1 || rows > 1024 || cols > 127) return cudaErrorInvalidValue;
-  const size_t smem = assoc_ws_bytes(1, cols, rows, false);
+  const size_t smem = round_ws_bytes(1, cols, rows);
   if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
   k_munkres_batch<<<n, 32, smem, st>>>(n, rows, cols, cost, assignment);
   return cudaGetLastError();
@@ -114,14 +162,16 @@ cudaError_t launch_munkres_batch(int n, int rows, int cols, const double* cost, 
 
 
 size_t associate_smem_bytes(int n_cams, int p_max, int h_cap, bool* needs_scratch) {
-  size_t b = assoc_ws_bytes(n_cams, p_max, h_cap, true);
+  (void)h_cap;
+  size_t b = pair_ws_bytes(n_cams, p_max, true);
   bool scratch = b > kAssocSmemTarget;
-  if (scratch) b = assoc_ws_bytes(n_cams, p_max, h_cap, false);
+  if (scratch) b = pair_ws_bytes(n_cams, p_max, false);
   if (needs_scratch) *needs_scratch = scratch;
   return b;
 }
 
 size_t associate_pair_table_bytes(int n_cams, int p_max) { return assoc_pair_table_entries(n_cams, p_max) * sizeof(double); }
+size_t associate_meta_bytes(int n_cams, int p_max) { return frame_meta_bytes(n_cams, p_max); }
 
 static int env_int(const char* name, int fallback) {
   const char* v = getenv(name);
@@ -139,38 +189,51 @@ cudaError_t init_kernels(LaunchCfg* cfg, int device) {
   if (cfg->n_sm <= 0) cfg->n_sm = 148;
   cfg->assoc_threads = env_int("SES3D_ASSOC_THREADS", 0);
   if (cfg->assoc_threads) cfg->assoc_threads = std::max(32, std::min(256, cfg->assoc_threads / 32 * 32));
+  cfg->rounds_warps = std::max(1, std::min(4, env_int("SES3D_ROUNDS_WARPS", 4)));
   cfg->reproj_cap = env_int("SES3D_REPROJ_CAP", 0);
   cfg->reproj_scap = std::max(1, env_int("SES3D_REPROJ_SCAP", 6));
   cfg->reproj_threads = std::max(32, std::min(128, env_int("SES3D_REPROJ_THREADS", 128) / 32 * 32));
   cfg->tri_warps = env_int("SES3D_TRI_WARPS", 2);
   cfg->tri_warps_f64 = env_int("SES3D_TRI_WARPS_F64", 4);
+  cfg->tri_dynamic = env_int("SES3D_TRI_DYNAMIC", 1);
   const int budget = (int)kSmemBudget;
-  if ((e = cudaFuncSetAttribute(k_associate, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_rounds, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_reproject, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_finproj, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_munkres_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
   return init_kernels_tri(device);
 }
 
-cudaError_t launch_associate(const LaunchCfg& cfg, const Tables& tb, LaunchDims d, const ses3d_person2d* persons, const int32_t* n_persons,
-                             float* nk_scratch, double* pair_table, int8_t* hyp_det, int32_t* n_hyp, int32_t* n_hung,
-                             int32_t* overflow, int32_t* hyp_of_dump, int32_t* keep, uint32_t* work,
-                             int32_t* work_count, cudaStream_t st) {
+// K2 = K2a + K2b. n_out_zero (nullable): per-frame output count to clear (frames without work items never reach the
+// finalize step of a fused pipeline).
+cudaError_t launch_associate(const LaunchCfg& cfg, const Tables& tb, LaunchDims d, const ses3d_person2d* persons,
+                             const int32_t* n_persons, float* nk_scratch, double* pair_table, unsigned char* meta,
+                             int8_t* hyp_det, int32_t* n_hyp, int32_t* n_hung, int32_t* overflow, int32_t* hyp_of_dump,
+                             int32_t* keep, uint32_t* work, int32_t* work_count, cudaStream_t st) {
   bool scratch;
   const size_t smem = associate_smem_bytes(tb.n_cams, d.p_max, d.h_cap, &scratch);
   if (smem > kSmemBudget) return cudaErrorInvalidConfiguration;
-  // big rigs: hundreds of thousands of detection pairs per frame -> 256 threads; ordinary rigs (B200, hall16 x 6,
-  // ms per 16384 frames): 32 -> 1.66, 64 -> 1.41, 96 -> 1.37, 128 -> 1.42, 192 -> 1.67
-  int threads = scratch ? 256 : 96;
-  if (d.n_frames <= 296) threads = 256;   // fewer frames than two per SM: latency mode (single-frame call 75 -> 60 us)
+  // the pair pass is pure throughput work: wide CTAs. B200, hall16 x 6 (ms per 16384 frames): see RESULTS.md
+  int threads = scratch ? 256 : 128;
+  if (d.n_frames <= 296) threads = 256;   // fewer frames than two per SM: latency mode
   if (cfg.assoc_threads) threads = cfg.assoc_threads;
   if (scratch && !nk_scratch) return cudaErrorInvalidValue;
+  if (!pair_table || !meta) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(work_count, 0, 2 * sizeof(int32_t), st);   // [0] item count, [1] K3's claim counter
   if (e != cudaSuccess) return e;
-  if (!pair_table) return cudaErrorInvalidValue;
-  k_associate<<<d.n_frames, threads, smem, st>>>(tb, d.n_frames, d.p_max, d.h_cap, persons, n_persons,
-                                                 scratch ? nk_scratch : nullptr, pair_table, hyp_det, n_hyp, n_hung,
-                                                 overflow, hyp_of_dump, keep, work, work_count);
+  const size_t meta_stride = frame_meta_bytes(tb.n_cams, d.p_max);
+  k_pairs<<<d.n_frames, threads, smem, st>>>(tb, d.n_frames, d.p_max, persons, n_persons, scratch ? nk_scratch : nullptr,
+                                             pair_table, meta, meta_stride);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  const size_t rws = round_ws_bytes(tb.n_cams, d.p_max, d.h_cap);
+  int warps = cfg.rounds_warps;
+  while (warps > 1 && rws * warps > kSmemBudget) warps >>= 1;
+  if (rws * warps > kSmemBudget) return cudaErrorInvalidConfiguration;
+  k_rounds<<<(d.n_frames + warps - 1) / warps, 32 * warps, rws * warps, st>>>(
+      tb, d.n_frames, d.p_max, d.h_cap, rws, n_persons, pair_table, meta, meta_stride, hyp_det, n_hyp, n_hung, overflow,
+      hyp_of_dump, keep, work, work_count, nullptr);
   return cudaGetLastError();
 }
 
@@ -182,14 +245,34 @@ cudaError_t launch_finalize(const Tables& tb, LaunchDims d, const int32_t* n_hyp
   return cudaGetLastError();
 }
 
+static void reproject_config(const LaunchCfg& cfg, const Tables& tb, int h_max, int* cap_rec, int* s_cap, size_t* smem) {
+  // staging capacity in records: ~28 KB, at least one camera of h_max persons, at most the whole frame
+  int cr = std::max(h_max, std::min(tb.n_cams * h_max, std::max(48, 2 * h_max)));   // B200, hall16 x 6: 16 -> 1.25 ms, 32 -> 1.02, 48 -> 0.97, 64 -> 1.10, 96 -> 1.28
+  if (cfg.reproj_cap) cr = std::max(h_max, cfg.reproj_cap);
+  *cap_rec = cr;
+  *s_cap = reproj_s_cap(tb.n_cams, h_max, cfg.reproj_scap);
+  *smem = reproj_ws_bytes(tb.n_cams, cr, *s_cap);
+}
+
+cudaError_t launch_finproj(const LaunchCfg& cfg, const Tables& tb, LaunchDims d, const int32_t* n_hyp,
+                           ses3d_person_cov* tmp, const int32_t* keep, ses3d_person_cov* out3d, int32_t* n_out3d,
+                           ses3d_person2d* out2d, int32_t* n_out2d, cudaStream_t st) {
+  int cap_rec, s_cap;
+  size_t smem;
+  reproject_config(cfg, tb, d.h_cap, &cap_rec, &s_cap, &smem);
+  smem = std::max(smem, fin_ws_bytes(d.h_cap));
+  if (smem > kSmemBudget) return cudaErrorInvalidConfiguration;
+  k_finproj<<<d.n_frames, cfg.reproj_threads, smem, st>>>(tb, d.n_frames, d.h_cap, cap_rec, s_cap, n_hyp, tmp, keep, out3d,
+                                                         n_out3d, out2d, n_out2d);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_reproject(const LaunchCfg& cfg, const Tables& tb, int n_frames, int h_max,
                              const ses3d_person_cov* persons3d, const int32_t* n_persons3d, ses3d_person2d* out,
                              int32_t* n_out, cudaStream_t st) {
-  // staging capacity in records: ~28 KB, at least one camera of h_max persons, at most the whole frame
-  int cap_rec = std::max(h_max, std::min(tb.n_cams * h_max, std::max(48, 2 * h_max)));   // B200, hall16 x 6: 16 -> 1.25 ms, 32 -> 1.02, 48 -> 0.97, 64 -> 1.10, 96 -> 1.28
-  if (cfg.reproj_cap) cap_rec = std::max(h_max, cfg.reproj_cap);
-  const int s_cap = reproj_s_cap(tb.n_cams, h_max, cfg.reproj_scap);
-  const size_t smem = reproj_ws_bytes(tb.n_cams, cap_rec, s_cap);
+  int cap_rec, s_cap;
+  size_t smem;
+  reproject_config(cfg, tb, h_max, &cap_rec, &s_cap, &smem);
   if (smem > kSmemBudget) return cudaErrorInvalidConfiguration;
   const int threads = cfg.reproj_threads;
   k_reproject<<<n_frames, threads, smem, st>>>(tb, n_frames, h_max, cap_rec, s_cap, persons3d, n_persons3d, out, n_out);

@@ -15,7 +15,7 @@ template <class T, int kWarpsPerCta>
 __global__ void __launch_bounds__(32 * kWarpsPerCta, sizeof(T) == 4 ? 24 / kWarpsPerCta : 1)
 k_triangulate(const Tables tb, int p_max, int h_cap, size_t ws_bytes, const ses3d_person2d* __restrict__ persons,
               const int8_t* __restrict__ hyp_det, const uint32_t* __restrict__ work, int32_t* work_count,
-              ses3d_person_cov* __restrict__ tmp, int32_t* __restrict__ keep, float* far_scratch) {
+              ses3d_person_cov* __restrict__ tmp, int32_t* __restrict__ keep, float* far_scratch, int dynamic) {
   const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31u);
   const int n_work = work_count[0];
   WarpTeam tm;
@@ -27,10 +27,16 @@ k_triangulate(const Tables tb, int p_max, int h_cap, size_t ws_bytes, const ses3
   // dynamic work distribution: work_count[1] is the next unclaimed item (zeroed with work_count[0] by K2's launcher).
   // A hypothesis can cost several times the average (far joints are re-solved exactly), so items are handed out one by
   // one instead of in fixed strides - no warp is left holding a queue behind a slow item.
+  const int total_warps = (int)gridDim.x * kWarpsPerCta;
+  int w_static = (int)blockIdx.x * kWarpsPerCta + warp - total_warps;
   for (;;) {
     int w = 0;
-    if (lane == 0) w = atomicAdd(work_count + 1, 1);
-    w = __shfl_sync(0xffffffffu, w, 0);
+    if (dynamic) {
+      if (lane == 0) w = atomicAdd(work_count + 1, 1);
+      w = __shfl_sync(0xffffffffu, w, 0);
+    } else {
+      w = (w_static += total_warps);
+    }
     if (w >= n_work) break;
     const size_t fh = work[w];  // frame * h_cap + hypothesis
     const size_t f = fh / h_cap;
@@ -66,7 +72,7 @@ static cudaError_t launch_tri_impl(LaunchCfg& cfg, const Tables& tb, LaunchDims 
   const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((units + W - 1) / W, (size_t)cfg.n_sm * per_sm));
   if (sizeof(T) != 4 || far_scratch_bytes < (size_t)grid * W * triangulate_far_scratch_bytes_per_warp()) far_scratch = nullptr;
   k_triangulate<T, W><<<grid, 32 * W, smem, st>>>(tb, d.p_max, d.h_cap, ws_bytes, persons, hyp_det, work, work_count, tmp,
-                                                  keep, far_scratch);
+                                                  keep, far_scratch, cfg.tri_dynamic);
   return cudaGetLastError();
 }
 

@@ -21,6 +21,8 @@ struct LaunchCfg {
   int reproj_scap = 6;
   int reproj_threads = 128;
   int tri_warps = 2, tri_warps_f64 = 4;
+  int rounds_warps = 4;        // frames (warps) per CTA of the camera-rounds kernel
+  int tri_dynamic = 1;         // K3 hands work items out one by one (0: fixed strides)
   struct OccEntry { const void* fn; size_t smem; int per_sm; };
   OccEntry occ[8] = {};
   int n_occ = 0;
@@ -28,13 +30,15 @@ struct LaunchCfg {
 cudaError_t init_kernels(LaunchCfg* cfg, int device);
 cudaError_t init_prior_kernels(int device);
 
-// K2: one CTA per frame. nk_scratch != nullptr selects the global-memory keypoint path.
-cudaError_t launch_associate(const LaunchCfg& cfg, const Tables& tb, LaunchDims d, const ses3d_person2d* persons, const int32_t* n_persons,
-                             float* nk_scratch, double* pair_table, int8_t* hyp_det, int32_t* n_hyp, int32_t* n_hung,
-                             int32_t* overflow, int32_t* hyp_of_dump, int32_t* keep, uint32_t* work,
-                             int32_t* work_count, cudaStream_t st);
+// K2 = K2a (pair table, one CTA per frame) + K2b (camera rounds, one warp per frame). nk_scratch != nullptr selects
+// the global-memory keypoint path; meta = n_frames x associate_meta_bytes() hand-over scratch.
+cudaError_t launch_associate(const LaunchCfg& cfg, const Tables& tb, LaunchDims d, const ses3d_person2d* persons,
+                             const int32_t* n_persons, float* nk_scratch, double* pair_table, unsigned char* meta,
+                             int8_t* hyp_det, int32_t* n_hyp, int32_t* n_hung, int32_t* overflow, int32_t* hyp_of_dump,
+                             int32_t* keep, uint32_t* work, int32_t* work_count, cudaStream_t st);
 size_t associate_smem_bytes(int n_cams, int p_max, int h_cap, bool* needs_scratch);
 size_t associate_pair_table_bytes(int n_cams, int p_max);   // per frame
+size_t associate_meta_bytes(int n_cams, int p_max);         // per frame
 
 // K3: one warp per (frame, hypothesis) work item, persistent grid over the work list K2 wrote; work_count[0] = number
 // of items, work_count[1] = next unclaimed item (both zeroed by launch_associate). far_scratch: global workspace of
@@ -47,6 +51,11 @@ size_t triangulate_far_scratch_bytes(const LaunchCfg& cfg);
 // K4: one CTA per frame
 cudaError_t launch_finalize(const Tables& tb, LaunchDims d, const int32_t* n_hyp, ses3d_person_cov* tmp,
                             const int32_t* keep, ses3d_person_cov* out, int32_t* n_out, cudaStream_t st);
+
+// K4 + K6 fused for the process calls: one CTA per frame
+cudaError_t launch_finproj(const LaunchCfg& cfg, const Tables& tb, LaunchDims d, const int32_t* n_hyp,
+                           ses3d_person_cov* tmp, const int32_t* keep, ses3d_person_cov* out3d, int32_t* n_out3d,
+                           ses3d_person2d* out2d, int32_t* n_out2d, cudaStream_t st);
 
 // K6: one CTA per frame
 cudaError_t launch_reproject(const LaunchCfg& cfg, const Tables& tb, int n_frames, int h_max, const ses3d_person_cov* persons3d,

@@ -624,7 +624,7 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
   // far points and high-residual joints (FP32 mode): exact re-solve of the final view set, see exact_weighted_resolve.
   // jflag (the leave-one-out marks are spent) now marks the far joints: their covariance is solved exactly as well.
   tm.pfor(NKP, [&](int k) { ws.jflag[k] = 0; });
-  if (sizeof(T) == 4) {
+  if (sizeof(T) == 4 && (tb.exact_mode & 1)) {
     const int cap_n = (int)((size_t)Y_CHUNK * 3 - 16) / 8;
     // Most far joints belong to garbage hypotheses and never reach the output: when the skeleton's root (MidHip, else
     // the mean of both hips, S3D:924-935) lies inside the far-point radius, a joint more than 3 m beyond that radius
@@ -661,7 +661,7 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
       // residual scales the published score (S3D:840-844) - solved exactly, both match the oracle to the last bit.
       if (!far && !(ws.jerr[k] > max_reproj)) continue;
       exact_weighted_resolve(tm, tb, ws, k, ws.vlist + k * C, n);
-      if (far && n <= FAR_COV_MAX_VIEWS && ws.far_scratch) tm.single([&] { ws.jflag[k] = 2; });
+      if (far && n <= FAR_COV_MAX_VIEWS && ws.far_scratch && (tb.exact_mode & 2)) tm.single([&] { ws.jflag[k] = 2; });
     }
   }
 

@@ -42,6 +42,7 @@ void* hostsim_create(int32_t n_cams, const ses3d_camera* cams, const ses3d_param
   s->tb.f_row = s->host.f_row.data();
   s->tb.model = s->host.model;
   s->tb.prm = *prm;
+  s->tb.exact_mode = 3;
   return s;
 }
 void hostsim_destroy(void* h) { delete static_cast<Sim*>(h); }
@@ -59,7 +60,8 @@ int hostsim_triangulate_batch(void* h, int32_t n_frames, int32_t p_max, const se
   const Tables& tb = s->tb;
   const int C = tb.n_cams;
   const bool big = g_big_rig_path;   // keypoints in "global scratch"
-  std::vector<unsigned char> wsa(assoc_ws_bytes(C, p_max, h_max, !big) + 64), wsf(fin_ws_bytes(h_max) + 64);
+  std::vector<unsigned char> wsa(pair_ws_bytes(C, p_max, !big) + 64), wsr(round_ws_bytes(C, p_max, h_max) + 64),
+      wsf(fin_ws_bytes(h_max) + 64), meta_buf(frame_meta_bytes(C, p_max) + 64);
   std::vector<float> nk_scratch(big ? (size_t)C * p_max * NKP * 2 : 0);
   const bool f64 = tb.prm.precision == SES3D_PRECISION_FP64;
   std::vector<unsigned char> wst((f64 ? tri_ws_bytes<double>(C) : tri_ws_bytes<float>(C)) + 64);
@@ -72,13 +74,22 @@ int hostsim_triangulate_batch(void* h, int32_t n_frames, int32_t p_max, const se
   SerialTeam tm;
   for (int f = 0; f < n_frames; ++f) {
     const ses3d_person2d* pf = persons + (size_t)f * C * p_max;
+    // K2a: pair table + compact detection list; K2b: camera rounds (the two kernels of the association)
     Arena a1(wsa.data());
+    AssocWs pws;
+    pair_ws_layout(a1, C, p_max, !big, &pws);
+    if (big) pws.nk = nk_scratch.data();
+    pws.E = pair_table.data();
+    const FrameMeta meta = frame_meta_at(meta_buf.data(), C, p_max);
+    pairs_frame(tm, tb, p_max, pf, n_persons + (size_t)f * C, pws, meta);
+    Arena a1b(wsr.data());
     AssocWs aws;
-    assoc_ws_layout(a1, C, p_max, h_max, !big, &aws);
-    if (big) aws.nk = nk_scratch.data();
+    round_ws_layout(a1b, C, p_max, h_max, &aws);
+    aws.voff = meta.voff; aws.vslot = meta.vslot; aws.pscore = meta.pscore;
     aws.E = pair_table.data();
     int32_t n_hyp = 0, n_hung = 0;
-    associate_frame(tm, tb, p_max, h_max, pf, n_persons + (size_t)f * C, aws, hyp_det.data(), &n_hyp, &n_hung, &overflow);
+    rounds_frame(tm, tb, p_max, h_max, n_persons + (size_t)f * C, *meta.n_valid, aws, hyp_det.data(), &n_hyp, &n_hung,
+                 &overflow);
     if (n_hyp_out) n_hyp_out[f] = n_hyp;
     if (n_hung_out) n_hung_out[f] = n_hung;
     if (hyp_of) {

@@ -54,7 +54,29 @@ def _stale(out: Path, deps):
     return any(d.stat().st_mtime > t for d in deps if d.exists())
 
 
+SYNTH_LIB = PKG / "libses3d_synth.so"
+
+
+def build_synth(force=False, verbose=False):
+    """The host-side synthetic frame generator as its own small library (g++, no CUDA): test / bench input source.
+    Kept apart from libses3d.so so that a process which only needs inputs (e.g. bench.py --impl reference, which
+    times the CPU oracle) never maps the product library."""
+    deps = [CSRC / "synth.cpp", CSRC / "synth.h", INCLUDE / "ses3d.h", Path(__file__)]
+    if not force and not _stale(SYNTH_LIB, deps):
+        return SYNTH_LIB
+    cxx = shutil.which("g++") or shutil.which("c++")
+    if not cxx:
+        raise RuntimeError("g++ not found: the synthetic generator library cannot be built")
+    cmd = [cxx, "-O3", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", f"-I{INCLUDE}",
+           f"-I{CSRC}", "-o", str(SYNTH_LIB), str(CSRC / "synth.cpp"), "-lpthread"]
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.run(cmd, check=True)
+    return SYNTH_LIB
+
+
 def build(force=False, verbose=False, ptxas_info=False):
+    build_synth(force, verbose)
     headers = list(CSRC.glob("*.h")) + list(INCLUDE.glob("*.h")) + [Path(__file__)]
     sources = [CSRC / name for name, _ in UNITS if (CSRC / name).exists()]
     if not force and not ptxas_info and not _stale(LIB, sources + headers):

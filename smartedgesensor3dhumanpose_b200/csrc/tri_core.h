@@ -626,27 +626,52 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
   tm.pfor(NKP, [&](int k) { ws.jflag[k] = 0; });
   if (sizeof(T) == 4 && (tb.exact_mode & 1)) {
     const int cap_n = (int)((size_t)Y_CHUNK * 3 - 16) / 8;
-    // Most far joints belong to garbage hypotheses and never reach the output: when the skeleton's root (MidHip, else
-    // the mean of both hips, S3D:924-935) lies inside the far-point radius, a joint more than 3 m beyond that radius
-    // is certainly further than max_joint_dist_to_root from it and is reset (S3D:937-953) whatever its last digits
-    // are - no exact solve needed. (Its approximate position still feeds a child's limb-length inflation; at these
-    // distances that term changes by parts in 1e5.)
-    bool root_near = false;
-    if (tb.prm.max_joint_dist_to_root <= 2.5) {
-      auto near = [&](int slot) {
+    // Most far joints belong to garbage hypotheses (two detections of different people matched) and never reach the
+    // output. Exactness is only owed to what is published, so two conservative filters run on the approximate
+    // positions first (evaluated identically by every thread):
+    //  (a) the hypothesis is certainly dropped by the plausibility count (S3D:923-968): even when every joint whose
+    //      root distance is not clearly beyond the limit is counted as kept, num_valid <= min_num_valid_keypoints.
+    //      "Clearly" = by more than a margin that bounds the difference between the approximate and the exact position
+    //      (1e-4 relative to the distances involved - an order above anything measured - plus 1 mm);
+    //  (b) the root lies inside the far-point radius and the joint more than 3 m beyond it: the joint is reset by the
+    //      root-distance rule (S3D:937-953) whatever its last digits are.
+    // LM refinement moves the points after this step, so the filters are off when it is enabled.
+    bool root_near = false, dropped = false;
+    if (!tb.prm.lm_refine) {
+      auto joint_of = [&](int slot) {
         for (int k = 0; k < NKP; ++k)
-          if (tb.model.fusion_idx[k] == slot) {
-            const T x = ws.jX[k * 3], y = ws.jX[k * 3 + 1], z = ws.jX[k * 3 + 2];
-            return ws.jn[k] >= 2 && x * x + y * y + z * z <= T(FAR_POINT_R2);
-          }
-        return false;
+          if (tb.model.fusion_idx[k] == slot) return ws.jn[k] >= 2 ? k : -1;
+        return -1;
       };
-      auto present = [&](int slot) {
-        for (int k = 0; k < NKP; ++k)
-          if (tb.model.fusion_idx[k] == slot) return ws.jn[k] >= 2;
-        return false;
-      };
-      root_near = present(SES3D_FBP_MIDHIP) ? near(SES3D_FBP_MIDHIP) : (near(SES3D_FBP_LHIP) && near(SES3D_FBP_RHIP));
+      int T_cnt = 0;
+      for (int k = 0; k < NKP; ++k) T_cnt += ws.jn[k] >= 2 ? 1 : 0;
+      const int k_mid = joint_of(SES3D_FBP_MIDHIP), k_lh = joint_of(SES3D_FBP_LHIP), k_rh = joint_of(SES3D_FBP_RHIP);
+      bool have_root = false;
+      double rx = 0, ry = 0, rz = 0;
+      if (k_mid >= 0) {
+        have_root = true;
+        rx = ws.jX[k_mid * 3]; ry = ws.jX[k_mid * 3 + 1]; rz = ws.jX[k_mid * 3 + 2];
+      } else if (k_lh >= 0 && k_rh >= 0) {
+        have_root = true;
+        rx = 0.5 * ((double)ws.jX[k_lh * 3] + (double)ws.jX[k_rh * 3]);
+        ry = 0.5 * ((double)ws.jX[k_lh * 3 + 1] + (double)ws.jX[k_rh * 3 + 1]);
+        rz = 0.5 * ((double)ws.jX[k_lh * 3 + 2] + (double)ws.jX[k_rh * 3 + 2]);
+      }
+      if (!have_root) {
+        dropped = T_cnt <= tb.prm.min_num_valid_keypoints;   // num_valid = T when the root loop is skipped
+      } else {
+        const double rn = sqrt(rx * rx + ry * ry + rz * rz);
+        int f_certain = 0;   // joints certainly further than max_joint_dist_to_root from the root
+        for (int k = 0; k < NKP; ++k) {
+          if (ws.jn[k] < 2) continue;
+          const double x = ws.jX[k * 3], y = ws.jX[k * 3 + 1], z = ws.jX[k * 3 + 2];
+          const double d = sqrt((x - rx) * (x - rx) + (y - ry) * (y - ry) + (z - rz) * (z - rz));
+          const double margin = 1e-4 * (rn + sqrt(x * x + y * y + z * z)) + 1e-3;
+          if (d > tb.prm.max_joint_dist_to_root + margin) ++f_certain;   // NaN distances count as kept
+        }
+        dropped = 2 * T_cnt - NFUS - f_certain <= tb.prm.min_num_valid_keypoints;   // S3D:937-953, see SURVEY a10
+        root_near = rn * rn <= (double)FAR_POINT_R2 && tb.prm.max_joint_dist_to_root <= 2.5;
+      }
     }
     const T r_skip = T(23.0 * 23.0);
     for (int k = 0; k < NKP; ++k) {
@@ -654,7 +679,8 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
       if (n < 2 || n > cap_n) continue;
       const T x = ws.jX[k * 3], y = ws.jX[k * 3 + 1], z = ws.jX[k * 3 + 2];
       const T r2 = x * x + y * y + z * z;
-      if (root_near && r2 > r_skip && r2 < T(1e30)) continue;   // will be reset by the root-distance rule
+      if (dropped) continue;                                     // (a) nothing of this hypothesis is published
+      if (root_near && r2 > r_skip && r2 < T(1e30)) continue;   // (b) will be reset by the root-distance rule
       const bool far = r2 > T(FAR_POINT_R2);
       // second trigger: a residual above the acceptance threshold (gross outlier left in the view set). The large
       // smallest singular value narrows the gap to the next one, which amplifies rounding the same way, and the

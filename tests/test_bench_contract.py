@@ -23,6 +23,10 @@ def test_reference_arm_prints_one_contract_line():
     assert d["impl"] == "reference" and d["metric"] == "joints_triangulated_per_sec" and d["value"] > 0
     assert d["config"]["workload"] == "cfg5_ring8x4" and d["vs_baseline"] is None
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    # the node itself cannot be built here: the arm is a port whose Munkres solver is the reference's verbatim file
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["label"] in ("port+reference-hungarian", "port")
+    # the reference arm must not map the product library: its inputs come from libses3d_synth.so
+    assert "frames_per_step_per_gpu" in d["config"] and "p_max" in d["config"] and "h_max" in d["config"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     # ranks other than 0 exit quietly
     r1 = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference"], capture_output=True, text=True,

@@ -184,9 +184,10 @@ int ses3d_process_batch(ses3d_handle h, int32_t n_frames, int32_t p_max,
  *   out2d          dense reprojected Person2D records, frame- then camera-major, n_out2d [n_frames][n_cams],
  *                  capacity cap2d records
  * Offsets are the exclusive prefix sums of the count arrays; totals are returned. Synchronous.
- * When out3d / out2d are device memory or pinned (page-locked) host memory the results are written straight into
- * them by the pack kernels - for pinned memory as posted writes over PCIe, no staging copy and no host round trip
- * between the internal chunks; pageable host outputs are staged on the device and copied. */
+ * Device outputs are written straight to their final position by the pack kernels (running offsets stay on the
+ * device, no host round trip between the internal chunks). Host outputs are packed on the device and leave through
+ * the copy engine, chunk by chunk, overlapped with the upload and the kernels of the neighbouring chunks
+ * (SES3D_RAGGED_DIRECT=1 makes the pack kernels write into pinned host memory themselves - measured slower). */
 int ses3d_process_batch_ragged(ses3d_handle h, int32_t n_frames, int32_t p_max,
                                const ses3d_person2d* persons_dense, const int32_t* n_persons,
                                int32_t h_max, ses3d_person_cov* out3d, int64_t cap3d, int32_t* n_out3d,

@@ -106,7 +106,10 @@ struct ses3d_handle_s {
   int device_split = 2;              // sub-batches of a device-buffer call that run on concurrent streams
   ses3d::LaunchCfg cfg;              // SM count + tuning overrides, fixed at create
   int ragged_chunk_env = 0;          // SES3D_RAGGED_CHUNK
-  int ragged_direct = 1;             // SES3D_RAGGED_DIRECT=0: always stage dense results on the device first
+  // SES3D_RAGGED_DIRECT: -1 (default) = pack kernels write straight into the caller's buffers only when those are in
+  // device memory; 1 = also into pinned host memory (posted PCIe writes from the SMs: measured 17.0 ms against 10.6 ms
+  // for the copy-engine path per 16 384 frames of hall16 x 6, profiles/r02_e2e_timeline.json); 0 = always stage
+  int ragged_direct = -1;
   // ragged calls: running output totals {3-D records, 2-D records} live on the device and are carried from chunk to
   // chunk by the scan kernels; scan_ev orders the scans of consecutive chunks across the slot streams
   DevBuf d_run;
@@ -453,12 +456,12 @@ bool device_accessible(const void* p, void** dev_ptr) {
 
 // Ragged variant of process_batch (host or device buffers): dense records in, dense records out.
 //
-// Direct mode (outputs in device memory or in pinned host memory, i.e. whenever a kernel can address them): the
-// running output offsets stay on the device - every chunk's scan kernels start from the totals the previous chunk
-// left in d_run (ordered by one event per chunk) - and the pack kernels write the occupied records straight to their
-// final position in the caller's buffers, for pinned host memory as posted writes over PCIe. No staging copy, no
-// host round trip between chunks; the host synchronises once at the end. Staged mode (pageable host outputs): the
-// dense results are packed on the device and copied out once the host knows the chunk totals.
+// Direct mode (outputs in device memory; opt-in for pinned host memory): the running output offsets stay on the
+// device - every chunk's scan kernels start from the totals the previous chunk left in d_run (ordered by one event per
+// chunk) - and the pack kernels write the occupied records straight to their final position in the caller's buffers.
+// No staging copy, no host round trip between chunks; the host synchronises once at the end. Staged mode (host
+// outputs, the default): the dense results are packed on the device and leave through the copy engine once the host
+// knows the chunk totals - SM-issued posted writes to pinned memory reach only ~60 % of the copy engine's PCIe rate.
 int run_ragged_impl(ses3d_handle_s* h, int n_frames, int p_max, const ses3d_person2d* persons_dense,
                     const int32_t* n_persons, int h_max, ses3d_person_cov* out3d, long long cap3d, int32_t* n_out3d,
                     ses3d_person2d* out2d, long long cap2d, int32_t* n_out2d, long long* total3d, long long* total2d,
@@ -505,7 +508,7 @@ int run_ragged_impl(ses3d_handle_s* h, int n_frames, int p_max, const ses3d_pers
     counts = counts_host.data();
   }
   void *d3 = out3d, *d2 = out2d;
-  bool direct = h->ragged_direct != 0;
+  bool direct = dev ? h->ragged_direct != 0 : h->ragged_direct > 0;
   if (direct && !dev) direct = device_accessible(out3d, &d3) && device_accessible(out2d, &d2);
   // B200, 16384 frames of hall16 x 6 (ms per call): chunk 1024 -> 10.2, 1536 -> 10.3, 2048 -> 10.4, 3072 -> 10.8
   int chunk = std::max(1, std::min(4096, std::max(512, (n_frames + 15) / 16)));

@@ -277,15 +277,10 @@ SES_HD void exact_row(const float* P, int half, float m, float conf, bool weight
     for (int c = 0; c < 4; ++c) row[c] = xmul(row[c], conf);
 }
 
-template <class Team>
-SES_HD void exact_weighted_resolve(Team& tm, const Tables& tb, const TriWs<float>& ws, int k, const uint8_t* list, int n) {
-  float X[3];
-  exact_dlt(tm, ws.Y, 2 * n, [&](int r, float* row) {
-    const int o = list[r >> 1], half = r & 1;
-    const ViewKp<float>& v = ws.vw[o * NKP + k];
-    exact_row(tb.camf[ws.obs_cam[o]].P, half, half ? v.y : v.x, v.conf, true, row);
-  }, X);
-  double avg = 0., norm = 0.;   // calcReprojectionError, S3D:425-438
+// calcReprojectionError (S3D:425-438) in the oracle's arithmetic (no contraction, IEEE division / square root)
+SES_HD double exact_reproj_error(const Tables& tb, const TriWs<float>& ws, int k, const uint8_t* list, int n,
+                                 const float X[3]) {
+  double avg = 0., norm = 0.;
   for (int i = 0; i < n; ++i) {
     const int o = list[i];
     const ViewKp<float>& v = ws.vw[o * NKP + k];
@@ -298,20 +293,33 @@ SES_HD void exact_weighted_resolve(Team& tm, const Tables& tb, const TriWs<float
     avg += static_cast<double>(xmul(v.conf, e));
     norm += static_cast<double>(v.conf);
   }
+  return avg / norm;
+}
+
+template <class Team>
+SES_HD void exact_weighted_resolve(Team& tm, const Tables& tb, const TriWs<float>& ws, int k, const uint8_t* list, int n) {
+  float X[3];
+  exact_dlt(tm, ws.Y, 2 * n, [&](int r, float* row) {
+    const int o = list[r >> 1], half = r & 1;
+    const ViewKp<float>& v = ws.vw[o * NKP + k];
+    exact_row(tb.camf[ws.obs_cam[o]].P, half, half ? v.y : v.x, v.conf, true, row);
+  }, X);
+  const double e_avg = exact_reproj_error(tb, ws, k, list, n, X);
   tm.single([&] {
     ws.jX[k * 3] = X[0]; ws.jX[k * 3 + 1] = X[1]; ws.jX[k * 3 + 2] = X[2];
-    ws.jerr[k] = avg / norm;
+    ws.jerr[k] = e_avg;
   });
 }
 template <class Team>
 SES_HD void exact_weighted_resolve(Team&, const Tables&, const TriWs<double>&, int, const uint8_t*, int) {}
 
-// The same solve run by ONE thread on its own copy of A (B: rows x 4 followed by the 4 x 4 rotation accumulator):
-// the oracle's onesided_jacobi statement for statement. Used where many independent solves exist at once (the sigma
-// points of a far joint), one per lane.
-SES_HDN void exact_dlt_serial(float* B, int rows, float X[3]) {
-  float* W = B + 4 * rows;
-  for (int i = 0; i < 16; ++i) W[i] = (i >> 2) == (i & 3) ? 1.f : 0.f;
+// The same solve run by ONE thread on its own copy of A (rows x 4 followed by the 4 x 4 rotation accumulator): the
+// oracle's onesided_jacobi statement for statement. Used where many independent solves exist at once (the far joints
+// of a hypothesis, the sigma points of a far joint), one per lane. Element e of a lane's copy lives at B[e * ld]: the
+// lanes' copies are interleaved (ld = team size), so a warp-wide access to "element e" is one coalesced line.
+SES_HDN void exact_dlt_serial(float* B, int ld, int rows, float X[3]) {
+  float* W = B + (size_t)4 * rows * ld;
+  for (int i = 0; i < 16; ++i) W[i * ld] = (i >> 2) == (i & 3) ? 1.f : 0.f;
   const float eps = 1.1920929e-7f;
   for (int sweep = 0; sweep < 60; ++sweep) {
     bool rotated = false;
@@ -319,7 +327,7 @@ SES_HDN void exact_dlt_serial(float* B, int rows, float X[3]) {
       for (int q = p + 1; q < 4; ++q) {
         float alpha = 0.f, beta = 0.f, gamma = 0.f;
         for (int r = 0; r < rows; ++r) {
-          const float bp = B[r * 4 + p], bq = B[r * 4 + q];
+          const float bp = B[(r * 4 + p) * ld], bq = B[(r * 4 + q) * ld];
           alpha = xadd(alpha, xmul(bp, bp));
           beta = xadd(beta, xmul(bq, bq));
           gamma = xadd(gamma, xmul(bp, bq));
@@ -331,10 +339,10 @@ SES_HDN void exact_dlt_serial(float* B, int rows, float X[3]) {
         const float c = xdiv(1.f, xsqrt(xadd(1.f, xmul(t, t))));
         const float sn = xmul(c, t);
         for (int r = 0; r < rows + 4; ++r) {
-          float* row = B + r * 4;
-          const float bp = row[p], bq = row[q];
-          row[p] = xsub(xmul(c, bp), xmul(sn, bq));
-          row[q] = xadd(xmul(sn, bp), xmul(c, bq));
+          float* row = B + (size_t)r * 4 * ld;
+          const float bp = row[p * ld], bq = row[q * ld];
+          row[p * ld] = xsub(xmul(c, bp), xmul(sn, bq));
+          row[q * ld] = xadd(xmul(sn, bp), xmul(c, bq));
         }
       }
     if (!rotated) break;
@@ -343,73 +351,130 @@ SES_HDN void exact_dlt_serial(float* B, int rows, float X[3]) {
   float best_s = FLT_MAX;
   for (int c = 0; c < 4; ++c) {
     float sq = 0.f;
-    for (int r = 0; r < rows; ++r) sq = xadd(sq, xmul(B[r * 4 + c], B[r * 4 + c]));
+    for (int r = 0; r < rows; ++r) sq = xadd(sq, xmul(B[(r * 4 + c) * ld], B[(r * 4 + c) * ld]));
     if (sq < best_s) { best_s = sq; best = c; }
   }
-  const float w = W[12 + best];
-  X[0] = xdiv(W[best], w); X[1] = xdiv(W[4 + best], w); X[2] = xdiv(W[8 + best], w);
+  const float w = W[(12 + best) * ld];
+  X[0] = xdiv(W[best * ld], w); X[1] = xdiv(W[(4 + best) * ld], w); X[2] = xdiv(W[(8 + best) * ld], w);
 }
 
-// Unscented covariance of a far joint in the oracle's arithmetic (calc_covariance S3D:508-523 with draw_sigma_points
-// S3D:489-506 and mod_samples S3D:471-487). For a point hundreds of metres away the sigma points straddle the pole
-// of X = v_xyz / v_w, so anything but the same arithmetic gives an unrelated (equally meaningless) covariance.
-// The 4n + 1 solves are independent: one per lane, each on a private copy of A in the workspace `scratch`
-// ([team size][FAR_COV_MAX_VIEWS * 8 + 16] floats, global memory on the GPU); the transformed points are staged in
-// the (idle) sigma-point buffer and folded in sample order like the reference does.
 constexpr int FAR_COV_MAX_VIEWS = 16;
-constexpr int FAR_COV_STRIDE = FAR_COV_MAX_VIEWS * 8 + 16;
+constexpr int FAR_COV_STRIDE = FAR_COV_MAX_VIEWS * 8 + 16;   // floats per private solve copy
+
+// Exact weighted re-solve of every joint whose jflag has bit 0 set and that fits a private copy (n <= FAR_COV_MAX_VIEWS):
+// the solves are independent, so each lane takes one joint - a garbage hypothesis with 17 far joints costs one pass
+// instead of 17 cooperative solves. Joints with more views go through the cooperative solver (exact_weighted_resolve).
 template <class Team>
-SES_HD void exact_far_covariance(Team& tm, const Tables& tb, int p_max, const ses3d_person2d* persons,
-                                 const TriWs<float>& ws, int k, const uint8_t* list, int n, float* scratch) {
-  const float dimk = xadd((float)(2 * n), 0.5f);          // T(dim) + kappa
-  const float wden = xmul(2.f, dimk);
-  const float w0 = xdiv(xmul(2.f, 0.5f), wden), wi = xdiv(1.f, wden);
-  const float b = xsqrt(dimk);
-  const int n_samples = 4 * n + 1;   // <= 65 <= Y_CHUNK
-  tm.pfor(n_samples, [&](int s) {
-    const int vi = s > 0 ? (s - 1) >> 2 : -1, m = (s - 1) & 3;
-    float px = 0.f, py = 0.f;   // the perturbed keypoint of view vi
-    if (vi >= 0) {
-      const int o = list[vi], cam = ws.obs_cam[o];
-      const ses3d_keypoint2d& kp = persons[cam * p_max + ws.obs_det[o]].keypoints[k];
-      const CamF& cm = tb.camf[cam];
-      const ViewKp<float>& v = ws.vw[o * NKP + k];
-      const float cxx = xdiv(kp.cov[0], xmul(cm.fx, cm.fx)), cxy = xdiv(kp.cov[1], xmul(cm.fx, cm.fy)),
-                  cyy = xdiv(kp.cov[2], xmul(cm.fy, cm.fy));            // normalize_keypoints S3D:324-327
-      const float l11 = xsqrt(cxx), l21 = xdiv(cxy, l11);
-      const float l22 = xsqrt(xsub(cyy, xmul(l21, l21)));
-      const float dx1 = xmul(l11, b), dy1 = xmul(l21, b), dy2 = xmul(l22, b);
-      px = v.x; py = v.y;
-      if (m == 0) { px = xsub(v.x, dx1); py = xsub(v.y, dy1); }
-      else if (m == 1) { py = xsub(v.y, dy2); }
-      else if (m == 2) { px = xadd(v.x, dx1); py = xadd(v.y, dy1); }
-      else { py = xadd(v.y, dy2); }
-    }
-    float* B = scratch + (size_t)(s % tm.size()) * FAR_COV_STRIDE;
+SES_HD void exact_weighted_resolve_lanes(Team& tm, const Tables& tb, const TriWs<float>& ws, int C, float* scratch) {
+  const int ld = tm.size();
+  tm.pfor(NKP, [&](int k) {
+    const int n = ws.jn[k];
+    if (!(ws.jflag[k] & 1) || n > FAR_COV_MAX_VIEWS) return;
+    const uint8_t* list = ws.vlist + k * C;
+    float* B = scratch + (k % ld);
     for (int r = 0; r < 2 * n; ++r) {
-      const int i = r >> 1, o = list[i], half = r & 1;
+      const int o = list[r >> 1], half = r & 1;
       const ViewKp<float>& v = ws.vw[o * NKP + k];
-      const float coord = i == vi ? (half ? py : px) : (half ? v.y : v.x);
-      exact_row(tb.camf[ws.obs_cam[o]].P, half, coord, 1.f, false, B + r * 4);
+      float row[4];
+      exact_row(tb.camf[ws.obs_cam[o]].P, half, half ? v.y : v.x, v.conf, true, row);
+      for (int c = 0; c < 4; ++c) B[(r * 4 + c) * ld] = row[c];
     }
-    exact_dlt_serial(B, 2 * n, ws.Y + s * 3);
-  });
-  tm.single([&] {
-    const float m0 = ws.jX[k * 3], m1 = ws.jX[k * 3 + 1], m2 = ws.jX[k * 3 + 2];
-    float c00 = 0.f, c01 = 0.f, c02 = 0.f, c11 = 0.f, c12 = 0.f, c22 = 0.f;
-    for (int s = 0; s < n_samples; ++s) {
-      const float w = s == 0 ? w0 : wi;
-      const float d0 = xsub(ws.Y[s * 3], m0), d1 = xsub(ws.Y[s * 3 + 1], m1), d2 = xsub(ws.Y[s * 3 + 2], m2);
-      c00 = xadd(c00, xmul(xmul(d0, w), d0)); c01 = xadd(c01, xmul(xmul(d0, w), d1)); c02 = xadd(c02, xmul(xmul(d0, w), d2));
-      c11 = xadd(c11, xmul(xmul(d1, w), d1)); c12 = xadd(c12, xmul(xmul(d1, w), d2)); c22 = xadd(c22, xmul(xmul(d2, w), d2));
-    }
-    float* cv = ws.cov + k * 6;
-    cv[0] = c00; cv[1] = c01; cv[2] = c02; cv[3] = c11; cv[4] = c12; cv[5] = c22;
+    float X[3];
+    exact_dlt_serial(B, ld, 2 * n, X);
+    ws.jX[k * 3] = X[0]; ws.jX[k * 3 + 1] = X[1]; ws.jX[k * 3 + 2] = X[2];
+    ws.jerr[k] = exact_reproj_error(tb, ws, k, list, n, X);
   });
 }
 template <class Team>
-SES_HD void exact_far_covariance(Team&, const Tables&, int, const ses3d_person2d*, const TriWs<double>&, int,
-                                 const uint8_t*, int, float*) {}
+SES_HD void exact_weighted_resolve_lanes(Team&, const Tables&, const TriWs<double>&, int, float*) {}
+
+// Unscented covariance of the far joints (jflag bit 1) in the oracle's arithmetic (calc_covariance S3D:508-523 with
+// draw_sigma_points S3D:489-506 and mod_samples S3D:471-487). For a point hundreds of metres away the sigma points
+// straddle the pole of X = v_xyz / v_w, so anything but the same arithmetic gives an unrelated (equally meaningless)
+// covariance. The 4n + 1 solves of ALL far joints of the hypothesis form one index space: one solve per lane on a
+// private copy of A in `scratch` ([FAR_COV_STRIDE][team size] floats, global memory on the GPU), Y_CHUNK solves per
+// pass; the transformed points are staged in the (idle) sigma-point buffer and folded per joint in sample order like
+// the reference does.
+template <class Team>
+SES_HD void exact_far_covariances(Team& tm, const Tables& tb, int p_max, const ses3d_person2d* persons,
+                                  const TriWs<float>& ws, int C, float* scratch) {
+  const int ld = tm.size();
+  for (int k0 = 0; k0 < NKP;) {
+    tm.single([&] {  // batch [k0,k1): far joints whose 4n+1 solves fit into the staging buffer; soff = staging offsets
+      int k1 = k0, used = 0;
+      while (k1 < NKP) {
+        const int need = (ws.jflag[k1] & 2) ? 4 * ws.jn[k1] + 1 : 0;
+        if (used + need > Y_CHUNK && used > 0) break;
+        ws.soff[k1] = used;
+        used += need;
+        ++k1;
+      }
+      ws.scal[2] = k1;
+      ws.scal[3] = used;
+    });
+    const int k1 = ws.scal[2], used = ws.scal[3];
+    if (used > 0) {
+      tm.pfor(used, [&](int i) {
+        int k = k0;
+        while (k < k1 - 1 && !((ws.jflag[k] & 2) && i < ws.soff[k] + 4 * ws.jn[k] + 1)) ++k;
+        const int s = i - ws.soff[k], n = ws.jn[k];
+        const uint8_t* list = ws.vlist + k * C;
+        const float dimk = xadd((float)(2 * n), 0.5f);          // T(dim) + kappa
+        const float b = xsqrt(dimk);
+        const int vi = s > 0 ? (s - 1) >> 2 : -1, m = (s - 1) & 3;
+        float px = 0.f, py = 0.f;   // the perturbed keypoint of view vi
+        if (vi >= 0) {
+          const int o = list[vi], cam = ws.obs_cam[o];
+          const ses3d_keypoint2d& kp = persons[cam * p_max + ws.obs_det[o]].keypoints[k];
+          const CamF& cm = tb.camf[cam];
+          const ViewKp<float>& v = ws.vw[o * NKP + k];
+          const float cxx = xdiv(kp.cov[0], xmul(cm.fx, cm.fx)), cxy = xdiv(kp.cov[1], xmul(cm.fx, cm.fy)),
+                      cyy = xdiv(kp.cov[2], xmul(cm.fy, cm.fy));            // normalize_keypoints S3D:324-327
+          const float l11 = xsqrt(cxx), l21 = xdiv(cxy, l11);
+          const float l22 = xsqrt(xsub(cyy, xmul(l21, l21)));
+          const float dx1 = xmul(l11, b), dy1 = xmul(l21, b), dy2 = xmul(l22, b);
+          px = v.x; py = v.y;
+          if (m == 0) { px = xsub(v.x, dx1); py = xsub(v.y, dy1); }
+          else if (m == 1) { py = xsub(v.y, dy2); }
+          else if (m == 2) { px = xadd(v.x, dx1); py = xadd(v.y, dy1); }
+          else { py = xadd(v.y, dy2); }
+        }
+        float* B = scratch + (i % ld);
+        for (int r = 0; r < 2 * n; ++r) {
+          const int vr = r >> 1, o = list[vr], half = r & 1;
+          const ViewKp<float>& v = ws.vw[o * NKP + k];
+          const float coord = vr == vi ? (half ? py : px) : (half ? v.y : v.x);
+          float row[4];
+          exact_row(tb.camf[ws.obs_cam[o]].P, half, coord, 1.f, false, row);
+          for (int c = 0; c < 4; ++c) B[(r * 4 + c) * ld] = row[c];
+        }
+        exact_dlt_serial(B, ld, 2 * n, ws.Y + i * 3);
+      });
+      tm.pfor(k1 - k0, [&](int kk) {
+        const int k = k0 + kk;
+        if (!(ws.jflag[k] & 2)) return;
+        const int n = ws.jn[k], n_samples = 4 * n + 1;
+        const float dimk = xadd((float)(2 * n), 0.5f);
+        const float wden = xmul(2.f, dimk);
+        const float w0 = xdiv(xmul(2.f, 0.5f), wden), wi = xdiv(1.f, wden);
+        const float* Yk = ws.Y + ws.soff[k] * 3;
+        const float m0 = ws.jX[k * 3], m1 = ws.jX[k * 3 + 1], m2 = ws.jX[k * 3 + 2];
+        float c00 = 0.f, c01 = 0.f, c02 = 0.f, c11 = 0.f, c12 = 0.f, c22 = 0.f;
+        for (int s = 0; s < n_samples; ++s) {
+          const float w = s == 0 ? w0 : wi;
+          const float d0 = xsub(Yk[s * 3], m0), d1 = xsub(Yk[s * 3 + 1], m1), d2 = xsub(Yk[s * 3 + 2], m2);
+          c00 = xadd(c00, xmul(xmul(d0, w), d0)); c01 = xadd(c01, xmul(xmul(d0, w), d1)); c02 = xadd(c02, xmul(xmul(d0, w), d2));
+          c11 = xadd(c11, xmul(xmul(d1, w), d1)); c12 = xadd(c12, xmul(xmul(d1, w), d2)); c22 = xadd(c22, xmul(xmul(d2, w), d2));
+        }
+        float* cv = ws.cov + k * 6;
+        cv[0] = c00; cv[1] = c01; cv[2] = c02; cv[3] = c11; cv[4] = c12; cv[5] = c22;
+      });
+    }
+    k0 = k1;
+  }
+}
+template <class Team>
+SES_HD void exact_far_covariances(Team&, const Tables&, int, const ses3d_person2d*, const TriWs<double>&, int, float*) {}
 
 // LM refinement of sum conf^2 * ||hnorm(P X~) - x||^2 (self-specified, not in the reference)
 template <class T>
@@ -622,13 +687,27 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
   }
 
   // far points and high-residual joints (FP32 mode): exact re-solve of the final view set, see exact_weighted_resolve.
-  // jflag (the leave-one-out marks are spent) now marks the far joints: their covariance is solved exactly as well.
-  tm.pfor(NKP, [&](int k) { ws.jflag[k] = 0; });
-  if (sizeof(T) == 4 && (tb.exact_mode & 1)) {
-    const int cap_n = (int)((size_t)Y_CHUNK * 3 - 16) / 8;
+  // jflag (the leave-one-out marks are spent) now holds bit 0 = re-solve exactly, bit 1 = far joint (its covariance is
+  // solved exactly as well). Triggers: the approximate position lies beyond the far-point radius, or the residual is
+  // above the acceptance threshold (a gross outlier left in the view set: the large smallest singular value narrows
+  // the gap to the next one, which amplifies rounding the same way, and the residual scales the published score,
+  // S3D:840-844 - solved exactly, both match the oracle to the last bit).
+  const bool exact_on = sizeof(T) == 4 && (tb.exact_mode & 1);
+  const int cap_n = (int)((size_t)Y_CHUNK * 3 - 16) / 8;   // views the cooperative solver can stage
+  tm.pfor(NKP, [&](int k) {
+    int fl = 0;
+    const int n = ws.jn[k];
+    if (exact_on && n >= 2 && n <= cap_n) {
+      const T x = ws.jX[k * 3], y = ws.jX[k * 3 + 1], z = ws.jX[k * 3 + 2];
+      const bool far = x * x + y * y + z * z > T(FAR_POINT_R2);
+      if (far || ws.jerr[k] > max_reproj) fl = far ? 3 : 1;
+    }
+    ws.jflag[k] = fl;
+  });
+  if (exact_on && tm.first(NKP, [&](int k) { return ws.jflag[k] != 0; }) < NKP) {
     // Most far joints belong to garbage hypotheses (two detections of different people matched) and never reach the
     // output. Exactness is only owed to what is published, so two conservative filters run on the approximate
-    // positions first (evaluated identically by every thread):
+    // positions first:
     //  (a) the hypothesis is certainly dropped by the plausibility count (S3D:923-968): even when every joint whose
     //      root distance is not clearly beyond the limit is counted as kept, num_valid <= min_num_valid_keypoints.
     //      "Clearly" = by more than a margin that bounds the difference between the approximate and the exact position
@@ -636,59 +715,61 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
     //  (b) the root lies inside the far-point radius and the joint more than 3 m beyond it: the joint is reset by the
     //      root-distance rule (S3D:937-953) whatever its last digits are.
     // LM refinement moves the points after this step, so the filters are off when it is enabled.
-    bool root_near = false, dropped = false;
-    if (!tb.prm.lm_refine) {
-      auto joint_of = [&](int slot) {
-        for (int k = 0; k < NKP; ++k)
-          if (tb.model.fusion_idx[k] == slot) return ws.jn[k] >= 2 ? k : -1;
-        return -1;
-      };
-      int T_cnt = 0;
-      for (int k = 0; k < NKP; ++k) T_cnt += ws.jn[k] >= 2 ? 1 : 0;
-      const int k_mid = joint_of(SES3D_FBP_MIDHIP), k_lh = joint_of(SES3D_FBP_LHIP), k_rh = joint_of(SES3D_FBP_RHIP);
-      bool have_root = false;
-      double rx = 0, ry = 0, rz = 0;
-      if (k_mid >= 0) {
-        have_root = true;
-        rx = ws.jX[k_mid * 3]; ry = ws.jX[k_mid * 3 + 1]; rz = ws.jX[k_mid * 3 + 2];
-      } else if (k_lh >= 0 && k_rh >= 0) {
-        have_root = true;
-        rx = 0.5 * ((double)ws.jX[k_lh * 3] + (double)ws.jX[k_rh * 3]);
-        ry = 0.5 * ((double)ws.jX[k_lh * 3 + 1] + (double)ws.jX[k_rh * 3 + 1]);
-        rz = 0.5 * ((double)ws.jX[k_lh * 3 + 2] + (double)ws.jX[k_rh * 3 + 2]);
-      }
-      if (!have_root) {
-        dropped = T_cnt <= tb.prm.min_num_valid_keypoints;   // num_valid = T when the root loop is skipped
-      } else {
-        const double rn = sqrt(rx * rx + ry * ry + rz * rz);
-        int f_certain = 0;   // joints certainly further than max_joint_dist_to_root from the root
-        for (int k = 0; k < NKP; ++k) {
-          if (ws.jn[k] < 2) continue;
-          const double x = ws.jX[k * 3], y = ws.jX[k * 3 + 1], z = ws.jX[k * 3 + 2];
-          const double d = sqrt((x - rx) * (x - rx) + (y - ry) * (y - ry) + (z - rz) * (z - rz));
-          const double margin = 1e-4 * (rn + sqrt(x * x + y * y + z * z)) + 1e-3;
-          if (d > tb.prm.max_joint_dist_to_root + margin) ++f_certain;   // NaN distances count as kept
+    tm.single([&] {
+      bool root_near = false, dropped = false;
+      if (!tb.prm.lm_refine) {
+        auto joint_of = [&](int slot) {
+          for (int k = 0; k < NKP; ++k)
+            if (tb.model.fusion_idx[k] == slot) return ws.jn[k] >= 2 ? k : -1;
+          return -1;
+        };
+        int T_cnt = 0;
+        for (int k = 0; k < NKP; ++k) T_cnt += ws.jn[k] >= 2 ? 1 : 0;
+        const int k_mid = joint_of(SES3D_FBP_MIDHIP), k_lh = joint_of(SES3D_FBP_LHIP), k_rh = joint_of(SES3D_FBP_RHIP);
+        bool have_root = false;
+        double rx = 0, ry = 0, rz = 0;
+        if (k_mid >= 0) {
+          have_root = true;
+          rx = ws.jX[k_mid * 3]; ry = ws.jX[k_mid * 3 + 1]; rz = ws.jX[k_mid * 3 + 2];
+        } else if (k_lh >= 0 && k_rh >= 0) {
+          have_root = true;
+          rx = 0.5 * ((double)ws.jX[k_lh * 3] + (double)ws.jX[k_rh * 3]);
+          ry = 0.5 * ((double)ws.jX[k_lh * 3 + 1] + (double)ws.jX[k_rh * 3 + 1]);
+          rz = 0.5 * ((double)ws.jX[k_lh * 3 + 2] + (double)ws.jX[k_rh * 3 + 2]);
         }
-        dropped = 2 * T_cnt - NFUS - f_certain <= tb.prm.min_num_valid_keypoints;   // S3D:937-953, see SURVEY a10
-        root_near = rn * rn <= (double)FAR_POINT_R2 && tb.prm.max_joint_dist_to_root <= 2.5;
+        if (!have_root) {
+          dropped = T_cnt <= tb.prm.min_num_valid_keypoints;   // num_valid = T when the root loop is skipped
+        } else {
+          const double rn = sqrt(rx * rx + ry * ry + rz * rz);
+          int f_certain = 0;   // joints certainly further than max_joint_dist_to_root from the root
+          for (int k = 0; k < NKP; ++k) {
+            if (ws.jn[k] < 2) continue;
+            const double x = ws.jX[k * 3], y = ws.jX[k * 3 + 1], z = ws.jX[k * 3 + 2];
+            const double d = sqrt((x - rx) * (x - rx) + (y - ry) * (y - ry) + (z - rz) * (z - rz));
+            const double margin = 1e-4 * (rn + sqrt(x * x + y * y + z * z)) + 1e-3;
+            if (d > tb.prm.max_joint_dist_to_root + margin) ++f_certain;   // NaN distances count as kept
+          }
+          dropped = 2 * T_cnt - NFUS - f_certain <= tb.prm.min_num_valid_keypoints;   // S3D:937-953, see SURVEY a10
+          root_near = rn * rn <= (double)FAR_POINT_R2 && tb.prm.max_joint_dist_to_root <= 2.5;
+        }
       }
-    }
-    const T r_skip = T(23.0 * 23.0);
-    for (int k = 0; k < NKP; ++k) {
-      const int n = ws.jn[k];
-      if (n < 2 || n > cap_n) continue;
-      const T x = ws.jX[k * 3], y = ws.jX[k * 3 + 1], z = ws.jX[k * 3 + 2];
-      const T r2 = x * x + y * y + z * z;
-      if (dropped) continue;                                     // (a) nothing of this hypothesis is published
-      if (root_near && r2 > r_skip && r2 < T(1e30)) continue;   // (b) will be reset by the root-distance rule
-      const bool far = r2 > T(FAR_POINT_R2);
-      // second trigger: a residual above the acceptance threshold (gross outlier left in the view set). The large
-      // smallest singular value narrows the gap to the next one, which amplifies rounding the same way, and the
-      // residual scales the published score (S3D:840-844) - solved exactly, both match the oracle to the last bit.
-      if (!far && !(ws.jerr[k] > max_reproj)) continue;
-      exact_weighted_resolve(tm, tb, ws, k, ws.vlist + k * C, n);
-      if (far && n <= FAR_COV_MAX_VIEWS && ws.far_scratch && (tb.exact_mode & 2)) tm.single([&] { ws.jflag[k] = 2; });
-    }
+      const T r_skip = T(23.0 * 23.0);
+      const bool far_cov = ws.far_scratch && (tb.exact_mode & 2);
+      for (int k = 0; k < NKP; ++k) {
+        int fl = ws.jflag[k];
+        if (!fl) continue;
+        const T x = ws.jX[k * 3], y = ws.jX[k * 3 + 1], z = ws.jX[k * 3 + 2];
+        const T r2 = x * x + y * y + z * z;
+        if (dropped) fl = 0;                                           // (a) nothing of this hypothesis is published
+        else if (root_near && r2 > r_skip && r2 < T(1e30)) fl = 0;     // (b) will be reset by the root-distance rule
+        else if (!(far_cov && ws.jn[k] <= FAR_COV_MAX_VIEWS)) fl &= 1;
+        ws.jflag[k] = fl;
+      }
+    });
+    if (ws.far_scratch) exact_weighted_resolve_lanes(tm, tb, ws, C, ws.far_scratch);
+    for (int k = 0; k < NKP; ++k)   // joints the lane-parallel pass cannot hold (or no private scratch): cooperative
+      if ((ws.jflag[k] & 1) && (!ws.far_scratch || ws.jn[k] > FAR_COV_MAX_VIEWS))
+        exact_weighted_resolve(tm, tb, ws, k, ws.vlist + k * C, ws.jn[k]);
   }
 
   // optional LM, down-weight (S3D:840-844), then the unweighted base system of the final view set:
@@ -708,7 +789,7 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
     }
     if (err > max_reproj) avg_score = (float)((double)avg_score * (max_reproj / err));
     ws.jscore[k] = avg_score;
-    if (ws.jflag[k] == 2) return;   // far joint: covariance by exact_far_covariance below
+    if (ws.jflag[k] & 2) return;   // far joint: covariance by exact_far_covariances below
     double G[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = 0; i < n; ++i) {
       const int o = list[i];
@@ -752,7 +833,7 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
 
   tm.single([&] {
     int off = 0;
-    for (int k = 0; k < NKP; ++k) { ws.soff[k] = off; off += (ws.jn[k] >= 2 && ws.jflag[k] != 2) ? 4 * ws.jn[k] : 0; }
+    for (int k = 0; k < NKP; ++k) { ws.soff[k] = off; off += (ws.jn[k] >= 2 && !(ws.jflag[k] & 2)) ? 4 * ws.jn[k] : 0; }
     ws.soff[NKP] = off;
   });
   const int n_samples_total = ws.soff[NKP];
@@ -819,7 +900,7 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
     // covariance about the weighted-DLT point, samples in the reference's order (S3D:521-522)
     tm.pfor(NKP, [&](int k) {
       const int n = ws.jn[k];
-      if (n < 2 || ws.jflag[k] == 2) return;
+      if (n < 2 || (ws.jflag[k] & 2)) return;
       int a = ws.soff[k], b = ws.soff[k + 1];
       a = a > s0 ? a : s0;
       b = b < s0 + cnt ? b : s0 + cnt;
@@ -837,8 +918,8 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
     });
   }
 
-  for (int k = 0; k < NKP; ++k)
-    if (ws.jflag[k] == 2) exact_far_covariance(tm, tb, p_max, persons, ws, k, ws.vlist + k * C, ws.jn[k], ws.far_scratch);
+  if (exact_on && ws.far_scratch && tm.first(NKP, [&](int k) { return (ws.jflag[k] & 2) != 0; }) < NKP)
+    exact_far_covariances(tm, tb, p_max, persons, ws, C, ws.far_scratch);
 
   // output keypoints (S3D:849-857); the record shares storage with the sigma-point staging, which is done
   tm.pfor(NFUS, [&](int s) { zero_kp(ws.kp[s]); });

@@ -293,7 +293,8 @@ typedef struct ses3d_assembler_config {
   int64_t inter_message_lower_bound_ns;  /* 20 ms                          S3D:1220 */
   double age_penalty;                    /* 2.0                            S3D:1221 */
   int64_t max_interval_ns;               /* < 0: unlimited (ros::DURATION_MAX) */
-  double max_sync_diff_s;                /* 0.067                          S3D:64, 1051 */
+  double max_sync_diff_s;                /* 0.067                          S3D:64, 1051; < 0: synchroniser only -
+                                            no worker gating, every synchronised tuple is emitted unchanged */
 } ses3d_assembler_config;
 typedef struct ses3d_assembler_s* ses3d_assembler;
 
@@ -309,6 +310,14 @@ int ses3d_assembler_pop(ses3d_assembler a, int64_t* ids, int64_t* stamps_ns, uin
 /* stats: {frames emitted, frames skipped by the backwards-time rule (S3D:1043-1046), blanked cameras,
  * messages dropped by queue overflow, tuples signalled by the synchroniser} */
 int ses3d_assembler_stats(ses3d_assembler a, int64_t stats[5]);
+
+/* The 1-slot latest-wins mailbox between the synchroniser callback and the worker thread (S3D:999-1025), replayed
+ * deterministically: frame i reaches the slot at t_ready_ns[i] (non-decreasing) and overwrites an unread frame; the idle
+ * worker takes the slot's content and is busy for busy_ns[i]. taken[i] = 1: processed, 0: overwritten unseen;
+ * t_start_ns (nullable): when processing of frame i began (-1 if dropped). Returns the number of processed frames. Use
+ * it to thin a replayed frame list to what the live node would have processed at a given per-frame cost. */
+int ses3d_mailbox_replay(int32_t n, const int64_t* t_ready_ns, const int64_t* busy_ns, uint8_t* taken,
+                         int64_t* t_start_ns);
 
 /* ------------------------------------------------------------- wire format
  * ROS-free (de)serialisation of the ROS 1 wire encoding of person_msgs/Person2DList and PersonCovList

@@ -191,3 +191,30 @@ class RefAssembler:
         self.stats["blanked_cameras"] += sum(blank)
         self.stats["emitted"] += 1
         self.ready.append(dict(ids=[m for _, m in tup], stamps_ns=[s for s, _ in tup], blank=blank, pivot=idx))
+
+
+def mailbox_replay(t_ready, busy):
+    """The 1-slot latest-wins mailbox between skeletonCallback (S3D:999-1006: store under the mutex, notify) and the
+    worker loop (S3D:1017-1025: wait for `updated`, copy, clear) as an event simulation over the store events, written
+    independently of csrc/frame_assembler.cpp. Returns (taken flags, start times)."""
+    n = len(t_ready)
+    taken, start = [0] * n, [-1] * n
+    state = {"slot": None, "busy_until": float("-inf")}
+
+    def take(at):
+        k = state["slot"]
+        state["slot"] = None
+        taken[k], start[k] = 1, at
+        state["busy_until"] = at + max(busy[k], 0)
+
+    for i in range(n):
+        t = t_ready[i]
+        # the worker came free strictly before this store and found a frame waiting: it took it then
+        if state["slot"] is not None and state["busy_until"] < t:
+            take(state["busy_until"])
+        state["slot"] = i                      # the store; an unread frame is overwritten
+        if state["busy_until"] <= t:           # an idle worker is woken by the notify
+            take(t)
+    if state["slot"] is not None:              # what is left in the slot when the stream ends is processed last
+        take(state["busy_until"])
+    return taken, start

@@ -75,3 +75,16 @@ def pack_frames(frames, n_cams, p_max):
             persons[f, c, :len(plist)] = plist
             n_persons[f, c] = len(plist)
     return persons, n_persons
+
+
+def mailbox_replay(t_ready_ns, busy_ns):
+    """The node's 1-slot latest-wins mailbox (S3D:999-1025) replayed: which frames a worker that needs busy_ns[i] for
+    frame i processes when frame i reaches the slot at t_ready_ns[i]. Returns (taken uint8 [n], t_start_ns int64 [n])."""
+    t = np.ascontiguousarray(t_ready_ns, dtype=np.int64)
+    b = np.ascontiguousarray(busy_ns, dtype=np.int64)
+    if t.shape != b.shape or t.ndim != 1:
+        raise ValueError("t_ready_ns and busy_ns must be 1-D arrays of the same length")
+    taken = np.zeros(len(t), np.uint8)
+    start = np.full(len(t), -1, np.int64)
+    _lib.check(min(0, _lib.load().ses3d_mailbox_replay(len(t), t.ctypes.data, b.ctypes.data, taken.ctypes.data, start.ctypes.data)))
+    return taken, start

@@ -189,8 +189,8 @@ int triangulate_on_device(ses3d_handle_s* h, Scratch& sc, cudaStream_t st, int n
     CU(sc.n_hung.ensure((size_t)nf * 4));
     CU(sc.keep.ensure((size_t)nf * h_max * 4));
     CU(sc.tmp.ensure((size_t)nf * h_max * sizeof(ses3d_person_cov)));
-    CU(sc.work.ensure((size_t)nf * h_max * 4));
-    CU(sc.work_count.ensure(8));
+    CU(sc.work.ensure((size_t)nf * h_max * 4 * ses3d::kTriBuckets));
+    CU(sc.work_count.ensure(64));
     if (h->prm.precision == SES3D_PRECISION_FP32) CU(sc.far.ensure(ses3d::triangulate_far_scratch_bytes(h->cfg)));
     if (need_nk) CU(sc.nk.ensure((size_t)nf * C * p_max * ses3d::NKP * 3 * sizeof(float)));
     LaunchDims d{nf, p_max, h_max};
@@ -855,8 +855,8 @@ int ses3d_reserve(ses3d_handle h, int32_t n_frames, int32_t p_max, int32_t h_max
     CU(s.sc.n_hung.ensure((size_t)nf * 4));
     CU(s.sc.keep.ensure((size_t)nf * h_max * 4));
     CU(s.sc.tmp.ensure((size_t)nf * h_max * sizeof(ses3d_person_cov)));
-    CU(s.sc.work.ensure((size_t)nf * h_max * 4));
-    CU(s.sc.work_count.ensure(8));
+    CU(s.sc.work.ensure((size_t)nf * h_max * 4 * ses3d::kTriBuckets));
+    CU(s.sc.work_count.ensure(64));
     if (h->prm.precision == SES3D_PRECISION_FP32) CU(s.sc.far.ensure(ses3d::triangulate_far_scratch_bytes(h->cfg)));
     if (need_nk) CU(s.sc.nk.ensure((size_t)nf * C * p_max * ses3d::NKP * 3 * sizeof(float)));
   }

@@ -212,6 +212,17 @@ struct ses3d_assembler_s {
   // ---- worker gating, S3D:1029-1057
   void signal(const std::vector<Msg>& tuple) {
     ++n_signalled;
+    if (cfg.max_sync_diff_s < 0.0) {   // synchroniser only: every tuple is handed on as it is (the node gates itself)
+      Frame f;
+      f.msgs = tuple;
+      f.blank.assign(n, 0);
+      f.pivot = 0;
+      for (uint32_t i = 1; i < n; ++i)
+        if (tuple[i].stamp > tuple[f.pivot].stamp) f.pivot = (int)i;
+      ready.push_back(f);
+      ++n_emitted;
+      return;
+    }
     double t_max = 0.0;
     int t_max_idx = -1;
     for (uint32_t i = 0; i < n; ++i) {
@@ -294,6 +305,36 @@ int ses3d_assembler_pop(ses3d_assembler a, int64_t* ids, int64_t* stamps_ns, uin
   if (pivot) *pivot = f.pivot;
   a->ready.pop_front();
   return 1;
+}
+
+// The 1-slot latest-wins mailbox between the synchroniser callback (ROS spinner thread) and the worker thread
+// (skeletonCallback / skeletonThreadCallback, S3D:999-1025) as a deterministic replay. The callback stores frame i in
+// the slot at t_ready[i] and overwrites whatever is still there; the worker, when idle, takes the slot's content (or
+// sleeps until the next store) and is busy for busy[i]. taken[i] = 1: processed, 0: overwritten before the worker saw it.
+int ses3d_mailbox_replay(int32_t n, const int64_t* t_ready_ns, const int64_t* busy_ns, uint8_t* taken,
+                         int64_t* t_start_ns) {
+  if (n < 0 || (n > 0 && (!t_ready_ns || !busy_ns || !taken))) return SES3D_E_INVALID;
+  for (int32_t i = 1; i < n; ++i)
+    if (t_ready_ns[i] < t_ready_ns[i - 1]) return SES3D_E_INVALID;
+  int64_t free_at = INT64_MIN;   // the worker starts out waiting on the condition variable
+  int processed = 0;
+  int32_t i = 0;
+  while (i < n) {
+    int32_t j = i;   // newest frame stored by the time the worker looks at the slot
+    if (free_at > t_ready_ns[i])
+      while (j + 1 < n && t_ready_ns[j + 1] <= free_at) ++j;
+    for (int32_t k = i; k < j; ++k) {
+      taken[k] = 0;
+      if (t_start_ns) t_start_ns[k] = -1;
+    }
+    const int64_t start = free_at > t_ready_ns[j] ? free_at : t_ready_ns[j];
+    taken[j] = 1;
+    if (t_start_ns) t_start_ns[j] = start;
+    free_at = start + (busy_ns[j] > 0 ? busy_ns[j] : 0);
+    ++processed;
+    i = j + 1;
+  }
+  return processed;
 }
 
 int ses3d_assembler_stats(ses3d_assembler a, int64_t stats[5]) {

@@ -10,6 +10,10 @@
 #pragma once
 #include "common.h"
 
+#ifndef SES_UNROLL1
+#define SES_UNROLL1 0   // 1: keep the short solver iterations as loops (A/B switch, scripts/build_variants.py)
+#endif
+
 namespace ses3d {
 
 SES_HD double ses_rsqrt(double x);
@@ -161,9 +165,18 @@ SES_HD void sym4_smallest(const Sym4V<T>& m, T v[4]) {
   if (m.a33 < best) { best = m.a33; v[0] = m.v03; v[1] = m.v13; v[2] = m.v23; v[3] = m.v33; }
 }
 
-// Eigenvector of the smallest eigenvalue of the symmetric 4x4 matrix g (cold start).
+// Eigenvector of the smallest eigenvalue of the symmetric 4x4 matrix g (cold start). Not inlined: it is the rarely
+// taken fallback of every fast solve, and each inlined copy (~5 KB of SASS) would sit in the middle of a hot path.
+#ifndef SES_COLD_JACOBI
+#define SES_COLD_JACOBI 1
+#endif
+#if SES_COLD_JACOBI
+#define SES_JACOBI_FN SES_HDN
+#else
+#define SES_JACOBI_FN SES_HD
+#endif
 template <class T>
-SES_HD void smallest_eigvec4(const double g[10], T v[4]) {
+SES_JACOBI_FN void smallest_eigvec4(const double g[10], T v[4]) {
   Sym4V<T> m;
   sym4_load(m, g);
   jacobi4(m);
@@ -247,6 +260,9 @@ SES_HD bool invit4(const double G[10], T v[4]) {
   if (ses_abs(d3) < floor3) d3 = floor3;
   const T i3 = ses_rcp(d3);
   T x0 = 0, x1 = 0, x2 = 0, x3 = 1;
+#if SES_UNROLL1
+#pragma unroll 1
+#endif
   for (int it = 0; it < 6; ++it) {
     // L z = x, z /= d, L^T y = z
     T z0 = x0;
@@ -273,10 +289,17 @@ SES_HD bool invit4(const double G[10], T v[4]) {
   return false;
 }
 
-// Smallest eigenvector: inverse iteration, Jacobi when it declines.
+// Smallest eigenvector: inverse iteration, Jacobi when it declines. The out-of-line fallback works on copies: handing
+// it the caller's G and v would make those arrays addressable and push them out of registers on the hot path too.
 template <class T>
 SES_HD void smallest_eigvec4_fast(const double G[10], T v[4]) {
-  if (!invit4<T>(G, v)) smallest_eigvec4<T>(G, v);
+  if (!invit4<T>(G, v)) {
+    double Gc[10];
+    T vc[4];
+    for (int i = 0; i < 10; ++i) Gc[i] = G[i];
+    smallest_eigvec4<T>(Gc, vc);
+    v[0] = vc[0]; v[1] = vc[1]; v[2] = vc[2]; v[3] = vc[3];
+  }
 }
 
 // Coordinates of a row r in the basis [v | Q]: s = r.v and p = Q^T r, with Q the Householder
@@ -307,6 +330,9 @@ template <class T>
 SES_HD bool secular_smallest(T a, const T b[3], const T C[6], T x[3]) {
   const T conv = sizeof(T) == 4 ? T(2e-6) : T(1e-13);
   T lam = a;
+#if SES_UNROLL1
+#pragma unroll 1
+#endif
   for (int it = 0; it < 5; ++it) {
     const T m00 = C[0] - lam;
     if (!(m00 > T(0))) return false;

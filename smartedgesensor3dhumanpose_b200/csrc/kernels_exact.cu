@@ -57,17 +57,17 @@ k_rounds(const Tables tb, int n_frames, int p_max, int h_cap, size_t ws_bytes, c
   // work list for K3: every hypothesis with at least two observations (S3D:684); order is irrelevant
   // because results are addressed by (frame, hypothesis)
   tm.pfor(h_cap, [&](int h) { keep[(size_t)f * h_cap + h] = 0; });
-  tm.single([&] {
-    const int nh = ws.scal[SC_N_HYP];
-    int n_active = 0;
-    for (int h = 0; h < nh; ++h) n_active += ws.hyp_nobs[h] >= 2 ? 1 : 0;
-    if (n_active > 0) {
-      int at = atomicAdd(work_count, n_active);
-      for (int h = 0; h < nh; ++h)
-        if (ws.hyp_nobs[h] >= 2) work[at++] = (uint32_t)((size_t)f * h_cap + h);
-    }
-    if (n_out_zero) n_out_zero[f] = 0;
+  // The list is kept in kTriBuckets sub-lists by observation count (the cost of a hypothesis grows with it): K3 runs
+  // the long items first and its lockstep CTAs take items of similar cost.
+  const size_t work_cap = (size_t)n_frames * h_cap;
+  tm.pfor(ws.scal[SC_N_HYP], [&](int h) {
+    const int nobs = ws.hyp_nobs[h];
+    if (nobs < 2) return;
+    const int b = (nobs < kTriBuckets + 1 ? nobs : kTriBuckets + 1) - 2;
+    const int at = atomicAdd(work_count + b, 1);
+    work[(size_t)b * work_cap + at] = (uint32_t)((size_t)f * h_cap + h);
   });
+  tm.single([&] { if (n_out_zero) n_out_zero[f] = 0; });
   if (hyp_of_dump) {  // [C][p_max] hypothesis index of each detection
     int32_t* ho = hyp_of_dump + (size_t)f * C * p_max;
     tm.pfor(C * p_max, [&](int i) { ho[i] = -1; });
@@ -193,9 +193,10 @@ cudaError_t init_kernels(LaunchCfg* cfg, int device) {
   cfg->reproj_cap = env_int("SES3D_REPROJ_CAP", 0);
   cfg->reproj_scap = std::max(1, env_int("SES3D_REPROJ_SCAP", 6));
   cfg->reproj_threads = std::max(32, std::min(128, env_int("SES3D_REPROJ_THREADS", 128) / 32 * 32));
-  cfg->tri_warps = env_int("SES3D_TRI_WARPS", 2);
+  cfg->tri_warps = env_int("SES3D_TRI_WARPS", 4);
   cfg->tri_warps_f64 = env_int("SES3D_TRI_WARPS_F64", 4);
   cfg->tri_dynamic = env_int("SES3D_TRI_DYNAMIC", 1);
+  cfg->tri_lockstep = env_int("SES3D_TRI_LOCKSTEP", 1);
   const int budget = (int)kSmemBudget;
   if ((e = cudaFuncSetAttribute(k_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_rounds, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
@@ -221,7 +222,8 @@ cudaError_t launch_associate(const LaunchCfg& cfg, const Tables& tb, LaunchDims 
   if (cfg.assoc_threads) threads = cfg.assoc_threads;
   if (scratch && !nk_scratch) return cudaErrorInvalidValue;
   if (!pair_table || !meta) return cudaErrorInvalidValue;
-  cudaError_t e = cudaMemsetAsync(work_count, 0, 2 * sizeof(int32_t), st);   // [0] item count, [1] K3's claim counter
+  // [0, kTriBuckets) item counts per observation-count bucket, [kTriBuckets] K3's claim counter
+  cudaError_t e = cudaMemsetAsync(work_count, 0, (kTriBuckets + 1) * sizeof(int32_t), st);
   if (e != cudaSuccess) return e;
   const size_t meta_stride = frame_meta_bytes(tb.n_cams, d.p_max);
   k_pairs<<<d.n_frames, threads, smem, st>>>(tb, d.n_frames, d.p_max, persons, n_persons, scratch ? nk_scratch : nullptr,

@@ -6,6 +6,8 @@
 
 namespace ses3d {
 
+constexpr int kTriBuckets = 8;   // == TRI_BUCKETS (tri_core.h): K3 work sub-lists by observation count
+
 struct LaunchDims {
   int n_frames, p_max, h_cap;
 };
@@ -20,9 +22,10 @@ struct LaunchCfg {
   int reproj_cap = 0;          // 0 = automatic
   int reproj_scap = 6;
   int reproj_threads = 128;
-  int tri_warps = 2, tri_warps_f64 = 4;
+  int tri_warps = 4, tri_warps_f64 = 4;
   int rounds_warps = 4;        // frames (warps) per CTA of the camera-rounds kernel
   int tri_dynamic = 1;         // K3 hands work items out one by one (0: fixed strides)
+  int tri_lockstep = 1;        // K3: the warps of a CTA pass the phases of their hypotheses together (I-cache sharing)
   struct OccEntry { const void* fn; size_t smem; int per_sm; };
   OccEntry occ[8] = {};
   int n_occ = 0;
@@ -40,8 +43,9 @@ size_t associate_smem_bytes(int n_cams, int p_max, int h_cap, bool* needs_scratc
 size_t associate_pair_table_bytes(int n_cams, int p_max);   // per frame
 size_t associate_meta_bytes(int n_cams, int p_max);         // per frame
 
-// K3: one warp per (frame, hypothesis) work item, persistent grid over the work list K2 wrote; work_count[0] = number
-// of items, work_count[1] = next unclaimed item (both zeroed by launch_associate). far_scratch: global workspace of
+// K3: one warp per (frame, hypothesis) work item, persistent grid over the work lists K2 wrote: kTriBuckets sub-lists
+// of n_frames * h_cap slots each (by observation count), work_count[b] = items in sub-list b, work_count[kTriBuckets]
+// = claim counter (all zeroed by launch_associate). far_scratch: global workspace of
 // triangulate_far_scratch_bytes() for the exact covariance of far joints (nullptr / too small: approximate path).
 cudaError_t launch_triangulate(LaunchCfg& cfg, const Tables& tb, LaunchDims d, const ses3d_person2d* persons,
                                const int8_t* hyp_det, const uint32_t* work, int32_t* work_count, ses3d_person_cov* tmp,

@@ -4,6 +4,10 @@
 //                     Items must be independent (no two items write the same location).
 //   team.single(f)    the leader runs f(), then barrier.
 //   team.sync()       barrier with memory ordering among the team's threads.
+//   team.phase()      marks the start of an algorithm phase; a no-op except for LockstepWarpTeam, where it is a
+//                     CTA-wide barrier that keeps the CTA's warps (one team each) inside the same stretch of code so
+//                     that they share instruction-cache lines. Every path through an algorithm must pass the same
+//                     number of phase() calls.
 //
 // WarpTeam: 32 lanes of one warp (barrier = __syncwarp). BlockTeam: the whole CTA
 // (barrier = __syncthreads). SerialTeam: a plain loop (CPU test build only).
@@ -31,6 +35,7 @@ struct SerialTeam {
   template <class F> double sum(int n, F&& f) { double s = 0.0; for (int i = 0; i < n; ++i) s += f(i); return s; }
   template <class F> void per_warp(int n, F&& f) { for (int i = 0; i < n; ++i) f(*this, i); }
   void sync() {}
+  void phase() {}
   int rank() const { return 0; }
   int size() const { return 1; }
 };
@@ -81,8 +86,14 @@ struct WarpTeam {
   }
   template <class F> __device__ __forceinline__ void per_warp(int n, F&& f) { for (int i = 0; i < n; ++i) f(*this, i); }
   __device__ __forceinline__ void sync() { __syncwarp(); }
+  __device__ __forceinline__ void phase() {}
   __device__ __forceinline__ int rank() const { return (int)(threadIdx.x & 31u); }
   __device__ __forceinline__ int size() const { return 32; }
+};
+
+// A warp team whose phase() is a CTA barrier: the warps of a CTA work on different items but stay in the same phase.
+struct LockstepWarpTeam : WarpTeam {
+  __device__ __forceinline__ void phase() { __syncthreads(); }
 };
 
 struct BlockTeam {
@@ -105,6 +116,7 @@ struct BlockTeam {
     __syncthreads();
   }
   __device__ __forceinline__ void sync() { __syncthreads(); }
+  __device__ __forceinline__ void phase() {}
   __device__ __forceinline__ int rank() const { return (int)threadIdx.x; }
   __device__ __forceinline__ int size() const { return (int)blockDim.x; }
 };

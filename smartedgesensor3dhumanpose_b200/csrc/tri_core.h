@@ -21,6 +21,15 @@
 #include "geom.h"
 #include "team.h"
 
+#ifndef SES_COLD_PATHS
+#define SES_COLD_PATHS 1   // 1: rare paths are out-of-line functions (A/B switch, scripts/build_variants.py)
+#endif
+#if SES_COLD_PATHS
+#define SES_COLD_FN SES_HDN
+#else
+#define SES_COLD_FN SES_HD
+#endif
+
 namespace ses3d {
 
 template <class T>
@@ -29,6 +38,8 @@ struct ViewKp {  // one normalised keypoint of one observation (conf = -1: below
 };
 
 constexpr int Y_CHUNK = 256;  // sigma points solved per pass (bounds the shared-memory staging)
+constexpr int TRI_PHASES = 6;  // team.phase() calls on every path through triangulate_hypothesis
+constexpr int TRI_BUCKETS = 8; // K3 work lists by observation count: 2, 3, ..., 8, >= 9
 
 template <class T>
 struct TriWs {
@@ -201,6 +212,23 @@ SES_HD void solve_weighted(const Tables& tb, const TriWs<T>& ws, int k, const ui
   *err = reproj_error<T>(tb, ws, k, list, n, skip, X);
 }
 
+// COLD CALLS. The rarely taken paths (Jacobi fallback, 3-view re-solve, leave-one-out, LM, exact re-solves) are
+// out-of-line functions so that their code does not sit inside the hot instruction stream (the kernel is fetch-bound,
+// see kernels_tri.cu). An object whose address is handed to such a function becomes addressable and is demoted from
+// registers to local memory on EVERY path, so call sites pass copies (of the workspace struct, of small arrays).
+//
+// The same solve for the rare call sites (3-view re-solve, leave-one-out): one shared out-of-line copy.
+template <class T>
+struct ColdSolve { T x, y, z; double err; };
+template <class T>
+SES_COLD_FN ColdSolve<T> solve_weighted_cold(const Tables& tb, const TriWs<T>& ws, int k, const uint8_t* list, int n, int skip) {
+  T X[3];
+  ColdSolve<T> r;
+  solve_weighted<T>(tb, ws, k, list, n, skip, X, &r.err);
+  r.x = X[0]; r.y = X[1]; r.z = X[2];
+  return r;   // by value: the caller's X / err stay in registers
+}
+
 // ---- far points: exact re-solve in the oracle's operation order ----------------------------------------------
 // The DLT returns a homogeneous vector v and the joint is X = v_xyz / v_w (hnormalized, S3D:459). For a point at
 // distance |X| from the rig origin v_w ~ 1/|X|, so a rounding error dv of the unit vector moves X by ~ dv |X|^2: two
@@ -297,7 +325,7 @@ SES_HD double exact_reproj_error(const Tables& tb, const TriWs<float>& ws, int k
 }
 
 template <class Team>
-SES_HD void exact_weighted_resolve(Team& tm, const Tables& tb, const TriWs<float>& ws, int k, const uint8_t* list, int n) {
+SES_COLD_FN void exact_weighted_resolve(Team& tm, const Tables& tb, const TriWs<float>& ws, int k, const uint8_t* list, int n) {
   float X[3];
   exact_dlt(tm, ws.Y, 2 * n, [&](int r, float* row) {
     const int o = list[r >> 1], half = r & 1;
@@ -365,7 +393,7 @@ constexpr int FAR_COV_STRIDE = FAR_COV_MAX_VIEWS * 8 + 16;   // floats per priva
 // the solves are independent, so each lane takes one joint - a garbage hypothesis with 17 far joints costs one pass
 // instead of 17 cooperative solves. Joints with more views go through the cooperative solver (exact_weighted_resolve).
 template <class Team>
-SES_HD void exact_weighted_resolve_lanes(Team& tm, const Tables& tb, const TriWs<float>& ws, int C, float* scratch) {
+SES_COLD_FN void exact_weighted_resolve_lanes(Team& tm, const Tables& tb, const TriWs<float>& ws, int C, float* scratch) {
   const int ld = tm.size();
   tm.pfor(NKP, [&](int k) {
     const int n = ws.jn[k];
@@ -396,8 +424,8 @@ SES_HD void exact_weighted_resolve_lanes(Team&, const Tables&, const TriWs<doubl
 // pass; the transformed points are staged in the (idle) sigma-point buffer and folded per joint in sample order like
 // the reference does.
 template <class Team>
-SES_HD void exact_far_covariances(Team& tm, const Tables& tb, int p_max, const ses3d_person2d* persons,
-                                  const TriWs<float>& ws, int C, float* scratch) {
+SES_COLD_FN void exact_far_covariances(Team& tm, const Tables& tb, int p_max, const ses3d_person2d* persons,
+                                   const TriWs<float>& ws, int C, float* scratch) {
   const int ld = tm.size();
   for (int k0 = 0; k0 < NKP;) {
     tm.single([&] {  // batch [k0,k1): far joints whose 4n+1 solves fit into the staging buffer; soff = staging offsets
@@ -478,7 +506,7 @@ SES_HD void exact_far_covariances(Team&, const Tables&, int, const ses3d_person2
 
 // LM refinement of sum conf^2 * ||hnorm(P X~) - x||^2 (self-specified, not in the reference)
 template <class T>
-SES_HD void lm_refine_joint(const Tables& tb, const TriWs<T>& ws, int k, const uint8_t* list, int n, T X[3]) {
+SES_COLD_FN void lm_refine_joint(const Tables& tb, const TriWs<T>& ws, int k, const uint8_t* list, int n, T X[3]) {
   auto cost_at = [&](const T* Y) {
     T f = 0;
     for (int i = 0; i < n; ++i) {
@@ -558,6 +586,7 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
   const double max_reproj = tb.prm.reproj_error_max_acceptable;
   const float thr = tb.prm.triangulation_threshold;
 
+  tm.phase();   // 1 of TRI_PHASES: gather + normalise
   tm.single([&] {
     int n = 0;
     for (int c = 0; c < C; ++c)
@@ -567,6 +596,7 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
   const int n_obs = ws.scal[0];
   if (n_obs < 2) {  // S3D:684: hypotheses with a single observation are not triangulated
     tm.single([&] { *keep = 0; });
+    for (int i = 1; i < TRI_PHASES; ++i) tm.phase();
     return;
   }
 
@@ -578,6 +608,7 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
   });
 
   // per joint: gather views, weighted DLT, 3-view epipolar rejection (S3D:718-792)
+  tm.phase();   // 2: weighted solves
   tm.pfor(NKP, [&](int k) {
     uint8_t* list = ws.vlist + k * C;
     int n = 0;
@@ -615,7 +646,9 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
       if (best != -1) {
         for (int i = best; i < 2; ++i) list[i] = list[i + 1];
         n = 2;
-        solve_weighted<T>(tb, ws, k, list, n, -1, X, &err);
+        const TriWs<T> wc = ws;   // out-of-line calls get copies: ws must not become addressable (see COLD CALLS)
+        const ColdSolve<T> cs = solve_weighted_cold<T>(tb, wc, k, list, n, -1);
+        X[0] = cs.x; X[1] = cs.y; X[2] = cs.z; err = cs.err;
         avg_score = ((float)ws.vw[list[0] * NKP + k].conf + (float)ws.vw[list[1] * NKP + k].conf) / 2.0f;
       }
     } else if (err > max_reproj && n >= 4) {
@@ -627,6 +660,7 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
     ws.jscore[k] = avg_score;
   });
 
+  tm.phase();   // 3: the rare paths (leave-one-out, exact re-solves)
   // leave-one-out (S3D:793-838), rare: joints with a large error are handled in batches that fit
   // the scratch; one (joint, left-out view) solve per thread, then the reference's sequential selection
   for (int k0 = 0; k0 < NKP;) {
@@ -647,11 +681,10 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
       tm.pfor(used, [&](int i) {
         int k = k0;
         while (k < NKP - 1 && !(ws.jflag[k] && i < ws.soff[k] + ws.jn[k])) ++k;
-        T X[3];
-        double e;
-        solve_weighted<T>(tb, ws, k, ws.vlist + k * C, ws.jn[k], i - ws.soff[k], X, &e);
-        ws.looX[i * 3] = X[0]; ws.looX[i * 3 + 1] = X[1]; ws.looX[i * 3 + 2] = X[2];
-        ws.looErr[i] = e;
+        const TriWs<T> wc = ws;
+        const ColdSolve<T> cs = solve_weighted_cold<T>(tb, wc, k, wc.vlist + k * C, wc.jn[k], i - wc.soff[k]);
+        ws.looX[i * 3] = cs.x; ws.looX[i * 3 + 1] = cs.y; ws.looX[i * 3 + 2] = cs.z;
+        ws.looErr[i] = cs.err;
       });
       tm.pfor(k1 - k0, [&](int kk) {
         const int k = k0 + kk;
@@ -766,12 +799,14 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
         ws.jflag[k] = fl;
       }
     });
-    if (ws.far_scratch) exact_weighted_resolve_lanes(tm, tb, ws, C, ws.far_scratch);
+    const TriWs<T> wc = ws;
+    if (wc.far_scratch) exact_weighted_resolve_lanes(tm, tb, wc, C, wc.far_scratch);
     for (int k = 0; k < NKP; ++k)   // joints the lane-parallel pass cannot hold (or no private scratch): cooperative
       if ((ws.jflag[k] & 1) && (!ws.far_scratch || ws.jn[k] > FAR_COV_MAX_VIEWS))
-        exact_weighted_resolve(tm, tb, ws, k, ws.vlist + k * C, ws.jn[k]);
+        exact_weighted_resolve(tm, tb, wc, k, wc.vlist + k * C, wc.jn[k]);
   }
 
+  tm.phase();   // 4: base systems
   // optional LM, down-weight (S3D:840-844), then the unweighted base system of the final view set:
   // its full eigen-decomposition is the warm-start basis and its smallest eigenvector is sigma point 0
   tm.pfor(NKP, [&](int k) {
@@ -783,7 +818,10 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
     float avg_score = ws.jscore[k];
     T X[3] = {ws.jX[k * 3], ws.jX[k * 3 + 1], ws.jX[k * 3 + 2]};
     if (tb.prm.lm_refine) {
-      lm_refine_joint<T>(tb, ws, k, list, n, X);
+      T Xr[3] = {X[0], X[1], X[2]};   // a copy: the out-of-line call must not make X addressable
+      const TriWs<T> wc = ws;
+      lm_refine_joint<T>(tb, wc, k, list, n, Xr);
+      X[0] = Xr[0]; X[1] = Xr[1]; X[2] = Xr[2];
       err = reproj_error<T>(tb, ws, k, list, n, -1, X);
       ws.jX[k * 3] = X[0]; ws.jX[k * 3 + 1] = X[1]; ws.jX[k * 3 + 2] = X[2];
     }
@@ -831,6 +869,7 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
     cv[3] = (d1 * w0) * d1; cv[4] = (d1 * w0) * d2; cv[5] = (d2 * w0) * d2;
   });
 
+  tm.phase();   // 5: sigma points
   tm.single([&] {
     int off = 0;
     for (int k = 0; k < NKP; ++k) { ws.soff[k] = off; off += (ws.jn[k] >= 2 && !(ws.jflag[k] & 2)) ? 4 * ws.jn[k] : 0; }
@@ -892,7 +931,9 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
           dlt_row_fast<T>(P2, 0, i2 == vi ? nx : v2.x, r); gram_add<T>(G, r, 1.0);
           dlt_row_fast<T>(P2, 1, i2 == vi ? ny : v2.y, r); gram_add<T>(G, r, 1.0);
         }
-        smallest_eigvec4<T>(G, e);
+        T ec[4];
+        smallest_eigvec4<T>(G, ec);
+        e[0] = ec[0]; e[1] = ec[1]; e[2] = ec[2]; e[3] = ec[3];
       }
       const T inv = ses_rcp(e[3]);
       ws.Y[ii * 3] = e[0] * inv; ws.Y[ii * 3 + 1] = e[1] * inv; ws.Y[ii * 3 + 2] = e[2] * inv;
@@ -918,8 +959,12 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
     });
   }
 
+  tm.phase();   // 6: far covariances, skeleton assembly, plausibility, output
   if (exact_on && ws.far_scratch && tm.first(NKP, [&](int k) { return (ws.jflag[k] & 2) != 0; }) < NKP)
-    exact_far_covariances(tm, tb, p_max, persons, ws, C, ws.far_scratch);
+  {
+    const TriWs<T> wc = ws;
+    exact_far_covariances(tm, tb, p_max, persons, wc, C, wc.far_scratch);
+  }
 
   // output keypoints (S3D:849-857); the record shares storage with the sigma-point staging, which is done
   tm.pfor(NFUS, [&](int s) { zero_kp(ws.kp[s]); });

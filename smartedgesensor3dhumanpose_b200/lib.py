@@ -1,19 +1,21 @@
 """ctypes loader of the C-ABI library (libses3d.so, include/ses3d.h). No fallback: if the
 library is missing or no CUDA device is present, the calls fail loudly."""
 import ctypes as C
+import os
 from pathlib import Path
 
 from .layouts import AssocDump, Params, PriorParams, SynthConfig
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libses3d.so"
+# SES3D_LIB: development override (A/B builds of the kernels, scripts/build_variants.py); the product path is fixed
+LIB_PATH = Path(os.environ["SES3D_LIB"]) if os.environ.get("SES3D_LIB") else PKG / "libses3d.so"
 
 EXPORTS = ("ses3d_default_params", "ses3d_create", "ses3d_destroy", "ses3d_get_tables", "ses3d_triangulate_batch",
            "ses3d_reproject_batch", "ses3d_process_batch", "ses3d_process_batch_ragged", "ses3d_reserve", "ses3d_munkres_batch", "ses3d_launch_count",
            "ses3d_set_profiling", "ses3d_last_kernel_ms", "ses3d_last_error_string", "ses3d_version",
            "ses3d_synth_frames", "ses3d_synth_frames_device", "ses3d_assembler_default_config",
            "ses3d_assembler_create", "ses3d_assembler_destroy", "ses3d_assembler_add", "ses3d_assembler_pop",
-           "ses3d_assembler_stats", "ses3d_wire_decode_person2dlist", "ses3d_wire_encode_person2dlist",
+           "ses3d_assembler_stats", "ses3d_mailbox_replay", "ses3d_wire_decode_person2dlist", "ses3d_wire_encode_person2dlist",
            "ses3d_wire_decode_personcovlist", "ses3d_wire_encode_personcovlist", "ses3d_prior_default_params",
            "ses3d_prior_create", "ses3d_prior_destroy", "ses3d_prior_reset", "ses3d_prior_run", "ses3d_prior_get_tracks",
            "ses3d_prior_launch_count", "ses3d_prior_last_kernel_ms", "ses3d_measure_fma_peak", "ses3d_markers_batch", "ses3d_prior_run_ragged",
@@ -67,6 +69,7 @@ def load():
     L.ses3d_assembler_add.argtypes = [vp, i32, i64, i64]
     L.ses3d_assembler_pop.argtypes = [vp, vp, vp, vp, vp]
     L.ses3d_assembler_stats.argtypes = [vp, vp]
+    L.ses3d_mailbox_replay.argtypes = [i32, vp, vp, vp, vp]
     sz = C.c_size_t
     L.ses3d_wire_decode_person2dlist.argtypes = [vp, sz, vp, vp, vp, sz, vp, vp, i32]
     L.ses3d_wire_encode_person2dlist.argtypes = [u32, i64, C.c_char_p, C.c_float, vp, i32, vp, sz]

@@ -428,6 +428,17 @@ int ses3d_markers_batch(ses3d_handle h, int32_t n_frames, int32_t h_max, const s
                         const int32_t* n_persons3d, int32_t style, ses3d_ellipsoid* ellipsoids, double* segments,
                         int32_t* n_segments, int8_t* segment_slot, uint32_t flags, void* stream);
 
+/* 2-D overlay renderer: the image person_msgs/scripts/pose2D_plot_node.py publishes for one Person2DList
+ * (draw_humans :18-66 on a white rgb8 canvas, callback_pose :82-91; the node uses 640 x 480). Per person, in this
+ * order: a filled circle (radius max(1, width/360) * 5) at every keypoint with score >= 0.25 in the COCO colour of the
+ * joint, a line (thickness max(1, width/360) * 4) for every CocoPairs limb whose two joints were drawn in the colour
+ * of its second joint, the bounding box grown by 6 px (thickness max(1, width/360) * 2) in colour 0.
+ *   persons [n_images][p_max], n_persons [n_images], rgb [n_images][height][width][3]
+ * OpenCV's exact pixel coverage is not reproduced (no OpenCV here): coverage rules are documented in kernels_overlay.cu. */
+int ses3d_overlay_batch(ses3d_handle h, int32_t n_images, int32_t p_max, const ses3d_person2d* persons,
+                        const int32_t* n_persons, int32_t width, int32_t height, uint8_t* rgb, uint32_t flags,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -143,6 +143,17 @@ class GeometryPipeline:
                                                _p(n_seg), _p(slot), HOST_BUFFERS, None))
         return dict(ellipsoids=ell, segments=seg, n_segments=n_seg, segment_slot=slot)
 
+    def overlay_batch(self, persons, n_persons, width=640, height=480):
+        """The overlay images of person_msgs/scripts/pose2D_plot_node.py: persons [N][p_max] Person2D,
+        n_persons [N] -> uint8 [N][height][width][3] (rgb8, white background)."""
+        persons = np.ascontiguousarray(persons, dtype=person2d_dtype)
+        N, p_max = persons.shape
+        n_persons = np.ascontiguousarray(n_persons, dtype=np.int32).reshape(N)
+        rgb = np.zeros((N, height, width, 3), np.uint8)
+        _lib.check(self._L.ses3d_overlay_batch(self._h, N, p_max, _p(persons), _p(n_persons), width, height, _p(rgb),
+                                               HOST_BUFFERS, None))
+        return rgb
+
     # ----------------------------------------------------- device-buffer calls
     # Arguments are raw device addresses (e.g. torch_tensor.data_ptr()) on this handle's GPU. These calls are
     # STREAM-ORDERED: they enqueue on `stream` (0 = the legacy default stream) and return without waiting. A capacity

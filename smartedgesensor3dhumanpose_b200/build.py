@@ -30,6 +30,7 @@ UNITS = [
     ("kernels_prior.cu", []),
     ("kernels_peak.cu", []),
     ("kernels_markers.cu", []),
+    ("kernels_overlay.cu", []),
     ("prior_api.cpp", []),
     ("api.cpp", []),
     ("multi.cpp", []),

@@ -79,7 +79,16 @@ struct Slot {  // one in-flight chunk of a host-buffer call
   DevBuf in_dense, in_off, off3, off2, c3d, c2d;  // ragged calls: dense staging + offsets
   long long* totals = nullptr;                    // pinned host: {total3d, total2d} of the chunk in flight
   cudaEvent_t done = nullptr;
+  // ragged host calls: the upload of a chunk runs on its own stream so that it only waits for the kernels that read
+  // the slot's input buffers last (kern_done), not for the download of that older chunk's results
+  cudaStream_t up = nullptr;
+  cudaEvent_t up_done = nullptr, kern_done = nullptr;
   void release() {
+    if (up_done) cudaEventDestroy(up_done);
+    if (kern_done) cudaEventDestroy(kern_done);
+    up_done = kern_done = nullptr;
+    if (up) cudaStreamDestroy(up);
+    up = nullptr;
     sc.release(); persons.release(); n_persons.release(); out3d.release(); n_out3d.release(); out2d.release();
     n_out2d.release(); hyp_of.release(); dump_nhyp.release(); dump_nhung.release(); in_dense.release(); in_off.release(); off3.release(); off2.release();
     c3d.release(); c2d.release();
@@ -100,7 +109,7 @@ struct ses3d_handle_s {
   ses3d::HostTables host;
   DevBuf d_camf, d_camd, d_F, d_frow, d_overflow;
   ses3d::Tables tb;
-  static constexpr int kSlots = 3;   // H2D of chunk i+1, kernels of chunk i and D2H of chunk i-1 overlap
+  static constexpr int kSlots = 5;   // chunks in flight: the upload runs ahead of the kernels, the download trails them
   Slot slot[kSlots];
   cudaEvent_t fork_ev = nullptr;     // device-buffer calls: the caller's stream forks into the slot streams
   int device_split = 2;              // sub-batches of a device-buffer call that run on concurrent streams
@@ -113,7 +122,7 @@ struct ses3d_handle_s {
   // ragged calls: running output totals {3-D records, 2-D records} live on the device and are carried from chunk to
   // chunk by the scan kernels; scan_ev orders the scans of consecutive chunks across the slot streams
   DevBuf d_run;
-  cudaEvent_t scan_ev[kSlots] = {nullptr, nullptr, nullptr};
+  cudaEvent_t scan_ev[kSlots] = {};
   // pinned host words: [0..1] totals of the last ragged call, [2] overflow flag snapshot of the last device-buffer call
   long long* h_words = nullptr;
   // device-buffer calls return without synchronising; dev_done marks the end of the last one on its stream
@@ -222,7 +231,7 @@ int triangulate_on_device(ses3d_handle_s* h, Scratch& sc, cudaStream_t st, int n
       CU(ses3d::launch_finalize(h->tb, d, n_hyp, sc.tmp.as<ses3d_person_cov>(), sc.keep.as<int32_t>(),
                                 out + (size_t)f0 * h_max, n_out + f0, st));
     }
-    h->launches += 4;
+    h->launches += 2 + ses3d::associate_launches(h->cfg, p_max);   // K2a (+ dense instance), K2b, K3, K4 / K4+K6
   }
   return SES3D_OK;
 }
@@ -314,7 +323,7 @@ int run_batch(ses3d_handle_s* h, int stages, int n_frames, int p_max, const ses3
     // stress different resources (FP32 pipe / FP64 pipe / shared-memory latency) and none fills an SM's issue
     // slots or its register / shared-memory budget alone, so CTAs of neighbouring stages co-reside and the
     // tail of one kernel overlaps the head of the next. Profiling runs serially so per-kernel times stay clean.
-    int n_split = (h->profiling || n_frames < 4096) ? 1 : std::min(h->device_split, (int)ses3d_handle_s::kSlots);
+    int n_split = (h->profiling || n_frames < 4096) ? 1 : std::min(h->device_split, 3);
     if (n_split <= 1) {
       const bool fused = (stages & TRI) && (stages & REP);
       if (stages & TRI) {
@@ -477,7 +486,7 @@ int run_ragged(ses3d_handle_s* h, int n_frames, int p_max, const ses3d_person2d*
                                  n_out2d, total3d, total2d, flags);
   if (rc != SES3D_OK) {   // nothing may still be writing into the caller's buffers when a failed call returns
     const std::string msg = g_last_error;
-    for (Slot& sl : h->slot) cudaStreamSynchronize(sl.stream);
+    for (Slot& sl : h->slot) { cudaStreamSynchronize(sl.up); cudaStreamSynchronize(sl.stream); }
     g_last_error = msg;
   }
   return rc;
@@ -514,11 +523,13 @@ int run_ragged_impl(ses3d_handle_s* h, int n_frames, int p_max, const ses3d_pers
   int chunk = std::max(1, std::min(4096, std::max(512, (n_frames + 15) / 16)));
   if (h->ragged_chunk_env > 0) chunk = h->ragged_chunk_env;
   long long in_done = 0, run3 = 0, run2 = 0;
-  struct Pending { int slot; bool active; } prev{0, false};
+  // staged mode: chunks whose kernels are enqueued but whose packed results have not been sent home yet (oldest first)
+  int pending[ses3d_handle_s::kSlots];
+  int n_pending = 0;
   int status = SES3D_OK;
 
-  auto finish = [&](const Pending& pd) -> int {  // staged mode: totals known -> copy the dense results out
-    Slot& s = h->slot[pd.slot];
+  auto finish = [&](int slot) -> int {  // staged mode: totals known -> copy the dense results out
+    Slot& s = h->slot[slot];
     CU(cudaEventSynchronize(s.done));
     const long long t3 = s.totals[0], t2 = s.totals[1];
     if (run3 + t3 > cap3d || run2 + t2 > cap2d) return fail(SES3D_E_CAPACITY, "ragged output buffer too small");
@@ -528,14 +539,24 @@ int run_ragged_impl(ses3d_handle_s* h, int n_frames, int p_max, const ses3d_pers
     run2 += t2;
     return SES3D_OK;
   };
+  auto finish_oldest = [&]() -> int {
+    const int rc = finish(pending[0]);
+    for (int i = 1; i < n_pending; ++i) pending[i - 1] = pending[i];
+    --n_pending;
+    return rc;
+  };
 
   if (direct) {
     CU(h->d_run.ensure(16));
     CU(cudaMemsetAsync(h->d_run.p, 0, 16, h->slot[0].stream));
   }
   int ci = 0;
-  for (int f0 = 0; f0 < n_frames && status == SES3D_OK; f0 += chunk, ++ci) {
-    const int nf = std::min(chunk, n_frames - f0);
+  // The first chunks are short (1/4, 1/2 of the regular size): the download - the longest leg of a host call - can
+  // only start once the first chunk has been uploaded and processed, so a short first chunk shortens the pipeline fill.
+  int nf = 0;
+  for (int f0 = 0; f0 < n_frames && status == SES3D_OK; f0 += nf, ++ci) {
+    const int ramp = (!dev && n_frames >= 4 * chunk) ? (ci == 0 ? chunk / 4 : ci == 1 ? chunk / 2 : chunk) : chunk;
+    nf = std::min(std::max(ramp, 1), n_frames - f0);
     const int si = ci % ses3d_handle_s::kSlots;
     Slot& s = h->slot[si];
     cudaStream_t st = s.stream;
@@ -556,8 +577,13 @@ int run_ragged_impl(ses3d_handle_s* h, int n_frames, int p_max, const ses3d_pers
       CU(s.c3d.ensure((size_t)nf * h_max * sizeof(ses3d_person_cov)));
       CU(s.c2d.ensure(u_in * h_max * sizeof(ses3d_person2d)));
     }
-    CU(cudaMemcpyAsync(s.n_persons.p, n_persons + (size_t)f0 * C, u_in * 4, in_kind, st));
-    if (n_in) CU(cudaMemcpyAsync(s.in_dense.p, persons_dense + in_done, (size_t)n_in * sizeof(ses3d_person2d), in_kind, st));
+    // upload on the slot's own upload stream: behind the kernels of the slot's previous chunk (they read these buffers),
+    // ahead of everything else - the results of that older chunk may still be on their way to the host
+    CU(cudaStreamWaitEvent(s.up, s.kern_done, 0));
+    CU(cudaMemcpyAsync(s.n_persons.p, n_persons + (size_t)f0 * C, u_in * 4, in_kind, s.up));
+    if (n_in) CU(cudaMemcpyAsync(s.in_dense.p, persons_dense + in_done, (size_t)n_in * sizeof(ses3d_person2d), in_kind, s.up));
+    CU(cudaEventRecord(s.up_done, s.up));
+    CU(cudaStreamWaitEvent(st, s.up_done, 0));
     in_done += n_in;
     CU(ses3d::launch_scan_counts(s.n_persons.as<int32_t>(), (int)u_in, p_max, s.in_off.as<long long>(), nullptr, st));
     CU(ses3d::launch_move_records(1, (int)u_in, p_max, (int)sizeof(ses3d_person2d), s.n_persons.as<int32_t>(),
@@ -566,6 +592,7 @@ int run_ragged_impl(ses3d_handle_s* h, int n_frames, int p_max, const ses3d_pers
                                    s.n_persons.as<int32_t>(), s.out3d.as<ses3d_person_cov>(), s.n_out3d.as<int32_t>(),
                                    nullptr, nullptr, nullptr, s.out2d.as<ses3d_person2d>(), s.n_out2d.as<int32_t>());
     if (rc) { status = rc; break; }
+    CU(cudaEventRecord(s.kern_done, st));
     if (direct) {
       // the scans continue the running totals of the previous chunk (which ran on another slot's stream)
       if (ci > 0) CU(cudaStreamWaitEvent(st, h->scan_ev[(ci - 1) % ses3d_handle_s::kSlots], 0));
@@ -594,10 +621,16 @@ int run_ragged_impl(ses3d_handle_s* h, int n_frames, int p_max, const ses3d_pers
     CU(cudaMemcpyAsync(n_out3d + f0, s.n_out3d.p, (size_t)nf * 4, out_kind, st));
     CU(cudaMemcpyAsync(n_out2d + (size_t)f0 * C, s.n_out2d.p, u_in * 4, out_kind, st));
     CU(cudaEventRecord(s.done, st));
-    if (prev.active) status = finish(prev);   // overlaps with the chunk just enqueued
-    prev = Pending{si, true};
+    pending[n_pending++] = si;
+    // Results leave in chunk order. The next chunk reuses the oldest pending slot once kSlots - 1 are in flight, so
+    // that one is sent home first (blocking on its totals); anything else whose totals have already arrived follows
+    // without waiting - the uploads of up to kSlots - 1 chunks run ahead of the kernels, which lets the upload
+    // finish early and the tail of the download use the link alone.
+    while (status == SES3D_OK && n_pending > 0 &&
+           (n_pending >= ses3d_handle_s::kSlots - 1 || cudaEventQuery(h->slot[pending[0]].done) == cudaSuccess))
+      status = finish_oldest();
   }
-  if (!direct && status == SES3D_OK && prev.active) status = finish(prev);
+  while (!direct && status == SES3D_OK && n_pending > 0) status = finish_oldest();
   if (direct && status == SES3D_OK && ci > 0) {
     // totals + overflow flag ride at the end of the last chunk's stream, which is ordered behind every scan
     cudaStream_t st = h->slot[(ci - 1) % ses3d_handle_s::kSlots].stream;
@@ -680,6 +713,9 @@ int ses3d_create(int32_t n_cams, const ses3d_camera* cams, const ses3d_params* p
     ue = cudaStreamCreateWithFlags(&h->slot[i].stream, cudaStreamNonBlocking);
     if (ue == cudaSuccess) ue = cudaMallocHost(reinterpret_cast<void**>(&h->slot[i].totals), 2 * sizeof(long long));
     if (ue == cudaSuccess) ue = cudaEventCreateWithFlags(&h->slot[i].done, cudaEventDisableTiming);
+    if (ue == cudaSuccess) ue = cudaStreamCreateWithFlags(&h->slot[i].up, cudaStreamNonBlocking);
+    if (ue == cudaSuccess) ue = cudaEventCreateWithFlags(&h->slot[i].up_done, cudaEventDisableTiming);
+    if (ue == cudaSuccess) ue = cudaEventCreateWithFlags(&h->slot[i].kern_done, cudaEventDisableTiming);
   }
   if (ue == cudaSuccess) ue = cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming);
   if (ue == cudaSuccess) ue = cudaEventCreateWithFlags(&h->dev_done, cudaEventDisableTiming);
@@ -689,6 +725,9 @@ int ses3d_create(int32_t n_cams, const ses3d_camera* cams, const ses3d_params* p
   if (ue == cudaSuccess) { h->h_words[0] = h->h_words[1] = h->h_words[2] = h->h_words[3] = 0; }
   if (ue == cudaSuccess) ue = h->d_run.ensure(16);
   if (ue == cudaSuccess) ue = ses3d::init_kernels(&h->cfg, device);
+  // the table uploads above are synchronous copies from pageable memory: they may return before the DMA has landed
+  // and are not ordered against the handle's non-blocking streams - wait for them once, here
+  if (ue == cudaSuccess) ue = cudaDeviceSynchronize();
   // tuning overrides are read here, once; nothing on the per-batch path touches the environment
   if (const char* env = getenv("SES3D_DEVICE_SPLIT")) h->device_split = std::max(1, atoi(env));
   if (const char* env = getenv("SES3D_RAGGED_CHUNK")) h->ragged_chunk_env = std::max(1, atoi(env));
@@ -831,6 +870,41 @@ int ses3d_markers_batch(ses3d_handle h, int32_t n_frames, int32_t h_max, const s
   return SES3D_OK;
 }
 
+int ses3d_overlay_batch(ses3d_handle h, int32_t n_images, int32_t p_max, const ses3d_person2d* persons,
+                        const int32_t* n_persons, int32_t width, int32_t height, uint8_t* rgb, uint32_t flags, void* stream) {
+  if (!h) return fail(SES3D_E_INVALID, "null handle");
+  if (n_images < 0 || p_max < 1 || p_max > 1024 || width < 1 || height < 1 || width > 16384 || height > 16384)
+    return fail(SES3D_E_INVALID, "bad n_images / p_max / image size");
+  if (n_images == 0) return SES3D_OK;
+  if (!persons || !n_persons || !rgb) return fail(SES3D_E_INVALID, "NULL buffer");
+  std::lock_guard<std::mutex> lock(h->mu);
+  CU(cudaSetDevice(h->device));
+  if (flags & SES3D_DEVICE_BUFFERS) {
+    CU(ses3d::launch_overlay(n_images, p_max, persons, n_persons, width, height, rgb, static_cast<cudaStream_t>(stream)));
+    ++h->launches;
+    return SES3D_OK;
+  }
+  Slot& s = h->slot[0];
+  cudaStream_t st = s.stream;
+  const size_t img_bytes = (size_t)width * height * 3;
+  // images are rendered in groups that keep the staging below ~256 MiB
+  const int group = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_images, ((size_t)256 << 20) / img_bytes));
+  CU(s.persons.ensure((size_t)group * p_max * sizeof(ses3d_person2d)));
+  CU(s.n_persons.ensure((size_t)group * 4));
+  CU(s.out2d.ensure((size_t)group * img_bytes + 16));
+  for (int i0 = 0; i0 < n_images; i0 += group) {
+    const int n = std::min(group, n_images - i0);
+    CU(cudaMemcpyAsync(s.persons.p, persons + (size_t)i0 * p_max, (size_t)n * p_max * sizeof(ses3d_person2d), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(s.n_persons.p, n_persons + i0, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CU(ses3d::launch_overlay(n, p_max, s.persons.as<ses3d_person2d>(), s.n_persons.as<int32_t>(), width, height,
+                             s.out2d.as<unsigned char>(), st));
+    ++h->launches;
+    CU(cudaMemcpyAsync(rgb + (size_t)i0 * img_bytes, s.out2d.p, (size_t)n * img_bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  return SES3D_OK;
+}
+
 int ses3d_check(ses3d_handle h) {
   if (!h) return fail(SES3D_E_INVALID, "null handle");
   std::lock_guard<std::mutex> lock(h->mu);
@@ -872,10 +946,13 @@ int ses3d_munkres_batch(ses3d_handle h, int32_t n, int32_t rows, int32_t cols, c
   const size_t cb = (size_t)n * rows * cols * sizeof(double), ab = (size_t)n * rows * sizeof(int32_t);
   CU(dc.ensure(cb));
   cudaError_t e = da.ensure(ab);
-  if (e == cudaSuccess) e = cudaMemcpy(dc.p, cost, cb, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = ses3d::launch_munkres_batch(n, rows, cols, dc.as<double>(), da.as<int32_t>(), h->slot[0].stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(h->slot[0].stream);
-  if (e == cudaSuccess) e = cudaMemcpy(assignment, da.p, ab, cudaMemcpyDeviceToHost);
+  // everything on ONE stream: a synchronous cudaMemcpy from pageable memory may return before its DMA has landed and
+  // is not ordered against the handle's non-blocking streams (seen once as a wrong assignment on a 44 x 20 problem)
+  cudaStream_t st = h->slot[0].stream;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dc.p, cost, cb, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = ses3d::launch_munkres_batch(n, rows, cols, dc.as<double>(), da.as<int32_t>(), st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(assignment, da.p, ab, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   dc.release();
   da.release();
   h->launches += 1;

@@ -62,6 +62,8 @@ struct AssocWs {
   uint32_t* kmask;    // [C*p_max] bit k: keypoint k has score > threshold (the strict test of calcCost, S3D:354)
   uint8_t* valid;     // [C*p_max] more than 8 valid keypoints (S3D:579,599), by slot
   uint32_t* pstart;   // [C*p_max+1] cross-camera pairs before compact detection b (b pairs with every earlier camera's)
+  float* lines;       // [n_warps][2][PAIR_TILE][17][4] epipolar lines (x, y, z, norm) of a camera-pair tile; nullptr =
+                      // flat pair pass only
   // ---- both
   double* E;          // [n(n-1)/2], n = C*p_max: pair table in global memory, index b(b-1)/2 + a for a < b
                       //   (compact indices of valid detections, camera-major); -1 = no joint in common
@@ -81,8 +83,14 @@ struct AssocWs {
 
 // Shared-memory workspace of the pair kernel; nk_inside = false keeps the keypoints in global scratch
 // (rigs whose frame does not fit in shared memory). vslot / voff / pscore are staged here and copied to FrameMeta.
+constexpr int PAIR_TILE = 20;   // detections per side of a camera-pair tile (tiled pair pass)
+SES_HD size_t pair_tile_floats() { return (size_t)2 * PAIR_TILE * NKP * 4; }
+
+// tile_warps > 0 reserves the per-warp line buffers of the tiled pair pass
 template <class A>
-SES_HD void pair_ws_layout(A& ar, int C, int p_max, bool nk_inside, AssocWs* ws) {
+SES_HD void pair_ws_layout(A& ar, int C, int p_max, bool nk_inside, AssocWs* ws, int tile_warps = 0) {
+  float* lines = tile_warps > 0 ? ar.template take<float>((size_t)tile_warps * pair_tile_floats()) : nullptr;
+  if (ws) ws->lines = lines;
   float* nk = nk_inside ? ar.template take<float>((size_t)C * p_max * NKP * 2) : nullptr;
   uint32_t* kmask = ar.template take<uint32_t>((size_t)C * p_max);
   uint32_t* pstart = ar.template take<uint32_t>((size_t)C * p_max + 1);
@@ -95,9 +103,9 @@ SES_HD void pair_ws_layout(A& ar, int C, int p_max, bool nk_inside, AssocWs* ws)
     ws->kmask = kmask; ws->pstart = pstart; ws->scal = scal; ws->vslot = vslot; ws->voff = voff; ws->valid = valid;
   }
 }
-inline size_t pair_ws_bytes(int C, int p_max, bool nk_inside) {
+inline size_t pair_ws_bytes(int C, int p_max, bool nk_inside, int tile_warps = 0) {
   ArenaSizer s;
-  pair_ws_layout(s, C, p_max, nk_inside, nullptr);
+  pair_ws_layout(s, C, p_max, nk_inside, nullptr, tile_warps);
   return (s.used + 15) / 16 * 16;
 }
 
@@ -269,9 +277,15 @@ SES_HD void munkres_coop(WT& tm, const AssocWs& ws, const double* in, int n_r, i
 
 // K2a, one frame. persons [C][p_max], n_persons [C]. Outputs: the pair table ws.E and the compact detection list
 // (meta). ws = pair_ws_layout.
+// Dense frame = on average >= 4 valid detections per camera: its pair table is built by camera-pair tiles (needs the
+// line buffers ws.lines). defer_dense: this call has no line buffers and leaves the pair table of dense frames to a
+// second call that has them (GPU: k_pairs with a small workspace for the usual sparse frames, k_pairs_dense with the
+// line buffers for the rest; both run pairs_frame, a frame's table is written by exactly one of them).
+SES_HD bool pairs_frame_is_dense(int n_valid, int C) { return n_valid >= 4 * C; }
+
 template <class Team>
 SES_HD void pairs_frame(Team& tm, const Tables& tb, int p_max, const ses3d_person2d* persons, const int32_t* n_persons,
-                        const AssocWs& ws, const FrameMeta& meta) {
+                        const AssocWs& ws, const FrameMeta& meta, bool defer_dense = false) {
   const int C = tb.n_cams;
   const float thr = tb.prm.triangulation_threshold;
   auto np = [&](int c) { const int n = n_persons[c]; return n < 0 ? 0 : (n > p_max ? p_max : n); };
@@ -328,7 +342,70 @@ SES_HD void pairs_frame(Team& tm, const Tables& tb, int p_max, const ses3d_perso
   tm.pfor(C + 1, [&](int c) { meta.voff[c] = ws.voff[c]; });
 
   // pair table: mean symmetric epipolar distance of every cross-camera pair of valid detections, the inner loop of
-  // calcCost (S3D:347-368), joints in ascending order, float distances summed in double
+  // calcCost (S3D:347-368), joints in ascending order, float distances summed in double.
+  //
+  // Dense frames (crowds: on average >= 4 valid detections per camera): camera-pair tiles, one warp each. The epipolar
+  // line of a keypoint in the other camera (l1 = F p1 resp. l2 = F^T p2) and its norm depend on one detection and the
+  // camera pair only, so a tile of na x nb pairs computes its (na + nb) x 17 lines once into the warp's buffer and a
+  // pair costs two dot products and two divisions per joint instead of two 3x3 products, two square roots and two
+  // divisions - the same operations on the same values, hence the same bits. Sparse frames (the hall rig sees ~2
+  // detections per camera: a line would be used twice) keep the flat pass below.
+  if (defer_dense && pairs_frame_is_dense(n_valid, C)) return;
+  if (ws.lines && pairs_frame_is_dense(n_valid, C)) {
+    tm.per_warp(C * (C - 1) / 2, [&](auto& wt, int t) {
+      int ca = 0;   // t = f_row[ca] + cb - ca - 1 (get_fundamental_idx order)
+      while (ca + 2 < C && tb.f_row[ca + 1] <= t) ++ca;
+      const int cb = t - tb.f_row[ca] + ca + 1;
+      const int a_beg = ws.voff[ca], na = ws.voff[ca + 1] - a_beg, b_beg = ws.voff[cb], nb = ws.voff[cb + 1] - b_beg;
+      if (na == 0 || nb == 0) return;
+      const float* F = tb.F + (size_t)t * 9;
+      float* LA = ws.lines + (size_t)(t % tm.n_warps()) * pair_tile_floats();   // [PAIR_TILE][17][4], detections of ca
+      float* LB = LA + (size_t)PAIR_TILE * NKP * 4;                              // detections of cb
+      for (int ia = 0; ia < na; ia += PAIR_TILE)
+        for (int ib = 0; ib < nb; ib += PAIR_TILE) {
+          const int ta = (na - ia) < PAIR_TILE ? (na - ia) : PAIR_TILE, tb_n = (nb - ib) < PAIR_TILE ? (nb - ib) : PAIR_TILE;
+          wt.pfor((ta + tb_n) * NKP, [&](int i) {
+            const int k = i % NKP, q = i / NKP;
+            const bool side_a = q < ta;
+            const int slot = side_a ? ws.vslot[a_beg + ia + q] : ws.vslot[b_beg + ib + (q - ta)];
+            if (!((ws.kmask[slot] >> k) & 1u)) return;
+            const float x = ws.nk[((size_t)slot * NKP + k) * 2], y = ws.nk[((size_t)slot * NKP + k) * 2 + 1];
+            float lx, ly, lz;
+            if (side_a) {   // l1 = F (x1, y1, 1)
+              lx = sum3(F[0] * x, F[1] * y, F[2] * 1.0f); ly = sum3(F[3] * x, F[4] * y, F[5] * 1.0f);
+              lz = sum3(F[6] * x, F[7] * y, F[8] * 1.0f);
+            } else {        // l2 = F^T (x2, y2, 1)
+              lx = sum3(F[0] * x, F[3] * y, F[6] * 1.0f); ly = sum3(F[1] * x, F[4] * y, F[7] * 1.0f);
+              lz = sum3(F[2] * x, F[5] * y, F[8] * 1.0f);
+            }
+            float* o = (side_a ? LA + (size_t)(q * NKP + k) * 4 : LB + (size_t)((q - ta) * NKP + k) * 4);
+            o[0] = lx; o[1] = ly; o[2] = lz; o[3] = ses_sqrt(lx * lx + ly * ly);
+          });
+          wt.pfor(ta * tb_n, [&](int i) {
+            const int qa = i / tb_n, qb = i % tb_n;
+            const int a = a_beg + ia + qa, b = b_beg + ib + qb;
+            const int sa = ws.vslot[a], sb = ws.vslot[b];
+            const float* hk = ws.nk + ((size_t)sa * NKP) * 2;
+            const float* dk = ws.nk + ((size_t)sb * NKP) * 2;
+            uint32_t m = ws.kmask[sa] & ws.kmask[sb];
+            double cost = 0.;
+            int n_joints = 0;
+            while (m) {
+              const int k = ses_ctz(m);
+              m &= m - 1;
+              const float* l1 = LA + (size_t)(qa * NKP + k) * 4;
+              const float* l2 = LB + (size_t)(qb * NKP + k) * 4;
+              const float d1 = ses_abs(sum3(dk[2 * k] * l1[0], dk[2 * k + 1] * l1[1], 1.0f * l1[2])) / l1[3];
+              const float d2 = ses_abs(sum3(hk[2 * k] * l2[0], hk[2 * k + 1] * l2[1], 1.0f * l2[2])) / l2[3];
+              cost += static_cast<double>(d1 + d2);
+              ++n_joints;
+            }
+            ws.E[(size_t)b * (b - 1) / 2 + a] = n_joints > 0 ? cost / n_joints : -1.0;
+          });
+        }
+    });
+    return;
+  }
   tm.pfor((int)ws.pstart[n_valid], [&](int e) {
     // e -> (a, b): b = the detection whose pair range contains e (binary search), a = offset inside it
     int lo = 0, hi = n_valid;   // invariant: pstart[lo] <= e < pstart[hi]
@@ -391,8 +468,12 @@ SES_HD void rounds_frame(Team& tm, const Tables& tb, int p_max, int h_cap, const
     ws.scal[SC_CURSOR] = c;
   });
 
-  // camera rounds (S3D:588-674)
-  for (int cam = ws.scal[SC_CURSOR]; cam < C; ++cam) {
+  // camera rounds (S3D:588-674). Every frame passes exactly C phase marks (one per camera, skipped rounds included), so
+  // a lockstep team keeps the frames of a CTA inside the same round - the rounds are ~70 KB of branchy code.
+  const int first_cam = ws.scal[SC_CURSOR];
+  for (int cam = 0; cam < C; ++cam) {
+    tm.phase();
+    if (cam < first_cam) continue;
     const int b0 = ws.voff[cam], n_det = ws.voff[cam + 1] - b0, n_hyp = ws.scal[SC_N_HYP];
     if (n_det == 0) continue;  // covers "no person" and "no valid person" (S3D:539-541, 608-609)
 

@@ -11,7 +11,7 @@
 #include "common.h"
 
 #ifndef SES_UNROLL1
-#define SES_UNROLL1 0   // 1: keep the short solver iterations as loops (A/B switch, scripts/build_variants.py)
+#define SES_UNROLL1 1   // 1: keep the short solver iterations as loops: -0.02 ms / 16384 frames (A/B: scripts/build_variants.py)
 #endif
 
 namespace ses3d {
@@ -165,10 +165,10 @@ SES_HD void sym4_smallest(const Sym4V<T>& m, T v[4]) {
   if (m.a33 < best) { best = m.a33; v[0] = m.v03; v[1] = m.v13; v[2] = m.v23; v[3] = m.v33; }
 }
 
-// Eigenvector of the smallest eigenvalue of the symmetric 4x4 matrix g (cold start). Not inlined: it is the rarely
-// taken fallback of every fast solve, and each inlined copy (~5 KB of SASS) would sit in the middle of a hot path.
+// Eigenvector of the smallest eigenvalue of the symmetric 4x4 matrix g (cold start): the rarely taken fallback of every
+// fast solve. SES_COLD_JACOBI selects whether it is a shared out-of-line function (smaller hot code) or inlined.
 #ifndef SES_COLD_JACOBI
-#define SES_COLD_JACOBI 1
+#define SES_COLD_JACOBI 0   // 1 = out of line: measured +0.01 .. 0.03 ms (call ABI costs more than the fetch it saves)
 #endif
 #if SES_COLD_JACOBI
 #define SES_JACOBI_FN SES_HDN

@@ -5,6 +5,7 @@
 // then match the CPU oracle bit for bit as well. The algorithms live in *_core.h; this
 // file only binds a CTA to a frame and carves the shared-memory workspace.
 #include <algorithm>
+#include <type_traits>
 #include <cstdlib>
 
 #include "assoc_core.h"
@@ -16,25 +17,33 @@ namespace ses3d {
 
 extern __shared__ __align__(16) unsigned char smem_raw[];
 
-// K2a: pair table + compact detection list of one frame per CTA (assoc_core.h::pairs_frame)
+// K2a: pair table + compact detection list of one frame per CTA (assoc_core.h::pairs_frame). tile_warps > 0 makes this
+// the dense-frame instance: it carries the line buffers of the tiled pair pass, looks only at frames the first
+// instance found dense (their detection count is in the frame's meta record) and redoes their set-up itself.
 __global__ void __launch_bounds__(256)
 k_pairs(const Tables tb, int n_frames, int p_max, const ses3d_person2d* __restrict__ persons,
         const int32_t* __restrict__ n_persons, float* nk_scratch, double* pair_table, unsigned char* meta_base,
-        size_t meta_stride) {
+        size_t meta_stride, int tile_warps, int defer_dense) {
   const int f = blockIdx.x;
   if (f >= n_frames) return;
   const int C = tb.n_cams;
+  const FrameMeta meta = frame_meta_at(meta_base + (size_t)f * meta_stride, C, p_max);
+  if (tile_warps > 0 && !pairs_frame_is_dense(*meta.n_valid, C)) return;
   Arena ar(smem_raw);
   AssocWs ws;
-  pair_ws_layout(ar, C, p_max, nk_scratch == nullptr, &ws);
+  pair_ws_layout(ar, C, p_max, nk_scratch == nullptr, &ws, tile_warps);
   if (nk_scratch) ws.nk = nk_scratch + (size_t)f * C * p_max * NKP * 2;
   ws.E = pair_table + (size_t)f * assoc_pair_table_entries(C, p_max);
   BlockTeam tm;
-  pairs_frame(tm, tb, p_max, persons + (size_t)f * C * p_max, n_persons + (size_t)f * C, ws,
-              frame_meta_at(meta_base + (size_t)f * meta_stride, C, p_max));
+  pairs_frame(tm, tb, p_max, persons + (size_t)f * C * p_max, n_persons + (size_t)f * C, ws, meta, defer_dense != 0);
 }
 
-// K2b: the sequential camera rounds, one WARP per frame (assoc_core.h::rounds_frame), plus the K3 work list
+// K2b: the sequential camera rounds, one WARP per frame (assoc_core.h::rounds_frame), plus the K3 work list.
+// kLockstep: the CTA's frames pass the camera rounds together (team.phase() = CTA barrier) to share instruction-cache
+// lines (the rounds are ~70 KB of branchy code, a third of the stall samples were instruction fetch). Measured on B200:
+// 0.945 ms with, 0.898 ms without per 16384 frames (K2a + K2b) - the rounds of different frames differ too much in
+// length for the barrier to pay, so it is off by default (SES3D_ROUNDS_LOCKSTEP=1 enables it).
+template <bool kLockstep>
 __global__ void __launch_bounds__(128)
 k_rounds(const Tables tb, int n_frames, int p_max, int h_cap, size_t ws_bytes, const int32_t* __restrict__ n_persons,
          const double* pair_table, unsigned char* meta_base, size_t meta_stride, int8_t* __restrict__ hyp_det,
@@ -42,15 +51,18 @@ k_rounds(const Tables tb, int n_frames, int p_max, int h_cap, size_t ws_bytes, c
          int32_t* __restrict__ keep, uint32_t* __restrict__ work, int32_t* work_count, int32_t* __restrict__ n_out_zero) {
   const int warp = (int)(threadIdx.x >> 5);
   const int f = (int)blockIdx.x * (int)(blockDim.x >> 5) + warp;
-  if (f >= n_frames) return;
   const int C = tb.n_cams;
+  typename std::conditional<kLockstep, LockstepWarpTeam, WarpTeam>::type tm;
+  if (f >= n_frames) {   // padding warp of the last CTA: keep the barrier count of rounds_frame
+    for (int c = 0; c < C; ++c) tm.phase();
+    return;
+  }
   Arena ar(smem_raw + (size_t)warp * ws_bytes);
   AssocWs ws;
   round_ws_layout(ar, C, p_max, h_cap, &ws);
   const FrameMeta meta = frame_meta_at(meta_base + (size_t)f * meta_stride, C, p_max);
   ws.voff = meta.voff; ws.vslot = meta.vslot; ws.pscore = meta.pscore;
   ws.E = const_cast<double*>(pair_table) + (size_t)f * assoc_pair_table_entries(C, p_max);
-  WarpTeam tm;
   int8_t* hd = hyp_det + (size_t)f * h_cap * C;
   rounds_frame(tm, tb, p_max, h_cap, n_persons + (size_t)f * C, *meta.n_valid, ws, hd, n_hyp + f,
                n_hung ? n_hung + f : nullptr, overflow);
@@ -93,25 +105,28 @@ k_finalize(const Tables tb, int n_frames, int h_cap, const int32_t* __restrict__
                  out + (size_t)f * h_cap, n_out + f);
 }
 
-__global__ void __launch_bounds__(128)
-k_reproject(const Tables tb, int n_frames, int h_max, int cap_rec, int s_cap,
+// kThreads / kMinBlocks only set the register budget (launch bounds); the launchers pick the instance from the CTA size
+template <int kThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
+k_reproject(const Tables tb, int n_frames, int h_max, int s_cap,
             const ses3d_person_cov* __restrict__ persons3d,
             const int32_t* __restrict__ n_persons3d, ses3d_person2d* __restrict__ out, int32_t* __restrict__ n_out) {
   const int f = blockIdx.x;
   if (f >= n_frames) return;
   Arena ar(smem_raw);
   ReprojWs ws;
-  reproj_ws_layout(ar, tb.n_cams, cap_rec, s_cap, &ws);
+  reproj_ws_layout(ar, tb.n_cams, (int)(blockDim.x >> 5), s_cap, &ws);
   BlockTeam tm;
-  reproject_frame(tm, tb, h_max, cap_rec, persons3d + (size_t)f * h_max, n_persons3d[f], ws,
+  reproject_frame(tm, tb, h_max, persons3d + (size_t)f * h_max, n_persons3d[f], ws,
                   out + (size_t)f * tb.n_cams * h_max, n_out + (size_t)f * tb.n_cams);
 }
 
 // K4 + K6 fused (process calls): the CTA first compacts / merges the frame's skeletons into the PersonCovList
 // (finalize_frame), then re-projects that list into every camera (reproject_frame). The two steps use the shared
 // memory one after the other (aliased workspaces); the list is read back through L1 / L2, it never waits for DRAM.
-__global__ void __launch_bounds__(128)
-k_finproj(const Tables tb, int n_frames, int h_max, int cap_rec, int s_cap, const int32_t* __restrict__ n_hyp,
+template <int kThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
+k_finproj(const Tables tb, int n_frames, int h_max, int s_cap, const int32_t* __restrict__ n_hyp,
           ses3d_person_cov* tmp, const int32_t* __restrict__ keep, ses3d_person_cov* out3d, int32_t* n_out3d,
           ses3d_person2d* __restrict__ out2d, int32_t* __restrict__ n_out2d) {
   const int f = blockIdx.x;
@@ -128,8 +143,8 @@ k_finproj(const Tables tb, int n_frames, int h_max, int cap_rec, int s_cap, cons
   tm.sync();
   Arena ar(smem_raw);
   ReprojWs ws;
-  reproj_ws_layout(ar, tb.n_cams, cap_rec, s_cap, &ws);
-  reproject_frame(tm, tb, h_max, cap_rec, out3d + (size_t)f * h_max, n_out3d[f], ws,
+  reproj_ws_layout(ar, tb.n_cams, (int)(blockDim.x >> 5), s_cap, &ws);
+  reproject_frame(tm, tb, h_max, out3d + (size_t)f * h_max, n_out3d[f], ws,
                   out2d + (size_t)f * tb.n_cams * h_max, n_out2d + (size_t)f * tb.n_cams);
 }
 
@@ -170,6 +185,7 @@ size_t associate_smem_bytes(int n_cams, int p_max, int h_cap, bool* needs_scratc
   return b;
 }
 
+int associate_launches(const LaunchCfg& cfg, int p_max) { return (cfg.pairs_tiled && p_max >= 4) ? 3 : 2; }
 size_t associate_pair_table_bytes(int n_cams, int p_max) { return assoc_pair_table_entries(n_cams, p_max) * sizeof(double); }
 size_t associate_meta_bytes(int n_cams, int p_max) { return frame_meta_bytes(n_cams, p_max); }
 
@@ -190,19 +206,24 @@ cudaError_t init_kernels(LaunchCfg* cfg, int device) {
   cfg->assoc_threads = env_int("SES3D_ASSOC_THREADS", 0);
   if (cfg->assoc_threads) cfg->assoc_threads = std::max(32, std::min(256, cfg->assoc_threads / 32 * 32));
   cfg->rounds_warps = std::max(1, std::min(4, env_int("SES3D_ROUNDS_WARPS", 4)));
-  cfg->reproj_cap = env_int("SES3D_REPROJ_CAP", 0);
   cfg->reproj_scap = std::max(1, env_int("SES3D_REPROJ_SCAP", 6));
-  cfg->reproj_threads = std::max(32, std::min(128, env_int("SES3D_REPROJ_THREADS", 128) / 32 * 32));
+  cfg->reproj_threads = std::max(0, std::min(512, env_int("SES3D_REPROJ_THREADS", 128) / 32 * 32));   // 0 = one warp per camera, at most 16
   cfg->tri_warps = env_int("SES3D_TRI_WARPS", 4);
   cfg->tri_warps_f64 = env_int("SES3D_TRI_WARPS_F64", 4);
   cfg->tri_dynamic = env_int("SES3D_TRI_DYNAMIC", 1);
   cfg->tri_lockstep = env_int("SES3D_TRI_LOCKSTEP", 1);
+  cfg->rounds_lockstep = env_int("SES3D_ROUNDS_LOCKSTEP", 0);
+  cfg->pairs_tiled = env_int("SES3D_PAIRS_TILED", 1);
   const int budget = (int)kSmemBudget;
   if ((e = cudaFuncSetAttribute(k_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_rounds, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_rounds<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_rounds<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_reproject, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_finproj, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
+#define SES_RP_ATTR(T_, B_)                                                                                                 \
+  if ((e = cudaFuncSetAttribute(k_reproject<T_, B_>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e; \
+  if ((e = cudaFuncSetAttribute(k_finproj<T_, B_>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
+  SES_RP_ATTR(128, 5) SES_RP_ATTR(256, 3) SES_RP_ATTR(512, 1)
+#undef SES_RP_ATTR
   if ((e = cudaFuncSetAttribute(k_munkres_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
   return init_kernels_tri(device);
 }
@@ -226,16 +247,34 @@ cudaError_t launch_associate(const LaunchCfg& cfg, const Tables& tb, LaunchDims 
   cudaError_t e = cudaMemsetAsync(work_count, 0, (kTriBuckets + 1) * sizeof(int32_t), st);
   if (e != cudaSuccess) return e;
   const size_t meta_stride = frame_meta_bytes(tb.n_cams, d.p_max);
+  // sparse frames (and every frame of rigs with < 4 slots per camera) in the small-workspace instance, dense frames
+  // in a second instance that carries the line buffers of the tiled pair pass
+  const int tile_warps = (cfg.pairs_tiled && d.p_max >= 4) ? 8 : 0;
   k_pairs<<<d.n_frames, threads, smem, st>>>(tb, d.n_frames, d.p_max, persons, n_persons, scratch ? nk_scratch : nullptr,
-                                             pair_table, meta, meta_stride);
+                                             pair_table, meta, meta_stride, 0, tile_warps > 0);
+  if (tile_warps > 0) {
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    const size_t smem_dense = pair_ws_bytes(tb.n_cams, d.p_max, !scratch, tile_warps);
+    if (smem_dense > kSmemBudget) return cudaErrorInvalidConfiguration;
+    k_pairs<<<d.n_frames, 32 * tile_warps, smem_dense, st>>>(tb, d.n_frames, d.p_max, persons, n_persons,
+                                                             scratch ? nk_scratch : nullptr, pair_table, meta, meta_stride,
+                                                             tile_warps, 0);
+  }
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   const size_t rws = round_ws_bytes(tb.n_cams, d.p_max, d.h_cap);
   int warps = cfg.rounds_warps;
+  // few frames (crowd rigs: 512 frames per step): one frame per CTA spreads them over all SMs instead of a quarter
+  while (warps > 1 && (d.n_frames + warps - 1) / warps < 2 * cfg.n_sm) warps >>= 1;
   while (warps > 1 && rws * warps > kSmemBudget) warps >>= 1;
   if (rws * warps > kSmemBudget) return cudaErrorInvalidConfiguration;
-  k_rounds<<<(d.n_frames + warps - 1) / warps, 32 * warps, rws * warps, st>>>(
-      tb, d.n_frames, d.p_max, d.h_cap, rws, n_persons, pair_table, meta, meta_stride, hyp_det, n_hyp, n_hung, overflow,
-      hyp_of_dump, keep, work, work_count, nullptr);
+  if (cfg.rounds_lockstep)
+    k_rounds<true><<<(d.n_frames + warps - 1) / warps, 32 * warps, rws * warps, st>>>(
+        tb, d.n_frames, d.p_max, d.h_cap, rws, n_persons, pair_table, meta, meta_stride, hyp_det, n_hyp, n_hung, overflow,
+        hyp_of_dump, keep, work, work_count, nullptr);
+  else
+    k_rounds<false><<<(d.n_frames + warps - 1) / warps, 32 * warps, rws * warps, st>>>(
+        tb, d.n_frames, d.p_max, d.h_cap, rws, n_persons, pair_table, meta, meta_stride, hyp_det, n_hyp, n_hung, overflow,
+        hyp_of_dump, keep, work, work_count, nullptr);
   return cudaGetLastError();
 }
 
@@ -247,37 +286,44 @@ cudaError_t launch_finalize(const Tables& tb, LaunchDims d, const int32_t* n_hyp
   return cudaGetLastError();
 }
 
-static void reproject_config(const LaunchCfg& cfg, const Tables& tb, int h_max, int* cap_rec, int* s_cap, size_t* smem) {
-  // staging capacity in records: ~28 KB, at least one camera of h_max persons, at most the whole frame
-  int cr = std::max(h_max, std::min(tb.n_cams * h_max, std::max(48, 2 * h_max)));   // B200, hall16 x 6: 16 -> 1.25 ms, 32 -> 1.02, 48 -> 0.97, 64 -> 1.10, 96 -> 1.28
-  if (cfg.reproj_cap) cr = std::max(h_max, cfg.reproj_cap);
-  *cap_rec = cr;
+// Cameras are dealt round-robin to the CTA's warps, s_cap persons per batch. B200, hall16 x 6, ms per 16384 frames
+// (fused with finalize): 4 warps 1.41, 8 warps 1.77, 16 warps (one per camera, 1 CTA / SM at 128 registers) 3.97 -
+// the FP64 projection needs ~96 registers, so small CTAs keep more warps resident.
+static void reproject_config(const LaunchCfg& cfg, const Tables& tb, int h_max, int* threads, int* s_cap, size_t* smem) {
+  int warps = cfg.reproj_threads > 0 ? cfg.reproj_threads / 32 : std::min(tb.n_cams, 16);
+  warps = std::max(1, std::min(warps, std::min(tb.n_cams, 16)));   // __launch_bounds__(512)
+  *threads = 32 * warps;
   *s_cap = reproj_s_cap(tb.n_cams, h_max, cfg.reproj_scap);
-  *smem = reproj_ws_bytes(tb.n_cams, cr, *s_cap);
+  *smem = reproj_ws_bytes(tb.n_cams, warps, *s_cap);
 }
 
 cudaError_t launch_finproj(const LaunchCfg& cfg, const Tables& tb, LaunchDims d, const int32_t* n_hyp,
                            ses3d_person_cov* tmp, const int32_t* keep, ses3d_person_cov* out3d, int32_t* n_out3d,
                            ses3d_person2d* out2d, int32_t* n_out2d, cudaStream_t st) {
-  int cap_rec, s_cap;
+  int threads, s_cap;
   size_t smem;
-  reproject_config(cfg, tb, d.h_cap, &cap_rec, &s_cap, &smem);
+  reproject_config(cfg, tb, d.h_cap, &threads, &s_cap, &smem);
   smem = std::max(smem, fin_ws_bytes(d.h_cap));
   if (smem > kSmemBudget) return cudaErrorInvalidConfiguration;
-  k_finproj<<<d.n_frames, cfg.reproj_threads, smem, st>>>(tb, d.n_frames, d.h_cap, cap_rec, s_cap, n_hyp, tmp, keep, out3d,
-                                                         n_out3d, out2d, n_out2d);
+#define SES_FP(T_, B_) k_finproj<T_, B_><<<d.n_frames, threads, smem, st>>>(tb, d.n_frames, d.h_cap, s_cap, n_hyp, tmp, keep, \
+                                                                            out3d, n_out3d, out2d, n_out2d)
+  if (threads <= 128) SES_FP(128, 5);
+  else if (threads <= 256) SES_FP(256, 3);
+  else SES_FP(512, 1);
+#undef SES_FP
   return cudaGetLastError();
 }
 
 cudaError_t launch_reproject(const LaunchCfg& cfg, const Tables& tb, int n_frames, int h_max,
                              const ses3d_person_cov* persons3d, const int32_t* n_persons3d, ses3d_person2d* out,
                              int32_t* n_out, cudaStream_t st) {
-  int cap_rec, s_cap;
+  int threads, s_cap;
   size_t smem;
-  reproject_config(cfg, tb, h_max, &cap_rec, &s_cap, &smem);
+  reproject_config(cfg, tb, h_max, &threads, &s_cap, &smem);
   if (smem > kSmemBudget) return cudaErrorInvalidConfiguration;
-  const int threads = cfg.reproj_threads;
-  k_reproject<<<n_frames, threads, smem, st>>>(tb, n_frames, h_max, cap_rec, s_cap, persons3d, n_persons3d, out, n_out);
+  if (threads <= 128) k_reproject<128, 5><<<n_frames, threads, smem, st>>>(tb, n_frames, h_max, s_cap, persons3d, n_persons3d, out, n_out);
+  else if (threads <= 256) k_reproject<256, 3><<<n_frames, threads, smem, st>>>(tb, n_frames, h_max, s_cap, persons3d, n_persons3d, out, n_out);
+  else k_reproject<512, 1><<<n_frames, threads, smem, st>>>(tb, n_frames, h_max, s_cap, persons3d, n_persons3d, out, n_out);
   return cudaGetLastError();
 }
 

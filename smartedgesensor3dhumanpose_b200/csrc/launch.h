@@ -19,12 +19,13 @@ struct LaunchCfg {
   int device = 0;
   int n_sm = 148;
   int assoc_threads = 0;       // 0 = automatic
-  int reproj_cap = 0;          // 0 = automatic
-  int reproj_scap = 6;
-  int reproj_threads = 128;
+  int reproj_scap = 6;         // persons per batch of the reprojection kernel
+  int reproj_threads = 128;    // 0 = one warp per camera (at most 16 warps)
   int tri_warps = 4, tri_warps_f64 = 4;
   int rounds_warps = 4;        // frames (warps) per CTA of the camera-rounds kernel
   int tri_dynamic = 1;         // K3 hands work items out one by one (0: fixed strides)
+  int pairs_tiled = 1;         // K2a: dense frames build their pair table by camera-pair tiles (second k_pairs instance)
+  int rounds_lockstep = 0;     // K2b: the frames of a CTA pass the camera rounds together (measured slower)
   int tri_lockstep = 1;        // K3: the warps of a CTA pass the phases of their hypotheses together (I-cache sharing)
   struct OccEntry { const void* fn; size_t smem; int per_sm; };
   OccEntry occ[8] = {};
@@ -40,6 +41,7 @@ cudaError_t launch_associate(const LaunchCfg& cfg, const Tables& tb, LaunchDims 
                              int8_t* hyp_det, int32_t* n_hyp, int32_t* n_hung, int32_t* overflow, int32_t* hyp_of_dump,
                              int32_t* keep, uint32_t* work, int32_t* work_count, cudaStream_t st);
 size_t associate_smem_bytes(int n_cams, int p_max, int h_cap, bool* needs_scratch);
+int associate_launches(const LaunchCfg& cfg, int p_max);    // kernels launch_associate enqueues (2 or 3)
 size_t associate_pair_table_bytes(int n_cams, int p_max);   // per frame
 size_t associate_meta_bytes(int n_cams, int p_max);         // per frame
 
@@ -94,4 +96,10 @@ namespace ses3d {
 cudaError_t launch_markers(const SkeletonModel& model, int n_frames, int h_max, int style,
                            const ses3d_person_cov* persons3d, const int32_t* n_persons3d, ses3d_ellipsoid* ell,
                            double* seg, int32_t* n_seg, int8_t* seg_slot, cudaStream_t st);
+}  // namespace ses3d
+
+// K9 (kernels_overlay.cu): 2-D skeleton overlay images, one CTA per image
+namespace ses3d {
+cudaError_t launch_overlay(int n_images, int p_max, const ses3d_person2d* persons, const int32_t* n_persons, int width,
+                           int height, unsigned char* rgb, cudaStream_t st);
 }  // namespace ses3d

@@ -38,6 +38,7 @@ struct SerialTeam {
   void phase() {}
   int rank() const { return 0; }
   int size() const { return 1; }
+  int n_warps() const { return 1; }
 };
 
 // Reserve the next slot of a list shared by the team's threads (order is unspecified on the GPU).
@@ -89,6 +90,7 @@ struct WarpTeam {
   __device__ __forceinline__ void phase() {}
   __device__ __forceinline__ int rank() const { return (int)(threadIdx.x & 31u); }
   __device__ __forceinline__ int size() const { return 32; }
+  __device__ __forceinline__ int n_warps() const { return 1; }
 };
 
 // A warp team whose phase() is a CTA barrier: the warps of a CTA work on different items but stay in the same phase.
@@ -119,6 +121,7 @@ struct BlockTeam {
   __device__ __forceinline__ void phase() {}
   __device__ __forceinline__ int rank() const { return (int)threadIdx.x; }
   __device__ __forceinline__ int size() const { return (int)blockDim.x; }
+  __device__ __forceinline__ int n_warps() const { return (int)(blockDim.x >> 5); }
 };
 #endif
 

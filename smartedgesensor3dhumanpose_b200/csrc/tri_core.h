@@ -22,7 +22,9 @@
 #include "team.h"
 
 #ifndef SES_COLD_PATHS
-#define SES_COLD_PATHS 1   // 1: rare paths are out-of-line functions (A/B switch, scripts/build_variants.py)
+#define SES_COLD_PATHS 0   // 1: rare paths as out-of-line functions - measured +0.05 ms / 16384 frames on B200 (the call
+                           // ABI and the lost cross-call scheduling cost more than the instruction fetch saved); A/B
+                           // switch for scripts/build_variants.py
 #endif
 #if SES_COLD_PATHS
 #define SES_COLD_FN SES_HDN
@@ -212,10 +214,12 @@ SES_HD void solve_weighted(const Tables& tb, const TriWs<T>& ws, int k, const ui
   *err = reproj_error<T>(tb, ws, k, list, n, skip, X);
 }
 
-// COLD CALLS. The rarely taken paths (Jacobi fallback, 3-view re-solve, leave-one-out, LM, exact re-solves) are
-// out-of-line functions so that their code does not sit inside the hot instruction stream (the kernel is fetch-bound,
-// see kernels_tri.cu). An object whose address is handed to such a function becomes addressable and is demoted from
-// registers to local memory on EVERY path, so call sites pass copies (of the workspace struct, of small arrays).
+// COLD CALLS. The rarely taken paths (Jacobi fallback, 3-view re-solve, leave-one-out, LM, exact re-solves) can be
+// built as out-of-line functions (SES_COLD_PATHS / SES_COLD_JACOBI = 1) so that their code does not sit inside the hot
+// instruction stream (the kernel is fetch-bound, see kernels_tri.cu). An object whose address is handed to such a
+// function becomes addressable and is demoted from registers to local memory on EVERY path, so call sites pass copies
+// (of the workspace struct, of small arrays). Measured on B200 (profiles/r02_tri_build_variants.txt): inlined 1.427 ms,
+// out of line 1.484 ms per 16 384 frames - the default is inlined.
 //
 // The same solve for the rare call sites (3-view re-solve, leave-one-out): one shared out-of-line copy.
 template <class T>

@@ -18,7 +18,7 @@ EXPORTS = ("ses3d_default_params", "ses3d_create", "ses3d_destroy", "ses3d_get_t
            "ses3d_assembler_stats", "ses3d_mailbox_replay", "ses3d_wire_decode_person2dlist", "ses3d_wire_encode_person2dlist",
            "ses3d_wire_decode_personcovlist", "ses3d_wire_encode_personcovlist", "ses3d_prior_default_params",
            "ses3d_prior_create", "ses3d_prior_destroy", "ses3d_prior_reset", "ses3d_prior_run", "ses3d_prior_get_tracks",
-           "ses3d_prior_launch_count", "ses3d_prior_last_kernel_ms", "ses3d_measure_fma_peak", "ses3d_markers_batch", "ses3d_prior_run_ragged",
+           "ses3d_prior_launch_count", "ses3d_prior_last_kernel_ms", "ses3d_measure_fma_peak", "ses3d_markers_batch", "ses3d_overlay_batch", "ses3d_prior_run_ragged",
            "ses3d_n_cams", "ses3d_check", "ses3d_bind_thread_to_device_numa", "ses3d_create_multi", "ses3d_multi_destroy",
            "ses3d_multi_device_count", "ses3d_multi_handle", "ses3d_multi_process_batch",
            "ses3d_multi_process_batch_ragged")
@@ -90,6 +90,7 @@ def load():
     L.ses3d_prior_last_kernel_ms.argtypes = [vp, vp]
     L.ses3d_measure_fma_peak.argtypes = [i32, i32, C.POINTER(C.c_double)]
     L.ses3d_markers_batch.argtypes = [vp, i32, i32, vp, vp, i32, vp, vp, vp, vp, u32, vp]
+    L.ses3d_overlay_batch.argtypes = [vp, i32, i32, vp, vp, i32, i32, vp, u32, vp]
     L.ses3d_n_cams.argtypes = [vp]
     L.ses3d_check.argtypes = [vp]
     L.ses3d_bind_thread_to_device_numa.argtypes = [i32, C.POINTER(i32)]

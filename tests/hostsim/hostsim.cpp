@@ -60,7 +60,7 @@ int hostsim_triangulate_batch(void* h, int32_t n_frames, int32_t p_max, const se
   const Tables& tb = s->tb;
   const int C = tb.n_cams;
   const bool big = g_big_rig_path;   // keypoints in "global scratch"
-  std::vector<unsigned char> wsa(pair_ws_bytes(C, p_max, !big) + 64), wsr(round_ws_bytes(C, p_max, h_max) + 64),
+  std::vector<unsigned char> wsa(pair_ws_bytes(C, p_max, !big, 1) + 64), wsr(round_ws_bytes(C, p_max, h_max) + 64),
       wsf(fin_ws_bytes(h_max) + 64), meta_buf(frame_meta_bytes(C, p_max) + 64);
   std::vector<float> nk_scratch(big ? (size_t)C * p_max * NKP * 2 : 0);
   const bool f64 = tb.prm.precision == SES3D_PRECISION_FP64;
@@ -77,7 +77,7 @@ int hostsim_triangulate_batch(void* h, int32_t n_frames, int32_t p_max, const se
     // K2a: pair table + compact detection list; K2b: camera rounds (the two kernels of the association)
     Arena a1(wsa.data());
     AssocWs pws;
-    pair_ws_layout(a1, C, p_max, !big, &pws);
+    pair_ws_layout(a1, C, p_max, !big, &pws, 1);   // with the line buffer: dense frames take the tiled pair pass
     if (big) pws.nk = nk_scratch.data();
     pws.E = pair_table.data();
     const FrameMeta meta = frame_meta_at(meta_buf.data(), C, p_max);
@@ -127,16 +127,15 @@ int hostsim_reproject_batch(void* h, int32_t n_frames, int32_t h_max, int32_t ca
   Sim* s = static_cast<Sim*>(h);
   const Tables& tb = s->tb;
   const int C = tb.n_cams;
-  // cam_tile > 0 forces that many cameras per pass for a full frame; 0 = everything in one pass
-  const int cap_rec = (cam_tile <= 0 ? C : cam_tile) * h_max;
-  const int s_cap = reproj_s_cap(C, h_max, cam_tile > 0 ? 3 : h_max);   // small person batches when a tile size is forced
-  std::vector<unsigned char> wsr(reproj_ws_bytes(C, cap_rec, s_cap) + 64);
+  // cam_tile > 0 forces person batches of that size (several passes over the sigma-point staging); 0 = one batch
+  const int s_cap = reproj_s_cap(C, h_max, cam_tile > 0 ? cam_tile : h_max);
+  std::vector<unsigned char> wsr(reproj_ws_bytes(C, 1, s_cap) + 64);
   SerialTeam tm;
   for (int f = 0; f < n_frames; ++f) {
     Arena a(wsr.data());
     ReprojWs ws;
-    reproj_ws_layout(a, C, cap_rec, s_cap, &ws);
-    reproject_frame(tm, tb, h_max, cap_rec, p3d + (size_t)f * h_max, n_p3d[f], ws, out + (size_t)f * C * h_max,
+    reproj_ws_layout(a, C, 1, s_cap, &ws);
+    reproject_frame(tm, tb, h_max, p3d + (size_t)f * h_max, n_p3d[f], ws, out + (size_t)f * C * h_max,
                     n_out + (size_t)f * C);
   }
   return 0;

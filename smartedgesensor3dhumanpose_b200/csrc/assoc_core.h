@@ -283,9 +283,12 @@ SES_HD void munkres_coop(WT& tm, const AssocWs& ws, const double* in, int n_r, i
 // line buffers for the rest; both run pairs_frame, a frame's table is written by exactly one of them).
 SES_HD bool pairs_frame_is_dense(int n_valid, int C) { return n_valid >= 4 * C; }
 
+// part / n_parts: the frame's pair list may be cut into n_parts slices handled by different teams (crowd rigs: one frame
+// has ~10^6 pairs and there are too few frames to fill the GPU). Every slice repeats the cheap set-up; slice 0 alone
+// writes the frame's meta record.
 template <class Team>
 SES_HD void pairs_frame(Team& tm, const Tables& tb, int p_max, const ses3d_person2d* persons, const int32_t* n_persons,
-                        const AssocWs& ws, const FrameMeta& meta, bool defer_dense = false) {
+                        const AssocWs& ws, const FrameMeta& meta, bool defer_dense = false, int part = 0, int n_parts = 1) {
   const int C = tb.n_cams;
   const float thr = tb.prm.triangulation_threshold;
   auto np = [&](int c) { const int n = n_persons[c]; return n < 0 ? 0 : (n > p_max ? p_max : n); };
@@ -293,16 +296,19 @@ SES_HD void pairs_frame(Team& tm, const Tables& tb, int p_max, const ses3d_perso
   // normalize_keypoints for every detection of the frame (S3D:312-333)
   tm.pfor(C * p_max * NKP, [&](int i) {
     const int k = i % NKP, cd = i / NKP, c = cd / p_max, d = cd % p_max;
-    float* o = ws.nk + (size_t)i * 2;
-    o[0] = 0.f; o[1] = 0.f;
+    float x = 0.f, y = 0.f;
     if (d < np(c)) {
       const ses3d_keypoint2d& kp = persons[cd].keypoints[k];
       const CamF& cm = tb.camf[c];
       if (kp.score >= thr) {
-        o[0] = (kp.x - cm.cx) / cm.fx;
-        o[1] = (kp.y - cm.cy) / cm.fy;
+        x = (kp.x - cm.cx) / cm.fx;
+        y = (kp.y - cm.cy) / cm.fy;
       }
     }
+    // one store of the final value: when the keypoints live in global scratch, other slices of the same frame write
+    // the identical values concurrently and may already be reading
+    float* o = ws.nk + (size_t)i * 2;
+    o[0] = x; o[1] = y;
   });
   tm.pfor(C * p_max, [&](int cd) {
     const int c = cd / p_max, d = cd % p_max;
@@ -335,11 +341,13 @@ SES_HD void pairs_frame(Team& tm, const Tables& tb, int p_max, const ses3d_perso
     ws.voff[C] = (uint16_t)n;
     ws.pstart[n] = pairs;
     ws.scal[SC_N_VALID] = n;
-    *meta.n_valid = n;
+    if (part == 0) *meta.n_valid = n;
   });
   const int n_valid = ws.scal[SC_N_VALID];
-  tm.pfor(n_valid, [&](int a) { meta.vslot[a] = ws.vslot[a]; meta.pscore[a] = persons[ws.vslot[a]].score; });
-  tm.pfor(C + 1, [&](int c) { meta.voff[c] = ws.voff[c]; });
+  if (part == 0) {
+    tm.pfor(n_valid, [&](int a) { meta.vslot[a] = ws.vslot[a]; meta.pscore[a] = persons[ws.vslot[a]].score; });
+    tm.pfor(C + 1, [&](int c) { meta.voff[c] = ws.voff[c]; });
+  }
 
   // pair table: mean symmetric epipolar distance of every cross-camera pair of valid detections, the inner loop of
   // calcCost (S3D:347-368), joints in ascending order, float distances summed in double.
@@ -406,7 +414,10 @@ SES_HD void pairs_frame(Team& tm, const Tables& tb, int p_max, const ses3d_perso
     });
     return;
   }
-  tm.pfor((int)ws.pstart[n_valid], [&](int e) {
+  const long long n_pairs = (long long)ws.pstart[n_valid];
+  const int e_lo = (int)(n_pairs * part / n_parts), e_hi = (int)(n_pairs * (part + 1) / n_parts);
+  tm.pfor(e_hi - e_lo, [&](int e_rel) {
+    const int e = e_lo + e_rel;
     // e -> (a, b): b = the detection whose pair range contains e (binary search), a = offset inside it
     int lo = 0, hi = n_valid;   // invariant: pstart[lo] <= e < pstart[hi]
     while (hi - lo > 1) {

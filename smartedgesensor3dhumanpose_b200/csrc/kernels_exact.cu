@@ -23,8 +23,8 @@ extern __shared__ __align__(16) unsigned char smem_raw[];
 __global__ void __launch_bounds__(256)
 k_pairs(const Tables tb, int n_frames, int p_max, const ses3d_person2d* __restrict__ persons,
         const int32_t* __restrict__ n_persons, float* nk_scratch, double* pair_table, unsigned char* meta_base,
-        size_t meta_stride, int tile_warps, int defer_dense) {
-  const int f = blockIdx.x;
+        size_t meta_stride, int tile_warps, int defer_dense, int n_parts) {
+  const int f = (int)(blockIdx.x / (unsigned)n_parts), part = (int)(blockIdx.x % (unsigned)n_parts);
   if (f >= n_frames) return;
   const int C = tb.n_cams;
   const FrameMeta meta = frame_meta_at(meta_base + (size_t)f * meta_stride, C, p_max);
@@ -35,7 +35,8 @@ k_pairs(const Tables tb, int n_frames, int p_max, const ses3d_person2d* __restri
   if (nk_scratch) ws.nk = nk_scratch + (size_t)f * C * p_max * NKP * 2;
   ws.E = pair_table + (size_t)f * assoc_pair_table_entries(C, p_max);
   BlockTeam tm;
-  pairs_frame(tm, tb, p_max, persons + (size_t)f * C * p_max, n_persons + (size_t)f * C, ws, meta, defer_dense != 0);
+  pairs_frame(tm, tb, p_max, persons + (size_t)f * C * p_max, n_persons + (size_t)f * C, ws, meta, defer_dense != 0, part,
+              n_parts);
 }
 
 // K2b: the sequential camera rounds, one WARP per frame (assoc_core.h::rounds_frame), plus the K3 work list.
@@ -43,18 +44,27 @@ k_pairs(const Tables tb, int n_frames, int p_max, const ses3d_person2d* __restri
 // lines (the rounds are ~70 KB of branchy code, a third of the stall samples were instruction fetch). Measured on B200:
 // 0.945 ms with, 0.898 ms without per 16384 frames (K2a + K2b) - the rounds of different frames differ too much in
 // length for the barrier to pay, so it is off by default (SES3D_ROUNDS_LOCKSTEP=1 enables it).
-template <bool kLockstep>
-__global__ void __launch_bounds__(128)
+// kMode 2: one CTA per frame (BlockTeam; the cost-matrix gathers spread over the whole CTA, Munkres on its first warp) -
+// for rigs whose frames are heavy and few (crowds: a frame's 64 camera rounds take ~15 ms on a single warp, and 512
+// frames do not fill the GPU with one warp each).
+enum { ROUNDS_WARP = 0, ROUNDS_WARP_LOCKSTEP = 1, ROUNDS_BLOCK = 2 };
+template <int kMode> struct RoundsTeam { typedef WarpTeam type; };
+template <> struct RoundsTeam<ROUNDS_WARP_LOCKSTEP> { typedef LockstepWarpTeam type; };
+template <> struct RoundsTeam<ROUNDS_BLOCK> { typedef BlockTeam type; };
+
+template <int kMode>
+__global__ void __launch_bounds__(kMode == ROUNDS_BLOCK ? 256 : 128)
 k_rounds(const Tables tb, int n_frames, int p_max, int h_cap, size_t ws_bytes, const int32_t* __restrict__ n_persons,
          const double* pair_table, unsigned char* meta_base, size_t meta_stride, int8_t* __restrict__ hyp_det,
          int32_t* __restrict__ n_hyp, int32_t* __restrict__ n_hung, int32_t* overflow, int32_t* hyp_of_dump,
          int32_t* __restrict__ keep, uint32_t* __restrict__ work, int32_t* work_count, int32_t* __restrict__ n_out_zero) {
-  const int warp = (int)(threadIdx.x >> 5);
-  const int f = (int)blockIdx.x * (int)(blockDim.x >> 5) + warp;
+  const int warp = kMode == ROUNDS_BLOCK ? 0 : (int)(threadIdx.x >> 5);
+  const int f = kMode == ROUNDS_BLOCK ? (int)blockIdx.x : (int)blockIdx.x * (int)(blockDim.x >> 5) + warp;
   const int C = tb.n_cams;
-  typename std::conditional<kLockstep, LockstepWarpTeam, WarpTeam>::type tm;
-  if (f >= n_frames) {   // padding warp of the last CTA: keep the barrier count of rounds_frame
-    for (int c = 0; c < C; ++c) tm.phase();
+  typename RoundsTeam<kMode>::type tm;
+  if (f >= n_frames) {   // padding warp of the last CTA: keep the barrier count of rounds_frame (lockstep mode)
+    if (kMode == ROUNDS_WARP_LOCKSTEP)
+      for (int c = 0; c < C; ++c) tm.phase();
     return;
   }
   Arena ar(smem_raw + (size_t)warp * ws_bytes);
@@ -213,11 +223,14 @@ cudaError_t init_kernels(LaunchCfg* cfg, int device) {
   cfg->tri_dynamic = env_int("SES3D_TRI_DYNAMIC", 1);
   cfg->tri_lockstep = env_int("SES3D_TRI_LOCKSTEP", 1);
   cfg->rounds_lockstep = env_int("SES3D_ROUNDS_LOCKSTEP", 0);
-  cfg->pairs_tiled = env_int("SES3D_PAIRS_TILED", 1);
+  cfg->pairs_tiled = env_int("SES3D_PAIRS_TILED", 0);
+  cfg->rounds_block = env_int("SES3D_ROUNDS_BLOCK", -1);
+  cfg->pairs_split = env_int("SES3D_PAIRS_SPLIT", 0);
   const int budget = (int)kSmemBudget;
   if ((e = cudaFuncSetAttribute(k_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_rounds<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_rounds<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_rounds<ROUNDS_WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_rounds<ROUNDS_WARP_LOCKSTEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_rounds<ROUNDS_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
 #define SES_RP_ATTR(T_, B_)                                                                                                 \
   if ((e = cudaFuncSetAttribute(k_reproject<T_, B_>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e; \
@@ -250,31 +263,39 @@ cudaError_t launch_associate(const LaunchCfg& cfg, const Tables& tb, LaunchDims 
   // sparse frames (and every frame of rigs with < 4 slots per camera) in the small-workspace instance, dense frames
   // in a second instance that carries the line buffers of the tiled pair pass
   const int tile_warps = (cfg.pairs_tiled && d.p_max >= 4) ? 8 : 0;
-  k_pairs<<<d.n_frames, threads, smem, st>>>(tb, d.n_frames, d.p_max, persons, n_persons, scratch ? nk_scratch : nullptr,
-                                             pair_table, meta, meta_stride, 0, tile_warps > 0);
+  // big rigs with few frames per launch (crowds): several CTAs share a frame's pair list so that the GPU is full
+  int n_parts = 1;
+  if (cfg.pairs_split > 0) n_parts = cfg.pairs_split;
+  // B200, 64 x 20 crowd, 512 frames (K2a + K2b ms): 1 slice 34.3, 2: 31.2, 4: 27.4, 8: 26.6, 16: 26.6
+  else if (scratch && tile_warps == 0) n_parts = std::max(1, std::min(16, (28 * cfg.n_sm + d.n_frames - 1) / d.n_frames));
+  if (tile_warps > 0) n_parts = 1;   // the dense instance reads the meta record slice 0 of the first instance wrote
+  k_pairs<<<d.n_frames * n_parts, threads, smem, st>>>(tb, d.n_frames, d.p_max, persons, n_persons,
+                                                       scratch ? nk_scratch : nullptr, pair_table, meta, meta_stride, 0,
+                                                       tile_warps > 0, n_parts);
   if (tile_warps > 0) {
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     const size_t smem_dense = pair_ws_bytes(tb.n_cams, d.p_max, !scratch, tile_warps);
     if (smem_dense > kSmemBudget) return cudaErrorInvalidConfiguration;
     k_pairs<<<d.n_frames, 32 * tile_warps, smem_dense, st>>>(tb, d.n_frames, d.p_max, persons, n_persons,
                                                              scratch ? nk_scratch : nullptr, pair_table, meta, meta_stride,
-                                                             tile_warps, 0);
+                                                             tile_warps, 0, 1);
   }
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   const size_t rws = round_ws_bytes(tb.n_cams, d.p_max, d.h_cap);
   int warps = cfg.rounds_warps;
-  // few frames (crowd rigs: 512 frames per step): one frame per CTA spreads them over all SMs instead of a quarter
-  while (warps > 1 && (d.n_frames + warps - 1) / warps < 2 * cfg.n_sm) warps >>= 1;
   while (warps > 1 && rws * warps > kSmemBudget) warps >>= 1;
   if (rws * warps > kSmemBudget) return cudaErrorInvalidConfiguration;
-  if (cfg.rounds_lockstep)
-    k_rounds<true><<<(d.n_frames + warps - 1) / warps, 32 * warps, rws * warps, st>>>(
-        tb, d.n_frames, d.p_max, d.h_cap, rws, n_persons, pair_table, meta, meta_stride, hyp_det, n_hyp, n_hung, overflow,
-        hyp_of_dump, keep, work, work_count, nullptr);
-  else
-    k_rounds<false><<<(d.n_frames + warps - 1) / warps, 32 * warps, rws * warps, st>>>(
-        tb, d.n_frames, d.p_max, d.h_cap, rws, n_persons, pair_table, meta, meta_stride, hyp_det, n_hyp, n_hung, overflow,
-        hyp_of_dump, keep, work, work_count, nullptr);
+#define SES_ROUNDS(MODE, GRID, THREADS, SMEM)                                                                              \
+  k_rounds<MODE><<<(GRID), (THREADS), (SMEM), st>>>(tb, d.n_frames, d.p_max, d.h_cap, rws, n_persons, pair_table, meta,      \
+                                                    meta_stride, hyp_det, n_hyp, n_hung, overflow, hyp_of_dump, keep, work,  \
+                                                    work_count, nullptr)
+  // heavy frames (big cost matrices: >= 256 entries) that are too few to fill the GPU one warp each: CTA per frame
+  const bool block_mode = cfg.rounds_block == 1 ||
+                          (cfg.rounds_block < 0 && d.h_cap * d.p_max >= 256 && d.n_frames < 8 * cfg.n_sm * warps);
+  if (block_mode) SES_ROUNDS(ROUNDS_BLOCK, d.n_frames, 256, rws);
+  else if (cfg.rounds_lockstep) SES_ROUNDS(ROUNDS_WARP_LOCKSTEP, (d.n_frames + warps - 1) / warps, 32 * warps, rws * warps);
+  else SES_ROUNDS(ROUNDS_WARP, (d.n_frames + warps - 1) / warps, 32 * warps, rws * warps);
+#undef SES_ROUNDS
   return cudaGetLastError();
 }
 

@@ -399,15 +399,22 @@ def test_device_calls_are_stream_ordered_and_overflow_is_reported_by_check():
 
 
 def test_ragged_call_direct_and_staged_modes_agree():
-    """Pinned outputs are written directly by the pack kernels (mapped memory), pageable outputs are staged: same bytes."""
+    """Host outputs leave through the copy engine (staged, the default); with SES3D_RAGGED_DIRECT=1 the pack kernels
+    write pinned outputs themselves (mapped memory): same bytes either way."""
+    import os
     import torch
     from smartedgesensor3dhumanpose_b200.layouts import person2d_dtype, person_cov_dtype
     fr = helpers.make_workload("cfg2_hall16x6", 5000)
-    gpu = api.GeometryPipeline(fr["cameras"])
     h_max, p_max = fr["h_max"], fr["persons"].shape[2]
     dense_in = api.to_ragged(fr["persons"], fr["n_persons"])
     res = []
     for pinned in (False, True):
+        if pinned:
+            os.environ["SES3D_RAGGED_DIRECT"] = "1"   # read once, at ses3d_create
+        try:
+            gpu = api.GeometryPipeline(fr["cameras"])
+        finally:
+            os.environ.pop("SES3D_RAGGED_DIRECT", None)
         def buf(n, dt):
             if not pinned:
                 return np.zeros(n, dt)

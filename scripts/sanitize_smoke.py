@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Small end-to-end run for compute-sanitizer (memcheck / racecheck / initcheck / synccheck):
     compute-sanitizer --tool racecheck python scripts/sanitize_smoke.py
-Covers the padded, ragged and device-generator paths, outlier branches, FP64 mode and the crowd (global-scratch) rig."""
+Covers the padded, ragged and device-generator paths, outlier branches (incl. far joints: the exact re-solves), FP64
+mode, the crowd rig (global scratch, sliced pair list, CTA-per-frame rounds), the multi-device entry, markers and the
+overlay renderer."""
 import sys
 from pathlib import Path
 
@@ -15,7 +17,7 @@ from smartedgesensor3dhumanpose_b200.layouts import default_params, person2d_dty
 from tests import helpers  # noqa: E402
 
 for name, n, prm, outl in [("cfg2_hall16x6", 24, {}, 0.06), ("cfg5_ring8x4", 16, {"precision": 1, "lm_refine": 1}, 0.0),
-                           ("cfg4_crowd64x20", 1, {}, 0.0)]:
+                           ("cfg3_hall16x6_dropout", 48, {}, 0.0), ("cfg4_crowd64x20", 2, {}, 0.0)]:
     fr = helpers.make_workload(name, n, h_max=40 if outl else None) if outl else helpers.make_workload(name, n)
     if outl:
         helpers.inject_outliers(fr, outl)
@@ -28,5 +30,9 @@ for name, n, prm, outl in [("cfg2_hall16x6", 24, {}, 0.06), ("cfg5_ring8x4", 16,
     t3, t2 = pipe.process_batch_ragged(dense, fr["n_persons"], fr["persons"].shape[2], fr["h_max"], o3,
                                        np.zeros(n, np.int32), o2, np.zeros((n, C), np.int32))
     print(name, "persons3d", int(r["n_out3d"].sum()), "ragged totals", t3, t2)
+    if name == "cfg2_hall16x6":
+        mk = pipe.markers_batch(r["persons3d"], r["n_out3d"], style=0)
+        img = pipe.overlay_batch(fr["persons"][0], fr["n_persons"][0], 320, 240)
+        print("markers", int(mk["n_segments"].sum()), "overlay", img.shape, int((img != 255).any(-1).sum()))
     pipe.close()
 print("sanitize smoke done")

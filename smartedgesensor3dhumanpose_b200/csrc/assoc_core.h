@@ -479,12 +479,8 @@ SES_HD void rounds_frame(Team& tm, const Tables& tb, int p_max, int h_cap, const
     ws.scal[SC_CURSOR] = c;
   });
 
-  // camera rounds (S3D:588-674). Every frame passes exactly C phase marks (one per camera, skipped rounds included), so
-  // a lockstep team keeps the frames of a CTA inside the same round - the rounds are ~70 KB of branchy code.
-  const int first_cam = ws.scal[SC_CURSOR];
-  for (int cam = 0; cam < C; ++cam) {
-    tm.phase();
-    if (cam < first_cam) continue;
+  // camera rounds (S3D:588-674)
+  for (int cam = ws.scal[SC_CURSOR]; cam < C; ++cam) {
     const int b0 = ws.voff[cam], n_det = ws.voff[cam + 1] - b0, n_hyp = ws.scal[SC_N_HYP];
     if (n_det == 0) continue;  // covers "no person" and "no valid person" (S3D:539-541, 608-609)
 

@@ -10,18 +10,22 @@
 
 namespace ses3d {
 
+constexpr int FIN_MAX_WARPS = 16;   // per-warp term buffers are provisioned for teams of up to 16 warps
+
 struct FinWs {
   int* list;    // [h_cap] kept hypothesis indices, in order
   int* scal;    // [2]
   double* D;    // [h_cap*h_cap] pairwise distances of the kept persons
+  double* term; // [FIN_MAX_WARPS][32] per-joint distance terms of the pair a warp is working on (-1 = joint not shared)
 };
 
 template <class A>
 SES_HD void fin_ws_layout(A& ar, int h_cap, FinWs* ws) {
   double* D = ar.template take<double>((size_t)h_cap * h_cap);
+  double* term = ar.template take<double>((size_t)FIN_MAX_WARPS * 32);
   int* list = ar.template take<int>(h_cap);
   int* scal = ar.template take<int>(2);
-  if (ws) { ws->D = D; ws->list = list; ws->scal = scal; }
+  if (ws) { ws->D = D; ws->list = list; ws->scal = scal; ws->term = term; }
 }
 inline size_t fin_ws_bytes(int h_cap) {
   ArenaSizer s;
@@ -71,9 +75,33 @@ SES_HD void finalize_frame(Team& tm, const Tables& tb, int h_cap, int n_hyp, ses
     ws.scal[0] = n;
   });
   const int n0 = ws.scal[0];
-  tm.pfor(n0 * n0, [&](int e) {
-    const int i = e / n0, j = e % n0;
-    if (i < j) ws.D[e] = dist3d(tmp[ws.list[i]], tmp[ws.list[j]]);
+  // calc_3D_dist of every pair (S3D:392-408), one warp per pair: the 21 per-joint distances (an FP64 square root each)
+  // in parallel, then summed by the leader in joint order - the reference's sequential sum, bit for bit. (One thread
+  // per pair left ~10 threads of the CTA grinding through 21 dependent square roots while the rest waited at the
+  // barrier: 43 % of k_finproj's barrier stalls.)
+  const int slots = tm.n_warps();   // item e runs on warp e % n_warps; the launchers keep teams at <= FIN_MAX_WARPS warps
+  tm.per_warp(n0 * (n0 - 1) / 2, [&](auto& wt, int e) {
+    int i = 0, rem = e;   // e -> (i, j), i < j, rows of the upper triangle in order
+    while (rem >= n0 - 1 - i) { rem -= n0 - 1 - i; ++i; }
+    const int j = i + 1 + rem;
+    const ses3d_person_cov &a = tmp[ws.list[i]], &b = tmp[ws.list[j]];
+    double* term = ws.term + (size_t)(e % slots) * 32;
+    wt.pfor(NFUS, [&](int s) {
+      const ses3d_keypoint_cov &p = a.keypoints[s], &q = b.keypoints[s];
+      double t = -1.0;
+      if (p.score > 0 && q.score > 0) {
+        const double dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
+        t = sqrt(dx * dx + dy * dy + dz * dz);
+      }
+      term[s] = t;
+    });
+    wt.single([&] {
+      int n = 0;
+      double d = 0;
+      for (int s = 0; s < NFUS; ++s)
+        if (!(term[s] == -1.0)) { d += term[s]; ++n; }   // -1 = joint not shared; a NaN distance is summed like the reference does
+      ws.D[i * n0 + j] = n > 0 ? d / n : MAX_COSTS;
+    });
   });
   tm.single([&] {
     // positions hold original indices into list/D; erased entries are compacted away

@@ -40,16 +40,15 @@ k_pairs(const Tables tb, int n_frames, int p_max, const ses3d_person2d* __restri
 }
 
 // K2b: the sequential camera rounds, one WARP per frame (assoc_core.h::rounds_frame), plus the K3 work list.
-// kLockstep: the CTA's frames pass the camera rounds together (team.phase() = CTA barrier) to share instruction-cache
-// lines (the rounds are ~70 KB of branchy code, a third of the stall samples were instruction fetch). Measured on B200:
-// 0.945 ms with, 0.898 ms without per 16384 frames (K2a + K2b) - the rounds of different frames differ too much in
-// length for the barrier to pay, so it is off by default (SES3D_ROUNDS_LOCKSTEP=1 enables it).
-// kMode 2: one CTA per frame (BlockTeam; the cost-matrix gathers spread over the whole CTA, Munkres on its first warp) -
-// for rigs whose frames are heavy and few (crowds: a frame's 64 camera rounds take ~15 ms on a single warp, and 512
-// frames do not fill the GPU with one warp each).
-enum { ROUNDS_WARP = 0, ROUNDS_WARP_LOCKSTEP = 1, ROUNDS_BLOCK = 2 };
+// A lockstep variant (the frames of a CTA passing the camera rounds together behind a CTA barrier, to share
+// instruction-cache lines: the rounds are ~70 KB of branchy code and a third of the stall samples were instruction
+// fetch) was measured on B200 and removed: 0.945 ms against 0.898 ms per 16384 frames (K2a + K2b) - the rounds of
+// different frames differ too much in length for the barrier to pay.
+// kMode ROUNDS_BLOCK: one CTA per frame (BlockTeam; the cost-matrix gathers spread over the whole CTA, Munkres on its
+// first warp) - for rigs whose frames are heavy and few (crowds: a frame's 64 camera rounds take ~15 ms on a single
+// warp, and 512 frames do not fill the GPU with one warp each).
+enum { ROUNDS_WARP = 0, ROUNDS_BLOCK = 2 };
 template <int kMode> struct RoundsTeam { typedef WarpTeam type; };
-template <> struct RoundsTeam<ROUNDS_WARP_LOCKSTEP> { typedef LockstepWarpTeam type; };
 template <> struct RoundsTeam<ROUNDS_BLOCK> { typedef BlockTeam type; };
 
 template <int kMode>
@@ -62,11 +61,7 @@ k_rounds(const Tables tb, int n_frames, int p_max, int h_cap, size_t ws_bytes, c
   const int f = kMode == ROUNDS_BLOCK ? (int)blockIdx.x : (int)blockIdx.x * (int)(blockDim.x >> 5) + warp;
   const int C = tb.n_cams;
   typename RoundsTeam<kMode>::type tm;
-  if (f >= n_frames) {   // padding warp of the last CTA: keep the barrier count of rounds_frame (lockstep mode)
-    if (kMode == ROUNDS_WARP_LOCKSTEP)
-      for (int c = 0; c < C; ++c) tm.phase();
-    return;
-  }
+  if (f >= n_frames) return;   // padding warp of the last CTA (no CTA-wide barrier follows in warp mode)
   Arena ar(smem_raw + (size_t)warp * ws_bytes);
   AssocWs ws;
   round_ws_layout(ar, C, p_max, h_cap, &ws);
@@ -222,14 +217,12 @@ cudaError_t init_kernels(LaunchCfg* cfg, int device) {
   cfg->tri_warps_f64 = env_int("SES3D_TRI_WARPS_F64", 4);
   cfg->tri_dynamic = env_int("SES3D_TRI_DYNAMIC", 1);
   cfg->tri_lockstep = env_int("SES3D_TRI_LOCKSTEP", 1);
-  cfg->rounds_lockstep = env_int("SES3D_ROUNDS_LOCKSTEP", 0);
   cfg->pairs_tiled = env_int("SES3D_PAIRS_TILED", 0);
   cfg->rounds_block = env_int("SES3D_ROUNDS_BLOCK", -1);
   cfg->pairs_split = env_int("SES3D_PAIRS_SPLIT", 0);
   const int budget = (int)kSmemBudget;
   if ((e = cudaFuncSetAttribute(k_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_rounds<ROUNDS_WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_rounds<ROUNDS_WARP_LOCKSTEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_rounds<ROUNDS_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
 #define SES_RP_ATTR(T_, B_)                                                                                                 \
@@ -293,7 +286,6 @@ cudaError_t launch_associate(const LaunchCfg& cfg, const Tables& tb, LaunchDims 
   const bool block_mode = cfg.rounds_block == 1 ||
                           (cfg.rounds_block < 0 && d.h_cap * d.p_max >= 256 && d.n_frames < 8 * cfg.n_sm * warps);
   if (block_mode) SES_ROUNDS(ROUNDS_BLOCK, d.n_frames, 256, rws);
-  else if (cfg.rounds_lockstep) SES_ROUNDS(ROUNDS_WARP_LOCKSTEP, (d.n_frames + warps - 1) / warps, 32 * warps, rws * warps);
   else SES_ROUNDS(ROUNDS_WARP, (d.n_frames + warps - 1) / warps, 32 * warps, rws * warps);
 #undef SES_ROUNDS
   return cudaGetLastError();

@@ -69,14 +69,11 @@ k_triangulate(const Tables tb, int p_max, int h_cap, size_t work_cap, size_t ws_
       __syncthreads();
       if (base >= wv.total) break;
       uint32_t item = 0;
-      if (wv.at(work, work_cap, kWarpsPerCta, base + warp, &item)) {
-        const size_t fh = item;  // frame * h_cap + hypothesis
-        const size_t f = fh / h_cap;
-        triangulate_hypothesis<T>(tm, tb, p_max, persons + f * tb.n_cams * p_max, hyp_det + fh * tb.n_cams, ws, tmp + fh,
-                                  keep + fh);
-      } else {
-        for (int i = 0; i < TRI_PHASES; ++i) tm.phase();   // padding slot: keep the barrier count
-      }
+      const bool live = wv.at(work, work_cap, kWarpsPerCta, base + warp, &item);   // false: padding slot
+      const size_t fh = item;  // frame * h_cap + hypothesis
+      const size_t f = fh / h_cap;
+      triangulate_hypothesis<T>(tm, tb, p_max, persons + f * tb.n_cams * p_max, hyp_det + fh * tb.n_cams, ws, tmp + fh,
+                                keep + fh, nullptr, live);
     }
     return;
   }

@@ -28,7 +28,6 @@ struct LaunchCfg {
                                // measured SLOWER than the flat pass on every rig (crowd 49 vs 30 ms), kept for A/B only
   int pairs_split = 0;         // K2a: CTAs per frame (0 = automatic: > 1 only for big rigs with few frames per launch)
   int rounds_block = -1;       // K2b: CTA per frame instead of warp per frame (-1 = automatic: heavy, few frames)
-  int rounds_lockstep = 0;     // K2b: the frames of a CTA pass the camera rounds together (measured slower)
   int tri_lockstep = 1;        // K3: the warps of a CTA pass the phases of their hypotheses together (I-cache sharing)
   struct OccEntry { const void* fn; size_t smem; int per_sm; };
   OccEntry occ[8] = {};

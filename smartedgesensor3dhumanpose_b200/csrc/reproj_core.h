@@ -159,9 +159,11 @@ SES_HD void reproject_frame(Team& tm, const Tables& tb, int h_max, const ses3d_p
         if (reproj_certainly_outside(ws.ctr + (size_t)e * 4, tb.camf[c], cm)) return;
         list[team_append(cnt)] = (uint16_t)e;
       });
-      if (cnt[0] == 0) return;   // nobody of this batch is anywhere near this camera's image (the common case)
+      const int n_surv = cnt[0];
+      wt.sync();   // every lane has read the count before the leader resets it for the warp's next camera
+      if (n_surv == 0) return;   // nobody of this batch is anywhere near this camera's image (the common case)
       wt.pfor(np_b * words, [&](int e) { reinterpret_cast<uint32_t*>(stage)[e] = 0u; });
-      wt.pfor(cnt[0], [&](int li) {
+      wt.pfor(n_surv, [&](int li) {
         const int e = list[li];
         const int pl = e / NKP, k = e % NKP;
         const float score = ws.sscore[e];

@@ -4,6 +4,9 @@
 //                     Items must be independent (no two items write the same location).
 //   team.single(f)    the leader runs f(), then barrier.
 //   team.sync()       barrier with memory ordering among the team's threads.
+//   team.shared_pfor(n, tag, f)   phase() followed by a pfor over the member's own n items, f(0, tag, i), skipped when
+//                     tag == 0 (a lockstep member without work still passes the barrier). The member index exists so
+//                     that a team of teams may spread the items of all members over all of its threads.
 //   team.phase()      marks the start of an algorithm phase; a no-op except for LockstepWarpTeam, where it is a
 //                     CTA-wide barrier that keeps the CTA's warps (one team each) inside the same stretch of code so
 //                     that they share instruction-cache lines. Every path through an algorithm must pass the same
@@ -36,6 +39,7 @@ struct SerialTeam {
   template <class F> void per_warp(int n, F&& f) { for (int i = 0; i < n; ++i) f(*this, i); }
   void sync() {}
   void phase() {}
+  template <class F> void shared_pfor(int n, int tag, F&& f) { if (tag) for (int i = 0; i < n; ++i) f(0, tag, i); }
   int rank() const { return 0; }
   int size() const { return 1; }
   int n_warps() const { return 1; }
@@ -88,6 +92,10 @@ struct WarpTeam {
   template <class F> __device__ __forceinline__ void per_warp(int n, F&& f) { for (int i = 0; i < n; ++i) f(*this, i); }
   __device__ __forceinline__ void sync() { __syncwarp(); }
   __device__ __forceinline__ void phase() {}
+  template <class F> __device__ __forceinline__ void shared_pfor(int n, int tag, F&& f) {
+    if (tag) for (int i = (int)(threadIdx.x & 31u); i < n; i += 32) f(0, tag, i);
+    __syncwarp();
+  }
   __device__ __forceinline__ int rank() const { return (int)(threadIdx.x & 31u); }
   __device__ __forceinline__ int size() const { return 32; }
   __device__ __forceinline__ int n_warps() const { return 1; }
@@ -96,6 +104,15 @@ struct WarpTeam {
 // A warp team whose phase() is a CTA barrier: the warps of a CTA work on different items but stay in the same phase.
 struct LockstepWarpTeam : WarpTeam {
   __device__ __forceinline__ void phase() { __syncthreads(); }
+  // A shared phase starts with the CTA barrier; every member then runs its own items. (Spreading the items of all
+  // members over all threads of the CTA - 4 x 17 joints on 128 lanes instead of 17 of 32 lanes per warp - was built and
+  // measured on B200: 1.47 ms against 1.42 ms per 16 384 frames. The second barrier and the workspace indirection cost
+  // more than the idle lanes.)
+  template <class F> __device__ __forceinline__ void shared_pfor(int n, int tag, F&& f) {
+    __syncthreads();
+    if (tag) for (int i = (int)(threadIdx.x & 31u); i < n; i += 32) f(0, tag, i);
+    __syncwarp();
+  }
 };
 
 struct BlockTeam {
@@ -119,6 +136,10 @@ struct BlockTeam {
   }
   __device__ __forceinline__ void sync() { __syncthreads(); }
   __device__ __forceinline__ void phase() {}
+  template <class F> __device__ __forceinline__ void shared_pfor(int n, int tag, F&& f) {
+    if (tag) for (int i = (int)threadIdx.x; i < n; i += (int)blockDim.x) f(0, tag, i);
+    __syncthreads();
+  }
   __device__ __forceinline__ int rank() const { return (int)threadIdx.x; }
   __device__ __forceinline__ int size() const { return (int)blockDim.x; }
   __device__ __forceinline__ int n_warps() const { return (int)(blockDim.x >> 5); }

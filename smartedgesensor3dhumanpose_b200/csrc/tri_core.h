@@ -582,38 +582,49 @@ SES_HD void zero_kp(ses3d_keypoint_cov& kp) {
 
 // One hypothesis. hyp_det_row [C]: detection slot per camera (-1 = not observed).
 // Writes *out (the PersonCov record) and *keep (1 if the person passes S3D:968).
+//
+// live = false: this member of a lockstep team has no hypothesis (padding slot); it only passes the phase barriers - every
+// member executes the same barrier call sites. team_ws: workspaces of all members when a team of teams spreads the two
+// per-joint phases over all its threads (team.shared_pfor passes the member index); nullptr = every member runs its own
+// joints (the measured optimum, see team.h).
 template <class T, class Team>
 SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const ses3d_person2d* persons,
                                    const int8_t* hyp_det_row, const TriWs<T>& ws, ses3d_person_cov* out,
-                                   int32_t* keep) {
+                                   int32_t* keep, const TriWs<T>* team_ws = nullptr, bool live = true) {
   const int C = tb.n_cams;
   const double max_reproj = tb.prm.reproj_error_max_acceptable;
   const float thr = tb.prm.triangulation_threshold;
+  if (!team_ws) team_ws = &ws;
 
   tm.phase();   // 1 of TRI_PHASES: gather + normalise
-  tm.single([&] {
-    int n = 0;
-    for (int c = 0; c < C; ++c)
-      if (hyp_det_row[c] >= 0) { ws.obs_cam[n] = (uint8_t)c; ws.obs_det[n] = (uint8_t)hyp_det_row[c]; ++n; }
-    ws.scal[0] = n;
-  });
-  const int n_obs = ws.scal[0];
-  if (n_obs < 2) {  // S3D:684: hypotheses with a single observation are not triangulated
-    tm.single([&] { *keep = 0; });
-    for (int i = 1; i < TRI_PHASES; ++i) tm.phase();
-    return;
+  int n_obs_own = 0;
+  if (live) {
+    tm.single([&] {
+      int n = 0;
+      for (int c = 0; c < C; ++c)
+        if (hyp_det_row[c] >= 0) { ws.obs_cam[n] = (uint8_t)c; ws.obs_det[n] = (uint8_t)hyp_det_row[c]; ++n; }
+      ws.scal[0] = n;
+    });
+    n_obs_own = ws.scal[0];
+    if (n_obs_own < 2) {  // S3D:684: hypotheses with a single observation are not triangulated
+      tm.single([&] { *keep = 0; });
+      n_obs_own = 0;
+      live = false;
+    }
+  }
+  if (live) {
+    // normalised keypoints of the hypothesis' observations
+    tm.pfor(n_obs_own * NKP, [&](int i) {
+      const int o = i / NKP, k = i % NKP;
+      const int cam = ws.obs_cam[o];
+      normalize_kp(tb, cam, persons[cam * p_max + ws.obs_det[o]].keypoints[k], ws.vw[i]);
+    });
   }
 
-  // normalised keypoints of the hypothesis' observations
-  tm.pfor(n_obs * NKP, [&](int i) {
-    const int o = i / NKP, k = i % NKP;
-    const int cam = ws.obs_cam[o];
-    normalize_kp(tb, cam, persons[cam * p_max + ws.obs_det[o]].keypoints[k], ws.vw[i]);
-  });
-
   // per joint: gather views, weighted DLT, 3-view epipolar rejection (S3D:718-792)
-  tm.phase();   // 2: weighted solves
-  tm.pfor(NKP, [&](int k) {
+  // 2: weighted solves (shared phase; the explicit capture list keeps member-specific state out of the body)
+  tm.shared_pfor(NKP, n_obs_own, [&tb, team_ws, C, thr, max_reproj](int member, int n_obs, int k) {
+    const TriWs<T>& ws = team_ws[member];
     uint8_t* list = ws.vlist + k * C;
     int n = 0;
     float avg_score = 0;
@@ -665,9 +676,13 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
   });
 
   tm.phase();   // 3: the rare paths (leave-one-out, exact re-solves)
+  const bool exact_on = sizeof(T) == 4 && (tb.exact_mode & 1);
+  const int cap_n = (int)((size_t)Y_CHUNK * 3 - 16) / 8;   // views the cooperative solver can stage
+  if (live) {
   // leave-one-out (S3D:793-838), rare: joints with a large error are handled in batches that fit
   // the scratch; one (joint, left-out view) solve per thread, then the reference's sequential selection
-  for (int k0 = 0; k0 < NKP;) {
+  const bool any_loo = tm.first(NKP, [&](int k) { return ws.jflag[k] != 0; }) < NKP;   // usually none: skip the batching
+  for (int k0 = any_loo ? 0 : NKP; k0 < NKP;) {
     tm.single([&] {  // batch [k0,k1): flagged joints whose n solves fit into loo_cap; soff = scratch offsets
       int k1 = k0, used = 0;
       while (k1 < NKP) {
@@ -729,8 +744,6 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
   // above the acceptance threshold (a gross outlier left in the view set: the large smallest singular value narrows
   // the gap to the next one, which amplifies rounding the same way, and the residual scales the published score,
   // S3D:840-844 - solved exactly, both match the oracle to the last bit).
-  const bool exact_on = sizeof(T) == 4 && (tb.exact_mode & 1);
-  const int cap_n = (int)((size_t)Y_CHUNK * 3 - 16) / 8;   // views the cooperative solver can stage
   tm.pfor(NKP, [&](int k) {
     int fl = 0;
     const int n = ws.jn[k];
@@ -810,10 +823,11 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
         exact_weighted_resolve(tm, tb, wc, k, wc.vlist + k * C, wc.jn[k]);
   }
 
-  tm.phase();   // 4: base systems
-  // optional LM, down-weight (S3D:840-844), then the unweighted base system of the final view set:
-  // its full eigen-decomposition is the warm-start basis and its smallest eigenvector is sigma point 0
-  tm.pfor(NKP, [&](int k) {
+  }   // live (phase 3)
+  // 4: base systems (shared phase): optional LM, down-weight (S3D:840-844), then the unweighted base system of the final
+  // view set: its full eigen-decomposition is the warm-start basis and its smallest eigenvector is sigma point 0
+  tm.shared_pfor(NKP, n_obs_own, [&tb, team_ws, C, max_reproj](int member, int, int k) {
+    const TriWs<T>& ws = team_ws[member];
     const int n = ws.jn[k];
     for (int i = 0; i < 6; ++i) ws.cov[k * 6 + i] = T(0);
     if (n < 2) return;
@@ -874,6 +888,7 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
   });
 
   tm.phase();   // 5: sigma points
+  if (live) {
   tm.single([&] {
     int off = 0;
     for (int k = 0; k < NKP; ++k) { ws.soff[k] = off; off += (ws.jn[k] >= 2 && !(ws.jflag[k] & 2)) ? 4 * ws.jn[k] : 0; }
@@ -963,7 +978,9 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
     });
   }
 
+  }   // live (phase 5)
   tm.phase();   // 6: far covariances, skeleton assembly, plausibility, output
+  if (!live) return;
   if (exact_on && ws.far_scratch && tm.first(NKP, [&](int k) { return (ws.jflag[k] & 2) != 0; }) < NKP)
   {
     const TriWs<T> wc = ws;

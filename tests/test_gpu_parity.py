@@ -30,7 +30,7 @@ def _run_pair(name, n_frames, params=None, outliers=0.0, **over):
 
 
 @pytest.mark.parametrize("name,n_frames", [("cfg1_ring4x1", 2000), ("cfg2_hall16x6", 1500), ("cfg3_hall16x6_dropout", 1500),
-                                           ("cfg5_ring8x4", 1500), ("dense_ring16x6", 300), ("cfg4_crowd64x20", 12)])
+                                           ("cfg5_ring8x4", 1500), ("dense_ring16x6", 300), ("cfg4_crowd64x20", 96)])
 def test_association_bit_exact_and_joints_fp32(name, n_frames):
     fr, orc, gpu, ro, rg = _run_pair(name, n_frames)
     assert np.array_equal(gpu.tables()[1], orc.tables()[1]), "fundamental matrices differ"
@@ -124,7 +124,7 @@ def test_lm_refinement_matches_oracle():
     helpers.compare_persons3d(ro, rg, POS_TOL_FP32, cov_rtol=5e-2)
 
 
-@pytest.mark.parametrize("name,n_frames", [("cfg2_hall16x6", 800), ("cfg5_ring8x4", 500), ("cfg4_crowd64x20", 8)])
+@pytest.mark.parametrize("name,n_frames", [("cfg2_hall16x6", 800), ("cfg5_ring8x4", 500), ("cfg4_crowd64x20", 48)])
 def test_reprojection_bit_exact(name, n_frames):
     fr, orc, gpu, ro, rg = _run_pair(name, n_frames)
     # feed the ORACLE's 3-D persons to both, so the comparison isolates the reprojection stage

@@ -22,3 +22,13 @@ for f in ['bench_${T}_reference','bench_${T}']:
     d=json.loads(open('gpurun_out/'+f+'.json').read().strip().splitlines()[-1]); print(f, d['value'], d.get('frames_per_sec'), d.get('ms_per_step'), d.get('e2e',{}).get('value'), d.get('roofline',{}).get('frac'))
     for k,v in d.get('extra',{}).items(): print('  ',k, {kk: v.get(kk) for kk in ('ms_per_step','frames_per_sec','value')}, v.get('parity',{}).get('ok'), v.get('roofline',{}).get('kernel'), v.get('roofline',{}).get('frac'), v.get('error'))
 PY
+for tool in memcheck racecheck synccheck initcheck; do
+  timeout 1500 compute-sanitizer --tool $tool python scripts/sanitize_smoke.py > gpurun_out/${T}_san_$tool.log 2>&1
+  echo "== $tool"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|sanitize smoke done" gpurun_out/${T}_san_$tool.log | tail -3
+done
+timeout 900 compute-sanitizer --tool racecheck python scripts/sanitize_prior.py > gpurun_out/${T}_san_prior_racecheck.log 2>&1
+grep -E "RACECHECK SUMMARY" gpurun_out/${T}_san_prior_racecheck.log | tail -1
+timeout 900 python scripts/bench_prior.py > gpurun_out/bench_prior_${T}.json 2> gpurun_out/${T}_bench_prior_err.log; python -c "
+import json; d=json.loads(open('gpurun_out/bench_prior_${T}.json').read().strip().splitlines()[-1]); print('prior', d['value'], d.get('ms_per_step'), d.get('e2e',{}).get('value'))"
+timeout 900 python scripts/bench_chain.py > gpurun_out/bench_chain_${T}.json 2> gpurun_out/${T}_err_chain.log; python -c "
+import json; d=json.loads(open('gpurun_out/bench_chain_${T}.json').read().strip().splitlines()[-1]); print('chain', d.get('value'), d.get('frames_per_sec'), d.get('ms_per_step'))"

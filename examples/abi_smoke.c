@@ -79,6 +79,16 @@ int main(void) {
   }
   ses3d_assembler_destroy(asmb);
 
+  /* latest-wins mailbox replay: a 100 ms worker on a 25 Hz stream processes every third frame and always the newest */
+  {
+    int64_t t_ready[10], busy[10];
+    uint8_t taken[10];
+    int i, n_taken;
+    for (i = 0; i < 10; ++i) { t_ready[i] = (int64_t)i * 40000000LL; busy[i] = 100000000LL; }
+    n_taken = ses3d_mailbox_replay(10, t_ready, busy, taken, NULL);
+    if (n_taken < 3 || n_taken > 5 || !taken[0] || !taken[9] || taken[1]) return 18;
+  }
+
   /* the compute path needs a GPU: without one the library must say so instead of computing on the CPU */
   rc = ses3d_create(4, cams, &prm, 0, &h);
   if (rc != SES3D_OK) {
@@ -95,6 +105,31 @@ int main(void) {
            out3d[0].keypoints[SES3D_FBP_NOSE].x, out3d[0].keypoints[SES3D_FBP_NOSE].y, out3d[0].keypoints[SES3D_FBP_NOSE].z,
            n2[0], n2[1], n2[2], n2[3]);
     if (n3 != 1 || n2[0] != 1) return 12;
+
+    /* the same call through the single-process multi-GPU entry (device list; here: every visible device) */
+    {
+      ses3d_multi m = NULL;
+      ses3d_person_cov m3d[8];
+      ses3d_person2d m2d[4 * 8];
+      int32_t mn3 = 0, mn2[4];
+      if (ses3d_create_multi(4, cams, &prm, 0, NULL, &m) != SES3D_OK) { printf("%s\n", ses3d_last_error_string()); return 19; }
+      const int32_t n_dev = ses3d_multi_device_count(m);
+      if (n_dev < 1) return 20;
+      rc = ses3d_multi_process_batch(m, 1, 2, persons, n_persons, 8, m3d, &mn3, m2d, mn2, NULL);
+      if (rc != SES3D_OK || mn3 != n3 || mn2[0] != n2[0] || memcmp(&m3d[0], &out3d[0], sizeof(m3d[0])) != 0) return 21;
+      ses3d_multi_destroy(m);
+      printf("multi: %d device(s), identical record\n", n_dev);
+    }
+    /* 2-D overlay of the reprojected skeletons of camera 0 (pose2D_plot_node.py) on a canvas of the camera's size */
+    {
+      static uint8_t rgb[720 * 1280 * 3];
+      int32_t n_img = n2[0];
+      int i, coloured = 0;
+      rc = ses3d_overlay_batch(h, 1, 8, out2d, &n_img, 1280, 720, rgb, SES3D_HOST_BUFFERS, NULL);
+      if (rc != SES3D_OK) { printf("%s\n", ses3d_last_error_string()); return 22; }
+      for (i = 0; i < 720 * 1280; ++i) coloured += (rgb[3 * i] != 255 || rgb[3 * i + 1] != 255 || rgb[3 * i + 2] != 255);
+      printf("overlay: %d coloured pixels\n", coloured);
+    }
 
     /* pose_prior: feed the same skeleton as 12 consecutive 30 Hz messages; it is published from the 11th on */
     {

@@ -9,7 +9,7 @@ The CUDA library (libses3d.so) is built with `python -m smartedgesensor3dhumanpo
 """
 from .layouts import default_params  # noqa: F401
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
 __all__ = ["GeometryPipeline", "Skeleton3D", "PoseReprojection", "PosePrior", "PriorTracker", "default_params"]
 
 

@@ -975,6 +975,6 @@ int ses3d_last_kernel_ms(ses3d_handle h, float ms[4]) {
 }
 
 const char* ses3d_last_error_string(void) { return g_last_error.c_str(); }
-const char* ses3d_version(void) { return "ses3d 0.1.0 (sm_100a)"; }
+const char* ses3d_version(void) { return "ses3d 0.2.0 (sm_100a)"; }
 
 }  // extern "C"

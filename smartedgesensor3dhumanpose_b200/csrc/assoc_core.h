@@ -164,8 +164,17 @@ SES_HD float epipolar_symmetric(const float* F, float x1, float y1, float x2, fl
 // cooperatively by a warp-sized team (lanes over rows / columns / entries):
 // every search of the reference ("first zero in this scan order") becomes a ballot + find-first-set over
 // the same index order, so primes, stars and covers - and therefore ties - resolve identically.
+#ifndef SES_COLD_MUNKRES
+#define SES_COLD_MUNKRES 0   // 1: the solver as an out-of-line function - measured slower on B200 (K2a + K2b 0.91 -> 1.11 ms
+                             // per 16384 hall frames, dense ring 1.47 -> 1.61); A/B switch for scripts/build_variants.py
+#endif
+#if SES_COLD_MUNKRES
+#define SES_MUNKRES_FN SES_HDN
+#else
+#define SES_MUNKRES_FN SES_HD
+#endif
 template <class WT>
-SES_HD void munkres_coop(WT& tm, const AssocWs& ws, const double* in, int n_r, int n_c, int* assignment) {
+SES_MUNKRES_FN void munkres_coop(WT& tm, const AssocWs& ws, const double* in, int n_r, int n_c, int* assignment) {
   const int n_e = n_r * n_c;
   double* dist = ws.dist;
   uint8_t *star = ws.star, *prime = ws.prime, *nstar = ws.nstar, *cov_r = ws.cov_r, *cov_c = ws.cov_c;
@@ -528,7 +537,10 @@ SES_HD void rounds_frame(Team& tm, const Tables& tb, int p_max, int h_cap, const
     });
     tm.single([&] { if (ws.scal[SC_AMBIG]) ++ws.scal[SC_N_HUNG]; });
     if (ws.scal[SC_AMBIG]) {  // S3D:628-634: full Munkres on the cost matrix
-      tm.warp0([&](auto& wt) { munkres_coop(wt, ws, ws.cost, n_hyp, n_det, ws.assignment); });
+      tm.warp0([&](auto& wt) {
+        const AssocWs wc = ws;   // a copy: an out-of-line solver must not make the workspace struct addressable
+        munkres_coop(wt, wc, wc.cost, n_hyp, n_det, wc.assignment);
+      });
     }
     tm.single([&] {
       for (int d = 0; d < n_det; ++d) ws.handled[d] = 0;

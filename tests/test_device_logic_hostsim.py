@@ -175,7 +175,8 @@ def test_reprojection_prefilter_is_exact_near_borders_and_behind_cameras():
         assert po["n_out"].sum() > 100
 
 
-@pytest.mark.parametrize("name,n_frames", [("cfg4_crowd64x20", 3), ("cfg2_hall16x6", 80), ("cfg3_hall16x6_dropout", 80)])
+@pytest.mark.parametrize("name,n_frames", [("cfg4_crowd64x20", 3), ("cfg2_hall16x6", 80), ("cfg3_hall16x6_dropout", 80),
+                                           ("dense_ring16x6", 30), ("cfg5_ring8x4", 80), ("cfg1_ring4x1", 60)])
 def test_big_rig_association_path_bit_exact(name, n_frames):
     """Rigs that do not fit shared memory keep the normalised keypoints in global scratch; every association index and
     record must be identical to the shared-memory path and to the oracle."""

@@ -207,8 +207,11 @@ SES_HD float ses_rcp(float x) {
 SES_HD double ses_rcp(double x) {
 #if defined(__CUDA_ARCH__)
   const double ax = fabs(x);
-  if (ax > 1e-30 && ax < 1e30) {
-    double y = (double)__frcp_rn((float)x);
+  if (ax > 1e-290 && ax < 1e290) {
+    // the double-precision SFU seed (MUFU.RCP64H, ~20 bits) instead of a round trip through float: the two F2F
+    // conversions were 11 % of the FP64 kernel's instructions
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     y = y * (2.0 - x * y);
     y = y * (2.0 - x * y);
     return y;
@@ -225,8 +228,9 @@ SES_HD float ses_rsqrt(float x) {
 }
 SES_HD double ses_rsqrt(double x) {
 #if defined(__CUDA_ARCH__)
-  if (x > 1e-30 && x < 1e30) {
-    double y = (double)rsqrtf((float)x);
+  if (x > 1e-290 && x < 1e290) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));   // MUFU.RSQ64H seed, refined below
     y = y * (1.5 - 0.5 * x * y * y);
     y = y * (1.5 - 0.5 * x * y * y);
     return y;

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -47,11 +48,16 @@ const char* last_error() { return g_last_error.c_str(); }
 }  // namespace ses3d
 namespace {
 
+// Bumped whenever a device buffer moves: captured single-frame graphs hold raw device addresses and are rebuilt
+// when the generation they were captured under is no longer current.
+std::atomic<uint64_t> g_alloc_gen{1};
+
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
   cudaError_t ensure(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
+    g_alloc_gen.fetch_add(1, std::memory_order_relaxed);
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
@@ -60,7 +66,11 @@ struct DevBuf {
     if (e == cudaSuccess) cap = want;
     return e;
   }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  void release() {
+    if (p) { cudaFree(p); g_alloc_gen.fetch_add(1, std::memory_order_relaxed); }
+    p = nullptr;
+    cap = 0;
+  }
   template <class T> T* as() const { return static_cast<T*>(p); }
 };
 
@@ -103,6 +113,29 @@ struct Slot {  // one in-flight chunk of a host-buffer call
 
 }  // namespace
 
+// Single-frame host calls (the ROS nodes: one message set per call) replay a captured CUDA graph: input copy,
+// the kernel chain, output copies and the overflow word in ONE launch, staged through pinned memory the handle owns.
+struct FrameGraph {
+  int p_max = 0, h_max = 0;
+  uint64_t alloc_gen = 0;        // g_alloc_gen at capture
+  cudaGraphExec_t exec = nullptr;
+  int n_kernels = 0;             // kernel launches one replay stands for
+  bool broken = false;           // capture failed once: stay on the eager path
+  // one contiguous record [persons | n_persons | 3-D | n_3d | overflow word | 2-D | n_2d] in pinned host memory and,
+  // mirrored, in device memory: one upload, one clear and one download per replay whatever the stage mask
+  unsigned char* pin = nullptr;
+  size_t pin_bytes = 0;
+  DevBuf dev;
+  void release() {
+    if (exec) cudaGraphExecDestroy(exec);
+    exec = nullptr;
+    dev.release();
+    if (pin) cudaFreeHost(pin);
+    pin = nullptr;
+    pin_bytes = 0;
+  }
+};
+
 struct ses3d_handle_s {
   int device = 0;
   ses3d_params prm;
@@ -133,6 +166,8 @@ struct ses3d_handle_s {
   bool profiling = false;
   float kernel_ms[4] = {0, 0, 0, 0};
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending_events;
+  FrameGraph fgraph[3];              // by stage mask - 1: triangulate, reproject, both
+  int frame_graph = 1;               // SES3D_FRAME_GRAPH=0: single-frame host calls take the eager path
 };
 
 namespace {
@@ -184,8 +219,9 @@ void resolve_events(ses3d_handle_s* h) {
 int triangulate_on_device(ses3d_handle_s* h, Scratch& sc, cudaStream_t st, int n_frames, int p_max, int h_max,
                           const ses3d_person2d* persons, const int32_t* n_persons, ses3d_person_cov* out,
                           int32_t* n_out, int32_t* hyp_of, int32_t* n_hyp_dump, int32_t* n_hung_dump,
-                          ses3d_person2d* out2d = nullptr, int32_t* n_out2d = nullptr) {
+                          ses3d_person2d* out2d = nullptr, int32_t* n_out2d = nullptr, int32_t* overflow = nullptr) {
   const int C = h->tb.n_cams;
+  if (!overflow) overflow = h->d_overflow.as<int32_t>();   // the handle's sticky flag unless the caller keeps its own
   bool need_nk = false;
   ses3d::associate_smem_bytes(C, p_max, h_max, &need_nk);
   const int dchunk = device_chunk(C, p_max);
@@ -211,7 +247,7 @@ int triangulate_on_device(ses3d_handle_s* h, Scratch& sc, cudaStream_t st, int n
       ProfScope ps(h, 0, st);
       CU(ses3d::launch_associate(h->cfg, h->tb, d, pin, nin, need_nk ? sc.nk.as<float>() : nullptr, sc.pairs.as<double>(),
                                  sc.meta.as<unsigned char>(), sc.hyp_det.as<int8_t>(),
-                                 n_hyp, n_hung, h->d_overflow.as<int32_t>(),
+                                 n_hyp, n_hung, overflow,
                                  hyp_of ? hyp_of + (size_t)f0 * C * p_max : nullptr, sc.keep.as<int32_t>(),
                                  sc.work.as<uint32_t>(), sc.work_count.as<int32_t>(), st));
     }
@@ -296,11 +332,226 @@ int host_chunk_frames(int n_frames) { return std::max(1, std::min(8192, std::max
 
 enum Stage { TRI = 1, REP = 2 };
 
+int run_batch_locked(ses3d_handle_s* h, int stages, int n_frames, int p_max, const ses3d_person2d* persons,
+                     const int32_t* n_persons, int h_max, ses3d_person_cov* io3d, int32_t* n_io3d, ses3d_person2d* out2d,
+                     int32_t* n_out2d, const ses3d_assoc_dump* dump, uint32_t flags, void* stream);
+
+// One chunk of a host-buffer call on its slot: zero the padded outputs, upload, the kernel chain, download. Everything
+// is asynchronous on the slot's stream (and therefore capturable into a graph once the slot's buffers are big enough).
+struct HostChunk {
+  const ses3d_person2d* persons = nullptr;
+  const int32_t* n_persons = nullptr;
+  ses3d_person_cov* io3d = nullptr;
+  int32_t* n_io3d = nullptr;
+  ses3d_person2d* out2d = nullptr;
+  int32_t* n_out2d = nullptr;
+  int32_t *hyp_of = nullptr, *n_hyp = nullptr, *n_hung = nullptr;
+};
+
+int enqueue_host_chunk(ses3d_handle_s* h, int stages, Slot& s, int nf, int p_max, int h_max, const HostChunk& hc) {
+  const int C = h->tb.n_cams;
+  cudaStream_t st = s.stream;
+  CU(s.out3d.ensure((size_t)nf * h_max * sizeof(ses3d_person_cov)));
+  CU(s.n_out3d.ensure((size_t)nf * 4));
+  // padded outputs travel whole: unused slots are zero, never stale device memory
+  if ((stages & TRI) && hc.io3d) CU(cudaMemsetAsync(s.out3d.p, 0, (size_t)nf * h_max * sizeof(ses3d_person_cov), st));
+  const bool fused = (stages & TRI) && (stages & REP);
+  if (stages & REP) {
+    CU(s.out2d.ensure((size_t)nf * C * h_max * sizeof(ses3d_person2d)));
+    CU(s.n_out2d.ensure((size_t)nf * C * 4));
+    CU(cudaMemsetAsync(s.out2d.p, 0, (size_t)nf * C * h_max * sizeof(ses3d_person2d), st));
+  }
+  if (stages & TRI) {
+    CU(s.persons.ensure((size_t)nf * C * p_max * sizeof(ses3d_person2d)));
+    CU(s.n_persons.ensure((size_t)nf * C * 4));
+    CU(cudaMemcpyAsync(s.persons.p, hc.persons, (size_t)nf * C * p_max * sizeof(ses3d_person2d), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(s.n_persons.p, hc.n_persons, (size_t)nf * C * 4, cudaMemcpyHostToDevice, st));
+    int32_t* d_hyp_of = nullptr;
+    if (hc.hyp_of) {
+      CU(s.hyp_of.ensure((size_t)nf * C * p_max * 4));
+      d_hyp_of = s.hyp_of.as<int32_t>();
+    }
+    int32_t *d_nhyp = nullptr, *d_nhung = nullptr;   // a host chunk may span several device chunks
+    if (hc.n_hyp) { CU(s.dump_nhyp.ensure((size_t)nf * 4)); d_nhyp = s.dump_nhyp.as<int32_t>(); }
+    if (hc.n_hung) { CU(s.dump_nhung.ensure((size_t)nf * 4)); d_nhung = s.dump_nhung.as<int32_t>(); }
+    int rc = triangulate_on_device(h, s.sc, st, nf, p_max, h_max, s.persons.as<ses3d_person2d>(),
+                                   s.n_persons.as<int32_t>(), s.out3d.as<ses3d_person_cov>(),
+                                   s.n_out3d.as<int32_t>(), d_hyp_of, d_nhyp, d_nhung,
+                                   fused ? s.out2d.as<ses3d_person2d>() : nullptr,
+                                   fused ? s.n_out2d.as<int32_t>() : nullptr);
+    if (rc) return rc;
+    if (hc.io3d) CU(cudaMemcpyAsync(hc.io3d, s.out3d.p, (size_t)nf * h_max * sizeof(ses3d_person_cov), cudaMemcpyDeviceToHost, st));
+    if (hc.n_io3d) CU(cudaMemcpyAsync(hc.n_io3d, s.n_out3d.p, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
+    if (hc.hyp_of) CU(cudaMemcpyAsync(hc.hyp_of, d_hyp_of, (size_t)nf * C * p_max * 4, cudaMemcpyDeviceToHost, st));
+    if (hc.n_hyp) CU(cudaMemcpyAsync(hc.n_hyp, d_nhyp, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
+    if (hc.n_hung) CU(cudaMemcpyAsync(hc.n_hung, d_nhung, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
+  } else {
+    CU(cudaMemcpyAsync(s.out3d.p, hc.io3d, (size_t)nf * h_max * sizeof(ses3d_person_cov), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(s.n_out3d.p, hc.n_io3d, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+  }
+  if (stages & REP) {
+    if (!fused) {
+      int rc = reproject_on_device(h, st, nf, h_max, s.out3d.as<ses3d_person_cov>(), s.n_out3d.as<int32_t>(),
+                                   s.out2d.as<ses3d_person2d>(), s.n_out2d.as<int32_t>());
+      if (rc) return rc;
+    }
+    CU(cudaMemcpyAsync(hc.out2d, s.out2d.p, (size_t)nf * C * h_max * sizeof(ses3d_person2d), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hc.n_out2d, s.n_out2d.p, (size_t)nf * C * 4, cudaMemcpyDeviceToHost, st));
+  }
+  return SES3D_OK;
+}
+
+// Single-frame host call through a captured graph. *done = false means "not handled, take the eager path" (first
+// call of a shape: the eager path sizes the slot's scratch, the graph is captured right after it for the next call).
+struct FrameStage {   // byte offsets into FrameGraph::pin / FrameGraph::dev
+  size_t persons, n_persons, io3d, n_io3d, flag, out2d, n_out2d, total;
+};
+FrameStage frame_stage_layout(int C, int p_max, int h_max) {
+  FrameStage o;
+  size_t at = 0;
+  auto take = [&at](size_t bytes) { const size_t r = at; at += (bytes + 255) & ~(size_t)255; return r; };
+  o.persons = take((size_t)C * p_max * sizeof(ses3d_person2d));
+  o.n_persons = take((size_t)C * 4);
+  o.io3d = take((size_t)h_max * sizeof(ses3d_person_cov));
+  o.n_io3d = take(4);
+  o.flag = take(8);
+  o.out2d = take((size_t)C * h_max * sizeof(ses3d_person2d));
+  o.n_out2d = take((size_t)C * 4);
+  o.total = at;
+  return o;
+}
+
+int capture_frame_graph(ses3d_handle_s* h, int stages, int p_max, int h_max) {
+  FrameGraph& g = h->fgraph[stages - 1];
+  if (g.broken) return SES3D_OK;
+  const int C = h->tb.n_cams;
+  const FrameStage o = frame_stage_layout(C, p_max, h_max);
+  if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+  if (g.pin_bytes < o.total) {
+    if (g.pin) cudaFreeHost(g.pin);
+    g.pin = nullptr;
+    g.pin_bytes = 0;
+    if (cudaMallocHost(reinterpret_cast<void**>(&g.pin), o.total) != cudaSuccess) {
+      cudaGetLastError();
+      g.broken = true;
+      return SES3D_OK;
+    }
+    g.pin_bytes = o.total;
+  }
+  if (g.dev.ensure(o.total) != cudaSuccess) {
+    cudaGetLastError();
+    g.broken = true;
+    return SES3D_OK;
+  }
+  Slot& s = h->slot[0];
+  cudaStream_t st = s.stream;
+  unsigned char* d = g.dev.as<unsigned char>();
+  auto at = [d](size_t off) { return d + off; };
+  const uint64_t gen0 = g_alloc_gen.load(std::memory_order_relaxed);
+  const int64_t launches0 = h->launches;
+  const std::string err0 = g_last_error;
+  const bool tri = (stages & TRI) != 0, rep = (stages & REP) != 0;
+  // upload [up0, up1), clear [z0, z1), download [dn0, dn1)
+  const size_t up0 = tri ? o.persons : o.io3d, up1 = tri ? o.io3d : o.out2d;   // reproject alone: 3-D + count + zero flag
+  const size_t z0 = tri ? o.io3d : o.out2d, z1 = rep ? o.total : o.out2d;
+  const size_t dn0 = z0, dn1 = z1;
+  cudaGraph_t graph = nullptr;
+  bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+  if (ok) {
+    ok = cudaMemsetAsync(at(z0), 0, z1 - z0, st) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(at(up0), g.pin + up0, up1 - up0, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    if (ok && tri)
+      ok = triangulate_on_device(h, s.sc, st, 1, p_max, h_max, reinterpret_cast<const ses3d_person2d*>(at(o.persons)),
+                                 reinterpret_cast<const int32_t*>(at(o.n_persons)),
+                                 reinterpret_cast<ses3d_person_cov*>(at(o.io3d)), reinterpret_cast<int32_t*>(at(o.n_io3d)),
+                                 nullptr, nullptr, nullptr, rep ? reinterpret_cast<ses3d_person2d*>(at(o.out2d)) : nullptr,
+                                 rep ? reinterpret_cast<int32_t*>(at(o.n_out2d)) : nullptr,
+                                 reinterpret_cast<int32_t*>(at(o.flag))) == SES3D_OK;
+    if (ok && rep && !tri)
+      ok = reproject_on_device(h, st, 1, h_max, reinterpret_cast<const ses3d_person_cov*>(at(o.io3d)),
+                               reinterpret_cast<const int32_t*>(at(o.n_io3d)),
+                               reinterpret_cast<ses3d_person2d*>(at(o.out2d)),
+                               reinterpret_cast<int32_t*>(at(o.n_out2d))) == SES3D_OK;
+    ok = ok && cudaMemcpyAsync(g.pin + dn0, at(dn0), dn1 - dn0, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    const cudaError_t ee = cudaStreamEndCapture(st, &graph);   // always ends the capture, also after a failure
+    ok = ok && ee == cudaSuccess && graph != nullptr;
+  }
+  g.n_kernels = (int)(h->launches - launches0);
+  h->launches = launches0;   // nothing ran
+  ok = ok && g_alloc_gen.load(std::memory_order_relaxed) == gen0;   // a buffer moved: the eager call had not sized it
+  if (ok) ok = cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess;
+  if (graph) cudaGraphDestroy(graph);
+  if (!ok) {
+    cudaGetLastError();
+    g_last_error = err0;
+    if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+    g.broken = true;
+    return SES3D_OK;
+  }
+  g.p_max = p_max;
+  g.h_max = h_max;
+  g.alloc_gen = gen0;
+  return SES3D_OK;
+}
+
+int run_frame_graph(ses3d_handle_s* h, int stages, int p_max, int h_max, const ses3d_person2d* persons,
+                    const int32_t* n_persons, ses3d_person_cov* io3d, int32_t* n_io3d, ses3d_person2d* out2d,
+                    int32_t* n_out2d, bool* done) {
+  *done = false;
+  FrameGraph& g = h->fgraph[stages - 1];
+  if (g.broken) return SES3D_OK;
+  const int C = h->tb.n_cams;
+  const bool hit = g.exec && g.p_max == p_max && g.h_max == h_max &&
+                   g.alloc_gen == g_alloc_gen.load(std::memory_order_relaxed);
+  if (!hit) {
+    // eager call now (sizes the buffers, produces this call's results), capture for the next one
+    h->frame_graph = 0;
+    const int rc = run_batch_locked(h, stages, 1, p_max, persons, n_persons, h_max, io3d, n_io3d, out2d, n_out2d, nullptr, 0,
+                                    nullptr);
+    h->frame_graph = 1;
+    *done = true;
+    if (rc) return rc;
+    return capture_frame_graph(h, stages, p_max, h_max);
+  }
+  const FrameStage o = frame_stage_layout(C, p_max, h_max);
+  Slot& s = h->slot[0];
+  if (stages & TRI) {
+    std::memcpy(g.pin + o.persons, persons, (size_t)C * p_max * sizeof(ses3d_person2d));
+    std::memcpy(g.pin + o.n_persons, n_persons, (size_t)C * 4);
+  } else {
+    std::memcpy(g.pin + o.io3d, io3d, (size_t)h_max * sizeof(ses3d_person_cov));
+    std::memcpy(g.pin + o.n_io3d, n_io3d, 4);
+  }
+  *reinterpret_cast<long long*>(g.pin + o.flag) = 0;
+  CU(order_after_device_work(h, s.stream));
+  CU(cudaGraphLaunch(g.exec, s.stream));
+  h->launches += g.n_kernels;
+  CU(cudaStreamSynchronize(s.stream));
+  *done = true;
+  if (*reinterpret_cast<const int32_t*>(g.pin + o.flag)) return overflow_error(h);
+  if (stages & TRI) {
+    if (io3d) std::memcpy(io3d, g.pin + o.io3d, (size_t)h_max * sizeof(ses3d_person_cov));
+    if (n_io3d) std::memcpy(n_io3d, g.pin + o.n_io3d, 4);
+  }
+  if (stages & REP) {
+    std::memcpy(out2d, g.pin + o.out2d, (size_t)C * h_max * sizeof(ses3d_person2d));
+    std::memcpy(n_out2d, g.pin + o.n_out2d, (size_t)C * 4);
+  }
+  return SES3D_OK;
+}
+
 // Shared implementation of the three batch entry points.
 int run_batch(ses3d_handle_s* h, int stages, int n_frames, int p_max, const ses3d_person2d* persons,
               const int32_t* n_persons, int h_max, ses3d_person_cov* io3d, int32_t* n_io3d, ses3d_person2d* out2d,
               int32_t* n_out2d, const ses3d_assoc_dump* dump, uint32_t flags, void* stream) {
   std::lock_guard<std::mutex> lock(h->mu);
+  return run_batch_locked(h, stages, n_frames, p_max, persons, n_persons, h_max, io3d, n_io3d, out2d, n_out2d, dump, flags,
+                          stream);
+}
+
+int run_batch_locked(ses3d_handle_s* h, int stages, int n_frames, int p_max, const ses3d_person2d* persons,
+                     const int32_t* n_persons, int h_max, ses3d_person_cov* io3d, int32_t* n_io3d, ses3d_person2d* out2d,
+                     int32_t* n_out2d, const ses3d_assoc_dump* dump, uint32_t flags, void* stream) {
   CU(cudaSetDevice(h->device));
   const int C = h->tb.n_cams;
   if (n_frames == 0) return SES3D_OK;
@@ -373,66 +624,30 @@ int run_batch(ses3d_handle_s* h, int stages, int n_frames, int p_max, const ses3
     return SES3D_OK;   // stream-ordered: no host synchronisation (ses3d_check / the next call report an overflow)
   }
 
-  // host buffers: stream chunks through the slots
+  // host buffers
+  if (n_frames == 1 && !dump && !h->profiling && h->frame_graph) {
+    bool done = false;
+    const int rc = run_frame_graph(h, stages, p_max, h_max, persons, n_persons, io3d, n_io3d, out2d, n_out2d, &done);
+    if (rc || done) return rc;
+  }
+  // stream chunks through the slots
   for (Slot& sl : h->slot) CU(order_after_device_work(h, sl.stream));
   const int chunk = host_chunk_frames(n_frames);
   int ci = 0;
   for (int f0 = 0; f0 < n_frames; f0 += chunk, ++ci) {
     const int nf = std::min(chunk, n_frames - f0);
-    Slot& s = h->slot[ci % ses3d_handle_s::kSlots];
-    cudaStream_t st = s.stream;
-    CU(s.out3d.ensure((size_t)nf * h_max * sizeof(ses3d_person_cov)));
-    CU(s.n_out3d.ensure((size_t)nf * 4));
-    // padded outputs travel whole: unused slots are zero, never stale device memory
-    if ((stages & TRI) && io3d) CU(cudaMemsetAsync(s.out3d.p, 0, (size_t)nf * h_max * sizeof(ses3d_person_cov), st));
-    const bool fused = (stages & TRI) && (stages & REP);
-    if (stages & REP) {
-      CU(s.out2d.ensure((size_t)nf * C * h_max * sizeof(ses3d_person2d)));
-      CU(s.n_out2d.ensure((size_t)nf * C * 4));
-      CU(cudaMemsetAsync(s.out2d.p, 0, (size_t)nf * C * h_max * sizeof(ses3d_person2d), st));
-    }
-    if (stages & TRI) {
-      CU(s.persons.ensure((size_t)nf * C * p_max * sizeof(ses3d_person2d)));
-      CU(s.n_persons.ensure((size_t)nf * C * 4));
-      CU(cudaMemcpyAsync(s.persons.p, persons + (size_t)f0 * C * p_max, (size_t)nf * C * p_max * sizeof(ses3d_person2d),
-                         cudaMemcpyHostToDevice, st));
-      CU(cudaMemcpyAsync(s.n_persons.p, n_persons + (size_t)f0 * C, (size_t)nf * C * 4, cudaMemcpyHostToDevice, st));
-      int32_t* d_hyp_of = nullptr;
-      if (hyp_of) {
-        CU(s.hyp_of.ensure((size_t)nf * C * p_max * 4));
-        d_hyp_of = s.hyp_of.as<int32_t>();
-      }
-      int32_t *d_nhyp = nullptr, *d_nhung = nullptr;   // a host chunk may span several device chunks
-      if (n_hyp_d) { CU(s.dump_nhyp.ensure((size_t)nf * 4)); d_nhyp = s.dump_nhyp.as<int32_t>(); }
-      if (n_hung_d) { CU(s.dump_nhung.ensure((size_t)nf * 4)); d_nhung = s.dump_nhung.as<int32_t>(); }
-      int rc = triangulate_on_device(h, s.sc, st, nf, p_max, h_max, s.persons.as<ses3d_person2d>(),
-                                     s.n_persons.as<int32_t>(), s.out3d.as<ses3d_person_cov>(),
-                                     s.n_out3d.as<int32_t>(), d_hyp_of, d_nhyp, d_nhung,
-                                     fused ? s.out2d.as<ses3d_person2d>() : nullptr,
-                                     fused ? s.n_out2d.as<int32_t>() : nullptr);
-      if (rc) return rc;
-      if (io3d) CU(cudaMemcpyAsync(io3d + (size_t)f0 * h_max, s.out3d.p, (size_t)nf * h_max * sizeof(ses3d_person_cov),
-                                   cudaMemcpyDeviceToHost, st));
-      if (n_io3d) CU(cudaMemcpyAsync(n_io3d + f0, s.n_out3d.p, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
-      if (hyp_of) CU(cudaMemcpyAsync(hyp_of + (size_t)f0 * C * p_max, d_hyp_of, (size_t)nf * C * p_max * 4,
-                                     cudaMemcpyDeviceToHost, st));
-      if (n_hyp_d) CU(cudaMemcpyAsync(n_hyp_d + f0, d_nhyp, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
-      if (n_hung_d) CU(cudaMemcpyAsync(n_hung_d + f0, d_nhung, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
-    } else {
-      CU(cudaMemcpyAsync(s.out3d.p, io3d + (size_t)f0 * h_max, (size_t)nf * h_max * sizeof(ses3d_person_cov),
-                         cudaMemcpyHostToDevice, st));
-      CU(cudaMemcpyAsync(s.n_out3d.p, n_io3d + f0, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
-    }
-    if (stages & REP) {
-      if (!fused) {
-        int rc = reproject_on_device(h, st, nf, h_max, s.out3d.as<ses3d_person_cov>(), s.n_out3d.as<int32_t>(),
-                                     s.out2d.as<ses3d_person2d>(), s.n_out2d.as<int32_t>());
-        if (rc) return rc;
-      }
-      CU(cudaMemcpyAsync(out2d + (size_t)f0 * C * h_max, s.out2d.p, (size_t)nf * C * h_max * sizeof(ses3d_person2d),
-                         cudaMemcpyDeviceToHost, st));
-      CU(cudaMemcpyAsync(n_out2d + (size_t)f0 * C, s.n_out2d.p, (size_t)nf * C * 4, cudaMemcpyDeviceToHost, st));
-    }
+    HostChunk hc;
+    hc.persons = persons ? persons + (size_t)f0 * C * p_max : nullptr;
+    hc.n_persons = n_persons ? n_persons + (size_t)f0 * C : nullptr;
+    hc.io3d = io3d ? io3d + (size_t)f0 * h_max : nullptr;
+    hc.n_io3d = n_io3d ? n_io3d + f0 : nullptr;
+    hc.out2d = out2d ? out2d + (size_t)f0 * C * h_max : nullptr;
+    hc.n_out2d = n_out2d ? n_out2d + (size_t)f0 * C : nullptr;
+    hc.hyp_of = hyp_of ? hyp_of + (size_t)f0 * C * p_max : nullptr;
+    hc.n_hyp = n_hyp_d ? n_hyp_d + f0 : nullptr;
+    hc.n_hung = n_hung_d ? n_hung_d + f0 : nullptr;
+    const int rc = enqueue_host_chunk(h, stages, h->slot[ci % ses3d_handle_s::kSlots], nf, p_max, h_max, hc);
+    if (rc) return rc;
   }
   // the sticky overflow flag rides at the end of every used stream (pinned word per slot): no extra blocking copy
   const int used = std::min(ci, (int)ses3d_handle_s::kSlots);
@@ -732,6 +947,7 @@ int ses3d_create(int32_t n_cams, const ses3d_camera* cams, const ses3d_params* p
   if (const char* env = getenv("SES3D_DEVICE_SPLIT")) h->device_split = std::max(1, atoi(env));
   if (const char* env = getenv("SES3D_RAGGED_CHUNK")) h->ragged_chunk_env = std::max(1, atoi(env));
   if (const char* env = getenv("SES3D_RAGGED_DIRECT")) h->ragged_direct = atoi(env);
+  if (const char* env = getenv("SES3D_FRAME_GRAPH")) h->frame_graph = atoi(env);
   if (ue != cudaSuccess) {
     ses3d_destroy(h);
     return cuda_fail(ue, "ses3d_create upload");
@@ -752,6 +968,7 @@ int ses3d_create(int32_t n_cams, const ses3d_camera* cams, const ses3d_params* p
 int ses3d_destroy(ses3d_handle h) {
   if (!h) return SES3D_OK;
   cudaSetDevice(h->device);
+  for (FrameGraph& g : h->fgraph) g.release();
   for (Slot& s : h->slot) s.release();
   if (h->fork_ev) cudaEventDestroy(h->fork_ev);
   if (h->dev_done) { cudaEventSynchronize(h->dev_done); cudaEventDestroy(h->dev_done); }

@@ -220,6 +220,8 @@ cudaError_t init_kernels(LaunchCfg* cfg, int device) {
   cfg->pairs_tiled = env_int("SES3D_PAIRS_TILED", 0);
   cfg->rounds_block = env_int("SES3D_ROUNDS_BLOCK", -1);
   cfg->pairs_split = env_int("SES3D_PAIRS_SPLIT", 0);
+  cfg->latency_frames = env_int("SES3D_LATENCY_FRAMES", -1);
+  if (cfg->latency_frames < 0) cfg->latency_frames = cfg->n_sm;
   const int budget = (int)kSmemBudget;
   if ((e = cudaFuncSetAttribute(k_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_rounds<ROUNDS_WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget)) != cudaSuccess) return e;
@@ -261,6 +263,11 @@ cudaError_t launch_associate(const LaunchCfg& cfg, const Tables& tb, LaunchDims 
   if (cfg.pairs_split > 0) n_parts = cfg.pairs_split;
   // B200, 64 x 20 crowd, 512 frames (K2a + K2b ms): 1 slice 34.3, 2: 31.2, 4: 27.4, 8: 26.6, 16: 26.6
   else if (scratch && tile_warps == 0) n_parts = std::max(1, std::min(16, (28 * cfg.n_sm + d.n_frames - 1) / d.n_frames));
+  // a handful of frames (the per-message calls of the ROS nodes): slices of ~256 pairs, one pair per thread
+  else if (tile_warps == 0 && cfg.latency_frames > 0 && d.n_frames * 16 <= cfg.latency_frames) {
+    const int n = tb.n_cams * d.p_max;
+    n_parts = std::max(1, std::min(16, n * (n - 1) / 2 / 256));
+  }
   if (tile_warps > 0) n_parts = 1;   // the dense instance reads the meta record slice 0 of the first instance wrote
   k_pairs<<<d.n_frames * n_parts, threads, smem, st>>>(tb, d.n_frames, d.p_max, persons, n_persons,
                                                        scratch ? nk_scratch : nullptr, pair_table, meta, meta_stride, 0,
@@ -302,8 +309,11 @@ cudaError_t launch_finalize(const Tables& tb, LaunchDims d, const int32_t* n_hyp
 // Cameras are dealt round-robin to the CTA's warps, s_cap persons per batch. B200, hall16 x 6, ms per 16384 frames
 // (fused with finalize): 4 warps 1.41, 8 warps 1.77, 16 warps (one per camera, 1 CTA / SM at 128 registers) 3.97 -
 // the FP64 projection needs ~96 registers, so small CTAs keep more warps resident.
-static void reproject_config(const LaunchCfg& cfg, const Tables& tb, int h_max, int* threads, int* s_cap, size_t* smem) {
+static void reproject_config(const LaunchCfg& cfg, const Tables& tb, int n_frames, int h_max, int* threads, int* s_cap,
+                             size_t* smem) {
   int warps = cfg.reproj_threads > 0 ? cfg.reproj_threads / 32 : std::min(tb.n_cams, 16);
+  // fewer frames than SMs: occupancy is irrelevant, one warp per camera shortens the frame's critical path
+  if (cfg.latency_frames > 0 && n_frames <= cfg.latency_frames) warps = std::min(tb.n_cams, 16);
   warps = std::max(1, std::min(warps, std::min(tb.n_cams, 16)));   // __launch_bounds__(512)
   *threads = 32 * warps;
   *s_cap = reproj_s_cap(tb.n_cams, h_max, cfg.reproj_scap);
@@ -315,7 +325,7 @@ cudaError_t launch_finproj(const LaunchCfg& cfg, const Tables& tb, LaunchDims d,
                            ses3d_person2d* out2d, int32_t* n_out2d, cudaStream_t st) {
   int threads, s_cap;
   size_t smem;
-  reproject_config(cfg, tb, d.h_cap, &threads, &s_cap, &smem);
+  reproject_config(cfg, tb, d.n_frames, d.h_cap, &threads, &s_cap, &smem);
   smem = std::max(smem, fin_ws_bytes(d.h_cap));
   if (smem > kSmemBudget) return cudaErrorInvalidConfiguration;
 #define SES_FP(T_, B_) k_finproj<T_, B_><<<d.n_frames, threads, smem, st>>>(tb, d.n_frames, d.h_cap, s_cap, n_hyp, tmp, keep, \
@@ -332,7 +342,7 @@ cudaError_t launch_reproject(const LaunchCfg& cfg, const Tables& tb, int n_frame
                              int32_t* n_out, cudaStream_t st) {
   int threads, s_cap;
   size_t smem;
-  reproject_config(cfg, tb, h_max, &threads, &s_cap, &smem);
+  reproject_config(cfg, tb, n_frames, h_max, &threads, &s_cap, &smem);
   if (smem > kSmemBudget) return cudaErrorInvalidConfiguration;
   if (threads <= 128) k_reproject<128, 5><<<n_frames, threads, smem, st>>>(tb, n_frames, h_max, s_cap, persons3d, n_persons3d, out, n_out);
   else if (threads <= 256) k_reproject<256, 3><<<n_frames, threads, smem, st>>>(tb, n_frames, h_max, s_cap, persons3d, n_persons3d, out, n_out);

@@ -26,6 +26,7 @@ struct LaunchCfg {
   int tri_dynamic = 1;         // K3 hands work items out one by one (0: fixed strides)
   int pairs_tiled = 0;         // K2a: dense frames build their pair table by camera-pair tiles (second k_pairs instance);
                                // measured SLOWER than the flat pass on every rig (crowd 49 vs 30 ms), kept for A/B only
+  int latency_frames = 0;      // launches of at most this many frames use the low-latency shapes (default: SM count)
   int pairs_split = 0;         // K2a: CTAs per frame (0 = automatic: > 1 only for big rigs with few frames per launch)
   int rounds_block = -1;       // K2b: CTA per frame instead of warp per frame (-1 = automatic: heavy, few frames)
   int tri_lockstep = 1;        // K3: the warps of a CTA pass the phases of their hypotheses together (I-cache sharing)

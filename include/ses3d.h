@@ -150,7 +150,10 @@ int ses3d_get_tables(ses3d_handle h, float* P, float* F);
  * detections is not an error (n_out = 0, S3D:557-560).
  * stream: a cudaStream_t cast to void*, used by device-buffer calls only. NULL means the legacy default stream
  * (stream 0), exactly as a NULL cudaStream_t does in the CUDA runtime.
- * Host-buffer calls are synchronous. Device-buffer calls are STREAM-ORDERED: the kernels are enqueued on `stream`
+ * Host-buffer calls are synchronous. A host-buffer call with n_frames = 1 and no association dump (the per-message
+ * call of the ROS nodes) replays a CUDA graph the handle captured on the previous call of the same shape: one launch
+ * for upload, kernels and download; results are identical to the batched call (SES3D_FRAME_GRAPH=0 disables it).
+ * Device-buffer calls are STREAM-ORDERED: the kernels are enqueued on `stream`
  * and the call returns without waiting, so the caller can enqueue the next batch, or its own consumers, behind
  * it. A capacity overflow (more hypotheses than h_max in some frame) of such a call is reported by ses3d_check()
  * or by the next batch call on the handle, whichever comes first. One handle owns one set of device scratch: calls

@@ -90,6 +90,12 @@ struct ses3d_prior_s {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int ragged_chunk_env = 0;       // SES3D_PRIOR_RAGGED_CHUNK, read at create
+  // streaming calls (a few messages, the ROS node): one contiguous record [inputs | outputs | stream states] in pinned
+  // host memory and its mirror on the device - one upload, one clear, one download instead of a dozen small copies
+  Buf small_dev;
+  unsigned char* small_pin = nullptr;
+  size_t small_pin_bytes = 0;
+  int small_msgs = 4;             // SES3D_PRIOR_SMALL_MSGS: calls of at most this many messages take that path (0 = off)
   bool dev_run_pending = false;   // a device-buffer run was enqueued on a caller's stream; ev1 marks its end
   float last_ms = 0.f;
   int64_t launches = 0;
@@ -155,6 +161,7 @@ int ses3d_prior_create(const ses3d_prior_params* params, int32_t n_sequences, in
   ses3d_prior_s* h = new ses3d_prior_s;
   h->device = device;
   if (const char* env = getenv("SES3D_PRIOR_RAGGED_CHUNK")) h->ragged_chunk_env = atoi(env);
+  if (const char* env = getenv("SES3D_PRIOR_SMALL_MSGS")) h->small_msgs = std::max(0, atoi(env));
   h->n_sequences = n_sequences;
   h->max_tracks = max_tracks;
   h->pt.prm = prm;
@@ -188,6 +195,8 @@ int ses3d_prior_destroy(ses3d_prior h) {
                  &h->out_pred, &h->out_n, &h->out_delay, &h->out_track})
     b->release();
   for (PriorSlot& sl : h->rs) sl.release();
+  h->small_dev.release();
+  if (h->small_pin) cudaFreeHost(h->small_pin);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -245,6 +254,54 @@ int ses3d_prior_run(ses3d_prior h, int32_t n_sequences, int32_t n_frames, int32_
     return SES3D_OK;
   }
 
+  if (h->small_msgs > 0 && n_msg <= (size_t)h->small_msgs) {
+    size_t at = 0;
+    auto take = [&at](size_t bytes) { const size_t r = at; at += (bytes + 255) & ~(size_t)255; return r; };
+    const size_t i_persons = take(rec), i_n = take(4 * n_msg), i_stamp = take(8 * n_msg),
+                 i_delay = take(4 * n_msg * (size_t)std::max(n_cams, 1));
+    const size_t o_fused = take(rec), o_pred = take(rec), o_n = take(4 * n_msg), o_delay = take(4 * n_msg),
+                 o_track = take(4 * n_msg * h_max), o_end = at;
+    const size_t st_bytes = sizeof(ses3d::PriorSeqState) * (size_t)n_sequences;
+    const size_t p_states = take(st_bytes);   // host side only: the stream states live in their own device buffer
+    if (h->small_pin_bytes < at) {
+      if (h->small_pin) cudaFreeHost(h->small_pin);
+      h->small_pin = nullptr;
+      h->small_pin_bytes = 0;
+      CU(cudaMallocHost(reinterpret_cast<void**>(&h->small_pin), at));
+      h->small_pin_bytes = at;
+    }
+    CU(h->small_dev.ensure(o_end));
+    unsigned char* pin = h->small_pin;
+    unsigned char* dv = h->small_dev.as<unsigned char>();
+    std::memcpy(pin + i_persons, persons, rec);
+    std::memcpy(pin + i_n, n_persons, 4 * n_msg);
+    std::memcpy(pin + i_stamp, stamp_ns, 8 * n_msg);
+    if (n_cams > 0) std::memcpy(pin + i_delay, fb_delay, 4 * n_msg * n_cams);
+    CU(cudaMemcpyAsync(dv, pin, o_fused, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(dv + o_fused, 0, o_end - o_fused, st));   // unpublished slots of the outputs read as zero records
+    CU(cudaEventRecord(h->ev0, st));
+    CU(ses3d::launch_prior(h->pt, n_sequences, n_frames, h_max, h->max_tracks, states, tracks, order,
+                           reinterpret_cast<const ses3d_person_cov*>(dv + i_persons),
+                           reinterpret_cast<const int32_t*>(dv + i_n), reinterpret_cast<const int64_t*>(dv + i_stamp), n_cams,
+                           n_cams > 0 ? reinterpret_cast<const float*>(dv + i_delay) : nullptr,
+                           reinterpret_cast<ses3d_person_cov*>(dv + o_fused), reinterpret_cast<ses3d_person_cov*>(dv + o_pred),
+                           reinterpret_cast<int32_t*>(dv + o_n), reinterpret_cast<float*>(dv + o_delay),
+                           track_of ? reinterpret_cast<int32_t*>(dv + o_track) : nullptr, st));
+    CU(cudaEventRecord(h->ev1, st));
+    ++h->launches;
+    CU(cudaMemcpyAsync(pin + o_fused, dv + o_fused, o_end - o_fused, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(pin + p_states, states, st_bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    std::memcpy(fused, pin + o_fused, rec);
+    std::memcpy(pred, pin + o_pred, rec);
+    std::memcpy(n_out, pin + o_n, 4 * n_msg);
+    if (pred_delay) std::memcpy(pred_delay, pin + o_delay, 4 * n_msg);
+    if (track_of) std::memcpy(track_of, pin + o_track, 4 * n_msg * h_max);
+    const auto* hs = reinterpret_cast<const ses3d::PriorSeqState*>(pin + p_states);
+    for (int i = 0; i < n_sequences; ++i)
+      if (hs[i].overflow) return ses3d::set_error(SES3D_E_CAPACITY, "ses3d_prior_run: a stream needed more than max_tracks tracks");
+    return SES3D_OK;
+  }
   CU(h->in_persons.ensure(rec));
   CU(h->in_n.ensure(4 * n_msg));
   CU(h->in_stamp.ensure(8 * n_msg));

@@ -92,11 +92,12 @@ struct Slot {  // one in-flight chunk of a host-buffer call
   // ragged host calls: the upload of a chunk runs on its own stream so that it only waits for the kernels that read
   // the slot's input buffers last (kern_done), not for the download of that older chunk's results
   cudaStream_t up = nullptr;
-  cudaEvent_t up_done = nullptr, kern_done = nullptr;
+  cudaEvent_t up_done = nullptr, kern_done = nullptr, down_done = nullptr;
   void release() {
     if (up_done) cudaEventDestroy(up_done);
     if (kern_done) cudaEventDestroy(kern_done);
-    up_done = kern_done = nullptr;
+    if (down_done) cudaEventDestroy(down_done);
+    up_done = kern_done = down_done = nullptr;
     if (up) cudaStreamDestroy(up);
     up = nullptr;
     sc.release(); persons.release(); n_persons.release(); out3d.release(); n_out3d.release(); out2d.release();
@@ -152,6 +153,13 @@ struct ses3d_handle_s {
   // device memory; 1 = also into pinned host memory (posted PCIe writes from the SMs: measured 17.0 ms against 10.6 ms
   // for the copy-engine path per 16 384 frames of hall16 x 6, profiles/r02_e2e_timeline.json); 0 = always stage
   int ragged_direct = -1;
+  // Ragged host calls: all uploads share one stream and all result downloads another (one copy per direction in
+  // flight; the slot streams carry the kernels). B200, 16 384 frames of hall16 x 6, two boxes: 10.11 / 10.39 ms with
+  // per-slot copy streams and 1024-frame chunks, 9.86 / ~10.1 ms with shared copy streams and 1536-frame chunks
+  int ragged_one_down = 1;           // SES3D_RAGGED_ONE_DOWN=0: downloads on the slot streams
+  cudaStream_t down = nullptr;
+  int ragged_one_up = 1;             // SES3D_RAGGED_ONE_UP=0: uploads on the slots' own upload streams
+  int ragged_slots = kSlots;         // SES3D_RAGGED_SLOTS: chunks in flight of a ragged host call (2..kSlots)
   // ragged calls: running output totals {3-D records, 2-D records} live on the device and are carried from chunk to
   // chunk by the scan kernels; scan_ev orders the scans of consecutive chunks across the slot streams
   DevBuf d_run;
@@ -734,8 +742,8 @@ int run_ragged_impl(ses3d_handle_s* h, int n_frames, int p_max, const ses3d_pers
   void *d3 = out3d, *d2 = out2d;
   bool direct = dev ? h->ragged_direct != 0 : h->ragged_direct > 0;
   if (direct && !dev) direct = device_accessible(out3d, &d3) && device_accessible(out2d, &d2);
-  // B200, 16384 frames of hall16 x 6 (ms per call): chunk 1024 -> 10.2, 1536 -> 10.3, 2048 -> 10.4, 3072 -> 10.8
-  int chunk = std::max(1, std::min(4096, std::max(512, (n_frames + 15) / 16)));
+  // B200, 16384 frames of hall16 x 6 (ms per call, shared copy streams): chunk 768 -> 10.1, 1536 -> 9.86, 2048 -> 10.3
+  int chunk = std::max(1, std::min(4096, std::max(512, (n_frames * 3 + 31) / 32)));
   if (h->ragged_chunk_env > 0) chunk = h->ragged_chunk_env;
   long long in_done = 0, run3 = 0, run2 = 0;
   // staged mode: chunks whose kernels are enqueued but whose packed results have not been sent home yet (oldest first)
@@ -748,8 +756,14 @@ int run_ragged_impl(ses3d_handle_s* h, int n_frames, int p_max, const ses3d_pers
     CU(cudaEventSynchronize(s.done));
     const long long t3 = s.totals[0], t2 = s.totals[1];
     if (run3 + t3 > cap3d || run2 + t2 > cap2d) return fail(SES3D_E_CAPACITY, "ragged output buffer too small");
-    if (t3) CU(cudaMemcpyAsync(out3d + run3, s.c3d.p, (size_t)t3 * sizeof(ses3d_person_cov), out_kind, s.stream));
-    if (t2) CU(cudaMemcpyAsync(out2d + run2, s.c2d.p, (size_t)t2 * sizeof(ses3d_person2d), out_kind, s.stream));
+    // (the host has seen s.done: the packed records are complete, a different stream may read them)
+    cudaStream_t ds = h->ragged_one_down ? h->down : s.stream;
+    if (t3) CU(cudaMemcpyAsync(out3d + run3, s.c3d.p, (size_t)t3 * sizeof(ses3d_person_cov), out_kind, ds));
+    if (t2) CU(cudaMemcpyAsync(out2d + run2, s.c2d.p, (size_t)t2 * sizeof(ses3d_person2d), out_kind, ds));
+    if (h->ragged_one_down) {
+      CU(cudaEventRecord(s.down_done, ds));
+      CU(cudaStreamWaitEvent(s.stream, s.down_done, 0));
+    }
     run3 += t3;
     run2 += t2;
     return SES3D_OK;
@@ -766,13 +780,14 @@ int run_ragged_impl(ses3d_handle_s* h, int n_frames, int p_max, const ses3d_pers
     CU(cudaMemsetAsync(h->d_run.p, 0, 16, h->slot[0].stream));
   }
   int ci = 0;
+  const int n_slots = dev ? (int)ses3d_handle_s::kSlots : h->ragged_slots;
   // The first chunks are short (1/4, 1/2 of the regular size): the download - the longest leg of a host call - can
   // only start once the first chunk has been uploaded and processed, so a short first chunk shortens the pipeline fill.
   int nf = 0;
   for (int f0 = 0; f0 < n_frames && status == SES3D_OK; f0 += nf, ++ci) {
     const int ramp = (!dev && n_frames >= 4 * chunk) ? (ci == 0 ? chunk / 4 : ci == 1 ? chunk / 2 : chunk) : chunk;
     nf = std::min(std::max(ramp, 1), n_frames - f0);
-    const int si = ci % ses3d_handle_s::kSlots;
+    const int si = ci % n_slots;
     Slot& s = h->slot[si];
     cudaStream_t st = s.stream;
     long long n_in = 0;
@@ -794,10 +809,11 @@ int run_ragged_impl(ses3d_handle_s* h, int n_frames, int p_max, const ses3d_pers
     }
     // upload on the slot's own upload stream: behind the kernels of the slot's previous chunk (they read these buffers),
     // ahead of everything else - the results of that older chunk may still be on their way to the host
-    CU(cudaStreamWaitEvent(s.up, s.kern_done, 0));
-    CU(cudaMemcpyAsync(s.n_persons.p, n_persons + (size_t)f0 * C, u_in * 4, in_kind, s.up));
-    if (n_in) CU(cudaMemcpyAsync(s.in_dense.p, persons_dense + in_done, (size_t)n_in * sizeof(ses3d_person2d), in_kind, s.up));
-    CU(cudaEventRecord(s.up_done, s.up));
+    cudaStream_t up = h->ragged_one_up ? h->slot[0].up : s.up;
+    CU(cudaStreamWaitEvent(up, s.kern_done, 0));
+    CU(cudaMemcpyAsync(s.n_persons.p, n_persons + (size_t)f0 * C, u_in * 4, in_kind, up));
+    if (n_in) CU(cudaMemcpyAsync(s.in_dense.p, persons_dense + in_done, (size_t)n_in * sizeof(ses3d_person2d), in_kind, up));
+    CU(cudaEventRecord(s.up_done, up));
     CU(cudaStreamWaitEvent(st, s.up_done, 0));
     in_done += n_in;
     CU(ses3d::launch_scan_counts(s.n_persons.as<int32_t>(), (int)u_in, p_max, s.in_off.as<long long>(), nullptr, st));
@@ -810,7 +826,7 @@ int run_ragged_impl(ses3d_handle_s* h, int n_frames, int p_max, const ses3d_pers
     CU(cudaEventRecord(s.kern_done, st));
     if (direct) {
       // the scans continue the running totals of the previous chunk (which ran on another slot's stream)
-      if (ci > 0) CU(cudaStreamWaitEvent(st, h->scan_ev[(ci - 1) % ses3d_handle_s::kSlots], 0));
+      if (ci > 0) CU(cudaStreamWaitEvent(st, h->scan_ev[(ci - 1) % n_slots], 0));
       long long* run = h->d_run.as<long long>();
       CU(ses3d::launch_scan_counts(s.n_out3d.as<int32_t>(), nf, h_max, s.off3.as<long long>(), run, st));
       CU(ses3d::launch_scan_counts(s.n_out2d.as<int32_t>(), (int)u_in, h_max, s.off2.as<long long>(), run + 1, st));
@@ -842,13 +858,13 @@ int run_ragged_impl(ses3d_handle_s* h, int n_frames, int p_max, const ses3d_pers
     // without waiting - the uploads of up to kSlots - 1 chunks run ahead of the kernels, which lets the upload
     // finish early and the tail of the download use the link alone.
     while (status == SES3D_OK && n_pending > 0 &&
-           (n_pending >= ses3d_handle_s::kSlots - 1 || cudaEventQuery(h->slot[pending[0]].done) == cudaSuccess))
+           (n_pending >= n_slots - 1 || cudaEventQuery(h->slot[pending[0]].done) == cudaSuccess))
       status = finish_oldest();
   }
   while (!direct && status == SES3D_OK && n_pending > 0) status = finish_oldest();
   if (direct && status == SES3D_OK && ci > 0) {
     // totals + overflow flag ride at the end of the last chunk's stream, which is ordered behind every scan
-    cudaStream_t st = h->slot[(ci - 1) % ses3d_handle_s::kSlots].stream;
+    cudaStream_t st = h->slot[(ci - 1) % n_slots].stream;
     CU(cudaMemcpyAsync(&h->h_words[0], h->d_run.p, 16, cudaMemcpyDeviceToHost, st));
   }
   for (Slot& sl : h->slot) CU(cudaStreamSynchronize(sl.stream));
@@ -931,6 +947,7 @@ int ses3d_create(int32_t n_cams, const ses3d_camera* cams, const ses3d_params* p
     if (ue == cudaSuccess) ue = cudaStreamCreateWithFlags(&h->slot[i].up, cudaStreamNonBlocking);
     if (ue == cudaSuccess) ue = cudaEventCreateWithFlags(&h->slot[i].up_done, cudaEventDisableTiming);
     if (ue == cudaSuccess) ue = cudaEventCreateWithFlags(&h->slot[i].kern_done, cudaEventDisableTiming);
+    if (ue == cudaSuccess) ue = cudaEventCreateWithFlags(&h->slot[i].down_done, cudaEventDisableTiming);
   }
   if (ue == cudaSuccess) ue = cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming);
   if (ue == cudaSuccess) ue = cudaEventCreateWithFlags(&h->dev_done, cudaEventDisableTiming);
@@ -948,6 +965,10 @@ int ses3d_create(int32_t n_cams, const ses3d_camera* cams, const ses3d_params* p
   if (const char* env = getenv("SES3D_RAGGED_CHUNK")) h->ragged_chunk_env = std::max(1, atoi(env));
   if (const char* env = getenv("SES3D_RAGGED_DIRECT")) h->ragged_direct = atoi(env);
   if (const char* env = getenv("SES3D_FRAME_GRAPH")) h->frame_graph = atoi(env);
+  if (const char* env = getenv("SES3D_RAGGED_ONE_UP")) h->ragged_one_up = atoi(env);
+  if (const char* env = getenv("SES3D_RAGGED_ONE_DOWN")) h->ragged_one_down = atoi(env);
+  if (ue == cudaSuccess) ue = cudaStreamCreateWithFlags(&h->down, cudaStreamNonBlocking);
+  if (const char* env = getenv("SES3D_RAGGED_SLOTS")) h->ragged_slots = std::max(2, std::min((int)ses3d_handle_s::kSlots, atoi(env)));
   if (ue != cudaSuccess) {
     ses3d_destroy(h);
     return cuda_fail(ue, "ses3d_create upload");
@@ -970,6 +991,7 @@ int ses3d_destroy(ses3d_handle h) {
   cudaSetDevice(h->device);
   for (FrameGraph& g : h->fgraph) g.release();
   for (Slot& s : h->slot) s.release();
+  if (h->down) cudaStreamDestroy(h->down);
   if (h->fork_ev) cudaEventDestroy(h->fork_ev);
   if (h->dev_done) { cudaEventSynchronize(h->dev_done); cudaEventDestroy(h->dev_done); }
   for (cudaEvent_t& e : h->scan_ev) if (e) cudaEventDestroy(e);

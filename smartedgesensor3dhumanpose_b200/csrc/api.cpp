@@ -486,14 +486,16 @@ int capture_frame_graph(ses3d_handle_s* h, int stages, int p_max, int h_max) {
   }
   g.n_kernels = (int)(h->launches - launches0);
   h->launches = launches0;   // nothing ran
-  ok = ok && g_alloc_gen.load(std::memory_order_relaxed) == gen0;   // a buffer moved: the eager call had not sized it
-  if (ok) ok = cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess;
+  // a device buffer of the library moved while capturing (the counter is process-wide: another handle growing its
+  // buffers on another thread also lands here): drop this capture, the next call tries again
+  const bool moved = g_alloc_gen.load(std::memory_order_relaxed) != gen0;
+  if (ok && !moved) ok = cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess;
   if (graph) cudaGraphDestroy(graph);
-  if (!ok) {
+  if (!ok || moved) {
     cudaGetLastError();
     g_last_error = err0;
     if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
-    g.broken = true;
+    if (!ok) g.broken = true;
     return SES3D_OK;
   }
   g.p_max = p_max;

@@ -106,6 +106,22 @@ int main(void) {
            n2[0], n2[1], n2[2], n2[3]);
     if (n3 != 1 || n2[0] != 1) return 12;
 
+    /* the per-message call of a node: the second call of a shape captured a CUDA graph, later calls replay it -
+     * same record every time */
+    {
+      int rep;
+      for (rep = 0; rep < 5; ++rep) {
+        ses3d_person_cov r3d[8];
+        ses3d_person2d r2d[4 * 8];
+        int32_t rn3 = 0, rn2[4];
+        rc = ses3d_process_batch(h, 1, 2, persons, n_persons, 8, r3d, &rn3, r2d, rn2, NULL, SES3D_HOST_BUFFERS, NULL);
+        if (rc != SES3D_OK || rn3 != n3 || memcmp(r3d, out3d, sizeof r3d) != 0 || memcmp(r2d, out2d, sizeof r2d) != 0 ||
+            memcmp(rn2, n2, sizeof rn2) != 0)
+          return 23;
+      }
+      printf("single-frame replays: identical records\n");
+    }
+
     /* the same call through the single-process multi-GPU entry (device list; here: every visible device) */
     {
       ses3d_multi m = NULL;

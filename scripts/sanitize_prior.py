@@ -32,6 +32,13 @@ for pm, nh, people in [(0, 0, 7), (1, 1, 3)]:
     n_out, _, total = trk.run_ragged(dense, seq["n_persons"], seq["stamp_ns"], H, fused, pred, seq["fb_delay"])
     assert total == r["n_out"].sum() and np.array_equal(n_out, r["n_out"])
     trk.close()
+    # streaming: one message per call (the contiguous small-call record) equals the batched launch
+    trk = api.PriorTracker(default_prior_params(pose_method=pm, normalize_by_height=nh, min_num_obs_track=2), 3)
+    for t in range(seq["persons"].shape[1]):
+        rs = trk.run(seq["persons"][:, t:t + 1], seq["n_persons"][:, t:t + 1], seq["stamp_ns"][:, t:t + 1],
+                     seq["fb_delay"][:, t:t + 1])
+        assert rs["fused"][:, 0].tobytes() == r["fused"][:, t].tobytes()
+    trk.close()
 # visualisation kernel on fused skeletons
 from smartedgesensor3dhumanpose_b200 import rigs  # noqa: E402
 pipe = api.GeometryPipeline(rigs.ring8())

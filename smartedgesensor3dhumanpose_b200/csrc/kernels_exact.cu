@@ -48,6 +48,11 @@ k_pairs(const Tables tb, int n_frames, int p_max, const ses3d_person2d* __restri
 // first warp) - for rigs whose frames are heavy and few (crowds: a frame's 64 camera rounds take ~15 ms on a single
 // warp, and 512 frames do not fill the GPU with one warp each).
 enum { ROUNDS_WARP = 0, ROUNDS_BLOCK = 2 };
+// per-warp staging area of a low-latency k_rounds launch: pair-table entries, person scores, slots, camera offsets
+__host__ __device__ inline size_t rounds_stage_bytes(int C, int p_max, int stage_entries) {
+  const size_t n = (size_t)C * p_max;
+  return ((size_t)stage_entries * 8 + n * 4 + n * 2 + (size_t)(C + 1) * 2 + 15) / 16 * 16;
+}
 template <int kMode> struct RoundsTeam { typedef WarpTeam type; };
 template <> struct RoundsTeam<ROUNDS_BLOCK> { typedef BlockTeam type; };
 
@@ -56,7 +61,8 @@ __global__ void __launch_bounds__(kMode == ROUNDS_BLOCK ? 256 : 128)
 k_rounds(const Tables tb, int n_frames, int p_max, int h_cap, size_t ws_bytes, const int32_t* __restrict__ n_persons,
          const double* pair_table, unsigned char* meta_base, size_t meta_stride, int8_t* __restrict__ hyp_det,
          int32_t* __restrict__ n_hyp, int32_t* __restrict__ n_hung, int32_t* overflow, int32_t* hyp_of_dump,
-         int32_t* __restrict__ keep, uint32_t* __restrict__ work, int32_t* work_count, int32_t* __restrict__ n_out_zero) {
+         int32_t* __restrict__ keep, uint32_t* __restrict__ work, int32_t* work_count, int32_t* __restrict__ n_out_zero,
+         int stage_entries) {
   const int warp = kMode == ROUNDS_BLOCK ? 0 : (int)(threadIdx.x >> 5);
   const int f = kMode == ROUNDS_BLOCK ? (int)blockIdx.x : (int)blockIdx.x * (int)(blockDim.x >> 5) + warp;
   const int C = tb.n_cams;
@@ -68,6 +74,24 @@ k_rounds(const Tables tb, int n_frames, int p_max, int h_cap, size_t ws_bytes, c
   const FrameMeta meta = frame_meta_at(meta_base + (size_t)f * meta_stride, C, p_max);
   ws.voff = meta.voff; ws.vslot = meta.vslot; ws.pscore = meta.pscore;
   ws.E = const_cast<double*>(pair_table) + (size_t)f * assoc_pair_table_entries(C, p_max);
+  if (kMode == ROUNDS_WARP && stage_entries > 0) {
+    // Low-latency launches (a handful of frames): every camera round starts with dependent loads of the frame's meta
+    // record and pair-table entries, ~1.5 us of L2 round trips per round on an otherwise idle SM. Stage the frame's
+    // part of both in shared memory once (coalesced, all loads in flight together).
+    const int n_max = C * p_max, nv = *meta.n_valid, need = nv * (nv - 1) / 2, lane = (int)(threadIdx.x & 31u);
+    if (need <= stage_entries) {
+      unsigned char* sp = smem_raw + (size_t)(blockDim.x >> 5) * ws_bytes + (size_t)warp * rounds_stage_bytes(C, p_max, stage_entries);
+      double* Es = reinterpret_cast<double*>(sp);
+      float* ps = reinterpret_cast<float*>(Es + stage_entries);
+      uint16_t* vs = reinterpret_cast<uint16_t*>(ps + n_max);
+      uint16_t* vo = vs + n_max;
+      for (int i = lane; i < need; i += 32) Es[i] = ws.E[i];
+      for (int i = lane; i < nv; i += 32) { ps[i] = meta.pscore[i]; vs[i] = meta.vslot[i]; }
+      for (int i = lane; i <= C; i += 32) vo[i] = meta.voff[i];
+      __syncwarp();
+      ws.E = Es; ws.pscore = ps; ws.vslot = vs; ws.voff = vo;
+    }
+  }
   int8_t* hd = hyp_det + (size_t)f * h_cap * C;
   rounds_frame(tm, tb, p_max, h_cap, n_persons + (size_t)f * C, *meta.n_valid, ws, hd, n_hyp + f,
                n_hung ? n_hung + f : nullptr, overflow);
@@ -288,12 +312,22 @@ cudaError_t launch_associate(const LaunchCfg& cfg, const Tables& tb, LaunchDims 
 #define SES_ROUNDS(MODE, GRID, THREADS, SMEM)                                                                              \
   k_rounds<MODE><<<(GRID), (THREADS), (SMEM), st>>>(tb, d.n_frames, d.p_max, d.h_cap, rws, n_persons, pair_table, meta,      \
                                                     meta_stride, hyp_det, n_hyp, n_hung, overflow, hyp_of_dump, keep, work,  \
-                                                    work_count, nullptr)
+                                                    work_count, nullptr, stage_entries)
   // heavy frames (big cost matrices: >= 256 entries) that are too few to fill the GPU one warp each: CTA per frame
   const bool block_mode = cfg.rounds_block == 1 ||
                           (cfg.rounds_block < 0 && d.h_cap * d.p_max >= 256 && d.n_frames < 8 * cfg.n_sm * warps);
+  int stage_entries = 0;
+  if (!block_mode && cfg.latency_frames > 0 && d.n_frames * 16 <= cfg.latency_frames) {
+    // one frame per CTA, the frame's meta record and pair table staged in shared memory (as much as fits)
+    warps = 1;
+    const size_t room = kSmemBudget - rws;
+    const int n = tb.n_cams * d.p_max;
+    stage_entries = n * (n - 1) / 2;
+    while (stage_entries > 0 && rounds_stage_bytes(tb.n_cams, d.p_max, stage_entries) > room) stage_entries /= 2;
+  }
+  const size_t stage = stage_entries > 0 ? rounds_stage_bytes(tb.n_cams, d.p_max, stage_entries) : 0;
   if (block_mode) SES_ROUNDS(ROUNDS_BLOCK, d.n_frames, 256, rws);
-  else SES_ROUNDS(ROUNDS_WARP, (d.n_frames + warps - 1) / warps, 32 * warps, rws * warps);
+  else SES_ROUNDS(ROUNDS_WARP, (d.n_frames + warps - 1) / warps, 32 * warps, (rws + stage) * warps);
 #undef SES_ROUNDS
   return cudaGetLastError();
 }

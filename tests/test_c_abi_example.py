@@ -31,4 +31,5 @@ def test_c_client_single_frame_call_on_gpu(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     assert "persons3d = 1" in r.stdout
     assert "pose_prior: track 0, 12 observations" in r.stdout
+    assert "single-frame replays: identical records" in r.stdout
     assert "identical record" in r.stdout and "overlay:" in r.stdout and "overlay: 0 coloured" not in r.stdout

@@ -64,8 +64,10 @@ cudaError_t launch_prior_reset(const ses3d_prior_params& prm, int n_seq, PriorSe
 // tuning overrides, read once per handle creation (ses3d_prior_create -> init_prior_kernels), never per launch
 static int g_prior_group_env = 0, g_prior_warps_env = 0;
 cudaError_t init_prior_kernels(int) {
-  if (const char* env = getenv("SES3D_PRIOR_GROUP")) g_prior_group_env = atoi(env);
-  if (const char* env = getenv("SES3D_PRIOR_WARPS")) g_prior_warps_env = atoi(env);
+  const char* eg = getenv("SES3D_PRIOR_GROUP");
+  const char* ew = getenv("SES3D_PRIOR_WARPS");
+  g_prior_group_env = eg ? atoi(eg) : 0;   // re-read at every create: an override does not outlive its variable
+  g_prior_warps_env = ew ? atoi(ew) : 0;
   return cudaFuncSetAttribute(k_prior, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
@@ -83,6 +85,14 @@ cudaError_t launch_prior(const PriorTables& pt, int n_seq, int n_frames, int h_m
   // two warps per stream whatever h_max is: a fuller message simply takes more rounds of groups, and the smaller CTA
   // keeps eight streams resident per SM (demo chain, h_max 16, 2048 streams: 40.8 ms with 4 warps -> 36.3 ms with 2)
   int warps = std::max(1, std::min(2, (h_max + group - 1) / group));
+  // Few streams (a ROS node tracks ONE; anything that leaves the GPU under-filled): occupancy is irrelevant, the
+  // time of a message is what counts - one detection per warp, up to six warps. B200, 32 messages x 6 people per
+  // stream, ms per launch (3 x 2 warps -> 1 x 6 warps): 1 stream 3.94 -> 3.30, 64: 4.18 -> 3.58, 256: 4.75 -> 4.19,
+  // 512: 5.14 -> 7.58 (so the switch sits at 256 streams).
+  if (n_seq <= 256 && g_prior_group_env <= 0 && g_prior_warps_env <= 0) {
+    group = 1;
+    warps = std::max(1, std::min(6, h_max));
+  }
   if (g_prior_warps_env > 0) warps = std::max(1, std::min(8, g_prior_warps_env));
   size_t ws_bytes = 0, transient_bytes = 0;
   prior_ws_bytes(h_max, max_tracks, &ws_bytes, &transient_bytes);

@@ -66,6 +66,12 @@ def test_graph_path_of_the_separate_stages_and_eager_switch():
             assert _same(t["persons3d"][0], tri["persons3d"][f]) and t["n_out"][0] == tri["n_out"][f]
             r = p.reproject_batch(t["persons3d"], t["n_out"])
             assert _same(r["persons2d"][0], rep["persons2d"][f]) and _same(r["n_out"][0], rep["n_out"][f])
+    # 3-D output not wanted (NULL out3d): the replay skips that copy, the 2-D records are the same
+    both = pipe.process_batch(fr["persons"], fr["n_persons"], h_max)
+    for f in (7, 8, 9, 7):
+        r = pipe.process_batch(fr["persons"][f:f + 1], fr["n_persons"][f:f + 1], h_max, want_3d=False)
+        assert r["persons3d"] is None and r["n_out3d"][0] == both["n_out3d"][f]
+        assert _same(r["persons2d"][0], both["persons2d"][f]) and _same(r["n_out2d"][0], both["n_out2d"][f])
     # a call that asks for the association dump stays on the eager path and still agrees
     d = pipe.triangulate_batch(fr["persons"][5:6], fr["n_persons"][5:6], h_max, dump=True)
     assert _same(d["persons3d"][0], tri["persons3d"][5]) and d["n_hyp"][0] >= d["n_out"][0]

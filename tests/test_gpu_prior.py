@@ -71,6 +71,26 @@ def test_prior_streaming_and_node_mirror():
     assert len(fused) == 0
 
 
+def test_prior_results_do_not_depend_on_the_launch_shape():
+    """Few streams run one detection per warp on up to six warps, many streams three detections per warp on two
+    (kernels_prior.cu::launch_prior); SES3D_PRIOR_GROUP / SES3D_PRIOR_WARPS force a shape. Same bytes either way."""
+    import os
+    seq = synth_person_sequences(5, 24, 7, seed=77, joint_dropout=0.15, person_dropout=0.1, h_max=10)
+    prm = default_prior_params(min_num_obs_track=3)
+    ref = api.PriorTracker(prm, 5).run(seq["persons"], seq["n_persons"], seq["stamp_ns"], seq["fb_delay"])   # 1 x 6
+    assert ref["n_out"].sum() > 0
+    for group, warps in [(3, 2), (2, 3), (1, 4), (3, 1)]:
+        os.environ["SES3D_PRIOR_GROUP"], os.environ["SES3D_PRIOR_WARPS"] = str(group), str(warps)
+        try:
+            trk = api.PriorTracker(prm, 5)
+        finally:
+            del os.environ["SES3D_PRIOR_GROUP"], os.environ["SES3D_PRIOR_WARPS"]
+        r = trk.run(seq["persons"], seq["n_persons"], seq["stamp_ns"], seq["fb_delay"])
+        for k in ("fused", "pred", "n_out", "pred_delay", "track_of"):
+            assert r[k].tobytes() == ref[k].tobytes(), (group, warps, k)
+        trk.close()
+
+
 def test_prior_device_buffers_and_chain():
     """Device-resident call (torch only provides the memory) fed by the triangulation stage's output layout."""
     import torch

@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--workload", default="cfg2_hall16x6")
     ap.add_argument("--out", default="")
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--window", default="", help="lo,hi in ms: list every GPU activity that starts in the window (stderr)")
     a = ap.parse_args()
     import torch
     from torch.profiler import ProfilerActivity, profile
@@ -75,8 +76,28 @@ def main():
         t0 = time.perf_counter(); step(); wall.append((time.perf_counter() - t0) * 1e3)
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         t0 = time.perf_counter(); step(); torch.cuda.synchronize(); prof_wall = (time.perf_counter() - t0) * 1e3
+    copies = []
     if a.out:
-        prof.export_chrome_trace(a.out.replace(".json", "_chrome.json"))
+        chrome = a.out.replace(".json", "_chrome.json")
+        prof.export_chrome_trace(chrome)
+        # per-copy list (bytes are only in the chrome trace): start, duration, size, rate - big copies only
+        tr = json.load(open(chrome))
+        cp = [e for e in tr.get("traceEvents", []) if e.get("cat") == "gpu_memcpy" and e.get("args", {}).get("bytes", 0) >= 1 << 20]
+        if cp:
+            t0c = min(e["ts"] for e in tr["traceEvents"] if e.get("cat") in ("gpu_memcpy", "kernel", "gpu_memset"))
+            for e in sorted(cp, key=lambda e: e["ts"]):
+                kind = "HtoD" if "HtoD" in e["name"] else "DtoH" if "DtoH" in e["name"] else "other"
+                copies.append({"kind": kind, "start_ms": round((e["ts"] - t0c) / 1e3, 3), "dur_ms": round(e["dur"] / 1e3, 3),
+                               "mb": round(e["args"]["bytes"] / 1e6, 2), "gbs": round(e["args"]["bytes"] / e["dur"] / 1e3, 1),
+                               "stream": e["args"].get("stream")})
+        if a.window:
+            lo, hi = [float(x) for x in a.window.split(",")]
+            for e in sorted(tr["traceEvents"], key=lambda e: e.get("ts", 0)):
+                if e.get("cat") in ("gpu_memcpy", "kernel", "gpu_memset") and lo <= (e["ts"] - t0c) / 1e3 <= hi:
+                    print("%8.3f %7.3f s%-3s %s %s" % ((e["ts"] - t0c) / 1e3, e["dur"] / 1e3, e["args"].get("stream"),
+                                                     e["name"].split("(")[0].replace("void ses3d::", "").replace("ses3d::", "")[:28],
+                                                     ("%.1fMB" % (e["args"]["bytes"] / 1e6)) if "bytes" in e.get("args", {}) else
+                                                     ("grid %s" % (e["args"].get("grid"),))), file=sys.stderr)
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     by = defaultdict(list)
     t_min = min(e.time_range.start for e in evs)
@@ -100,6 +121,7 @@ def main():
         if not name.startswith("mem"):
             kernels += iv
     res["all_kernels_busy_union_ms"] = union_ms(kernels)
+    res["copies_over_1mb"] = copies
     print(json.dumps(res, indent=1))
     if a.out:
         Path(a.out).write_text(json.dumps(res, indent=1))

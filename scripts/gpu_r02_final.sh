@@ -15,6 +15,8 @@ rm -f gpurun_out/prof_k_pairs_${T}.ncu-rep gpurun_out/prof_k_rounds_${T}.ncu-rep
 timeout 300 python scripts/e2e_timeline.py --out gpurun_out/${T}_tl.json > /dev/null 2>> gpurun_out/${T}_bench_err.log
 rm -f gpurun_out/*_chrome.json
 timeout 300 python scripts/latency_probe.py > gpurun_out/latency_${T}.txt 2>&1; tail -3 gpurun_out/latency_${T}.txt
+timeout 300 python scripts/latency_kernels.py 2>&1 | grep -v -i warn > gpurun_out/${T}_latency_kernels.txt; tail -2 gpurun_out/${T}_latency_kernels.txt
+timeout 200 python scripts/pcie_probe_concurrent.py > gpurun_out/${T}_link_n1.json 2>/dev/null; timeout 200 python scripts/pcie_probe_pieces.py 2>&1 | grep -v -i warn > gpurun_out/${T}_link_pieces.txt
 timeout 1500 python scripts/soak_parity.py > gpurun_out/${T}_soak.jsonl 2> gpurun_out/${T}_soak.err; cut -c1-400 gpurun_out/${T}_soak.jsonl
 python - <<PY
 import json

@@ -57,7 +57,9 @@ for k, v in summ.items():
 for f in (f"bench_{tag}.json", f"bench_{tag}_reference.json", f"bench_prior_{tag}.json", f"bench_chain_{tag}.json", f"latency_{tag}.txt"):
     if (G / f).exists():
         shutil.copy(G / f, P / f)
-for src, dst in ((f"{tag}_soak.jsonl", f"{tag}_soak.jsonl"), (f"{tag}_tl.json", f"{tag}_e2e_timeline.json")):
+for src, dst in ((f"{tag}_soak.jsonl", f"{tag}_soak.jsonl"), (f"{tag}_tl.json", f"{tag}_e2e_timeline.json"),
+                 (f"{tag}_latency_kernels.txt", f"{tag}_latency_kernels.txt"), (f"{tag}_link_n1.json", f"{tag}_link_n1.json"),
+                 (f"{tag}_link_pieces.txt", f"{tag}_link_pieces.txt")):
     if (G / src).exists():
         shutil.copy(G / src, P / dst)
 rows = list(csv.reader(open(G / f"launches_{tag}.csv")))

@@ -356,6 +356,12 @@ SES_HD void pairs_frame(Team& tm, const Tables& tb, int p_max, const ses3d_perso
   if (part == 0) {
     tm.pfor(n_valid, [&](int a) { meta.vslot[a] = ws.vslot[a]; meta.pscore[a] = persons[ws.vslot[a]].score; });
     tm.pfor(C + 1, [&](int c) { meta.voff[c] = ws.voff[c]; });
+    // same-camera pairs are never evaluated (and never looked up); give their table entries a defined value so that
+    // the triangle [0, n_valid(n_valid-1)/2) can be copied as a block (low-latency k_rounds stages it in shared memory)
+    tm.pfor(n_valid, [&](int b) {
+      const int c = ws.vslot[b] / p_max;
+      for (int a = ws.voff[c]; a < b; ++a) ws.E[(size_t)b * (b - 1) / 2 + a] = -1.0;
+    });
   }
 
   // pair table: mean symmetric epipolar distance of every cross-camera pair of valid detections, the inner loop of

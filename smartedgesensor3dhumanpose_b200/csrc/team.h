@@ -25,6 +25,10 @@ namespace ses3d {
 //                         sub-algorithms such as the Munkres solver inside a CTA-wide team)
 //   team.sum(n, f)        sum of f(i) over [0,n) as double (same value on every thread; warp / serial teams)
 //   team.per_warp(n, f)   run f(warp_team, i) for i in [0,n), items spread over the team's warps, then barrier
+//   team.compact(n, pred, emit)   emit(i, pos) for every i in [0,n) with pred(i), pos = number of passing items
+//                         before i (stream compaction in index order); returns the count (warp / serial teams)
+//   team.count(n, pred)   number of i in [0,n) with pred(i) (same value on every thread; warp / serial teams)
+//   team.scan(n, f, out)  out[i] = f(0) + ... + f(i-1) for i in [0,n], n <= 32 (warp / serial teams), then barrier
 struct SerialTeam {
   template <class F> void pfor(int n, F&& f) { for (int i = 0; i < n; ++i) f(i); }
   template <class F> void single(F&& f) { f(); }
@@ -37,6 +41,17 @@ struct SerialTeam {
   template <class F> void warp0(F&& f) { f(*this); }
   template <class F> double sum(int n, F&& f) { double s = 0.0; for (int i = 0; i < n; ++i) s += f(i); return s; }
   template <class F> void per_warp(int n, F&& f) { for (int i = 0; i < n; ++i) f(*this, i); }
+  template <class P, class E> int compact(int n, P&& pred, E&& emit) {
+    int pos = 0;
+    for (int i = 0; i < n; ++i) if (pred(i)) emit(i, pos++);
+    return pos;
+  }
+  template <class P> int count(int n, P&& pred) { int c = 0; for (int i = 0; i < n; ++i) c += pred(i) ? 1 : 0; return c; }
+  template <class F> void scan(int n, F&& f, int* out) {
+    int run = 0;
+    for (int i = 0; i < n; ++i) { out[i] = run; run += f(i); }
+    out[n] = run;
+  }
   void sync() {}
   void phase() {}
   template <class F> void shared_pfor(int n, int tag, F&& f) { if (tag) for (int i = 0; i < n; ++i) f(0, tag, i); }
@@ -90,6 +105,38 @@ struct WarpTeam {
     return s;
   }
   template <class F> __device__ __forceinline__ void per_warp(int n, F&& f) { for (int i = 0; i < n; ++i) f(*this, i); }
+  template <class P, class E> __device__ __forceinline__ int compact(int n, P&& pred, E&& emit) {
+    const unsigned lane = threadIdx.x & 31u;
+    int count = 0;
+    for (int base = 0; base < n; base += 32) {
+      const int i = base + (int)lane;
+      const bool p = i < n && pred(i);
+      const unsigned b = __ballot_sync(0xffffffffu, p);
+      if (p) emit(i, count + __popc(b & ((1u << lane) - 1u)));
+      count += __popc(b);
+    }
+    __syncwarp();
+    return count;
+  }
+  template <class P> __device__ __forceinline__ int count(int n, P&& pred) {
+    const int lane = (int)(threadIdx.x & 31u);
+    int c = 0;
+    for (int base = 0; base < n; base += 32) c += __popc(__ballot_sync(0xffffffffu, base + lane < n && pred(base + lane)));
+    return c;
+  }
+  template <class F> __device__ __forceinline__ void scan(int n, F&& f, int* out) {   // n <= 32
+    const unsigned lane = threadIdx.x & 31u;
+    const int v = (int)lane < n ? f((int)lane) : 0;
+    int incl = v;
+    for (int off = 1; off < 32; off <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, incl, off);
+      if ((int)lane >= off) incl += o;
+    }
+    if ((int)lane < n) out[lane] = incl - v;
+    if ((int)lane == n - 1) out[n] = incl;
+    if (n == 0 && lane == 0) out[0] = 0;
+    __syncwarp();
+  }
   __device__ __forceinline__ void sync() { __syncwarp(); }
   __device__ __forceinline__ void phase() {}
   template <class F> __device__ __forceinline__ void shared_pfor(int n, int tag, F&& f) {

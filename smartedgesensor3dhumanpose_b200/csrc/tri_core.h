@@ -85,8 +85,8 @@ SES_HD void tri_ws_layout(A& ar, int C, TriWs<T>* ws) {
   int* jflag = ar.template take<int>(NKP);
   int* soff = ar.template take<int>(NKP + 1);
   int* scal = ar.template take<int>(4);
+  uint8_t* kmap = reinterpret_cast<uint8_t*>(ar.template take<uint32_t>((size_t)NKP * C));   // filled word-wise
   uint8_t* vlist = ar.template take<uint8_t>((size_t)NKP * C);
-  uint8_t* kmap = ar.template take<uint8_t>((size_t)NKP * 4 * C);
   uint8_t* obs_cam = ar.template take<uint8_t>(C);
   uint8_t* obs_det = ar.template take<uint8_t>(C);
   if (ws) {
@@ -599,13 +599,9 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
   tm.phase();   // 1 of TRI_PHASES: gather + normalise
   int n_obs_own = 0;
   if (live) {
-    tm.single([&] {
-      int n = 0;
-      for (int c = 0; c < C; ++c)
-        if (hyp_det_row[c] >= 0) { ws.obs_cam[n] = (uint8_t)c; ws.obs_det[n] = (uint8_t)hyp_det_row[c]; ++n; }
-      ws.scal[0] = n;
-    });
-    n_obs_own = ws.scal[0];
+    // observation list in camera order: stream compaction of the hypothesis' row of the association table
+    n_obs_own = tm.compact(C, [&](int c) { return hyp_det_row[c] >= 0; },
+                           [&](int c, int pos) { ws.obs_cam[pos] = (uint8_t)c; ws.obs_det[pos] = (uint8_t)hyp_det_row[c]; });
     if (n_obs_own < 2) {  // S3D:684: hypotheses with a single observation are not triangulated
       tm.single([&] { *keep = 0; });
       n_obs_own = 0;
@@ -889,14 +885,12 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
 
   tm.phase();   // 5: sigma points
   if (live) {
-  tm.single([&] {
-    int off = 0;
-    for (int k = 0; k < NKP; ++k) { ws.soff[k] = off; off += (ws.jn[k] >= 2 && !(ws.jflag[k] & 2)) ? 4 * ws.jn[k] : 0; }
-    ws.soff[NKP] = off;
-  });
+  static_assert(NKP <= 32, "team.scan handles at most 32 items");
+  tm.scan(NKP, [&](int k) { return (ws.jn[k] >= 2 && !(ws.jflag[k] & 2)) ? 4 * ws.jn[k] : 0; }, ws.soff);
   const int n_samples_total = ws.soff[NKP];
-  tm.pfor(NKP, [&](int k) {
-    for (int i = ws.soff[k]; i < ws.soff[k + 1]; ++i) ws.kmap[i] = (uint8_t)k;
+  tm.pfor(NKP, [&](int k) {   // a joint owns 4n consecutive samples: four map entries per store
+    uint32_t* km = reinterpret_cast<uint32_t*>(ws.kmap);
+    for (int w = ws.soff[k] >> 2; w < (ws.soff[k + 1] >> 2); ++w) km[w] = (uint32_t)k * 0x01010101u;
   });
 
   // unscented sigma points 1..4n (S3D:471-506) of all joints in one index space, Y_CHUNK per pass
@@ -1044,18 +1038,14 @@ SES_HD void triangulate_hypothesis(Team& tm, const Tables& tb, int p_max, const 
       zero_kp(kp);
     }
   });
+  // every slot that is empty after the reset decrements the counter (S3D:940-951): joints reset by the distance test
+  // and the never-filled slots alike; joints that were triangulated with a non-positive score were counted once and
+  // are removed here as "empty" exactly like the reference does (kp.score > 0 is its only test)
+  int num_valid_all = tm.count(NKP, [&](int k) { return ws.jn[k] >= 2; });
+  if (ws.jerr[3] > 0) num_valid_all -= tm.count(NFUS, [&](int s) { return !(ws.kp[s].score > 0); });
   tm.single([&] {
     const ses3d_keypoint_cov* K = ws.kp;
-    int num_valid = 0;
-    for (int k = 0; k < NKP; ++k) num_valid += ws.jn[k] >= 2 ? 1 : 0;
-    if (ws.jerr[3] > 0) {
-      // every slot that is empty after the reset decrements the counter (S3D:940-951): joints reset by the
-      // distance test and the never-filled slots alike
-      for (int s = 0; s < NFUS; ++s)
-        if (!(K[s].score > 0)) --num_valid;
-      // joints that were triangulated with a non-positive score were counted once above and are removed here
-      // as "empty" exactly like the reference does (kp.score > 0 is its only test)
-    }
+    int num_valid = num_valid_all;
     double feet = 0.0;
     if (K[SES3D_FBP_LANKLE].score > 0 && K[SES3D_FBP_RANKLE].score > 0)
       feet = (K[SES3D_FBP_LANKLE].z + K[SES3D_FBP_RANKLE].z) / 2.0;

@@ -548,21 +548,34 @@ SES_HD void rounds_frame(Team& tm, const Tables& tb, int p_max, int h_cap, const
         munkres_coop(wt, wc, wc.cost, n_hyp, n_det, wc.assignment);
       });
     }
-    tm.single([&] {
-      for (int d = 0; d < n_det; ++d) ws.handled[d] = 0;
-      for (int h = 0; h < n_hyp; ++h) {  // S3D:637-660
-        const int d = ws.assignment[h];
-        if (d < 0) continue;
-        ws.handled[d] = 1;
-        if (!ws.mask[h + n_hyp * d]) add_hyp(b0 + d);
-        else {
-          const int o = ws.hyp_nobs[h];
-          ws.hyp_obs[(size_t)h * C + o] = (uint16_t)(b0 + d);
-          ws.hyp_nobs[h] = (uint8_t)(o + 1);
-        }
+    // Apply the assignment (S3D:637-673). The assignment is a matching (one detection per hypothesis at most and vice
+    // versa), so the per-hypothesis updates are independent; the new one-observation hypotheses keep the reference's
+    // push_back order - first the assigned-but-vetoed detections in hypothesis order, then the unassigned detections
+    // in detection order - through two stream compactions.
+    tm.pfor(n_det, [&](int d) { ws.handled[d] = 0; });
+    tm.pfor(n_hyp, [&](int h) {
+      const int d = ws.assignment[h];
+      if (d < 0) return;
+      ws.handled[d] = 1;
+      if (ws.mask[h + n_hyp * d]) {
+        const int o = ws.hyp_nobs[h];
+        ws.hyp_obs[(size_t)h * C + o] = (uint16_t)(b0 + d);
+        ws.hyp_nobs[h] = (uint8_t)(o + 1);
       }
-      for (int d = 0; d < n_det; ++d)  // S3D:662-673
-        if (!ws.handled[d]) add_hyp(b0 + d);
+    });
+    auto new_hyp = [&](int idx, int a) {   // add_hyp at a known position; beyond h_cap it only counts (overflow below)
+      if (idx >= h_cap) return;
+      ws.hyp_obs[(size_t)idx * C] = (uint16_t)a;
+      ws.hyp_nobs[idx] = 1;
+    };
+    const int n_vetoed = tm.compact(n_hyp, [&](int h) { const int d = ws.assignment[h]; return d >= 0 && !ws.mask[h + n_hyp * d]; },
+                                    [&](int h, int pos) { new_hyp(n_hyp + pos, b0 + ws.assignment[h]); });
+    const int n_free = tm.compact(n_det, [&](int d) { return !ws.handled[d]; },
+                                  [&](int d, int pos) { new_hyp(n_hyp + n_vetoed + pos, b0 + d); });
+    tm.single([&] {
+      int total = n_hyp + n_vetoed + n_free;
+      if (total > h_cap) { ws.scal[SC_OVERFLOW] = 1; total = h_cap; }
+      ws.scal[SC_N_HYP] = total;
     });
   }
 

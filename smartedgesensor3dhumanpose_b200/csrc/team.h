@@ -181,6 +181,19 @@ struct BlockTeam {
     for (int i = (int)(threadIdx.x >> 5); i < n; i += nw) { WarpTeam w; f(w, i); }
     __syncthreads();
   }
+  // stream compaction on the CTA's first warp (the lists are short), count broadcast through shared memory
+  template <class P, class E> __device__ __forceinline__ int compact(int n, P&& pred, E&& emit) {
+    __shared__ int s_count;
+    if (threadIdx.x < 32) {
+      WarpTeam w;
+      const int c = w.compact(n, pred, emit);
+      if (threadIdx.x == 0) s_count = c;
+    }
+    __syncthreads();
+    const int c = s_count;
+    __syncthreads();
+    return c;
+  }
   __device__ __forceinline__ void sync() { __syncthreads(); }
   __device__ __forceinline__ void phase() {}
   template <class F> __device__ __forceinline__ void shared_pfor(int n, int tag, F&& f) {

@@ -527,8 +527,7 @@ SES_HD void rounds_frame(Team& tm, const Tables& tb, int p_max, int h_cap, const
     // provisional assignment = the last passing detection per hypothesis (S3D:616-626); the Munkres solve is
     // needed when any row or column of the mask has more than one hit (S3D:628). One thread per row / column;
     // the flag write is the same value from every writer.
-    tm.single([&] { ws.scal[SC_AMBIG] = 0; });
-    tm.pfor(n_hyp + n_det, [&](int i) {
+    const bool ambiguous = tm.count(n_hyp + n_det, [&](int i) {
       int cnt = 0;
       if (i < n_hyp) {
         int last = -1;
@@ -537,12 +536,13 @@ SES_HD void rounds_frame(Team& tm, const Tables& tb, int p_max, int h_cap, const
         ws.assignment[i] = last;
       } else {
         const int d = i - n_hyp;
+        ws.handled[d] = 0;   // (reset for the update below)
         for (int h = 0; h < n_hyp; ++h) cnt += ws.mask[h + n_hyp * d];
       }
-      if (cnt > 1) ws.scal[SC_AMBIG] = 1;
-    });
-    tm.single([&] { if (ws.scal[SC_AMBIG]) ++ws.scal[SC_N_HUNG]; });
-    if (ws.scal[SC_AMBIG]) {  // S3D:628-634: full Munkres on the cost matrix
+      return cnt > 1;
+    }) > 0;
+    tm.sync();   // assignment / handled are read by other threads next
+    if (ambiguous) {  // S3D:628-634: full Munkres on the cost matrix
       tm.warp0([&](auto& wt) {
         const AssocWs wc = ws;   // a copy: an out-of-line solver must not make the workspace struct addressable
         munkres_coop(wt, wc, wc.cost, n_hyp, n_det, wc.assignment);
@@ -552,7 +552,6 @@ SES_HD void rounds_frame(Team& tm, const Tables& tb, int p_max, int h_cap, const
     // versa), so the per-hypothesis updates are independent; the new one-observation hypotheses keep the reference's
     // push_back order - first the assigned-but-vetoed detections in hypothesis order, then the unassigned detections
     // in detection order - through two stream compactions.
-    tm.pfor(n_det, [&](int d) { ws.handled[d] = 0; });
     tm.pfor(n_hyp, [&](int h) {
       const int d = ws.assignment[h];
       if (d < 0) return;
@@ -576,6 +575,7 @@ SES_HD void rounds_frame(Team& tm, const Tables& tb, int p_max, int h_cap, const
       int total = n_hyp + n_vetoed + n_free;
       if (total > h_cap) { ws.scal[SC_OVERFLOW] = 1; total = h_cap; }
       ws.scal[SC_N_HYP] = total;
+      if (ambiguous) ++ws.scal[SC_N_HUNG];
     });
   }
 

@@ -181,6 +181,14 @@ struct BlockTeam {
     for (int i = (int)(threadIdx.x >> 5); i < n; i += nw) { WarpTeam w; f(w, i); }
     __syncthreads();
   }
+  template <class P> __device__ __forceinline__ int count(int n, P&& pred) {
+    int c = 0;
+    for (int base = 0; base < n; base += (int)blockDim.x) {
+      const int i = base + (int)threadIdx.x;
+      c += __syncthreads_count(i < n && pred(i));
+    }
+    return c;
+  }
   // stream compaction on the CTA's first warp (the lists are short), count broadcast through shared memory
   template <class P, class E> __device__ __forceinline__ int compact(int n, P&& pred, E&& emit) {
     __shared__ int s_count;

@@ -1,5 +1,5 @@
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_frame_graph.py -q -m gpu -x 2>&1 | tail -3
+timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -3
 for rep in 1 2; do
 timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/r02_bench_as_$rep.json 2> gpurun_out/r02_bench_as.err
 python -c "

@@ -17,7 +17,6 @@ rm -f gpurun_out/*_chrome.json
 timeout 300 python scripts/latency_probe.py > gpurun_out/latency_${T}.txt 2>&1; tail -3 gpurun_out/latency_${T}.txt
 timeout 300 python scripts/latency_kernels.py 2>&1 | grep -v -i warn > gpurun_out/${T}_latency_kernels.txt; tail -2 gpurun_out/${T}_latency_kernels.txt
 timeout 200 python scripts/pcie_probe_concurrent.py > gpurun_out/${T}_link_n1.json 2>/dev/null; timeout 200 python scripts/pcie_probe_pieces.py 2>&1 | grep -v -i warn > gpurun_out/${T}_link_pieces.txt
-timeout 1500 python scripts/soak_parity.py > gpurun_out/${T}_soak.jsonl 2> gpurun_out/${T}_soak.err; cut -c1-400 gpurun_out/${T}_soak.jsonl
 python - <<PY
 import json
 for f in ['bench_${T}_reference','bench_${T}']:
@@ -34,3 +33,5 @@ timeout 900 python scripts/bench_prior.py > gpurun_out/bench_prior_${T}.json 2> 
 import json; d=json.loads(open('gpurun_out/bench_prior_${T}.json').read().strip().splitlines()[-1]); print('prior', d['value'], d.get('ms_per_step'), d.get('e2e',{}).get('value'))"
 timeout 900 python scripts/bench_chain.py > gpurun_out/bench_chain_${T}.json 2> gpurun_out/${T}_err_chain.log; python -c "
 import json; d=json.loads(open('gpurun_out/bench_chain_${T}.json').read().strip().splitlines()[-1]); print('chain', d.get('value'), d.get('frames_per_sec'), d.get('ms_per_step'))"
+# the large-sample parity soak last (the longest item; everything above is already on disk if the budget runs out)
+timeout 420 python scripts/soak_parity.py > gpurun_out/${T}_soak.jsonl 2> gpurun_out/${T}_soak.err; cut -c1-300 gpurun_out/${T}_soak.jsonl

@@ -41,7 +41,9 @@ struct WorkView {
 };
 
 template <class T, int kWarpsPerCta, bool kLockstep>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, sizeof(T) == 4 ? 24 / kWarpsPerCta : 1)
+// register budget: 24 warps per SM in FP32 mode; 12 in FP64 mode (168 registers: three 4-warp CTAs per SM - at 171 only
+// two fit, measured 3.55 -> 3.89 ms on config 3)
+__global__ void __launch_bounds__(32 * kWarpsPerCta, sizeof(T) == 4 ? 24 / kWarpsPerCta : (kWarpsPerCta <= 12 ? 12 / kWarpsPerCta : 1))
 k_triangulate(const Tables tb, int p_max, int h_cap, size_t work_cap, size_t ws_bytes,
               const ses3d_person2d* __restrict__ persons, const int8_t* __restrict__ hyp_det,
               const uint32_t* __restrict__ work, int32_t* work_count, ses3d_person_cov* __restrict__ tmp,

@@ -6,8 +6,9 @@
 // ses3d_process_batch     <- both, chained on the device
 //
 // There is no CPU fallback: every entry point that computes needs a CUDA device and fails
-// with SES3D_E_CUDA otherwise. Host-buffer calls stream the batch through two device slots
-// (H2D, kernels and D2H of neighbouring chunks overlap); device-buffer calls run in place.
+// with SES3D_E_CUDA otherwise. Host-buffer calls stream the batch through the handle's device slots
+// (H2D, kernels and D2H of neighbouring chunks overlap; single-frame calls replay a captured CUDA graph);
+// device-buffer calls run in place and are stream-ordered.
 // Device scratch belongs to the handle, grows monotonically and is reused across calls.
 #include <cuda_runtime.h>
 
